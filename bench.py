@@ -1,0 +1,478 @@
+#!/usr/bin/env python
+"""bench.py -- reads -> coverage -> profile matrix on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5] [--scale S]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      (CPU arm: the oracle's C port on the host cores)
+
+A "step" is one pass of the hot path over one sample: rcp_reads_load (global-coordinate map +
+index sort) -> rcp_coverage (exact per-base int32 coverage of every region) ->
+rcp_profile_matrix (regions x bins fp64, column-major) [-> NCCL gather of the row blocks to rank 0
+when N > 1].  `value` times that with the decoded reads/regions already resident in HBM;
+`e2e` times the same through the public host API with pinned HOST buffers, copies included.
+Regions shard across ranks with no data-path collective except the final row gather (weak
+scaling: every rank owns a full-size region slice and its overlapping reads).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC = "reads/s through coverage + profileMatrix (reads -> per-base coverage -> regions x bins)"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(W.CONFIGS))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_pass(w, frac):
+    """One pass of the oracle's C port over the first `frac` of the reads and regions of
+    workload `w`.  Returns (seconds, reads processed, description)."""
+    from oracle import c_oracle as CO
+    from oracle import recoup_oracle as O
+    n = max(int(len(w["read_start"]) * frac), 1)
+    t0 = time.perf_counter()
+    ix = CO.Index(w["read_chrom"][:n], w["read_start"][:n], w["read_end"][:n], w["read_strand"][:n],
+                  w["chrom_len"], frag_len=w["frag_len"])
+    if w["region"] == "rna":
+        G = max(int((len(w["exon_ptr"]) - 1) * frac), 1)
+        ptr = w["exon_ptr"][:G + 1]
+        ne = int(ptr[-1])
+        f1, f2 = w["flank"]
+        gs, ge, gst, gc = (w["region_start"][:G], w["region_end"][:G], w["region_strand"][:G],
+                           w["region_chrom"][:G])
+        ls, le = O.get_flanking_ranges(gs, ge, gst, f1, "upstream")
+        rs, re_ = O.get_flanking_ranges(gs, ge, gst, f2, "downstream")
+        center = CO.coverage_list(ix, ptr, w["exon_chrom"][:ne], w["exon_start"][:ne],
+                                  w["exon_end"][:ne], w["exon_strand"][:ne])
+        left = CO.coverage(ix, gc, ls, le, gst)
+        right = CO.coverage(ix, gc, rs, re_, gst)
+        # merge + bins on the list form (python); small next to the coverage passes
+        merged = CO.concat3(left.to_list(), center.to_list(), right.to_list())
+        O.profile_matrix(merged, w["flank"], w["bin_params"])
+        n_units = G
+    else:
+        R = max(int(len(w["region_start"]) * frac), 1)
+        s, e = O.get_regional_ranges(w["region_start"][:R], w["region_end"][:R],
+                                     w["region_strand"][:R], w["region"], w["flank"])
+        dense = CO.coverage(ix, w["region_chrom"][:R], s, e, w["region_strand"][:R])
+        lens = dense.len[dense.len > 0]
+        equal = bool((lens == lens[0]).all()) if lens.size else True
+        CO.profile_matrix(dense, w["flank"], w["bin_params"], equal)
+        n_units = R
+    dt = time.perf_counter() - t0
+    return dt, n, "first %d reads and %d regions of %s" % (n, n_units, w["name"])
+
+
+def cpu_baseline(w, budget_s=20.0):
+    from oracle import c_oracle as CO
+    frac = min(1.0, 2_000_000 / max(len(w["read_start"]), 1))
+    dt, n, what = cpu_pass(w, frac)                       # calibration pass
+    rate = n / dt
+    frac2 = min(1.0, budget_s * rate / len(w["read_start"]))
+    if frac2 > frac * 1.5:
+        dt, n, what = cpu_pass(w, frac2)
+    return {"value": n / dt, "unit": UNIT, "cores": CO.threads(), "kind": "port",
+            "sample": what + " (oracle C port, OpenMP over regions; R itself is not installable "
+                             "here)", "seconds": round(dt, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  R/Bioconductor cannot run in this image (no
+    R, no network), so this arm times the oracle's C/OpenMP port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = W.CONFIGS[args.workload](scale=args.scale)
+    from oracle import c_oracle as CO
+    total = max(len(w["read_start"]), 1)
+    frac = min(1.0, 2_000_000 / total)
+    dt, n, what = cpu_pass(w, frac)                       # calibration
+    per_step_s = min(20.0, 150.0 / max(args.steps + args.warmup, 1))
+    frac = min(1.0, max(frac, per_step_s * (n / dt) / total))
+    for _ in range(args.warmup):
+        cpu_pass(w, frac)
+    t = 0.0
+    reads = 0
+    for _ in range(args.steps):
+        dt, n, what = cpu_pass(w, frac)
+        t += dt
+        reads += n
+    val = reads / t
+    cb = {"value": val, "unit": UNIT, "cores": CO.threads(), "kind": "port", "sample": what}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64",
+        "data": "synthetic", "config": {"workload": w["name"], "sample": what},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import recoup_b200 as rb
+    from recoup_b200 import _lib
+    from recoup_b200.ranges import getFlankingRanges, getRegionalRanges
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rb.init(local)
+    L = _lib.lib
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
+
+    # ---- this rank's slice: a full-size sample of the named workload (weak scaling) ----
+    w = W.CONFIGS[args.workload](scale=args.scale, seed={"C2": 1001, "C3": 1003, "C4": 1004,
+                                                          "C5": 1005}[args.workload] + 7919 * rank)
+    N = len(w["read_start"])
+    is_rna = w["region"] == "rna"
+    genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"],
+                       strand=w["region_strand"], seqlevels=w["chrom_names"])
+    f1, f2 = w["flank"]
+    bp = w["bin_params"]
+    if is_rna:
+        left = getFlankingRanges(genes, f1, "upstream")
+        right = getFlankingRanges(genes, f2, "downstream")
+        R = len(genes)
+    else:
+        win = getRegionalRanges(genes, w["region"], w["flank"])
+        R = len(win)
+    clen = np.ascontiguousarray(w["chrom_len"], dtype=np.int64)
+    clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
+    n_chrom = clen.shape[0]
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    d_reads = [to_dev(w[k]) for k in ("read_chrom", "read_start", "read_end", "read_strand")]
+    if is_rna:
+        d_left = [to_dev(x) for x in (left.seqnames, left.start, left.end, left.strand)]
+        d_right = [to_dev(x) for x in (right.seqnames, right.start, right.end, right.strand)]
+        ex = [np.ascontiguousarray(w[k]) for k in ("exon_chrom", "exon_start", "exon_end", "exon_strand")]
+        ex_ptr = np.ascontiguousarray(w["exon_ptr"], dtype=np.int64)
+    else:
+        d_win = [to_dev(x) for x in (win.seqnames, win.start, win.end, win.strand)]
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    equal_lengths = 1 if w["region"] in ("tss", "tes", "custom") else 0
+    ncols_box = {}
+    out_box = {}
+    stats = {}
+
+    def device_step():
+        """reads (HBM) -> index -> coverage -> matrix (HBM)."""
+        h = C.c_int(0)
+        _lib.check(L.rcp_reads_load(N, vp(d_reads[0]), vp(d_reads[1]), vp(d_reads[2]), vp(d_reads[3]),
+                                    n_chrom, clen_p, int(w["frag_len"]), _lib.MEM_DEVICE, C.byref(h)))
+        cov = C.c_int(0)
+        if is_rna:
+            hc, hl, hr = C.c_int(0), C.c_int(0), C.c_int(0)
+            _lib.check(L.rcp_coverage_list(h.value, R, ex_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           hp(ex[0]), hp(ex[1]), hp(ex[2]), hp(ex[3]), 1,
+                                           _lib.STRAND_ANY, _lib.MEM_HOST, C.byref(hc)))
+            _lib.check(L.rcp_coverage(h.value, R, vp(d_left[0]), vp(d_left[1]), vp(d_left[2]),
+                                      vp(d_left[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hl)))
+            _lib.check(L.rcp_coverage(h.value, R, vp(d_right[0]), vp(d_right[1]), vp(d_right[2]),
+                                      vp(d_right[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hr)))
+            _lib.check(L.rcp_coverage_concat3(hl.value, hc.value, hr.value, C.byref(cov)))
+            for x in (hc, hl, hr):
+                L.rcp_coverage_free(x.value)
+        else:
+            _lib.check(L.rcp_coverage(h.value, R, vp(d_win[0]), vp(d_win[1]), vp(d_win[2]),
+                                      vp(d_win[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(cov)))
+        if "n" not in ncols_box:
+            nc = C.c_int64(0)
+            _lib.check(L.rcp_profile_ncols(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
+                                           bp["regionBinSize"], C.byref(nc)))
+            ncols_box["n"] = nc.value
+            out_box["m"] = torch.empty((nc.value, R), dtype=torch.float64, device=dev)  # col-major R x nc
+            tl, nn = C.c_int64(0), C.c_int64(0)
+            L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
+            stats["total_len"], stats["n_null"] = tl.value, nn.value
+        _lib.check(L.rcp_profile_matrix(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
+                                        bp["regionBinSize"], _lib.STAT[bp["sumStat"]],
+                                        _lib.INTERP[bp["interpolation"]], 42, 0,
+                                        vp(out_box["m"]), R, _lib.MEM_DEVICE))
+        L.rcp_coverage_free(cov.value)
+        L.rcp_reads_free(h.value)
+
+    gather_box = {}
+
+    def gather_step():
+        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...))."""
+        if world == 1:
+            return
+        m = out_box["m"]
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                if "bufs" not in gather_box:
+                    gather_box["bufs"] = [torch.empty_like(m) for _ in range(world)]
+                    gather_box["full"] = torch.empty((m.shape[0], R * world), dtype=torch.float64, device=dev)
+                    gather_box["idx"] = [torch.arange(r * R, (r + 1) * R, dtype=torch.int64, device=dev)
+                                         for r in range(world)]
+                dist.gather(m, gather_box["bufs"], dst=0)
+                for r in range(world):
+                    _lib.check(L.rcp_rows_scatter(vp(gather_box["bufs"][r]), R, R, m.shape[0],
+                                                  vp(gather_box["idx"][r]), vp(gather_box["full"]),
+                                                  R * world))
+            else:
+                dist.gather(m, None, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+        gather_step()
+    barrier()
+
+    # ---- timed: device-resident ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.rcp_launch_count(1)
+    _lib.check(L.rcp_timing_enable(1))
+    _lib.check(L.rcp_timing_read(1, 0, None, None))
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+        gather_step()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = int(L.rcp_launch_count(0))
+    n_st = 0
+    while L.rcp_timing_stage_name(n_st):
+        n_st += 1
+    ms = (C.c_double * n_st)()
+    cnt = (C.c_int64 * n_st)()
+    _lib.check(L.rcp_timing_read(1, n_st, ms, cnt))
+    _lib.check(L.rcp_timing_enable(0))
+    stage = {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
+             for i in range(n_st) if cnt[i] > 0}
+    clocks = sampler.stop()
+
+    # ---- timed: end to end through the public host API (pinned host buffers) ----
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:1]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    pins = [pinned(w[k]) for k in ("read_chrom", "read_start", "read_end", "read_strand")]
+    host_views = [p.numpy() for p in pins]
+    h2d = sum(v.nbytes for v in host_views)
+    if is_rna:
+        grl = rb.GRangesList(rb.GRanges(w["exon_chrom"], w["exon_start"], w["exon_end"],
+                                        strand=w["exon_strand"], seqlevels=w["chrom_names"]),
+                             w["exon_ptr"])
+        h2d += sum(ex[i].nbytes for i in range(4)) + 2 * 13 * R
+    else:
+        h2d += 13 * R
+    ncols = ncols_box["n"]
+    d2h = 8 * R * ncols + 4 * R
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        reads = rb.GRanges(host_views[0], host_views[1], host_views[2], strand=host_views[3],
+                           seqlevels=w["chrom_names"], seqlengths=clen)
+        sample = [dict(id="s", name="s", ranges=reads)]
+        if is_rna:
+            rb.coverageRnaRef(sample, grl, genes, w["flank"])
+        else:
+            if w["frag_len"]:
+                sample[0]["coverage"] = rb.calcCoverage(reads, win, frag_len=w["frag_len"])
+            else:
+                rb.coverageRef(sample, genes, w["region"], w["flank"])
+        rb.profileMatrix(sample, w["flank"], bp)
+        m = sample[0]["profile"]
+        sample[0]["coverage"].free()
+        for dr in reads._device.values():
+            dr.free()
+        reads._device.clear()
+        return m
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mat = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = elapsed_ms / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+    e2e_value = world * N / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_len = stats["total_len"]
+        # algorithmic bytes per launch (SURVEY 8d / DESIGN.md):
+        #   coverage stage  8 B/read + 4 B/covered base + 16 B/region
+        #   profile stage   4 B/covered base + 8 B/matrix cell
+        alg = {
+            "cov_tile": 8 * N + 4 * total_len + 16 * R,
+            "cov_small": 8 * N + 4 * total_len + 16 * R,
+            "prof_bin": 4 * total_len + 8 * R * ncols,
+            "prof_base": 4 * total_len + 8 * R * ncols,
+            "index_sort": None,
+        }
+        own = {k: v for k, v in stage.items() if k in ("cov_tile", "cov_small", "cov_list", "prof_bin",
+                                                      "prof_base")}
+        dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
+        roof = None
+        if dom and alg.get(dom):
+            ach = alg[dom] / (own[dom][0] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": own[dom][0], "algorithmic_bytes": alg[dom]}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32 coverage / f64 matrix",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "regions_per_gpu": R, "reads_per_gpu": N,
+                       "matrix_cols": ncols, "covered_bases_per_gpu": total_len,
+                       "null_regions": stats["n_null"],
+                       "l2": "inputs (%.0f MB) and coverage (%.0f MB) exceed the 126 MB L2"
+                             % (13 * N / 1e6, 4 * total_len / 1e6),
+                       "parallelism": "regions sharded over %d GPU(s), NCCL row gather" % world},
+            "stage_ms_per_step": {k: v[0] * v[1] / args.steps for k, v in stage.items()},
+            "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/*
+ * recoup_b200.h -- plain C ABI of librecoup_b200.so
+ *
+ * B200-native (sm_100a) implementation of recoup's coverage -> profile-matrix hot path.
+ * The reference (hjanime/recoup, /root/reference) is interpreted R with NO native interface
+ * (NAMESPACE:1-33 has no useDynLib); the path sits behind exported R closures.  Each entry point
+ * below names the reference closure (file:line under /root/reference) whose body it replaces.
+ * The R-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - coordinates 1-based closed [start,end]; strand +1 '+', -1 '-', 0 '*'.
+ *   - chromosomes are dense ids 0..n_chrom-1 (as.integer(seqnames)-1).
+ *   - every function returns RCP_OK (0) or an RCP_ERR_* code; rcp_last_error() gives the text.
+ *     Nothing longjmps / calls back into the host language.  Per-region failures of the
+ *     reference ("Caught invalid genomic area!", coverage.R:217-222) are DATA (a NULL coverage),
+ *     never errors.
+ *   - the caller owns every pointer it passes; outputs are caller-allocated.  The library owns
+ *     device memory behind integer handles (reads / coverage), released by the *_free calls or
+ *     rcp_shutdown().
+ *   - `mem` says where the caller's arrays live: RCP_MEM_HOST (pageable or pinned host memory)
+ *     or RCP_MEM_DEVICE (pointers valid on the bound GPU; no copies are made).
+ *   - one process drives one GPU (rcp_init(device)); calls are serialised by the caller.
+ *   - there is NO CPU fallback: without a usable sm_100 GPU every compute call fails with
+ *     RCP_ERR_NOGPU.
+ */
+#ifndef RECOUP_B200_H
+#define RECOUP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCP_ABI_VERSION 1
+
+enum {
+    RCP_OK = 0,
+    RCP_ERR_CUDA = 1,        /* a CUDA runtime call failed                      */
+    RCP_ERR_ARG = 2,         /* bad argument (R's stop() in the reference)      */
+    RCP_ERR_HANDLE = 3,      /* unknown / freed handle                          */
+    RCP_ERR_NOGPU = 4,       /* no CUDA device, or rcp_init() not called        */
+    RCP_ERR_UNSUPPORTED = 5, /* documented unsupported corner   */
+    RCP_ERR_DATA = 6         /* input arrays violate the stated contract        */
+};
+
+#define RCP_MEM_HOST 0
+#define RCP_MEM_DEVICE 1
+
+/* `strand` argument of calcCoverage (coverage.R:126,141-144): NULL or one of "+","-","*" */
+#define RCP_STRAND_ANY 2
+
+/* `where` of binCoverageMatrix/baseCoverageMatrix (profile.R:100-101,153-155) */
+#define RCP_WHERE_WHOLE 0      /* flank = NULL */
+#define RCP_WHERE_CENTER 1
+#define RCP_WHERE_UPSTREAM 2
+#define RCP_WHERE_DOWNSTREAM 3
+
+#define RCP_STAT_MEAN 0
+#define RCP_STAT_MEDIAN 1
+
+#define RCP_INTERP_AUTO 0
+#define RCP_INTERP_SPLINE 1
+#define RCP_INTERP_LINEAR 2          /* dead code in the reference (util.R:49) -> UNSUPPORTED */
+#define RCP_INTERP_NEIGHBORHOOD 3
+
+#define RCP_SAMPLE_REJECTION 0       /* R >= 3.6.0 sample.kind (default) */
+#define RCP_SAMPLE_ROUNDING 1        /* R <  3.6.0                       */
+
+/* ---------------------------------------------------------------- library / device -------- */
+const char* rcp_last_error(void);
+int rcp_abi_version(void);
+/* Bind this process to CUDA device `device` (one process per GPU). Replaces the reference's
+ * "grid launch" cmclapply (util.R:364-382): `rc` is accepted and ignored by the R shim. */
+int rcp_init(int device);
+int rcp_shutdown(void);
+int rcp_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes);
+/* cudaStream_t on which every kernel of the library is launched (for external event timing). */
+void* rcp_stream(void);
+int rcp_sync(void);
+/* Kernels launched by this library since rcp_init / the last reset (bench.py "gpu_launches"). */
+int64_t rcp_launch_count(int reset);
+
+/* Optional CUDA-event timing of the library's stages on its own stream (bench.py roofline).
+ * rcp_timing_read synchronises, then reports accumulated milliseconds / launches per stage
+ * (stage i is named rcp_timing_stage_name(i); NULL past the last stage). */
+int rcp_timing_enable(int on);
+int rcp_timing_read(int reset, int capacity, double* ms_out, int64_t* count_out);
+const char* rcp_timing_stage_name(int stage);
+
+/* ---------------------------------------------------------------- base-R RNG -------------- */
+/* `set.seed(seed); sample(1:n, k)` -- the bin layout of splitVector (util.R:78-79). */
+int rcp_r_sample(int n, int k, int seed, int sample_kind, int* out /* k */);
+/* rank[i] = position (1-based) of bin i+1 in `set.seed(seed); sample(1:n, n)`; bin i gets an
+ * extra base iff rank[i] <= dif (util.R:74-80). */
+int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out /* n */);
+
+/* ---------------------------------------------------------------- reads ------------------- */
+/* Upload decoded reads (the `ranges` GRanges produced by preprocessRanges, ranges.R:1-65) and
+ * build the device index (reads sorted by global coordinate).  `strand` may be NULL (all '*').
+ * chrom_len[c] must be the known seqlength (> 0).  Reads must satisfy 1 <= start <= end and,
+ * after the optional extension, are trimmed into [1, chrom_len] like readBam's trim()
+ * (ranges.R:117).  frag_len > 0 applies the fragment extension named by the north star
+ * (`trim(resize(reads, frag_len, fix="start"))`; absent from the reference snapshot), 0 = off. */
+int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                   const int8_t* strand, int n_chrom, const int64_t* chrom_len, int frag_len,
+                   int mem, int* reads_out);
+int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes);
+int rcp_reads_free(int reads);
+
+/* ---------------------------------------------------------------- coverage ---------------- */
+/* calcCoverage(input, mask = GRanges, strand, ignore.strand) (coverage.R:126-174 with
+ * coverageFromRanges, coverage.R:176-226): one window per region, exact integer per-base
+ * coverage, reversed on '-' regions, NULL when no read overlaps / window leaves the chromosome.
+ * strand_filter: RCP_STRAND_ANY or +1/-1/0.  The result stays on the device behind *cov_out. */
+int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32_t* start,
+                 const int32_t* end, const int8_t* strand, int ignore_strand, int strand_filter,
+                 int mem, int* cov_out);
+/* calcCoverage(input, mask = GRangesList, ...) (coverage.R:177-178,202-207): element g owns
+ * ranges ptr[g]..ptr[g+1]-1 (the exons of one gene, list order); coverage is stitched in list
+ * order; chromosome and strand are those of the element's FIRST range (coverage.R:182,185);
+ * a read overlapping k ranges of the element counts k times (coverage.R:190-192). */
+int rcp_coverage_list(int reads, int64_t n_elements, const int64_t* ptr, const int32_t* chrom,
+                      const int32_t* start, const int32_t* end, const int8_t* strand,
+                      int ignore_strand, int strand_filter, int mem, int* cov_out);
+/* The merge step of coverageRnaRef (coverage.R:115-120): c(left, center, right) per element,
+ * NULL if any part is NULL. */
+int rcp_coverage_concat3(int left, int center, int right, int* cov_out);
+/* Linear normalisation (recoup.R:559-577): every coverage value is multiplied by `factor`. */
+int rcp_coverage_set_scale(int cov, double factor);
+int rcp_coverage_info(int cov, int64_t* n_regions, int64_t* total_len, int64_t* n_null,
+                      double* scale);
+/* lengths(coverage): 0 for NULL entries (profile.R:6). */
+int rcp_coverage_lengths(int cov, int32_t* len_out /* n_regions */);
+/* Copy the unscaled integer coverage of regions [first, first+count) to the host, packed back to
+ * back (region i occupies len[i] ints).  `capacity` = ints available in `out`. */
+int rcp_coverage_fetch(int cov, int64_t first, int64_t count, int32_t* out, int64_t capacity);
+int rcp_coverage_free(int cov);
+
+/* ---------------------------------------------------------------- profile matrix ---------- */
+/* binCoverageMatrix(cvrg, binSize, stat, interpolation, flank, where) (profile.R:153-212) with
+ * splitVector (util.R:15-85): writes an [n_regions x n_bins] block, column-major with leading
+ * dimension ld >= n_regions, at `out`.  NULL coverage -> zero row (profile.R:191-197). */
+int rcp_bin_matrix(int cov, int where, int f1, int f2, int n_bins, int stat, int interp,
+                   int seed, int sample_kind, double* out, int64_t ld, int mem);
+/* baseCoverageMatrix(cvrg, flank, where) (profile.R:100-151): [n_regions x n_cols] per-base
+ * block, same layout.  RCP_WHERE_WHOLE: n_cols must equal the common region length. */
+int rcp_base_matrix(int cov, int where, int f1, int f2, int64_t n_cols, double* out, int64_t ld,
+                    int mem);
+/* Number of columns profileMatrix produces (profile.R:13-96) for these parameters. */
+int rcp_profile_ncols(int cov, int equal_lengths, int f1, int f2, int flank_bin_size,
+                      int region_bin_size, int64_t* ncols_out);
+/* profileMatrix for ONE sample (profile.R:1-98): `equal_lengths` is the decision the reference
+ * takes on the first sample (profile.R:6-10).  Writes cbind(left, center, right). */
+int rcp_profile_matrix(int cov, int equal_lengths, int f1, int f2, int flank_bin_size,
+                       int region_bin_size, int stat, int interp, int seed, int sample_kind,
+                       double* out, int64_t ld, int mem);
+
+/* ---------------------------------------------------------------- fused path -------------- */
+/* coverageRef + profileMatrix for fixed-width windows WITHOUT materialising $coverage
+ * (coverage.R:1-42 + profile.R:83-96): windows of equal length, n_bins bins (0 = per base).
+ * is_null_out (n_regions, may be NULL) receives the NULL flags. */
+int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom,
+                         const int32_t* start, const int32_t* end, const int8_t* strand,
+                         int ignore_strand, int strand_filter, int n_bins, int seed,
+                         int sample_kind, double scale, double* out, int64_t ld,
+                         uint8_t* is_null_out, int mem);
+
+/* ---------------------------------------------------------------- multi-GPU helper -------- */
+/* Scatter a row block into the gathered matrix: dst[row_index[i] + c*ld_dst] =
+ * src[i + c*ld_src] for i < n_rows, c < n_cols (all pointers on the device).  Used after the
+ * NCCL gather of per-rank row blocks (the reference's do.call(rbind, ...), profile.R:150,208). */
+int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
+                     const int64_t* row_index, double* dst, int64_t ld_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOUP_B200_H */

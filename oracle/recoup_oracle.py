@@ -213,6 +213,9 @@ def calc_coverage(reads, mask, strand=None, ignore_strand=True):
         ptr = np.asarray(mask["ptr"], dtype=np.int64)
         for i in range(ptr.shape[0] - 1):
             a, b = int(ptr[i]), int(ptr[i + 1])
+            if b <= a:      # empty element: seqnames(x)[1] is NA -> "not found" -> NULL
+                out.append(None)
+                continue
             out.append(coverage_from_ranges(reads, int(chrom[a]), ms[a:b], me[a:b], mst[a:b],
                                             ignore_strand))
     else:

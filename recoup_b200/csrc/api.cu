@@ -1,0 +1,657 @@
+// C ABI of librecoup_b200.so (include/recoup_b200.h): context, handle tables, argument checks.
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <memory>
+
+#include "r_rng.cuh"
+#include "rcp_internal.cuh"
+
+namespace rcp {
+
+Ctx g_ctx;
+static thread_local std::string g_error;
+static std::map<int, std::unique_ptr<ReadsIdx>> g_reads;
+static std::map<int, std::unique_ptr<Coverage>> g_covs;
+static int g_next_handle = 1;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+// ---- stage timers ----
+static bool g_timing = false;
+struct TimerRec { int stage; cudaEvent_t a, b; };
+static std::vector<TimerRec> g_pending;
+static std::vector<cudaEvent_t> g_free_events;
+static double g_stage_ms[ST_N];
+static int64_t g_stage_count[ST_N];
+static const char* const g_stage_names[ST_N] = {
+    "index_map", "index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
+    "prof_bin", "prof_interp", "prof_base", "fused"};
+
+static cudaEvent_t take_event() {
+    if (!g_free_events.empty()) {
+        cudaEvent_t e = g_free_events.back();
+        g_free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+StageTimer::StageTimer(int stage) : slot(-1) {
+    if (!g_timing || !g_ctx.ready) return;
+    TimerRec r;
+    r.stage = stage;
+    r.a = take_event();
+    r.b = take_event();
+    cudaEventRecord(r.a, g_ctx.stream);
+    g_pending.push_back(r);
+    slot = (int)g_pending.size() - 1;
+}
+StageTimer::~StageTimer() {
+    if (slot >= 0 && slot < (int)g_pending.size()) cudaEventRecord(g_pending[(size_t)slot].b, g_ctx.stream);
+}
+
+static void drain_timers() {
+    if (g_pending.empty()) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    for (auto& r : g_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_stage_ms[r.stage] += ms;
+            g_stage_count[r.stage]++;
+        }
+        g_free_events.push_back(r.a);
+        g_free_events.push_back(r.b);
+    }
+    g_pending.clear();
+}
+
+int require_ready() {
+    if (!g_ctx.ready)
+        return fail(RCP_ERR_NOGPU, "rcp_init() has not bound a CUDA device (no CPU fallback exists)");
+    return RCP_OK;
+}
+
+ReadsIdx* get_reads(int h) {
+    auto it = g_reads.find(h);
+    return it == g_reads.end() ? nullptr : it->second.get();
+}
+Coverage* get_coverage(int h) {
+    auto it = g_covs.find(h);
+    return it == g_covs.end() ? nullptr : it->second.get();
+}
+int new_coverage(Coverage** out, int* handle) {
+    const int h = g_next_handle++;
+    g_covs[h] = std::unique_ptr<Coverage>(new Coverage());
+    *out = g_covs[h].get();
+    *handle = h;
+    return RCP_OK;
+}
+static void drop_coverage(int h) {
+    auto it = g_covs.find(h);
+    if (it != g_covs.end()) {
+        coverage_release(*it->second);
+        g_covs.erase(it);
+    }
+}
+
+// implemented in the other translation units
+int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+                    const int32_t* end, const int8_t* strand, int n_chrom,
+                    const int64_t* chrom_len, int frag_len, int mem);
+int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                    const int32_t* end, const int8_t* strand, int ignore_strand,
+                    int strand_filter, int mem, Coverage* cv);
+int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_ranges,
+                  const int32_t* chrom, const int32_t* start, const int32_t* end,
+                  const int8_t* strand, int ignore_strand, int strand_filter, int mem,
+                  Coverage* cv);
+int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv);
+int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
+                   int64_t capacity);
+int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins, int stat,
+                      int interp, int seed, int sample_kind, double* d_out, int64_t ld);
+int base_matrix_device(const Coverage& cv, int where, int f1, int f2, int64_t n_cols,
+                       double* d_out, int64_t ld);
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+rows_scatter_kernel(const double* __restrict__ src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
+                    const int64_t* __restrict__ row_index, double* __restrict__ dst,
+                    int64_t ld_dst) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t c = blockIdx.y;
+    dst[row_index[i] + c * ld_dst] = src[i + c * ld_src];
+}
+
+bool valid_strand_filter(int f) { return f == RCP_STRAND_ANY || f == 1 || f == -1 || f == 0; }
+
+// Output staging: a device buffer the kernels write, copied to the caller's host matrix (column
+// by column when ld differs) or the caller's own device pointer.
+struct MatrixOut {
+    double* dev = nullptr;
+    bool owned = false;
+    int64_t ld_dev = 0;
+    int init(double* out, int64_t ld, int64_t rows, int64_t cols, int mem) {
+        if (mem == RCP_MEM_DEVICE) {
+            dev = out;
+            ld_dev = ld;
+            return RCP_OK;
+        }
+        owned = true;
+        ld_dev = rows;
+        return dalloc(&dev, (size_t)(rows * cols));
+    }
+    int finish(double* out, int64_t ld, int64_t rows, int64_t cols) {
+        if (!owned) return RCP_OK;
+        if (rows > 0 && cols > 0)
+            RCP_CUDA(cudaMemcpy2DAsync(out, (size_t)ld * sizeof(double), dev,
+                                       (size_t)ld_dev * sizeof(double),
+                                       (size_t)rows * sizeof(double), (size_t)cols,
+                                       cudaMemcpyDeviceToHost, g_ctx.stream));
+        RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        return RCP_OK;
+    }
+    ~MatrixOut() {
+        if (owned) dfree(dev);
+    }
+};
+
+int check_bins(int n_bins, int stat, int interp) {
+    if (n_bins < 1) return fail(RCP_ERR_ARG, "binSize must be >= 1 (got %d)", n_bins);
+    if (stat != RCP_STAT_MEAN && stat != RCP_STAT_MEDIAN)
+        return fail(RCP_ERR_ARG, "sumStat must be mean or median");
+    if (interp == RCP_INTERP_LINEAR)
+        return fail(RCP_ERR_UNSUPPORTED,
+                    "interpolation=\"linear\" is dead code in the reference (R/util.R:49 spells "
+                    "the switch label 'inear'); not reproduced");
+    if (interp != RCP_INTERP_AUTO && interp != RCP_INTERP_SPLINE && interp != RCP_INTERP_NEIGHBORHOOD)
+        return fail(RCP_ERR_ARG, "unknown interpolation code %d", interp);
+    return RCP_OK;
+}
+
+// columns of the three blocks of profile.R:13-78 (0 = block absent)
+struct Blocks {
+    int64_t left, center, right;
+    bool left_binned, right_binned;
+};
+
+int r_round_half_even(double x) {
+    // R's round(): IEC 60559 round-half-even on the double value
+    return (int)nearbyint(x);
+}
+
+int profile_blocks(const Coverage& cv, int equal_lengths, int f1, int f2, int fbs, int rbs,
+                   int64_t common_len, Blocks* b) {
+    b->left = b->center = b->right = 0;
+    b->left_binned = b->right_binned = false;
+    if (f1 < 0 || f2 < 0 || fbs < 0 || rbs < 0) return fail(RCP_ERR_ARG, "negative flank or bin size");
+    if (equal_lengths) {
+        b->center = rbs != 0 ? rbs : common_len;                       // profile.R:86-93
+        return RCP_OK;
+    }
+    if (rbs < 1)
+        return fail(RCP_ERR_ARG, "regionBinSize must be >= 1 when coverage lengths differ");
+    b->center = rbs;
+    if (fbs != 0) {                                                    // profile.R:25-57
+        const double tot = (double)f1 + (double)f2;
+        if (f1 != 0) {
+            b->left = r_round_half_even((double)(2 * fbs) * ((double)f1 / tot));
+            b->left_binned = true;
+        }
+        if (f2 != 0) {
+            b->right = r_round_half_even((double)(2 * fbs) * ((double)f2 / tot));
+            b->right_binned = true;
+        }
+        if ((f1 != 0 && b->left < 1) || (f2 != 0 && b->right < 1))
+            return fail(RCP_ERR_ARG, "flank bin count rounds to zero");
+    } else {                                                           // profile.R:58-77
+        b->left = f1;
+        b->right = f2;
+    }
+    (void)cv;
+    return RCP_OK;
+}
+
+// length of the first non-NULL coverage (profile.R:103-111); synchronises.
+int common_length(const Coverage& cv, int64_t* out) {
+    *out = 0;
+    if (cv.n_regions == 0) return RCP_OK;
+    std::vector<int32_t> len((size_t)cv.n_regions);
+    RCP_CUDA(cudaMemcpyAsync(len.data(), cv.len, (size_t)cv.n_regions * 4, cudaMemcpyDeviceToHost,
+                             g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (int32_t l : len)
+        if (l > 0) {
+            *out = l;
+            break;
+        }
+    return RCP_OK;
+}
+
+}  // namespace
+}  // namespace rcp
+
+using namespace rcp;
+
+extern "C" {
+
+const char* rcp_last_error(void) { return g_error.c_str(); }
+int rcp_abi_version(void) { return RCP_ABI_VERSION; }
+
+int rcp_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RCP_ERR_NOGPU, "no CUDA device available (%s); librecoup_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(RCP_ERR_ARG, "device %d outside [0, %d)", device, n);
+    if (g_ctx.ready && g_ctx.device == device) return RCP_OK;
+    if (g_ctx.ready) rcp_shutdown();
+    RCP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RCP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(RCP_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.cc_major = prop.major;
+    g_ctx.cc_minor = prop.minor;
+    g_ctx.mem_bytes = prop.totalGlobalMem;
+    RCP_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    // keep freed blocks in the stream-ordered pool: repeated calls reuse them without driver calls
+    cudaMemPool_t pool;
+    RCP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    RCP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    g_ctx.launches = 0;
+    g_ctx.ready = true;
+    return RCP_OK;
+}
+
+int rcp_shutdown(void) {
+    if (!g_ctx.ready) return RCP_OK;
+    for (auto& kv : g_reads) reads_release(*kv.second);
+    g_reads.clear();
+    for (auto& kv : g_covs) coverage_release(*kv.second);
+    g_covs.clear();
+    drain_timers();
+    g_timing = false;
+    for (cudaEvent_t e : g_free_events) cudaEventDestroy(e);
+    g_free_events.clear();
+    cudaStreamSynchronize(g_ctx.stream);
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Ctx();
+    return RCP_OK;
+}
+
+int rcp_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes) {
+    RCP_TRY(require_ready());
+    if (device) *device = g_ctx.device;
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (cc_major) *cc_major = g_ctx.cc_major;
+    if (cc_minor) *cc_minor = g_ctx.cc_minor;
+    if (mem_bytes) *mem_bytes = (int64_t)g_ctx.mem_bytes;
+    return RCP_OK;
+}
+
+void* rcp_stream(void) { return g_ctx.ready ? (void*)g_ctx.stream : nullptr; }
+
+int rcp_sync(void) {
+    RCP_TRY(require_ready());
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return RCP_OK;
+}
+
+int rcp_timing_enable(int on) {
+    RCP_TRY(require_ready());
+    drain_timers();
+    g_timing = on != 0;
+    return RCP_OK;
+}
+
+int rcp_timing_read(int reset, int capacity, double* ms_out, int64_t* count_out) {
+    RCP_TRY(require_ready());
+    drain_timers();
+    for (int i = 0; i < ST_N && i < capacity; i++) {
+        if (ms_out) ms_out[i] = g_stage_ms[i];
+        if (count_out) count_out[i] = g_stage_count[i];
+    }
+    if (reset)
+        for (int i = 0; i < ST_N; i++) {
+            g_stage_ms[i] = 0.0;
+            g_stage_count[i] = 0;
+        }
+    return RCP_OK;
+}
+
+const char* rcp_timing_stage_name(int stage) {
+    return (stage >= 0 && stage < ST_N) ? g_stage_names[stage] : nullptr;
+}
+
+int64_t rcp_launch_count(int reset) {
+    const int64_t v = g_ctx.launches;
+    if (reset) g_ctx.launches = 0;
+    return v;
+}
+
+// ---- RNG (host only; needs no GPU) ---------------------------------------------------------
+int rcp_r_sample(int n, int k, int seed, int sample_kind, int* out) {
+    if (n < 0 || k < 0 || k > n)
+        return fail(RCP_ERR_ARG, "cannot take a sample of %d from a population of %d", k, n);
+    if (sample_kind != RCP_SAMPLE_REJECTION && sample_kind != RCP_SAMPLE_ROUNDING)
+        return fail(RCP_ERR_ARG, "unknown sample kind %d", sample_kind);
+    if (k > 0 && out == nullptr) return fail(RCP_ERR_ARG, "out is NULL");
+    std::vector<int> x((size_t)n);
+    std::unique_ptr<RRng> rng(new RRng);
+    rng->seed((uint32_t)seed, sample_kind);
+    rng->sample(n, k, x.data(), out);
+    return RCP_OK;
+}
+
+int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out) {
+    if (n < 0) return fail(RCP_ERR_ARG, "n < 0");
+    std::vector<int> perm((size_t)n);
+    RCP_TRY(rcp_r_sample(n, n, seed, sample_kind, perm.data()));
+    for (int pos = 0; pos < n; pos++) rank_out[perm[(size_t)pos] - 1] = pos + 1;
+    return RCP_OK;
+}
+
+// ---- reads ---------------------------------------------------------------------------------
+int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                   const int8_t* strand, int n_chrom, const int64_t* chrom_len, int frag_len,
+                   int mem, int* reads_out) {
+    RCP_TRY(require_ready());
+    if (n < 0 || n_chrom < 1 || chrom_len == nullptr || reads_out == nullptr || frag_len < 0)
+        return fail(RCP_ERR_ARG, "rcp_reads_load: bad scalar argument");
+    if (n > 0 && (chrom == nullptr || start == nullptr || end == nullptr))
+        return fail(RCP_ERR_ARG, "rcp_reads_load: NULL array");
+    if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
+    std::unique_ptr<ReadsIdx> r(new ReadsIdx());
+    int rc = reads_load_impl(*r, n, chrom, start, end, strand, n_chrom, chrom_len, frag_len, mem);
+    if (rc != RCP_OK) {
+        reads_release(*r);
+        return rc;
+    }
+    const int h = g_next_handle++;
+    g_reads[h] = std::move(r);
+    *reads_out = h;
+    return RCP_OK;
+}
+
+int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes) {
+    ReadsIdx* r = get_reads(reads);
+    if (!r) return fail(RCP_ERR_HANDLE, "unknown reads handle %d", reads);
+    if (n) *n = r->n;
+    if (n_chrom) *n_chrom = r->n_chrom;
+    if (device_bytes) *device_bytes = (int64_t)r->device_bytes;
+    return RCP_OK;
+}
+
+int rcp_reads_free(int reads) {
+    auto it = g_reads.find(reads);
+    if (it == g_reads.end()) return fail(RCP_ERR_HANDLE, "unknown reads handle %d", reads);
+    reads_release(*it->second);
+    g_reads.erase(it);
+    return RCP_OK;
+}
+
+// ---- coverage ------------------------------------------------------------------------------
+int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32_t* start,
+                 const int32_t* end, const int8_t* strand, int ignore_strand, int strand_filter,
+                 int mem, int* cov_out) {
+    RCP_TRY(require_ready());
+    ReadsIdx* r = get_reads(reads);
+    if (!r) return fail(RCP_ERR_HANDLE, "unknown reads handle %d", reads);
+    if (n_regions < 0 || cov_out == nullptr) return fail(RCP_ERR_ARG, "rcp_coverage: bad argument");
+    if (n_regions > 0 && (!chrom || !start || !end)) return fail(RCP_ERR_ARG, "rcp_coverage: NULL array");
+    if (!valid_strand_filter(strand_filter)) return fail(RCP_ERR_ARG, "bad strand filter %d", strand_filter);
+    if (n_regions > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 regions");
+    Coverage* cv;
+    int h;
+    RCP_TRY(new_coverage(&cv, &h));
+    int rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                             strand_filter, mem, cv);
+    if (rc != RCP_OK) {
+        drop_coverage(h);
+        return rc;
+    }
+    *cov_out = h;
+    return RCP_OK;
+}
+
+int rcp_coverage_list(int reads, int64_t n_elements, const int64_t* ptr, const int32_t* chrom,
+                      const int32_t* start, const int32_t* end, const int8_t* strand,
+                      int ignore_strand, int strand_filter, int mem, int* cov_out) {
+    RCP_TRY(require_ready());
+    ReadsIdx* r = get_reads(reads);
+    if (!r) return fail(RCP_ERR_HANDLE, "unknown reads handle %d", reads);
+    if (n_elements < 0 || ptr == nullptr || cov_out == nullptr)
+        return fail(RCP_ERR_ARG, "rcp_coverage_list: bad argument");
+    if (mem != RCP_MEM_HOST)
+        return fail(RCP_ERR_UNSUPPORTED, "rcp_coverage_list takes host arrays (ptr is read on the host)");
+    if (!valid_strand_filter(strand_filter)) return fail(RCP_ERR_ARG, "bad strand filter %d", strand_filter);
+    for (int64_t g = 0; g < n_elements; g++)
+        if (ptr[g + 1] < ptr[g]) return fail(RCP_ERR_ARG, "ptr is not non-decreasing at %lld", (long long)g);
+    if (ptr[0] != 0) return fail(RCP_ERR_ARG, "ptr[0] must be 0");
+    const int64_t n_ranges = ptr[n_elements];
+    if (n_ranges > 0 && (!chrom || !start || !end)) return fail(RCP_ERR_ARG, "rcp_coverage_list: NULL array");
+    Coverage* cv;
+    int h;
+    RCP_TRY(new_coverage(&cv, &h));
+    int rc = coverage_list(*r, n_elements, ptr, n_ranges, chrom, start, end, strand,
+                           ignore_strand != 0, strand_filter, mem, cv);
+    if (rc != RCP_OK) {
+        drop_coverage(h);
+        return rc;
+    }
+    *cov_out = h;
+    return RCP_OK;
+}
+
+int rcp_coverage_concat3(int left, int center, int right, int* cov_out) {
+    RCP_TRY(require_ready());
+    Coverage *a = get_coverage(left), *b = get_coverage(center), *c = get_coverage(right);
+    if (!a || !b || !c) return fail(RCP_ERR_HANDLE, "unknown coverage handle");
+    if (cov_out == nullptr) return fail(RCP_ERR_ARG, "cov_out is NULL");
+    Coverage* cv;
+    int h;
+    RCP_TRY(new_coverage(&cv, &h));
+    int rc = coverage_concat3(*a, *b, *c, cv);
+    if (rc != RCP_OK) {
+        drop_coverage(h);
+        return rc;
+    }
+    cv->scale = b->scale;
+    *cov_out = h;
+    return RCP_OK;
+}
+
+int rcp_coverage_set_scale(int cov, double factor) {
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    cv->scale = factor;
+    return RCP_OK;
+}
+
+int rcp_coverage_info(int cov, int64_t* n_regions, int64_t* total_len, int64_t* n_null,
+                      double* scale) {
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (n_regions) *n_regions = cv->n_regions;
+    if (total_len) *total_len = cv->total_len;
+    if (n_null) *n_null = cv->n_null;
+    if (scale) *scale = cv->scale;
+    return RCP_OK;
+}
+
+int rcp_coverage_lengths(int cov, int32_t* len_out) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (cv->n_regions == 0) return RCP_OK;
+    if (!len_out) return fail(RCP_ERR_ARG, "len_out is NULL");
+    RCP_CUDA(cudaMemcpyAsync(len_out, cv->len, (size_t)cv->n_regions * 4, cudaMemcpyDeviceToHost,
+                             g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return RCP_OK;
+}
+
+int rcp_coverage_fetch(int cov, int64_t first, int64_t count, int32_t* out, int64_t capacity) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    return coverage_fetch(*cv, first, count, out, capacity);
+}
+
+int rcp_coverage_free(int cov) {
+    if (!get_coverage(cov)) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    drop_coverage(cov);
+    return RCP_OK;
+}
+
+// ---- profile -------------------------------------------------------------------------------
+int rcp_bin_matrix(int cov, int where, int f1, int f2, int n_bins, int stat, int interp, int seed,
+                   int sample_kind, double* out, int64_t ld, int mem) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    RCP_TRY(check_bins(n_bins, stat, interp));
+    if (where < RCP_WHERE_WHOLE || where > RCP_WHERE_DOWNSTREAM) return fail(RCP_ERR_ARG, "bad where");
+    if (f1 < 0 || f2 < 0) return fail(RCP_ERR_ARG, "negative flank");
+    if (ld < cv->n_regions || out == nullptr) return fail(RCP_ERR_ARG, "bad output matrix");
+    MatrixOut m;
+    RCP_TRY(m.init(out, ld, cv->n_regions, n_bins, mem));
+    RCP_TRY(bin_matrix_device(*cv, where, f1, f2, n_bins, stat, interp, seed, sample_kind, m.dev,
+                              m.ld_dev));
+    return m.finish(out, ld, cv->n_regions, n_bins);
+}
+
+int rcp_base_matrix(int cov, int where, int f1, int f2, int64_t n_cols, double* out, int64_t ld,
+                    int mem) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (where < RCP_WHERE_WHOLE || where > RCP_WHERE_DOWNSTREAM || where == RCP_WHERE_CENTER)
+        return fail(RCP_ERR_ARG, "baseCoverageMatrix takes where = whole / upstream / downstream");
+    if (f1 < 0 || f2 < 0 || n_cols < 0) return fail(RCP_ERR_ARG, "negative size");
+    if (where == RCP_WHERE_UPSTREAM && n_cols != f1) return fail(RCP_ERR_ARG, "n_cols must equal flank[1]");
+    if (where == RCP_WHERE_DOWNSTREAM && n_cols != f2) return fail(RCP_ERR_ARG, "n_cols must equal flank[2]");
+    if (ld < cv->n_regions || out == nullptr) return fail(RCP_ERR_ARG, "bad output matrix");
+    MatrixOut m;
+    RCP_TRY(m.init(out, ld, cv->n_regions, n_cols, mem));
+    RCP_TRY(base_matrix_device(*cv, where, f1, f2, n_cols, m.dev, m.ld_dev));
+    return m.finish(out, ld, cv->n_regions, n_cols);
+}
+
+int rcp_profile_ncols(int cov, int equal_lengths, int f1, int f2, int flank_bin_size,
+                      int region_bin_size, int64_t* ncols_out) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    int64_t common = 0;
+    if (equal_lengths && region_bin_size == 0) RCP_TRY(common_length(*cv, &common));
+    Blocks b;
+    RCP_TRY(profile_blocks(*cv, equal_lengths, f1, f2, flank_bin_size, region_bin_size, common, &b));
+    *ncols_out = b.left + b.center + b.right;
+    return RCP_OK;
+}
+
+int rcp_profile_matrix(int cov, int equal_lengths, int f1, int f2, int flank_bin_size,
+                       int region_bin_size, int stat, int interp, int seed, int sample_kind,
+                       double* out, int64_t ld, int mem) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (ld < cv->n_regions || out == nullptr) return fail(RCP_ERR_ARG, "bad output matrix");
+    int64_t common = 0;
+    if (equal_lengths && region_bin_size == 0) RCP_TRY(common_length(*cv, &common));
+    Blocks b;
+    RCP_TRY(profile_blocks(*cv, equal_lengths, f1, f2, flank_bin_size, region_bin_size, common, &b));
+    const int64_t ncols = b.left + b.center + b.right;
+    const int64_t R = cv->n_regions;
+    MatrixOut m;
+    RCP_TRY(m.init(out, ld, R, ncols, mem));
+    if (equal_lengths) {
+        if (region_bin_size != 0) {
+            // profile.R:88-90 does not forward `interpolation`: binCoverageMatrix's default "auto"
+            RCP_TRY(check_bins(region_bin_size, stat, RCP_INTERP_AUTO));
+            RCP_TRY(bin_matrix_device(*cv, RCP_WHERE_WHOLE, 0, 0, region_bin_size, stat,
+                                      RCP_INTERP_AUTO, seed, sample_kind, m.dev, m.ld_dev));
+        } else {
+            RCP_TRY(base_matrix_device(*cv, RCP_WHERE_WHOLE, 0, 0, common, m.dev, m.ld_dev));
+        }
+    } else {
+        RCP_TRY(check_bins((int)b.center, stat, interp));
+        double* p = m.dev;
+        if (b.left > 0) {
+            if (b.left_binned)
+                RCP_TRY(bin_matrix_device(*cv, RCP_WHERE_UPSTREAM, f1, f2, (int)b.left, stat, interp,
+                                          seed, sample_kind, p, m.ld_dev));
+            else
+                RCP_TRY(base_matrix_device(*cv, RCP_WHERE_UPSTREAM, f1, f2, b.left, p, m.ld_dev));
+            p += b.left * m.ld_dev;
+        }
+        RCP_TRY(bin_matrix_device(*cv, RCP_WHERE_CENTER, f1, f2, (int)b.center, stat, interp, seed,
+                                  sample_kind, p, m.ld_dev));
+        p += b.center * m.ld_dev;
+        if (b.right > 0) {
+            if (b.right_binned)
+                RCP_TRY(bin_matrix_device(*cv, RCP_WHERE_DOWNSTREAM, f1, f2, (int)b.right, stat,
+                                          interp, seed, sample_kind, p, m.ld_dev));
+            else
+                RCP_TRY(base_matrix_device(*cv, RCP_WHERE_DOWNSTREAM, f1, f2, b.right, p, m.ld_dev));
+        }
+    }
+    return m.finish(out, ld, R, ncols);
+}
+
+// ---- fused path (round 1: composed from the two stages; the coverage is released at once) ----
+int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom, const int32_t* start,
+                         const int32_t* end, const int8_t* strand, int ignore_strand,
+                         int strand_filter, int n_bins, int seed, int sample_kind, double scale,
+                         double* out, int64_t ld, uint8_t* is_null_out, int mem) {
+    int h = 0;
+    RCP_TRY(rcp_coverage(reads, n_regions, chrom, start, end, strand, ignore_strand, strand_filter,
+                         mem, &h));
+    Coverage* cv = get_coverage(h);
+    cv->scale = scale;
+    int rc = rcp_profile_matrix(h, 1, 0, 0, 0, n_bins, RCP_STAT_MEAN, RCP_INTERP_AUTO, seed,
+                                sample_kind, out, ld, mem);
+    if (rc == RCP_OK && is_null_out && n_regions > 0) {
+        cudaError_t e = cudaMemcpyAsync(is_null_out, cv->is_null, (size_t)n_regions,
+                                        mem == RCP_MEM_DEVICE ? cudaMemcpyDeviceToDevice
+                                                              : cudaMemcpyDeviceToHost,
+                                        g_ctx.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+        if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "null-flag copy failed: %s", cudaGetErrorString(e));
+    }
+    drop_coverage(h);
+    return rc;
+}
+
+int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
+                     const int64_t* row_index, double* dst, int64_t ld_dst) {
+    RCP_TRY(require_ready());
+    if (n_rows <= 0 || n_cols <= 0) return RCP_OK;
+    if (n_cols > 65535) return fail(RCP_ERR_UNSUPPORTED, "rows_scatter: more than 65535 columns");
+    rows_scatter_kernel<<<dim3((unsigned)((n_rows + 255) / 256), (unsigned)n_cols), 256, 0,
+                          g_ctx.stream>>>(src, ld_src, n_rows, n_cols, row_index, dst, ld_dst);
+    RCP_LAUNCHED();
+    return RCP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,915 @@
+// Coverage kernels (sm_100a): calcCoverage / coverageFromRanges of the reference
+// (/root/reference/R/coverage.R:126-226) over the rank index built by index.cu.
+//
+// For a window [gs, ge] in global coordinates and sorted arrays xs (starts), ye (ends+1):
+//     reads overlapping the window   n_ov = #{xs <= ge} - #{ye <= gs}          (NULL rule)
+//     coverage entering a tile at t  base = #{xs <  t} - #{ye <  t}
+//     inside the tile                diff[p-t] = #{xs == p} - #{ye == p},  cov = base + cumsum
+// so a tile needs only two contiguous slices of xs and ye (found by binary search), a
+// shared-memory difference array filled with warp-aggregated atomics, a block prefix scan and
+// one coalesced int32 store (reversed for '-' regions, coverage.R:212-213).  Tiles of one
+// region are independent: no carry is passed between CTAs.
+//
+//   region_plan_kernel   1 thread / region : geometry checks, NULL rule, slice bounds
+//   cov_small_kernel     1 warp  / region  : regions of <= 1024 bp (warp-private smem tile)
+//   cov_tile_kernel      1 CTA   / tile    : longer regions cut into <= 4096-bp tiles
+//   list_plan_kernel / cov_list_kernel     : GRangesList elements (exons stitched per gene,
+//                                            read multiplicity, coverage.R:202-207)
+#include "rcp_internal.cuh"
+
+namespace rcp {
+
+namespace {
+
+constexpr int CTA = 256;
+constexpr int WARPS = CTA / 32;
+constexpr int TILE = 4096;             // positions per CTA tile (16 KB of int32)
+constexpr int SEG = TILE / WARPS;      // 512 positions scanned by one warp
+constexpr int ROW = 128;               // positions handled by one warp-wide int4 access
+constexpr int SMALL_MAX = 1024;        // regions up to this length use the warp kernel
+constexpr int PAD = 32;                // region offsets are multiples of 32 ints (128 B)
+
+template <int NS>
+struct Sources {
+    const uint32_t* xs[NS];
+    const uint32_t* ye[NS];
+    uint32_t n[NS];
+};
+
+struct RegionArrays {
+    // outputs of the plan kernel, one entry per region (x NS where noted)
+    uint32_t* gs;        // global coordinate of the first base
+    int32_t* len;        // 0 for NULL
+    uint8_t* flags;      // bit0 reverse, bits1..3 class mask
+    uint8_t* is_null;
+    uint32_t* ix0;       // [R*NS] lower_bound(xs, gs)
+    uint32_t* ix1;       // [R*NS] lower_bound(xs, ge+1)
+    uint32_t* iy0;       // [R*NS] lower_bound(ye, gs)
+    uint32_t* iy1;       // [R*NS] lower_bound(ye, ge+1)
+    int64_t* padded;     // padded length (scan input)
+    int64_t* ntiles;     // tiles of the CTA kernel (scan input)
+};
+
+// first index in [lo, hi) with a[idx] >= key
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo,
+                                                    uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// classes (bit0 '+', bit1 '-', bit2 '*') a region may count under the strand rules of
+// calcCoverage(strand=) (coverage.R:141-144) and findOverlaps(ignore.strand=) (coverage.R:191)
+__device__ __forceinline__ unsigned class_mask(int region_strand, int ignore_strand,
+                                               int strand_filter) {
+    unsigned m = 7u;
+    if (strand_filter != RCP_STRAND_ANY) m = strand_filter > 0 ? 1u : (strand_filter < 0 ? 2u : 4u);
+    if (!ignore_strand) {
+        if (region_strand > 0) m &= 5u;
+        else if (region_strand < 0) m &= 6u;
+    }
+    return m;
+}
+
+// err bits: 1 chrom id out of range, 2 end < start - 1
+template <int NS>
+__global__ void __launch_bounds__(CTA)
+region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
+                   const int32_t* __restrict__ end, const int8_t* __restrict__ strand,
+                   const uint32_t* __restrict__ chrom_off, const int64_t* __restrict__ chrom_len,
+                   int n_chrom, Sources<NS> src, int ignore_strand, int strand_filter,
+                   RegionArrays out, unsigned int* __restrict__ err,
+                   unsigned long long* __restrict__ stats /* [0] n_null, [1] total_len */) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    unsigned long long my_null = 0, my_len = 0;
+    if (r < R) {
+        const int c = chrom[r];
+        int64_t s = start[r], e = end[r];
+        const int st = strand ? (int)strand[r] : 0;
+        bool null = false;
+        uint32_t gs = 0;
+        int64_t L = 0;
+        unsigned mask = NS == 1 ? 1u : class_mask(st, ignore_strand, strand_filter);
+        if (c < 0 || c >= n_chrom) {
+            atomicOr(err, 1u);
+            null = true;
+        } else if (e < s - 1) {
+            atomicOr(err, 2u);
+            null = true;
+        } else {
+            // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start
+            // mixes signs, an end past the chromosome is out of bounds -> tryCatch -> NULL;
+            // a zero index is silently dropped.
+            if (s < 0 || e > chrom_len[c]) null = true;
+            if (s == 0) s = 1;
+            L = e - s + 1;
+            if (L <= 0) { L = 0; null = true; }
+            gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
+        }
+        if (!null) {
+            const uint32_t ge = gs + (uint32_t)(L - 1);
+            long long nov = 0;
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+                if ((mask >> k) & 1u) {
+                    const uint32_t n = src.n[k];
+                    x0 = lower_bound_u32(src.xs[k], 0, n, gs);
+                    x1 = lower_bound_u32(src.xs[k], x0, n, ge + 1u);
+                    y0 = lower_bound_u32(src.ye[k], 0, n, gs);
+                    const uint32_t yov = lower_bound_u32(src.ye[k], y0, n, gs + 1u);
+                    y1 = lower_bound_u32(src.ye[k], yov, n, ge + 1u);
+                    nov += (long long)x1 - (long long)yov;
+                }
+                out.ix0[r * NS + k] = x0;
+                out.ix1[r * NS + k] = x1;
+                out.iy0[r * NS + k] = y0;
+                out.iy1[r * NS + k] = y1;
+            }
+            if (nov <= 0) null = true;          // coverage.R:198,224-225
+        }
+        const int32_t len = null ? 0 : (int32_t)L;
+        out.gs[r] = gs;
+        out.len[r] = len;
+        out.flags[r] = (uint8_t)((st < 0 ? 1u : 0u) | (mask << 1));
+        out.is_null[r] = null ? 1 : 0;
+        out.padded[r] = ((int64_t)len + PAD - 1) / PAD * PAD;
+        out.ntiles[r] = len > SMALL_MAX ? ((int64_t)len + TILE - 1) / TILE : 0;
+        my_null = null ? 1 : 0;
+        my_len = (unsigned long long)len;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
+        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_null) atomicAdd(&stats[0], my_null);
+        if (my_len) atomicAdd(&stats[1], my_len);
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+fill_tiles_kernel(int64_t R, const int64_t* __restrict__ ntiles,
+                  const int64_t* __restrict__ tile_off, int32_t* __restrict__ tile_region) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (r >= R) return;
+    const int64_t n = ntiles[r], o = tile_off[r];
+    for (int64_t j = 0; j < n; j++) tile_region[o + j] = (int32_t)r;
+}
+
+// ---- shared device pieces -------------------------------------------------------------------
+
+// Add `sign` once per valid lane to diff[pos]; lanes hold NON-DECREASING positions (they walk a
+// sorted array), so equal positions sit in adjacent lanes and one atomic per run is enough.
+__device__ __forceinline__ void warp_aggregated_add(int* diff, uint32_t pos, bool valid,
+                                                    int sign) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t key = valid ? pos : 0xffffffffu;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (key != prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (head && valid) {
+        const unsigned above = heads & ~((2u << lane) - 1u);
+        const int run_end = above ? (__ffs(above) - 1) : 32;
+        atomicAdd(diff + pos, sign * (run_end - (int)lane));
+    }
+}
+
+// In-place inclusive scan of rows [row_lo, row_hi) of `diff` by ONE warp (a row = 128 ints read
+// as one int4 per lane); returns the warp's total in every lane.
+__device__ __forceinline__ int warp_scan_rows(int* diff, int row_lo, int row_hi) {
+    const unsigned lane = threadIdx.x & 31;
+    int carry = 0;
+    for (int row = row_lo; row < row_hi; row++) {
+        int4* p = reinterpret_cast<int4*>(diff + row * ROW) + lane;
+        int4 v = *p;
+        v.y += v.x;
+        v.z += v.y;
+        v.w += v.z;
+        int inc = v.w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const int ex = inc - v.w + carry;
+        v.x += ex;
+        v.y += ex;
+        v.z += ex;
+        v.w += ex;
+        *p = v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    return carry;
+}
+
+// Store tile values to the region's output.  Tile covers region-relative positions
+// [t0, t0 + tlen); value(k) = add[k / seg_len] + vals[k] for k relative to the tile.
+// Output index of region position q is q ('+') or L-1-q ('-').  `tid`/`nthreads` describe the
+// cooperating threads (a CTA or one warp).  dst is 16-byte aligned at index 0.
+template <bool HAS_SEG>
+__device__ __forceinline__ void store_tile(int32_t* __restrict__ dst, int L, bool rev, int t0,
+                                           int tlen, const int* vals, const int* seg_add,
+                                           int base, int tid, int nthreads) {
+    const int o_lo = rev ? (L - t0 - tlen) : t0;
+    const int o_hi = o_lo + tlen;
+    for (int g = (o_lo & ~3) + 4 * tid; g < o_hi; g += 4 * nthreads) {
+        int v[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int o = g + q;
+            ok[q] = (o >= o_lo) && (o < o_hi);
+            const int k = rev ? (L - 1 - o - t0) : (o - t0);
+            v[q] = 0;
+            if (ok[q]) v[q] = base + vals[k] + (HAS_SEG ? seg_add[k / SEG] : 0);
+        }
+        if (ok[0] && ok[3]) {
+            *reinterpret_cast<int4*>(dst + g) = make_int4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ok[q]) dst[g + q] = v[q];
+        }
+    }
+}
+
+// ---- warp-per-region kernel (L <= SMALL_MAX) -----------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(CTA)
+cov_small_kernel(int64_t R, RegionArrays ra, Sources<NS> src, const int64_t* __restrict__ off,
+                 int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int sm[WARPS][SMALL_MAX + ROW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * WARPS + warp;
+    if (r >= R) return;
+    const int L = ra.len[r];
+    if (L == 0 || L > SMALL_MAX) return;
+    int* diff = sm[warp];
+    const int nrows = (L + ROW - 1) / ROW;
+    for (int i = lane; i < nrows * (ROW / 4); i += 32)
+        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t gs = ra.gs[r];
+    const unsigned flags = ra.flags[r];
+    const unsigned mask = flags >> 1;
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        if (!((mask >> k) & 1u)) continue;
+        const uint32_t x0 = ra.ix0[r * NS + k], x1 = ra.ix1[r * NS + k];
+        const uint32_t y0 = ra.iy0[r * NS + k], y1 = ra.iy1[r * NS + k];
+        base += (int)(x0 - y0);
+        for (uint32_t i0 = x0; i0 < x1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool ok = i < x1;
+            const uint32_t p = ok ? (__ldg(src.xs[k] + i) - gs) : 0u;
+            warp_aggregated_add(diff, p, ok, +1);
+        }
+        for (uint32_t i0 = y0; i0 < y1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool ok = i < y1;
+            const uint32_t p = ok ? (__ldg(src.ye[k] + i) - gs) : 0u;
+            warp_aggregated_add(diff, p, ok, -1);
+        }
+    }
+    __syncwarp();
+    warp_scan_rows(diff, 0, nrows);
+    __syncwarp();
+    store_tile<false>(cov + off[r], L, (flags & 1u) != 0, 0, L, diff, nullptr, base, lane, 32);
+}
+
+// ---- CTA-per-tile kernel --------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(CTA)
+cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restrict__ tile_off,
+                RegionArrays ra, Sources<NS> src, const int64_t* __restrict__ off,
+                int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int diff[TILE];
+    __shared__ int wtot[WARPS];
+    __shared__ int wpre[WARPS];
+    __shared__ uint32_t bnd[4 * NS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r = tile_region[blockIdx.x];
+    const int j = (int)((int64_t)blockIdx.x - tile_off[r]);
+    const int L = ra.len[r];
+    const int m = (L + TILE - 1) / TILE;
+    const int tile_len = (((L + m - 1) / m) + ROW - 1) / ROW * ROW;
+    const int t0 = j * tile_len;
+    const int tlen = min(tile_len, L - t0);
+    const uint32_t gts = ra.gs[r] + (uint32_t)t0;
+    const unsigned flags = ra.flags[r];
+    const unsigned mask = flags >> 1;
+    // slice bounds of this tile: searched inside the region's own slices (a few steps)
+    if (tid < 4 * NS) {
+        const int k = tid >> 2, which = tid & 3;
+        const bool is_x = which < 2;
+        const uint32_t key = (which & 1) ? gts + (uint32_t)tlen : gts;
+        const uint32_t lo = is_x ? ra.ix0[r * NS + k] : ra.iy0[r * NS + k];
+        const uint32_t hi = is_x ? ra.ix1[r * NS + k] : ra.iy1[r * NS + k];
+        uint32_t res = lo;
+        if ((mask >> k) & 1u)
+            res = lower_bound_u32(is_x ? src.xs[k] : src.ye[k], lo, hi, key);
+        bnd[tid] = res;
+    }
+    const int nrows = (tlen + ROW - 1) / ROW;
+    for (int i = tid; i < nrows * (ROW / 4); i += CTA)
+        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        if (!((mask >> k) & 1u)) continue;
+        const uint32_t x0 = bnd[4 * k + 0], x1 = bnd[4 * k + 1];
+        const uint32_t y0 = bnd[4 * k + 2], y1 = bnd[4 * k + 3];
+        base += (int)(x0 - y0);
+        for (uint32_t i0 = x0 + warp * 32; i0 < x1; i0 += CTA) {
+            const uint32_t i = i0 + lane;
+            const bool ok = i < x1;
+            const uint32_t p = ok ? (__ldg(src.xs[k] + i) - gts) : 0u;
+            warp_aggregated_add(diff, p, ok, +1);
+        }
+        for (uint32_t i0 = y0 + warp * 32; i0 < y1; i0 += CTA) {
+            const uint32_t i = i0 + lane;
+            const bool ok = i < y1;
+            const uint32_t p = ok ? (__ldg(src.ye[k] + i) - gts) : 0u;
+            warp_aggregated_add(diff, p, ok, -1);
+        }
+    }
+    __syncthreads();
+    {
+        const int row_lo = warp * (SEG / ROW);
+        const int row_hi = min(row_lo + SEG / ROW, nrows);
+        const int tot = warp_scan_rows(diff, row_lo, row_hi);
+        if (lane == 0) wtot[warp] = tot;
+    }
+    __syncthreads();
+    if (tid < WARPS) {
+        int p = 0;
+        for (int w = 0; w < tid; w++) p += wtot[w];
+        wpre[tid] = p;
+    }
+    __syncthreads();
+    store_tile<true>(cov + off[r], L, (flags & 1u) != 0, t0, tlen, diff, wpre, base, tid, CTA);
+}
+
+// ---- GRangesList elements -------------------------------------------------------------------
+struct ListArrays {
+    // per range (exon), global coordinates
+    uint32_t* xgs;       // global start (after the zero-index drop)
+    uint32_t* xge;       // global end; xge < xgs marks a zero-width range
+    int32_t* xoff;       // offset of the range inside the stitched element
+    // per element
+    int32_t* len;
+    uint8_t* flags;      // bit0 reverse
+    uint8_t* is_null;
+    uint32_t* clo;       // candidate reads [clo, chi) in start-sorted order
+    uint32_t* chi;
+    uint32_t* span_lo;   // global start of the leftmost range
+    int64_t* padded;
+    int64_t* ntiles;
+};
+
+__device__ __forceinline__ bool strand_ok(int read_strand, int range_strand, int ignore_strand,
+                                          int strand_filter) {
+    if (strand_filter != RCP_STRAND_ANY && read_strand != strand_filter) return false;
+    if (ignore_strand || range_strand == 0 || read_strand == 0) return true;
+    return read_strand == range_strand;
+}
+
+// err bits: 1 chrom id, 2 end < start-1, 4 ranges of one element on different chromosomes
+__global__ void __launch_bounds__(CTA)
+list_plan_kernel(int64_t G, const int64_t* __restrict__ ptr, const int32_t* __restrict__ chrom,
+                 const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                 const int8_t* __restrict__ strand, const uint32_t* __restrict__ chrom_off,
+                 const int64_t* __restrict__ chrom_len, int n_chrom,
+                 const uint32_t* __restrict__ xs, const uint32_t* __restrict__ p_end1,
+                 const int8_t* __restrict__ p_strand, const uint32_t* __restrict__ p_maxend1,
+                 uint32_t n_reads, int ignore_strand, int strand_filter, ListArrays out,
+                 unsigned int* __restrict__ err, unsigned long long* __restrict__ stats) {
+    const int64_t g = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    unsigned long long my_null = 0, my_len = 0;
+    if (g < G) {
+        const int64_t a = ptr[g], b = ptr[g + 1];
+        bool null = (b <= a);
+        int64_t L = 0;
+        uint32_t lo = 0xffffffffu, hi = 0;
+        int st0 = 0;
+        if (!null) {
+            const int c = chrom[a];
+            st0 = strand ? (int)strand[a] : 0;
+            if (c < 0 || c >= n_chrom) {
+                atomicOr(err, 1u);
+                null = true;
+            } else {
+                const int64_t clen = chrom_len[c];
+                const uint32_t coff = chrom_off[c];
+                for (int64_t i = a; i < b; i++) {
+                    int64_t s = start[i], e = end[i];
+                    if (chrom[i] != c) atomicOr(err, 4u);
+                    if (e < s - 1) { atomicOr(err, 2u); null = true; }
+                    if (s < 0 || e > clen) null = true;      // coverage.R:206 inside tryCatch
+                    if (s == 0) s = 1;
+                    int64_t w = e - s + 1;
+                    if (w < 0) w = 0;
+                    const uint32_t gs = coff + (uint32_t)(s > 0 ? s : 0);
+                    out.xgs[i] = gs;
+                    out.xge[i] = gs + (uint32_t)w - 1u;
+                    out.xoff[i] = (int32_t)L;
+                    L += w;
+                    if (w > 0) {
+                        lo = min(lo, gs);
+                        hi = max(hi, gs + (uint32_t)w - 1u);
+                    }
+                }
+                if (L == 0 || L > 0x7fffffff) null = true;
+            }
+        }
+        uint32_t clo = 0, chi = 0;
+        if (!null) {
+            // candidates: start <= span end, and the running max of (end+1) has reached span start
+            chi = lower_bound_u32(xs, 0, n_reads, hi + 1u);
+            clo = lower_bound_u32(p_maxend1, 0, chi, lo + 1u);
+            // NULL rule: at least one (range, read) hit (coverage.R:190-198)
+            bool any = false;
+            for (uint32_t i = clo; i < chi && !any; i++) {
+                const uint32_t rs = xs[i], re1 = p_end1[i];
+                if (re1 <= lo) continue;
+                const int rst = p_strand ? (int)p_strand[i] : 0;
+                for (int64_t q = a; q < b; q++) {
+                    const uint32_t s = out.xgs[q], e = out.xge[q];
+                    if (e + 1u == s) continue;
+                    if (rs <= e && re1 > s &&
+                        strand_ok(rst, strand ? (int)strand[q] : 0, ignore_strand, strand_filter)) {
+                        any = true;
+                        break;
+                    }
+                }
+            }
+            if (!any) null = true;
+        }
+        const int32_t len = null ? 0 : (int32_t)L;
+        out.len[g] = len;
+        out.flags[g] = (uint8_t)(st0 < 0 ? 1u : 0u);
+        out.is_null[g] = null ? 1 : 0;
+        out.clo[g] = clo;
+        out.chi[g] = chi;
+        out.span_lo[g] = lo;
+        out.padded[g] = ((int64_t)len + PAD - 1) / PAD * PAD;
+        out.ntiles[g] = ((int64_t)len + TILE - 1) / TILE;
+        my_null = null ? 1 : 0;
+        my_len = (unsigned long long)len;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
+        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_null) atomicAdd(&stats[0], my_null);
+        if (my_len) atomicAdd(&stats[1], my_len);
+    }
+}
+
+// One CTA per (element, tile of the stitched vector).  Every candidate read is tested against
+// every range of the element: it contributes `mult` (= number of ranges it overlaps,
+// coverage.R:190-192) on each overlapped range, clipped to the tile.
+__global__ void __launch_bounds__(CTA)
+cov_list_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restrict__ tile_off,
+                const int64_t* __restrict__ ptr, const int8_t* __restrict__ strand,
+                ListArrays la, const uint32_t* __restrict__ xs,
+                const uint32_t* __restrict__ p_end1, const int8_t* __restrict__ p_strand,
+                int ignore_strand, int strand_filter, const int64_t* __restrict__ off,
+                int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int diff[TILE];
+    __shared__ int wtot[WARPS];
+    __shared__ int wpre[WARPS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t g = tile_region[blockIdx.x];
+    const int j = (int)((int64_t)blockIdx.x - tile_off[g]);
+    const int L = la.len[g];
+    const int m = (L + TILE - 1) / TILE;
+    const int tile_len = (((L + m - 1) / m) + ROW - 1) / ROW * ROW;
+    const int t0 = j * tile_len;
+    const int tlen = min(tile_len, L - t0);
+    const int t1 = t0 + tlen - 1;
+    const int nrows = (tlen + ROW - 1) / ROW;
+    for (int i = tid; i < nrows * (ROW / 4); i += CTA)
+        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    const int64_t a = ptr[g], b = ptr[g + 1];
+    const uint32_t clo = la.clo[g], chi = la.chi[g], span_lo = la.span_lo[g];
+    for (uint32_t i = clo + tid; i < chi; i += CTA) {
+        const uint32_t rs = __ldg(xs + i), re1 = __ldg(p_end1 + i);
+        if (re1 <= span_lo) continue;
+        const int rst = p_strand ? (int)__ldg(p_strand + i) : 0;
+        if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
+        int mult = 0;
+        for (int64_t q = a; q < b; q++) {
+            const uint32_t s = __ldg(la.xgs + q), e = __ldg(la.xge + q);
+            if (e + 1u == s) continue;
+            if (rs <= e && re1 > s &&
+                strand_ok(rst, strand ? (int)__ldg(strand + q) : 0, ignore_strand, strand_filter))
+                mult++;
+        }
+        if (mult == 0) continue;
+        for (int64_t q = a; q < b; q++) {
+            const uint32_t s = __ldg(la.xgs + q), e = __ldg(la.xge + q);
+            if (e + 1u == s) continue;
+            // the selected read covers the chromosome-long vector wherever it lies: every
+            // range it touches sees it, hit or not (coverage.R:201-206)
+            if (!(rs <= e && re1 > s)) continue;
+            const int xo = __ldg(la.xoff + q);
+            const int pa = xo + (int)(max(rs, s) - s);
+            const int pb = xo + (int)(min(re1 - 1u, e) - s);
+            if (pb < t0 || pa > t1) continue;
+            atomicAdd(diff + (max(pa, t0) - t0), mult);
+            if (pb + 1 <= t1) atomicSub(diff + (pb + 1 - t0), mult);
+        }
+    }
+    __syncthreads();
+    {
+        const int row_lo = warp * (SEG / ROW);
+        const int row_hi = min(row_lo + SEG / ROW, nrows);
+        const int tot = warp_scan_rows(diff, row_lo, row_hi);
+        if (lane == 0) wtot[warp] = tot;
+    }
+    __syncthreads();
+    if (tid < WARPS) {
+        int p = 0;
+        for (int w = 0; w < tid; w++) p += wtot[w];
+        wpre[tid] = p;
+    }
+    __syncthreads();
+    store_tile<true>(cov + off[g], L, (la.flags[g] & 1u) != 0, t0, tlen, diff, wpre, 0, tid, CTA);
+}
+
+// ---- c(left, center, right) -----------------------------------------------------------------
+__global__ void __launch_bounds__(CTA)
+concat_plan_kernel(int64_t R, const uint8_t* __restrict__ n0, const uint8_t* __restrict__ n1,
+                   const uint8_t* __restrict__ n2, const int32_t* __restrict__ l0,
+                   const int32_t* __restrict__ l1, const int32_t* __restrict__ l2,
+                   int32_t* __restrict__ len, uint8_t* __restrict__ is_null,
+                   int64_t* __restrict__ padded, unsigned long long* __restrict__ stats) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (r >= R) return;
+    const bool null = n0[r] || n1[r] || n2[r];                    // coverage.R:116-117
+    const int64_t L = null ? 0 : (int64_t)l0[r] + l1[r] + l2[r];
+    len[r] = (int32_t)L;
+    is_null[r] = null ? 1 : 0;
+    padded[r] = (L + PAD - 1) / PAD * PAD;
+    if (null) atomicAdd(&stats[0], 1ull);
+    else atomicAdd(&stats[1], (unsigned long long)L);
+}
+
+__global__ void __launch_bounds__(CTA)
+concat_copy_kernel(const int32_t* __restrict__ c0, const int64_t* __restrict__ o0,
+                   const int32_t* __restrict__ l0, const int32_t* __restrict__ c1,
+                   const int64_t* __restrict__ o1, const int32_t* __restrict__ l1,
+                   const int32_t* __restrict__ c2, const int64_t* __restrict__ o2,
+                   const int32_t* __restrict__ l2, const int32_t* __restrict__ len,
+                   const int64_t* __restrict__ off, int32_t* __restrict__ cov) {
+    const int64_t r = blockIdx.x;
+    if (len[r] == 0) return;
+    int32_t* dst = cov + off[r];
+    const int a = l0[r], b = l1[r], c = l2[r];
+    for (int i = threadIdx.x; i < a; i += CTA) dst[i] = c0[o0[r] + i];
+    for (int i = threadIdx.x; i < b; i += CTA) dst[a + i] = c1[o1[r] + i];
+    for (int i = threadIdx.x; i < c; i += CTA) dst[a + b + i] = c2[o2[r] + i];
+}
+
+__global__ void __launch_bounds__(CTA)
+pack_kernel(const int32_t* __restrict__ cov, const int64_t* __restrict__ off,
+            const int32_t* __restrict__ len, const int64_t* __restrict__ packed_off,
+            int64_t first, int32_t* __restrict__ out) {
+    const int64_t r = first + blockIdx.x;
+    const int L = len[r];
+    const int32_t* src = cov + off[r];
+    int32_t* dst = out + packed_off[blockIdx.x];
+    for (int i = threadIdx.x; i < L; i += CTA) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(CTA)
+len_to_i64_kernel(int64_t n, const int32_t* __restrict__ len, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (i < n) out[i] = len[i];
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+int alloc_coverage_arrays(Coverage* cv, int64_t R) {
+    cv->n_regions = R;
+    RCP_TRY(dalloc(&cv->off, (size_t)R + 1));
+    RCP_TRY(dalloc(&cv->len, (size_t)R));
+    RCP_TRY(dalloc(&cv->is_null, (size_t)R));
+    return RCP_OK;
+}
+
+template <int NS>
+int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t* chrom,
+                         const int32_t* start, const int32_t* end, const int8_t* strand,
+                         int ignore_strand, int strand_filter, Coverage* cv) {
+    RCP_TRY(alloc_coverage_arrays(cv, R));
+    RegionArrays ra;
+    RCP_TRY(dalloc(&ra.gs, (size_t)R));
+    ra.len = cv->len;
+    RCP_TRY(dalloc(&ra.flags, (size_t)R));
+    ra.is_null = cv->is_null;
+    RCP_TRY(dalloc(&ra.ix0, (size_t)R * NS));
+    RCP_TRY(dalloc(&ra.ix1, (size_t)R * NS));
+    RCP_TRY(dalloc(&ra.iy0, (size_t)R * NS));
+    RCP_TRY(dalloc(&ra.iy1, (size_t)R * NS));
+    RCP_TRY(dalloc(&ra.padded, (size_t)R));
+    RCP_TRY(dalloc(&ra.ntiles, (size_t)R));
+    int64_t* tile_off = nullptr;
+    RCP_TRY(dalloc(&tile_off, (size_t)R + 1));
+    unsigned int* d_err = nullptr;
+    unsigned long long* d_stats = nullptr;
+    RCP_TRY(dalloc(&d_err, 1));
+    RCP_TRY(dalloc(&d_stats, 2));
+    RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), g_ctx.stream));
+
+    struct Host {
+        int64_t total_padded, total_tiles;
+        unsigned long long stats[2];
+        unsigned int err;
+    } h = {0, 0, {0, 0}, 0};
+    {
+        StageTimer t(ST_COV_PLAN);
+        if (R > 0) {
+            region_plan_kernel<NS><<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
+                R, chrom, start, end, strand, rd.d_chrom_off, rd.d_chrom_len, rd.n_chrom, src,
+                ignore_strand, strand_filter, ra, d_err, d_stats);
+            RCP_LAUNCHED();
+        }
+        RCP_TRY(exclusive_scan2_i64(ra.padded, cv->off, cv->off + R, ra.ntiles, tile_off,
+                                    tile_off + R, R));
+    }
+    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    int rc = RCP_OK;
+    if (h.err & 1u) rc = fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
+    else if (h.err & 2u) rc = fail(RCP_ERR_DATA, "a region has end < start - 1");
+    if (rc == RCP_OK) {
+        cv->total_padded = h.total_padded;
+        cv->n_null = (int64_t)h.stats[0];
+        cv->total_len = (int64_t)h.stats[1];
+        rc = dalloc(&cv->cov, (size_t)h.total_padded);
+    }
+    int32_t* tile_region = nullptr;
+    if (rc == RCP_OK && h.total_tiles > 0) {
+        rc = dalloc(&tile_region, (size_t)h.total_tiles);
+        if (rc == RCP_OK) {
+            {
+                StageTimer t(ST_COV_PLAN);
+                fill_tiles_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(R, ra.ntiles,
+                                                                                tile_off, tile_region);
+                g_ctx.launches++;
+            }
+            StageTimer t(ST_COV_TILE);
+            cov_tile_kernel<NS><<<(unsigned)h.total_tiles, CTA, 0, g_ctx.stream>>>(
+                tile_region, tile_off, ra, src, cv->off, cv->cov);
+            g_ctx.launches++;
+        }
+    }
+    if (rc == RCP_OK && R > 0) {
+        StageTimer t(ST_COV_SMALL);
+        cov_small_kernel<NS><<<blocks_for(R, WARPS), CTA, 0, g_ctx.stream>>>(R, ra, src, cv->off,
+                                                                             cv->cov);
+        g_ctx.launches++;
+    }
+    if (rc == RCP_OK && cudaGetLastError() != cudaSuccess)
+        rc = fail(RCP_ERR_CUDA, "coverage kernel launch failed");
+    dfree(tile_region);
+    dfree(ra.gs);
+    dfree(ra.flags);
+    dfree(ra.ix0);
+    dfree(ra.ix1);
+    dfree(ra.iy0);
+    dfree(ra.iy1);
+    dfree(ra.padded);
+    dfree(ra.ntiles);
+    dfree(tile_off);
+    dfree(d_err);
+    dfree(d_stats);
+    return rc;
+}
+
+}  // namespace
+
+void coverage_release(Coverage& c) {
+    dfree(c.cov);
+    dfree(c.off);
+    dfree(c.len);
+    dfree(c.is_null);
+}
+
+int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                    const int32_t* end, const int8_t* strand, int ignore_strand,
+                    int strand_filter, int mem, Coverage* cv) {
+    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_chrom.init(chrom, (size_t)R, mem));
+    RCP_TRY(d_start.init(start, (size_t)R, mem));
+    RCP_TRY(d_end.init(end, (size_t)R, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)R, mem));
+    const bool unstranded = (strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr);
+    if (unstranded) {
+        RCP_TRY(reads_build_class(rd, CLS_ALL));
+        Sources<1> src;
+        src.xs[0] = rd.cls[CLS_ALL].xs;
+        src.ye[0] = rd.cls[CLS_ALL].ye;
+        src.n[0] = (uint32_t)rd.cls[CLS_ALL].n;
+        return coverage_ranges_impl<1>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
+                                       d_strand.ptr, ignore_strand, strand_filter, cv);
+    }
+    Sources<3> src;
+    for (int k = 0; k < 3; k++) {
+        RCP_TRY(reads_build_class(rd, CLS_PLUS + k));
+        src.xs[k] = rd.cls[CLS_PLUS + k].xs;
+        src.ye[k] = rd.cls[CLS_PLUS + k].ye;
+        src.n[k] = (uint32_t)rd.cls[CLS_PLUS + k].n;
+    }
+    return coverage_ranges_impl<3>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr,
+                                   ignore_strand, strand_filter, cv);
+}
+
+int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_ranges,
+                  const int32_t* chrom, const int32_t* start, const int32_t* end,
+                  const int8_t* strand, int ignore_strand, int strand_filter, int mem,
+                  Coverage* cv) {
+    RCP_TRY(reads_build_pairs(rd));
+    DevIn<int64_t> d_ptr;
+    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_ptr.init(ptr, (size_t)G + 1, mem));
+    RCP_TRY(d_chrom.init(chrom, (size_t)n_ranges, mem));
+    RCP_TRY(d_start.init(start, (size_t)n_ranges, mem));
+    RCP_TRY(d_end.init(end, (size_t)n_ranges, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)n_ranges, mem));
+    RCP_TRY(alloc_coverage_arrays(cv, G));
+    ListArrays la;
+    RCP_TRY(dalloc(&la.xgs, (size_t)n_ranges));
+    RCP_TRY(dalloc(&la.xge, (size_t)n_ranges));
+    RCP_TRY(dalloc(&la.xoff, (size_t)n_ranges));
+    la.len = cv->len;
+    la.is_null = cv->is_null;
+    RCP_TRY(dalloc(&la.flags, (size_t)G));
+    RCP_TRY(dalloc(&la.clo, (size_t)G));
+    RCP_TRY(dalloc(&la.chi, (size_t)G));
+    RCP_TRY(dalloc(&la.span_lo, (size_t)G));
+    RCP_TRY(dalloc(&la.padded, (size_t)G));
+    RCP_TRY(dalloc(&la.ntiles, (size_t)G));
+    int64_t* tile_off = nullptr;
+    RCP_TRY(dalloc(&tile_off, (size_t)G + 1));
+    unsigned int* d_err = nullptr;
+    unsigned long long* d_stats = nullptr;
+    RCP_TRY(dalloc(&d_err, 1));
+    RCP_TRY(dalloc(&d_stats, 2));
+    RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), g_ctx.stream));
+    struct Host {
+        int64_t total_padded, total_tiles;
+        unsigned long long stats[2];
+        unsigned int err;
+    } h = {0, 0, {0, 0}, 0};
+    StageTimer list_timer(ST_COV_LIST);
+    if (G > 0) {
+        list_plan_kernel<<<blocks_for(G, CTA), CTA, 0, g_ctx.stream>>>(
+            G, d_ptr.ptr, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, rd.d_chrom_off,
+            rd.d_chrom_len, rd.n_chrom, rd.cls[CLS_ALL].xs, rd.p_end1, rd.p_strand, rd.p_maxend1,
+            (uint32_t)rd.n, ignore_strand, strand_filter, la, d_err, d_stats);
+        RCP_LAUNCHED();
+    }
+    RCP_TRY(exclusive_scan2_i64(la.padded, cv->off, cv->off + G, la.ntiles, tile_off,
+                                tile_off + G, G));
+    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    int rc = RCP_OK;
+    if (h.err & 1u) rc = fail(RCP_ERR_DATA, "a range has a chromosome id outside [0, n_chrom)");
+    else if (h.err & 2u) rc = fail(RCP_ERR_DATA, "a range has end < start - 1");
+    else if (h.err & 4u)
+        rc = fail(RCP_ERR_DATA, "the ranges of one list element lie on different chromosomes");
+    if (rc == RCP_OK) {
+        cv->total_padded = h.total_padded;
+        cv->n_null = (int64_t)h.stats[0];
+        cv->total_len = (int64_t)h.stats[1];
+        rc = dalloc(&cv->cov, (size_t)h.total_padded);
+    }
+    int32_t* tile_region = nullptr;
+    if (rc == RCP_OK && h.total_tiles > 0) {
+        rc = dalloc(&tile_region, (size_t)h.total_tiles);
+        if (rc == RCP_OK) {
+            fill_tiles_kernel<<<blocks_for(G, CTA), CTA, 0, g_ctx.stream>>>(G, la.ntiles, tile_off,
+                                                                            tile_region);
+            g_ctx.launches++;
+            cov_list_kernel<<<(unsigned)h.total_tiles, CTA, 0, g_ctx.stream>>>(
+                tile_region, tile_off, d_ptr.ptr, d_strand.ptr, la, rd.cls[CLS_ALL].xs, rd.p_end1,
+                rd.p_strand, ignore_strand, strand_filter, cv->off, cv->cov);
+            g_ctx.launches++;
+            if (cudaGetLastError() != cudaSuccess)
+                rc = fail(RCP_ERR_CUDA, "list coverage kernel launch failed");
+        }
+    }
+    dfree(tile_region);
+    dfree(la.xgs);
+    dfree(la.xge);
+    dfree(la.xoff);
+    dfree(la.flags);
+    dfree(la.clo);
+    dfree(la.chi);
+    dfree(la.span_lo);
+    dfree(la.padded);
+    dfree(la.ntiles);
+    dfree(tile_off);
+    dfree(d_err);
+    dfree(d_stats);
+    return rc;
+}
+
+int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv) {
+    const int64_t R = a.n_regions;
+    if (b.n_regions != R || c.n_regions != R)
+        return fail(RCP_ERR_ARG, "concat3: the three coverages have different lengths");
+    RCP_TRY(alloc_coverage_arrays(cv, R));
+    int64_t* padded = nullptr;
+    unsigned long long* d_stats = nullptr;
+    RCP_TRY(dalloc(&padded, (size_t)R));
+    RCP_TRY(dalloc(&d_stats, 2));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 16, g_ctx.stream));
+    if (R > 0) {
+        concat_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
+            R, a.is_null, b.is_null, c.is_null, a.len, b.len, c.len, cv->len, cv->is_null, padded,
+            d_stats);
+        RCP_LAUNCHED();
+    }
+    RCP_TRY(exclusive_scan_i64(padded, cv->off, R, cv->off + R));
+    int64_t total = 0;
+    unsigned long long stats[2] = {0, 0};
+    StageTimer concat_timer(ST_COV_CONCAT);
+    RCP_CUDA(cudaMemcpyAsync(&total, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    cv->total_padded = total;
+    cv->n_null = (int64_t)stats[0];
+    cv->total_len = (int64_t)stats[1];
+    RCP_TRY(dalloc(&cv->cov, (size_t)total));
+    if (R > 0) {
+        concat_copy_kernel<<<(unsigned)R, CTA, 0, g_ctx.stream>>>(a.cov, a.off, a.len, b.cov, b.off,
+                                                                 b.len, c.cov, c.off, c.len,
+                                                                 cv->len, cv->off, cv->cov);
+        RCP_LAUNCHED();
+    }
+    dfree(padded);
+    dfree(d_stats);
+    return RCP_OK;
+}
+
+int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
+                   int64_t capacity) {
+    if (first < 0 || count < 0 || first + count > cv.n_regions)
+        return fail(RCP_ERR_ARG, "fetch: region range [%lld, %lld) outside [0, %lld)",
+                    (long long)first, (long long)(first + count), (long long)cv.n_regions);
+    if (count == 0) return RCP_OK;
+    int64_t *len64 = nullptr, *poff = nullptr;
+    RCP_TRY(dalloc(&len64, (size_t)count));
+    RCP_TRY(dalloc(&poff, (size_t)count + 1));
+    len_to_i64_kernel<<<blocks_for(count, CTA), CTA, 0, g_ctx.stream>>>(count, cv.len + first, len64);
+    RCP_LAUNCHED();
+    RCP_TRY(exclusive_scan_i64(len64, poff, count, poff + count));
+    int64_t total = 0;
+    RCP_CUDA(cudaMemcpyAsync(&total, poff + count, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    int rc = RCP_OK;
+    if (total > capacity) {
+        rc = fail(RCP_ERR_ARG, "fetch: %lld ints needed, capacity %lld", (long long)total,
+                  (long long)capacity);
+    } else if (total > 0) {
+        int32_t* packed = nullptr;
+        rc = dalloc(&packed, (size_t)total);
+        if (rc == RCP_OK) {
+            pack_kernel<<<(unsigned)count, CTA, 0, g_ctx.stream>>>(cv.cov, cv.off, cv.len, poff,
+                                                                  first, packed);
+            g_ctx.launches++;
+            cudaError_t e = cudaMemcpyAsync(out, packed, (size_t)total * 4, cudaMemcpyDeviceToHost,
+                                            g_ctx.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+            if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "fetch copy failed: %s", cudaGetErrorString(e));
+            dfree(packed);
+        }
+    }
+    dfree(len64);
+    dfree(poff);
+    return rc;
+}
+
+}  // namespace rcp

@@ -1,0 +1,410 @@
+// rcp_reads_load: reads -> device index.
+//
+// Every read is mapped to a 32-bit GLOBAL coordinate  g = chrom_off[chrom] + pos  (chromosomes
+// laid end to end with a 2-position gap), and two arrays are sorted INDEPENDENTLY:
+//     xs = sorted(global start)          ye = sorted(global end + 1)
+// Exact coverage then follows from ranks alone:
+//     cov(p) = #{xs <= p} - #{ye <= p}
+// so the coverage kernels never need (start,end) pairs, never depend on the read width and can
+// cut any region into tiles without carrying state between tiles (coverage.cu).
+// Replaces splitBySeqname + the per-region findOverlaps/coverage of the reference
+// (/root/reference/R/util.R:1-13, R/coverage.R:189-201).
+#include "rcp_internal.cuh"
+
+namespace rcp {
+
+namespace {
+
+constexpr int TPB = 256;
+
+// bit0 chrom id out of range, bit1 start < 1 or end < start, bit2 start beyond the chromosome
+__global__ void __launch_bounds__(TPB)
+reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
+                       const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                       const int8_t* __restrict__ strand, const uint32_t* __restrict__ chrom_off,
+                       const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
+                       uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
+                       int8_t* __restrict__ strand_out, unsigned int* __restrict__ err,
+                       unsigned long long* __restrict__ cls_count) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    unsigned int my_err = 0;
+    unsigned int np = 0, nm = 0, ns = 0;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+        const int c = chrom[i];
+        int64_t s = start[i], e = end[i];
+        const int st = strand ? (int)strand[i] : 0;
+        uint32_t gs = 0, ge1 = 0;
+        if (c < 0 || c >= n_chrom) {
+            my_err |= 1u;
+        } else if (s < 1 || e < s) {
+            my_err |= 2u;
+        } else {
+            const int64_t len = chrom_len[c];
+            if (frag_len > 0) {           // resize(fix="start"): '-' keeps its end
+                if (st < 0) s = e - frag_len + 1;
+                else e = s + frag_len - 1;
+            }
+            if (s < 1) s = 1;             // trim()
+            if (e > len) e = len;
+            if (s > len || e < s) my_err |= 4u;
+            else {
+                gs = chrom_off[c] + (uint32_t)s;
+                ge1 = chrom_off[c] + (uint32_t)e + 1u;
+            }
+        }
+        g_start[i] = gs;
+        g_end1[i] = ge1;
+        if (strand_out) strand_out[i] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
+        np += st > 0;
+        nm += st < 0;
+        ns += st == 0;
+    }
+    // block-level reduction of the three strand counters and the error mask
+    __shared__ unsigned int sh[4];
+    if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int d = 16; d > 0; d >>= 1) {
+        np += __shfl_xor_sync(0xffffffffu, np, d);
+        nm += __shfl_xor_sync(0xffffffffu, nm, d);
+        ns += __shfl_xor_sync(0xffffffffu, ns, d);
+        my_err |= __shfl_xor_sync(0xffffffffu, my_err, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh[0], np);
+        atomicAdd(&sh[1], nm);
+        atomicAdd(&sh[2], ns);
+        atomicOr(&sh[3], my_err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh[0]) atomicAdd(&cls_count[0], (unsigned long long)sh[0]);
+        if (sh[1]) atomicAdd(&cls_count[1], (unsigned long long)sh[1]);
+        if (sh[2]) atomicAdd(&cls_count[2], (unsigned long long)sh[2]);
+        if (sh[3]) atomicOr(err, sh[3]);
+    }
+}
+
+// keep the reads of one strand (order is irrelevant: both outputs are sorted afterwards)
+__global__ void __launch_bounds__(TPB)
+compact_strand_kernel(int64_t n, const uint32_t* __restrict__ g_start,
+                      const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
+                      int want, uint32_t* __restrict__ xs, uint32_t* __restrict__ ye,
+                      unsigned long long* __restrict__ cursor) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n_round; i += stride) {
+        const bool keep = (i < n) && ((int)strand[i] == want);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+            xs[o] = g_start[i];
+            ye[o] = g_end1[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) iota_kernel(int64_t n, uint32_t* __restrict__ v) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride)
+        v[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(TPB)
+gather_pairs_kernel(int64_t n, const uint32_t* __restrict__ perm,
+                    const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
+                    uint32_t* __restrict__ p_end1, int8_t* __restrict__ p_strand) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+        const uint32_t j = perm[i];
+        p_end1[i] = g_end1[j];
+        if (p_strand) p_strand[i] = strand[j];
+    }
+}
+
+// ---- running maximum over uint32 (three-kernel scan, tiles of 2048) ----------------------
+constexpr int MX_ITEMS = 8;
+constexpr int MX_TILE = TPB * MX_ITEMS;
+
+__device__ __forceinline__ uint32_t block_max_scan(uint32_t v, uint32_t* total) {
+    // inclusive running max over the block's threads
+    __shared__ uint32_t wmax[TPB / 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = max(v, o);
+    }
+    if (lane == 31) wmax[warp] = v;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TPB / 32; w++) {
+        uint32_t s = wmax[w];
+        if (w < (int)warp) pre = max(pre, s);
+        tot = max(tot, s);
+    }
+    __syncthreads();
+    *total = tot;
+    return max(pre, v);
+}
+
+__global__ void __launch_bounds__(TPB)
+max_reduce_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ partial) {
+    const int64_t base = (int64_t)blockIdx.x * MX_TILE;
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < MX_ITEMS; k++) {
+        int64_t i = base + (int64_t)k * TPB + threadIdx.x;
+        if (i < n) m = max(m, in[i]);
+    }
+    uint32_t tot;
+    block_max_scan(m, &tot);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// partial[b] <- max of all tiles BEFORE b (exclusive), one block
+__global__ void __launch_bounds__(TPB)
+max_partials_kernel(uint32_t* __restrict__ partial, int64_t nb) {
+    uint32_t carry = 0;
+    for (int64_t b0 = 0; b0 < nb; b0 += TPB) {
+        int64_t i = b0 + threadIdx.x;
+        uint32_t v = (i < nb) ? partial[i] : 0;
+        uint32_t tot;
+        uint32_t inc = block_max_scan(v, &tot);
+        // exclusive = max over previous threads: recompute from the neighbour
+        uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        __shared__ uint32_t last_of_warp[TPB / 32];
+        if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t ex;
+        if ((threadIdx.x & 31) != 0) ex = prev;
+        else ex = (threadIdx.x == 0) ? 0u : last_of_warp[(threadIdx.x >> 5) - 1];
+        __syncthreads();
+        if (i < nb) partial[i] = max(carry, ex);
+        carry = max(carry, tot);
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+max_apply_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
+                 const uint32_t* __restrict__ partial) {
+    const int64_t base = (int64_t)blockIdx.x * MX_TILE + (int64_t)threadIdx.x * MX_ITEMS;
+    uint32_t v[MX_ITEMS];
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < MX_ITEMS; k++) {
+        int64_t i = base + k;
+        v[k] = (i < n) ? in[i] : 0;
+        m = max(m, v[k]);
+    }
+    uint32_t tot;
+    uint32_t inc = block_max_scan(m, &tot);
+    // running max of everything before this thread's first element
+    uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    __shared__ uint32_t last_of_warp[TPB / 32];
+    if ((threadIdx.x & 31) == 31) last_of_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t run;
+    if ((threadIdx.x & 31) != 0) run = prev;
+    else run = (threadIdx.x == 0) ? 0u : last_of_warp[(threadIdx.x >> 5) - 1];
+    run = max(run, partial[blockIdx.x]);
+#pragma unroll
+    for (int k = 0; k < MX_ITEMS; k++) {
+        int64_t i = base + k;
+        run = max(run, v[k]);
+        if (i < n) out[i] = run;
+    }
+}
+
+int running_max_u32(const uint32_t* in, uint32_t* out, int64_t n) {
+    if (n <= 0) return RCP_OK;
+    const int64_t nb = (n + MX_TILE - 1) / MX_TILE;
+    uint32_t* partial = nullptr;
+    RCP_TRY(dalloc(&partial, (size_t)nb));
+    max_reduce_kernel<<<(unsigned)nb, TPB, 0, g_ctx.stream>>>(in, n, partial);
+    RCP_LAUNCHED();
+    max_partials_kernel<<<1, TPB, 0, g_ctx.stream>>>(partial, nb);
+    RCP_LAUNCHED();
+    max_apply_kernel<<<(unsigned)nb, TPB, 0, g_ctx.stream>>>(in, out, n, partial);
+    RCP_LAUNCHED();
+    dfree(partial);
+    return RCP_OK;
+}
+
+inline unsigned grid_for(int64_t n) {
+    int64_t b = (n + TPB - 1) / TPB;
+    int64_t cap = (int64_t)g_ctx.sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace
+
+void reads_release(ReadsIdx& r) {
+    dfree(r.d_chrom_len);
+    dfree(r.d_chrom_off);
+    dfree(r.g_start);
+    dfree(r.g_end1);
+    dfree(r.d_strand);
+    for (int c = 0; c < CLS_N; c++) {
+        dfree(r.cls[c].xs);
+        dfree(r.cls[c].ye);
+        r.cls[c].built = false;
+    }
+    dfree(r.p_end1);
+    dfree(r.p_strand);
+    dfree(r.p_maxend1);
+    r.pairs_built = false;
+}
+
+int reads_build_class(ReadsIdx& r, int cls) {
+    SortedClass& sc = r.cls[cls];
+    if (sc.built) return RCP_OK;
+    if (cls == CLS_ALL) {
+        sc.n = r.n;
+        RCP_TRY(dalloc(&sc.xs, (size_t)r.n));
+        RCP_TRY(dalloc(&sc.ye, (size_t)r.n));
+        RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
+                                 g_ctx.stream));
+        RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
+                                 g_ctx.stream));
+    } else {
+        // sc.n was filled from the strand histogram at load time
+        RCP_TRY(dalloc(&sc.xs, (size_t)sc.n));
+        RCP_TRY(dalloc(&sc.ye, (size_t)sc.n));
+        if (sc.n > 0) {
+            if (!r.has_strand) {   // every read is '*': the STAR class is everything
+                RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4,
+                                         cudaMemcpyDeviceToDevice, g_ctx.stream));
+                RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4,
+                                         cudaMemcpyDeviceToDevice, g_ctx.stream));
+            } else {
+                unsigned long long* cursor = nullptr;
+                RCP_TRY(dalloc(&cursor, 1));
+                RCP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), g_ctx.stream));
+                const int want = cls == CLS_PLUS ? 1 : (cls == CLS_MINUS ? -1 : 0);
+                compact_strand_kernel<<<grid_for(r.n), TPB, 0, g_ctx.stream>>>(
+                    r.n, r.g_start, r.g_end1, r.d_strand, want, sc.xs, sc.ye, cursor);
+                RCP_LAUNCHED();
+                dfree(cursor);
+            }
+        }
+    }
+    {
+        StageTimer t(ST_INDEX_SORT);
+        RCP_TRY(sort_keys_u32(sc.xs, sc.n, r.key_bits));
+        RCP_TRY(sort_keys_u32(sc.ye, sc.n, r.key_bits));
+    }
+    r.device_bytes += (size_t)sc.n * 8;
+    sc.built = true;
+    return RCP_OK;
+}
+
+int reads_build_pairs(ReadsIdx& r) {
+    if (r.pairs_built) return RCP_OK;
+    RCP_TRY(reads_build_class(r, CLS_ALL));
+    uint32_t *keys = nullptr, *perm = nullptr;
+    RCP_TRY(dalloc(&keys, (size_t)r.n));
+    RCP_TRY(dalloc(&perm, (size_t)r.n));
+    RCP_CUDA(cudaMemcpyAsync(keys, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
+                             g_ctx.stream));
+    iota_kernel<<<grid_for(r.n), TPB, 0, g_ctx.stream>>>(r.n, perm);
+    RCP_LAUNCHED();
+    {
+        StageTimer t(ST_INDEX_SORT);
+        RCP_TRY(sort_pairs_u32(keys, perm, r.n, r.key_bits));
+    }
+    RCP_TRY(dalloc(&r.p_end1, (size_t)r.n));
+    if (r.has_strand) RCP_TRY(dalloc(&r.p_strand, (size_t)r.n));
+    gather_pairs_kernel<<<grid_for(r.n), TPB, 0, g_ctx.stream>>>(r.n, perm, r.g_end1, r.d_strand,
+                                                                r.p_end1, r.p_strand);
+    RCP_LAUNCHED();
+    RCP_TRY(dalloc(&r.p_maxend1, (size_t)r.n));
+    RCP_TRY(running_max_u32(r.p_end1, r.p_maxend1, r.n));
+    dfree(keys);
+    dfree(perm);
+    r.device_bytes += (size_t)r.n * (8 + (r.has_strand ? 1 : 0));
+    r.pairs_built = true;
+    return RCP_OK;
+}
+
+// Builds the raw global-coordinate arrays and the ALL class.  Synchronises once to validate.
+int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+                    const int32_t* end, const int8_t* strand, int n_chrom,
+                    const int64_t* chrom_len, int frag_len, int mem) {
+    r.n = n;
+    r.n_chrom = n_chrom;
+    r.has_strand = strand != nullptr;
+    r.chrom_len.assign(chrom_len, chrom_len + n_chrom);
+    r.chrom_off.resize((size_t)n_chrom + 1);
+    uint64_t off = 0;
+    for (int c = 0; c < n_chrom; c++) {
+        if (chrom_len[c] <= 0)
+            return fail(RCP_ERR_UNSUPPORTED,
+                        "chrom_len[%d] = %lld: unknown (NA) seqlengths are not supported", c,
+                        (long long)chrom_len[c]);
+        r.chrom_off[c] = (uint32_t)off;
+        off += (uint64_t)chrom_len[c] + 2;
+        if (off >= 0xfffffff0ull)
+            return fail(RCP_ERR_UNSUPPORTED,
+                        "genome longer than 2^32 positions: 64-bit coordinates not implemented");
+    }
+    r.chrom_off[n_chrom] = (uint32_t)off;
+    r.key_bits = 1;
+    while (r.key_bits < 32 && (1ull << r.key_bits) <= off) r.key_bits++;
+
+    RCP_TRY(dalloc(&r.d_chrom_len, (size_t)n_chrom));
+    RCP_TRY(dalloc(&r.d_chrom_off, (size_t)n_chrom + 1));
+    RCP_CUDA(cudaMemcpyAsync(r.d_chrom_len, r.chrom_len.data(), (size_t)n_chrom * 8,
+                             cudaMemcpyHostToDevice, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(r.d_chrom_off, r.chrom_off.data(), ((size_t)n_chrom + 1) * 4,
+                             cudaMemcpyHostToDevice, g_ctx.stream));
+
+    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_chrom.init(chrom, (size_t)n, mem));
+    RCP_TRY(d_start.init(start, (size_t)n, mem));
+    RCP_TRY(d_end.init(end, (size_t)n, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)n, mem));
+
+    RCP_TRY(dalloc(&r.g_start, (size_t)n));
+    RCP_TRY(dalloc(&r.g_end1, (size_t)n));
+    if (r.has_strand) RCP_TRY(dalloc(&r.d_strand, (size_t)n));
+    unsigned int* d_err = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    RCP_TRY(dalloc(&d_err, 1));
+    RCP_TRY(dalloc(&d_cnt, 3));
+    RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
+    if (n > 0) {
+        StageTimer t(ST_INDEX_MAP);
+        reads_to_global_kernel<<<grid_for(n), TPB, 0, g_ctx.stream>>>(
+            n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
+            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt);
+        RCP_LAUNCHED();
+    }
+    unsigned int h_err = 0;
+    unsigned long long h_cnt[3] = {0, 0, 0};
+    RCP_TRY(reads_build_class(r, CLS_ALL));
+    RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    dfree(d_err);
+    dfree(d_cnt);
+    if (h_err & 1u) return fail(RCP_ERR_DATA, "a read has a chromosome id outside [0, n_chrom)");
+    if (h_err & 2u) return fail(RCP_ERR_DATA, "a read violates 1 <= start <= end");
+    if (h_err & 4u) return fail(RCP_ERR_DATA, "a read starts beyond the end of its chromosome");
+    r.cls[CLS_PLUS].n = (int64_t)h_cnt[0];
+    r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
+    r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
+    r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
+    return RCP_OK;
+}
+
+}  // namespace rcp

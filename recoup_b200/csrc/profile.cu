@@ -1,0 +1,489 @@
+// Profile-matrix kernels (sm_100a): binCoverageMatrix / baseCoverageMatrix / splitVector of the
+// reference (/root/reference/R/profile.R:100-212, R/util.R:15-85).
+//
+//   bin_matrix_kernel    1 CTA / region: bin edges from R's seed-42 rank table (util.R:74-80),
+//                        segmented integer sums with sub-warp groups sized to the bin width,
+//                        fp64 mean (or exact median by value bisection) written column-major
+//   interp_kernel        regions shorter than the bin count (util.R:17-73): fmm spline or
+//                        neighbourhood fill, one warp per flagged region
+//   base_matrix_kernel   per-base matrix: int32 -> fp64 tiled transpose (profile.R:100-151)
+#include "r_rng.cuh"
+#include "rcp_internal.cuh"
+
+namespace rcp {
+
+namespace {
+
+constexpr int CTA = 256;
+constexpr int WARPS = CTA / 32;
+
+struct Seg {
+    int a, b;   // [a, b) inside the region's coverage vector
+};
+
+__device__ __forceinline__ Seg segment_of(int L, int where, int f1, int f2) {
+    Seg s;
+    switch (where) {
+        case RCP_WHERE_CENTER: s.a = f1; s.b = L - f2; break;          // profile.R:170
+        case RCP_WHERE_UPSTREAM: s.a = 0; s.b = f1; break;              // profile.R:178
+        case RCP_WHERE_DOWNSTREAM: s.a = L - f2; s.b = L; break;        // profile.R:185
+        default: s.a = 0; s.b = L; break;                               // profile.R:159-162
+    }
+    if (s.a < 0) s.a = 0;
+    if (s.b > L) s.b = L;
+    if (s.b < s.a) s.b = s.a;
+    return s;
+}
+
+struct BinArgs {
+    const int32_t* cov;
+    const int64_t* off;
+    const int32_t* len;
+    const uint8_t* is_null;
+    const int* rank;          // device rank table of n bins
+    int where, f1, f2, n;
+    double scale;
+    double* out;
+    int64_t ld;
+    int32_t* short_list;      // regions with segment shorter than n (for interp_kernel)
+    unsigned int* short_count;
+};
+
+template <bool MEDIAN>
+__global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
+    extern __shared__ int sh[];
+    int* edges = sh;                    // n + 1
+    __shared__ int wcount[WARPS];
+    __shared__ int chunk_carry;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r = blockIdx.x;
+    const int n = p.n;
+    double* out = p.out + r;
+    if (p.is_null[r]) {                 // profile.R:191-197: NULL -> zero row
+        for (int i = tid; i < n; i += CTA) out[(int64_t)i * p.ld] = 0.0;
+        return;
+    }
+    const int L = p.len[r];
+    const Seg sg = segment_of(L, p.where, p.f1, p.f2);
+    const int Ls = sg.b - sg.a;
+    if (Ls < n) {                       // util.R:17: interpolation path, handled separately
+        if (tid == 0) {
+            if (Ls <= 0) {
+                for (int i = 0; i < n; i++) out[(int64_t)i * p.ld] = 0.0;
+            } else {
+                p.short_list[atomicAdd(p.short_count, 1u)] = (int32_t)r;
+            }
+        }
+        return;
+    }
+    // ---- bin edges: bin i has bsz + [rank[i] <= dif] elements (util.R:74-80) ----
+    const int bsz = Ls / n, dif = Ls - bsz * n;
+    if (tid == 0) chunk_carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += CTA) {
+        const int i = c0 + tid;
+        const bool extra = (i < n) && (p.rank[i] <= dif);
+        const unsigned bal = __ballot_sync(0xffffffffu, extra);
+        if (lane == 0) wcount[warp] = __popc(bal);
+        __syncthreads();
+        int pre = chunk_carry;
+        for (int w = 0; w < warp; w++) pre += wcount[w];
+        pre += __popc(bal & ((1u << lane) - 1u));
+        if (i < n) edges[i] = sg.a + i * bsz + pre;
+        __syncthreads();
+        if (tid == CTA - 1) chunk_carry = pre + (extra ? 1 : 0);
+        __syncthreads();
+    }
+    if (tid == 0) edges[n] = sg.b;
+    __syncthreads();
+    // ---- segmented reduction: groups of g lanes per bin ----
+    int g = 1;
+    while (g < 32 && g < bsz) g <<= 1;
+    const int per_warp = 32 / g;
+    const int sub = lane / g, li = lane % g;
+    const int32_t* src = p.cov + p.off[r];
+    for (int b0 = warp * per_warp; b0 < n; b0 += WARPS * per_warp) {
+        const int i = b0 + sub;
+        const bool ok = i < n;
+        const int lo = ok ? edges[i] : 0, hi = ok ? edges[i + 1] : 0;
+        const int cnt = hi - lo;
+        if (!MEDIAN) {
+            long long s = 0;
+            for (int q = lo + li; q < hi; q += g) s += __ldg(src + q);
+            for (int d = g >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (ok && li == 0) out[(int64_t)i * p.ld] = p.scale * ((double)s / (double)cnt);
+        } else {
+            // exact median by bisection on the value range: k-th smallest = least v with
+            // #{x <= v} >= k+1
+            int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
+            for (int q = lo + li; q < hi; q += g) {
+                const int v = __ldg(src + q);
+                vmin = min(vmin, v);
+                vmax = max(vmax, v);
+            }
+            for (int d = g >> 1; d > 0; d >>= 1) {
+                vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+                vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+            }
+            const int k1 = (cnt - 1) / 2, k2 = cnt / 2;
+            int res[2];
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int k = t == 0 ? k1 : k2;
+                int a = vmin, b = vmax;          // answer in [a, b]
+                // all lanes of the WARP iterate the same number of times (shuffles are
+                // warp-wide): bound by the warp-wide maximum range
+                int span = ok ? (b - a) : 0;
+                for (int d = 16; d > 0; d >>= 1) span = max(span, __shfl_xor_sync(0xffffffffu, span, d));
+                while (span > 0) {
+                    const int mid = a + ((b - a) >> 1);
+                    int c = 0;
+                    for (int q = lo + li; q < hi; q += g) c += (__ldg(src + q) <= mid);
+                    for (int d = g >> 1; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                    if (a < b) {
+                        if (c >= k + 1) b = mid;
+                        else a = mid + 1;
+                    }
+                    span >>= 1;
+                }
+                res[t] = a;
+            }
+            if (ok && li == 0)
+                out[(int64_t)i * p.ld] = p.scale * (((double)res[0] + (double)res[1]) * 0.5);
+        }
+    }
+}
+
+// ---- interpolation of short segments (util.R:17-73) ------------------------------------------
+struct InterpArgs {
+    const int32_t* cov;
+    const int64_t* off;
+    const int32_t* len;
+    int where, f1, f2, n;
+    int interp, seed, sample_kind;
+    double scale;
+    double* out;
+    int64_t ld;
+    const int32_t* short_list;
+    const unsigned int* short_count;
+};
+
+// dynamic smem per warp-CTA: 4n doubles + 2n ints + RRng
+__global__ void __launch_bounds__(32) interp_kernel(InterpArgs p) {
+    extern __shared__ double shd[];
+    const int n = p.n;
+    double* y = shd;               // input values (L) / neighbourhood vector (n)
+    double* cb = shd + n;          // spline b / neighbourhood pre-fill copy
+    double* cc = shd + 2 * n;
+    double* cd = shd + 3 * n;
+    int* ia = reinterpret_cast<int*>(shd + 4 * n);   // n ints
+    int* ib = ia + n;                                 // n ints
+    RRng* rng = reinterpret_cast<RRng*>(ib + n);
+    const int lane = threadIdx.x;
+    const unsigned int count = *p.short_count;
+    for (unsigned int w = blockIdx.x; w < count; w += gridDim.x) {
+        const int64_t r = p.short_list[w];
+        const int L_all = p.len[r];
+        const Seg sg = segment_of(L_all, p.where, p.f1, p.f2);
+        const int L = sg.b - sg.a;
+        const int32_t* src = p.cov + p.off[r] + sg.a;
+        double* out = p.out + r;
+        __syncwarp();
+        bool neighborhood = p.interp == RCP_INTERP_NEIGHBORHOOD;
+        if (p.interp == RCP_INTERP_AUTO) neighborhood = ((double)(n - L) / (double)n) < 0.2;
+        if (neighborhood && (L < 4 || n < 6)) {
+            // R's sample() would stop(); flagged as NaN row (the host rejects these sizes first)
+            for (int i = lane; i < n; i += 32) out[(int64_t)i * p.ld] = nan("");
+            continue;
+        }
+        if (!neighborhood) {
+            // ---- stats::spline(method = "fmm"), x = 1..L, xout = seq(1, L, length.out = n)
+            for (int i = lane; i < L; i += 32) y[i] = (double)src[i];
+            __syncwarp();
+            if (lane == 0) {
+                double *b = cb, *c = cc, *d = cd;
+                for (int i = 0; i < L; i++) b[i] = c[i] = d[i] = 0.0;
+                if (L == 2) {
+                    b[0] = b[1] = y[1] - y[0];
+                } else if (L >= 3) {
+                    const int nm1 = L - 1;
+                    d[0] = 1.0;                       // x[i+1] - x[i] == 1
+                    c[1] = (y[1] - y[0]) / d[0];
+                    for (int i = 1; i < nm1; i++) {
+                        d[i] = 1.0;
+                        b[i] = 2.0 * (d[i - 1] + d[i]);
+                        c[i + 1] = (y[i + 1] - y[i]) / d[i];
+                        c[i] = c[i + 1] - c[i];
+                    }
+                    b[0] = -d[0];
+                    b[L - 1] = -d[L - 2];
+                    c[0] = c[L - 1] = 0.0;
+                    if (L > 3) {
+                        c[0] = c[2] / 2.0 - c[1] / 2.0;              // x[3]-x[1] = x[2]-x[0] = 2
+                        c[L - 1] = c[L - 2] / 2.0 - c[L - 3] / 2.0;
+                        c[0] = c[0] * d[0] * d[0] / 3.0;             // x[3]-x[0] = 3
+                        c[L - 1] = -c[L - 1] * d[L - 2] * d[L - 2] / 3.0;
+                    }
+                    for (int i = 1; i < L; i++) {
+                        const double t = d[i - 1] / b[i - 1];
+                        b[i] = b[i] - t * d[i - 1];
+                        c[i] = c[i] - t * c[i - 1];
+                    }
+                    c[L - 1] = c[L - 1] / b[L - 1];
+                    for (int i = L - 2; i >= 0; i--) c[i] = (c[i] - d[i] * c[i + 1]) / b[i];
+                    b[L - 1] = (y[L - 1] - y[L - 2]) / d[L - 2] + d[L - 2] * (c[L - 2] + 2.0 * c[L - 1]);
+                    for (int i = 0; i < nm1; i++) {
+                        b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i]);
+                        d[i] = (c[i + 1] - c[i]) / d[i];
+                        c[i] = 3.0 * c[i];
+                    }
+                    c[L - 1] = 3.0 * c[L - 1];
+                    d[L - 1] = d[L - 2];
+                }
+            }
+            __syncwarp();
+            const double by = n > 2 ? ((double)L - 1.0) / (double)(n - 1) : 0.0;
+            for (int l = lane; l < n; l += 32) {
+                double ul = 1.0 + (double)l * by;
+                if (l == 0) ul = 1.0;
+                if (l == n - 1 && n > 1) ul = (double)L;
+                int i = (int)floor(ul) - 1;
+                if (i > L - 2) i = L - 2;
+                if (i < 0) i = 0;
+                const double dx = ul - (double)(i + 1);
+                double v = y[i] + dx * (cb[i] + dx * (cc[i] + dx * cd[i]));
+                if (v < 0.0) v = 0.0;                                 // util.R:42,47
+                out[(int64_t)l * p.ld] = p.scale * v;
+            }
+        } else {
+            // ---- neighbourhood fill (util.R:24-38 / 54-68)
+            for (int i = lane; i < n; i += 32) {
+                y[i] = nan("");
+                ia[i] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                y[0] = (double)src[0];
+                y[1] = (double)src[1];
+                y[n - 2] = (double)src[L - 2];
+                y[n - 1] = (double)src[L - 1];
+                rng->seed((uint32_t)p.seed, p.sample_kind);
+                // orig.pos <- sort(sample(3:(n-2), L-4)): mark the picks, sweep in order
+                const int pool = n - 4, k = L - 4;
+                int* x = ib;
+                for (int i = 0; i < pool; i++) x[i] = i;
+                int m = pool;
+                for (int i = 0; i < k; i++) {
+                    const int j = (int)rng->index((uint32_t)m);
+                    ia[x[j]] = 1;                      // value 3 + x[j]  (1-based position)
+                    x[j] = x[--m];
+                }
+                int q = 2;
+                for (int i = 0; i < pool; i++)
+                    if (ia[i]) y[2 + i] = (double)src[q++];
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) cb[i] = y[i];
+            __syncwarp();
+            for (int z = lane; z < n; z += 32) {
+                double v = cb[z];
+                if (isnan(v)) {                        // mean(y[c(z-2,z-1,z+1,z+2)], na.rm=TRUE)
+                    double s = 0.0;
+                    int c = 0;
+                    const int nb[4] = {z - 2, z - 1, z + 1, z + 2};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const double u = cb[nb[t]];    // z in [2, n-3] -> always in range
+                        if (!isnan(u)) { s += u; c++; }
+                    }
+                    v = c ? s / (double)c : nan("");
+                }
+                out[(int64_t)z * p.ld] = p.scale * v;
+            }
+        }
+    }
+}
+
+// ---- per-base matrix --------------------------------------------------------------------------
+struct BaseArgs {
+    const int32_t* cov;
+    const int64_t* off;
+    const int32_t* len;
+    const uint8_t* is_null;
+    int where, f1, f2;
+    int64_t R, n_cols;
+    double scale;
+    double* out;
+    int64_t ld;
+};
+
+__global__ void __launch_bounds__(256) base_matrix_kernel(BaseArgs p) {
+    __shared__ int tile[32][33];
+    __shared__ int64_t r_off[32];
+    __shared__ int r_a[32], r_b[32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+    if (ty == 0) {
+        const int64_t r = r0 + tx;
+        int a = 0, b = 0;
+        int64_t o = 0;
+        if (r < p.R && !p.is_null[r]) {
+            const Seg sg = segment_of(p.len[r], p.where, p.f1, p.f2);
+            a = sg.a;
+            b = sg.b;
+            o = p.off[r];
+        }
+        r_off[tx] = o;
+        r_a[tx] = a;
+        r_b[tx] = b;
+    }
+    __syncthreads();
+    for (int jj = ty; jj < 32; jj += 8) {
+        const int64_t k = k0 + tx;
+        const int q = r_a[jj] + (int)k;
+        int v = 0;
+        if (k < p.n_cols && q < r_b[jj]) v = __ldg(p.cov + r_off[jj] + q);
+        tile[jj][tx] = v;
+    }
+    __syncthreads();
+    for (int jj = ty; jj < 32; jj += 8) {
+        const int64_t k = k0 + jj, r = r0 + tx;
+        if (r < p.R && k < p.n_cols) p.out[k * p.ld + r] = p.scale * (double)tile[tx][jj];
+    }
+}
+
+}  // namespace
+
+// out points to DEVICE memory here; the api layer stages host outputs.
+int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins, int stat,
+                      int interp, int seed, int sample_kind, double* d_out, int64_t ld) {
+    const int64_t R = cv.n_regions;
+    if (R == 0) return RCP_OK;
+    // rank table of `set.seed(seed); sample(1:n, n)` (host, n is small)
+    std::vector<int> rank((size_t)n_bins), perm((size_t)n_bins), scratch((size_t)n_bins);
+    {
+        RRng* rng = new RRng;
+        rng->seed((uint32_t)seed, sample_kind);
+        rng->sample(n_bins, n_bins, scratch.data(), perm.data());
+        delete rng;
+        for (int pos = 0; pos < n_bins; pos++) rank[(size_t)perm[(size_t)pos] - 1] = pos + 1;
+    }
+    int* d_rank = nullptr;
+    int32_t* short_list = nullptr;
+    unsigned int* short_count = nullptr;
+    RCP_TRY(dalloc(&d_rank, (size_t)n_bins));
+    RCP_TRY(dalloc(&short_list, (size_t)R));
+    RCP_TRY(dalloc(&short_count, 1));
+    RCP_CUDA(cudaMemcpyAsync(d_rank, rank.data(), (size_t)n_bins * sizeof(int),
+                             cudaMemcpyHostToDevice, g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(short_count, 0, sizeof(unsigned int), g_ctx.stream));
+    // the pageable source of the rank copy must outlive the copy: cudaMemcpyAsync from pageable
+    // memory returns after the source has been staged, so `rank` may go out of scope later.
+    BinArgs a;
+    a.cov = cv.cov;
+    a.off = cv.off;
+    a.len = cv.len;
+    a.is_null = cv.is_null;
+    a.rank = d_rank;
+    a.where = where;
+    a.f1 = f1;
+    a.f2 = f2;
+    a.n = n_bins;
+    a.scale = cv.scale;
+    a.out = d_out;
+    a.ld = ld;
+    a.short_list = short_list;
+    a.short_count = short_count;
+    const size_t smem = ((size_t)n_bins + 1) * sizeof(int);
+    if (smem > 200 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than 51000 bins per segment");
+    {
+    StageTimer t(ST_PROF_BIN);
+    if (stat == RCP_STAT_MEDIAN) {
+        if (smem > 48 * 1024)
+            RCP_CUDA(cudaFuncSetAttribute(bin_matrix_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bin_matrix_kernel<true><<<(unsigned)R, CTA, smem, g_ctx.stream>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            RCP_CUDA(cudaFuncSetAttribute(bin_matrix_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bin_matrix_kernel<false><<<(unsigned)R, CTA, smem, g_ctx.stream>>>(a);
+    }
+    RCP_LAUNCHED();
+    }
+    InterpArgs ia;
+    ia.cov = cv.cov;
+    ia.off = cv.off;
+    ia.len = cv.len;
+    ia.where = where;
+    ia.f1 = f1;
+    ia.f2 = f2;
+    ia.n = n_bins;
+    ia.interp = interp;
+    ia.seed = seed;
+    ia.sample_kind = sample_kind;
+    ia.scale = cv.scale;
+    ia.out = d_out;
+    ia.ld = ld;
+    ia.short_list = short_list;
+    ia.short_count = short_count;
+    const size_t ismem = (size_t)n_bins * (4 * sizeof(double) + 2 * sizeof(int)) + 8 + sizeof(RRng);
+    if (ismem > 220 * 1024)
+        return fail(RCP_ERR_UNSUPPORTED, "interpolation supports at most ~5500 bins per segment");
+    if (ismem > 48 * 1024)
+        RCP_CUDA(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ismem));
+    int iblocks = g_ctx.sm_count * 8;
+    if ((int64_t)iblocks > R) iblocks = (int)R;
+    {
+        StageTimer t(ST_PROF_INTERP);
+        interp_kernel<<<(unsigned)iblocks, 32, ismem, g_ctx.stream>>>(ia);
+        RCP_LAUNCHED();
+    }
+    dfree(d_rank);
+    dfree(short_list);
+    dfree(short_count);
+    return RCP_OK;
+}
+
+int base_matrix_device(const Coverage& cv, int where, int f1, int f2, int64_t n_cols,
+                       double* d_out, int64_t ld) {
+    const int64_t R = cv.n_regions;
+    if (R == 0 || n_cols == 0) return RCP_OK;
+    BaseArgs a;
+    a.cov = cv.cov;
+    a.off = cv.off;
+    a.len = cv.len;
+    a.is_null = cv.is_null;
+    a.where = where;
+    a.f1 = f1;
+    a.f2 = f2;
+    a.R = R;
+    a.n_cols = n_cols;
+    a.scale = cv.scale;
+    a.out = d_out;
+    a.ld = ld;
+    StageTimer t(ST_PROF_BASE);
+    const int64_t gy = (R + 31) / 32, gx = (n_cols + 31) / 32;
+    if (gy > 65535) {
+        // grid.y is limited to 65535: walk the rows in slabs
+        for (int64_t y0 = 0; y0 < gy; y0 += 65535) {
+            BaseArgs s = a;
+            const int64_t rows0 = y0 * 32;
+            s.off = a.off + rows0;
+            s.len = a.len + rows0;
+            s.is_null = a.is_null + rows0;
+            s.R = (R - rows0) < 65535 * 32 ? (R - rows0) : 65535 * 32;
+            s.out = a.out + rows0;
+            const int64_t gys = (s.R + 31) / 32;
+            base_matrix_kernel<<<dim3((unsigned)gx, (unsigned)gys), dim3(32, 8), 0, g_ctx.stream>>>(s);
+            RCP_LAUNCHED();
+        }
+    } else {
+        base_matrix_kernel<<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, g_ctx.stream>>>(a);
+        RCP_LAUNCHED();
+    }
+    return RCP_OK;
+}
+
+}  // namespace rcp

@@ -1,0 +1,172 @@
+// Internal declarations shared by the translation units of librecoup_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "recoup_b200.h"
+
+namespace rcp {
+
+// ------------------------------------------------------------------ context / errors -------
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t mem_bytes = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;      // kernels launched by this library
+};
+extern Ctx g_ctx;
+
+int fail(int code, const char* fmt, ...);   // records the message, returns code
+int require_ready();                         // RCP_OK or RCP_ERR_NOGPU
+
+#define RCP_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::rcp::fail(RCP_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,        \
+                               __LINE__, cudaGetErrorString(_e));                              \
+    } while (0)
+
+#define RCP_TRY(expr)                                                                          \
+    do {                                                                                       \
+        int _rc = (expr);                                                                      \
+        if (_rc != RCP_OK) return _rc;                                                         \
+    } while (0)
+
+#define RCP_LAUNCHED()                                                                         \
+    do {                                                                                       \
+        ::rcp::g_ctx.launches++;                                                               \
+        RCP_CUDA(cudaGetLastError());                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------ stage timers -----------
+// Optional CUDA-event timing of the library's own stages on the library stream (used by
+// bench.py for the roofline object).  Off by default; when off a StageTimer does nothing.
+enum Stage {
+    ST_INDEX_MAP = 0,   // reads -> global coordinates (+ strand compaction)
+    ST_INDEX_SORT,      // radix sorts of the index
+    ST_COV_PLAN,        // region plan kernel + offset scans + tile list
+    ST_COV_TILE,        // cov_tile_kernel
+    ST_COV_SMALL,       // cov_small_kernel
+    ST_COV_LIST,        // list plan + cov_list_kernel
+    ST_COV_CONCAT,      // c(left, center, right)
+    ST_PROF_BIN,        // bin_matrix_kernel
+    ST_PROF_INTERP,     // interp_kernel
+    ST_PROF_BASE,       // base_matrix_kernel
+    ST_FUSED,           // fused coverage+profile kernel
+    ST_N
+};
+struct StageTimer {
+    int slot;
+    explicit StageTimer(int stage);
+    ~StageTimer();
+};
+
+// stream-ordered device allocation on the library stream
+template <class T>
+inline int dalloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMallocAsync((void**)p, n * sizeof(T), g_ctx.stream);
+    if (e != cudaSuccess)
+        return fail(RCP_ERR_CUDA, "device allocation of %zu bytes failed: %s", n * sizeof(T),
+                    cudaGetErrorString(e));
+    return RCP_OK;
+}
+template <class T>
+inline void dfree(T*& p) {
+    if (p) cudaFreeAsync((void*)p, g_ctx.stream);
+    p = nullptr;
+}
+
+// A caller array that must be readable on the device: either the caller's own device pointer or
+// a stream-ordered staging copy of host memory.
+template <class T>
+struct DevIn {
+    const T* ptr = nullptr;
+    T* owned = nullptr;
+    int init(const T* src, size_t n, int mem) {
+        if (mem == RCP_MEM_DEVICE || src == nullptr) {
+            ptr = src;
+            return RCP_OK;
+        }
+        RCP_TRY(dalloc(&owned, n));
+        RCP_CUDA(cudaMemcpyAsync(owned, src, n * sizeof(T), cudaMemcpyHostToDevice, g_ctx.stream));
+        ptr = owned;
+        return RCP_OK;
+    }
+    ~DevIn() { dfree(owned); }
+};
+
+// ------------------------------------------------------------------ reads index ------------
+// Strand classes of the sorted arrays.  ALL is used when no strand restriction applies.
+enum { CLS_ALL = 0, CLS_PLUS = 1, CLS_MINUS = 2, CLS_STAR = 3, CLS_N = 4 };
+
+struct SortedClass {
+    bool built = false;
+    int64_t n = 0;
+    uint32_t* xs = nullptr;   // sorted global start coordinates
+    uint32_t* ye = nullptr;   // sorted global (end + 1) coordinates, sorted independently
+};
+
+struct ReadsIdx {
+    int64_t n = 0;
+    int n_chrom = 0;
+    bool has_strand = false;
+    int key_bits = 32;
+    std::vector<int64_t> chrom_len;     // host copies
+    std::vector<uint32_t> chrom_off;    // n_chrom + 1, global coordinate of position 0
+    int64_t* d_chrom_len = nullptr;
+    uint32_t* d_chrom_off = nullptr;
+    // raw reads in global coordinates (kept for lazily built classes / pairs)
+    uint32_t* g_start = nullptr;
+    uint32_t* g_end1 = nullptr;         // end + 1
+    int8_t* d_strand = nullptr;         // nullptr when !has_strand
+    SortedClass cls[CLS_N];
+    // start-sorted pairs (lazy; RNA / GRangesList path)
+    bool pairs_built = false;
+    uint32_t* p_end1 = nullptr;         // (end+1) in start-sorted order
+    int8_t* p_strand = nullptr;         // strand in start-sorted order (nullptr when !has_strand)
+    uint32_t* p_maxend1 = nullptr;      // running max of p_end1
+    size_t device_bytes = 0;
+};
+
+int reads_build_class(ReadsIdx& r, int cls);   // lazily build a strand class
+int reads_build_pairs(ReadsIdx& r);            // lazily build the start-sorted pair arrays
+void reads_release(ReadsIdx& r);
+
+// ------------------------------------------------------------------ coverage ---------------
+struct Coverage {
+    int64_t n_regions = 0;
+    int64_t total_padded = 0;    // ints allocated in `cov`
+    int64_t total_len = 0;       // sum of len
+    int64_t n_null = 0;
+    double scale = 1.0;
+    int32_t* cov = nullptr;      // dense int32, region r at [off[r], off[r] + len[r])
+    int64_t* off = nullptr;      // n_regions + 1, multiples of 32 ints
+    int32_t* len = nullptr;      // n_regions, 0 for NULL
+    uint8_t* is_null = nullptr;  // n_regions
+};
+void coverage_release(Coverage& c);
+
+ReadsIdx* get_reads(int h);
+Coverage* get_coverage(int h);
+int new_coverage(Coverage** out, int* handle);
+
+// ------------------------------------------------------------------ primitives -------------
+// radix sort (sort.cu)
+int sort_keys_u32(uint32_t* keys_in_out, int64_t n, int end_bit);
+int sort_pairs_u32(uint32_t* keys_in_out, uint32_t* vals_in_out, int64_t n, int end_bit);
+// exclusive prefix sum of int64 (scan.cu); out may alias in; total (optional) receives the sum
+// on the DEVICE (d_total) -- nothing is synchronised.
+int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, int64_t* d_total);
+int exclusive_scan2_i64(const int64_t* in0, int64_t* out0, int64_t* d_total0, const int64_t* in1,
+                        int64_t* out1, int64_t* d_total1, int64_t n);
+
+}  // namespace rcp

@@ -1,0 +1,128 @@
+"""Host mirror of /root/reference/R/profile.R over librecoup_b200.so.
+
+    profileMatrix(input, flank, binParams, rc=NULL)                          profile.R:1-98
+    binCoverageMatrix(cvrg, binSize, stat, interpolation, flank, where, rc)  profile.R:153-212
+    baseCoverageMatrix(cvrg, flank, where, rc)                               profile.R:100-151
+
+The `$profile` of a sample is a double matrix [regions x bins] with rownames = region names
+(contract T2); here a Fortran-ordered numpy array (`ProfileMatrix`) carrying
+`rownames` / `colnames`.  `rc` is accepted and ignored.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .coverage import CoverageList, _message
+
+R_SEED = 42   # splitVector(..., seed=42), util.R:15
+
+
+class ProfileMatrix(np.ndarray):
+    def __new__(cls, array, rownames=None, colnames=None):
+        obj = np.asfortranarray(array).view(cls)
+        obj.rownames = rownames
+        obj.colnames = colnames
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.rownames = getattr(obj, "rownames", None)
+        self.colnames = getattr(obj, "colnames", None)
+
+
+def _out(n_rows, n_cols):
+    return np.zeros((n_rows, n_cols), dtype=np.float64, order="F")
+
+
+def _ld(mat):
+    return max(mat.shape[0], 1)
+
+
+def _sample_kind(kind):
+    return _lib.SAMPLE_KIND[kind]
+
+
+def binCoverageMatrix(cvrg, binSize=1000, stat="mean", interpolation="auto", flank=None,
+                      where="center", rc=None, seed=R_SEED, sample_kind="Rejection"):
+    """profile.R:153-212 (+ splitVector, util.R:15-85)."""
+    if isinstance(stat, (list, tuple)):
+        stat = stat[0]
+    if isinstance(interpolation, (list, tuple)):
+        interpolation = interpolation[0]
+    if not isinstance(cvrg, CoverageList):
+        raise TypeError("cvrg must be the CoverageList returned by calcCoverage")
+    f1, f2 = (0, 0) if flank is None else (int(flank[0]), int(flank[1]))
+    w = _lib.WHERE["whole"] if flank is None else _lib.WHERE[where]
+    out = _out(len(cvrg), int(binSize))
+    _lib.check(_lib.lib.rcp_bin_matrix(cvrg.handle, w, f1, f2, int(binSize), _lib.STAT[stat],
+                                       _lib.INTERP[interpolation], int(seed),
+                                       _sample_kind(sample_kind),
+                                       out.ctypes.data_as(C.c_void_p), _ld(out), _lib.MEM_HOST))
+    return ProfileMatrix(out, rownames=cvrg.names,
+                         colnames=[str(i + 1) for i in range(int(binSize))])
+
+
+def baseCoverageMatrix(cvrg, flank=None, where="upstream", rc=None):
+    """profile.R:100-151."""
+    if not isinstance(cvrg, CoverageList):
+        raise TypeError("cvrg must be the CoverageList returned by calcCoverage")
+    if flank is None:
+        lens = cvrg.lengths()
+        nz = lens[lens > 0]
+        size = int(nz[0]) if nz.size else 0                              # profile.R:103-111
+        f1 = f2 = 0
+        w = _lib.WHERE["whole"]
+    else:
+        f1, f2 = int(flank[0]), int(flank[1])
+        size = f1 if where == "upstream" else f2                          # profile.R:128,135
+        w = _lib.WHERE[where]
+    out = _out(len(cvrg), size)
+    if size > 0 and len(cvrg) > 0:
+        _lib.check(_lib.lib.rcp_base_matrix(cvrg.handle, w, f1, f2, size,
+                                            out.ctypes.data_as(C.c_void_p), _ld(out),
+                                            _lib.MEM_HOST))
+    return ProfileMatrix(out, rownames=cvrg.names)
+
+
+def haveEqualLengths(cvrg):
+    """profile.R:6-10: lengths of the first sample's coverages, zero-length (NULL) dropped."""
+    lens = cvrg.lengths()
+    lens = lens[lens != 0]
+    return bool(np.all(lens == lens[0])) if lens.size else True
+
+
+def _profile_one(cvrg, equal, flank, binParams, seed, sample_kind):
+    f1, f2 = int(flank[0]), int(flank[1])
+    fbs = int(binParams.get("flankBinSize", 0))
+    rbs = int(binParams.get("regionBinSize", 0))
+    stat = binParams.get("sumStat", "mean")
+    interp = binParams.get("interpolation", "auto")
+    if isinstance(stat, (list, tuple)):
+        stat = stat[0]
+    if isinstance(interp, (list, tuple)):
+        interp = interp[0]
+    ncols = C.c_int64(0)
+    _lib.check(_lib.lib.rcp_profile_ncols(cvrg.handle, int(equal), f1, f2, fbs, rbs, C.byref(ncols)))
+    out = _out(len(cvrg), ncols.value)
+    if out.size:
+        _lib.check(_lib.lib.rcp_profile_matrix(cvrg.handle, int(equal), f1, f2, fbs, rbs,
+                                               _lib.STAT[stat], _lib.INTERP[interp], int(seed),
+                                               _sample_kind(sample_kind),
+                                               out.ctypes.data_as(C.c_void_p), _ld(out),
+                                               _lib.MEM_HOST))
+    return ProfileMatrix(out, rownames=cvrg.names)
+
+
+def profileMatrix(input, flank, binParams, rc=None, seed=R_SEED, sample_kind="Rejection"):
+    """profile.R:1-98.  Fills `profile` of every sample dict; returns `input` unchanged when all
+    samples already have one (profile.R:2-4).  The equal-length decision is taken on the FIRST
+    sample only, as in the reference (profile.R:6)."""
+    if all(x.get("profile") is not None for x in input):
+        return input
+    equal = haveEqualLengths(input[0]["coverage"])
+    for x in input:
+        _message("Calculating profile for ", x.get("name"))
+        x["profile"] = _profile_one(x["coverage"], equal, flank, binParams, seed, sample_kind)
+    return input

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def fixture_data():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "recoup_test_data.npz"))
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """Binds the CUDA library to cuda:0; fails (never skips) when the GPU path is unusable."""
+    import recoup_b200 as rb
+    rb.init(0)
+    return rb

@@ -1,0 +1,407 @@
+"""Parity tests proper: the CUDA library, called through the C ABI (via the host mirror), against
+the oracle on the same seeded inputs.  Coverage must be BIT-EXACT; profile matrices within
+1e-6 relative (north_star).  Run with `-m gpu` on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import recoup_oracle as O
+from tests.helpers import (assert_coverage_equal, assert_matrix_close, both_reads, both_regions,
+                           fixture_exons, fixture_genes, fixture_reads, synth_reads)
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: the reference's bundled fixture
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [0, 1])
+def test_c1_fixture_tss_100_bins(gpu, fixture_data, k):
+    rb = gpu
+    o_reads, g_reads = fixture_reads(fixture_data, k)
+    o_genes, g_genes = fixture_genes(fixture_data)
+    want_cov = O.coverage_ref(o_reads, o_genes, "tss", (2000, 2000))
+    inp = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRef(inp, g_genes, "tss", (2000, 2000))
+    cov = inp[0]["coverage"]
+    assert cov.names == list(fixture_data["gene_names"])
+    assert cov.n_null == (6 if k == 0 else 4)
+    assert_coverage_equal(cov.to_list(), want_cov)
+    bp = dict(flankBinSize=0, regionBinSize=100, sumStat="mean", interpolation="auto")
+    rb.profileMatrix(inp, (2000, 2000), bp)
+    m = inp[0]["profile"]
+    assert m.shape == (100, 100) and m.flags.f_contiguous and m.rownames == cov.names
+    assert_matrix_close(m, O.profile_matrix(want_cov, (2000, 2000), bp))
+
+
+@pytest.mark.parametrize("region,flank,bp", [
+    ("tes", (1000, 3000), dict(flankBinSize=0, regionBinSize=0)),
+    ("tss", (500, 1500), dict(flankBinSize=0, regionBinSize=64, sumStat="median")),
+    ("genebody", (2000, 2000), dict(flankBinSize=50, regionBinSize=150, sumStat="mean",
+                                    interpolation="auto")),
+    ("genebody", (2000, 1000), dict(flankBinSize=0, regionBinSize=60, sumStat="median",
+                                    interpolation="spline")),
+    ("genebody", (0, 1000), dict(flankBinSize=30, regionBinSize=200, sumStat="mean",
+                                 interpolation="auto")),
+])
+def test_fixture_regions_and_profiles(gpu, fixture_data, region, flank, bp):
+    rb = gpu
+    o_reads, g_reads = fixture_reads(fixture_data, 0)
+    o_genes, g_genes = fixture_genes(fixture_data)
+    want_cov = O.coverage_ref(o_reads, o_genes, region, flank)
+    inp = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRef(inp, g_genes, region, flank)
+    assert_coverage_equal(inp[0]["coverage"].to_list(), want_cov)
+    rb.profileMatrix(inp, flank, bp)
+    assert_matrix_close(inp[0]["profile"], O.profile_matrix(want_cov, flank, bp))
+
+
+def test_fixture_rna(gpu, fixture_data):
+    rb = gpu
+    o_reads, g_reads = fixture_reads(fixture_data, 0)
+    o_genes, g_genes = fixture_genes(fixture_data)
+    o_ex, g_ex = fixture_exons(fixture_data)
+    want = O.coverage_rna_ref(o_reads, o_ex, o_genes, (2000, 2000))
+    inp = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRnaRef(inp, g_ex, g_genes, (2000, 2000))
+    cov = inp[0]["coverage"]
+    assert cov.names == list(fixture_data["exon_gene_names"])
+    assert_coverage_equal(cov.to_list(), want)
+    bp = dict(flankBinSize=50, regionBinSize=150, sumStat="mean", interpolation="auto")
+    rb.profileMatrix(inp, (2000, 2000), bp)
+    assert_matrix_close(inp[0]["profile"], O.profile_matrix(want, (2000, 2000), bp))
+    # the centre part alone is calcCoverage over the GRangesList
+    center = rb.calcCoverage(g_reads, g_ex)
+    assert_coverage_equal(center.to_list(), O.calc_coverage(o_reads, o_ex))
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic: every NULL / strand / size rule
+# ------------------------------------------------------------------------------------------------
+def _regions(rng, n, clen, lengths):
+    clen = np.asarray(clen)
+    chrom = rng.integers(0, clen.shape[0], size=n)
+    L = rng.choice(np.asarray(lengths), size=n)
+    start = (rng.random(n) * (clen[chrom] + 300)).astype(np.int64) - 150
+    strand = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=n)
+    return chrom, start, start + L - 1, strand
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+@pytest.mark.parametrize("ignore,filt", [(True, None), (False, None), (True, "+"), (False, "-"),
+                                         (True, "*")])
+def test_random_regions_all_strand_modes(gpu, seed, ignore, filt):
+    rb = gpu
+    rng = np.random.default_rng(seed)
+    clen = [30000, 70000, 900, 15000]
+    chrom, s, e, st = synth_reads(rng, 20000, clen, width=(1, 400))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    # lengths straddling the warp kernel (<= 1024), one tile and many tiles
+    rc, rs, re_, rst = _regions(rng, 300, clen, [1, 2, 31, 32, 33, 127, 128, 129, 1000, 1023,
+                                                 1024, 1025, 4095, 4096, 4097, 8192, 9000, 20011])
+    rs[:4] = [0, -1, 1, 2]
+    re_[:4] = rs[:4] + [500, 500, 2000, 5000]
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    filt_code = None if filt is None else {"+": 1, "-": -1, "*": 0}[filt]
+    want = O.calc_coverage(o_reads, o_mask, filt_code, ignore)
+    got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+    assert_coverage_equal(got.to_list(), want)
+    lens = got.lengths()
+    assert [int(l) for l in lens] == [0 if w is None else len(w) for w in want]
+    assert any(w is None for w in want) and sum(w is not None for w in want) > 50
+
+
+def test_pileups_long_reads_and_no_strand(gpu):
+    rb = gpu
+    rng = np.random.default_rng(21)
+    clen = [200000]
+    # 5000 duplicates at one position (warp-aggregated atomics), very long reads (rank method is
+    # width independent), plus background
+    chrom, s, e, st = synth_reads(rng, 30000, clen, width=(30, 60))
+    s[:5000] = 77777
+    e[:5000] = 77777 + 49
+    s[5000:5050] = rng.integers(1, 50000, size=50)
+    e[5000:5050] = s[5000:5050] + rng.integers(60000, 120000, size=50)
+    o_reads = O.Reads(chrom, s, e, np.zeros_like(st), clen)
+    g_reads = rb.GRanges(chrom, s, e, seqlevels=["c0"], seqlengths=clen)          # no strand given
+    rc, rs, re_, rst = _regions(rng, 200, clen, [200, 1000, 5000, 30000])
+    rs[0], re_[0] = 77000, 79999
+    rs[1], re_[1] = 1, 200000
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 1)
+    want = O.calc_coverage(o_reads, o_mask)
+    got = rb.calcCoverage(g_reads, g_mask)
+    assert_coverage_equal(got.to_list(), want)
+    assert want[0].max() >= 5000
+    # ignore.strand=FALSE with strandless reads: '*' reads match every region
+    got2 = rb.calcCoverage(g_reads, g_mask, ignore_strand=False)
+    assert_coverage_equal(got2.to_list(), want)
+
+
+def test_empty_inputs(gpu):
+    rb = gpu
+    clen = [1000]
+    none = rb.GRanges(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                      seqlevels=["c0"], seqlengths=clen)
+    _, g_mask = both_regions([0, 0], [1, 10], [100, 20], [1, -1], 1)
+    cov = rb.calcCoverage(none, g_mask)
+    assert cov.to_list() == [None, None] and cov.n_null == 2                  # no reads: all NULL
+    m = rb.binCoverageMatrix(cov, binSize=5)
+    assert m.shape == (2, 5) and (np.asarray(m) == 0).all()
+    some = rb.GRanges(np.zeros(2, np.int32), [5, 50], [30, 80], seqlevels=["c0"], seqlengths=clen)
+    empty_mask = rb.GRanges(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                            seqlevels=["c0"])
+    cov0 = rb.calcCoverage(some, empty_mask)
+    assert len(cov0) == 0 and cov0.to_list() == []
+    # a region on a chromosome the reads do not know -> NULL (coverage.R:194-197)
+    other = rb.GRanges(["cX", "c0"], [5, 5], [30, 30], strand=["+", "+"], seqlevels=["cX", "c0"])
+    cov1 = rb.calcCoverage(some, other)
+    got = cov1.to_list()
+    assert got[0] is None and got[1].tolist() == [1] * 26
+
+
+def test_fragment_extension(gpu):
+    rb = gpu
+    rng = np.random.default_rng(31)
+    clen = [40000, 9000]
+    chrom, s, e, st = synth_reads(rng, 8000, clen, width=(36, 36))
+    s[:10] = 1
+    e[:10] = 36
+    es, ee = O.extend_fragments(s, e, st, 200, chrom, clen)
+    o_reads = O.Reads(chrom, es, ee, st, clen)
+    g_reads = rb.GRanges(chrom, s, e, strand=st, seqlevels=["c0", "c1"], seqlengths=clen)
+    rc, rs, re_, rst = _regions(rng, 60, clen, [500, 3000])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 2)
+    want = O.calc_coverage(o_reads, o_mask)
+    got = rb.calcCoverage(g_reads, g_mask, frag_len=200)
+    assert_coverage_equal(got.to_list(), want)
+
+
+@pytest.mark.parametrize("ignore", [True, False])
+def test_granges_list_multiplicity(gpu, ignore):
+    rb = gpu
+    rng = np.random.default_rng(41)
+    clen = [60000, 25000]
+    chrom, s, e, st = synth_reads(rng, 15000, clen, width=(20, 1500))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    ptr, xc, xs, xe, xst = [0], [], [], [], []
+    for g in range(80):
+        c = int(rng.integers(0, 2))
+        ne = int(rng.integers(1, 12))
+        pos = int(rng.integers(1, clen[c] - 12000))
+        gst = int(rng.choice([1, -1, 0]))
+        ex = []
+        for _ in range(ne):
+            w = int(rng.integers(1, 700))
+            ex.append((pos, pos + w - 1))
+            pos += w + int(rng.integers(1, 400))
+        if g % 7 == 0:
+            ex = ex[::-1]                       # list order is respected, not genomic order
+        if g % 11 == 0 and ne > 1:
+            ex[1] = (ex[0][0] + 3, ex[0][1] + 9)    # overlapping ranges
+        for a, b in ex:
+            xc.append(c); xs.append(a); xe.append(b); xst.append(gst)
+        ptr.append(len(xs))
+    ptr.append(len(xs))                         # empty element -> NULL
+    # one giant element (> 4096 stitched bases -> several tiles)
+    for q in range(30):
+        xc.append(0); xs.append(2000 + q * 900); xe.append(2000 + q * 900 + 499); xst.append(-1)
+    ptr.append(len(xs))
+    o_mask = dict(ptr=ptr, chrom=xc, start=xs, end=xe, strand=xst)
+    u = rb.GRanges(np.asarray(xc, np.int32), xs, xe, strand=np.asarray(xst, np.int8),
+                   seqlevels=["c0", "c1"])
+    g_mask = rb.GRangesList(u, ptr)
+    want = O.calc_coverage(o_reads, o_mask, None, ignore)
+    got = rb.calcCoverage(g_reads, g_mask, ignore_strand=ignore)
+    assert_coverage_equal(got.to_list(), want)
+    assert want[-2] is None and want[-1] is not None and len(want[-1]) == 15000
+
+
+# ------------------------------------------------------------------------------------------------
+# profile matrix
+# ------------------------------------------------------------------------------------------------
+def _gene_like_coverage(rb, rng, n_regions=120, flank=(300, 200)):
+    clen = [400000]
+    chrom, s, e, st = synth_reads(rng, 60000, clen, width=(50, 150))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    w = rng.choice([1, 3, 9, 40, 55, 70, 100, 500, 3000, 9000], size=n_regions)
+    gs = rng.integers(1000, 380000, size=n_regions)
+    gst = rng.choice(np.array([1, -1], dtype=np.int8), size=n_regions)
+    s2, e2 = O.get_regional_ranges(gs, gs + w - 1, gst, "genebody", flank)
+    o_mask, g_mask = both_regions(np.zeros(n_regions, int), s2, e2, gst, 1)
+    want = O.calc_coverage(o_reads, o_mask)
+    got = rb.calcCoverage(g_reads, g_mask)
+    return want, got
+
+
+@pytest.mark.parametrize("bp", [
+    dict(flankBinSize=20, regionBinSize=60, sumStat="mean", interpolation="auto"),
+    dict(flankBinSize=20, regionBinSize=60, sumStat="median", interpolation="auto"),
+    dict(flankBinSize=0, regionBinSize=45, sumStat="mean", interpolation="spline"),
+    dict(flankBinSize=7, regionBinSize=50, sumStat="median", interpolation="spline"),
+    dict(flankBinSize=33, regionBinSize=257, sumStat="mean", interpolation="auto"),
+])
+def test_unequal_length_profiles(gpu, bp):
+    rb = gpu
+    rng = np.random.default_rng(51)
+    flank = (300, 200)
+    want_cov, got_cov = _gene_like_coverage(rb, rng, flank=flank)
+    assert_coverage_equal(got_cov.to_list(), want_cov)
+    want = O.profile_matrix(want_cov, flank, bp)
+    inp = [dict(id="s", name="s", coverage=got_cov)]
+    rb.profileMatrix(inp, flank, bp)
+    assert_matrix_close(inp[0]["profile"], want)
+
+
+@pytest.mark.parametrize("interp", ["auto", "spline", "neighborhood"])
+@pytest.mark.parametrize("stat", ["mean", "median"])
+def test_interpolation_kernels(gpu, interp, stat):
+    """Segments shorter than the bin count (util.R:17-73): spline, neighbourhood and the 'auto'
+    switch at (n - L) / n < 0.2."""
+    rb = gpu
+    rng = np.random.default_rng(61)
+    clen = [50000]
+    chrom, s, e, st = synth_reads(rng, 30000, clen, width=(20, 90))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    n_bins = 40
+    lengths = np.array([4, 5, 7, 12, 20, 31, 32, 33, 35, 38, 39, 40, 41, 80, 200])
+    if interp != "neighborhood":
+        lengths = np.concatenate([[1, 2, 3], lengths])
+    starts = rng.integers(100, 45000, size=lengths.shape[0])
+    strand = rng.choice(np.array([1, -1], dtype=np.int8), size=lengths.shape[0])
+    o_mask, g_mask = both_regions(np.zeros(len(lengths), int), starts, starts + lengths - 1, strand, 1)
+    want_cov = O.calc_coverage(o_reads, o_mask)
+    got_cov = rb.calcCoverage(g_reads, g_mask)
+    assert_coverage_equal(got_cov.to_list(), want_cov)
+    want = O.bin_coverage_matrix(want_cov, n_bins, stat, interp)
+    got = rb.binCoverageMatrix(got_cov, binSize=n_bins, stat=stat, interpolation=interp)
+    assert_matrix_close(got, want)
+    assert got.colnames == [str(i + 1) for i in range(n_bins)]
+
+
+def test_rounding_sample_kind_and_scale(gpu):
+    rb = gpu
+    rng = np.random.default_rng(71)
+    want_cov, got_cov = _gene_like_coverage(rb, rng, n_regions=40)
+    bp = dict(flankBinSize=20, regionBinSize=60, sumStat="mean", interpolation="auto")
+    want = O.profile_matrix(want_cov, (300, 200), bp, sample_kind="Rounding")
+    inp = [dict(id="s", name="s", coverage=got_cov)]
+    rb.profileMatrix(inp, (300, 200), bp, sample_kind="Rounding")
+    assert_matrix_close(inp[0]["profile"], want)
+    # linear normalisation (recoup.R:559-577): coverage * factor before binning
+    got_cov.set_scale(0.37)
+    inp = [dict(id="s", name="s", coverage=got_cov)]
+    rb.profileMatrix(inp, (300, 200), bp)
+    want_scaled = O.profile_matrix([None if c is None else c * 0.37 for c in want_cov],
+                                   (300, 200), bp)
+    assert_matrix_close(inp[0]["profile"], want_scaled)
+
+
+def test_per_base_matrix_and_linear_interp_error(gpu):
+    rb = gpu
+    rng = np.random.default_rng(81)
+    clen = [90000]
+    chrom, s, e, st = synth_reads(rng, 20000, clen, width=(30, 70))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    sites = rng.integers(600, 89000, size=333)
+    sst = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=333)
+    s2, e2 = O.get_regional_ranges(sites, sites, sst, "custom", (500, 500))
+    o_mask, g_mask = both_regions(np.zeros(333, int), s2, e2, sst, 1)
+    want_cov = O.calc_coverage(o_reads, o_mask)
+    got_cov = rb.calcCoverage(g_reads, g_mask)
+    assert_coverage_equal(got_cov.to_list(), want_cov)
+    bp = dict(flankBinSize=0, regionBinSize=0)
+    inp = [dict(id="s", name="s", coverage=got_cov)]
+    rb.profileMatrix(inp, (500, 500), bp)
+    want = O.profile_matrix(want_cov, (500, 500), bp)
+    assert inp[0]["profile"].shape == (333, 1000)
+    assert np.array_equal(np.asarray(inp[0]["profile"]), want)          # integers: exact
+    up = rb.baseCoverageMatrix(got_cov, flank=(37, 90), where="upstream")
+    dn = rb.baseCoverageMatrix(got_cov, flank=(37, 90), where="downstream")
+    assert np.array_equal(np.asarray(up), O.base_coverage_matrix(want_cov, (37, 90), "upstream"))
+    assert np.array_equal(np.asarray(dn), O.base_coverage_matrix(want_cov, (37, 90), "downstream"))
+    with pytest.raises(rb.RecoupError) as ei:
+        rb.binCoverageMatrix(got_cov, binSize=10, interpolation="linear")
+    assert ei.value.code == 5 and "inear" in str(ei.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at a larger size + the C twin as a mid-size checker
+# ------------------------------------------------------------------------------------------------
+def test_midsize_against_c_oracle_and_properties(gpu):
+    rb = gpu
+    rng = np.random.default_rng(91)
+    clen = [3_000_000, 1_500_000, 700_000]
+    n = 1_500_000
+    chrom, s, e, st = synth_reads(rng, n, clen, width=(200, 200))
+    g_reads = rb.GRanges(chrom, s, e, strand=st, seqlevels=["a", "b", "c"], seqlengths=clen)
+    R = 3000
+    tss = rng.integers(6000, 600_000, size=R)
+    rc = rng.integers(0, 3, size=R)
+    rst = rng.choice(np.array([1, -1], dtype=np.int8), size=R)
+    s2, e2 = O.get_regional_ranges(tss, tss, rst, "tss", (5000, 5000))
+    _, g_mask = both_regions(rc, s2, e2, rst, 3)
+    cov = rb.calcCoverage(g_reads, g_mask)
+    ix = CO.Index(chrom, s, e, st, clen)
+    dense = CO.coverage(ix, rc, s2, e2, rst)
+    assert_coverage_equal(cov.to_list(), dense.to_list())
+    bp = dict(flankBinSize=0, regionBinSize=200)
+    inp = [dict(id="s", name="s", coverage=cov)]
+    rb.profileMatrix(inp, (5000, 5000), bp)
+    m = np.asarray(inp[0]["profile"])
+    assert_matrix_close(m, CO.profile_matrix(dense, (5000, 5000), bp, True))
+    # property: a row's mean * 10000 == bases of reads inside the window (checksum of checksums)
+    got_rows = m.mean(axis=1) * 10000
+    lens = dense.len
+    for r in rng.integers(0, R, size=50):
+        if lens[r] == 0:
+            continue
+        on = chrom == rc[r]
+        ov = np.minimum(e[on], e2[r]) - np.maximum(s[on], s2[r]) + 1
+        assert abs(got_rows[r] - ov[ov > 0].sum()) < 1e-6 * max(1.0, got_rows[r])
+    # linearity: coverage(A u B) == coverage(A) + coverage(B) wherever all three are non-NULL
+    half = n // 2
+    ga = rb.GRanges(chrom[:half], s[:half], e[:half], strand=st[:half], seqlevels=["a", "b", "c"],
+                    seqlengths=clen)
+    gb = rb.GRanges(chrom[half:], s[half:], e[half:], strand=st[half:], seqlevels=["a", "b", "c"],
+                    seqlengths=clen)
+    sub = rb.GRanges(rc[:200].astype(np.int32), s2[:200], e2[:200], strand=rst[:200],
+                     seqlevels=["a", "b", "c"])
+    ca = rb.calcCoverage(ga, sub).to_list()
+    cb = rb.calcCoverage(gb, sub).to_list()
+    call = cov.fetch(0, 200)
+    for x, y, zed in zip(ca, cb, call):
+        if zed is None:
+            assert x is None and y is None
+        else:
+            xx = np.zeros_like(zed) if x is None else x
+            yy = np.zeros_like(zed) if y is None else y
+            assert np.array_equal(xx + yy, zed)
+    # strand symmetry: flipping the region strand reverses the vector
+    flipped = rb.GRanges(rc[:200].astype(np.int32), s2[:200], e2[:200], strand=-rst[:200],
+                         seqlevels=["a", "b", "c"])
+    cf = rb.calcCoverage(g_reads, flipped).to_list()
+    for x, y in zip(cf, call):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert np.array_equal(x[::-1], y)
+
+
+def test_handles_and_errors(gpu):
+    rb = gpu
+    from recoup_b200 import _lib
+    assert _lib.lib.rcp_coverage_free(987654) == _lib.RCP_ERR_HANDLE
+    assert _lib.lib.rcp_reads_free(987654) == _lib.RCP_ERR_HANDLE
+    bad = rb.GRanges(np.zeros(2, np.int32), [5, 0], [30, 9], seqlevels=["c0"], seqlengths=[100])
+    mask = rb.GRanges(np.zeros(1, np.int32), [1], [10], seqlevels=["c0"])
+    with pytest.raises(rb.RecoupError) as ei:
+        rb.calcCoverage(bad, mask)                      # a read with start < 1
+    assert ei.value.code == _lib.RCP_ERR_DATA
+    sm = C.c_int(0)
+    assert _lib.lib.rcp_device_info(None, C.byref(sm), None, None, None) == 0 and sm.value >= 100
+    before = _lib.lib.rcp_launch_count(1)
+    ok = rb.GRanges(np.zeros(2, np.int32), [5, 20], [30, 90], seqlevels=["c0"], seqlengths=[100])
+    cov = rb.calcCoverage(ok, mask)
+    assert cov[0].tolist() == [0, 0, 0, 0, 1, 1, 1, 1, 1, 1]
+    assert _lib.lib.rcp_launch_count(0) > 0 and before >= 0

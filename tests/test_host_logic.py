@@ -1,0 +1,83 @@
+"""Host-side mirror logic (no GPU): geometry against the oracle, argument errors of the
+reference's closures."""
+import numpy as np
+import pytest
+
+import recoup_b200 as rb
+from oracle import recoup_oracle as O
+
+
+def _random_ranges(rng, n):
+    start = rng.integers(50_000, 1_000_000, size=n)
+    width = rng.integers(1, 5000, size=n)
+    strand = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=n)
+    return start, start + width - 1, strand
+
+
+@pytest.mark.parametrize("region", ["tss", "tes", "genebody", "custom"])
+@pytest.mark.parametrize("flank", [(2000, 2000), (0, 500), (1000, 0), (0, 0), (5000, 300)])
+def test_regional_ranges_match_oracle(region, flank):
+    rng = np.random.default_rng(5)
+    s, e, st = _random_ranges(rng, 200)
+    gr = rb.GRanges(np.zeros(200, np.int32), s, e, strand=st, seqlevels=["c0"])
+    got = rb.getRegionalRanges(gr, region, flank)
+    ws, we = O.get_regional_ranges(s, e, st, region, flank)
+    assert np.array_equal(got.start, ws) and np.array_equal(got.end, we)
+    if region in ("tss", "tes"):
+        assert np.all(got.width == flank[0] + flank[1])      # promoters(): upstream+downstream
+    if region == "genebody":
+        assert np.all(got.width == (e - s + 1) + flank[0] + flank[1])
+
+
+def test_custom_one_bp_ranges_behave_like_tss():
+    s = np.array([1000, 2000, 3000])
+    st = np.array([1, -1, 0], dtype=np.int8)
+    gr = rb.GRanges(np.zeros(3, np.int32), s, s, strand=st, seqlevels=["c0"])
+    a = rb.getRegionalRanges(gr, "custom", (500, 500))
+    b = rb.getRegionalRanges(gr, "tss", (500, 500))
+    assert np.array_equal(a.start, b.start) and np.array_equal(a.end, b.end)
+    # documented promoters() formulas: '+' [s-f1, s+f2-1], '-' [e-f2+1, e+f1]
+    assert (a.start[0], a.end[0]) == (500, 1499)
+    assert (a.start[1], a.end[1]) == (1501, 2500)
+
+
+@pytest.mark.parametrize("direction", ["upstream", "downstream"])
+def test_flanking_ranges_match_oracle(direction):
+    rng = np.random.default_rng(6)
+    s, e, st = _random_ranges(rng, 100)
+    gr = rb.GRanges(np.zeros(100, np.int32), s, e, strand=st, seqlevels=["c0"])
+    got = rb.getFlankingRanges(gr, 1000, direction)
+    ws, we = O.get_flanking_ranges(s, e, st, 1000, direction)
+    assert np.array_equal(got.start, ws) and np.array_equal(got.end, we)
+    assert np.all(got.width == 1000)
+
+
+def test_calccoverage_argument_errors_follow_the_reference():
+    gr = rb.GRanges(np.zeros(1, np.int32), [1], [10], seqlevels=["c0"], seqlengths=[100])
+    with pytest.raises(ValueError, match="mask argument must be a GRanges or GRangesList"):
+        rb.calcCoverage(gr, mask=[1, 2, 3])                                  # coverage.R:131-132
+    with pytest.raises(ValueError, match="input argument must be a GenomicRanges"):
+        rb.calcCoverage(12345, mask=gr)                                      # coverage.R:127-130
+    with pytest.raises(NotImplementedError):
+        rb.calcCoverage("sample.bam", mask=gr)
+
+
+def test_coverage_ref_early_return_when_all_samples_have_coverage():
+    sentinel = object()
+    inp = [dict(id="a", coverage=sentinel), dict(id="b", coverage=sentinel)]
+    assert rb.coverageRef(inp, None, "tss") is inp                           # coverage.R:4-6
+    assert rb.coverageRnaRef(inp, None, None, (10, 10)) is inp               # coverage.R:81-83
+    inp2 = [dict(id="a", profile=sentinel)]
+    assert rb.profileMatrix(inp2, (1, 1), {}) is inp2                        # profile.R:2-4
+
+
+def test_granges_container():
+    gr = rb.GRanges(["chrB", "chrA", "chrB"], [5, 1, 9], width=[3, 3, 3], strand=["+", "-", "*"])
+    assert gr.seqlevels == ["chrB", "chrA"]
+    assert gr.seqnames.tolist() == [0, 1, 0]
+    assert gr.end.tolist() == [7, 3, 11]
+    assert gr.strand.tolist() == [1, -1, 0]
+    sub = gr.subset(np.array([True, False, True]))
+    assert len(sub) == 2 and sub.start.tolist() == [5, 9]
+    with pytest.raises(ValueError):
+        rb.GRangesList(gr, [0, 2])
