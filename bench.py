@@ -59,6 +59,8 @@ def peaks():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up until
+    after the e2e loop; rows are stamped on arrival so the timed window can be cut out."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,18 +74,21 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,23 +96,33 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            f = [x.strip() for x in row.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for _t, row in rows:
+                f = [x.strip() for x in row.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+
+        inside = [r for r in self.rows if t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = self.rows          # timed region shorter than the sampling period
+            window = "warm-up + timed + e2e loops (timed region < 3 samples long)"
+        sm, mx, reasons = digest(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,26 +344,28 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ----
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         device_step()
         gather_step()
     barrier()
 
     # ---- timed: device-resident ----
-    sampler = ClockSampler(local)
-    sampler.start()
     L.rcp_launch_count(1)
     _lib.check(L.rcp_timing_enable(1))
     _lib.check(L.rcp_timing_read(1, 0, None, None))
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         device_step()
         gather_step()
     ev1.record(stream)
     barrier()
+    t_end = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = int(L.rcp_launch_count(0))
     n_st = 0
@@ -360,7 +377,6 @@ def run_b200(args):
     _lib.check(L.rcp_timing_enable(0))
     stage = {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
              for i in range(n_st) if cnt[i] > 0}
-    clocks = sampler.stop()
 
     # ---- timed: end to end through the public host API (pinned host buffers) ----
     def pinned(a):
@@ -408,6 +424,7 @@ def run_b200(args):
         mat = e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop(t_begin, t_end)
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)

@@ -341,7 +341,7 @@ def test_midsize_against_c_oracle_and_properties(gpu):
     rc = rng.integers(0, 3, size=R)
     rst = rng.choice(np.array([1, -1], dtype=np.int8), size=R)
     s2, e2 = O.get_regional_ranges(tss, tss, rst, "tss", (5000, 5000))
-    _, g_mask = both_regions(rc, s2, e2, rst, 3)
+    g_mask = rb.GRanges(rc.astype(np.int32), s2, e2, strand=rst, seqlevels=["a", "b", "c"])
     cov = rb.calcCoverage(g_reads, g_mask)
     ix = CO.Index(chrom, s, e, st, clen)
     dense = CO.coverage(ix, rc, s2, e2, rst)
