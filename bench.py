@@ -398,10 +398,17 @@ def run_b200(args):
     d2h = 8 * R * ncols + 4 * R
     e2e_steps = max(2, min(args.steps, 5))
 
+    phases = {"upload+index": 0.0, "coverage": 0.0, "profile+download": 0.0}
+
     def e2e_step():
+        """The calls a user of the reference API makes, on pinned HOST arrays."""
+        t_a = time.perf_counter()
         reads = rb.GRanges(host_views[0], host_views[1], host_views[2], strand=host_views[3],
                            seqlevels=w["chrom_names"], seqlengths=clen)
         sample = [dict(id="s", name="s", ranges=reads)]
+        rb.device_reads(reads, w["frag_len"])
+        L.rcp_sync()
+        t_b = time.perf_counter()
         if is_rna:
             rb.coverageRnaRef(sample, grl, genes, w["flank"])
         else:
@@ -409,15 +416,23 @@ def run_b200(args):
                 sample[0]["coverage"] = rb.calcCoverage(reads, win, frag_len=w["frag_len"])
             else:
                 rb.coverageRef(sample, genes, w["region"], w["flank"])
+        L.rcp_sync()
+        t_c = time.perf_counter()
         rb.profileMatrix(sample, w["flank"], bp)
         m = sample[0]["profile"]
+        t_d = time.perf_counter()
         sample[0]["coverage"].free()
         for dr in reads._device.values():
             dr.free()
         reads._device.clear()
+        phases["upload+index"] += t_b - t_a
+        phases["coverage"] += t_c - t_b
+        phases["profile+download"] += t_d - t_c
         return m
 
     e2e_step()
+    for k in phases:
+        phases[k] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -425,6 +440,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop(t_begin, t_end)
+    assert mat.shape == (R, ncols)
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -472,7 +488,8 @@ def run_b200(args):
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "phases_ms": {k: 1e3 * v / e2e_steps for k, v in phases.items()}},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -23,17 +23,19 @@ namespace {
 
 constexpr int CTA = 256;
 constexpr int WARPS = CTA / 32;
-constexpr int TILE = 4096;             // positions per CTA tile (16 KB of int32)
-constexpr int SEG = TILE / WARPS;      // 512 positions scanned by one warp
+constexpr int TILE = 7168;             // positions per CTA tile (28 KB of int32; 8 CTAs per SM)
 constexpr int ROW = 128;               // positions handled by one warp-wide int4 access
+constexpr int MAX_ROWS = TILE / ROW;   // 56
 constexpr int SMALL_MAX = 1024;        // regions up to this length use the warp kernel
 constexpr int PAD = 32;                // region offsets are multiples of 32 ints (128 B)
 
+// ye[i] is read as ye[i] + yshift: in uniform-width mode ye aliases xs and yshift is the width.
 template <int NS>
 struct Sources {
     const uint32_t* xs[NS];
     const uint32_t* ye[NS];
     uint32_t n[NS];
+    uint32_t yshift[NS];
 };
 
 struct RegionArrays {
@@ -50,13 +52,36 @@ struct RegionArrays {
     int64_t* ntiles;     // tiles of the CTA kernel (scan input)
 };
 
-// first index in [lo, hi) with a[idx] >= key
+// first index in [lo, hi) with a[idx] + shift >= key
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo,
-                                                    uint32_t hi, uint32_t key) {
+                                                    uint32_t hi, uint32_t key, uint32_t shift = 0) {
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(a + mid) < key) lo = mid + 1;
+        if (__ldg(a + mid) + shift < key) lo = mid + 1;
         else hi = mid;
+    }
+    return lo;
+}
+
+// The same search done by a whole warp, 32 probes per step (all lanes pass the same arguments
+// and receive the same answer): a slice of a few thousand reads resolves in 2-3 dependent loads
+// instead of ~12.
+__device__ __forceinline__ uint32_t warp_lower_bound_u32(const uint32_t* __restrict__ a,
+                                                         uint32_t lo, uint32_t hi, uint32_t key,
+                                                         uint32_t shift) {
+    const uint32_t lane = threadIdx.x & 31;
+    while (lo < hi) {
+        const uint32_t step = (hi - lo + 31u) >> 5;
+        const uint32_t p = lo + (lane + 1u) * step - 1u;       // last element of chunk `lane`
+        const bool ge = (p < hi) ? (__ldg(a + p) + shift >= key) : true;
+        const unsigned b = __ballot_sync(0xffffffffu, ge);     // chunks past hi vote true
+        if (b == 0u) return hi;                                // all 32 chunks in range and < key
+        const uint32_t f = (uint32_t)__ffs(b) - 1u;
+        const uint32_t pf = lo + (f + 1u) * step - 1u;
+        lo += f * step;
+        if (pf < hi) hi = pf;          // a[pf] >= key: answer in [lo, pf]
+        else if (lo >= hi) return hi;  // every probed chunk was < key and nothing is left
+        // else: the unprobed tail chunk [lo, hi) remains (shorter than step)
     }
     return lo;
 }
@@ -119,9 +144,10 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
                     const uint32_t n = src.n[k];
                     x0 = lower_bound_u32(src.xs[k], 0, n, gs);
                     x1 = lower_bound_u32(src.xs[k], x0, n, ge + 1u);
-                    y0 = lower_bound_u32(src.ye[k], 0, n, gs);
-                    const uint32_t yov = lower_bound_u32(src.ye[k], y0, n, gs + 1u);
-                    y1 = lower_bound_u32(src.ye[k], yov, n, ge + 1u);
+                    const uint32_t sh = src.yshift[k];
+                    y0 = lower_bound_u32(src.ye[k], 0, n, gs, sh);
+                    const uint32_t yov = lower_bound_u32(src.ye[k], y0, n, gs + 1u, sh);
+                    y1 = lower_bound_u32(src.ye[k], yov, n, ge + 1u, sh);
                     nov += (long long)x1 - (long long)yov;
                 }
                 out.ix0[r * NS + k] = x0;
@@ -178,38 +204,69 @@ __device__ __forceinline__ void warp_aggregated_add(int* diff, uint32_t pos, boo
     }
 }
 
-// In-place inclusive scan of rows [row_lo, row_hi) of `diff` by ONE warp (a row = 128 ints read
-// as one int4 per lane); returns the warp's total in every lane.
-__device__ __forceinline__ int warp_scan_rows(int* diff, int row_lo, int row_hi) {
+// In-place inclusive scan of ONE row (128 ints, one int4 per lane) by one warp, starting from
+// `carry`; returns the row total in every lane.
+__device__ __forceinline__ int warp_scan_row(int* row_ptr, int carry) {
     const unsigned lane = threadIdx.x & 31;
-    int carry = 0;
-    for (int row = row_lo; row < row_hi; row++) {
-        int4* p = reinterpret_cast<int4*>(diff + row * ROW) + lane;
-        int4 v = *p;
-        v.y += v.x;
-        v.z += v.y;
-        v.w += v.z;
-        int inc = v.w;
+    int4* p = reinterpret_cast<int4*>(row_ptr) + lane;
+    int4 v = *p;
+    v.y += v.x;
+    v.z += v.y;
+    v.w += v.z;
+    int inc = v.w;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        const int ex = inc - v.w + carry;
-        v.x += ex;
-        v.y += ex;
-        v.z += ex;
-        v.w += ex;
-        *p = v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
     }
-    return carry;
+    const int ex = inc - v.w + carry;
+    v.x += ex;
+    v.y += ex;
+    v.z += ex;
+    v.w += ex;
+    *p = v;
+    return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// rows [0, nrows) of `diff`, one warp, carry passed from row to row
+__device__ __forceinline__ void warp_scan_rows(int* diff, int nrows) {
+    int carry = 0;
+    for (int row = 0; row < nrows; row++) carry += warp_scan_row(diff + row * ROW, carry);
+}
+
+// CTA-wide: every warp scans rows warp, warp+WARPS, ... independently, then warp 0 turns the row
+// totals into exclusive row prefixes.  Ends with a __syncthreads(); value(k) =
+// diff[k] + rowpre[k / ROW].
+__device__ __forceinline__ void block_scan_rows(int* diff, int nrows, int* rowpre) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < nrows; row += WARPS) {
+        const int tot = warp_scan_row(diff + row * ROW, 0);
+        if (lane == 0) rowpre[row] = tot;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int r0 = 0; r0 < nrows; r0 += 32) {
+            const int r = r0 + lane;
+            const int v = r < nrows ? rowpre[r] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (r < nrows) rowpre[r] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
 }
 
 // Store tile values to the region's output.  Tile covers region-relative positions
 // [t0, t0 + tlen); value(k) = add[k / seg_len] + vals[k] for k relative to the tile.
 // Output index of region position q is q ('+') or L-1-q ('-').  `tid`/`nthreads` describe the
 // cooperating threads (a CTA or one warp).  dst is 16-byte aligned at index 0.
+// value(k) = base + vals[k] (+ seg_add[k / ROW] when HAS_SEG).
 template <bool HAS_SEG>
 __device__ __forceinline__ void store_tile(int32_t* __restrict__ dst, int L, bool rev, int t0,
                                            int tlen, const int* vals, const int* seg_add,
@@ -225,7 +282,7 @@ __device__ __forceinline__ void store_tile(int32_t* __restrict__ dst, int L, boo
             ok[q] = (o >= o_lo) && (o < o_hi);
             const int k = rev ? (L - 1 - o - t0) : (o - t0);
             v[q] = 0;
-            if (ok[q]) v[q] = base + vals[k] + (HAS_SEG ? seg_add[k / SEG] : 0);
+            if (ok[q]) v[q] = base + vals[k] + (HAS_SEG ? seg_add[k / ROW] : 0);
         }
         if (ok[0] && ok[3]) {
             *reinterpret_cast<int4*>(dst + g) = make_int4(v[0], v[1], v[2], v[3]);
@@ -272,12 +329,12 @@ cov_small_kernel(int64_t R, RegionArrays ra, Sources<NS> src, const int64_t* __r
         for (uint32_t i0 = y0; i0 < y1; i0 += 32) {
             const uint32_t i = i0 + lane;
             const bool ok = i < y1;
-            const uint32_t p = ok ? (__ldg(src.ye[k] + i) - gs) : 0u;
+            const uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gs) : 0u;
             warp_aggregated_add(diff, p, ok, -1);
         }
     }
     __syncwarp();
-    warp_scan_rows(diff, 0, nrows);
+    warp_scan_rows(diff, nrows);
     __syncwarp();
     store_tile<false>(cov + off[r], L, (flags & 1u) != 0, 0, L, diff, nullptr, base, lane, 32);
 }
@@ -289,8 +346,7 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
                 RegionArrays ra, Sources<NS> src, const int64_t* __restrict__ off,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
-    __shared__ int wtot[WARPS];
-    __shared__ int wpre[WARPS];
+    __shared__ int rowpre[MAX_ROWS];
     __shared__ uint32_t bnd[4 * NS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t r = tile_region[blockIdx.x];
@@ -303,17 +359,20 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
     const uint32_t gts = ra.gs[r] + (uint32_t)t0;
     const unsigned flags = ra.flags[r];
     const unsigned mask = flags >> 1;
-    // slice bounds of this tile: searched inside the region's own slices (a few steps)
-    if (tid < 4 * NS) {
-        const int k = tid >> 2, which = tid & 3;
+    // slice bounds of this tile, searched warp-wide inside the region's own slices
+    for (int q = warp; q < 4 * NS; q += WARPS) {
+        const int k = q >> 2, which = q & 3;
         const bool is_x = which < 2;
         const uint32_t key = (which & 1) ? gts + (uint32_t)tlen : gts;
         const uint32_t lo = is_x ? ra.ix0[r * NS + k] : ra.iy0[r * NS + k];
         const uint32_t hi = is_x ? ra.ix1[r * NS + k] : ra.iy1[r * NS + k];
         uint32_t res = lo;
-        if ((mask >> k) & 1u)
-            res = lower_bound_u32(is_x ? src.xs[k] : src.ye[k], lo, hi, key);
-        bnd[tid] = res;
+        if ((mask >> k) & 1u) {
+            if (m == 1) res = (which & 1) ? hi : lo;
+            else res = warp_lower_bound_u32(is_x ? src.xs[k] : src.ye[k], lo, hi, key,
+                                            is_x ? 0u : src.yshift[k]);
+        }
+        if (lane == 0) bnd[q] = res;
     }
     const int nrows = (tlen + ROW - 1) / ROW;
     for (int i = tid; i < nrows * (ROW / 4); i += CTA)
@@ -335,25 +394,13 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
         for (uint32_t i0 = y0 + warp * 32; i0 < y1; i0 += CTA) {
             const uint32_t i = i0 + lane;
             const bool ok = i < y1;
-            const uint32_t p = ok ? (__ldg(src.ye[k] + i) - gts) : 0u;
+            const uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gts) : 0u;
             warp_aggregated_add(diff, p, ok, -1);
         }
     }
     __syncthreads();
-    {
-        const int row_lo = warp * (SEG / ROW);
-        const int row_hi = min(row_lo + SEG / ROW, nrows);
-        const int tot = warp_scan_rows(diff, row_lo, row_hi);
-        if (lane == 0) wtot[warp] = tot;
-    }
-    __syncthreads();
-    if (tid < WARPS) {
-        int p = 0;
-        for (int w = 0; w < tid; w++) p += wtot[w];
-        wpre[tid] = p;
-    }
-    __syncthreads();
-    store_tile<true>(cov + off[r], L, (flags & 1u) != 0, t0, tlen, diff, wpre, base, tid, CTA);
+    block_scan_rows(diff, nrows, rowpre);
+    store_tile<true>(cov + off[r], L, (flags & 1u) != 0, t0, tlen, diff, rowpre, base, tid, CTA);
 }
 
 // ---- GRangesList elements -------------------------------------------------------------------
@@ -484,9 +531,8 @@ cov_list_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
                 int ignore_strand, int strand_filter, const int64_t* __restrict__ off,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
-    __shared__ int wtot[WARPS];
-    __shared__ int wpre[WARPS];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ int rowpre[MAX_ROWS];
+    const int tid = threadIdx.x;
     const int64_t g = tile_region[blockIdx.x];
     const int j = (int)((int64_t)blockIdx.x - tile_off[g]);
     const int L = la.len[g];
@@ -530,20 +576,8 @@ cov_list_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
         }
     }
     __syncthreads();
-    {
-        const int row_lo = warp * (SEG / ROW);
-        const int row_hi = min(row_lo + SEG / ROW, nrows);
-        const int tot = warp_scan_rows(diff, row_lo, row_hi);
-        if (lane == 0) wtot[warp] = tot;
-    }
-    __syncthreads();
-    if (tid < WARPS) {
-        int p = 0;
-        for (int w = 0; w < tid; w++) p += wtot[w];
-        wpre[tid] = p;
-    }
-    __syncthreads();
-    store_tile<true>(cov + off[g], L, (la.flags[g] & 1u) != 0, t0, tlen, diff, wpre, 0, tid, CTA);
+    block_scan_rows(diff, nrows, rowpre);
+    store_tile<true>(cov + off[g], L, (la.flags[g] & 1u) != 0, t0, tlen, diff, rowpre, 0, tid, CTA);
 }
 
 // ---- c(left, center, right) -----------------------------------------------------------------
@@ -724,7 +758,8 @@ int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t
         RCP_TRY(reads_build_class(rd, CLS_ALL));
         Sources<1> src;
         src.xs[0] = rd.cls[CLS_ALL].xs;
-        src.ye[0] = rd.cls[CLS_ALL].ye;
+        src.ye[0] = rd.uniform_w ? rd.cls[CLS_ALL].xs : rd.cls[CLS_ALL].ye;
+        src.yshift[0] = rd.uniform_w;
         src.n[0] = (uint32_t)rd.cls[CLS_ALL].n;
         return coverage_ranges_impl<1>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
                                        d_strand.ptr, ignore_strand, strand_filter, cv);
@@ -733,7 +768,8 @@ int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t
     for (int k = 0; k < 3; k++) {
         RCP_TRY(reads_build_class(rd, CLS_PLUS + k));
         src.xs[k] = rd.cls[CLS_PLUS + k].xs;
-        src.ye[k] = rd.cls[CLS_PLUS + k].ye;
+        src.ye[k] = rd.uniform_w ? rd.cls[CLS_PLUS + k].xs : rd.cls[CLS_PLUS + k].ye;
+        src.yshift[k] = rd.uniform_w;
         src.n[k] = (uint32_t)rd.cls[CLS_PLUS + k].n;
     }
     return coverage_ranges_impl<3>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr,

@@ -25,10 +25,12 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
                        uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
                        int8_t* __restrict__ strand_out, unsigned int* __restrict__ err,
-                       unsigned long long* __restrict__ cls_count) {
+                       unsigned long long* __restrict__ cls_count,
+                       unsigned int* __restrict__ wminmax /* [0] min width, [1] max width */) {
     const int64_t stride = (int64_t)gridDim.x * TPB;
     unsigned int my_err = 0;
     unsigned int np = 0, nm = 0, ns = 0;
+    unsigned int wmin = 0xffffffffu, wmax = 0;
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
         const int c = chrom[i];
         int64_t s = start[i], e = end[i];
@@ -50,6 +52,8 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
             else {
                 gs = chrom_off[c] + (uint32_t)s;
                 ge1 = chrom_off[c] + (uint32_t)e + 1u;
+                wmin = min(wmin, ge1 - gs);
+                wmax = max(wmax, ge1 - gs);
             }
         }
         g_start[i] = gs;
@@ -60,10 +64,14 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         ns += st == 0;
     }
     // block-level reduction of the three strand counters and the error mask
-    __shared__ unsigned int sh[4];
+    __shared__ unsigned int sh[6];
     if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+    if (threadIdx.x == 4) sh[4] = 0xffffffffu;
+    if (threadIdx.x == 5) sh[5] = 0;
     __syncthreads();
     for (int d = 16; d > 0; d >>= 1) {
+        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, d));
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
         np += __shfl_xor_sync(0xffffffffu, np, d);
         nm += __shfl_xor_sync(0xffffffffu, nm, d);
         ns += __shfl_xor_sync(0xffffffffu, ns, d);
@@ -74,9 +82,13 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         atomicAdd(&sh[1], nm);
         atomicAdd(&sh[2], ns);
         atomicOr(&sh[3], my_err);
+        atomicMin(&sh[4], wmin);
+        atomicMax(&sh[5], wmax);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        atomicMin(&wminmax[0], sh[4]);
+        atomicMax(&wminmax[1], sh[5]);
         if (sh[0]) atomicAdd(&cls_count[0], (unsigned long long)sh[0]);
         if (sh[1]) atomicAdd(&cls_count[1], (unsigned long long)sh[1]);
         if (sh[2]) atomicAdd(&cls_count[2], (unsigned long long)sh[2]);
@@ -88,7 +100,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
 __global__ void __launch_bounds__(TPB)
 compact_strand_kernel(int64_t n, const uint32_t* __restrict__ g_start,
                       const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
-                      int want, uint32_t* __restrict__ xs, uint32_t* __restrict__ ye,
+                      int want, uint32_t* __restrict__ xs, uint32_t* __restrict__ ye /* may be null */,
                       unsigned long long* __restrict__ cursor) {
     const int64_t stride = (int64_t)gridDim.x * TPB;
     const unsigned lane = threadIdx.x & 31;
@@ -103,7 +115,7 @@ compact_strand_kernel(int64_t n, const uint32_t* __restrict__ g_start,
         if (keep) {
             const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
             xs[o] = g_start[i];
-            ye[o] = g_end1[i];
+            if (ye) ye[o] = g_end1[i];
         }
     }
 }
@@ -266,24 +278,28 @@ void reads_release(ReadsIdx& r) {
 int reads_build_class(ReadsIdx& r, int cls) {
     SortedClass& sc = r.cls[cls];
     if (sc.built) return RCP_OK;
+    const bool uni = r.uniform_w != 0;   // ye == xs + w: no second array, no second sort
     if (cls == CLS_ALL) {
         sc.n = r.n;
         RCP_TRY(dalloc(&sc.xs, (size_t)r.n));
-        RCP_TRY(dalloc(&sc.ye, (size_t)r.n));
         RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
                                  g_ctx.stream));
-        RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
-                                 g_ctx.stream));
+        if (!uni) {
+            RCP_TRY(dalloc(&sc.ye, (size_t)r.n));
+            RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
+                                     g_ctx.stream));
+        }
     } else {
         // sc.n was filled from the strand histogram at load time
         RCP_TRY(dalloc(&sc.xs, (size_t)sc.n));
-        RCP_TRY(dalloc(&sc.ye, (size_t)sc.n));
+        if (!uni) RCP_TRY(dalloc(&sc.ye, (size_t)sc.n));
         if (sc.n > 0) {
             if (!r.has_strand) {   // every read is '*': the STAR class is everything
                 RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4,
                                          cudaMemcpyDeviceToDevice, g_ctx.stream));
-                RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4,
-                                         cudaMemcpyDeviceToDevice, g_ctx.stream));
+                if (!uni)
+                    RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4,
+                                             cudaMemcpyDeviceToDevice, g_ctx.stream));
             } else {
                 unsigned long long* cursor = nullptr;
                 RCP_TRY(dalloc(&cursor, 1));
@@ -299,9 +315,9 @@ int reads_build_class(ReadsIdx& r, int cls) {
     {
         StageTimer t(ST_INDEX_SORT);
         RCP_TRY(sort_keys_u32(sc.xs, sc.n, r.key_bits));
-        RCP_TRY(sort_keys_u32(sc.ye, sc.n, r.key_bits));
+        if (!uni) RCP_TRY(sort_keys_u32(sc.ye, sc.n, r.key_bits));
     }
-    r.device_bytes += (size_t)sc.n * 8;
+    r.device_bytes += (size_t)sc.n * (uni ? 4 : 8);
     sc.built = true;
     return RCP_OK;
 }
@@ -378,31 +394,40 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     if (r.has_strand) RCP_TRY(dalloc(&r.d_strand, (size_t)n));
     unsigned int* d_err = nullptr;
     unsigned long long* d_cnt = nullptr;
+    unsigned int* d_w = nullptr;
     RCP_TRY(dalloc(&d_err, 1));
     RCP_TRY(dalloc(&d_cnt, 3));
+    RCP_TRY(dalloc(&d_w, 2));
+    const unsigned int w_init[2] = {0xffffffffu, 0u};
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(d_w, w_init, sizeof(w_init), cudaMemcpyHostToDevice, g_ctx.stream));
     if (n > 0) {
         StageTimer t(ST_INDEX_MAP);
         reads_to_global_kernel<<<grid_for(n), TPB, 0, g_ctx.stream>>>(
             n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
-            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt);
+            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt, d_w);
         RCP_LAUNCHED();
     }
-    unsigned int h_err = 0;
+    unsigned int h_err = 0, h_w[2] = {0, 0};
     unsigned long long h_cnt[3] = {0, 0, 0};
-    RCP_TRY(reads_build_class(r, CLS_ALL));
     RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h_w, d_w, sizeof(h_w), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     dfree(d_err);
     dfree(d_cnt);
+    dfree(d_w);
+    // every read has the same width w (fixed-length or fragment-extended libraries): the sorted
+    // ends are the sorted starts shifted by w
+    r.uniform_w = (h_err == 0 && n > 0 && h_w[0] == h_w[1]) ? h_w[0] : 0u;
     if (h_err & 1u) return fail(RCP_ERR_DATA, "a read has a chromosome id outside [0, n_chrom)");
     if (h_err & 2u) return fail(RCP_ERR_DATA, "a read violates 1 <= start <= end");
     if (h_err & 4u) return fail(RCP_ERR_DATA, "a read starts beyond the end of its chromosome");
     r.cls[CLS_PLUS].n = (int64_t)h_cnt[0];
     r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
     r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
+    RCP_TRY(reads_build_class(r, CLS_ALL));
     r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
     return RCP_OK;
 }

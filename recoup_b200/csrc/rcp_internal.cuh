@@ -112,13 +112,15 @@ struct SortedClass {
     bool built = false;
     int64_t n = 0;
     uint32_t* xs = nullptr;   // sorted global start coordinates
-    uint32_t* ye = nullptr;   // sorted global (end + 1) coordinates, sorted independently
+    uint32_t* ye = nullptr;   // sorted global (end + 1) coordinates, sorted independently;
+                              // nullptr in uniform-width mode (ye[i] == xs[i] + uniform_w)
 };
 
 struct ReadsIdx {
     int64_t n = 0;
     int n_chrom = 0;
     bool has_strand = false;
+    uint32_t uniform_w = 0;             // > 0: every read is exactly this wide (ye == xs + w)
     int key_bits = 32;
     std::vector<int64_t> chrom_len;     // host copies
     std::vector<uint32_t> chrom_off;    // n_chrom + 1, global coordinate of position 0

@@ -22,6 +22,8 @@ def strand_to_code(strand, n=None):
     if isinstance(strand, str):
         return np.full(1 if n is None else n, _STRAND_CODE[strand], dtype=np.int8)
     arr = np.asarray(strand)
+    if arr.dtype == np.int8:
+        return arr          # already coded; the library only looks at the sign
     if arr.dtype.kind in "US":
         out = np.zeros(arr.shape, dtype=np.int8)
         out[arr == "+"] = 1
