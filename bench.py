@@ -118,7 +118,7 @@ class ClockSampler:
         window = "timed region"
         if len(inside) < 3:
             inside = self.rows          # timed region shorter than the sampling period
-            window = "warm-up + timed + e2e loops (timed region < 3 samples long)"
+            window = "warm-up + timed region (timed region < 3 samples long)"
         sm, mx, reasons = digest(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
@@ -377,6 +377,9 @@ def run_b200(args):
     _lib.check(L.rcp_timing_enable(0))
     stage = {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
              for i in range(n_st) if cnt[i] > 0}
+    # the sampler polls nvidia-smi (a driver-lock heavy call): it covers warm-up + the timed
+    # device region only and is stopped before the host-API (e2e) loop
+    clocks = sampler.stop(t_begin, t_end)
 
     # ---- timed: end to end through the public host API (pinned host buffers) ----
     def pinned(a):
@@ -439,7 +442,6 @@ def run_b200(args):
         mat = e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    clocks = sampler.stop(t_begin, t_end)
     assert mat.shape == (R, ncols)
 
     # ---- reduce over ranks (max time) ----

@@ -36,6 +36,8 @@ struct Sources {
     const uint32_t* ye[NS];
     uint32_t n[NS];
     uint32_t yshift[NS];
+    uint8_t cls_bit[NS];   // bit of the region's class mask that enables this source
+    uint8_t corr[NS];      // 1: correction source of the uniform-width index (index.cu)
 };
 
 struct RegionArrays {
@@ -117,7 +119,7 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
         bool null = false;
         uint32_t gs = 0;
         int64_t L = 0;
-        unsigned mask = NS == 1 ? 1u : class_mask(st, ignore_strand, strand_filter);
+        unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
         if (c < 0 || c >= n_chrom) {
             atomicOr(err, 1u);
             null = true;
@@ -140,7 +142,7 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
 #pragma unroll
             for (int k = 0; k < NS; k++) {
                 uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-                if ((mask >> k) & 1u) {
+                if ((mask >> src.cls_bit[k]) & 1u) {
                     const uint32_t n = src.n[k];
                     x0 = lower_bound_u32(src.xs[k], 0, n, gs);
                     x1 = lower_bound_u32(src.xs[k], x0, n, ge + 1u);
@@ -148,7 +150,10 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
                     y0 = lower_bound_u32(src.ye[k], 0, n, gs, sh);
                     const uint32_t yov = lower_bound_u32(src.ye[k], y0, n, gs + 1u, sh);
                     y1 = lower_bound_u32(src.ye[k], yov, n, ge + 1u, sh);
-                    nov += (long long)x1 - (long long)yov;
+                    // reads overlapping the window: #{start <= ge} - #{end < gs}.  A correction
+                    // source only moves end events, so both of its counts are taken at gs.
+                    const uint32_t xov = src.corr[k] ? lower_bound_u32(src.xs[k], x0, x1, gs + 1u) : x1;
+                    nov += (long long)xov - (long long)yov;
                 }
                 out.ix0[r * NS + k] = x0;
                 out.ix1[r * NS + k] = x1;
@@ -316,7 +321,7 @@ cov_small_kernel(int64_t R, RegionArrays ra, Sources<NS> src, const int64_t* __r
     int base = 0;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
-        if (!((mask >> k) & 1u)) continue;
+        if (!((mask >> src.cls_bit[k]) & 1u)) continue;
         const uint32_t x0 = ra.ix0[r * NS + k], x1 = ra.ix1[r * NS + k];
         const uint32_t y0 = ra.iy0[r * NS + k], y1 = ra.iy1[r * NS + k];
         base += (int)(x0 - y0);
@@ -367,7 +372,7 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
         const uint32_t lo = is_x ? ra.ix0[r * NS + k] : ra.iy0[r * NS + k];
         const uint32_t hi = is_x ? ra.ix1[r * NS + k] : ra.iy1[r * NS + k];
         uint32_t res = lo;
-        if ((mask >> k) & 1u) {
+        if ((mask >> src.cls_bit[k]) & 1u) {
             if (m == 1) res = (which & 1) ? hi : lo;
             else res = warp_lower_bound_u32(is_x ? src.xs[k] : src.ye[k], lo, hi, key,
                                             is_x ? 0u : src.yshift[k]);
@@ -381,7 +386,7 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
     int base = 0;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
-        if (!((mask >> k) & 1u)) continue;
+        if (!((mask >> src.cls_bit[k]) & 1u)) continue;
         const uint32_t x0 = bnd[4 * k + 0], x1 = bnd[4 * k + 1];
         const uint32_t y0 = bnd[4 * k + 2], y1 = bnd[4 * k + 3];
         base += (int)(x0 - y0);
@@ -754,25 +759,52 @@ int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t
     RCP_TRY(d_end.init(end, (size_t)R, mem));
     RCP_TRY(d_strand.init(strand, (size_t)R, mem));
     const bool unstranded = (strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr);
+    const bool uni = rd.uniform_w != 0;
+    auto fill = [&](auto& src, int slot, int cls, int bit) {
+        const SortedClass& sc = rd.cls[cls];
+        src.xs[slot] = sc.xs;
+        src.ye[slot] = uni ? sc.xs : sc.ye;
+        src.yshift[slot] = rd.uniform_w;
+        src.n[slot] = (uint32_t)sc.n;
+        src.cls_bit[slot] = (uint8_t)bit;
+        src.corr[slot] = 0;
+    };
+    auto fill_corr = [&](auto& src, int slot, int cls, int bit) {
+        const SortedClass& sc = rd.cls[cls];
+        src.xs[slot] = sc.cxs;
+        src.ye[slot] = sc.cye;
+        src.yshift[slot] = 0;
+        src.n[slot] = (uint32_t)sc.cn;
+        src.cls_bit[slot] = (uint8_t)bit;
+        src.corr[slot] = 1;
+    };
     if (unstranded) {
         RCP_TRY(reads_build_class(rd, CLS_ALL));
-        Sources<1> src;
-        src.xs[0] = rd.cls[CLS_ALL].xs;
-        src.ye[0] = rd.uniform_w ? rd.cls[CLS_ALL].xs : rd.cls[CLS_ALL].ye;
-        src.yshift[0] = rd.uniform_w;
-        src.n[0] = (uint32_t)rd.cls[CLS_ALL].n;
-        return coverage_ranges_impl<1>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
+        if (!uni) {
+            Sources<1> src;
+            fill(src, 0, CLS_ALL, 0);
+            return coverage_ranges_impl<1>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
+                                           d_strand.ptr, ignore_strand, strand_filter, cv);
+        }
+        Sources<2> src;
+        fill(src, 0, CLS_ALL, 0);
+        fill_corr(src, 1, CLS_ALL, 0);
+        return coverage_ranges_impl<2>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
                                        d_strand.ptr, ignore_strand, strand_filter, cv);
     }
-    Sources<3> src;
-    for (int k = 0; k < 3; k++) {
-        RCP_TRY(reads_build_class(rd, CLS_PLUS + k));
-        src.xs[k] = rd.cls[CLS_PLUS + k].xs;
-        src.ye[k] = rd.uniform_w ? rd.cls[CLS_PLUS + k].xs : rd.cls[CLS_PLUS + k].ye;
-        src.yshift[k] = rd.uniform_w;
-        src.n[k] = (uint32_t)rd.cls[CLS_PLUS + k].n;
+    for (int k = 0; k < 3; k++) RCP_TRY(reads_build_class(rd, CLS_PLUS + k));
+    if (!uni) {
+        Sources<3> src;
+        for (int k = 0; k < 3; k++) fill(src, k, CLS_PLUS + k, k);
+        return coverage_ranges_impl<3>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr,
+                                       d_strand.ptr, ignore_strand, strand_filter, cv);
     }
-    return coverage_ranges_impl<3>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr,
+    Sources<6> src;
+    for (int k = 0; k < 3; k++) {
+        fill(src, k, CLS_PLUS + k, k);
+        fill_corr(src, 3 + k, CLS_PLUS + k, k);
+    }
+    return coverage_ranges_impl<6>(rd, src, R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr,
                                    ignore_strand, strand_filter, cv);
 }
 

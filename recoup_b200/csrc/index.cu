@@ -9,6 +9,10 @@
 // cut any region into tiles without carrying state between tiles (coverage.cu).
 // Replaces splitBySeqname + the per-region findOverlaps/coverage of the reference
 // (/root/reference/R/util.R:1-13, R/coverage.R:189-201).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "rcp_internal.cuh"
 
 namespace rcp {
@@ -17,7 +21,36 @@ namespace {
 
 constexpr int TPB = 256;
 
-// bit0 chrom id out of range, bit1 start < 1 or end < start, bit2 start beyond the chromosome
+// Reads -> global coordinates.  err bits: 1 chrom id out of range, 2 start < 1 or end < start,
+// 4 start beyond the chromosome.
+struct ExcBuf {
+    uint32_t* xw;        // start + w of reads whose width differs from w ("assumed" end + 1)
+    uint32_t* e1;        // their true end + 1
+    int8_t* st;          // their strand
+    uint32_t cap;
+    unsigned int* count; // may exceed cap: overflow => uniform-width mode is abandoned
+    uint32_t* w_out;     // the candidate width used
+};
+
+__device__ __forceinline__ bool map_read(int c, int64_t s, int64_t e, int st, int n_chrom,
+                                         const uint32_t* __restrict__ chrom_off,
+                                         const int64_t* __restrict__ chrom_len, int frag_len,
+                                         uint32_t* gs, uint32_t* ge1, unsigned int* err) {
+    if (c < 0 || c >= n_chrom) { *err |= 1u; return false; }
+    if (s < 1 || e < s) { *err |= 2u; return false; }
+    const int64_t len = chrom_len[c];
+    if (frag_len > 0) {           // resize(fix="start"): '-' keeps its end
+        if (st < 0) s = e - frag_len + 1;
+        else e = s + frag_len - 1;
+    }
+    if (s < 1) s = 1;             // trim()
+    if (e > len) e = len;
+    if (s > len || e < s) { *err |= 4u; return false; }
+    *gs = chrom_off[c] + (uint32_t)s;
+    *ge1 = chrom_off[c] + (uint32_t)e + 1u;
+    return true;
+}
+
 __global__ void __launch_bounds__(TPB)
 reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int32_t* __restrict__ start, const int32_t* __restrict__ end,
@@ -25,35 +58,32 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
                        uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
                        int8_t* __restrict__ strand_out, unsigned int* __restrict__ err,
-                       unsigned long long* __restrict__ cls_count,
-                       unsigned int* __restrict__ wminmax /* [0] min width, [1] max width */) {
+                       unsigned long long* __restrict__ cls_count, ExcBuf exc) {
     const int64_t stride = (int64_t)gridDim.x * TPB;
     unsigned int my_err = 0;
     unsigned int np = 0, nm = 0, ns = 0;
-    unsigned int wmin = 0xffffffffu, wmax = 0;
+    // candidate common width: the fragment length, else the width of read 0
+    uint32_t w = (uint32_t)frag_len;
+    if (frag_len <= 0) {
+        uint32_t a = 0, b = 0;
+        unsigned int e0 = 0;
+        if (map_read(chrom[0], start[0], end[0], strand ? (int)strand[0] : 0, n_chrom, chrom_off,
+                     chrom_len, 0, &a, &b, &e0))
+            w = b - a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *exc.w_out = w;
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-        const int c = chrom[i];
-        int64_t s = start[i], e = end[i];
         const int st = strand ? (int)strand[i] : 0;
         uint32_t gs = 0, ge1 = 0;
-        if (c < 0 || c >= n_chrom) {
-            my_err |= 1u;
-        } else if (s < 1 || e < s) {
-            my_err |= 2u;
-        } else {
-            const int64_t len = chrom_len[c];
-            if (frag_len > 0) {           // resize(fix="start"): '-' keeps its end
-                if (st < 0) s = e - frag_len + 1;
-                else e = s + frag_len - 1;
-            }
-            if (s < 1) s = 1;             // trim()
-            if (e > len) e = len;
-            if (s > len || e < s) my_err |= 4u;
-            else {
-                gs = chrom_off[c] + (uint32_t)s;
-                ge1 = chrom_off[c] + (uint32_t)e + 1u;
-                wmin = min(wmin, ge1 - gs);
-                wmax = max(wmax, ge1 - gs);
+        if (map_read(chrom[i], start[i], end[i], st, n_chrom, chrom_off, chrom_len, frag_len, &gs,
+                     &ge1, &my_err)) {
+            if (ge1 - gs != w) {
+                const unsigned int k = atomicAdd(exc.count, 1u);
+                if (k < exc.cap) {
+                    exc.xw[k] = gs + w;
+                    exc.e1[k] = ge1;
+                    exc.st[k] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
+                }
             }
         }
         g_start[i] = gs;
@@ -64,14 +94,10 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         ns += st == 0;
     }
     // block-level reduction of the three strand counters and the error mask
-    __shared__ unsigned int sh[6];
+    __shared__ unsigned int sh[4];
     if (threadIdx.x < 4) sh[threadIdx.x] = 0;
-    if (threadIdx.x == 4) sh[4] = 0xffffffffu;
-    if (threadIdx.x == 5) sh[5] = 0;
     __syncthreads();
     for (int d = 16; d > 0; d >>= 1) {
-        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, d));
-        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
         np += __shfl_xor_sync(0xffffffffu, np, d);
         nm += __shfl_xor_sync(0xffffffffu, nm, d);
         ns += __shfl_xor_sync(0xffffffffu, ns, d);
@@ -82,18 +108,26 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         atomicAdd(&sh[1], nm);
         atomicAdd(&sh[2], ns);
         atomicOr(&sh[3], my_err);
-        atomicMin(&sh[4], wmin);
-        atomicMax(&sh[5], wmax);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicMin(&wminmax[0], sh[4]);
-        atomicMax(&wminmax[1], sh[5]);
         if (sh[0]) atomicAdd(&cls_count[0], (unsigned long long)sh[0]);
         if (sh[1]) atomicAdd(&cls_count[1], (unsigned long long)sh[1]);
         if (sh[2]) atomicAdd(&cls_count[2], (unsigned long long)sh[2]);
         if (sh[3]) atomicOr(err, sh[3]);
     }
+}
+
+// correction events of one strand class; slots of other strands become +inf sentinels
+__global__ void __launch_bounds__(TPB)
+exc_select_kernel(uint32_t n_exc, const uint32_t* __restrict__ xw, const uint32_t* __restrict__ e1,
+                  const int8_t* __restrict__ st, int want /* 2 = every strand */,
+                  uint32_t* __restrict__ cxs, uint32_t* __restrict__ cye) {
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n_exc) return;
+    const bool keep = (want == 2) || ((int)st[i] == want);
+    cxs[i] = keep ? xw[i] : 0xffffffffu;
+    cye[i] = keep ? e1[i] : 0xffffffffu;
 }
 
 // keep the reads of one strand (order is irrelevant: both outputs are sorted afterwards)
@@ -267,8 +301,13 @@ void reads_release(ReadsIdx& r) {
     for (int c = 0; c < CLS_N; c++) {
         dfree(r.cls[c].xs);
         dfree(r.cls[c].ye);
+        dfree(r.cls[c].cxs);
+        dfree(r.cls[c].cye);
         r.cls[c].built = false;
     }
+    dfree(r.exc_xw);
+    dfree(r.exc_e1);
+    dfree(r.exc_st);
     dfree(r.p_end1);
     dfree(r.p_strand);
     dfree(r.p_maxend1);
@@ -312,10 +351,25 @@ int reads_build_class(ReadsIdx& r, int cls) {
             }
         }
     }
+    if (uni && r.n_exc > 0) {
+        // reads whose width is not w: the main source assumed "end + 1 = start + w" for them;
+        // the correction source cancels that event (+1 at start + w) and adds the true one
+        sc.cn = r.n_exc;
+        RCP_TRY(dalloc(&sc.cxs, (size_t)sc.cn));
+        RCP_TRY(dalloc(&sc.cye, (size_t)sc.cn));
+        const int want = cls == CLS_ALL ? 2 : (cls == CLS_PLUS ? 1 : (cls == CLS_MINUS ? -1 : 0));
+        exc_select_kernel<<<(unsigned)((sc.cn + TPB - 1) / TPB), TPB, 0, g_ctx.stream>>>(
+            (uint32_t)sc.cn, r.exc_xw, r.exc_e1, r.exc_st, r.has_strand ? want : 2, sc.cxs, sc.cye);
+        RCP_LAUNCHED();
+    }
     {
         StageTimer t(ST_INDEX_SORT);
         RCP_TRY(sort_keys_u32(sc.xs, sc.n, r.key_bits));
         if (!uni) RCP_TRY(sort_keys_u32(sc.ye, sc.n, r.key_bits));
+        if (sc.cn > 0) {
+            RCP_TRY(sort_keys_u32(sc.cxs, sc.cn, 32));
+            RCP_TRY(sort_keys_u32(sc.cye, sc.cn, 32));
+        }
     }
     r.device_bytes += (size_t)sc.n * (uni ? 4 : 8);
     sc.built = true;
@@ -354,6 +408,15 @@ int reads_build_pairs(ReadsIdx& r) {
 int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
                     const int64_t* chrom_len, int frag_len, int mem) {
+    const bool dbg = getenv("RCP_DEBUG_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rcp_reads_load] %-28s %8.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     r.n = n;
     r.n_chrom = n_chrom;
     r.has_strand = strand != nullptr;
@@ -388,25 +451,35 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     RCP_TRY(d_start.init(start, (size_t)n, mem));
     RCP_TRY(d_end.init(end, (size_t)n, mem));
     RCP_TRY(d_strand.init(strand, (size_t)n, mem));
+    lap("staging copies enqueued");
 
     RCP_TRY(dalloc(&r.g_start, (size_t)n));
     RCP_TRY(dalloc(&r.g_end1, (size_t)n));
     if (r.has_strand) RCP_TRY(dalloc(&r.d_strand, (size_t)n));
     unsigned int* d_err = nullptr;
     unsigned long long* d_cnt = nullptr;
-    unsigned int* d_w = nullptr;
+    unsigned int* d_w = nullptr;    // [0] exception count, [1] candidate width
     RCP_TRY(dalloc(&d_err, 1));
     RCP_TRY(dalloc(&d_cnt, 3));
     RCP_TRY(dalloc(&d_w, 2));
-    const unsigned int w_init[2] = {0xffffffffu, 0u};
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(d_w, w_init, sizeof(w_init), cudaMemcpyHostToDevice, g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(unsigned int), g_ctx.stream));
+    ExcBuf exc;
+    exc.cap = (uint32_t)((n / 64 > 4096) ? (n / 64) : 4096);
+    RCP_TRY(dalloc(&r.exc_xw, (size_t)exc.cap));
+    RCP_TRY(dalloc(&r.exc_e1, (size_t)exc.cap));
+    RCP_TRY(dalloc(&r.exc_st, (size_t)exc.cap));
+    exc.xw = r.exc_xw;
+    exc.e1 = r.exc_e1;
+    exc.st = r.exc_st;
+    exc.count = d_w;
+    exc.w_out = d_w + 1;
     if (n > 0) {
         StageTimer t(ST_INDEX_MAP);
         reads_to_global_kernel<<<grid_for(n), TPB, 0, g_ctx.stream>>>(
             n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
-            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt, d_w);
+            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt, exc);
         RCP_LAUNCHED();
     }
     unsigned int h_err = 0, h_w[2] = {0, 0};
@@ -414,13 +487,27 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_w, d_w, sizeof(h_w), cudaMemcpyDeviceToHost, g_ctx.stream));
+    lap("map kernel enqueued");
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    lap("sync (copies + map kernel)");
     dfree(d_err);
     dfree(d_cnt);
     dfree(d_w);
-    // every read has the same width w (fixed-length or fragment-extended libraries): the sorted
-    // ends are the sorted starts shifted by w
-    r.uniform_w = (h_err == 0 && n > 0 && h_w[0] == h_w[1]) ? h_w[0] : 0u;
+    // (nearly) every read has the same width w -- fixed-length or fragment-extended libraries;
+    // the few that do not (trimmed at a chromosome end) live in a correction source.  Then the
+    // sorted ends are the sorted starts shifted by w: one array, one sort.
+    if (h_err == 0 && n > 0 && h_w[1] > 0 && h_w[0] <= exc.cap) {
+        r.uniform_w = h_w[1];
+        r.n_exc = (int64_t)h_w[0];
+    } else {
+        r.uniform_w = 0;
+        r.n_exc = 0;
+    }
+    if (r.n_exc == 0) {
+        dfree(r.exc_xw);
+        dfree(r.exc_e1);
+        dfree(r.exc_st);
+    }
     if (h_err & 1u) return fail(RCP_ERR_DATA, "a read has a chromosome id outside [0, n_chrom)");
     if (h_err & 2u) return fail(RCP_ERR_DATA, "a read violates 1 <= start <= end");
     if (h_err & 4u) return fail(RCP_ERR_DATA, "a read starts beyond the end of its chromosome");
@@ -428,6 +515,7 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
     r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
     RCP_TRY(reads_build_class(r, CLS_ALL));
+    lap("class ALL enqueued");
     r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
     return RCP_OK;
 }

@@ -114,13 +114,21 @@ struct SortedClass {
     uint32_t* xs = nullptr;   // sorted global start coordinates
     uint32_t* ye = nullptr;   // sorted global (end + 1) coordinates, sorted independently;
                               // nullptr in uniform-width mode (ye[i] == xs[i] + uniform_w)
+    // uniform-width mode only: correction source for the reads whose width differs from w
+    int64_t cn = 0;
+    uint32_t* cxs = nullptr;  // sorted (start + w): cancels the assumed end event
+    uint32_t* cye = nullptr;  // sorted true (end + 1)
 };
 
 struct ReadsIdx {
     int64_t n = 0;
     int n_chrom = 0;
     bool has_strand = false;
-    uint32_t uniform_w = 0;             // > 0: every read is exactly this wide (ye == xs + w)
+    uint32_t uniform_w = 0;             // > 0: reads are this wide (ye == xs + w) except n_exc
+    int64_t n_exc = 0;                  // reads of another width (uniform-width mode)
+    uint32_t* exc_xw = nullptr;         // their start + w, true end + 1 and strand (unsorted)
+    uint32_t* exc_e1 = nullptr;
+    int8_t* exc_st = nullptr;
     int key_bits = 32;
     std::vector<int64_t> chrom_len;     // host copies
     std::vector<uint32_t> chrom_off;    // n_chrom + 1, global coordinate of position 0

@@ -178,6 +178,44 @@ def test_fragment_extension(gpu):
     assert_coverage_equal(got.to_list(), want)
 
 
+@pytest.mark.parametrize("ignore,filt", [(False, None), (True, "+"), (False, "-"), (True, None)])
+def test_uniform_width_index_with_trimmed_exceptions(gpu, ignore, filt):
+    """Fixed-width libraries use the one-sort index (ends = starts + w); reads trimmed at a
+    chromosome end are the exceptions carried by the correction source.  All strand modes."""
+    rb = gpu
+    rng = np.random.default_rng(33)
+    clen = [6000, 2500, 400]
+    chrom, s, e, st = synth_reads(rng, 12000, clen, width=(36, 36))
+    s[:40] = rng.integers(1, 30, size=40)                # pile reads onto the chromosome starts
+    e[:40] = s[:40] + 35
+    es, ee = O.extend_fragments(s, e, st, 200, chrom, clen)
+    assert 0 < int(((ee - es + 1) != 200).sum()) < 4096   # some, but few, exceptions
+    o_reads = O.Reads(chrom, es, ee, st, clen)
+    g_reads = rb.GRanges(chrom, s, e, strand=st, seqlevels=["c0", "c1", "c2"], seqlengths=clen)
+    rc, rs, re_, rst = _regions(rng, 150, clen, [1, 50, 199, 200, 201, 399, 1024, 1500, 2400])
+    rs[:6] = [1, 1, 1, 5800, 2300, 1]
+    re_[:6] = [100, 250, 6000, 6000, 2500, 400]
+    rc[:6] = [0, 1, 0, 0, 1, 2]
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 3)
+    filt_code = None if filt is None else {"+": 1, "-": -1, "*": 0}[filt]
+    want = O.calc_coverage(o_reads, o_mask, filt_code, ignore)
+    got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore, frag_len=200)
+    assert_coverage_equal(got.to_list(), want)
+
+
+@pytest.mark.parametrize("ignore,filt", [(False, None), (True, "-")])
+def test_uniform_width_fixture_stranded(gpu, fixture_data, ignore, filt):
+    rb = gpu
+    o_reads, g_reads = fixture_reads(fixture_data, 1)          # every read is 180 bp wide
+    o_genes, g_genes = fixture_genes(fixture_data)
+    filt_code = None if filt is None else {"+": 1, "-": -1}[filt]
+    want = O.coverage_ref(o_reads, o_genes, "genebody", (1500, 500), filt_code, ignore)
+    inp = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRef(inp, g_genes, "genebody", (1500, 500),
+                   strandedParams=dict(strand=filt, ignoreStrand=ignore))
+    assert_coverage_equal(inp[0]["coverage"].to_list(), want)
+
+
 @pytest.mark.parametrize("ignore", [True, False])
 def test_granges_list_multiplicity(gpu, ignore):
     rb = gpu
