@@ -209,94 +209,80 @@ __device__ __forceinline__ void warp_aggregated_add(int* diff, uint32_t pos, boo
     }
 }
 
-// In-place inclusive scan of ONE row (128 ints, one int4 per lane) by one warp, starting from
-// `carry`; returns the row total in every lane.
-__device__ __forceinline__ int warp_scan_row(int* row_ptr, int carry) {
+// --------------------------------------------------------------------------------------------
+// Scan + store.  `diff` holds the tile's difference array IN OUTPUT ORDER: for a '-' region the
+// events are scattered mirrored (index tlen-1-k), so the output is always written left to right
+// with aligned 16-byte stores straight from registers:
+//     '+'  out[k] = base + inclusive_prefix(k)
+//     '-'  out[k] = base + total - exclusive_prefix(k)        (a suffix sum of the mirrored array)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
     const unsigned lane = threadIdx.x & 31;
-    int4* p = reinterpret_cast<int4*>(row_ptr) + lane;
-    int4 v = *p;
-    v.y += v.x;
-    v.z += v.y;
-    v.w += v.z;
-    int inc = v.w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
     }
-    const int ex = inc - v.w + carry;
-    v.x += ex;
-    v.y += ex;
-    v.z += ex;
-    v.w += ex;
-    *p = v;
+    return v;
+}
+
+// One row (128 outputs at dst[0..127], `valid` of them real) by one warp.  `pre` = sum of every
+// diff before this row.  Returns the row total (all lanes).
+__device__ __forceinline__ int warp_row_scan_store(const int* row_ptr, int pre, int base_or_top,
+                                                   bool rev, int valid, int32_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int4 v = *(reinterpret_cast<const int4*>(row_ptr) + lane);
+    const int i0 = v.x, i1 = i0 + v.y, i2 = i1 + v.z, i3 = i2 + v.w;
+    const int inc = warp_inclusive_scan(i3);
+    const int ex = pre + inc - i3;                 // sum of everything before this lane's 4
+    int4 o;
+    if (!rev) {
+        o = make_int4(base_or_top + ex + i0, base_or_top + ex + i1, base_or_top + ex + i2,
+                      base_or_top + ex + i3);
+    } else {
+        o = make_int4(base_or_top - ex, base_or_top - ex - i0, base_or_top - ex - i1,
+                      base_or_top - ex - i2);
+    }
+    const int k = lane * 4;
+    if (k + 3 < valid) {
+        *reinterpret_cast<int4*>(dst + k) = o;
+    } else {
+        if (k < valid) dst[k] = o.x;
+        if (k + 1 < valid) dst[k + 1] = o.y;
+        if (k + 2 < valid) dst[k + 2] = o.z;
+    }
     return __shfl_sync(0xffffffffu, inc, 31);
 }
 
-// rows [0, nrows) of `diff`, one warp, carry passed from row to row
-__device__ __forceinline__ void warp_scan_rows(int* diff, int nrows) {
-    int carry = 0;
-    for (int row = 0; row < nrows; row++) carry += warp_scan_row(diff + row * ROW, carry);
-}
-
-// CTA-wide: every warp scans rows warp, warp+WARPS, ... independently, then warp 0 turns the row
-// totals into exclusive row prefixes.  Ends with a __syncthreads(); value(k) =
-// diff[k] + rowpre[k / ROW].
-__device__ __forceinline__ void block_scan_rows(int* diff, int nrows, int* rowpre) {
+// Whole CTA: tile of `tlen` outputs at dst (16-byte aligned).  rowpre needs MAX_ROWS + 1 ints.
+__device__ __forceinline__ void block_scan_store(const int* diff, int tlen, int base, bool rev,
+                                                 int* rowpre, int32_t* __restrict__ dst) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = warp; row < nrows; row += WARPS) {
-        const int tot = warp_scan_row(diff + row * ROW, 0);
-        if (lane == 0) rowpre[row] = tot;
+    const int nrows = (tlen + ROW - 1) / ROW;
+    for (int row = warp; row < nrows; row += WARPS) {          // pass A: row totals
+        const int4 v = *(reinterpret_cast<const int4*>(diff + row * ROW) + lane);
+        int s = v.x + v.y + v.z + v.w;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) rowpre[row] = s;
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0) {                                           // exclusive prefix of the rows
         int carry = 0;
         for (int r0 = 0; r0 < nrows; r0 += 32) {
             const int r = r0 + lane;
             const int v = r < nrows ? rowpre[r] : 0;
-            int inc = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
+            const int inc = warp_inclusive_scan(v);
             if (r < nrows) rowpre[r] = carry + inc - v;
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
+        if (lane == 0) rowpre[MAX_ROWS] = carry;               // tile total
     }
     __syncthreads();
-}
-
-// Store tile values to the region's output.  Tile covers region-relative positions
-// [t0, t0 + tlen); value(k) = add[k / seg_len] + vals[k] for k relative to the tile.
-// Output index of region position q is q ('+') or L-1-q ('-').  `tid`/`nthreads` describe the
-// cooperating threads (a CTA or one warp).  dst is 16-byte aligned at index 0.
-// value(k) = base + vals[k] (+ seg_add[k / ROW] when HAS_SEG).
-template <bool HAS_SEG>
-__device__ __forceinline__ void store_tile(int32_t* __restrict__ dst, int L, bool rev, int t0,
-                                           int tlen, const int* vals, const int* seg_add,
-                                           int base, int tid, int nthreads) {
-    const int o_lo = rev ? (L - t0 - tlen) : t0;
-    const int o_hi = o_lo + tlen;
-    for (int g = (o_lo & ~3) + 4 * tid; g < o_hi; g += 4 * nthreads) {
-        int v[4];
-        bool ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int o = g + q;
-            ok[q] = (o >= o_lo) && (o < o_hi);
-            const int k = rev ? (L - 1 - o - t0) : (o - t0);
-            v[q] = 0;
-            if (ok[q]) v[q] = base + vals[k] + (HAS_SEG ? seg_add[k / ROW] : 0);
-        }
-        if (ok[0] && ok[3]) {
-            *reinterpret_cast<int4*>(dst + g) = make_int4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (ok[q]) dst[g + q] = v[q];
-        }
-    }
+    const int top = rev ? base + rowpre[MAX_ROWS] : base;
+    for (int row = warp; row < nrows; row += WARPS)            // pass B: scan + store
+        warp_row_scan_store(diff + row * ROW, rowpre[row], top, rev, tlen - row * ROW,
+                            dst + row * ROW);
 }
 
 // ---- warp-per-region kernel (L <= SMALL_MAX) -----------------------------------------------
@@ -304,7 +290,7 @@ template <int NS>
 __global__ void __launch_bounds__(CTA)
 cov_small_kernel(int64_t R, RegionArrays ra, Sources<NS> src, const int64_t* __restrict__ off,
                  int32_t* __restrict__ cov) {
-    __shared__ __align__(16) int sm[WARPS][SMALL_MAX + ROW];
+    __shared__ __align__(16) int sm[WARPS][SMALL_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * WARPS + warp;
     if (r >= R) return;
@@ -318,40 +304,49 @@ cov_small_kernel(int64_t R, RegionArrays ra, Sources<NS> src, const int64_t* __r
     const uint32_t gs = ra.gs[r];
     const unsigned flags = ra.flags[r];
     const unsigned mask = flags >> 1;
-    int base = 0;
+    const bool rev = (flags & 1u) != 0;
+    const uint32_t last = (uint32_t)(L - 1);
+    int base = 0, total = 0;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
         if (!((mask >> src.cls_bit[k]) & 1u)) continue;
         const uint32_t x0 = ra.ix0[r * NS + k], x1 = ra.ix1[r * NS + k];
         const uint32_t y0 = ra.iy0[r * NS + k], y1 = ra.iy1[r * NS + k];
         base += (int)(x0 - y0);
+        total += (int)(x1 - x0) - (int)(y1 - y0);
         for (uint32_t i0 = x0; i0 < x1; i0 += 32) {
             const uint32_t i = i0 + lane;
             const bool ok = i < x1;
-            const uint32_t p = ok ? (__ldg(src.xs[k] + i) - gs) : 0u;
+            uint32_t p = ok ? (__ldg(src.xs[k] + i) - gs) : 0u;
+            if (rev) p = last - p;
             warp_aggregated_add(diff, p, ok, +1);
         }
         for (uint32_t i0 = y0; i0 < y1; i0 += 32) {
             const uint32_t i = i0 + lane;
             const bool ok = i < y1;
-            const uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gs) : 0u;
+            uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gs) : 0u;
+            if (rev) p = last - p;
             warp_aggregated_add(diff, p, ok, -1);
         }
     }
     __syncwarp();
-    warp_scan_rows(diff, nrows);
-    __syncwarp();
-    store_tile<false>(cov + off[r], L, (flags & 1u) != 0, 0, L, diff, nullptr, base, lane, 32);
+    int32_t* dst = cov + off[r];
+    const int top = rev ? base + total : base;
+    int pre = 0;
+    for (int row = 0; row < nrows; row++)
+        pre += warp_row_scan_store(diff + row * ROW, pre, top, rev, L - row * ROW, dst + row * ROW);
 }
 
 // ---- CTA-per-tile kernel --------------------------------------------------------------------
+// Tiles are cut in OUTPUT space (tile j = outputs [j*tile_len, ...)), so a '-' region's tile j
+// covers the genomic positions [L - o_hi, L - o_lo).
 template <int NS>
 __global__ void __launch_bounds__(CTA)
 cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restrict__ tile_off,
                 RegionArrays ra, Sources<NS> src, const int64_t* __restrict__ off,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
-    __shared__ int rowpre[MAX_ROWS];
+    __shared__ int rowpre[MAX_ROWS + 1];
     __shared__ uint32_t bnd[4 * NS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t r = tile_region[blockIdx.x];
@@ -359,11 +354,14 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
     const int L = ra.len[r];
     const int m = (L + TILE - 1) / TILE;
     const int tile_len = (((L + m - 1) / m) + ROW - 1) / ROW * ROW;
-    const int t0 = j * tile_len;
-    const int tlen = min(tile_len, L - t0);
-    const uint32_t gts = ra.gs[r] + (uint32_t)t0;
+    const int o_lo = j * tile_len;
+    const int tlen = min(tile_len, L - o_lo);
     const unsigned flags = ra.flags[r];
     const unsigned mask = flags >> 1;
+    const bool rev = (flags & 1u) != 0;
+    const int q0 = rev ? (L - o_lo - tlen) : o_lo;          // genomic offset of the tile
+    const uint32_t gts = ra.gs[r] + (uint32_t)q0;
+    const uint32_t last = (uint32_t)(tlen - 1);
     // slice bounds of this tile, searched warp-wide inside the region's own slices
     for (int q = warp; q < 4 * NS; q += WARPS) {
         const int k = q >> 2, which = q & 3;
@@ -393,19 +391,20 @@ cov_tile_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
         for (uint32_t i0 = x0 + warp * 32; i0 < x1; i0 += CTA) {
             const uint32_t i = i0 + lane;
             const bool ok = i < x1;
-            const uint32_t p = ok ? (__ldg(src.xs[k] + i) - gts) : 0u;
+            uint32_t p = ok ? (__ldg(src.xs[k] + i) - gts) : 0u;
+            if (rev) p = last - p;
             warp_aggregated_add(diff, p, ok, +1);
         }
         for (uint32_t i0 = y0 + warp * 32; i0 < y1; i0 += CTA) {
             const uint32_t i = i0 + lane;
             const bool ok = i < y1;
-            const uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gts) : 0u;
+            uint32_t p = ok ? (__ldg(src.ye[k] + i) + src.yshift[k] - gts) : 0u;
+            if (rev) p = last - p;
             warp_aggregated_add(diff, p, ok, -1);
         }
     }
     __syncthreads();
-    block_scan_rows(diff, nrows, rowpre);
-    store_tile<true>(cov + off[r], L, (flags & 1u) != 0, t0, tlen, diff, rowpre, base, tid, CTA);
+    block_scan_store(diff, tlen, base, rev, rowpre, cov + off[r] + o_lo);
 }
 
 // ---- GRangesList elements -------------------------------------------------------------------
@@ -536,15 +535,17 @@ cov_list_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
                 int ignore_strand, int strand_filter, const int64_t* __restrict__ off,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
-    __shared__ int rowpre[MAX_ROWS];
+    __shared__ int rowpre[MAX_ROWS + 1];
     const int tid = threadIdx.x;
     const int64_t g = tile_region[blockIdx.x];
     const int j = (int)((int64_t)blockIdx.x - tile_off[g]);
     const int L = la.len[g];
     const int m = (L + TILE - 1) / TILE;
     const int tile_len = (((L + m - 1) / m) + ROW - 1) / ROW * ROW;
-    const int t0 = j * tile_len;
-    const int tlen = min(tile_len, L - t0);
+    const int o_lo = j * tile_len;
+    const int tlen = min(tile_len, L - o_lo);
+    const bool rev = (la.flags[g] & 1u) != 0;
+    const int t0 = rev ? (L - o_lo - tlen) : o_lo;          // stitched offset of the tile
     const int t1 = t0 + tlen - 1;
     const int nrows = (tlen + ROW - 1) / ROW;
     for (int i = tid; i < nrows * (ROW / 4); i += CTA)
@@ -576,13 +577,19 @@ cov_list_kernel(const int32_t* __restrict__ tile_region, const int64_t* __restri
             const int pa = xo + (int)(max(rs, s) - s);
             const int pb = xo + (int)(min(re1 - 1u, e) - s);
             if (pb < t0 || pa > t1) continue;
-            atomicAdd(diff + (max(pa, t0) - t0), mult);
-            if (pb + 1 <= t1) atomicSub(diff + (pb + 1 - t0), mult);
+            // +mult on [max(pa,t0), min(pb,t1)] of the stitched vector, in output order
+            const int ka = max(pa, t0) - t0, kb1 = pb + 1 - t0;       // kb1 may equal tlen
+            if (!rev) {
+                atomicAdd(diff + ka, mult);
+                if (kb1 < tlen) atomicSub(diff + kb1, mult);
+            } else {
+                atomicAdd(diff + (tlen - 1 - ka), mult);
+                if (kb1 < tlen) atomicSub(diff + (tlen - 1 - kb1), mult);
+            }
         }
     }
     __syncthreads();
-    block_scan_rows(diff, nrows, rowpre);
-    store_tile<true>(cov + off[g], L, (la.flags[g] & 1u) != 0, t0, tlen, diff, rowpre, 0, tid, CTA);
+    block_scan_store(diff, tlen, 0, rev, rowpre, cov + off[g] + o_lo);
 }
 
 // ---- c(left, center, right) -----------------------------------------------------------------

@@ -51,15 +51,18 @@ __device__ __forceinline__ bool map_read(int c, int64_t s, int64_t e, int st, in
     return true;
 }
 
+// VEC = 4: every thread maps four consecutive reads with 16-byte loads/stores (all arrays
+// 16-byte aligned, checked on the host); the n % 4 tail and VEC = 1 use scalar accesses.
+template <int VEC>
 __global__ void __launch_bounds__(TPB)
 reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                        const int8_t* __restrict__ strand, const uint32_t* __restrict__ chrom_off,
                        const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
                        uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
-                       int8_t* __restrict__ strand_out, unsigned int* __restrict__ err,
-                       unsigned long long* __restrict__ cls_count, ExcBuf exc) {
-    const int64_t stride = (int64_t)gridDim.x * TPB;
+                       uint32_t* __restrict__ xs_out, int8_t* __restrict__ strand_out,
+                       unsigned int* __restrict__ err, unsigned long long* __restrict__ cls_count,
+                       ExcBuf exc) {
     unsigned int my_err = 0;
     unsigned int np = 0, nm = 0, ns = 0;
     // candidate common width: the fragment length, else the width of read 0
@@ -72,26 +75,53 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
             w = b - a;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *exc.w_out = w;
-    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-        const int st = strand ? (int)strand[i] : 0;
-        uint32_t gs = 0, ge1 = 0;
-        if (map_read(chrom[i], start[i], end[i], st, n_chrom, chrom_off, chrom_len, frag_len, &gs,
-                     &ge1, &my_err)) {
-            if (ge1 - gs != w) {
+
+    auto one = [&](int c, int s, int e, int st, uint32_t* gs, uint32_t* ge1) {
+        *gs = 0;
+        *ge1 = 0;
+        if (map_read(c, s, e, st, n_chrom, chrom_off, chrom_len, frag_len, gs, ge1, &my_err)) {
+            if (*ge1 - *gs != w) {
                 const unsigned int k = atomicAdd(exc.count, 1u);
                 if (k < exc.cap) {
-                    exc.xw[k] = gs + w;
-                    exc.e1[k] = ge1;
+                    exc.xw[k] = *gs + w;
+                    exc.e1[k] = *ge1;
                     exc.st[k] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
                 }
             }
         }
-        g_start[i] = gs;
-        g_end1[i] = ge1;
-        if (strand_out) strand_out[i] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
         np += st > 0;
         nm += st < 0;
         ns += st == 0;
+    };
+    auto sgn = [](int st) { return (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0)); };
+
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    const int64_t n_vec = (VEC == 4) ? (n >> 2) : 0;
+    for (int64_t v = (int64_t)blockIdx.x * TPB + threadIdx.x; v < n_vec; v += stride) {
+        const int4 c4 = __ldg(reinterpret_cast<const int4*>(chrom) + v);
+        const int4 s4 = __ldg(reinterpret_cast<const int4*>(start) + v);
+        const int4 e4 = __ldg(reinterpret_cast<const int4*>(end) + v);
+        char4 t4 = make_char4(0, 0, 0, 0);
+        if (strand) t4 = __ldg(reinterpret_cast<const char4*>(strand) + v);
+        uint4 gs, ge;
+        one(c4.x, s4.x, e4.x, t4.x, &gs.x, &ge.x);
+        one(c4.y, s4.y, e4.y, t4.y, &gs.y, &ge.y);
+        one(c4.z, s4.z, e4.z, t4.z, &gs.z, &ge.z);
+        one(c4.w, s4.w, e4.w, t4.w, &gs.w, &ge.w);
+        reinterpret_cast<uint4*>(g_start)[v] = gs;
+        reinterpret_cast<uint4*>(g_end1)[v] = ge;
+        reinterpret_cast<uint4*>(xs_out)[v] = gs;
+        if (strand_out)
+            reinterpret_cast<char4*>(strand_out)[v] = make_char4(sgn(t4.x), sgn(t4.y), sgn(t4.z), sgn(t4.w));
+    }
+    for (int64_t i = n_vec * 4 + (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+        const int st = strand ? (int)strand[i] : 0;
+        uint32_t gs, ge1;
+        one(chrom[i], start[i], end[i], st, &gs, &ge1);
+        g_start[i] = gs;
+        g_end1[i] = ge1;
+        xs_out[i] = gs;
+        if (strand_out) strand_out[i] = sgn(st);
     }
     // block-level reduction of the three strand counters and the error mask
     __shared__ unsigned int sh[4];
@@ -320,9 +350,11 @@ int reads_build_class(ReadsIdx& r, int cls) {
     const bool uni = r.uniform_w != 0;   // ye == xs + w: no second array, no second sort
     if (cls == CLS_ALL) {
         sc.n = r.n;
-        RCP_TRY(dalloc(&sc.xs, (size_t)r.n));
-        RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
-                                 g_ctx.stream));
+        if (sc.xs == nullptr) {    // normally pre-filled by the map kernel (reads_load_impl)
+            RCP_TRY(dalloc(&sc.xs, (size_t)r.n));
+            RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
+                                     g_ctx.stream));
+        }
         if (!uni) {
             RCP_TRY(dalloc(&sc.ye, (size_t)r.n));
             RCP_CUDA(cudaMemcpyAsync(sc.ye, r.g_end1, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
@@ -475,11 +507,23 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     exc.st = r.exc_st;
     exc.count = d_w;
     exc.w_out = d_w + 1;
+    RCP_TRY(dalloc(&r.cls[CLS_ALL].xs, (size_t)n));    // unsorted copy of g_start, sorted below
     if (n > 0) {
         StageTimer t(ST_INDEX_MAP);
-        reads_to_global_kernel<<<grid_for(n), TPB, 0, g_ctx.stream>>>(
-            n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
-            n_chrom, frag_len, r.g_start, r.g_end1, r.d_strand, d_err, d_cnt, exc);
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        const bool vec = al16(d_chrom.ptr) && al16(d_start.ptr) && al16(d_end.ptr) &&
+                         (d_strand.ptr == nullptr || (reinterpret_cast<uintptr_t>(d_strand.ptr) & 3u) == 0);
+        const unsigned grid = grid_for(vec ? (n + 3) / 4 : n);
+        if (vec)
+            reads_to_global_kernel<4><<<grid, TPB, 0, g_ctx.stream>>>(
+                n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
+                n_chrom, frag_len, r.g_start, r.g_end1, r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt,
+                exc);
+        else
+            reads_to_global_kernel<1><<<grid, TPB, 0, g_ctx.stream>>>(
+                n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
+                n_chrom, frag_len, r.g_start, r.g_end1, r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt,
+                exc);
         RCP_LAUNCHED();
     }
     unsigned int h_err = 0, h_w[2] = {0, 0};

@@ -49,9 +49,36 @@ struct BinArgs {
     unsigned int* short_count;
 };
 
+constexpr int STAGE_INTS = 12288;      // ints of one region staged in shared memory (48 KB)
+constexpr int STAGE_MAX_BIN = 128;     // bins narrower than this use the staged path
+
+// Sum of src[lo, hi) by one warp with 16-byte loads where the index is 4-aligned (src itself is
+// 128-byte aligned: region offsets are multiples of 32 ints).
+__device__ __forceinline__ long long warp_range_sum(const int32_t* __restrict__ src, int lo, int hi) {
+    const int lane = threadIdx.x & 31;
+    long long s = 0;
+    const int a4 = (lo + 3) & ~3, b4 = hi & ~3;
+    if (a4 >= b4) {
+        for (int q = lo + lane; q < hi; q += 32) s += __ldg(src + q);
+    } else {
+        if (lo + lane < a4) s += __ldg(src + lo + lane);
+        const int4* v = reinterpret_cast<const int4*>(src + a4);
+        const int nv = (b4 - a4) >> 2;
+        for (int q = lane; q < nv; q += 32) {
+            const int4 x = __ldg(v + q);
+            s += (long long)x.x + x.y + x.z + x.w;
+        }
+        if (b4 + lane < hi) s += __ldg(src + b4 + lane);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return s;
+}
+
+// One CTA per region.  dynamic smem: edges[n + 1] (+ pad) then STAGE_INTS staging ints.
 template <bool MEDIAN>
 __global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
-    extern __shared__ int sh[];
+    extern __shared__ __align__(16) int sh[];
     int* edges = sh;                    // n + 1
     __shared__ int wcount[WARPS];
     __shared__ int chunk_carry;
@@ -96,61 +123,91 @@ __global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
     }
     if (tid == 0) edges[n] = sg.b;
     __syncthreads();
-    // ---- segmented reduction: groups of g lanes per bin ----
+    const int32_t* src = p.cov + p.off[r];
+    if (!MEDIAN && bsz < STAGE_MAX_BIN) {
+        // ---- narrow bins: stage a run of whole bins in shared memory with coalesced 16-byte
+        // loads, then ONE THREAD PER BIN sums from shared memory (rotated start -> no bank
+        // conflicts), so the instruction count per coverage base stays ~5 ----
+        int* stage = sh + ((n + 1 + 3) & ~3);
+        const int bins_per_chunk = (STAGE_INTS - 4) / (bsz + 1);
+        const bool rotate = (bsz & 1) == 0;     // even stride: offset the lanes by one each
+        for (int bin0 = 0; bin0 < n; bin0 += bins_per_chunk) {
+            const int bin1 = min(n, bin0 + bins_per_chunk);
+            const int lo_al = edges[bin0] & ~3;
+            const int nvec = (edges[bin1] - lo_al + 3) >> 2;    // <= STAGE_INTS / 4, inside the padded region
+            __syncthreads();
+            const int4* gsrc = reinterpret_cast<const int4*>(src + lo_al);
+            for (int i = tid; i < nvec; i += CTA) reinterpret_cast<int4*>(stage)[i] = __ldg(gsrc + i);
+            __syncthreads();
+            for (int b = bin0 + tid; b < bin1; b += CTA) {
+                const int e0 = edges[b], len = edges[b + 1] - e0;
+                const int* x = stage + (e0 - lo_al);
+                int q = rotate ? (tid % len) : 0;
+                long long sum = 0;
+                for (int it = 0; it < len; it++) {
+                    sum += x[q];
+                    q = (q + 1 == len) ? 0 : q + 1;
+                }
+                out[(int64_t)b * p.ld] = p.scale * ((double)sum / (double)len);
+            }
+        }
+        return;
+    }
+    if (!MEDIAN) {
+        // ---- wide bins: one warp per bin, coalesced 16-byte global loads ----
+        for (int i = warp; i < n; i += WARPS) {
+            const int lo = edges[i], hi = edges[i + 1];
+            const long long sum = warp_range_sum(src, lo, hi);
+            if (lane == 0) out[(int64_t)i * p.ld] = p.scale * ((double)sum / (double)(hi - lo));
+        }
+        return;
+    }
+    // ---- median: groups of g lanes per bin, exact order statistics by value bisection ----
     int g = 1;
     while (g < 32 && g < bsz) g <<= 1;
     const int per_warp = 32 / g;
     const int sub = lane / g, li = lane % g;
-    const int32_t* src = p.cov + p.off[r];
     for (int b0 = warp * per_warp; b0 < n; b0 += WARPS * per_warp) {
         const int i = b0 + sub;
         const bool ok = i < n;
         const int lo = ok ? edges[i] : 0, hi = ok ? edges[i + 1] : 0;
         const int cnt = hi - lo;
-        if (!MEDIAN) {
-            long long s = 0;
-            for (int q = lo + li; q < hi; q += g) s += __ldg(src + q);
-            for (int d = g >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (ok && li == 0) out[(int64_t)i * p.ld] = p.scale * ((double)s / (double)cnt);
-        } else {
-            // exact median by bisection on the value range: k-th smallest = least v with
-            // #{x <= v} >= k+1
-            int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
-            for (int q = lo + li; q < hi; q += g) {
-                const int v = __ldg(src + q);
-                vmin = min(vmin, v);
-                vmax = max(vmax, v);
-            }
-            for (int d = g >> 1; d > 0; d >>= 1) {
-                vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
-                vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-            }
-            const int k1 = (cnt - 1) / 2, k2 = cnt / 2;
-            int res[2];
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int k = t == 0 ? k1 : k2;
-                int a = vmin, b = vmax;          // answer in [a, b]
-                // all lanes of the WARP iterate the same number of times (shuffles are
-                // warp-wide): bound by the warp-wide maximum range
-                int span = ok ? (b - a) : 0;
-                for (int d = 16; d > 0; d >>= 1) span = max(span, __shfl_xor_sync(0xffffffffu, span, d));
-                while (span > 0) {
-                    const int mid = a + ((b - a) >> 1);
-                    int c = 0;
-                    for (int q = lo + li; q < hi; q += g) c += (__ldg(src + q) <= mid);
-                    for (int d = g >> 1; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                    if (a < b) {
-                        if (c >= k + 1) b = mid;
-                        else a = mid + 1;
-                    }
-                    span >>= 1;
-                }
-                res[t] = a;
-            }
-            if (ok && li == 0)
-                out[(int64_t)i * p.ld] = p.scale * (((double)res[0] + (double)res[1]) * 0.5);
+        // k-th smallest = least v with #{x <= v} >= k+1
+        int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
+        for (int q = lo + li; q < hi; q += g) {
+            const int v = __ldg(src + q);
+            vmin = min(vmin, v);
+            vmax = max(vmax, v);
         }
+        for (int d = g >> 1; d > 0; d >>= 1) {
+            vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+            vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+        }
+        const int k1 = (cnt - 1) / 2, k2 = cnt / 2;
+        int res[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int k = t == 0 ? k1 : k2;
+            int a = vmin, b = vmax;          // answer in [a, b]
+            // every lane of the WARP iterates the same number of times (the shuffles are
+            // warp-wide): bound by the warp-wide maximum range
+            int span = ok ? (b - a) : 0;
+            for (int d = 16; d > 0; d >>= 1) span = max(span, __shfl_xor_sync(0xffffffffu, span, d));
+            while (span > 0) {
+                const int mid = a + ((b - a) >> 1);
+                int c = 0;
+                for (int q = lo + li; q < hi; q += g) c += (__ldg(src + q) <= mid);
+                for (int d = g >> 1; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                if (a < b) {
+                    if (c >= k + 1) b = mid;
+                    else a = mid + 1;
+                }
+                span >>= 1;
+            }
+            res[t] = a;
+        }
+        if (ok && li == 0)
+            out[(int64_t)i * p.ld] = p.scale * (((double)res[0] + (double)res[1]) * 0.5);
     }
 }
 
@@ -394,8 +451,10 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
     a.ld = ld;
     a.short_list = short_list;
     a.short_count = short_count;
-    const size_t smem = ((size_t)n_bins + 1) * sizeof(int);
-    if (smem > 200 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than 51000 bins per segment");
+    // edges (padded to 16 B) + the staging buffer of the narrow-bin path
+    const size_t smem = (((size_t)n_bins + 1 + 3) & ~(size_t)3) * sizeof(int) +
+                        (stat == RCP_STAT_MEDIAN ? 0 : (size_t)STAGE_INTS * sizeof(int));
+    if (smem > 200 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than ~38000 bins per segment");
     {
     StageTimer t(ST_PROF_BIN);
     if (stat == RCP_STAT_MEDIAN) {
