@@ -25,6 +25,61 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// ---- device memory: stream-ordered pool + exact-size cache of large blocks ----
+static const size_t kBigBlock = 16u << 20;
+static const size_t kCacheLimit = 24ull << 30;
+static std::map<void*, size_t> g_big_live;            // large blocks handed out
+static std::multimap<size_t, void*> g_big_free;       // large blocks released, by size
+static size_t g_cached_bytes = 0;
+
+static void cache_release_all() {
+    for (auto& kv : g_big_free) cudaFreeAsync(kv.second, g_ctx.stream);
+    g_big_free.clear();
+    g_cached_bytes = 0;
+}
+
+int device_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes >= kBigBlock) {
+        auto it = g_big_free.find(bytes);
+        if (it != g_big_free.end()) {
+            *p = it->second;
+            g_cached_bytes -= bytes;
+            g_big_free.erase(it);
+            g_big_live[*p] = bytes;
+            return RCP_OK;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes, g_ctx.stream);
+    if (e != cudaSuccess && !g_big_free.empty()) {       // give the cache back and retry once
+        cudaGetLastError();
+        cache_release_all();
+        e = cudaMallocAsync(p, bytes, g_ctx.stream);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(RCP_ERR_CUDA, "device allocation of %zu bytes failed: %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    if (bytes >= kBigBlock) g_big_live[*p] = bytes;
+    return RCP_OK;
+}
+
+void device_free(void* p) {
+    if (!p) return;
+    auto it = g_big_live.find(p);
+    if (it != g_big_live.end()) {
+        const size_t bytes = it->second;
+        g_big_live.erase(it);
+        if (g_cached_bytes + bytes <= kCacheLimit) {
+            g_big_free.insert({bytes, p});
+            g_cached_bytes += bytes;
+            return;
+        }
+    }
+    cudaFreeAsync(p, g_ctx.stream);
+}
+
 // ---- stage timers ----
 static bool g_timing = false;
 struct TimerRec { int stage; cudaEvent_t a, b; };
@@ -288,6 +343,8 @@ int rcp_shutdown(void) {
     g_reads.clear();
     for (auto& kv : g_covs) coverage_release(*kv.second);
     g_covs.clear();
+    cache_release_all();
+    g_big_live.clear();
     drain_timers();
     g_timing = false;
     for (cudaEvent_t e : g_free_events) cudaEventDestroy(e);

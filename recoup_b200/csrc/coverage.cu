@@ -102,6 +102,8 @@ __device__ __forceinline__ unsigned class_mask(int region_strand, int ignore_str
 }
 
 // err bits: 1 chrom id out of range, 2 end < start - 1
+// One WARP per region: the five searches per source run as 32-ary warp searches (6 dependent
+// loads over 50 M reads instead of 26), which is what bounds this latency-bound kernel.
 template <int NS>
 __global__ void __launch_bounds__(CTA)
 region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
@@ -110,58 +112,62 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
                    int n_chrom, Sources<NS> src, int ignore_strand, int strand_filter,
                    RegionArrays out, unsigned int* __restrict__ err,
                    unsigned long long* __restrict__ stats /* [0] n_null, [1] total_len */) {
-    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
-    unsigned long long my_null = 0, my_len = 0;
-    if (r < R) {
-        const int c = chrom[r];
-        int64_t s = start[r], e = end[r];
-        const int st = strand ? (int)strand[r] : 0;
-        bool null = false;
-        uint32_t gs = 0;
-        int64_t L = 0;
-        unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
-        if (c < 0 || c >= n_chrom) {
-            atomicOr(err, 1u);
-            null = true;
-        } else if (e < s - 1) {
-            atomicOr(err, 2u);
-            null = true;
-        } else {
-            // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start
-            // mixes signs, an end past the chromosome is out of bounds -> tryCatch -> NULL;
-            // a zero index is silently dropped.
-            if (s < 0 || e > chrom_len[c]) null = true;
-            if (s == 0) s = 1;
-            L = e - s + 1;
-            if (L <= 0) { L = 0; null = true; }
-            gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
-        }
-        if (!null) {
-            const uint32_t ge = gs + (uint32_t)(L - 1);
-            long long nov = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const int c = chrom[r];
+    int64_t s = start[r], e = end[r];
+    const int st = strand ? (int)strand[r] : 0;
+    bool null = false;
+    uint32_t gs = 0;
+    int64_t L = 0;
+    const unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
+    if (c < 0 || c >= n_chrom) {
+        if (lane == 0) atomicOr(err, 1u);
+        null = true;
+    } else if (e < s - 1) {
+        if (lane == 0) atomicOr(err, 2u);
+        null = true;
+    } else {
+        // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start mixes
+        // signs, an end past the chromosome is out of bounds -> tryCatch -> NULL; a zero index
+        // is silently dropped.
+        if (s < 0 || e > chrom_len[c]) null = true;
+        if (s == 0) s = 1;
+        L = e - s + 1;
+        if (L <= 0) { L = 0; null = true; }
+        gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
+    }
+    if (!null) {
+        const uint32_t ge = gs + (uint32_t)(L - 1);
+        long long nov = 0;
 #pragma unroll
-            for (int k = 0; k < NS; k++) {
-                uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-                if ((mask >> src.cls_bit[k]) & 1u) {
-                    const uint32_t n = src.n[k];
-                    x0 = lower_bound_u32(src.xs[k], 0, n, gs);
-                    x1 = lower_bound_u32(src.xs[k], x0, n, ge + 1u);
-                    const uint32_t sh = src.yshift[k];
-                    y0 = lower_bound_u32(src.ye[k], 0, n, gs, sh);
-                    const uint32_t yov = lower_bound_u32(src.ye[k], y0, n, gs + 1u, sh);
-                    y1 = lower_bound_u32(src.ye[k], yov, n, ge + 1u, sh);
-                    // reads overlapping the window: #{start <= ge} - #{end < gs}.  A correction
-                    // source only moves end events, so both of its counts are taken at gs.
-                    const uint32_t xov = src.corr[k] ? lower_bound_u32(src.xs[k], x0, x1, gs + 1u) : x1;
-                    nov += (long long)xov - (long long)yov;
-                }
+        for (int k = 0; k < NS; k++) {
+            uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+            if ((mask >> src.cls_bit[k]) & 1u) {
+                const uint32_t n = src.n[k];
+                const uint32_t sh = src.yshift[k];
+                x0 = warp_lower_bound_u32(src.xs[k], 0, n, gs, 0);
+                x1 = warp_lower_bound_u32(src.xs[k], x0, n, ge + 1u, 0);
+                y0 = warp_lower_bound_u32(src.ye[k], 0, n, gs, sh);
+                const uint32_t yov = warp_lower_bound_u32(src.ye[k], y0, n, gs + 1u, sh);
+                y1 = warp_lower_bound_u32(src.ye[k], yov, n, ge + 1u, sh);
+                // reads overlapping the window: #{start <= ge} - #{end < gs}.  A correction
+                // source only moves end events, so both of its counts are taken at gs.
+                const uint32_t xov =
+                    src.corr[k] ? warp_lower_bound_u32(src.xs[k], x0, x1, gs + 1u, 0) : x1;
+                nov += (long long)xov - (long long)yov;
+            }
+            if (lane == 0) {
                 out.ix0[r * NS + k] = x0;
                 out.ix1[r * NS + k] = x1;
                 out.iy0[r * NS + k] = y0;
                 out.iy1[r * NS + k] = y1;
             }
-            if (nov <= 0) null = true;          // coverage.R:198,224-225
         }
+        if (nov <= 0) null = true;          // coverage.R:198,224-225
+    }
+    if (lane == 0) {
         const int32_t len = null ? 0 : (int32_t)L;
         out.gs[r] = gs;
         out.len[r] = len;
@@ -169,16 +175,8 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
         out.is_null[r] = null ? 1 : 0;
         out.padded[r] = ((int64_t)len + PAD - 1) / PAD * PAD;
         out.ntiles[r] = len > SMALL_MAX ? ((int64_t)len + TILE - 1) / TILE : 0;
-        my_null = null ? 1 : 0;
-        my_len = (unsigned long long)len;
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
-        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (my_null) atomicAdd(&stats[0], my_null);
-        if (my_len) atomicAdd(&stats[1], my_len);
+        if (null) atomicAdd(&stats[0], 1ull);
+        else atomicAdd(&stats[1], (unsigned long long)len);
     }
 }
 
@@ -686,7 +684,7 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
     {
         StageTimer t(ST_COV_PLAN);
         if (R > 0) {
-            region_plan_kernel<NS><<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
+            region_plan_kernel<NS><<<blocks_for(R, WARPS), CTA, 0, g_ctx.stream>>>(
                 R, chrom, start, end, strand, rd.d_chrom_off, rd.d_chrom_len, rd.n_chrom, src,
                 ignore_strand, strand_filter, ra, d_err, d_stats);
             RCP_LAUNCHED();

@@ -68,20 +68,22 @@ struct StageTimer {
     ~StageTimer();
 };
 
-// stream-ordered device allocation on the library stream
+// Stream-ordered device allocation on the library stream.  Blocks of >= 16 MB are recycled by an
+// exact-size cache inside the library (api.cu): every use is ordered on the single library
+// stream, so handing a just-released block to the next request is safe and avoids the
+// re-mapping work cudaMallocAsync does for very large blocks.
+int device_alloc(void** p, size_t bytes);
+void device_free(void* p);
+
 template <class T>
 inline int dalloc(T** p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMallocAsync((void**)p, n * sizeof(T), g_ctx.stream);
-    if (e != cudaSuccess)
-        return fail(RCP_ERR_CUDA, "device allocation of %zu bytes failed: %s", n * sizeof(T),
-                    cudaGetErrorString(e));
-    return RCP_OK;
+    return device_alloc((void**)p, n * sizeof(T));
 }
 template <class T>
 inline void dfree(T*& p) {
-    if (p) cudaFreeAsync((void*)p, g_ctx.stream);
+    if (p) device_free((void*)p);
     p = nullptr;
 }
 
