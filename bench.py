@@ -471,10 +471,14 @@ def run_b200(args):
         dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
         roof = None
         if dom and alg.get(dom):
-            ach = alg[dom] / (own[dom][0] * 1e-3) / 1e9
+            # the stage's algorithmic bytes for ONE step over the stage's device time in one
+            # step (a stage may be several launches of the same kernel, e.g. one per segment)
+            per_step_ms = own[dom][0] * own[dom][1] / args.steps
+            ach = alg[dom] / (per_step_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                    "ms_per_launch": own[dom][0], "algorithmic_bytes": alg[dom]}
+                    "ms_per_step": per_step_ms, "launches_per_step": own[dom][1] / args.steps,
+                    "algorithmic_bytes": alg[dom]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -81,6 +81,12 @@ int rcp_sync(void);
 /* Kernels launched by this library since rcp_init / the last reset (bench.py "gpu_launches"). */
 int64_t rcp_launch_count(int reset);
 
+/* Page-locked host buffers for outputs (profile matrices): device->host copies into them run at
+ * full PCIe rate.  Released buffers are kept by the library and handed out again on an
+ * exact-size match, so a loop over samples pays the page-locking cost once. */
+int rcp_host_alloc(int64_t bytes, void** ptr_out);
+int rcp_host_free(void* ptr);
+
 /* Optional CUDA-event timing of the library's stages on its own stream (bench.py roofline).
  * rcp_timing_read synchronises, then reports accumulated milliseconds / launches per stage
  * (stage i is named rcp_timing_stage_name(i); NULL past the last stage). */

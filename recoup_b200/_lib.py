@@ -36,6 +36,8 @@ SIGNATURES = {
     "rcp_stream": (C.c_void_p, []),
     "rcp_sync": (C.c_int, []),
     "rcp_launch_count": (C.c_int64, [C.c_int]),
+    "rcp_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "rcp_host_free": (C.c_int, [C.c_void_p]),
     "rcp_timing_enable": (C.c_int, [C.c_int]),
     "rcp_timing_read": (C.c_int, [C.c_int, C.c_int, _f64p, _i64p]),
     "rcp_timing_stage_name": (C.c_char_p, [C.c_int]),

@@ -80,6 +80,18 @@ void device_free(void* p) {
     cudaFreeAsync(p, g_ctx.stream);
 }
 
+// ---- pinned host buffers with exact-size reuse ----
+static std::map<void*, size_t> g_host_live;
+static std::multimap<size_t, void*> g_host_free;
+static size_t g_host_cached = 0;
+static const size_t kHostCacheLimit = 32ull << 30;
+
+static void host_cache_release_all() {
+    for (auto& kv : g_host_free) cudaFreeHost(kv.second);
+    g_host_free.clear();
+    g_host_cached = 0;
+}
+
 // ---- stage timers ----
 static bool g_timing = false;
 struct TimerRec { int stage; cudaEvent_t a, b; };
@@ -345,6 +357,7 @@ int rcp_shutdown(void) {
     g_covs.clear();
     cache_release_all();
     g_big_live.clear();
+    host_cache_release_all();
     drain_timers();
     g_timing = false;
     for (cudaEvent_t e : g_free_events) cudaEventDestroy(e);
@@ -370,6 +383,45 @@ void* rcp_stream(void) { return g_ctx.ready ? (void*)g_ctx.stream : nullptr; }
 int rcp_sync(void) {
     RCP_TRY(require_ready());
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return RCP_OK;
+}
+
+int rcp_host_alloc(int64_t bytes, void** ptr_out) {
+    RCP_TRY(require_ready());
+    if (bytes < 0 || ptr_out == nullptr) return fail(RCP_ERR_ARG, "rcp_host_alloc: bad argument");
+    const size_t b = bytes > 0 ? (size_t)bytes : 1;
+    auto it = g_host_free.find(b);
+    if (it != g_host_free.end()) {
+        *ptr_out = it->second;
+        g_host_cached -= b;
+        g_host_free.erase(it);
+    } else {
+        cudaError_t e = cudaHostAlloc(ptr_out, b, cudaHostAllocDefault);
+        if (e != cudaSuccess && !g_host_free.empty()) {
+            cudaGetLastError();
+            host_cache_release_all();
+            e = cudaHostAlloc(ptr_out, b, cudaHostAllocDefault);
+        }
+        if (e != cudaSuccess)
+            return fail(RCP_ERR_CUDA, "pinned host allocation of %zu bytes failed: %s", b,
+                        cudaGetErrorString(e));
+    }
+    g_host_live[*ptr_out] = b;
+    return RCP_OK;
+}
+
+int rcp_host_free(void* ptr) {
+    if (!ptr) return RCP_OK;
+    auto it = g_host_live.find(ptr);
+    if (it == g_host_live.end()) return fail(RCP_ERR_HANDLE, "rcp_host_free: unknown buffer");
+    const size_t b = it->second;
+    g_host_live.erase(it);
+    if (g_ctx.ready && g_host_cached + b <= kHostCacheLimit) {
+        g_host_free.insert({b, ptr});
+        g_host_cached += b;
+    } else {
+        cudaFreeHost(ptr);
+    }
     return RCP_OK;
 }
 

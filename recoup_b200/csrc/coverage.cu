@@ -101,9 +101,38 @@ __device__ __forceinline__ unsigned class_mask(int region_strand, int ignore_str
     return m;
 }
 
+// lower_bound started from a nearby position `hint` (exponential probe, then bisection): the
+// five ranks a region needs lie within a few hundred reads of each other.
+__device__ __forceinline__ uint32_t gallop_lower_bound_u32(const uint32_t* __restrict__ a,
+                                                           uint32_t n, uint32_t hint,
+                                                           uint32_t key, uint32_t shift) {
+    if (n == 0) return 0;
+    if (hint >= n) hint = n - 1;
+    uint32_t lo, hi;
+    if (__ldg(a + hint) + shift < key) {          // answer in (hint, n]
+        lo = hint + 1;
+        uint32_t step = 1;
+        while (lo + step <= n && __ldg(a + lo + step - 1) + shift < key) {
+            lo += step;
+            step <<= 1;
+        }
+        hi = min(lo + step, n);
+        // invariant: everything before lo is < key; a[hi-1] >= key or hi == n
+    } else {                                      // answer in [0, hint]
+        hi = hint;
+        uint32_t step = 1;
+        while (hi >= step && __ldg(a + hi - step) + shift >= key) {
+            hi -= step;
+            step <<= 1;
+        }
+        lo = hi >= step ? hi - step + 1 : 0;
+    }
+    return lower_bound_u32(a, lo, hi, key, shift);
+}
+
 // err bits: 1 chrom id out of range, 2 end < start - 1
-// One WARP per region: the five searches per source run as 32-ary warp searches (6 dependent
-// loads over 50 M reads instead of 26), which is what bounds this latency-bound kernel.
+// One thread per region.  Only the first rank is a full-range bisection; the other four gallop
+// from it.
 template <int NS>
 __global__ void __launch_bounds__(CTA)
 region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
@@ -112,62 +141,58 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
                    int n_chrom, Sources<NS> src, int ignore_strand, int strand_filter,
                    RegionArrays out, unsigned int* __restrict__ err,
                    unsigned long long* __restrict__ stats /* [0] n_null, [1] total_len */) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (r >= R) return;
-    const int c = chrom[r];
-    int64_t s = start[r], e = end[r];
-    const int st = strand ? (int)strand[r] : 0;
-    bool null = false;
-    uint32_t gs = 0;
-    int64_t L = 0;
-    const unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
-    if (c < 0 || c >= n_chrom) {
-        if (lane == 0) atomicOr(err, 1u);
-        null = true;
-    } else if (e < s - 1) {
-        if (lane == 0) atomicOr(err, 2u);
-        null = true;
-    } else {
-        // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start mixes
-        // signs, an end past the chromosome is out of bounds -> tryCatch -> NULL; a zero index
-        // is silently dropped.
-        if (s < 0 || e > chrom_len[c]) null = true;
-        if (s == 0) s = 1;
-        L = e - s + 1;
-        if (L <= 0) { L = 0; null = true; }
-        gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
-    }
-    if (!null) {
-        const uint32_t ge = gs + (uint32_t)(L - 1);
-        long long nov = 0;
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    unsigned long long my_null = 0, my_len = 0;
+    if (r < R) {
+        const int c = chrom[r];
+        int64_t s = start[r], e = end[r];
+        const int st = strand ? (int)strand[r] : 0;
+        bool null = false;
+        uint32_t gs = 0;
+        int64_t L = 0;
+        const unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
+        if (c < 0 || c >= n_chrom) {
+            atomicOr(err, 1u);
+            null = true;
+        } else if (e < s - 1) {
+            atomicOr(err, 2u);
+            null = true;
+        } else {
+            // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start
+            // mixes signs, an end past the chromosome is out of bounds -> tryCatch -> NULL;
+            // a zero index is silently dropped.
+            if (s < 0 || e > chrom_len[c]) null = true;
+            if (s == 0) s = 1;
+            L = e - s + 1;
+            if (L <= 0) { L = 0; null = true; }
+            gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
+        }
+        if (!null) {
+            const uint32_t ge = gs + (uint32_t)(L - 1);
+            long long nov = 0;
 #pragma unroll
-        for (int k = 0; k < NS; k++) {
-            uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-            if ((mask >> src.cls_bit[k]) & 1u) {
-                const uint32_t n = src.n[k];
-                const uint32_t sh = src.yshift[k];
-                x0 = warp_lower_bound_u32(src.xs[k], 0, n, gs, 0);
-                x1 = warp_lower_bound_u32(src.xs[k], x0, n, ge + 1u, 0);
-                y0 = warp_lower_bound_u32(src.ye[k], 0, n, gs, sh);
-                const uint32_t yov = warp_lower_bound_u32(src.ye[k], y0, n, gs + 1u, sh);
-                y1 = warp_lower_bound_u32(src.ye[k], yov, n, ge + 1u, sh);
-                // reads overlapping the window: #{start <= ge} - #{end < gs}.  A correction
-                // source only moves end events, so both of its counts are taken at gs.
-                const uint32_t xov =
-                    src.corr[k] ? warp_lower_bound_u32(src.xs[k], x0, x1, gs + 1u, 0) : x1;
-                nov += (long long)xov - (long long)yov;
-            }
-            if (lane == 0) {
+            for (int k = 0; k < NS; k++) {
+                uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+                if ((mask >> src.cls_bit[k]) & 1u) {
+                    const uint32_t n = src.n[k];
+                    const uint32_t sh = src.yshift[k];
+                    x0 = lower_bound_u32(src.xs[k], 0, n, gs);
+                    x1 = gallop_lower_bound_u32(src.xs[k], n, x0, ge + 1u, 0);
+                    y0 = gallop_lower_bound_u32(src.ye[k], n, x0, gs, sh);
+                    const uint32_t yov = gallop_lower_bound_u32(src.ye[k], n, y0, gs + 1u, sh);
+                    y1 = gallop_lower_bound_u32(src.ye[k], n, x1, ge + 1u, sh);
+                    // reads overlapping the window: #{start <= ge} - #{end < gs}.  A correction
+                    // source only moves end events, so both of its counts are taken at gs.
+                    const uint32_t xov = src.corr[k] ? lower_bound_u32(src.xs[k], x0, x1, gs + 1u) : x1;
+                    nov += (long long)xov - (long long)yov;
+                }
                 out.ix0[r * NS + k] = x0;
                 out.ix1[r * NS + k] = x1;
                 out.iy0[r * NS + k] = y0;
                 out.iy1[r * NS + k] = y1;
             }
+            if (nov <= 0) null = true;          // coverage.R:198,224-225
         }
-        if (nov <= 0) null = true;          // coverage.R:198,224-225
-    }
-    if (lane == 0) {
         const int32_t len = null ? 0 : (int32_t)L;
         out.gs[r] = gs;
         out.len[r] = len;
@@ -175,8 +200,16 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
         out.is_null[r] = null ? 1 : 0;
         out.padded[r] = ((int64_t)len + PAD - 1) / PAD * PAD;
         out.ntiles[r] = len > SMALL_MAX ? ((int64_t)len + TILE - 1) / TILE : 0;
-        if (null) atomicAdd(&stats[0], 1ull);
-        else atomicAdd(&stats[1], (unsigned long long)len);
+        my_null = null ? 1 : 0;
+        my_len = (unsigned long long)len;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
+        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_null) atomicAdd(&stats[0], my_null);
+        if (my_len) atomicAdd(&stats[1], my_len);
     }
 }
 
@@ -684,7 +717,7 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
     {
         StageTimer t(ST_COV_PLAN);
         if (R > 0) {
-            region_plan_kernel<NS><<<blocks_for(R, WARPS), CTA, 0, g_ctx.stream>>>(
+            region_plan_kernel<NS><<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
                 R, chrom, start, end, strand, rd.d_chrom_off, rd.d_chrom_len, rd.n_chrom, src,
                 ignore_strand, strand_filter, ra, d_err, d_stats);
             RCP_LAUNCHED();

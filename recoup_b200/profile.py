@@ -9,6 +9,7 @@ The `$profile` of a sample is a double matrix [regions x bins] with rownames = r
 `rownames` / `colnames`.  `rc` is accepted and ignored.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -32,8 +33,26 @@ class ProfileMatrix(np.ndarray):
         self.colnames = getattr(obj, "colnames", None)
 
 
+def _release_pinned(ptr):
+    try:
+        _lib.lib.rcp_host_free(C.c_void_p(ptr))
+    except Exception:
+        pass
+
+
 def _out(n_rows, n_cols):
-    return np.zeros((n_rows, n_cols), dtype=np.float64, order="F")
+    """Column-major fp64 result matrix in page-locked host memory (rcp_host_alloc): the
+    device->host copy runs at PCIe rate and the buffer returns to the library's pool when the
+    last numpy view of it dies."""
+    n = int(n_rows) * int(n_cols)
+    if n == 0:
+        return np.zeros((n_rows, n_cols), dtype=np.float64, order="F")
+    _lib.ensure_init()
+    ptr = C.c_void_p(0)
+    _lib.check(_lib.lib.rcp_host_alloc(n * 8, C.byref(ptr)))
+    raw = (C.c_double * n).from_address(ptr.value)
+    weakref.finalize(raw, _release_pinned, ptr.value)
+    return np.frombuffer(raw, dtype=np.float64).reshape((n_rows, n_cols), order="F")
 
 
 def _ld(mat):

@@ -133,8 +133,11 @@ def rnaseq(scale=1.0, seed=1004, n_reads=100_000_000, n_genes=20_000, exons_per_
     # unspliced: one range from p0 to the matching position one exon further (covers the intron)
     nxt = np.minimum(j0 + 1, E - 1)
     b1e = np.where(unspliced, np.maximum(ex_start[g_of, nxt] + 10, b1s + read_len - 1), b1e)
-    # outside: shift into the first intron / upstream intergenic space
-    b1s = np.where(outside, np.maximum(gs[g_of] - flank - 500 - (t0 % 3000), 1), b1s)
+    # outside: the 5 % land in the two flanks (alternating), so the flank coverages are not NULL
+    up = (t0 & 1) == 0
+    ge_gene = ex_end[g_of, E - 1]
+    pos_out = np.where(up, gs[g_of] - 1 - (t0 % flank), ge_gene + 1 + (t0 % flank))
+    b1s = np.where(outside, np.maximum(pos_out - read_len // 2, 1), b1s)
     b1e = np.where(outside, b1s + read_len - 1, b1e)
     b1e = np.minimum(b1e, chrom_len[chrom_r])
     chrom = np.concatenate([chrom_r, chrom_r[keep2]])
