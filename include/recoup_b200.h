@@ -172,6 +172,11 @@ int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom,
                          int sample_kind, double scale, double* out, int64_t ld,
                          uint8_t* is_null_out, int mem);
 
+/* ---------------------------------------------------------------- diagnostics ------------- */
+/* Sort n 32-bit keys whose values are < 2^key_bits with the library's index sort (in place).
+ * Exposed so the hand-written sort can be tested directly against a host sort. */
+int rcp_sort_keys_u32(uint32_t* keys, int64_t n, int key_bits, int mem);
+
 /* ---------------------------------------------------------------- multi-GPU helper -------- */
 /* Scatter a row block into the gathered matrix: dst[row_index[i] + c*ld_dst] =
  * src[i + c*ld_src] for i < n_rows, c < n_cols (all pointers on the device).  Used after the

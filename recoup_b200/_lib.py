@@ -63,6 +63,7 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int]),
     "rcp_coverage_profile": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_double, _vp, C.c_int64, _vp, C.c_int]),
+    "rcp_sort_keys_u32": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int]),
     "rcp_rows_scatter": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64]),
 }
 

@@ -752,6 +752,25 @@ int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom, con
     return rc;
 }
 
+int rcp_sort_keys_u32(uint32_t* keys, int64_t n, int key_bits, int mem) {
+    RCP_TRY(require_ready());
+    if (n < 0 || key_bits < 1 || key_bits > 32 || (n > 0 && keys == nullptr))
+        return fail(RCP_ERR_ARG, "rcp_sort_keys_u32: bad argument");
+    if (n == 0) return RCP_OK;
+    if (mem == RCP_MEM_DEVICE) return sort_keys_u32(keys, n, key_bits);
+    uint32_t* d = nullptr;
+    RCP_TRY(dalloc(&d, (size_t)n));
+    RCP_CUDA(cudaMemcpyAsync(d, keys, (size_t)n * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    int rc = sort_keys_u32(d, n, key_bits);
+    if (rc == RCP_OK) {
+        cudaError_t e = cudaMemcpyAsync(keys, d, (size_t)n * 4, cudaMemcpyDeviceToHost, g_ctx.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+        if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "sort copy failed: %s", cudaGetErrorString(e));
+    }
+    dfree(d);
+    return rc;
+}
+
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
                      const int64_t* row_index, double* dst, int64_t ld_dst) {
     RCP_TRY(require_ready());

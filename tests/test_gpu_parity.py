@@ -443,3 +443,42 @@ def test_handles_and_errors(gpu):
     cov = rb.calcCoverage(ok, mask)
     assert cov[0].tolist() == [0, 0, 0, 0, 1, 1, 1, 1, 1, 1]
     assert _lib.lib.rcp_launch_count(0) > 0 and before >= 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the hand-written index sort, directly
+# ------------------------------------------------------------------------------------------------
+def _gpu_sort(keys, bits):
+    from recoup_b200 import _lib
+    a = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+    _lib.check(_lib.lib.rcp_sort_keys_u32(a.ctypes.data_as(C.c_void_p), a.shape[0], bits, _lib.MEM_HOST))
+    return a
+
+
+@pytest.mark.parametrize("n,bits", [(1, 32), (2, 32), (1000, 32), (32768, 32), (32769, 32),
+                                    (100_000, 27), (1_000_003, 32), (3_000_000, 17), (5_000_000, 32)])
+def test_index_sort_uniform_keys(gpu, n, bits):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(_gpu_sort(keys, bits), np.sort(keys))
+
+
+def test_index_sort_pileups_and_recursion(gpu):
+    """Buckets far over the 32 K-key capacity: one value repeated 400 K times, 150 K keys inside a
+    512-wide window, 90 K inside a 40 K-wide window, sorted / reversed inputs, all-equal input."""
+    rng = np.random.default_rng(5)
+    parts = [np.full(400_000, 2_000_000_123, dtype=np.uint32),
+             (3_000_000_000 + rng.integers(0, 512, size=150_000)).astype(np.uint32),
+             (1_000_000 + rng.integers(0, 40_000, size=90_000)).astype(np.uint32),
+             rng.integers(0, 1 << 32, size=1_200_000, dtype=np.uint64).astype(np.uint32),
+             np.array([0, 0, 0xFFFFFFFF, 0xFFFFFFFF, 1, 0xFFFFFFFE], dtype=np.uint32)]
+    keys = np.concatenate(parts)
+    rng.shuffle(keys)
+    want = np.sort(keys)
+    assert np.array_equal(_gpu_sort(keys, 32), want)
+    assert np.array_equal(_gpu_sort(want, 32), want)
+    assert np.array_equal(_gpu_sort(want[::-1], 32), want)
+    same = np.full(200_000, 77, dtype=np.uint32)
+    assert np.array_equal(_gpu_sort(same, 32), same)
+    small_range = rng.integers(0, 3, size=500_000).astype(np.uint32)      # 2 significant bits
+    assert np.array_equal(_gpu_sort(small_range, 2), np.sort(small_range))
