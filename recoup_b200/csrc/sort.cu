@@ -39,6 +39,7 @@ constexpr int MSD_THREADS = 1024;
 constexpr int MSD_ITEMS = 16;
 constexpr int MSD_TILE = MSD_THREADS * MSD_ITEMS;  // 16384 keys per CTA
 constexpr int MSD_MAX_BITS = 14;                   // <= 16384 buckets (2 x 64 KB of smem counters)
+constexpr int MSD_SORTED_MAX_NB = 8192;            // tile-sorted scatter up to this many buckets
 
 __global__ void __launch_bounds__(MSD_THREADS)
 msd_hist_kernel(const uint32_t* __restrict__ src, int64_t n, int shift, int nb,
@@ -99,20 +100,31 @@ msd_offsets_kernel(const uint32_t* __restrict__ hist, int nb, uint32_t* __restri
     if (over) atomicAdd(n_oversized, over);
 }
 
+// Pass 1.  SORTED = true (nb <= 8192): the tile is first grouped by bucket in shared memory, so
+// consecutive threads write consecutive addresses of a bucket's run (fewer L2 sectors per
+// store); SORTED = false: every key goes straight to its slot.
+template <bool SORTED>
 __global__ void __launch_bounds__(MSD_THREADS)
 msd_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n,
                    int shift, int nb, const uint32_t* __restrict__ bucket_off,
                    uint32_t* __restrict__ cursor) {
     extern __shared__ uint32_t sh[];
-    uint32_t* cnt = sh;          // nb: keys of this tile per bucket, then ...
-    uint32_t* base = sh + nb;    // nb: ... where the tile's run of that bucket starts in dst
+    uint32_t* cnt = sh;            // nb: keys of this tile per bucket, later a running cursor
+    uint32_t* base = sh + nb;      // nb: where the tile's run of that bucket starts in dst
+    uint32_t* loc = sh + 2 * nb;   // nb: where it starts inside the tile      (SORTED only)
+    uint32_t* tile = sh + 3 * nb;  // MSD_TILE keys grouped by bucket           (SORTED only)
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_sh;
     const uint32_t bm = (uint32_t)nb - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int b = threadIdx.x; b < nb; b += MSD_THREADS) cnt[b] = 0;
+    if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
     const int64_t tile0 = (int64_t)blockIdx.x * MSD_TILE;
+    const int tile_n = (int)min((int64_t)MSD_TILE, n - tile0);
     uint32_t key[MSD_ITEMS], rnk[MSD_ITEMS];
     // blocked-by-4 arrangement: 16-byte loads while the tile is full
-    const bool full = tile0 + MSD_TILE <= n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const bool full = tile_n == MSD_TILE && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
 #pragma unroll
     for (int q = 0; q < MSD_ITEMS / 4; q++) {
         const int64_t i = tile0 + ((int64_t)q * MSD_THREADS + threadIdx.x) * 4;
@@ -133,15 +145,51 @@ msd_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
         rnk[q] = (i < n) ? atomicAdd(&cnt[(key[q] >> shift) & bm], 1u) : 0u;
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += MSD_THREADS) {
-        const uint32_t c = cnt[b];
-        if (c) base[b] = bucket_off[b] + atomicAdd(&cursor[b], c);
-    }
-    __syncthreads();
+    if (SORTED) {
+        // exclusive scan of cnt -> loc (chunks of 1024 buckets), reserve the global runs
+        for (int b0 = 0; b0 < nb; b0 += MSD_THREADS) {
+            const int b = b0 + threadIdx.x;
+            const uint32_t c = b < nb ? cnt[b] : 0u;
+            uint32_t inc = c;
 #pragma unroll
-    for (int q = 0; q < MSD_ITEMS; q++) {
-        const int64_t i = tile0 + ((int64_t)(q >> 2) * MSD_THREADS + threadIdx.x) * 4 + (q & 3);
-        if (i < n) dst[base[(key[q] >> shift) & bm] + rnk[q]] = key[q];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            uint32_t pre = carry_sh;
+            for (int w = 0; w < warp; w++) pre += wsum[w];
+            if (b < nb) {
+                loc[b] = pre + inc - c;
+                if (c) base[b] = bucket_off[b] + atomicAdd(&cursor[b], c);
+            }
+            __syncthreads();
+            if (threadIdx.x == MSD_THREADS - 1) carry_sh = pre + inc;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < MSD_ITEMS; q++) {
+            const int64_t i = tile0 + ((int64_t)(q >> 2) * MSD_THREADS + threadIdx.x) * 4 + (q & 3);
+            if (i < n) tile[loc[(key[q] >> shift) & bm] + rnk[q]] = key[q];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tile_n; i += MSD_THREADS) {
+            const uint32_t k = tile[i];
+            const uint32_t b = (k >> shift) & bm;
+            dst[base[b] + ((uint32_t)i - loc[b])] = k;
+        }
+    } else {
+        for (int b = threadIdx.x; b < nb; b += MSD_THREADS) {
+            const uint32_t c = cnt[b];
+            if (c) base[b] = bucket_off[b] + atomicAdd(&cursor[b], c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < MSD_ITEMS; q++) {
+            const int64_t i = tile0 + ((int64_t)(q >> 2) * MSD_THREADS + threadIdx.x) * 4 + (q & 3);
+            if (i < n) dst[base[(key[q] >> shift) & bm] + rnk[q]] = key[q];
+        }
     }
 }
 
@@ -182,7 +230,14 @@ bucket_sort_kernel(const uint32_t* src, uint32_t* dst,   // may alias: no __rest
         for (int i = 0; i < BS_ITEMS; i++) {
             if (i < items) {
                 const uint32_t d = (key[i] >> shift) & dmask;
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                // lanes holding the same digit: one ballot per digit bit (the hardware
+                // MATCH.ANY is several times slower than 7 ballots)
+                unsigned peers = 0xffffffffu;
+#pragma unroll
+                for (int bb = 0; bb < BS_DBITS; bb++) {
+                    const unsigned vote = __ballot_sync(0xffffffffu, (d >> bb) & 1u);
+                    peers &= ((d >> bb) & 1u) ? vote : ~vote;
+                }
                 const int leader = __ffs(peers) - 1;
                 uint32_t old = 0;
                 if (lane == leader) {
@@ -252,8 +307,12 @@ int set_attrs() {
     if (g_attr_set) return RCP_OK;
     RCP_CUDA(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)BS_SMEM));
-    RCP_CUDA(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RCP_CUDA(cudaFuncSetAttribute(msd_scatter_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (1 << MSD_MAX_BITS) * 4)));
+    RCP_CUDA(cudaFuncSetAttribute(msd_scatter_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((3 * MSD_SORTED_MAX_NB + MSD_TILE) * 4)));
     RCP_CUDA(cudaFuncSetAttribute(msd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((1 << MSD_MAX_BITS) * 4)));
     g_attr_set = true;
@@ -272,7 +331,7 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
                                      g_ctx.stream));
         return RCP_OK;
     }
-    if (depth > 4) return fail(RCP_ERR_CUDA, "sort: recursion too deep");
+    if (depth > 8) return fail(RCP_ERR_CUDA, "sort: recursion too deep");
     if (n <= BS_CAP) {
         uint32_t h_off[2] = {0u, (uint32_t)n};
         uint32_t* d_off = nullptr;
@@ -286,6 +345,7 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
     // top bits so that the average bucket is ~12 K keys (capacity 32 K)
     int top = 1;
     while (top < MSD_MAX_BITS && (n >> top) > 12288) top++;
+    if (depth > 0) top = MSD_MAX_BITS;     // a pile-up: few distinct values, split as finely as possible
     if (top > bits) top = bits;
     const int shift = bits - top;
     const int nb = 1 << top;
@@ -306,8 +366,12 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
     msd_offsets_kernel<<<1, 1024, 0, g_ctx.stream>>>(hist, nb, off, n_over);
     RCP_LAUNCHED();
     const int tiles = (int)((n + MSD_TILE - 1) / MSD_TILE);
-    msd_scatter_kernel<<<tiles, MSD_THREADS, (size_t)nb * 8, g_ctx.stream>>>(
-        data, other, n, shift, nb, off, cursor);
+    if (nb <= MSD_SORTED_MAX_NB)
+        msd_scatter_kernel<true><<<tiles, MSD_THREADS, ((size_t)3 * nb + MSD_TILE) * 4, g_ctx.stream>>>(
+            data, other, n, shift, nb, off, cursor);
+    else
+        msd_scatter_kernel<false><<<tiles, MSD_THREADS, (size_t)nb * 8, g_ctx.stream>>>(
+            data, other, n, shift, nb, off, cursor);
     RCP_LAUNCHED();
     // buckets now sit in `other`; sorted buckets go to `result`
     bucket_sort_kernel<<<nb, BS_THREADS, BS_SMEM, g_ctx.stream>>>(other, result, off, shift);
