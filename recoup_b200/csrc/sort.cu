@@ -33,8 +33,12 @@ constexpr int BS_THREADS = 1024;
 constexpr int BS_WARPS = BS_THREADS / 32;
 constexpr int BS_ITEMS = 32;                       // keys per thread
 constexpr int BS_CAP = BS_THREADS * BS_ITEMS;      // 32768 keys per bucket
-constexpr int BS_DBITS = 7;
-constexpr int BS_BINS = 1 << BS_DBITS;
+constexpr int BS_LOW_BITS = 10;                    // finished per sub-bucket
+constexpr int BS_LOW_BINS = 1 << BS_LOW_BITS;
+constexpr int BS_MAX_A_BITS = 12;                  // shared-memory partition: <= 4096 sub-buckets
+constexpr int BS_MAX_A = 1 << BS_MAX_A_BITS;
+constexpr int BS_MAX_R_BITS = BS_LOW_BITS + BS_MAX_A_BITS;   // bits one bucket CTA can sort
+constexpr int BS_SMALL = 48;                       // sub-buckets up to this size: one thread
 constexpr int MSD_THREADS = 1024;
 constexpr int MSD_ITEMS = 16;
 constexpr int MSD_TILE = MSD_THREADS * MSD_ITEMS;  // 16384 keys per CTA
@@ -193,113 +197,134 @@ msd_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
     }
 }
 
-// One CTA per bucket: sort the low `r_bits` bits of src[off[b] .. off[b+1]) into dst (same
-// offsets; src == dst is allowed: the bucket is fully loaded before anything is written).
+// exclusive scan of cnt[0..count) into off[0..count] (off[count] = total) by the whole CTA
+__device__ __forceinline__ void cta_exclusive_scan(const uint32_t* cnt, uint32_t* off, int count,
+                                                   uint32_t* wsum, uint32_t* carry_sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *carry_sh = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < count; b0 += BS_THREADS) {
+        const int b = b0 + threadIdx.x;
+        const uint32_t c = b < count ? cnt[b] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t pre = *carry_sh;
+        for (int w = 0; w < warp; w++) pre += wsum[w];
+        if (b < count) off[b] = pre + inc - c;
+        __syncthreads();
+        if (threadIdx.x == BS_THREADS - 1) *carry_sh = pre + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[count] = *carry_sh;
+    __syncthreads();
+}
+
+// Pass 2.  One CTA per bucket: sort the low `r_bits` (<= 22) bits of src[off[b] .. off[b+1])
+// into dst (same offsets; src == dst is allowed: the bucket is loaded before anything is
+// written).  Keys only, so nothing has to be stable:
+//   A. partition the bucket in shared memory on all but its 10 lowest bits (two shared-memory
+//      atomics per key);
+//   B. every sub-bucket (a dozen keys on average) is finished by ONE thread with an insertion
+//      sort; the rare large ones (pile-ups) by the whole CTA with a counting sort on the last
+//      10 bits, regenerating the keys from the histogram.
 __global__ void __launch_bounds__(BS_THREADS, 1)
 bucket_sort_kernel(const uint32_t* src, uint32_t* dst,   // may alias: no __restrict__
                    const uint32_t* __restrict__ bucket_off, int r_bits) {
     extern __shared__ __align__(16) uint32_t smem_raw[];
-    uint32_t* buf = smem_raw;                                           // BS_CAP keys
-    unsigned short* rnk = reinterpret_cast<unsigned short*>(buf + BS_CAP);   // BS_CAP ranks
-    uint32_t* whist = reinterpret_cast<uint32_t*>(rnk + BS_CAP);        // [BS_WARPS][BS_BINS]
-    uint32_t* dig = whist + BS_WARPS * BS_BINS;                         // BS_BINS exclusive starts
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* buf = smem_raw;                    // BS_CAP keys
+    uint32_t* acnt = buf + BS_CAP;               // BS_MAX_A counters / cursors
+    uint32_t* aoff = acnt + BS_MAX_A;            // BS_MAX_A + 1 sub-bucket starts
+    uint32_t* lhist = aoff + BS_MAX_A + 1;       // BS_LOW_BINS + 1
+    uint32_t* big = lhist + BS_LOW_BINS + 1;     // BS_MAX_A ids of large sub-buckets
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_sh;
+    __shared__ uint32_t n_big;
+    const int tid = threadIdx.x;
     const uint32_t start = bucket_off[blockIdx.x];
     const int n = (int)(bucket_off[blockIdx.x + 1] - start);
     if (n <= 0 || n > BS_CAP) return;
     const int items = (n + BS_THREADS - 1) / BS_THREADS;
-    // warp-striped: warp w owns [w*32*items, (w+1)*32*items); item i of lane l sits at +i*32+l
-    const int wbase = warp * 32 * items + lane;
+    const int low = min(r_bits, BS_LOW_BITS);
+    const int na = 1 << (r_bits - low);
+    const uint32_t amask = (uint32_t)na - 1u, lmask = (1u << low) - 1u;
     uint32_t key[BS_ITEMS];
 #pragma unroll
     for (int i = 0; i < BS_ITEMS; i++) {
-        key[i] = 0xffffffffu;
-        if (i < items) {
-            const int idx = wbase + i * 32;
-            if (idx < n) key[i] = src[start + idx];
-        }
+        key[i] = 0;
+        const int idx = i * BS_THREADS + tid;
+        if (i < items && idx < n) key[i] = src[start + idx];
     }
-    const unsigned lt = (1u << lane) - 1u;
-    for (int shift = 0; shift < r_bits; shift += BS_DBITS) {
-        const int bits = min(BS_DBITS, r_bits - shift);
-        const uint32_t dmask = (1u << bits) - 1u;
-        for (int i = tid; i < BS_WARPS * BS_BINS; i += BS_THREADS) whist[i] = 0;
-        __syncthreads();
-        uint32_t* wh = whist + warp * BS_BINS;
+    for (int b = tid; b < na; b += BS_THREADS) acnt[b] = 0;
+    if (tid == 0) n_big = 0;
+    __syncthreads();
 #pragma unroll
-        for (int i = 0; i < BS_ITEMS; i++) {
-            if (i < items) {
-                const uint32_t d = (key[i] >> shift) & dmask;
-                // lanes holding the same digit: one ballot per digit bit (the hardware
-                // MATCH.ANY is several times slower than 7 ballots)
-                unsigned peers = 0xffffffffu;
+    for (int i = 0; i < BS_ITEMS; i++)
+        if (i < items && i * BS_THREADS + tid < n) atomicAdd(&acnt[(key[i] >> low) & amask], 1u);
+    __syncthreads();
+    cta_exclusive_scan(acnt, aoff, na, wsum, &carry_sh);
+    for (int b = tid; b < na; b += BS_THREADS) acnt[b] = aoff[b];     // running cursors
+    __syncthreads();
 #pragma unroll
-                for (int bb = 0; bb < BS_DBITS; bb++) {
-                    const unsigned vote = __ballot_sync(0xffffffffu, (d >> bb) & 1u);
-                    peers &= ((d >> bb) & 1u) ? vote : ~vote;
+    for (int i = 0; i < BS_ITEMS; i++)
+        if (i < items && i * BS_THREADS + tid < n)
+            buf[atomicAdd(&acnt[(key[i] >> low) & amask], 1u)] = key[i];
+    __syncthreads();
+    if (low > 0) {
+        for (int sb = tid; sb < na; sb += BS_THREADS) {
+            const int lo = (int)aoff[sb], m = (int)aoff[sb + 1] - lo;
+            if (m > BS_SMALL) {
+                big[atomicAdd(&n_big, 1u)] = (uint32_t)sb;
+            } else {
+                for (int x = lo + 1; x < lo + m; x++) {
+                    const uint32_t v = buf[x];
+                    int y = x;
+                    while (y > lo && buf[y - 1] > v) {
+                        buf[y] = buf[y - 1];
+                        y--;
+                    }
+                    buf[y] = v;
                 }
-                const int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if (lane == leader) {
-                    old = wh[d];
-                    wh[d] = old + __popc(peers);
+            }
+        }
+        __syncthreads();
+        const int nbig = (int)n_big;
+        const int lbins = 1 << low;
+        for (int q = 0; q < nbig; q++) {
+            const int sb = (int)big[q];
+            const int lo = (int)aoff[sb], m = (int)aoff[sb + 1] - lo;
+            const uint32_t hi_part = buf[lo] & ~lmask;        // shared by the whole sub-bucket
+            for (int b = tid; b < lbins; b += BS_THREADS) lhist[b] = 0;
+            __syncthreads();
+            for (int j = tid; j < m; j += BS_THREADS) atomicAdd(&lhist[buf[lo + j] & lmask], 1u);
+            __syncthreads();
+            cta_exclusive_scan(lhist, lhist, lbins, wsum, &carry_sh);   // in place: one element per thread
+            for (int j = tid; j < m; j += BS_THREADS) {
+                // value whose run [lhist[v], lhist[v+1]) contains position j
+                int a = 0, b = lbins;
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (lhist[mid] <= (uint32_t)j) a = mid;
+                    else b = mid;
                 }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                rnk[wbase + i * 32] = (unsigned short)(old + __popc(peers & lt));
-                __syncwarp();
+                buf[lo + j] = hi_part | (uint32_t)a;
             }
+            __syncthreads();
         }
-        __syncthreads();
-        // per digit: exclusive offsets of the warps, then of the digits
-        if (tid < BS_BINS) {
-            uint32_t run = 0;
-            for (int w = 0; w < BS_WARPS; w++) {
-                const uint32_t t = whist[w * BS_BINS + tid];
-                whist[w * BS_BINS + tid] = run;
-                run += t;
-            }
-            dig[tid] = run;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t carry = 0;
-            for (int d0 = 0; d0 < BS_BINS; d0 += 32) {
-                const uint32_t v = dig[d0 + lane];
-                uint32_t inc = v;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
-                    if (lane >= dd) inc += o;
-                }
-                dig[d0 + lane] = carry + inc - v;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < BS_ITEMS; i++) {
-            if (i < items) {
-                const uint32_t d = (key[i] >> shift) & dmask;
-                buf[dig[d] + wh[d] + rnk[wbase + i * 32]] = key[i];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < BS_ITEMS; i++)
-            if (i < items) key[i] = buf[wbase + i * 32];
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < BS_ITEMS; i++) {
-        if (i < items) {
-            const int idx = wbase + i * 32;
-            if (idx < n) dst[start + idx] = key[i];
-        }
+        const int idx = i * BS_THREADS + tid;
+        if (i < items && idx < n) dst[start + idx] = buf[idx];
     }
 }
 
-constexpr size_t BS_SMEM = (size_t)BS_CAP * 4 + (size_t)BS_CAP * 2 + (size_t)BS_WARPS * BS_BINS * 4 +
-                           (size_t)BS_BINS * 4;
+constexpr size_t BS_SMEM = ((size_t)BS_CAP + 3 * BS_MAX_A + 1 + BS_LOW_BINS + 1 + 2) * 4;
 
 bool g_attr_set = false;
 
@@ -332,7 +357,7 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
         return RCP_OK;
     }
     if (depth > 8) return fail(RCP_ERR_CUDA, "sort: recursion too deep");
-    if (n <= BS_CAP) {
+    if (n <= BS_CAP && bits <= BS_MAX_R_BITS) {
         uint32_t h_off[2] = {0u, (uint32_t)n};
         uint32_t* d_off = nullptr;
         RCP_TRY(dalloc(&d_off, 2));
@@ -346,6 +371,7 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
     int top = 1;
     while (top < MSD_MAX_BITS && (n >> top) > 12288) top++;
     if (depth > 0) top = MSD_MAX_BITS;     // a pile-up: few distinct values, split as finely as possible
+    if (top < bits - BS_MAX_R_BITS) top = bits - BS_MAX_R_BITS;   // a bucket CTA sorts <= 22 bits
     if (top > bits) top = bits;
     const int shift = bits - top;
     const int nb = 1 << top;
@@ -437,7 +463,7 @@ int sort_keys_u32(uint32_t* keys, int64_t n, int end_bit) {
     if (use_cub) return sort_keys_cub(keys, n, end_bit);
     RCP_TRY(set_attrs());
     uint32_t* alt = nullptr;
-    if (n > BS_CAP) RCP_TRY(dalloc(&alt, (size_t)n));
+    if (n > BS_CAP || end_bit > BS_MAX_R_BITS) RCP_TRY(dalloc(&alt, (size_t)n));
     // data in `keys`, scratch `alt`, result back in `keys`
     int rc = sort_segment(keys, alt, keys, n, end_bit, 0);
     dfree(alt);
