@@ -33,12 +33,9 @@ constexpr int BS_THREADS = 1024;
 constexpr int BS_WARPS = BS_THREADS / 32;
 constexpr int BS_ITEMS = 32;                       // keys per thread
 constexpr int BS_CAP = BS_THREADS * BS_ITEMS;      // 32768 keys per bucket
-constexpr int BS_LOW_BITS = 10;                    // finished per sub-bucket
-constexpr int BS_LOW_BINS = 1 << BS_LOW_BITS;
-constexpr int BS_MAX_A_BITS = 12;                  // shared-memory partition: <= 4096 sub-buckets
-constexpr int BS_MAX_A = 1 << BS_MAX_A_BITS;
-constexpr int BS_MAX_R_BITS = BS_LOW_BITS + BS_MAX_A_BITS;   // bits one bucket CTA can sort
-constexpr int BS_SMALL = 48;                       // sub-buckets up to this size: one thread
+constexpr int BS_DBITS = 7;                        // digit of the shared-memory LSD passes
+constexpr int BS_BINS = 1 << BS_DBITS;
+constexpr int BS_MAX_R_BITS = 32;                  // a bucket CTA can sort any number of low bits
 constexpr int MSD_THREADS = 1024;
 constexpr int MSD_ITEMS = 16;
 constexpr int MSD_TILE = MSD_THREADS * MSD_ITEMS;  // 16384 keys per CTA
@@ -197,134 +194,124 @@ msd_scatter_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
     }
 }
 
-// exclusive scan of cnt[0..count) into off[0..count] (off[count] = total) by the whole CTA
-__device__ __forceinline__ void cta_exclusive_scan(const uint32_t* cnt, uint32_t* off, int count,
-                                                   uint32_t* wsum, uint32_t* carry_sh) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) *carry_sh = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < count; b0 += BS_THREADS) {
-        const int b = b0 + threadIdx.x;
-        const uint32_t c = b < count ? cnt[b] : 0u;
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        uint32_t pre = *carry_sh;
-        for (int w = 0; w < warp; w++) pre += wsum[w];
-        if (b < count) off[b] = pre + inc - c;
-        __syncthreads();
-        if (threadIdx.x == BS_THREADS - 1) *carry_sh = pre + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) off[count] = *carry_sh;
-    __syncthreads();
-}
-
-// Pass 2.  One CTA per bucket: sort the low `r_bits` (<= 22) bits of src[off[b] .. off[b+1])
-// into dst (same offsets; src == dst is allowed: the bucket is loaded before anything is
-// written).  Keys only, so nothing has to be stable:
-//   A. partition the bucket in shared memory on all but its 10 lowest bits (two shared-memory
-//      atomics per key);
-//   B. every sub-bucket (a dozen keys on average) is finished by ONE thread with an insertion
-//      sort; the rare large ones (pile-ups) by the whole CTA with a counting sort on the last
-//      10 bits, regenerating the keys from the histogram.
+// One CTA per bucket: sort the low `r_bits` bits of src[off[b] .. off[b+1]) into dst (same
+// offsets; src == dst is allowed: the bucket is fully loaded before anything is written).
 __global__ void __launch_bounds__(BS_THREADS, 1)
 bucket_sort_kernel(const uint32_t* src, uint32_t* dst,   // may alias: no __restrict__
                    const uint32_t* __restrict__ bucket_off, int r_bits) {
     extern __shared__ __align__(16) uint32_t smem_raw[];
-    uint32_t* buf = smem_raw;                    // BS_CAP keys
-    uint32_t* acnt = buf + BS_CAP;               // BS_MAX_A counters / cursors
-    uint32_t* aoff = acnt + BS_MAX_A;            // BS_MAX_A + 1 sub-bucket starts
-    uint32_t* lhist = aoff + BS_MAX_A + 1;       // BS_LOW_BINS + 1
-    uint32_t* big = lhist + BS_LOW_BINS + 1;     // BS_MAX_A ids of large sub-buckets
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_sh;
-    __shared__ uint32_t n_big;
-    const int tid = threadIdx.x;
+    uint32_t* buf = smem_raw;                                           // BS_CAP keys
+    unsigned short* rnk = reinterpret_cast<unsigned short*>(buf + BS_CAP);   // BS_CAP ranks
+    uint32_t* whist = reinterpret_cast<uint32_t*>(rnk + BS_CAP);        // [BS_WARPS][BS_BINS]
+    uint32_t* dig = whist + BS_WARPS * BS_BINS;                         // BS_BINS exclusive starts
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t start = bucket_off[blockIdx.x];
     const int n = (int)(bucket_off[blockIdx.x + 1] - start);
     if (n <= 0 || n > BS_CAP) return;
     const int items = (n + BS_THREADS - 1) / BS_THREADS;
-    const int low = min(r_bits, BS_LOW_BITS);
-    const int na = 1 << (r_bits - low);
-    const uint32_t amask = (uint32_t)na - 1u, lmask = (1u << low) - 1u;
+    // warp-striped: warp w owns [w*32*items, (w+1)*32*items); item i of lane l sits at +i*32+l
+    const int wbase = warp * 32 * items + lane;
     uint32_t key[BS_ITEMS];
 #pragma unroll
     for (int i = 0; i < BS_ITEMS; i++) {
-        key[i] = 0;
-        const int idx = i * BS_THREADS + tid;
-        if (i < items && idx < n) key[i] = src[start + idx];
+        key[i] = 0xffffffffu;
+        if (i < items) {
+            const int idx = wbase + i * 32;
+            if (idx < n) key[i] = src[start + idx];
+        }
     }
-    for (int b = tid; b < na; b += BS_THREADS) acnt[b] = 0;
-    if (tid == 0) n_big = 0;
-    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    for (int shift = 0; shift < r_bits; shift += BS_DBITS) {
+        const int bits = min(BS_DBITS, r_bits - shift);
+        const uint32_t dmask = (1u << bits) - 1u;
+        for (int i = tid; i < BS_WARPS * BS_BINS; i += BS_THREADS) whist[i] = 0;
+        __syncthreads();
+        uint32_t* wh = whist + warp * BS_BINS;
+        // groups of four items: the 28 ballots of a group are independent and issue back to
+        // back; only the four counter updates are serial
 #pragma unroll
-    for (int i = 0; i < BS_ITEMS; i++)
-        if (i < items && i * BS_THREADS + tid < n) atomicAdd(&acnt[(key[i] >> low) & amask], 1u);
-    __syncthreads();
-    cta_exclusive_scan(acnt, aoff, na, wsum, &carry_sh);
-    for (int b = tid; b < na; b += BS_THREADS) acnt[b] = aoff[b];     // running cursors
-    __syncthreads();
+        for (int i0 = 0; i0 < BS_ITEMS; i0 += 4) {
+            if (i0 < items) {
+                unsigned peers[4];
 #pragma unroll
-    for (int i = 0; i < BS_ITEMS; i++)
-        if (i < items && i * BS_THREADS + tid < n)
-            buf[atomicAdd(&acnt[(key[i] >> low) & amask], 1u)] = key[i];
-    __syncthreads();
-    if (low > 0) {
-        for (int sb = tid; sb < na; sb += BS_THREADS) {
-            const int lo = (int)aoff[sb], m = (int)aoff[sb + 1] - lo;
-            if (m > BS_SMALL) {
-                big[atomicAdd(&n_big, 1u)] = (uint32_t)sb;
-            } else {
-                for (int x = lo + 1; x < lo + m; x++) {
-                    const uint32_t v = buf[x];
-                    int y = x;
-                    while (y > lo && buf[y - 1] > v) {
-                        buf[y] = buf[y - 1];
-                        y--;
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t d = (key[i0 + j] >> shift) & dmask;
+                    unsigned pm = 0xffffffffu;
+#pragma unroll
+                    for (int bb = 0; bb < BS_DBITS; bb++) {
+                        const unsigned vote = __ballot_sync(0xffffffffu, (d >> bb) & 1u);
+                        pm &= ((d >> bb) & 1u) ? vote : ~vote;
                     }
-                    buf[y] = v;
+                    peers[j] = pm;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (i0 + j < items) {
+                        const uint32_t d = (key[i0 + j] >> shift) & dmask;
+                        const int leader = __ffs(peers[j]) - 1;
+                        uint32_t old = 0;
+                        if (lane == leader) {
+                            old = wh[d];
+                            wh[d] = old + __popc(peers[j]);
+                        }
+                        old = __shfl_sync(0xffffffffu, old, leader);
+                        rnk[wbase + (i0 + j) * 32] = (unsigned short)(old + __popc(peers[j] & lt));
+                        __syncwarp();
+                    }
                 }
             }
         }
         __syncthreads();
-        const int nbig = (int)n_big;
-        const int lbins = 1 << low;
-        for (int q = 0; q < nbig; q++) {
-            const int sb = (int)big[q];
-            const int lo = (int)aoff[sb], m = (int)aoff[sb + 1] - lo;
-            const uint32_t hi_part = buf[lo] & ~lmask;        // shared by the whole sub-bucket
-            for (int b = tid; b < lbins; b += BS_THREADS) lhist[b] = 0;
-            __syncthreads();
-            for (int j = tid; j < m; j += BS_THREADS) atomicAdd(&lhist[buf[lo + j] & lmask], 1u);
-            __syncthreads();
-            cta_exclusive_scan(lhist, lhist, lbins, wsum, &carry_sh);   // in place: one element per thread
-            for (int j = tid; j < m; j += BS_THREADS) {
-                // value whose run [lhist[v], lhist[v+1]) contains position j
-                int a = 0, b = lbins;
-                while (b - a > 1) {
-                    const int mid = (a + b) >> 1;
-                    if (lhist[mid] <= (uint32_t)j) a = mid;
-                    else b = mid;
-                }
-                buf[lo + j] = hi_part | (uint32_t)a;
+        // per digit: exclusive offsets of the warps, then of the digits
+        if (tid < BS_BINS) {
+            uint32_t run = 0;
+            for (int w = 0; w < BS_WARPS; w++) {
+                const uint32_t t = whist[w * BS_BINS + tid];
+                whist[w * BS_BINS + tid] = run;
+                run += t;
             }
-            __syncthreads();
+            dig[tid] = run;
         }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t carry = 0;
+            for (int d0 = 0; d0 < BS_BINS; d0 += 32) {
+                const uint32_t v = dig[d0 + lane];
+                uint32_t inc = v;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+                    if (lane >= dd) inc += o;
+                }
+                dig[d0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < BS_ITEMS; i++) {
+            if (i < items) {
+                const uint32_t d = (key[i] >> shift) & dmask;
+                buf[dig[d] + wh[d] + rnk[wbase + i * 32]] = key[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < BS_ITEMS; i++)
+            if (i < items) key[i] = buf[wbase + i * 32];
+        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < BS_ITEMS; i++) {
-        const int idx = i * BS_THREADS + tid;
-        if (i < items && idx < n) dst[start + idx] = buf[idx];
+        if (i < items) {
+            const int idx = wbase + i * 32;
+            if (idx < n) dst[start + idx] = key[i];
+        }
     }
 }
 
-constexpr size_t BS_SMEM = ((size_t)BS_CAP + 3 * BS_MAX_A + 1 + BS_LOW_BINS + 1 + 2) * 4;
+constexpr size_t BS_SMEM = (size_t)BS_CAP * 4 + (size_t)BS_CAP * 2 + (size_t)BS_WARPS * BS_BINS * 4 +
+                           (size_t)BS_BINS * 4;
 
 bool g_attr_set = false;
 
@@ -403,8 +390,10 @@ int sort_segment(uint32_t* data, uint32_t* other, uint32_t* result, int64_t n, i
     bucket_sort_kernel<<<nb, BS_THREADS, BS_SMEM, g_ctx.stream>>>(other, result, off, shift);
     RCP_LAUNCHED();
     uint32_t h_over = 0;
-    RCP_CUDA(cudaMemcpyAsync(&h_over, n_over, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (n > BS_CAP) {      // with n <= BS_CAP no bucket can overflow: no need to look (or to wait)
+        RCP_CUDA(cudaMemcpyAsync(&h_over, n_over, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+        RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    }
     int rc = RCP_OK;
     if (h_over > 0) {
         // pile-ups: split the oversized buckets again on their next bits
