@@ -317,25 +317,20 @@ def run_b200(args):
 
     gather_box = {}
 
+    def rows_scatter(block, ids, k, full):
+        _lib.check(L.rcp_rows_scatter(vp(block), block.shape[1], k, block.shape[0], vp(ids),
+                                      vp(full), full.shape[1]))
+
     def gather_step():
-        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...))."""
+        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)),
+        placed into the full column-major matrix by rcp_rows_scatter."""
         if world == 1:
             return
-        m = out_box["m"]
+        from recoup_b200.sharding import gather_rows
         with torch.cuda.stream(stream):
-            if rank == 0:
-                if "bufs" not in gather_box:
-                    gather_box["bufs"] = [torch.empty_like(m) for _ in range(world)]
-                    gather_box["full"] = torch.empty((m.shape[0], R * world), dtype=torch.float64, device=dev)
-                    gather_box["idx"] = [torch.arange(r * R, (r + 1) * R, dtype=torch.int64, device=dev)
-                                         for r in range(world)]
-                dist.gather(m, gather_box["bufs"], dst=0)
-                for r in range(world):
-                    _lib.check(L.rcp_rows_scatter(vp(gather_box["bufs"][r]), R, R, m.shape[0],
-                                                  vp(gather_box["idx"][r]), vp(gather_box["full"]),
-                                                  R * world))
-            else:
-                dist.gather(m, None, dst=0)
+            gather_box["full"] = gather_rows(out_box["m"], np.arange(rank * R, (rank + 1) * R),
+                                             R * world, dst=0, scatter=rows_scatter,
+                                             sizes=[R] * world)
 
     def barrier():
         torch.cuda.synchronize()
