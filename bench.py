@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(W.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets"],
+                    help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
 
 
@@ -235,6 +237,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rb.init(local)
+    rb.set_coverage_path(args.path)
     L = _lib.lib
     dev = torch.device("cuda", local)
     stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
@@ -451,29 +454,54 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         total_len = stats["total_len"]
-        # algorithmic bytes per launch (SURVEY 8d / DESIGN.md):
-        #   coverage stage  8 B/read + 4 B/covered base + 16 B/region
-        #   profile stage   4 B/covered base + 8 B/matrix cell
-        alg = {
+        # Algorithmic bytes (SURVEY 8d / DESIGN.md 4).  Per STAGE:
+        #   reads_map  13 B/read in (chrom, start, end, strand) + 9 B/read out (global start,
+        #              end+1, strand)
+        #   coverage   8 B/read + 4 B/covered base + 16 B/region     (everything between the
+        #              mapped reads and the dense coverage: sort or bucketing included in the
+        #              TIME, not in the bytes)
+        #   profile    4 B/covered base + 8 B/matrix cell
+        # Per KERNEL (the `roofline` object, dominant kernel of the step): the bytes that kernel
+        # cannot avoid moving -- a pass over the reads 8 B/read (+1 with strand), the tile
+        # kernels 4 B/covered base written (+ 8 B/read on the index path, which reads the sorted
+        # arrays there), the bin kernel 4 B/covered base + 8 B/cell, the sort 8 B/key.
+        alg_kernel = {
+            "index_map": 22 * N,
+            "index_sort": 8 * N,
             "cov_tile": 8 * N + 4 * total_len + 16 * R,
             "cov_small": 8 * N + 4 * total_len + 16 * R,
+            "bkt_count": 8 * N,
+            "bkt_scatter": 8 * N,
+            "bkt_tile": 4 * total_len,
+            "bkt_small": 4 * total_len,
             "prof_bin": 4 * total_len + 8 * R * ncols,
             "prof_base": 4 * total_len + 8 * R * ncols,
-            "index_sort": None,
         }
-        own = {k: v for k, v in stage.items() if k in ("cov_tile", "cov_small", "cov_list", "prof_bin",
-                                                      "prof_base")}
+        groups = {
+            "reads_map": (["index_map"], 22 * N),
+            "coverage": (["index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
+                          "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small"],
+                         8 * N + 4 * total_len + 16 * R),
+            "profile": (["prof_bin", "prof_interp", "prof_base"], 4 * total_len + 8 * R * ncols),
+        }
+        per_step = {k: v[0] * v[1] / args.steps for k, v in stage.items()}
+        stage_roof = {}
+        for g, (members, nbytes) in groups.items():
+            ms_g = sum(per_step.get(m, 0.0) for m in members)
+            if ms_g > 0:
+                ach = nbytes / (ms_g * 1e-3) / 1e9
+                stage_roof[g] = {"ms_per_step": ms_g, "algorithmic_bytes": nbytes, "achieved": ach,
+                                 "frac": ach / peak}
+        own = {k: v for k, v in stage.items() if k in alg_kernel}
         dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
         roof = None
-        if dom and alg.get(dom):
-            # the stage's algorithmic bytes for ONE step over the stage's device time in one
-            # step (a stage may be several launches of the same kernel, e.g. one per segment)
-            per_step_ms = own[dom][0] * own[dom][1] / args.steps
-            ach = alg[dom] / (per_step_ms * 1e-3) / 1e9
+        if dom:
+            per_step_ms = per_step[dom]
+            ach = alg_kernel[dom] / (per_step_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "ms_per_step": per_step_ms, "launches_per_step": own[dom][1] / args.steps,
-                    "algorithmic_bytes": alg[dom]}
+                    "algorithmic_bytes": alg_kernel[dom], "stages": stage_roof}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -484,6 +512,7 @@ def run_b200(args):
                        "null_regions": stats["n_null"],
                        "l2": "inputs (%.0f MB) and coverage (%.0f MB) exceed the 126 MB L2"
                              % (13 * N / 1e6, 4 * total_len / 1e6),
+                       "coverage_path": args.path,
                        "parallelism": "regions sharded over %d GPU(s), NCCL row gather" % world},
             "stage_ms_per_step": {k: v[0] * v[1] / args.steps for k, v in stage.items()},
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),

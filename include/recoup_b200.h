@@ -94,6 +94,19 @@ int rcp_timing_enable(int on);
 int rcp_timing_read(int reset, int capacity, double* ms_out, int64_t* count_out);
 const char* rcp_timing_stage_name(int stage);
 
+/* How rcp_coverage (GRanges masks) finds the reads of each region.  Both give identical results.
+ *   RCP_PATH_BUCKETS  two passes over the unsorted reads drop each read into the buckets of the
+ *                     output tiles it overlaps (no sort);
+ *   RCP_PATH_INDEX    the reads are radix-sorted once per handle and every region is served by
+ *                     rank searches (cheaper when one handle serves many masks);
+ *   RCP_PATH_AUTO     (default) the index when the handle already has one, else buckets.
+ * The reference has one path (findOverlaps per region, coverage.R:189-193); this is a tuning
+ * knob with no counterpart there. */
+#define RCP_PATH_AUTO 0
+#define RCP_PATH_INDEX 1
+#define RCP_PATH_BUCKETS 2
+int rcp_set_coverage_path(int path);
+
 /* ---------------------------------------------------------------- base-R RNG -------------- */
 /* `set.seed(seed); sample(1:n, k)` -- the bin layout of splitVector (util.R:78-79). */
 int rcp_r_sample(int n, int k, int seed, int sample_kind, int* out /* k */);
@@ -102,8 +115,9 @@ int rcp_r_sample(int n, int k, int seed, int sample_kind, int* out /* k */);
 int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out /* n */);
 
 /* ---------------------------------------------------------------- reads ------------------- */
-/* Upload decoded reads (the `ranges` GRanges produced by preprocessRanges, ranges.R:1-65) and
- * build the device index (reads sorted by global coordinate).  `strand` may be NULL (all '*').
+/* Upload decoded reads (the `ranges` GRanges produced by preprocessRanges, ranges.R:1-65),
+ * validate them and map them to global coordinates on the device (the sorted index is built
+ * lazily by the first call that needs it).  `strand` may be NULL (all '*').
  * chrom_len[c] must be the known seqlength (> 0).  Reads must satisfy 1 <= start <= end and,
  * after the optional extension, are trimmed into [1, chrom_len] like readBam's trim()
  * (ranges.R:117).  frag_len > 0 applies the fragment extension named by the north star

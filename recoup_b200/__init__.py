@@ -6,7 +6,7 @@ Importing requires recoup_b200/librecoup_b200.so (built by __graft_entry__.build
 compute call requires a B200 -- there is no CPU fallback.
 """
 from . import _lib
-from ._lib import RecoupError, init, shutdown
+from ._lib import RecoupError, init, set_coverage_path, shutdown
 from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, coverageRnaRef,
                        device_reads, set_verbose)
 from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, haveEqualLengths,
@@ -14,7 +14,7 @@ from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, have
 from .ranges import GRanges, GRangesList, getFlankingRanges, getRegionalRanges
 
 __all__ = [
-    "RecoupError", "init", "shutdown", "GRanges", "GRangesList", "getRegionalRanges",
+    "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "getRegionalRanges",
     "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
     "haveEqualLengths", "ProfileMatrix", "set_verbose",

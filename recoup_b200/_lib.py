@@ -17,6 +17,7 @@ WHERE = {"whole": 0, "center": 1, "upstream": 2, "downstream": 3}
 STAT = {"mean": 0, "median": 1}
 INTERP = {"auto": 0, "spline": 1, "linear": 2, "neighborhood": 3}
 SAMPLE_KIND = {"Rejection": 0, "Rounding": 1}
+COVERAGE_PATH = {"auto": 0, "index": 1, "buckets": 2}
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -36,6 +37,7 @@ SIGNATURES = {
     "rcp_stream": (C.c_void_p, []),
     "rcp_sync": (C.c_int, []),
     "rcp_launch_count": (C.c_int64, [C.c_int]),
+    "rcp_set_coverage_path": (C.c_int, [C.c_int]),
     "rcp_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "rcp_host_free": (C.c_int, [C.c_void_p]),
     "rcp_timing_enable": (C.c_int, [C.c_int]),
@@ -111,6 +113,13 @@ def shutdown():
     global _initialised_device
     lib.rcp_shutdown()
     _initialised_device = None
+
+
+def set_coverage_path(path):
+    """"auto" | "index" | "buckets": how rcp_coverage finds each region's reads (same results;
+    see include/recoup_b200.h).  Takes effect for reads uploaded afterwards."""
+    ensure_init()
+    check(lib.rcp_set_coverage_path(COVERAGE_PATH[path]))
 
 
 def ensure_init():

@@ -101,7 +101,8 @@ static double g_stage_ms[ST_N];
 static int64_t g_stage_count[ST_N];
 static const char* const g_stage_names[ST_N] = {
     "index_map", "index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
-    "prof_bin", "prof_interp", "prof_base", "fused"};
+    "prof_bin", "prof_interp", "prof_base", "fused", "bkt_plan", "bkt_count", "bkt_scatter",
+    "bkt_tile", "bkt_small"};
 
 static cudaEvent_t take_event() {
     if (!g_free_events.empty()) {
@@ -179,6 +180,9 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
 int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int ignore_strand,
                     int strand_filter, int mem, Coverage* cv);
+int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                             const int32_t* end, const int8_t* strand, int ignore_strand,
+                             int strand_filter, int mem, Coverage* cv);
 int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_ranges,
                   const int32_t* chrom, const int32_t* start, const int32_t* end,
                   const int8_t* strand, int ignore_strand, int strand_filter, int mem,
@@ -451,6 +455,13 @@ const char* rcp_timing_stage_name(int stage) {
     return (stage >= 0 && stage < ST_N) ? g_stage_names[stage] : nullptr;
 }
 
+int rcp_set_coverage_path(int path) {
+    if (path != RCP_PATH_AUTO && path != RCP_PATH_INDEX && path != RCP_PATH_BUCKETS)
+        return fail(RCP_ERR_ARG, "unknown coverage path %d", path);
+    g_ctx.coverage_path = path;
+    return RCP_OK;
+}
+
 int64_t rcp_launch_count(int reset) {
     const int64_t v = g_ctx.launches;
     if (reset) g_ctx.launches = 0;
@@ -532,8 +543,21 @@ int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32
     Coverage* cv;
     int h;
     RCP_TRY(new_coverage(&cv, &h));
-    int rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
-                             strand_filter, mem, cv);
+    // RCP_PATH_AUTO: the sorted index serves the call when it already exists (built by an
+    // earlier call or by the GRangesList path); otherwise the reads are bucketed per tile, which
+    // costs two passes over the reads instead of a sort.
+    bool use_index = g_ctx.coverage_path == RCP_PATH_INDEX;
+    if (g_ctx.coverage_path == RCP_PATH_AUTO) {
+        const bool unstranded =
+            (strand_filter == RCP_STRAND_ANY) && (ignore_strand != 0 || strand == nullptr);
+        use_index = unstranded ? r->cls[CLS_ALL].built
+                               : (r->cls[CLS_PLUS].built && r->cls[CLS_MINUS].built &&
+                                  r->cls[CLS_STAR].built);
+    }
+    int rc = use_index ? coverage_ranges(*r, n_regions, chrom, start, end, strand,
+                                         ignore_strand != 0, strand_filter, mem, cv)
+                       : coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand,
+                                                  ignore_strand != 0, strand_filter, mem, cv);
     if (rc != RCP_OK) {
         drop_coverage(h);
         return rc;

@@ -1,0 +1,149 @@
+// Device helpers shared by the coverage kernels (coverage.cu: sorted-index path and
+// GRangesList path; coverage_buckets.cu: reads bucketed per output tile, no sort).
+#pragma once
+#include "rcp_internal.cuh"
+
+namespace rcp {
+namespace covk {
+
+constexpr int CTA = 256;
+constexpr int WARPS = CTA / 32;
+constexpr int TILE = 7168;             // positions per CTA tile (28 KB of int32; 8 CTAs per SM)
+constexpr int ROW = 128;               // positions handled by one warp-wide int4 access
+constexpr int MAX_ROWS = TILE / ROW;   // 56
+constexpr int SMALL_MAX = 1024;        // regions up to this length use the warp kernel
+constexpr int PAD = 32;                // region offsets are multiples of 32 ints (128 B)
+
+
+// classes (bit0 '+', bit1 '-', bit2 '*') a region may count under the strand rules of
+// calcCoverage(strand=) (coverage.R:141-144) and findOverlaps(ignore.strand=) (coverage.R:191)
+__device__ __forceinline__ unsigned class_mask(int region_strand, int ignore_strand,
+                                               int strand_filter) {
+    unsigned m = 7u;
+    if (strand_filter != RCP_STRAND_ANY) m = strand_filter > 0 ? 1u : (strand_filter < 0 ? 2u : 4u);
+    if (!ignore_strand) {
+        if (region_strand > 0) m &= 5u;
+        else if (region_strand < 0) m &= 6u;
+    }
+    return m;
+}
+
+// Window geometry of one region (coverage.R:209 inside the tryCatch of coverage.R:217-222):
+// `[start:end]` on the chromosome-long vector -- a negative start mixes signs, an end past the
+// chromosome is out of bounds -> NULL; a zero index is silently dropped.  Returns true when the
+// region is NULL for geometric reasons; *gs = global coordinate of the first base, *L = length.
+// err bits: 1 chrom id out of range, 2 end < start - 1.
+__device__ __forceinline__ bool window_geometry(int c, int64_t s, int64_t e, int n_chrom,
+                                                const uint32_t* __restrict__ chrom_off,
+                                                const int64_t* __restrict__ chrom_len,
+                                                unsigned int* __restrict__ err, uint32_t* gs,
+                                                int64_t* L) {
+    *gs = 0;
+    *L = 0;
+    if (c < 0 || c >= n_chrom) {
+        atomicOr(err, 1u);
+        return true;
+    }
+    if (e < s - 1) {
+        atomicOr(err, 2u);
+        return true;
+    }
+    bool null = false;
+    if (s < 0 || e > chrom_len[c]) null = true;
+    if (s == 0) s = 1;
+    int64_t len = e - s + 1;
+    if (len <= 0) { len = 0; null = true; }
+    *L = len;
+    *gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
+    return null;
+}
+
+__device__ __forceinline__ bool strand_ok(int read_strand, int range_strand, int ignore_strand,
+                                          int strand_filter) {
+    if (strand_filter != RCP_STRAND_ANY && read_strand != strand_filter) return false;
+    if (ignore_strand || range_strand == 0 || read_strand == 0) return true;
+    return read_strand == range_strand;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// Scan + store.  `diff` holds the tile's difference array IN OUTPUT ORDER: for a '-' region the
+// events are scattered mirrored (index tlen-1-k), so the output is always written left to right
+// with aligned 16-byte stores straight from registers:
+//     '+'  out[k] = base + inclusive_prefix(k)
+//     '-'  out[k] = base + total - exclusive_prefix(k)        (a suffix sum of the mirrored array)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// One row (128 outputs at dst[0..127], `valid` of them real) by one warp.  `pre` = sum of every
+// diff before this row.  Returns the row total (all lanes).
+__device__ __forceinline__ int warp_row_scan_store(const int* row_ptr, int pre, int base_or_top,
+                                                   bool rev, int valid, int32_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int4 v = *(reinterpret_cast<const int4*>(row_ptr) + lane);
+    const int i0 = v.x, i1 = i0 + v.y, i2 = i1 + v.z, i3 = i2 + v.w;
+    const int inc = warp_inclusive_scan(i3);
+    const int ex = pre + inc - i3;                 // sum of everything before this lane's 4
+    int4 o;
+    if (!rev) {
+        o = make_int4(base_or_top + ex + i0, base_or_top + ex + i1, base_or_top + ex + i2,
+                      base_or_top + ex + i3);
+    } else {
+        o = make_int4(base_or_top - ex, base_or_top - ex - i0, base_or_top - ex - i1,
+                      base_or_top - ex - i2);
+    }
+    const int k = lane * 4;
+    if (k + 3 < valid) {
+        *reinterpret_cast<int4*>(dst + k) = o;
+    } else {
+        if (k < valid) dst[k] = o.x;
+        if (k + 1 < valid) dst[k + 1] = o.y;
+        if (k + 2 < valid) dst[k + 2] = o.z;
+    }
+    return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// Whole CTA: tile of `tlen` outputs at dst (16-byte aligned).  rowpre needs MAX_ROWS + 1 ints.
+__device__ __forceinline__ void block_scan_store(const int* diff, int tlen, int base, bool rev,
+                                                 int* rowpre, int32_t* __restrict__ dst) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nrows = (tlen + ROW - 1) / ROW;
+    for (int row = warp; row < nrows; row += WARPS) {          // pass A: row totals
+        const int4 v = *(reinterpret_cast<const int4*>(diff + row * ROW) + lane);
+        int s = v.x + v.y + v.z + v.w;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) rowpre[row] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {                                           // exclusive prefix of the rows
+        int carry = 0;
+        for (int r0 = 0; r0 < nrows; r0 += 32) {
+            const int r = r0 + lane;
+            const int v = r < nrows ? rowpre[r] : 0;
+            const int inc = warp_inclusive_scan(v);
+            if (r < nrows) rowpre[r] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) rowpre[MAX_ROWS] = carry;               // tile total
+    }
+    __syncthreads();
+    const int top = rev ? base + rowpre[MAX_ROWS] : base;
+    for (int row = warp; row < nrows; row += WARPS)            // pass B: scan + store
+        warp_row_scan_store(diff + row * ROW, rowpre[row], top, rev, tlen - row * ROW,
+                            dst + row * ROW);
+}
+
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace covk
+}  // namespace rcp

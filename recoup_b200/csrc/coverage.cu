@@ -15,19 +15,14 @@
 //   cov_tile_kernel      1 CTA   / tile    : longer regions cut into <= 4096-bp tiles
 //   list_plan_kernel / cov_list_kernel     : GRangesList elements (exons stitched per gene,
 //                                            read multiplicity, coverage.R:202-207)
+#include "cov_common.cuh"
 #include "rcp_internal.cuh"
 
 namespace rcp {
 
-namespace {
+using namespace covk;
 
-constexpr int CTA = 256;
-constexpr int WARPS = CTA / 32;
-constexpr int TILE = 7168;             // positions per CTA tile (28 KB of int32; 8 CTAs per SM)
-constexpr int ROW = 128;               // positions handled by one warp-wide int4 access
-constexpr int MAX_ROWS = TILE / ROW;   // 56
-constexpr int SMALL_MAX = 1024;        // regions up to this length use the warp kernel
-constexpr int PAD = 32;                // region offsets are multiples of 32 ints (128 B)
+namespace {
 
 // ye[i] is read as ye[i] + yshift: in uniform-width mode ye aliases xs and yshift is the width.
 template <int NS>
@@ -88,19 +83,6 @@ __device__ __forceinline__ uint32_t warp_lower_bound_u32(const uint32_t* __restr
     return lo;
 }
 
-// classes (bit0 '+', bit1 '-', bit2 '*') a region may count under the strand rules of
-// calcCoverage(strand=) (coverage.R:141-144) and findOverlaps(ignore.strand=) (coverage.R:191)
-__device__ __forceinline__ unsigned class_mask(int region_strand, int ignore_strand,
-                                               int strand_filter) {
-    unsigned m = 7u;
-    if (strand_filter != RCP_STRAND_ANY) m = strand_filter > 0 ? 1u : (strand_filter < 0 ? 2u : 4u);
-    if (!ignore_strand) {
-        if (region_strand > 0) m &= 5u;
-        else if (region_strand < 0) m &= 6u;
-    }
-    return m;
-}
-
 // lower_bound started from a nearby position `hint` (exponential probe, then bisection): the
 // five ranks a region needs lie within a few hundred reads of each other.
 __device__ __forceinline__ uint32_t gallop_lower_bound_u32(const uint32_t* __restrict__ a,
@@ -145,28 +127,12 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
     unsigned long long my_null = 0, my_len = 0;
     if (r < R) {
         const int c = chrom[r];
-        int64_t s = start[r], e = end[r];
+        const int64_t s = start[r], e = end[r];
         const int st = strand ? (int)strand[r] : 0;
-        bool null = false;
         uint32_t gs = 0;
         int64_t L = 0;
         const unsigned mask = NS <= 2 ? 1u : class_mask(st, ignore_strand, strand_filter);
-        if (c < 0 || c >= n_chrom) {
-            atomicOr(err, 1u);
-            null = true;
-        } else if (e < s - 1) {
-            atomicOr(err, 2u);
-            null = true;
-        } else {
-            // `[start:end]` on the chromosome-long vector (coverage.R:209): a negative start
-            // mixes signs, an end past the chromosome is out of bounds -> tryCatch -> NULL;
-            // a zero index is silently dropped.
-            if (s < 0 || e > chrom_len[c]) null = true;
-            if (s == 0) s = 1;
-            L = e - s + 1;
-            if (L <= 0) { L = 0; null = true; }
-            gs = chrom_off[c] + (uint32_t)(s > 0 ? s : 0);
-        }
+        bool null = window_geometry(c, s, e, n_chrom, chrom_off, chrom_len, err, &gs, &L);
         if (!null) {
             const uint32_t ge = gs + (uint32_t)(L - 1);
             long long nov = 0;
@@ -238,82 +204,6 @@ __device__ __forceinline__ void warp_aggregated_add(int* diff, uint32_t pos, boo
         const int run_end = above ? (__ffs(above) - 1) : 32;
         atomicAdd(diff + pos, sign * (run_end - (int)lane));
     }
-}
-
-// --------------------------------------------------------------------------------------------
-// Scan + store.  `diff` holds the tile's difference array IN OUTPUT ORDER: for a '-' region the
-// events are scattered mirrored (index tlen-1-k), so the output is always written left to right
-// with aligned 16-byte stores straight from registers:
-//     '+'  out[k] = base + inclusive_prefix(k)
-//     '-'  out[k] = base + total - exclusive_prefix(k)        (a suffix sum of the mirrored array)
-// --------------------------------------------------------------------------------------------
-__device__ __forceinline__ int warp_inclusive_scan(int v) {
-    const unsigned lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += o;
-    }
-    return v;
-}
-
-// One row (128 outputs at dst[0..127], `valid` of them real) by one warp.  `pre` = sum of every
-// diff before this row.  Returns the row total (all lanes).
-__device__ __forceinline__ int warp_row_scan_store(const int* row_ptr, int pre, int base_or_top,
-                                                   bool rev, int valid, int32_t* __restrict__ dst) {
-    const int lane = threadIdx.x & 31;
-    const int4 v = *(reinterpret_cast<const int4*>(row_ptr) + lane);
-    const int i0 = v.x, i1 = i0 + v.y, i2 = i1 + v.z, i3 = i2 + v.w;
-    const int inc = warp_inclusive_scan(i3);
-    const int ex = pre + inc - i3;                 // sum of everything before this lane's 4
-    int4 o;
-    if (!rev) {
-        o = make_int4(base_or_top + ex + i0, base_or_top + ex + i1, base_or_top + ex + i2,
-                      base_or_top + ex + i3);
-    } else {
-        o = make_int4(base_or_top - ex, base_or_top - ex - i0, base_or_top - ex - i1,
-                      base_or_top - ex - i2);
-    }
-    const int k = lane * 4;
-    if (k + 3 < valid) {
-        *reinterpret_cast<int4*>(dst + k) = o;
-    } else {
-        if (k < valid) dst[k] = o.x;
-        if (k + 1 < valid) dst[k + 1] = o.y;
-        if (k + 2 < valid) dst[k + 2] = o.z;
-    }
-    return __shfl_sync(0xffffffffu, inc, 31);
-}
-
-// Whole CTA: tile of `tlen` outputs at dst (16-byte aligned).  rowpre needs MAX_ROWS + 1 ints.
-__device__ __forceinline__ void block_scan_store(const int* diff, int tlen, int base, bool rev,
-                                                 int* rowpre, int32_t* __restrict__ dst) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nrows = (tlen + ROW - 1) / ROW;
-    for (int row = warp; row < nrows; row += WARPS) {          // pass A: row totals
-        const int4 v = *(reinterpret_cast<const int4*>(diff + row * ROW) + lane);
-        int s = v.x + v.y + v.z + v.w;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) rowpre[row] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {                                           // exclusive prefix of the rows
-        int carry = 0;
-        for (int r0 = 0; r0 < nrows; r0 += 32) {
-            const int r = r0 + lane;
-            const int v = r < nrows ? rowpre[r] : 0;
-            const int inc = warp_inclusive_scan(v);
-            if (r < nrows) rowpre[r] = carry + inc - v;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) rowpre[MAX_ROWS] = carry;               // tile total
-    }
-    __syncthreads();
-    const int top = rev ? base + rowpre[MAX_ROWS] : base;
-    for (int row = warp; row < nrows; row += WARPS)            // pass B: scan + store
-        warp_row_scan_store(diff + row * ROW, rowpre[row], top, rev, tlen - row * ROW,
-                            dst + row * ROW);
 }
 
 // ---- warp-per-region kernel (L <= SMALL_MAX) -----------------------------------------------
@@ -454,13 +344,6 @@ struct ListArrays {
     int64_t* padded;
     int64_t* ntiles;
 };
-
-__device__ __forceinline__ bool strand_ok(int read_strand, int range_strand, int ignore_strand,
-                                          int strand_filter) {
-    if (strand_filter != RCP_STRAND_ANY && read_strand != strand_filter) return false;
-    if (ignore_strand || range_strand == 0 || read_strand == 0) return true;
-    return read_strand == range_strand;
-}
 
 // err bits: 1 chrom id, 2 end < start-1, 4 ranges of one element on different chromosomes
 __global__ void __launch_bounds__(CTA)
@@ -674,7 +557,6 @@ len_to_i64_kernel(int64_t n, const int32_t* __restrict__ len, int64_t* __restric
     if (i < n) out[i] = len[i];
 }
 
-inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 int alloc_coverage_arrays(Coverage* cv, int64_t R) {
     cv->n_regions = R;

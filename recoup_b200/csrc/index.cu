@@ -110,7 +110,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         one(c4.w, s4.w, e4.w, t4.w, &gs.w, &ge.w);
         reinterpret_cast<uint4*>(g_start)[v] = gs;
         reinterpret_cast<uint4*>(g_end1)[v] = ge;
-        reinterpret_cast<uint4*>(xs_out)[v] = gs;
+        if (xs_out) reinterpret_cast<uint4*>(xs_out)[v] = gs;
         if (strand_out)
             reinterpret_cast<char4*>(strand_out)[v] = make_char4(sgn(t4.x), sgn(t4.y), sgn(t4.z), sgn(t4.w));
     }
@@ -120,7 +120,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         one(chrom[i], start[i], end[i], st, &gs, &ge1);
         g_start[i] = gs;
         g_end1[i] = ge1;
-        xs_out[i] = gs;
+        if (xs_out) xs_out[i] = gs;
         if (strand_out) strand_out[i] = sgn(st);
     }
     // block-level reduction of the three strand counters and the error mask
@@ -436,7 +436,8 @@ int reads_build_pairs(ReadsIdx& r) {
     return RCP_OK;
 }
 
-// Builds the raw global-coordinate arrays and the ALL class.  Synchronises once to validate.
+// Builds the raw global-coordinate arrays (and, under RCP_PATH_INDEX, the ALL class at once; it
+// is otherwise built by the first call that needs it).  Synchronises once to validate.
 int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
                     const int64_t* chrom_len, int frag_len, int mem) {
@@ -507,7 +508,9 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     exc.st = r.exc_st;
     exc.count = d_w;
     exc.w_out = d_w + 1;
-    RCP_TRY(dalloc(&r.cls[CLS_ALL].xs, (size_t)n));    // unsorted copy of g_start, sorted below
+    // RCP_PATH_INDEX: the map kernel also writes the copy of g_start the index sort works on
+    const bool eager_index = g_ctx.coverage_path == RCP_PATH_INDEX;
+    if (eager_index) RCP_TRY(dalloc(&r.cls[CLS_ALL].xs, (size_t)n));
     if (n > 0) {
         StageTimer t(ST_INDEX_MAP);
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -558,8 +561,10 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     r.cls[CLS_PLUS].n = (int64_t)h_cnt[0];
     r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
     r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
-    RCP_TRY(reads_build_class(r, CLS_ALL));
-    lap("class ALL enqueued");
+    if (eager_index) {
+        RCP_TRY(reads_build_class(r, CLS_ALL));
+        lap("class ALL enqueued");
+    }
     r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
     return RCP_OK;
 }

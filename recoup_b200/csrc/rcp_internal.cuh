@@ -19,6 +19,7 @@ struct Ctx {
     size_t mem_bytes = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;      // kernels launched by this library
+    int coverage_path = RCP_PATH_AUTO;
 };
 extern Ctx g_ctx;
 
@@ -60,6 +61,11 @@ enum Stage {
     ST_PROF_INTERP,     // interp_kernel
     ST_PROF_BASE,       // base_matrix_kernel
     ST_FUSED,           // fused coverage+profile kernel
+    ST_BKT_PLAN,        // bucket path: windows, tiles, cell lists, NULL rule, offset scans
+    ST_BKT_COUNT,       // bucket path: count pass over the reads
+    ST_BKT_SCATTER,     // bucket path: scatter pass over the reads
+    ST_BKT_TILE,        // bucket path: bkt_tile_kernel
+    ST_BKT_SMALL,       // bucket path: bkt_small_kernel
     ST_N
 };
 struct StageTimer {
@@ -178,6 +184,7 @@ int sort_pairs_u32(uint32_t* keys_in_out, uint32_t* vals_in_out, int64_t n, int 
 // exclusive prefix sum of int64 (scan.cu); out may alias in; total (optional) receives the sum
 // on the DEVICE (d_total) -- nothing is synchronised.
 int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, int64_t* d_total);
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* d_total);
 int exclusive_scan2_i64(const int64_t* in0, int64_t* out0, int64_t* d_total0, const int64_t* in1,
                         int64_t* out1, int64_t* d_total1, int64_t n);
 
