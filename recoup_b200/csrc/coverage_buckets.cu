@@ -8,20 +8,26 @@
 //
 //   1. plan          regions -> windows (geometry / NULL rules) -> tiles (<= 7168 outputs, cut
 //                    in output space; regions <= 1024 bp are one warp-sized tile)
-//   2. cell lists    the genome is cut into 1024-bp cells; cell -> tiles overlapping it (CSR,
-//                    L2-resident: 4 B per cell + 4 B per (tile, cell) pair)
-//   3. count pass    every read looks up the cells it touches and bumps the counter of each
-//                    tile it overlaps (a read that hits no cell list costs two L2 loads)
+//   2. cell table    the genome is cut into 1024-bp cells; one 16-byte record per cell holds
+//                    the first tile overlapping it inline (L2-resident), further tiles in
+//                    overflow runs
+//   3. find pass     every read is checked against a shared-memory bitmap of the 16-kb blocks
+//                    some tile touches (most reads of a sparse mask stop there), then against
+//                    the 16-byte record of each cell it touches; a hit is clipped to the tile,
+//                    packed as ONE 32-bit event pair (first covered output | one past the last;
+//                    '-' regions are mirrored here, so the tile kernels are strand-agnostic),
+//                    appended to a hit list and counted per tile
 //   4. NULL rule     a region with no read in any tile is NULL (coverage.R:198,224-225);
 //                    offsets of the dense coverage and of the buckets by prefix sums
-//   5. scatter pass  the same walk; the read is clipped to the tile and stored as ONE packed
-//                    32-bit event pair (first covered output | one past the last) -- '-' regions
-//                    are mirrored here, so the tile kernels are strand-agnostic
+//   5. place pass    hit list -> per-tile buckets (a counting sort by tile)
 //   6. tile kernels  bucket -> shared-memory difference array (atomics) -> block prefix scan ->
 //                    aligned 16-byte stores of the int32 coverage
 //
-// HBM traffic per read: 2 x 8-9 B (the two passes) + 2 x 4 B per (read, tile) hit, against
-// >= 4 passes x 8 B per read for a radix sort of the whole read set.
+// HBM traffic: 8-9 B per read once + 20 B per (read, tile) hit, against >= 4 passes x 8 B per
+// read for a radix sort of the whole read set.
+#include <algorithm>
+#include <cstdlib>
+
 #include "cov_common.cuh"
 #include "rcp_internal.cuh"
 
@@ -31,18 +37,33 @@ using namespace covk;
 
 namespace {
 
-constexpr int CELL_SHIFT = 10;                       // 1024-bp cells
+constexpr int CELL_SHIFT = 10;                       // 1024-bp cells of the L2-resident table
+constexpr int BM_SHIFT = 14;                         // 16384-bp blocks of the shared-memory bitmap
 constexpr int CELLS_PER_BIG = ((TILE - 1) >> CELL_SHIFT) + 2;
 constexpr int CELLS_PER_SMALL = ((SMALL_MAX - 1) >> CELL_SHIFT) + 2;
-constexpr int RTPB = 256;
+constexpr int RTPB = 512;                            // threads of the read passes
+constexpr uint32_t NONE = 0xffffffffu;
 
 // tile record, first half: what the read passes need
 //   x = global coordinate of the first genomic base of the tile
-//   y = tlen (bits 0..15) | reverse (bit 16) | class mask (bits 17..19)
+//   y = tlen (bits 0..15) | reverse (bit 16) | class mask (bits 17..19)      (never 0)
 // second half: x = region, y = offset of the tile inside the region's output
 struct Tiles {
     uint2* a;
     uint2* b;
+};
+
+// Cell table: one 16-byte record per 1024-bp cell = the first tile overlapping the cell, inline
+// (x, y as in Tiles::a; y == 0: no tile; z = tile id; w = index of the cell's overflow records
+// or NONE).  Overflow records have the same layout and end with a y == 0 sentinel.  One 16-byte
+// load answers "which tile does this read hit" for almost every read.
+struct Cells {
+    uint4* rec;          // [n_cell]
+    uint4* ovf;
+    uint32_t* cnt;       // [n_cell + 1] tiles per cell (counts down to 0 while slots are handed out)
+    uint32_t* ovf_n;     // [n_cell + 1] overflow records per cell (0 or cnt incl. the sentinel)
+    uint32_t* ovf_ptr;   // [n_cell + 1] exclusive prefix of ovf_n
+    uint32_t* bitmap;    // 1 bit per 16384-bp block: some tile overlaps it
 };
 
 __global__ void __launch_bounds__(CTA)
@@ -79,12 +100,12 @@ __device__ __forceinline__ int64_t owner_of(const int64_t* __restrict__ off, int
     return lo;
 }
 
-// One thread per tile: tile record + the count of every cell it overlaps.
+// One thread per tile: tile record, the count of every cell it overlaps, its bitmap bits.
 __global__ void __launch_bounds__(CTA)
 bkt_tiles_kernel(int64_t R, int64_t Tb, int64_t Ts, const int64_t* __restrict__ off_big,
                  const int64_t* __restrict__ off_small, const uint32_t* __restrict__ gs,
                  const int32_t* __restrict__ plen, const uint8_t* __restrict__ flags, Tiles tiles,
-                 uint32_t* __restrict__ cell_cnt) {
+                 uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ bitmap) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (t >= Tb + Ts) return;
     int64_t r;
@@ -108,86 +129,256 @@ bkt_tiles_kernel(int64_t R, int64_t Tb, int64_t Ts, const int64_t* __restrict__ 
     }
     tiles.a[t] = make_uint2(tstart, tlen | ((uint32_t)flags[r] << 16));
     tiles.b[t] = make_uint2((uint32_t)r, o_lo);
-    const uint32_t c1 = (tstart + tlen - 1u) >> CELL_SHIFT;
-    for (uint32_t c = tstart >> CELL_SHIFT; c <= c1; c++) atomicAdd(cell_cnt + c, 1u);
+    const uint32_t last = tstart + tlen - 1u;
+    for (uint32_t c = tstart >> CELL_SHIFT; c <= (last >> CELL_SHIFT); c++) atomicAdd(cell_cnt + c, 1u);
+    for (uint32_t b = tstart >> BM_SHIFT; b <= (last >> BM_SHIFT); b++)
+        atomicOr(bitmap + (b >> 5), 1u << (b & 31u));
 }
 
-// cell -> tiles lists.  cell_cnt counts down to zero while the slots are handed out.
+// cells holding two or more tiles keep all but one in overflow records (+ a sentinel)
 __global__ void __launch_bounds__(CTA)
-bkt_cells_kernel(int64_t T, Tiles tiles, uint32_t* __restrict__ cell_cnt,
-                 const uint32_t* __restrict__ cell_ptr, uint32_t* __restrict__ cell_list) {
+bkt_ovf_count_kernel(int64_t n, const uint32_t* __restrict__ cnt, uint32_t* __restrict__ ovf_n) {
+    const int64_t c = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t k = cnt[c];
+    ovf_n[c] = k >= 2u ? k : 0u;
+}
+
+// Fills the cell table.  cnt counts down to zero while the slots are handed out: slot 0 is the
+// inline record, slots 1.. go to the overflow run (the holder of slot 1 also writes the sentinel).
+__global__ void __launch_bounds__(CTA)
+bkt_cells_kernel(int64_t T, Tiles tiles, Cells cells) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (t >= T) return;
     const uint2 a = tiles.a[t];
-    const uint32_t tlen = a.y & 0xffffu;
-    const uint32_t c1 = (a.x + tlen - 1u) >> CELL_SHIFT;
-    for (uint32_t c = a.x >> CELL_SHIFT; c <= c1; c++) {
-        const uint32_t slot = atomicSub(cell_cnt + c, 1u) - 1u;
-        cell_list[cell_ptr[c] + slot] = (uint32_t)t;
-    }
-}
-
-// The walk both read passes share.  A (read, tile) hit is credited in exactly one cell: the one
-// holding the first base of their intersection.
-template <bool SCATTER, bool STRANDED>
-__device__ __forceinline__ void visit_read(uint32_t s, uint32_t e1, int st,
-                                           const uint32_t* __restrict__ cell_ptr,
-                                           const uint32_t* __restrict__ cell_list,
-                                           const uint2* __restrict__ tile_a,
-                                           unsigned long long* __restrict__ tile_cnt,
-                                           const int64_t* __restrict__ boff,
-                                           uint32_t* __restrict__ bucket) {
-    if (e1 <= s) return;
-    const unsigned bit = st > 0 ? 0u : (st < 0 ? 1u : 2u);
-    const uint32_t c1 = (e1 - 1u) >> CELL_SHIFT;
-    for (uint32_t c = s >> CELL_SHIFT; c <= c1; c++) {
-        const uint32_t ja = __ldg(cell_ptr + c), jb = __ldg(cell_ptr + c + 1);
-        for (uint32_t j = ja; j < jb; j++) {
-            const uint32_t t = __ldg(cell_list + j);
-            const uint2 a = __ldg(tile_a + t);
-            const uint32_t ts = a.x, tl = a.y & 0xffffu;
-            if (!(ts < e1 && ts + tl > s)) continue;
-            const uint32_t is = max(ts, s);
-            if ((is >> CELL_SHIFT) != c) continue;
-            if (STRANDED && !((a.y >> (17 + bit)) & 1u)) continue;
-            if (!SCATTER) {
-                atomicAdd(tile_cnt + t, 1ull);
-            } else {
-                const unsigned long long slot = atomicAdd(tile_cnt + t, ~0ull) - 1ull;
-                uint32_t lo = is - ts, hi = min(e1, ts + tl) - ts;      // covered [lo, hi)
-                if (a.y & 0x10000u) {                                     // '-' region: mirror
-                    const uint32_t l2 = tl - hi;
-                    hi = tl - lo;
-                    lo = l2;
-                }
-                bucket[boff[t] + (int64_t)slot] = lo | (hi << 16);
-            }
+    const uint32_t last = a.x + (a.y & 0xffffu) - 1u;
+    for (uint32_t c = a.x >> CELL_SHIFT; c <= (last >> CELL_SHIFT); c++) {
+        const uint32_t slot = atomicSub(cells.cnt + c, 1u) - 1u;
+        const uint32_t p0 = cells.ovf_ptr[c], p1 = cells.ovf_ptr[c + 1];
+        if (slot == 0u) {
+            cells.rec[c] = make_uint4(a.x, a.y, (uint32_t)t, p1 > p0 ? p0 : NONE);
+        } else {
+            cells.ovf[p0 + slot - 1u] = make_uint4(a.x, a.y, (uint32_t)t, 0u);
+            if (slot == 1u) cells.ovf[p1 - 1u] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
 
-template <bool SCATTER, bool STRANDED>
-__global__ void __launch_bounds__(RTPB)
-bkt_reads_kernel(int64_t n, const uint32_t* __restrict__ g_start,
-                 const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
-                 const uint32_t* __restrict__ cell_ptr, const uint32_t* __restrict__ cell_list,
-                 const uint2* __restrict__ tile_a, unsigned long long* __restrict__ tile_cnt,
-                 const int64_t* __restrict__ boff, uint32_t* __restrict__ bucket) {
-    const int64_t stride = (int64_t)gridDim.x * RTPB;
-    const int64_t n_vec = n >> 2;
-    for (int64_t v = (int64_t)blockIdx.x * RTPB + threadIdx.x; v < n_vec; v += stride) {
-        const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(g_start) + v);
-        const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(g_end1) + v);
-        char4 t4 = make_char4(0, 0, 0, 0);
-        if (STRANDED && strand) t4 = __ldg(reinterpret_cast<const char4*>(strand) + v);
-        visit_read<SCATTER, STRANDED>(s4.x, e4.x, t4.x, cell_ptr, cell_list, tile_a, tile_cnt, boff, bucket);
-        visit_read<SCATTER, STRANDED>(s4.y, e4.y, t4.y, cell_ptr, cell_list, tile_a, tile_cnt, boff, bucket);
-        visit_read<SCATTER, STRANDED>(s4.z, e4.z, t4.z, cell_ptr, cell_list, tile_a, tile_cnt, boff, bucket);
-        visit_read<SCATTER, STRANDED>(s4.w, e4.w, t4.w, cell_ptr, cell_list, tile_a, tile_cnt, boff, bucket);
+// One (read, tile record) test.  A hit is credited in exactly one cell: the one holding the first
+// base of the intersection.  On a hit the read is clipped to the tile and packed as one event
+// pair (first covered output | one past the last, << 16), mirrored on '-' regions so that the
+// tile kernels only ever scan forwards.
+template <bool STRANDED>
+__device__ __forceinline__ bool record_hit(const uint4 rec, uint32_t c, uint32_t s, uint32_t e1,
+                                           unsigned bit, uint32_t* packed) {
+    const uint32_t ts = rec.x, tl = rec.y & 0xffffu;
+    if (!(ts < e1 && ts + tl > s)) return false;
+    const uint32_t is = max(ts, s);
+    if ((is >> CELL_SHIFT) != c) return false;
+    if (STRANDED && !((rec.y >> (17 + bit)) & 1u)) return false;
+    uint32_t lo = is - ts, hi = min(e1, ts + tl) - ts;           // covered [lo, hi)
+    if (rec.y & 0x10000u) {                                       // '-' region: mirror
+        const uint32_t l2 = tl - hi;
+        hi = tl - lo;
+        lo = l2;
     }
-    for (int64_t i = n_vec * 4 + (int64_t)blockIdx.x * RTPB + threadIdx.x; i < n; i += stride)
-        visit_read<SCATTER, STRANDED>(g_start[i], g_end1[i], (STRANDED && strand) ? (int)strand[i] : 0,
-                                      cell_ptr, cell_list, tile_a, tile_cnt, boff, bucket);
+    *packed = lo | (hi << 16);
+    return true;
+}
+
+// ---- pass 1: find ---------------------------------------------------------------------------
+// Every read -> the tiles it overlaps.  Persistent CTAs keep the block bitmap in shared memory;
+// the reads stream in with 16-byte evict-first loads.  The work is irregular (most reads of a
+// sparse mask hit nothing, some hit several tiles), so each warp runs it through two small
+// shared-memory queues and stays converged:
+//   item queue   (read, cell) pairs that passed the bitmap; a ROUND pops 32 of them, one per
+//                lane, loads the 16-byte cell record (or overflow record) and tests it; a record
+//                with a successor re-queues the read for the next record
+//   hit buffer   (tile, event pair) of the hits; flushed 128+ at a time to the global hit list
+//                with ONE atomic reservation and coalesced 8-byte stores
+// Each hit also bumps its tile's counter (fire-and-forget RED).  If the hit list overflows its
+// capacity the counters are still exact and the caller falls back to bkt_rescatter_kernel.
+constexpr int RWARPS = RTPB / 32;
+constexpr int QCAP = 64;
+constexpr int HB_FLUSH = 128;
+constexpr int HB_CAP = HB_FLUSH + 32;
+constexpr size_t FIND_SMEM_FIXED = (size_t)RWARPS * (QCAP * sizeof(uint4) + HB_CAP * sizeof(uint2));
+
+struct FindOut {
+    unsigned long long* tile_cnt;
+    uint2* hits;                    // (tile, event pair)
+    unsigned long long cap;         // entries available in `hits`
+    unsigned long long* hit_n;      // entries reserved so far (> cap: the list is incomplete)
+};
+
+template <bool STRANDED>
+__global__ void __launch_bounds__(RTPB)
+bkt_find_kernel(int64_t n, const uint32_t* __restrict__ g_start,
+                const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
+                const uint32_t* __restrict__ bitmap, int bm_words,
+                const uint4* __restrict__ cell_rec, const uint4* __restrict__ ovf, FindOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* q = reinterpret_cast<uint4*>(smem_raw) + (threadIdx.x >> 5) * QCAP;
+    uint2* hb = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(smem_raw) + RWARPS * QCAP) +
+                (threadIdx.x >> 5) * HB_CAP;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw + FIND_SMEM_FIXED);
+    for (int i = threadIdx.x; i < bm_words; i += RTPB) bm[i] = bitmap[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int qn = 0, hn = 0;             // warp-uniform fill levels
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.hit_n, (unsigned long long)hn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + (unsigned long long)hn <= out.cap)
+            for (int i = lane; i < hn; i += 32) out.hits[base + i] = hb[i];
+        hn = 0;
+        __syncwarp();
+    };
+    // pop the last `cnt` items (cnt <= 32), one per lane
+    auto round = [&](int cnt) {
+        __syncwarp();
+        const bool act = (int)lane < cnt;
+        uint4 it = make_uint4(0, 0, 0, 0);
+        if (act) it = q[qn - cnt + (int)lane];
+        qn -= cnt;
+        __syncwarp();
+        bool hit = false, more = false;
+        uint32_t tile = 0, packed = 0, next = 0;
+        if (act) {
+            const uint32_t c = it.z & 0x3fffffu;
+            const bool is_ovf = (it.w >> 31) != 0u;
+            const uint32_t idx = it.w & 0x7fffffffu;
+            const uint4 rec = is_ovf ? __ldg(ovf + idx) : __ldg(cell_rec + c);
+            if (rec.y != 0u) {
+                hit = record_hit<STRANDED>(rec, c, it.x, it.y, it.z >> 30, &packed);
+                tile = rec.z;
+                if (is_ovf) {
+                    more = true;            // the run ends with a y == 0 sentinel
+                    next = idx + 1u;
+                } else if (rec.w != NONE) {
+                    more = true;
+                    next = rec.w;
+                }
+            }
+        }
+        const unsigned mm = __ballot_sync(0xffffffffu, more);
+        if (more) q[qn + __popc(mm & lt)] = make_uint4(it.x, it.y, it.z, 0x80000000u | next);
+        qn += __popc(mm);
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            atomicAdd(out.tile_cnt + tile, 1ull);
+            hb[hn + __popc(hm & lt)] = make_uint2(tile, packed);
+        }
+        hn += __popc(hm);
+        if (hn >= HB_FLUSH) flush();
+    };
+    // one read per lane (invalid lanes pass e1 = 0)
+    auto slot = [&](uint32_t s, uint32_t e1, int st) {
+        bool cand = e1 > s;
+        uint32_t cur = s >> CELL_SHIFT, c1 = 0;
+        if (cand) {
+            const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
+            cand = (b1 > b0 + 1u) || (((bm[b0 >> 5] >> (b0 & 31u)) | (bm[b1 >> 5] >> (b1 & 31u))) & 1u);
+            c1 = (e1 - 1u) >> CELL_SHIFT;
+        }
+        const uint32_t tag = (st > 0 ? 0u : (st < 0 ? 1u : 2u)) << 30;
+        for (;;) {
+            const bool has = cand && cur <= c1;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (m == 0u) break;
+            if (has) q[qn + __popc(m & lt)] = make_uint4(s, e1, cur | tag, 0u);
+            qn += __popc(m);
+            cur++;
+            while (qn >= 32) round(32);
+        }
+    };
+
+    const int64_t n_vec = n >> 2;
+    const int64_t warps_total = (int64_t)gridDim.x * RWARPS;
+    const int64_t gw = (int64_t)blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    for (int64_t base = gw * 32; base < n_vec; base += warps_total * 32) {
+        const int64_t v = base + lane;
+        uint4 s4 = make_uint4(0, 0, 0, 0), e4 = make_uint4(0, 0, 0, 0);
+        char4 t4 = make_char4(0, 0, 0, 0);
+        if (v < n_vec) {
+            s4 = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
+            e4 = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
+            if (STRANDED && strand) t4 = __ldcs(reinterpret_cast<const char4*>(strand) + v);
+        }
+        slot(s4.x, e4.x, t4.x);
+        slot(s4.y, e4.y, t4.y);
+        slot(s4.z, e4.z, t4.z);
+        slot(s4.w, e4.w, t4.w);
+    }
+    if (gw == 0) {                  // the n % 4 tail
+        const int64_t i = n_vec * 4 + lane;
+        const bool ok = i < n;
+        slot(ok ? g_start[i] : 0u, ok ? g_end1[i] : 0u, (ok && STRANDED && strand) ? (int)strand[i] : 0);
+    }
+    while (qn > 0) round(min(qn, 32));
+    if (hn > 0) flush();
+}
+
+// ---- pass 2: place --------------------------------------------------------------------------
+// hit list -> per-tile buckets.  `cursor` starts at the tile's bucket offset.
+__global__ void __launch_bounds__(CTA)
+bkt_place_kernel(unsigned long long n_hits, const uint2* __restrict__ hits,
+                 unsigned long long* __restrict__ cursor, uint32_t* __restrict__ bucket) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * CTA;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * CTA + threadIdx.x; i < n_hits;
+         i += stride) {
+        const uint2 h = __ldcs(hits + i);
+        const unsigned long long slot = atomicAdd(cursor + h.x, 1ull);
+        bucket[slot] = h.y;
+    }
+}
+
+// ---- pass 2, fallback: the hit list did not fit, walk the reads again -------------------------
+template <bool STRANDED>
+__device__ __forceinline__ void rescatter_read(uint32_t s, uint32_t e1, int st,
+                                               const uint32_t* __restrict__ bm,
+                                               const uint4* __restrict__ cell_rec,
+                                               const uint4* __restrict__ ovf,
+                                               unsigned long long* __restrict__ cursor,
+                                               uint32_t* __restrict__ bucket) {
+    if (e1 <= s) return;
+    const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
+    if (!((b1 > b0 + 1u) || (((bm[b0 >> 5] >> (b0 & 31u)) | (bm[b1 >> 5] >> (b1 & 31u))) & 1u))) return;
+    const unsigned bit = st > 0 ? 0u : (st < 0 ? 1u : 2u);
+    const uint32_t c1 = (e1 - 1u) >> CELL_SHIFT;
+    for (uint32_t c = s >> CELL_SHIFT; c <= c1; c++) {
+        uint4 rec = __ldg(cell_rec + c);
+        if (rec.y == 0u) continue;
+        uint32_t p = rec.w, packed;
+        for (;;) {
+            if (record_hit<STRANDED>(rec, c, s, e1, bit, &packed))
+                bucket[atomicAdd(cursor + rec.z, 1ull)] = packed;
+            if (p == NONE) break;
+            rec = __ldg(ovf + p++);
+            if (rec.y == 0u) break;
+        }
+    }
+}
+
+template <bool STRANDED>
+__global__ void __launch_bounds__(RTPB)
+bkt_rescatter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
+                     const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
+                     const uint32_t* __restrict__ bitmap, int bm_words,
+                     const uint4* __restrict__ cell_rec, const uint4* __restrict__ ovf,
+                     unsigned long long* __restrict__ cursor, uint32_t* __restrict__ bucket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int i = threadIdx.x; i < bm_words; i += RTPB) bm[i] = bitmap[i];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * RTPB;
+    for (int64_t i = (int64_t)blockIdx.x * RTPB + threadIdx.x; i < n; i += stride)
+        rescatter_read<STRANDED>(__ldcs(g_start + i), __ldcs(g_end1 + i),
+                                 (STRANDED && strand) ? (int)strand[i] : 0, bm, cell_rec, ovf,
+                                 cursor, bucket);
 }
 
 // NULL rule (coverage.R:198,224-225): no overlapping read in any tile of the region.
@@ -225,68 +416,130 @@ bkt_null_kernel(int64_t R, int64_t Tb, const int64_t* __restrict__ off_big,
     }
 }
 
-// One CTA per tile of a long region.
+// Everything a tile kernel needs, in one 32-byte record (one dependent load instead of five).
+struct __align__(16) TileDesc {
+    int64_t out;         // offset of the tile's first output in the dense coverage
+    int64_t b0;          // first bucket entry
+    uint32_t n;          // bucket entries
+    int32_t tlen;        // outputs; 0 = the region is NULL, nothing to write
+    int32_t pad[2];
+};
+
 __global__ void __launch_bounds__(CTA)
-bkt_tile_kernel(Tiles tiles, const int64_t* __restrict__ boff, const uint32_t* __restrict__ bucket,
+bkt_desc_kernel(int64_t T, Tiles tiles, const int64_t* __restrict__ boff,
                 const uint8_t* __restrict__ is_null, const int64_t* __restrict__ off,
-                int32_t* __restrict__ cov) {
-    __shared__ __align__(16) int diff[TILE];
-    __shared__ int rowpre[MAX_ROWS + 1];
-    const int tid = threadIdx.x;
-    const int64_t t = blockIdx.x;
+                TileDesc* __restrict__ desc) {
+    const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (t >= T) return;
     const uint2 b = tiles.b[t];
-    if (is_null[b.x]) return;
-    const int tlen = (int)(tiles.a[t].y & 0xffffu);
-    const int nrows = (tlen + ROW - 1) / ROW;
-    for (int i = tid; i < nrows * (ROW / 4); i += CTA)
-        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-    const int64_t b1 = boff[t + 1];
-    for (int64_t i = boff[t] + tid; i < b1; i += CTA) {
-        const uint32_t e = __ldg(bucket + i);
-        const int lo = (int)(e & 0xffffu), hi = (int)(e >> 16);
-        atomicAdd(diff + lo, 1);
-        if (hi < tlen) atomicSub(diff + hi, 1);
-    }
-    __syncthreads();
-    block_scan_store(diff, tlen, 0, false, rowpre, cov + off[b.x] + b.y);
+    TileDesc d;
+    d.out = off[b.x] + b.y;
+    d.b0 = boff[t];
+    d.n = (uint32_t)(boff[t + 1] - boff[t]);
+    d.tlen = is_null[b.x] ? 0 : (int32_t)(tiles.a[t].y & 0xffffu);
+    d.pad[0] = d.pad[1] = 0;
+    desc[t] = d;
 }
 
-// One warp per short region (<= SMALL_MAX bases): warp-private tile, __syncwarp only.
+__device__ __forceinline__ TileDesc load_desc(const TileDesc* __restrict__ p) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    TileDesc d;
+    d.out = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
+    d.b0 = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+    d.n = (uint32_t)b.x;
+    d.tlen = b.y;
+    d.pad[0] = d.pad[1] = 0;
+    return d;
+}
+
+// Long regions: persistent CTAs walk the tiles.  Per tile: zero the shared-memory difference
+// array, add the bucket's event pairs with shared-memory atomics, scan, store.  The next tile's
+// descriptor and its first bucket entries are fetched before the current tile is scanned, so
+// their latency hides behind the scan and the stores.
+__global__ void __launch_bounds__(CTA, 5)
+bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* __restrict__ bucket,
+                int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int diff[TILE];
+    __shared__ int wtot[WARPS];
+    const int tid = threadIdx.x;
+    int64_t t = blockIdx.x;
+    if (t >= Tb) return;
+    TileDesc d = load_desc(desc + t);
+    uint32_t e0 = NONE, e1 = NONE;                  // NONE never is a valid pair (lo <= hi)
+    if ((uint32_t)tid < d.n) e0 = __ldcs(bucket + d.b0 + tid);
+    if ((uint32_t)tid + CTA < d.n) e1 = __ldcs(bucket + d.b0 + tid + CTA);
+    for (;;) {
+        const int tlen = d.tlen;
+        const int64_t tn = t + gridDim.x;
+        TileDesc dn;
+        dn.n = 0;
+        dn.tlen = 0;
+        if (tn < Tb) dn = load_desc(desc + tn);
+        if (tlen > 0) {
+            const int nrows = (tlen + ROW - 1) / ROW;
+            const int zrows = (nrows + WARPS - 1) / WARPS * WARPS;   // block_scan_store_fwd's padding
+            for (int i = tid; i < zrows * (ROW / 4); i += CTA)
+                reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
+            __syncthreads();
+            auto add = [&](uint32_t e) {
+                const int lo = (int)(e & 0xffffu), hi = (int)(e >> 16);
+                atomicAdd(diff + lo, 1);
+                if (hi < tlen) atomicSub(diff + hi, 1);
+            };
+            if (e0 != NONE) add(e0);
+            if (e1 != NONE) add(e1);
+            for (uint32_t i = 2 * CTA + tid; i < d.n; i += CTA) add(__ldcs(bucket + d.b0 + i));
+        }
+        // prefetch the next tile's first entries (consumed after the next zeroing)
+        e0 = e1 = NONE;
+        if (tn < Tb) {
+            if ((uint32_t)tid < dn.n) e0 = __ldcs(bucket + dn.b0 + tid);
+            if ((uint32_t)tid + CTA < dn.n) e1 = __ldcs(bucket + dn.b0 + tid + CTA);
+        }
+        if (tlen > 0) {
+            __syncthreads();
+            block_scan_store_fwd(diff, tlen, wtot, cov + d.out);
+        }
+        if (tn >= Tb) break;
+        __syncthreads();            // diff and wtot are reused
+        d = dn;
+        t = tn;
+    }
+}
+
+// Short regions (<= SMALL_MAX bases): one warp per region, warp-private tile, __syncwarp only.
 __global__ void __launch_bounds__(CTA)
-bkt_small_kernel(int64_t Tb, int64_t Ts, Tiles tiles, const int64_t* __restrict__ boff,
-                 const uint32_t* __restrict__ bucket, const uint8_t* __restrict__ is_null,
-                 const int64_t* __restrict__ off, int32_t* __restrict__ cov) {
+bkt_small_kernel(int64_t Ts, const TileDesc* __restrict__ desc, const uint32_t* __restrict__ bucket,
+                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int sm[WARPS][SMALL_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ts = (int64_t)blockIdx.x * WARPS + warp;
     if (ts >= Ts) return;
-    const int64_t t = Tb + ts;
-    const uint32_t r = tiles.b[t].x;
-    if (is_null[r]) return;
-    const int L = (int)(tiles.a[t].y & 0xffffu);
+    const TileDesc d = load_desc(desc + ts);
+    const int L = d.tlen;
+    if (L == 0) return;
     int* diff = sm[warp];
     const int nrows = (L + ROW - 1) / ROW;
     for (int i = lane; i < nrows * (ROW / 4); i += 32)
         reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
     __syncwarp();
-    const int64_t b1 = boff[t + 1];
-    for (int64_t i = boff[t] + lane; i < b1; i += 32) {
-        const uint32_t e = __ldg(bucket + i);
+    for (uint32_t i = lane; i < d.n; i += 32) {
+        const uint32_t e = __ldcs(bucket + d.b0 + i);
         const int lo = (int)(e & 0xffffu), hi = (int)(e >> 16);
         atomicAdd(diff + lo, 1);
         if (hi < L) atomicSub(diff + hi, 1);
     }
     __syncwarp();
-    int32_t* dst = cov + off[r];
-    int pre = 0;
-    for (int row = 0; row < nrows; row++)
-        pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, L - row * ROW, dst + row * ROW);
+    warp_scan_store_fwd(diff, L, cov + d.out);
 }
 
-inline unsigned reads_grid(int64_t n) {
+inline unsigned reads_grid(int64_t n, size_t smem) {
     int64_t b = ((n + 3) / 4 + RTPB - 1) / RTPB;
-    const int64_t cap = (int64_t)g_ctx.sm_count * 8;
+    // persistent CTAs: as many as fit per SM beside their queues and bitmap copies
+    int per_sm = 2048 / RTPB;
+    while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 220u * 1024u) per_sm--;
+    const int64_t cap = (int64_t)g_ctx.sm_count * per_sm;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (unsigned)b;
@@ -305,13 +558,18 @@ struct Work {
     unsigned int* err = nullptr;
     unsigned long long* stats = nullptr;
     Tiles tiles = {nullptr, nullptr};
-    uint32_t* cell_cnt = nullptr;
-    uint32_t* cell_ptr = nullptr;
-    uint32_t* cell_list = nullptr;
-    unsigned long long* tile_cnt = nullptr;
+    Cells cells = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int bm_words = 0;
+    unsigned long long* tile_cnt = nullptr;   // counts, then (pass 2) bucket cursors
+    uint2* hits = nullptr;
+    unsigned long long* hit_n = nullptr;
     int64_t* boff = nullptr;
     uint32_t* bucket = nullptr;
+    TileDesc* desc = nullptr;
     ~Work() {
+        dfree(hits);
+        dfree(hit_n);
+        dfree(desc);
         dfree(gs);
         dfree(plen);
         dfree(flags);
@@ -324,9 +582,12 @@ struct Work {
         dfree(stats);
         dfree(tiles.a);
         dfree(tiles.b);
-        dfree(cell_cnt);
-        dfree(cell_ptr);
-        dfree(cell_list);
+        dfree(cells.rec);
+        dfree(cells.ovf);
+        dfree(cells.cnt);
+        dfree(cells.ovf_n);
+        dfree(cells.ovf_ptr);
+        dfree(cells.bitmap);
         dfree(tile_cnt);
         dfree(boff);
         dfree(bucket);
@@ -334,16 +595,31 @@ struct Work {
 };
 
 template <bool STRANDED>
-int launch_reads_passes(bool scatter, const ReadsIdx& rd, const Work& w) {
-    const unsigned grid = reads_grid(rd.n);
-    if (!scatter)
-        bkt_reads_kernel<false, STRANDED><<<grid, RTPB, 0, g_ctx.stream>>>(
-            rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cell_ptr, w.cell_list, w.tiles.a,
-            w.tile_cnt, w.boff, w.bucket);
-    else
-        bkt_reads_kernel<true, STRANDED><<<grid, RTPB, 0, g_ctx.stream>>>(
-            rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cell_ptr, w.cell_list, w.tiles.a,
-            w.tile_cnt, w.boff, w.bucket);
+int launch_find(const ReadsIdx& rd, const Work& w, unsigned long long cap) {
+    const size_t smem = FIND_SMEM_FIXED + (size_t)w.bm_words * 4;
+    auto kern = bkt_find_kernel<STRANDED>;
+    RCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FindOut out;
+    out.tile_cnt = w.tile_cnt;
+    out.hits = w.hits;
+    out.cap = cap;
+    out.hit_n = w.hit_n;
+    kern<<<reads_grid(rd.n, smem), RTPB, smem, g_ctx.stream>>>(
+        rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, w.cells.rec,
+        w.cells.ovf, out);
+    RCP_LAUNCHED();
+    return RCP_OK;
+}
+
+template <bool STRANDED>
+int launch_rescatter(const ReadsIdx& rd, const Work& w) {
+    const size_t smem = (size_t)w.bm_words * 4;
+    auto kern = bkt_rescatter_kernel<STRANDED>;
+    RCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (rd.n + RTPB - 1) / RTPB;
+    kern<<<(unsigned)std::min<int64_t>(blocks, (int64_t)g_ctx.sm_count * 4), RTPB, smem,
+           g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words,
+                           w.cells.rec, w.cells.ovf, w.tile_cnt, w.bucket);
     RCP_LAUNCHED();
     return RCP_OK;
 }
@@ -383,9 +659,9 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
 
     struct Host {
         int64_t Tb, Ts, total_padded, hits;
-        unsigned long long stats[2];
+        unsigned long long stats[2], listed;
         unsigned int err;
-    } h = {0, 0, 0, 0, {0, 0}, 0};
+    } h = {0, 0, 0, 0, {0, 0}, 0, 0};
 
     // ---- 1. plan: windows and tile counts ------------------------------------------------
     {
@@ -409,36 +685,51 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
     if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
 
-    // ---- 2. tiles and cell lists ----------------------------------------------------------
-    const int64_t n_cell = ((int64_t)rd.chrom_off[(size_t)rd.n_chrom] >> CELL_SHIFT) + 2;
+    // ---- 2. tiles, cell table, block bitmap -------------------------------------------------
+    const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
+    const int64_t n_cell = (span >> CELL_SHIFT) + 2;
+    const int64_t pairs = Tb * CELLS_PER_BIG + Ts * CELLS_PER_SMALL;      // (tile, cell) bound
+    w.bm_words = (int)(((span >> BM_SHIFT) + 32) / 32);
     RCP_TRY(dalloc(&w.tiles.a, (size_t)T));
     RCP_TRY(dalloc(&w.tiles.b, (size_t)T));
     RCP_TRY(dalloc(&w.tile_cnt, (size_t)T + 1));
     RCP_TRY(dalloc(&w.boff, (size_t)T + 1));
-    RCP_TRY(dalloc(&w.cell_cnt, (size_t)n_cell + 1));
-    RCP_TRY(dalloc(&w.cell_ptr, (size_t)n_cell + 1));
-    RCP_TRY(dalloc(&w.cell_list, (size_t)(Tb * CELLS_PER_BIG + Ts * CELLS_PER_SMALL)));
+    RCP_TRY(dalloc(&w.cells.rec, (size_t)n_cell));
+    RCP_TRY(dalloc(&w.cells.cnt, (size_t)n_cell + 1));
+    RCP_TRY(dalloc(&w.cells.ovf_n, (size_t)n_cell + 1));
+    RCP_TRY(dalloc(&w.cells.ovf_ptr, (size_t)n_cell + 1));
+    RCP_TRY(dalloc(&w.cells.ovf, (size_t)(pairs + pairs / 2 + 1)));
+    RCP_TRY(dalloc(&w.cells.bitmap, (size_t)w.bm_words));
     {
         StageTimer t(ST_BKT_PLAN);
-        RCP_CUDA(cudaMemsetAsync(w.cell_cnt, 0, ((size_t)n_cell + 1) * 4, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(w.cells.rec, 0, (size_t)n_cell * sizeof(uint4), g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(w.cells.cnt, 0, ((size_t)n_cell + 1) * 4, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(w.cells.bitmap, 0, (size_t)w.bm_words * 4, g_ctx.stream));
         RCP_CUDA(cudaMemsetAsync(w.tile_cnt, 0, ((size_t)T + 1) * 8, g_ctx.stream));
         if (T > 0) {
             bkt_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(
-                R, Tb, Ts, w.off_big, w.off_small, w.gs, w.plen, w.flags, w.tiles, w.cell_cnt);
+                R, Tb, Ts, w.off_big, w.off_small, w.gs, w.plen, w.flags, w.tiles, w.cells.cnt,
+                w.cells.bitmap);
             RCP_LAUNCHED();
-        }
-        RCP_TRY(exclusive_scan_u32(w.cell_cnt, w.cell_ptr, n_cell + 1, nullptr));
-        if (T > 0) {
-            bkt_cells_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, w.tiles, w.cell_cnt,
-                                                                          w.cell_ptr, w.cell_list);
+            bkt_ovf_count_kernel<<<blocks_for(n_cell + 1, CTA), CTA, 0, g_ctx.stream>>>(
+                n_cell + 1, w.cells.cnt, w.cells.ovf_n);
+            RCP_LAUNCHED();
+            RCP_TRY(exclusive_scan_u32(w.cells.ovf_n, w.cells.ovf_ptr, n_cell + 1, nullptr));
+            bkt_cells_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, w.tiles, w.cells);
             RCP_LAUNCHED();
         }
     }
-    // ---- 3. count pass ----------------------------------------------------------------------
+    // ---- 3. pass 1: find the (read, tile) hits; count them per tile -------------------------
+    // The hit list holds one entry per read by default: enough unless regions overlap heavily
+    // (then pass 2 walks the reads again instead).  RCP_BKT_HIT_CAP overrides it (tests).
+    unsigned long long hit_cap = (unsigned long long)std::max<int64_t>(rd.n, 4096);
+    if (const char* e = getenv("RCP_BKT_HIT_CAP")) hit_cap = strtoull(e, nullptr, 10);
+    RCP_TRY(dalloc(&w.hits, (size_t)hit_cap));
+    RCP_TRY(dalloc(&w.hit_n, 1));
+    RCP_CUDA(cudaMemsetAsync(w.hit_n, 0, 8, g_ctx.stream));
     if (T > 0 && rd.n > 0) {
         StageTimer t(ST_BKT_COUNT);
-        RCP_TRY(stranded ? launch_reads_passes<true>(false, rd, w)
-                         : launch_reads_passes<false>(false, rd, w));
+        RCP_TRY(stranded ? launch_find<true>(rd, w, hit_cap) : launch_find<false>(rd, w, hit_cap));
     }
     // ---- 4. NULL rule, offsets ---------------------------------------------------------------
     {
@@ -456,6 +747,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.hits, w.boff + T, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.listed, w.hit_n, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
@@ -463,23 +755,38 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
     if (h.hits == 0) return RCP_OK;                 // every region is NULL
     RCP_TRY(dalloc(&w.bucket, (size_t)h.hits));
-    // ---- 5. scatter pass --------------------------------------------------------------------
+    RCP_TRY(dalloc(&w.desc, (size_t)T));
+    // ---- 5. pass 2: hits -> buckets (the counters become cursors starting at the offsets) -----
     {
         StageTimer t(ST_BKT_SCATTER);
-        RCP_TRY(stranded ? launch_reads_passes<true>(true, rd, w)
-                         : launch_reads_passes<false>(true, rd, w));
+        RCP_CUDA(cudaMemcpyAsync(w.tile_cnt, w.boff, (size_t)T * 8, cudaMemcpyDeviceToDevice,
+                                 g_ctx.stream));
+        if (h.listed <= hit_cap) {
+            const int64_t blocks = ((int64_t)h.listed + CTA - 1) / CTA;
+            bkt_place_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)g_ctx.sm_count * 16), CTA,
+                               0, g_ctx.stream>>>(h.listed, w.hits, w.tile_cnt, w.bucket);
+            RCP_LAUNCHED();
+        } else {
+            RCP_TRY(stranded ? launch_rescatter<true>(rd, w) : launch_rescatter<false>(rd, w));
+        }
+        bkt_desc_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, w.tiles, w.boff, cv->is_null,
+                                                                    cv->off, w.desc);
+        RCP_LAUNCHED();
     }
     // ---- 6. tiles -> coverage ---------------------------------------------------------------
     if (Tb > 0) {
         StageTimer t(ST_BKT_TILE);
-        bkt_tile_kernel<<<(unsigned)Tb, CTA, 0, g_ctx.stream>>>(w.tiles, w.boff, w.bucket,
-                                                                cv->is_null, cv->off, cv->cov);
+        int per_sm = 0;     // persistent CTAs: exactly one resident wave
+        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bkt_tile_kernel, CTA, 0));
+        if (per_sm < 1) per_sm = 1;
+        bkt_tile_kernel<<<(unsigned)std::min<int64_t>(Tb, (int64_t)g_ctx.sm_count * per_sm), CTA, 0,
+                          g_ctx.stream>>>(Tb, w.desc, w.bucket, cv->cov);
         RCP_LAUNCHED();
     }
     if (Ts > 0) {
         StageTimer t(ST_BKT_SMALL);
-        bkt_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(
-            Tb, Ts, w.tiles, w.boff, w.bucket, cv->is_null, cv->off, cv->cov);
+        bkt_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, w.desc + Tb, w.bucket,
+                                                                         cv->cov);
         RCP_LAUNCHED();
     }
     return RCP_OK;

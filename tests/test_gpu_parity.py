@@ -113,6 +113,33 @@ def test_random_regions_all_strand_modes(gpu, seed, ignore, filt):
     assert any(w is None for w in want) and sum(w is not None for w in want) > 50
 
 
+def test_bucket_path_overlapping_regions_and_hit_list_overflow(gpu, monkeypatch):
+    """Heavily overlapping regions give several hits per read (overflow runs of the cell table);
+    a hit list that is too small makes pass 2 walk the reads again.  Same results either way."""
+    rb = gpu
+    rng = np.random.default_rng(31)
+    clen = [120000, 40000]
+    chrom, s, e, st = synth_reads(rng, 40000, clen, width=(1, 3000))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    # 40 copies of the same few windows + nested windows + random ones, all strands
+    rc, rs, re_, rst = _regions(rng, 200, clen, [50, 500, 1024, 1025, 3000, 7168, 7169, 30000])
+    rc = np.concatenate([rc, np.zeros(120, dtype=rc.dtype)])
+    rs = np.concatenate([rs, np.tile([5000, 5000, 5100], 40)])
+    re_ = np.concatenate([re_, np.tile([5999, 25999, 5300], 40)])
+    rst = np.concatenate([rst, rng.choice(np.array([1, -1, 0], dtype=np.int8), size=120)])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    for ignore, filt in [(True, None), (False, None), (False, "+")]:
+        filt_code = None if filt is None else {"+": 1, "-": -1, "*": 0}[filt]
+        want = O.calc_coverage(o_reads, o_mask, filt_code, ignore)
+        monkeypatch.delenv("RCP_BKT_HIT_CAP", raising=False)
+        got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+        assert_coverage_equal(got.to_list(), want)
+        monkeypatch.setenv("RCP_BKT_HIT_CAP", "100")
+        got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+        assert_coverage_equal(got.to_list(), want)
+    monkeypatch.delenv("RCP_BKT_HIT_CAP", raising=False)
+
+
 def test_pileups_long_reads_and_no_strand(gpu):
     rb = gpu
     rng = np.random.default_rng(21)
