@@ -431,7 +431,10 @@ def run_b200(args):
         phases["profile+download"] += t_d - t_c
         return m
 
-    e2e_step()
+    # warm-up: two results alive at once, so that the library's pinned-buffer pool holds the two
+    # output matrices the timed loop alternates between (page-locking 32 MB costs ~12 ms)
+    keep = [e2e_step(), e2e_step()]
+    del keep
     for k in phases:
         phases[k] = 0.0
     barrier()

@@ -11,6 +11,7 @@ constexpr int WARPS = CTA / 32;
 constexpr int TILE = 7168;             // positions per CTA tile (28 KB of int32; 8 CTAs per SM)
 constexpr int ROW = 128;               // positions handled by one warp-wide int4 access
 constexpr int MAX_ROWS = TILE / ROW;   // 56
+static_assert(MAX_ROWS == 7 * WARPS, "tile kernels dispatch on 1..7 rows per warp");
 constexpr int SMALL_MAX = 1024;        // regions up to this length use the warp kernel
 constexpr int PAD = 32;                // region offsets are multiples of 32 ints (128 B)
 
@@ -198,27 +199,60 @@ __device__ __forceinline__ void warp_rows_out(const int* tile, int row0, int rpw
     }
 }
 
-// Whole CTA.  `diff` must be zero-padded up to WARPS * rpw rows, rpw = ceil(nrows / WARPS).
-// wtot needs WARPS ints.
+// rows [row0, row0 + RPW) of the scanned tile -> dst, fully unrolled
+template <int RPW>
+__device__ __forceinline__ void warp_rows_out_n(const int* tile, int row0, int tlen,
+                                                int32_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int base = row0 * ROW + lane * 4;
+    const int* src = tile + base;
+    int32_t* out = dst + base;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        const int o0 = base + k * ROW;
+        if (o0 + 3 < tlen) {
+            *reinterpret_cast<int4*>(out + k * ROW) = *reinterpret_cast<const int4*>(src + k * ROW);
+        } else if (o0 < tlen) {
+            const int4 o = *reinterpret_cast<const int4*>(src + k * ROW);
+            out[k * ROW] = o.x;
+            if (o0 + 1 < tlen) out[k * ROW + 1] = o.y;
+            if (o0 + 2 < tlen) out[k * ROW + 2] = o.z;
+        }
+    }
+}
+
+// Whole CTA, RPW rows per warp (compile-time: every loop unrolls, no predicates).  `diff` must be
+// zero-padded up to WARPS * RPW rows.  wtot needs WARPS ints.
+template <int RPW>
 __device__ __forceinline__ void block_scan_store_fwd(int* diff, int tlen, int* wtot,
                                                      int32_t* __restrict__ dst) {
-    constexpr int MAXR = MAX_ROWS / WARPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nrows = (tlen + ROW - 1) / ROW;
-    const int rpw = (nrows + WARPS - 1) / WARPS;
-    int* mine = diff + warp * rpw * ROW + lane * rpw * 4;
-    int4 v[MAXR];
-    const int sum = lane_load_sum<MAXR>(mine, rpw, v);
+    int* mine = diff + (warp * ROW + lane * 4) * RPW;
+    int4 v[RPW];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        v[k] = *(reinterpret_cast<const int4*>(mine) + k);
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
     const int inc = warp_inclusive_scan(sum);
     if (lane == 31) wtot[warp] = inc;
     __syncthreads();
-    int pre = 0;
+    int run = inc - sum;
 #pragma unroll
-    for (int w = 0; w < WARPS; w++)
-        if (w < warp) pre += wtot[w];
-    lane_rescan_store<MAXR>(mine, rpw, pre + inc - sum, v);
+    for (int w = 0; w < WARPS - 1; w++)
+        if (w < warp) run += wtot[w];
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        int4 o;
+        o.x = (run += v[k].x);
+        o.y = (run += v[k].y);
+        o.z = (run += v[k].z);
+        o.w = (run += v[k].w);
+        *(reinterpret_cast<int4*>(mine) + k) = o;
+    }
     __syncwarp();
-    warp_rows_out(diff, warp * rpw, rpw, tlen, dst);
+    warp_rows_out_n<RPW>(diff, warp * RPW, tlen, dst);
 }
 
 // One warp, warp-private tile of up to SMALL_MAX ints, zero-padded to whole rows.

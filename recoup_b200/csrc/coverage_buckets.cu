@@ -453,57 +453,76 @@ __device__ __forceinline__ TileDesc load_desc(const TileDesc* __restrict__ p) {
     return d;
 }
 
-// Long regions: persistent CTAs walk the tiles.  Per tile: zero the shared-memory difference
-// array, add the bucket's event pairs with shared-memory atomics, scan, store.  The next tile's
-// descriptor and its first bucket entries are fetched before the current tile is scanned, so
-// their latency hides behind the scan and the stores.
+// One tile, RPW rows per warp: zero the shared-memory difference array, add the bucket's event
+// pairs with shared-memory atomics, scan, store.  e0 / e1 are the bucket entries this thread
+// prefetched (NONE = none).
+template <int RPW>
+__device__ __forceinline__ void tile_body(int* diff, int* wtot, int tlen, uint32_t n,
+                                          const uint32_t* __restrict__ entries, uint32_t e0,
+                                          uint32_t e1, int32_t* __restrict__ dst) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < RPW; k++)       // WARPS * RPW rows = RPW int4 per thread
+        reinterpret_cast<int4*>(diff)[k * CTA + tid] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    auto add = [&](uint32_t e) {
+        const int lo = (int)(e & 0xffffu), hi = (int)(e >> 16);
+        atomicAdd(diff + lo, 1);
+        if (hi < tlen) atomicSub(diff + hi, 1);
+    };
+    if (e0 != NONE) add(e0);
+    if (e1 != NONE) add(e1);
+    for (uint32_t i = 2 * CTA + tid; i < n; i += CTA) add(__ldcs(entries + i));
+    __syncthreads();
+    block_scan_store_fwd<RPW>(diff, tlen, wtot, dst);
+}
+
+// Long regions: persistent CTAs walk the tiles.  The next tile's descriptor and its first bucket
+// entries are fetched before the current tile is processed, so their latency hides behind the
+// scan and the stores.
 __global__ void __launch_bounds__(CTA, 5)
 bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* __restrict__ bucket,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
     __shared__ int wtot[WARPS];
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x;
     int64_t t = blockIdx.x;
     if (t >= Tb) return;
     TileDesc d = load_desc(desc + t);
-    uint32_t e0 = NONE, e1 = NONE;                  // NONE never is a valid pair (lo <= hi)
-    if ((uint32_t)tid < d.n) e0 = __ldcs(bucket + d.b0 + tid);
-    if ((uint32_t)tid + CTA < d.n) e1 = __ldcs(bucket + d.b0 + tid + CTA);
+    uint32_t e0 = NONE, e1 = NONE;                  // NONE never is a valid pair (lo < hi)
+    if (tid < d.n) e0 = __ldcs(bucket + d.b0 + tid);
+    if (tid + CTA < d.n) e1 = __ldcs(bucket + d.b0 + tid + CTA);
     for (;;) {
-        const int tlen = d.tlen;
         const int64_t tn = t + gridDim.x;
         TileDesc dn;
+        dn.out = dn.b0 = 0;
         dn.n = 0;
         dn.tlen = 0;
-        if (tn < Tb) dn = load_desc(desc + tn);
-        if (tlen > 0) {
-            const int nrows = (tlen + ROW - 1) / ROW;
-            const int zrows = (nrows + WARPS - 1) / WARPS * WARPS;   // block_scan_store_fwd's padding
-            for (int i = tid; i < zrows * (ROW / 4); i += CTA)
-                reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
-            __syncthreads();
-            auto add = [&](uint32_t e) {
-                const int lo = (int)(e & 0xffffu), hi = (int)(e >> 16);
-                atomicAdd(diff + lo, 1);
-                if (hi < tlen) atomicSub(diff + hi, 1);
-            };
-            if (e0 != NONE) add(e0);
-            if (e1 != NONE) add(e1);
-            for (uint32_t i = 2 * CTA + tid; i < d.n; i += CTA) add(__ldcs(bucket + d.b0 + i));
-        }
-        // prefetch the next tile's first entries (consumed after the next zeroing)
-        e0 = e1 = NONE;
+        uint32_t f0 = NONE, f1 = NONE;
         if (tn < Tb) {
-            if ((uint32_t)tid < dn.n) e0 = __ldcs(bucket + dn.b0 + tid);
-            if ((uint32_t)tid + CTA < dn.n) e1 = __ldcs(bucket + dn.b0 + tid + CTA);
+            dn = load_desc(desc + tn);
+            if (tid < dn.n) f0 = __ldcs(bucket + dn.b0 + tid);
+            if (tid + CTA < dn.n) f1 = __ldcs(bucket + dn.b0 + tid + CTA);
         }
-        if (tlen > 0) {
-            __syncthreads();
-            block_scan_store_fwd(diff, tlen, wtot, cov + d.out);
+        if (d.tlen > 0) {
+            const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
+            const uint32_t* entries = bucket + d.b0;
+            int32_t* dst = cov + d.out;
+            switch (rpw) {
+                case 1: tile_body<1>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                case 2: tile_body<2>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                case 3: tile_body<3>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                case 4: tile_body<4>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                case 5: tile_body<5>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                case 6: tile_body<6>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+                default: tile_body<7>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
+            }
         }
         if (tn >= Tb) break;
         __syncthreads();            // diff and wtot are reused
         d = dn;
+        e0 = f0;
+        e1 = f1;
         t = tn;
     }
 }

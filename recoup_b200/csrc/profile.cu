@@ -50,6 +50,7 @@ struct BinArgs {
 };
 
 constexpr int STAGE_INTS = 12288;      // ints of one region staged in shared memory (48 KB)
+constexpr int STAGE_ALLOC = 13 * CTA * 4;   // + room for an odd number of int4 per thread (52 KB)
 constexpr int STAGE_MAX_BIN = 128;     // bins narrower than this use the staged path
 
 // Sum of src[lo, hi) by one warp with 16-byte loads where the index is 4-aligned (src itself is
@@ -105,50 +106,104 @@ __global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
     }
     // ---- bin edges: bin i has bsz + [rank[i] <= dif] elements (util.R:74-80) ----
     const int bsz = Ls / n, dif = Ls - bsz * n;
-    if (tid == 0) chunk_carry = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += CTA) {
-        const int i = c0 + tid;
-        const bool extra = (i < n) && (p.rank[i] <= dif);
-        const unsigned bal = __ballot_sync(0xffffffffu, extra);
-        if (lane == 0) wcount[warp] = __popc(bal);
+    if (dif == 0) {                     // equal bins: no rank table involved
+        for (int i = tid; i <= n; i += CTA) edges[i] = sg.a + i * bsz;
         __syncthreads();
-        int pre = chunk_carry;
-        for (int w = 0; w < warp; w++) pre += wcount[w];
-        pre += __popc(bal & ((1u << lane) - 1u));
-        if (i < n) edges[i] = sg.a + i * bsz + pre;
+    } else {
+        if (tid == 0) chunk_carry = 0;
         __syncthreads();
-        if (tid == CTA - 1) chunk_carry = pre + (extra ? 1 : 0);
+        for (int c0 = 0; c0 < n; c0 += CTA) {
+            const int i = c0 + tid;
+            const bool extra = (i < n) && (p.rank[i] <= dif);
+            const unsigned bal = __ballot_sync(0xffffffffu, extra);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();
+            int pre = chunk_carry;
+            for (int w = 0; w < warp; w++) pre += wcount[w];
+            pre += __popc(bal & ((1u << lane) - 1u));
+            if (i < n) edges[i] = sg.a + i * bsz + pre;
+            __syncthreads();
+            if (tid == CTA - 1) chunk_carry = pre + (extra ? 1 : 0);
+            __syncthreads();
+        }
+        if (tid == 0) edges[n] = sg.b;
         __syncthreads();
     }
-    if (tid == 0) edges[n] = sg.b;
-    __syncthreads();
     const int32_t* src = p.cov + p.off[r];
     if (!MEDIAN && bsz < STAGE_MAX_BIN) {
-        // ---- narrow bins: stage a run of whole bins in shared memory with coalesced 16-byte
-        // loads, then ONE THREAD PER BIN sums from shared memory (rotated start -> no bank
-        // conflicts), so the instruction count per coverage base stays ~5 ----
-        int* stage = sh + ((n + 1 + 3) & ~3);
+        // ---- narrow bins: a run of whole bins is staged in shared memory with coalesced 16-byte
+        // loads and turned IN PLACE into its inclusive prefix sum S (lane-serial: each thread
+        // scans an odd number of consecutive int4, one warp scan orders the threads); a bin sum
+        // is then S[last] - S[first - 1]: two shared-memory loads per bin instead of a walk.
+        // S is kept modulo 2^32; that is exact when max(coverage) * (bsz + 1) < 2^32, which
+        // the staging loop checks -- otherwise the run falls back to 64-bit walks.
+        uint32_t* stage = reinterpret_cast<uint32_t*>(sh + ((n + 1 + 3) & ~3));
         const int bins_per_chunk = (STAGE_INTS - 4) / (bsz + 1);
-        const bool rotate = (bsz & 1) == 0;     // even stride: offset the lanes by one each
         for (int bin0 = 0; bin0 < n; bin0 += bins_per_chunk) {
             const int bin1 = min(n, bin0 + bins_per_chunk);
             const int lo_al = edges[bin0] & ~3;
             const int nvec = (edges[bin1] - lo_al + 3) >> 2;    // <= STAGE_INTS / 4, inside the padded region
             __syncthreads();
             const int4* gsrc = reinterpret_cast<const int4*>(src + lo_al);
-            for (int i = tid; i < nvec; i += CTA) reinterpret_cast<int4*>(stage)[i] = __ldg(gsrc + i);
+            int vmax = 0;
+            for (int i = tid; i < nvec; i += CTA) {
+                const int4 x = __ldg(gsrc + i);
+                reinterpret_cast<int4*>(stage)[i] = x;
+                vmax = max(max(vmax, x.x), max(max(x.y, x.z), x.w));
+            }
+            vmax = __reduce_max_sync(0xffffffffu, vmax);
+            if (lane == 0) wcount[warp] = vmax;
             __syncthreads();
-            for (int b = bin0 + tid; b < bin1; b += CTA) {
-                const int e0 = edges[b], len = edges[b + 1] - e0;
-                const int* x = stage + (e0 - lo_al);
-                int q = rotate ? (tid % len) : 0;
-                long long sum = 0;
-                for (int it = 0; it < len; it++) {
-                    sum += x[q];
-                    q = (q + 1 == len) ? 0 : q + 1;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) vmax = max(vmax, wcount[w]);
+            if ((unsigned long long)vmax * (unsigned long long)(bsz + 1) < (1ull << 32)) {
+                const int K = ((nvec + CTA - 1) / CTA) | 1;        // odd: conflict-free LDS.128
+                const int v0 = tid * K, v1 = min(v0 + K, nvec);
+                uint32_t sum = 0;
+                for (int i = v0; i < v1; i++) {
+                    const uint4 x = reinterpret_cast<const uint4*>(stage)[i];
+                    sum += (x.x + x.y) + (x.z + x.w);
                 }
-                out[(int64_t)b * p.ld] = p.scale * ((double)sum / (double)len);
+                uint32_t inc = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                __syncthreads();                                   // wcount (max) fully read
+                if (lane == 31) wcount[warp] = (int)inc;
+                __syncthreads();
+                uint32_t run = inc - sum;
+#pragma unroll
+                for (int w = 0; w < WARPS - 1; w++)
+                    if (w < warp) run += (uint32_t)wcount[w];
+                for (int i = v0; i < v1; i++) {
+                    uint4 x = reinterpret_cast<const uint4*>(stage)[i];
+                    x.x = (run += x.x);
+                    x.y = (run += x.y);
+                    x.z = (run += x.z);
+                    x.w = (run += x.w);
+                    reinterpret_cast<uint4*>(stage)[i] = x;
+                }
+                __syncthreads();
+                for (int b = bin0 + tid; b < bin1; b += CTA) {
+                    const int e0 = edges[b] - lo_al, e1 = edges[b + 1] - lo_al;
+                    const uint32_t sum_b = stage[e1 - 1] - (e0 > 0 ? stage[e0 - 1] : 0u);
+                    out[(int64_t)b * p.ld] = p.scale * ((double)sum_b / (double)(e1 - e0));
+                }
+            } else {
+                const bool rotate = (bsz & 1) == 0;     // even stride: offset the lanes by one each
+                for (int b = bin0 + tid; b < bin1; b += CTA) {
+                    const int e0 = edges[b], len = edges[b + 1] - e0;
+                    const uint32_t* x = stage + (e0 - lo_al);
+                    int q = rotate ? (tid % len) : 0;
+                    long long sum = 0;
+                    for (int it = 0; it < len; it++) {
+                        sum += (long long)x[q];
+                        q = (q + 1 == len) ? 0 : q + 1;
+                    }
+                    out[(int64_t)b * p.ld] = p.scale * ((double)sum / (double)len);
+                }
             }
         }
         return;
@@ -453,7 +508,7 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
     a.short_count = short_count;
     // edges (padded to 16 B) + the staging buffer of the narrow-bin path
     const size_t smem = (((size_t)n_bins + 1 + 3) & ~(size_t)3) * sizeof(int) +
-                        (stat == RCP_STAT_MEDIAN ? 0 : (size_t)STAGE_INTS * sizeof(int));
+                        (stat == RCP_STAT_MEDIAN ? 0 : (size_t)STAGE_ALLOC * sizeof(int));
     if (smem > 200 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than ~38000 bins per segment");
     {
     StageTimer t(ST_PROF_BIN);
