@@ -169,13 +169,16 @@ region_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* 
         my_null = null ? 1 : 0;
         my_len = (unsigned long long)len;
     }
+    unsigned long long my_max = my_len;
     for (int d = 16; d > 0; d >>= 1) {
         my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
         my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
     }
     if ((threadIdx.x & 31) == 0) {
         if (my_null) atomicAdd(&stats[0], my_null);
         if (my_len) atomicAdd(&stats[1], my_len);
+        if (my_max) atomicMax(&stats[2], my_max);
     }
 }
 
@@ -428,13 +431,16 @@ list_plan_kernel(int64_t G, const int64_t* __restrict__ ptr, const int32_t* __re
         my_null = null ? 1 : 0;
         my_len = (unsigned long long)len;
     }
+    unsigned long long my_max = my_len;
     for (int d = 16; d > 0; d >>= 1) {
         my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
         my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
     }
     if ((threadIdx.x & 31) == 0) {
         if (my_null) atomicAdd(&stats[0], my_null);
         if (my_len) atomicAdd(&stats[1], my_len);
+        if (my_max) atomicMax(&stats[2], my_max);
     }
 }
 
@@ -520,8 +526,12 @@ concat_plan_kernel(int64_t R, const uint8_t* __restrict__ n0, const uint8_t* __r
     len[r] = (int32_t)L;
     is_null[r] = null ? 1 : 0;
     padded[r] = (L + PAD - 1) / PAD * PAD;
-    if (null) atomicAdd(&stats[0], 1ull);
-    else atomicAdd(&stats[1], (unsigned long long)L);
+    if (null) {
+        atomicAdd(&stats[0], 1ull);
+    } else {
+        atomicAdd(&stats[1], (unsigned long long)L);
+        atomicMax(&stats[2], (unsigned long long)L);
+    }
 }
 
 __global__ void __launch_bounds__(CTA)
@@ -587,15 +597,15 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
     unsigned int* d_err = nullptr;
     unsigned long long* d_stats = nullptr;
     RCP_TRY(dalloc(&d_err, 1));
-    RCP_TRY(dalloc(&d_stats, 2));
+    RCP_TRY(dalloc(&d_stats, 3));
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
 
     struct Host {
         int64_t total_padded, total_tiles;
-        unsigned long long stats[2];
+        unsigned long long stats[3];
         unsigned int err;
-    } h = {0, 0, {0, 0}, 0};
+    } h = {0, 0, {0, 0, 0}, 0};
     {
         StageTimer t(ST_COV_PLAN);
         if (R > 0) {
@@ -609,7 +619,7 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
     }
     RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     int rc = RCP_OK;
@@ -619,6 +629,7 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
         cv->total_padded = h.total_padded;
         cv->n_null = (int64_t)h.stats[0];
         cv->total_len = (int64_t)h.stats[1];
+        cv->max_len = (int32_t)h.stats[2];
         rc = dalloc(&cv->cov, (size_t)h.total_padded);
     }
     int32_t* tile_region = nullptr;
@@ -759,14 +770,14 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
     unsigned int* d_err = nullptr;
     unsigned long long* d_stats = nullptr;
     RCP_TRY(dalloc(&d_err, 1));
-    RCP_TRY(dalloc(&d_stats, 2));
+    RCP_TRY(dalloc(&d_stats, 3));
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
     struct Host {
         int64_t total_padded, total_tiles;
-        unsigned long long stats[2];
+        unsigned long long stats[3];
         unsigned int err;
-    } h = {0, 0, {0, 0}, 0};
+    } h = {0, 0, {0, 0, 0}, 0};
     StageTimer list_timer(ST_COV_LIST);
     if (G > 0) {
         list_plan_kernel<<<blocks_for(G, CTA), CTA, 0, g_ctx.stream>>>(
@@ -779,7 +790,7 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
                                 tile_off + G, G));
     RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     int rc = RCP_OK;
@@ -791,6 +802,7 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
         cv->total_padded = h.total_padded;
         cv->n_null = (int64_t)h.stats[0];
         cv->total_len = (int64_t)h.stats[1];
+        cv->max_len = (int32_t)h.stats[2];
         rc = dalloc(&cv->cov, (size_t)h.total_padded);
     }
     int32_t* tile_region = nullptr;
@@ -832,8 +844,8 @@ int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Co
     int64_t* padded = nullptr;
     unsigned long long* d_stats = nullptr;
     RCP_TRY(dalloc(&padded, (size_t)R));
-    RCP_TRY(dalloc(&d_stats, 2));
-    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 16, g_ctx.stream));
+    RCP_TRY(dalloc(&d_stats, 3));
+    RCP_CUDA(cudaMemsetAsync(d_stats, 0, 24, g_ctx.stream));
     if (R > 0) {
         concat_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
             R, a.is_null, b.is_null, c.is_null, a.len, b.len, c.len, cv->len, cv->is_null, padded,
@@ -842,14 +854,15 @@ int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Co
     }
     RCP_TRY(exclusive_scan_i64(padded, cv->off, R, cv->off + R));
     int64_t total = 0;
-    unsigned long long stats[2] = {0, 0};
+    unsigned long long stats[3] = {0, 0, 0};
     StageTimer concat_timer(ST_COV_CONCAT);
     RCP_CUDA(cudaMemcpyAsync(&total, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(stats, d_stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     cv->total_padded = total;
     cv->n_null = (int64_t)stats[0];
     cv->total_len = (int64_t)stats[1];
+    cv->max_len = (int32_t)stats[2];
     RCP_TRY(dalloc(&cv->cov, (size_t)total));
     if (R > 0) {
         concat_copy_kernel<<<(unsigned)R, CTA, 0, g_ctx.stream>>>(a.cov, a.off, a.len, b.cov, b.off,

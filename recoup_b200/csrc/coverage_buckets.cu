@@ -406,13 +406,16 @@ bkt_null_kernel(int64_t R, int64_t Tb, const int64_t* __restrict__ off_big,
         my_null = null ? 1 : 0;
         my_len = (unsigned long long)out;
     }
+    unsigned long long my_max = my_len;
     for (int d = 16; d > 0; d >>= 1) {
         my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
         my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
     }
     if ((threadIdx.x & 31) == 0) {
         if (my_null) atomicAdd(&stats[0], my_null);
         if (my_len) atomicAdd(&stats[1], my_len);
+        if (my_max) atomicMax(&stats[2], my_max);
     }
 }
 
@@ -477,33 +480,34 @@ __device__ __forceinline__ void tile_body(int* diff, int* wtot, int tlen, uint32
     block_scan_store_fwd<RPW>(diff, tlen, wtot, dst);
 }
 
-// Long regions: persistent CTAs walk the tiles.  The next tile's descriptor and its first bucket
-// entries are fetched before the current tile is processed, so their latency hides behind the
-// scan and the stores.
+// Long regions: persistent CTAs walk the tiles.  Nothing the current tile needs is loaded in
+// its own iteration: the descriptor is fetched two tiles ahead and the first bucket entries one
+// tile ahead, so their latency hides behind the scan and the stores of the tiles in between.
 __global__ void __launch_bounds__(CTA, 5)
 bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* __restrict__ bucket,
                 int32_t* __restrict__ cov) {
     __shared__ __align__(16) int diff[TILE];
     __shared__ int wtot[WARPS];
     const uint32_t tid = threadIdx.x;
+    const int64_t step = gridDim.x;
     int64_t t = blockIdx.x;
     if (t >= Tb) return;
+    TileDesc none;
+    none.out = none.b0 = 0;
+    none.n = 0;
+    none.tlen = 0;
+    none.pad[0] = none.pad[1] = 0;
     TileDesc d = load_desc(desc + t);
+    TileDesc dn = (t + step < Tb) ? load_desc(desc + t + step) : none;
     uint32_t e0 = NONE, e1 = NONE;                  // NONE never is a valid pair (lo < hi)
     if (tid < d.n) e0 = __ldcs(bucket + d.b0 + tid);
     if (tid + CTA < d.n) e1 = __ldcs(bucket + d.b0 + tid + CTA);
     for (;;) {
-        const int64_t tn = t + gridDim.x;
-        TileDesc dn;
-        dn.out = dn.b0 = 0;
-        dn.n = 0;
-        dn.tlen = 0;
+        // issue the loads of the following tiles first: dn is already in registers
+        const TileDesc dnn = (t + 2 * step < Tb) ? load_desc(desc + t + 2 * step) : none;
         uint32_t f0 = NONE, f1 = NONE;
-        if (tn < Tb) {
-            dn = load_desc(desc + tn);
-            if (tid < dn.n) f0 = __ldcs(bucket + dn.b0 + tid);
-            if (tid + CTA < dn.n) f1 = __ldcs(bucket + dn.b0 + tid + CTA);
-        }
+        if (tid < dn.n) f0 = __ldcs(bucket + dn.b0 + tid);
+        if (tid + CTA < dn.n) f1 = __ldcs(bucket + dn.b0 + tid + CTA);
         if (d.tlen > 0) {
             const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
             const uint32_t* entries = bucket + d.b0;
@@ -518,12 +522,13 @@ bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* _
                 default: tile_body<7>(diff, wtot, d.tlen, d.n, entries, e0, e1, dst); break;
             }
         }
-        if (tn >= Tb) break;
+        t += step;
+        if (t >= Tb) break;
         __syncthreads();            // diff and wtot are reused
         d = dn;
+        dn = dnn;
         e0 = f0;
         e1 = f1;
-        t = tn;
     }
 }
 
@@ -672,15 +677,15 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     RCP_TRY(dalloc(&w.off_small, (size_t)R + 1));
     RCP_TRY(dalloc(&w.padded, (size_t)R));
     RCP_TRY(dalloc(&w.err, 1));
-    RCP_TRY(dalloc(&w.stats, 2));
+    RCP_TRY(dalloc(&w.stats, 3));
     RCP_CUDA(cudaMemsetAsync(w.err, 0, sizeof(unsigned int), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(w.stats, 0, 2 * sizeof(unsigned long long), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(w.stats, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
 
     struct Host {
         int64_t Tb, Ts, total_padded, hits;
-        unsigned long long stats[2], listed;
+        unsigned long long stats[3], listed;
         unsigned int err;
-    } h = {0, 0, 0, 0, {0, 0}, 0, 0};
+    } h = {0, 0, 0, 0, {0, 0, 0}, 0, 0};
 
     // ---- 1. plan: windows and tile counts ------------------------------------------------
     {
@@ -765,12 +770,13 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     }
     RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.hits, w.boff + T, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 16, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.listed, w.hit_n, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
     cv->total_len = (int64_t)h.stats[1];
+    cv->max_len = (int32_t)h.stats[2];
     RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
     if (h.hits == 0) return RCP_OK;                 // every region is NULL
     RCP_TRY(dalloc(&w.bucket, (size_t)h.hits));

@@ -165,6 +165,7 @@ struct Coverage {
     int64_t total_padded = 0;    // ints allocated in `cov`
     int64_t total_len = 0;       // sum of len
     int64_t n_null = 0;
+    int32_t max_len = 0;         // longest region (sizes the staging buffers of the bin kernel)
     double scale = 1.0;
     int32_t* cov = nullptr;      // dense int32, region r at [off[r], off[r] + len[r])
     int64_t* off = nullptr;      // n_regions + 1, multiples of 32 ints
