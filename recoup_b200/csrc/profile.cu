@@ -271,20 +271,56 @@ __global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
 }
 
 // ---- mean bins: persistent, double-buffered ----------------------------------------------------
-// One 16-byte descriptor per region (written by bin_desc_kernel): x, y = offset of the region in
-// the dense coverage (low / high word), z, w = the segment [a, b) to bin (b <= a: NULL or empty
-// -> zero row).
+// One 32-byte descriptor per region (written by bin_desc_kernel), so that the main kernel does
+// no divisions and loads nothing else per region:
+//   x, y   offset of the region in the dense coverage (low / high word)
+//   z, w   the segment [a, b) to bin (b <= a: NULL or empty -> zero row)
+//   bsz, dif   bin width and the number of bins one base wider (util.R:74-80); bsz = 0: the
+//              segment is shorter than the bin count (interpolation list)
+//   lo_al, nvec   staging run (4-aligned first base, int4 count) when the whole segment is ONE
+//              staged run of narrow bins -- only those are prefetched; nvec = 0 otherwise
+struct __align__(16) BinDesc {
+    int off_lo, off_hi, a, b;
+    int bsz, dif, lo_al, nvec;
+};
+
+constexpr int BT = 512;                // threads of bin_mean_kernel
+constexpr int BWARPS = BT / 32;
+
 __global__ void __launch_bounds__(CTA)
 bin_desc_kernel(int64_t R, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
-                const uint8_t* __restrict__ is_null, int where, int f1, int f2,
-                int4* __restrict__ desc) {
+                const uint8_t* __restrict__ is_null, int where, int f1, int f2, int n,
+                int buf_ints, BinDesc* __restrict__ desc) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (r >= R) return;
     Seg sg;
     sg.a = sg.b = 0;
     if (!is_null[r]) sg = segment_of(len[r], where, f1, f2);
     const uint64_t o = (uint64_t)off[r];
-    desc[r] = make_int4((int)(uint32_t)o, (int)(uint32_t)(o >> 32), sg.a, sg.b);
+    BinDesc d;
+    d.off_lo = (int)(uint32_t)o;
+    d.off_hi = (int)(uint32_t)(o >> 32);
+    d.a = sg.a;
+    d.b = sg.b;
+    const int Ls = sg.b - sg.a;
+    d.bsz = Ls >= n ? Ls / n : 0;
+    d.dif = Ls >= n ? Ls - d.bsz * n : 0;
+    d.lo_al = sg.a & ~3;
+    d.nvec = 0;
+    if (d.bsz > 0 && d.bsz < STAGE_MAX_BIN && n <= (STAGE_INTS - 4) / (d.bsz + 1)) {
+        const int nvec = (sg.b - d.lo_al + 3) >> 2;
+        if (nvec * 4 <= buf_ints) d.nvec = nvec;
+    }
+    desc[r] = d;
+}
+
+__device__ __forceinline__ BinDesc load_bin_desc(const BinDesc* __restrict__ p) {
+    const int4 u = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    BinDesc d;
+    d.off_lo = u.x; d.off_hi = u.y; d.a = u.z; d.b = u.w;
+    d.bsz = v.x; d.dif = v.y; d.lo_al = v.z; d.nvec = v.w;
+    return d;
 }
 
 // Persistent CTAs walk the regions.  Narrow bins (< 128 bases, the usual case: TSS windows,
@@ -296,68 +332,55 @@ bin_desc_kernel(int64_t R, const int64_t* __restrict__ off, const int32_t* __res
 // issued before the current region is processed, so HBM latency hides behind the arithmetic.
 // Wide bins: one warp per bin, 16-byte global loads.  Segments shorter than the bin count go
 // to the interpolation list (util.R:17).
-__global__ void __launch_bounds__(CTA)
-bin_mean_kernel(BinArgs p, const int4* __restrict__ desc, int64_t R, int buf_ints) {
+__global__ void __launch_bounds__(BT)
+bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_ints) {
     extern __shared__ __align__(16) int sh[];
-    int* edges = sh;                                         // n + 1
+    int* edges = sh;                                         // n + 1 (unequal bins only)
     uint32_t* bufs = reinterpret_cast<uint32_t*>(sh + ((p.n + 1 + 3) & ~3));
-    __shared__ int wcount[WARPS];
-    __shared__ int wmaxs[WARPS];
+    __shared__ int wcount[BWARPS];
+    __shared__ int wmaxs[BWARPS];
     __shared__ int chunk_carry;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n;
     const int64_t step = gridDim.x;
     int64_t r = blockIdx.x;
     if (r >= R) return;
-    const int4 none = make_int4(0, 0, 0, 0);
+    BinDesc none;
+    none.off_lo = none.off_hi = none.a = none.b = none.bsz = none.dif = none.lo_al = none.nvec = 0;
 
-    // regions whose whole segment is one staged run of narrow bins can be prefetched
-    auto plan = [&](const int4 d, int* lo_al, int* nvec) {
-        const int Ls = d.w - d.z;
-        if (Ls < n || Ls <= 0) return false;
-        const int bsz = Ls / n;
-        if (bsz >= STAGE_MAX_BIN || n > (STAGE_INTS - 4) / (bsz + 1)) return false;
-        *lo_al = d.z & ~3;
-        *nvec = (d.w - *lo_al + 3) >> 2;
-        return *nvec * 4 <= buf_ints;
+    auto src_of = [&](const BinDesc& d) {
+        return p.cov + (int64_t)(((uint64_t)(uint32_t)d.off_hi << 32) | (uint32_t)d.off_lo);
     };
-    auto src_of = [&](const int4 d) {
-        return p.cov + (int64_t)(((uint64_t)(uint32_t)d.y << 32) | (uint32_t)d.x);
-    };
-    auto issue = [&](const int4 d, uint32_t* buf) {
-        int lo_al, nvec;
-        if (plan(d, &lo_al, &nvec)) {
-            const int32_t* g = src_of(d) + lo_al;
-            for (int i = tid; i < nvec; i += CTA) __pipeline_memcpy_async(buf + 4 * i, g + 4 * i, 16);
-        }
+    auto issue = [&](const BinDesc& d, uint32_t* buf) {
+        const int32_t* g = src_of(d) + d.lo_al;
+        for (int i = tid; i < d.nvec; i += BT) __pipeline_memcpy_async(buf + 4 * i, g + 4 * i, 16);
         __pipeline_commit();
     };
 
-    int4 d = __ldg(desc + r);
-    int4 dn = (r + step < R) ? __ldg(desc + r + step) : none;
+    BinDesc d = load_bin_desc(desc + r);
+    BinDesc dn = (r + step < R) ? load_bin_desc(desc + r + step) : none;
     int cur = 0;
     issue(d, bufs);
     for (;;) {
-        const int4 dnn = (r + 2 * step < R) ? __ldg(desc + r + 2 * step) : none;
+        const BinDesc dnn = (r + 2 * step < R) ? load_bin_desc(desc + r + 2 * step) : none;
         uint32_t* stage = bufs + (size_t)cur * buf_ints;
         issue(dn, bufs + (size_t)(cur ^ 1) * buf_ints);
         __pipeline_wait_prior(1);           // everything but the copy just issued has landed
         __syncthreads();
         double* out = p.out + r;
-        const int Ls = d.w - d.z;
+        const int Ls = d.b - d.a;
         if (Ls <= 0) {                      // NULL coverage -> zero row (profile.R:191-197)
-            for (int i = tid; i < n; i += CTA) out[(int64_t)i * p.ld] = 0.0;
-        } else if (Ls < n) {                // util.R:17: interpolation path, handled separately
+            for (int i = tid; i < n; i += BT) out[(int64_t)i * p.ld] = 0.0;
+        } else if (d.bsz == 0) {            // util.R:17: interpolation path, handled separately
             if (tid == 0) p.short_list[atomicAdd(p.short_count, 1u)] = (int32_t)r;
         } else {
             // ---- bin edges: bin i has bsz + [rank[i] <= dif] elements (util.R:74-80) ----
-            const int bsz = Ls / n, dif = Ls - bsz * n;
-            if (dif == 0) {                 // equal bins: no rank table involved
-                for (int i = tid; i <= n; i += CTA) edges[i] = d.z + i * bsz;
-            } else {
+            const int bsz = d.bsz, dif = d.dif;
+            const bool equal = dif == 0;    // equal bins: edge i = a + i * bsz, no table
+            if (!equal) {
                 if (tid == 0) chunk_carry = 0;
                 __syncthreads();
-                for (int c0 = 0; c0 < n; c0 += CTA) {
+                for (int c0 = 0; c0 < n; c0 += BT) {
                     const int i = c0 + tid;
                     const bool extra = (i < n) && (p.rank[i] <= dif);
                     const unsigned bal = __ballot_sync(0xffffffffu, extra);
@@ -366,38 +389,40 @@ bin_mean_kernel(BinArgs p, const int4* __restrict__ desc, int64_t R, int buf_int
                     int pre = chunk_carry;
                     for (int w = 0; w < warp; w++) pre += wcount[w];
                     pre += __popc(bal & ((1u << lane) - 1u));
-                    if (i < n) edges[i] = d.z + i * bsz + pre;
+                    if (i < n) edges[i] = d.a + i * bsz + pre;
                     __syncthreads();
-                    if (tid == CTA - 1) chunk_carry = pre + (extra ? 1 : 0);
+                    if (tid == BT - 1) chunk_carry = pre + (extra ? 1 : 0);
                     __syncthreads();
                 }
-                if (tid == 0) edges[n] = d.w;
+                if (tid == 0) edges[n] = d.b;
+                __syncthreads();
             }
-            __syncthreads();
+            auto edge = [&](int i) { return equal ? d.a + i * bsz : edges[i]; };
             const int32_t* src = src_of(d);
             if (bsz < STAGE_MAX_BIN) {
-                int pl_lo, pl_nvec;
-                const bool preloaded = plan(d, &pl_lo, &pl_nvec);
-                const int bins_per_chunk = (STAGE_INTS - 4) / (bsz + 1);
+                const bool preloaded = d.nvec > 0;
+                const int bins_per_chunk = preloaded ? n : (STAGE_INTS - 4) / (bsz + 1);
                 for (int bin0 = 0; bin0 < n; bin0 += bins_per_chunk) {
                     const int bin1 = min(n, bin0 + bins_per_chunk);
-                    const int lo_al = edges[bin0] & ~3;
-                    const int nvec = (edges[bin1] - lo_al + 3) >> 2;
+                    const int lo_al = preloaded ? d.lo_al : (edge(bin0) & ~3);
+                    const int nvec = preloaded ? d.nvec : ((edge(bin1) - lo_al + 3) >> 2);
                     if (!preloaded) {       // several runs per region: staged here, no overlap
                         __syncthreads();
                         const int4* gsrc = reinterpret_cast<const int4*>(src + lo_al);
-                        for (int i = tid; i < nvec; i += CTA)
+                        for (int i = tid; i < nvec; i += BT)
                             reinterpret_cast<int4*>(stage)[i] = __ldg(gsrc + i);
                         __syncthreads();
                     }
                     // pass 1: per-thread sum and max of K consecutive int4 (K odd: the 16-byte
                     // shared-memory accesses of a warp then fall into distinct banks)
-                    const int K = ((nvec + CTA - 1) / CTA) | 1;
+                    const int K = ((nvec + BT - 1) / BT) | 1;
                     const int v0 = min(tid * K, nvec), v1 = min(v0 + K, nvec);
+                    const uint4* sv = reinterpret_cast<const uint4*>(stage) + v0;
+                    const int kn = v1 - v0;
                     uint32_t sum = 0;
                     int vmax = 0;
-                    for (int i = v0; i < v1; i++) {
-                        const uint4 x = reinterpret_cast<const uint4*>(stage)[i];
+                    for (int i = 0; i < kn; i++) {
+                        const uint4 x = sv[i];
                         sum += (x.x + x.y) + (x.z + x.w);
                         vmax = max(max(vmax, (int)x.x), max(max((int)x.y, (int)x.z), (int)x.w));
                     }
@@ -412,30 +437,31 @@ bin_mean_kernel(BinArgs p, const int4* __restrict__ desc, int64_t R, int buf_int
                     if (lane == 0) wmaxs[warp] = vmax;
                     __syncthreads();
 #pragma unroll
-                    for (int w = 0; w < WARPS; w++) vmax = max(vmax, wmaxs[w]);
+                    for (int w = 0; w < BWARPS; w++) vmax = max(vmax, wmaxs[w]);
                     if ((unsigned long long)vmax * (unsigned long long)(bsz + 1) < (1ull << 32)) {
                         uint32_t run = inc - sum;
 #pragma unroll
-                        for (int w = 0; w < WARPS - 1; w++)
+                        for (int w = 0; w < BWARPS - 1; w++)
                             if (w < warp) run += (uint32_t)wcount[w];
-                        for (int i = v0; i < v1; i++) {
-                            uint4 x = reinterpret_cast<const uint4*>(stage)[i];
+                        uint4* wv = reinterpret_cast<uint4*>(stage) + v0;
+                        for (int i = 0; i < kn; i++) {
+                            uint4 x = wv[i];
                             x.x = (run += x.x);
                             x.y = (run += x.y);
                             x.z = (run += x.z);
                             x.w = (run += x.w);
-                            reinterpret_cast<uint4*>(stage)[i] = x;
+                            wv[i] = x;
                         }
                         __syncthreads();
-                        for (int b = bin0 + tid; b < bin1; b += CTA) {
-                            const int e0 = edges[b] - lo_al, e1 = edges[b + 1] - lo_al;
+                        for (int b = bin0 + tid; b < bin1; b += BT) {
+                            const int e0 = edge(b) - lo_al, e1 = edge(b + 1) - lo_al;
                             const uint32_t sum_b = stage[e1 - 1] - (e0 > 0 ? stage[e0 - 1] : 0u);
                             out[(int64_t)b * p.ld] = p.scale * ((double)sum_b / (double)(e1 - e0));
                         }
                     } else {
                         const bool rotate = (bsz & 1) == 0;
-                        for (int b = bin0 + tid; b < bin1; b += CTA) {
-                            const int e0 = edges[b], blen = edges[b + 1] - e0;
+                        for (int b = bin0 + tid; b < bin1; b += BT) {
+                            const int e0 = edge(b), blen = edge(b + 1) - e0;
                             const uint32_t* x = stage + (e0 - lo_al);
                             int q = rotate ? (tid % blen) : 0;
                             long long s64 = 0;
@@ -449,8 +475,8 @@ bin_mean_kernel(BinArgs p, const int4* __restrict__ desc, int64_t R, int buf_int
                 }
             } else {
                 // ---- wide bins: one warp per bin, coalesced 16-byte global loads ----
-                for (int i = warp; i < n; i += WARPS) {
-                    const int lo = edges[i], hi = edges[i + 1];
+                for (int i = warp; i < n; i += BWARPS) {
+                    const int lo = edge(i), hi = edge(i + 1);
                     const long long s64 = warp_range_sum(src, lo, hi);
                     if (lane == 0) out[(int64_t)i * p.ld] = p.scale * ((double)s64 / (double)(hi - lo));
                 }
@@ -708,7 +734,7 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
     a.short_count = short_count;
     const size_t edge_bytes = (((size_t)n_bins + 1 + 3) & ~(size_t)3) * sizeof(int);
     if (edge_bytes > 150 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than ~38000 bins per segment");
-    int4* d_desc = nullptr;
+    BinDesc* d_desc = nullptr;
     if (stat == RCP_STAT_MEDIAN) {
         StageTimer t(ST_PROF_BIN);
         const size_t smem = edge_bytes;
@@ -721,23 +747,23 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         // two staging buffers per CTA; the kernel is persistent (one resident wave of CTAs)
         RCP_TRY(dalloc(&d_desc, (size_t)R));
         StageTimer t(ST_PROF_BIN);
-        bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
-            R, cv.off, cv.len, cv.is_null, where, f1, f2, d_desc);
-        RCP_LAUNCHED();
         // longest segment any region can have here, + alignment slack, capped at one staged run
         int64_t seg_max = cv.max_len;
         if (where == RCP_WHERE_UPSTREAM) seg_max = std::min<int64_t>(seg_max, f1);
         else if (where == RCP_WHERE_DOWNSTREAM) seg_max = std::min<int64_t>(seg_max, f2);
         else if (where == RCP_WHERE_CENTER) seg_max = std::max<int64_t>(seg_max - f1 - f2, 0);
         const int buf_ints = (int)std::min<int64_t>(STAGE_INTS, ((seg_max + 10) & ~(int64_t)3));
+        bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
+            R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc);
+        RCP_LAUNCHED();
         const size_t smem = edge_bytes + 2 * (size_t)buf_ints * sizeof(int);
         RCP_CUDA(cudaFuncSetAttribute(bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         int per_sm = 0;
-        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_mean_kernel, CTA, smem));
+        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_mean_kernel, BT, smem));
         if (per_sm < 1) return fail(RCP_ERR_UNSUPPORTED, "bin kernel does not fit (%zu bytes of shared memory)", smem);
         const int64_t grid = std::min<int64_t>(R, (int64_t)g_ctx.sm_count * per_sm);
-        bin_mean_kernel<<<(unsigned)grid, CTA, smem, g_ctx.stream>>>(a, d_desc, R, buf_ints);
+        bin_mean_kernel<<<(unsigned)grid, BT, smem, g_ctx.stream>>>(a, d_desc, R, buf_ints);
         RCP_LAUNCHED();
     }
     InterpArgs ia;
