@@ -145,60 +145,14 @@ __device__ __forceinline__ void block_scan_store(const int* diff, int tlen, int 
 
 // --------------------------------------------------------------------------------------------
 // Forward scan + store, lane-serial (bucket path: '-' regions are mirrored when the events are
-// written, so the tile kernels only ever scan forwards).  A warp owns `rpw` consecutive rows
-// (rpw * 128 ints of `chunk`); lane l owns the rpw * 4 consecutive ints at chunk + l * rpw * 4
-// (16-byte loads with a lane stride of rpw * 16 bytes: conflict-free for odd rpw).  The lane
-// sums its run, one warp scan orders the lanes, the run is rescanned from the right start and
-// written back in place; the warp then streams its rows out with aligned 16-byte stores.  About
-// a third of the instructions of the row-by-row scan above (one shuffle scan per rpw * 128
+// written, so the tile kernels only ever scan forwards).  A warp owns RPW consecutive rows
+// (RPW * 128 ints); lane l owns the RPW * 4 consecutive ints at l * RPW * 4 of them (16-byte
+// loads with a lane stride of RPW * 16 bytes: conflict-free for odd RPW).  The lane sums its
+// run, one warp scan orders the lanes, the run is rescanned from the right start and written
+// back in place; the warp then streams its rows out with aligned 16-byte stores.  About a
+// third of the instructions of the row-by-row scan above (one shuffle scan per RPW * 128
 // outputs instead of per 128).
 // --------------------------------------------------------------------------------------------
-template <int MAXR>
-__device__ __forceinline__ int lane_load_sum(const int* mine, int rpw, int4 (&v)[MAXR]) {
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < MAXR; k++) {
-        if (k < rpw) {
-            v[k] = *(reinterpret_cast<const int4*>(mine) + k);
-            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-        }
-    }
-    return sum;
-}
-
-template <int MAXR>
-__device__ __forceinline__ void lane_rescan_store(int* mine, int rpw, int run, int4 (&v)[MAXR]) {
-#pragma unroll
-    for (int k = 0; k < MAXR; k++) {
-        if (k < rpw) {
-            int4 o;
-            o.x = (run += v[k].x);
-            o.y = (run += v[k].y);
-            o.z = (run += v[k].z);
-            o.w = (run += v[k].w);
-            *(reinterpret_cast<int4*>(mine) + k) = o;
-        }
-    }
-}
-
-// rows [row0, row0 + rpw) of the scanned tile -> dst (16-byte aligned), `tlen` real outputs
-__device__ __forceinline__ void warp_rows_out(const int* tile, int row0, int rpw, int tlen,
-                                              int32_t* __restrict__ dst) {
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < rpw; k++) {
-        const int o0 = (row0 + k) * ROW + lane * 4;
-        if (o0 >= tlen) break;
-        const int4 o = *reinterpret_cast<const int4*>(tile + o0);
-        if (o0 + 3 < tlen) {
-            *reinterpret_cast<int4*>(dst + o0) = o;
-        } else {
-            dst[o0] = o.x;
-            if (o0 + 1 < tlen) dst[o0 + 1] = o.y;
-            if (o0 + 2 < tlen) dst[o0 + 2] = o.z;
-        }
-    }
-}
-
 // rows [row0, row0 + RPW) of the scanned tile -> dst, fully unrolled
 template <int RPW>
 __device__ __forceinline__ void warp_rows_out_n(const int* tile, int row0, int tlen,
@@ -253,20 +207,6 @@ __device__ __forceinline__ void block_scan_store_fwd(int* diff, int tlen, int* w
     }
     __syncwarp();
     warp_rows_out_n<RPW>(diff, warp * RPW, tlen, dst);
-}
-
-// One warp, warp-private tile of up to SMALL_MAX ints, zero-padded to whole rows.
-__device__ __forceinline__ void warp_scan_store_fwd(int* diff, int tlen, int32_t* __restrict__ dst) {
-    constexpr int MAXR = SMALL_MAX / ROW;
-    const int lane = threadIdx.x & 31;
-    const int nrows = (tlen + ROW - 1) / ROW;
-    int* mine = diff + lane * nrows * 4;
-    int4 v[MAXR];
-    const int sum = lane_load_sum<MAXR>(mine, nrows, v);
-    const int inc = warp_inclusive_scan(sum);
-    lane_rescan_store<MAXR>(mine, nrows, inc - sum, v);
-    __syncwarp();
-    warp_rows_out(diff, 0, nrows, tlen, dst);
 }
 
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }

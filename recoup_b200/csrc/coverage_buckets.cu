@@ -555,7 +555,11 @@ bkt_small_kernel(int64_t Ts, const TileDesc* __restrict__ desc, const uint32_t* 
         if (hi < L) atomicSub(diff + hi, 1);
     }
     __syncwarp();
-    warp_scan_store_fwd(diff, L, cov + d.out);
+    // row by row (a lane-serial scan of 8 rows would put every lane's run in the same banks)
+    int32_t* dst = cov + d.out;
+    int pre = 0;
+    for (int row = 0; row < nrows; row++)
+        pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, L - row * ROW, dst + row * ROW);
 }
 
 inline unsigned reads_grid(int64_t n, size_t smem) {

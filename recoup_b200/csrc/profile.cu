@@ -54,7 +54,6 @@ struct BinArgs {
 };
 
 constexpr int STAGE_INTS = 12288;      // ints of one region staged in shared memory (48 KB)
-constexpr int STAGE_ALLOC = 13 * CTA * 4;   // + room for an odd number of int4 per thread (52 KB)
 constexpr int STAGE_MAX_BIN = 128;     // bins narrower than this use the staged path
 
 // Sum of src[lo, hi) by one warp with 16-byte loads where the index is 4-aligned (src itself is

@@ -485,13 +485,17 @@ def _gpu_sort(keys, bits):
 
 @pytest.mark.parametrize("n,bits", [(1, 32), (2, 32), (1000, 32), (32768, 32), (32769, 32),
                                     (100_000, 27), (1_000_003, 32), (3_000_000, 17), (5_000_000, 32)])
-def test_index_sort_uniform_keys(gpu, n, bits):
+@pytest.mark.parametrize("which", ["cub", "hand"])
+def test_index_sort_uniform_keys(gpu, monkeypatch, n, bits, which):
+    monkeypatch.setenv("RCP_SORT", which)      # RCP_SORT=hand: the hand-written bucket sort
     rng = np.random.default_rng(n)
     keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
     assert np.array_equal(_gpu_sort(keys, bits), np.sort(keys))
 
 
-def test_index_sort_pileups_and_recursion(gpu):
+@pytest.mark.parametrize("which", ["cub", "hand"])
+def test_index_sort_pileups_and_recursion(gpu, monkeypatch, which):
+    monkeypatch.setenv("RCP_SORT", which)
     """Buckets far over the 32 K-key capacity: one value repeated 400 K times, 150 K keys inside a
     512-wide window, 90 K inside a 40 K-wide window, sorted / reversed inputs, all-equal input."""
     rng = np.random.default_rng(5)
