@@ -495,6 +495,11 @@ def run_b200(args):
                 ach = nbytes / (ms_g * 1e-3) / 1e9
                 stage_roof[g] = {"ms_per_step": ms_g, "algorithmic_bytes": nbytes, "achieved": ach,
                                  "frac": ach / peak}
+        # measured DRAM traffic per launch (ncu --set full), available for the full-size C2 step
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_C2.json")
+        if args.workload == "C2" and args.scale == 1.0 and os.path.exists(tpath):
+            traffic = json.load(open(tpath))
         own = {k: v for k, v in stage.items() if k in alg_kernel}
         dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
         roof = None
@@ -502,7 +507,7 @@ def run_b200(args):
             per_step_ms = per_step[dom]
             ach = alg_kernel[dom] / (per_step_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                     "ms_per_step": per_step_ms, "launches_per_step": own[dom][1] / args.steps,
                     "algorithmic_bytes": alg_kernel[dom], "stages": stage_roof}
         out = {
