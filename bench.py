@@ -329,11 +329,13 @@ def run_b200(args):
         placed into the full column-major matrix by rcp_rows_scatter."""
         if world == 1:
             return
-        from recoup_b200.sharding import gather_rows
+        from recoup_b200.sharding import RowGather
         with torch.cuda.stream(stream):
-            gather_box["full"] = gather_rows(out_box["m"], np.arange(rank * R, (rank + 1) * R),
-                                             R * world, dst=0, scatter=rows_scatter,
-                                             sizes=[R] * world)
+            if "g" not in gather_box:       # buffers and row indices are set up once
+                gather_box["g"] = RowGather(out_box["m"].shape[0], np.arange(rank * R, (rank + 1) * R),
+                                            R * world, dev, out_box["m"].dtype, dst=0,
+                                            sizes=[R] * world)
+            gather_box["full"] = gather_box["g"].gather(out_box["m"], scatter=rows_scatter)
 
     def barrier():
         torch.cuda.synchronize()

@@ -49,46 +49,74 @@ def reads_for_slice(read_chrom, read_start, read_end, reg_chrom, reg_start, reg_
     return keep
 
 
-def gather_rows(local, row_ids, n_total, dst=0, group=None, scatter=None, sizes=None):
-    """Gather per-rank row blocks into the full matrix on rank `dst`.
+class RowGather:
+    """Gathers per-rank row blocks into the full matrix on rank `dst`, step after step: every
+    buffer (padded send block, receive blocks, row-index lists, the full matrix) is allocated and
+    the row indices are exchanged ONCE, so a step costs one NCCL gather plus the placement of the
+    blocks.
 
     local    torch tensor [n_cols, n_local]: a column-major  n_local x n_cols  block
     row_ids  int64 numpy array (n_local): the global row of each local row
-    returns  on `dst` a torch tensor [n_cols, n_total] (column-major n_total x n_cols), else None
     scatter  optional callable(block, ids, k, full) placing the first k rows of a block on the
              device (bench.py passes rcp_rows_scatter); default is torch index_copy_.
     sizes    optional list of every rank's n_local (skips the object all-gather)
     """
-    import torch
-    import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n_cols, n_local = int(local.shape[0]), int(local.shape[1])
-    if sizes is None:
-        sizes = [None] * world
-        dist.all_gather_object(sizes, n_local, group=group)
-    n_max = max(sizes) if sizes else 0
-    ids = torch.full((n_max,), -1, dtype=torch.int64, device=local.device)
-    ids[:n_local] = torch.as_tensor(np.asarray(row_ids, dtype=np.int64), device=local.device)
-    block = torch.zeros((n_cols, n_max), dtype=local.dtype, device=local.device)
-    block[:, :n_local] = local
-    if rank == dst:
-        blocks = [torch.empty_like(block) for _ in range(world)]
-        id_list = [torch.empty_like(ids) for _ in range(world)]
-    else:
-        blocks = id_list = None
-    dist.gather(block, blocks, dst=dst, group=group)
-    dist.gather(ids, id_list, dst=dst, group=group)
-    if rank != dst:
-        return None
-    full = torch.zeros((n_cols, n_total), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        k = sizes[r]
-        if k == 0:
-            continue
-        if scatter is not None:
-            scatter(blocks[r], id_list[r][:k], k, full)
+    def __init__(self, n_cols, row_ids, n_total, device, dtype, dst=0, group=None, sizes=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group, self.dst = group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_cols, self.n_total = int(n_cols), int(n_total)
+        n_local = int(np.asarray(row_ids).shape[0])
+        if sizes is None:
+            sizes = [None] * self.world
+            dist.all_gather_object(sizes, n_local, group=group)
+        self.sizes = list(sizes)
+        self.n_local = n_local
+        self.n_max = max(self.sizes) if self.sizes else 0
+        self.equal = all(k == self.n_max for k in self.sizes)
+        ids = torch.full((self.n_max,), -1, dtype=torch.int64, device=device)
+        ids[:n_local] = torch.as_tensor(np.asarray(row_ids, dtype=np.int64), device=device)
+        self.block = None if self.equal else torch.zeros((self.n_cols, self.n_max), dtype=dtype,
+                                                         device=device)
+        if self.rank == dst:
+            self.blocks = [torch.empty((self.n_cols, self.n_max), dtype=dtype, device=device)
+                           for _ in range(self.world)]
+            self.id_list = [torch.empty_like(ids) for _ in range(self.world)]
+            self.full = torch.zeros((self.n_cols, self.n_total), dtype=dtype, device=device)
         else:
-            full.index_copy_(1, id_list[r][:k], blocks[r][:, :k])
-    return full
+            self.blocks = self.id_list = self.full = None
+        dist.gather(ids, self.id_list, dst=dst, group=group)      # once
+
+    def gather(self, local, scatter=None):
+        """returns on `dst` a torch tensor [n_cols, n_total] (column-major n_total x n_cols, reused
+        by the next call), else None"""
+        import torch.distributed as dist
+
+        if self.equal and local.is_contiguous():
+            send = local
+        else:
+            self.block[:, :self.n_local] = local
+            send = self.block
+        dist.gather(send, self.blocks, dst=self.dst, group=self.group)
+        if self.rank != self.dst:
+            return None
+        for r in range(self.world):
+            k = self.sizes[r]
+            if k == 0:
+                continue
+            if scatter is not None:
+                scatter(self.blocks[r], self.id_list[r][:k], k, self.full)
+            else:
+                self.full.index_copy_(1, self.id_list[r][:k], self.blocks[r][:, :k])
+        return self.full
+
+
+def gather_rows(local, row_ids, n_total, dst=0, group=None, scatter=None, sizes=None):
+    """One-shot form of RowGather (allocates per call)."""
+    g = RowGather(int(local.shape[0]), row_ids, n_total, local.device, local.dtype, dst=dst,
+                  group=group, sizes=sizes)
+    return g.gather(local, scatter=scatter)

@@ -21,7 +21,7 @@ def _worker(rank, world, port, out_path):
     import workloads as W
     from oracle import c_oracle as CO
     from oracle import recoup_oracle as O
-    from recoup_b200.sharding import gather_rows, partition_regions, reads_for_slice
+    from recoup_b200.sharding import RowGather, gather_rows, partition_regions, reads_for_slice
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     w = W.gene_bodies(scale=0.004, seed=77)
@@ -37,6 +37,12 @@ def _worker(rank, world, port, out_path):
     m = CO.profile_matrix(dense, w["flank"], w["bin_params"], False)          # [n_local x 250]
     local = torch.from_numpy(np.ascontiguousarray(m.T))                      # [250, n_local]
     full = gather_rows(local, mine, len(s), dst=0)
+    # the persistent form: buffers and row indices set up once, then one gather per step
+    g = RowGather(local.shape[0], mine, len(s), local.device, local.dtype, dst=0)
+    for step in range(3):
+        again = g.gather(local * float(step + 1))
+        if rank == 0:
+            assert np.array_equal(again.numpy(), full.numpy() * float(step + 1))
     if rank == 0:
         np.save(out_path, full.numpy().T)
     dist.barrier()
