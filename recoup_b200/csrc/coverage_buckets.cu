@@ -8,7 +8,7 @@
 //
 //   1. plan          regions -> windows (geometry / NULL rules) -> tiles (<= 7168 outputs, cut
 //                    in output space; regions <= 1024 bp are one warp-sized tile)
-//   2. cell table    the genome is cut into 1024-bp cells; one 16-byte record per cell holds
+//   2. cell table    the genome is cut into 2048-bp cells; one 16-byte record per cell holds
 //                    the first tile overlapping it inline (L2-resident), further tiles in
 //                    overflow runs
 //   3. find pass     every read is checked against a shared-memory bitmap of the 16-kb blocks
@@ -37,7 +37,7 @@ using namespace covk;
 
 namespace {
 
-constexpr int CELL_SHIFT = 10;                       // 1024-bp cells of the L2-resident table
+constexpr int CELL_SHIFT = 11;                       // 2048-bp cells of the L2-resident table
 constexpr int BM_SHIFT = 14;                         // 16384-bp blocks of the shared-memory bitmap
 constexpr int CELLS_PER_BIG = ((TILE - 1) >> CELL_SHIFT) + 2;
 constexpr int CELLS_PER_SMALL = ((SMALL_MAX - 1) >> CELL_SHIFT) + 2;
@@ -53,7 +53,7 @@ struct Tiles {
     uint2* b;
 };
 
-// Cell table: one 16-byte record per 1024-bp cell = the first tile overlapping the cell, inline
+// Cell table: one 16-byte record per 2048-bp cell = the first tile overlapping the cell, inline
 // (x, y as in Tiles::a; y == 0: no tile; z = tile id; w = index of the cell's overflow records
 // or NONE).  Overflow records have the same layout and end with a y == 0 sentinel.  One 16-byte
 // load answers "which tile does this read hit" for almost every read.
