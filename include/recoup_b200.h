@@ -155,6 +155,15 @@ int rcp_coverage_lengths(int cov, int32_t* len_out /* n_regions */);
 /* Copy the unscaled integer coverage of regions [first, first+count) to the host, packed back to
  * back (region i occupies len[i] ints).  `capacity` = ints available in `out`. */
 int rcp_coverage_fetch(int cov, int64_t first, int64_t count, int32_t* out, int64_t capacity);
+/* The same regions as integer run-length encodings -- the Rle objects calcCoverage returns
+ * (coverage.R:171-173, contract T1 of SURVEY 8a: `input[[s]]$coverage` is a list of integer Rle
+ * or NULL).  run_ptr_out (count + 1) receives the offset of each region's runs; region i owns
+ * values / lengths [run_ptr[i], run_ptr[i+1]) with sum(lengths) = len[i]; NULL regions own none.
+ * Call with values_out = lengths_out = NULL to size the buffers (run_ptr_out[count] = total runs),
+ * then again with `capacity` entries in each.  The encoding runs on the device (run heads by
+ * neighbour comparison, compaction by prefix sums): only the runs cross PCIe. */
+int rcp_coverage_rle(int cov, int64_t first, int64_t count, int64_t* run_ptr_out,
+                     int32_t* values_out, int32_t* lengths_out, int64_t capacity);
 int rcp_coverage_free(int cov);
 
 /* ---------------------------------------------------------------- profile matrix ---------- */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rcp_coverage_info": (C.c_int, [C.c_int, _i64p, _i64p, _i64p, _f64p]),
     "rcp_coverage_lengths": (C.c_int, [C.c_int, _i32p]),
     "rcp_coverage_fetch": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i32p, C.c_int64]),
+    "rcp_coverage_rle": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i64p, _i32p, _i32p, C.c_int64]),
     "rcp_coverage_free": (C.c_int, [C.c_int]),
     "rcp_bin_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _vp, C.c_int64, C.c_int]),

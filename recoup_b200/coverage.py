@@ -153,6 +153,25 @@ class CoverageList:
             pos += l
         return out
 
+    def rle(self, first=0, count=None):
+        """Regions [first, first+count) as integer run-length encodings, the `Rle` objects
+        calcCoverage returns in the reference (coverage.R:171-173): a list of (values, lengths)
+        int32 array pairs, None for NULL.  Encoded on the device; only the runs are copied."""
+        if count is None:
+            count = self.n - first
+        ptr = np.zeros(count + 1, dtype=np.int64)
+        pp = ptr.ctypes.data_as(C.POINTER(C.c_int64))
+        _lib_check(_lib.lib.rcp_coverage_rle(self.handle, first, count, pp, None, None, 0))
+        total = int(ptr[count])
+        vals = np.zeros(max(total, 1), dtype=np.int32)
+        lens = np.zeros(max(total, 1), dtype=np.int32)
+        i32 = C.POINTER(C.c_int32)
+        _lib_check(_lib.lib.rcp_coverage_rle(self.handle, first, count, pp, vals.ctypes.data_as(i32),
+                                             lens.ctypes.data_as(i32), total))
+        null = self.is_null()[first:first + count]
+        return [None if null[i] else (vals[ptr[i]:ptr[i + 1]].copy(), lens[ptr[i]:ptr[i + 1]].copy())
+                for i in range(count)]
+
     def __getitem__(self, i):
         if isinstance(i, str):
             i = self.names.index(i)

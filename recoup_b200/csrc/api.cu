@@ -190,6 +190,8 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
 int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv);
 int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
                    int64_t capacity);
+int coverage_rle(const Coverage& cv, int64_t first, int64_t count, int64_t* run_ptr,
+                 int32_t* values, int32_t* lengths, int64_t capacity);
 int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins, int stat,
                       int interp, int seed, int sample_kind, double* d_out, int64_t ld);
 int base_matrix_device(const Coverage& cv, int where, int f1, int f2, int64_t n_cols,
@@ -648,6 +650,14 @@ int rcp_coverage_fetch(int cov, int64_t first, int64_t count, int32_t* out, int6
     Coverage* cv = get_coverage(cov);
     if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
     return coverage_fetch(*cv, first, count, out, capacity);
+}
+
+int rcp_coverage_rle(int cov, int64_t first, int64_t count, int64_t* run_ptr_out,
+                     int32_t* values_out, int32_t* lengths_out, int64_t capacity) {
+    RCP_TRY(require_ready());
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    return coverage_rle(*cv, first, count, run_ptr_out, values_out, lengths_out, capacity);
 }
 
 int rcp_coverage_free(int cov) {

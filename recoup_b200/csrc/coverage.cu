@@ -568,6 +568,79 @@ len_to_i64_kernel(int64_t n, const int32_t* __restrict__ len, int64_t* __restric
 }
 
 
+// ---- run-length encoding of $coverage (contract T1: one integer Rle per region) ---------------
+// runs of region r = #{i : i == 0 or cov[i] != cov[i-1]}
+__global__ void __launch_bounds__(CTA)
+rle_count_kernel(const int32_t* __restrict__ cov, const int64_t* __restrict__ off,
+                 const int32_t* __restrict__ len, int64_t first, int64_t* __restrict__ n_runs) {
+    __shared__ int wsum[WARPS];
+    const int64_t r = first + blockIdx.x;
+    const int L = len[r];
+    const int32_t* x = cov + off[r];
+    int c = 0;
+    for (int i = threadIdx.x; i < L; i += CTA) c += (i == 0) || (x[i] != x[i - 1]);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < WARPS; w++) t += wsum[w];
+        n_runs[blockIdx.x] = t;
+    }
+}
+
+// values[run] and the start position of every run, region by region (one CTA per region, chunks
+// of CTA elements with a running carry)
+__global__ void __launch_bounds__(CTA)
+rle_write_kernel(const int32_t* __restrict__ cov, const int64_t* __restrict__ off,
+                 const int32_t* __restrict__ len, int64_t first,
+                 const int64_t* __restrict__ run_ptr, int32_t* __restrict__ values,
+                 int32_t* __restrict__ starts) {
+    __shared__ int wsum[WARPS];
+    __shared__ int carry_s;
+    const int64_t r = first + blockIdx.x;
+    const int L = len[r];
+    const int32_t* x = cov + off[r];
+    const int64_t base = run_ptr[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < L; i0 += CTA) {
+        const int i = i0 + threadIdx.x;
+        int v = 0;
+        bool head = false;
+        if (i < L) {
+            v = x[i];
+            head = (i == 0) || (v != x[i - 1]);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int pre = carry_s;
+        for (int w = 0; w < warp; w++) pre += wsum[w];
+        if (head) {
+            const int64_t o = base + pre + __popc(bal & ((1u << lane) - 1u));
+            values[o] = v;
+            starts[o] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == CTA - 1) carry_s = pre + __popc(bal);
+        __syncthreads();
+    }
+}
+
+// lengths[run] = start of the next run of the same region (or the region length) - start
+__global__ void __launch_bounds__(CTA)
+rle_lengths_kernel(const int32_t* __restrict__ len, int64_t first,
+                   const int64_t* __restrict__ run_ptr, const int32_t* __restrict__ starts,
+                   int32_t* __restrict__ lengths) {
+    const int64_t r = first + blockIdx.x;
+    const int L = len[r];
+    const int64_t a = run_ptr[blockIdx.x], b = run_ptr[blockIdx.x + 1];
+    for (int64_t j = a + threadIdx.x; j < b; j += CTA)
+        lengths[j] = (j + 1 < b ? starts[j + 1] : L) - starts[j];
+}
+
 int alloc_coverage_arrays(Coverage* cv, int64_t R) {
     cv->n_regions = R;
     RCP_TRY(dalloc(&cv->off, (size_t)R + 1));
@@ -910,6 +983,63 @@ int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* ou
     }
     dfree(len64);
     dfree(poff);
+    return rc;
+}
+
+// Run-length encoding of regions [first, first + count): run_ptr (count + 1, host) receives the
+// offsets of each region's runs; values / lengths (host, `capacity` entries each, may be null to
+// only count) receive the runs.  NULL regions have no runs.
+int coverage_rle(const Coverage& cv, int64_t first, int64_t count, int64_t* run_ptr,
+                 int32_t* values, int32_t* lengths, int64_t capacity) {
+    if (first < 0 || count < 0 || first + count > cv.n_regions)
+        return fail(RCP_ERR_ARG, "rle: region range [%lld, %lld) outside [0, %lld)", (long long)first,
+                    (long long)(first + count), (long long)cv.n_regions);
+    if (run_ptr == nullptr) return fail(RCP_ERR_ARG, "rle: run_ptr is NULL");
+    run_ptr[0] = 0;
+    if (count == 0) return RCP_OK;
+    int64_t *n_runs = nullptr, *d_ptr = nullptr;
+    RCP_TRY(dalloc(&n_runs, (size_t)count));
+    RCP_TRY(dalloc(&d_ptr, (size_t)count + 1));
+    rle_count_kernel<<<(unsigned)count, CTA, 0, g_ctx.stream>>>(cv.cov, cv.off, cv.len, first, n_runs);
+    RCP_LAUNCHED();
+    RCP_TRY(exclusive_scan_i64(n_runs, d_ptr, count, d_ptr + count));
+    RCP_CUDA(cudaMemcpyAsync(run_ptr, d_ptr, ((size_t)count + 1) * 8, cudaMemcpyDeviceToHost,
+                             g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    const int64_t total = run_ptr[count];
+    int rc = RCP_OK;
+    if (values != nullptr || lengths != nullptr) {
+        if (values == nullptr || lengths == nullptr)
+            rc = fail(RCP_ERR_ARG, "rle: values and lengths must be given together");
+        else if (total > capacity)
+            rc = fail(RCP_ERR_ARG, "rle: %lld runs, capacity %lld", (long long)total, (long long)capacity);
+        else if (total > 0) {
+            int32_t *d_val = nullptr, *d_start = nullptr, *d_len = nullptr;
+            rc = dalloc(&d_val, (size_t)total);
+            if (rc == RCP_OK) rc = dalloc(&d_start, (size_t)total);
+            if (rc == RCP_OK) rc = dalloc(&d_len, (size_t)total);
+            if (rc == RCP_OK) {
+                rle_write_kernel<<<(unsigned)count, CTA, 0, g_ctx.stream>>>(cv.cov, cv.off, cv.len, first,
+                                                                           d_ptr, d_val, d_start);
+                g_ctx.launches++;
+                rle_lengths_kernel<<<(unsigned)count, CTA, 0, g_ctx.stream>>>(cv.len, first, d_ptr,
+                                                                             d_start, d_len);
+                g_ctx.launches++;
+                cudaError_t e = cudaMemcpyAsync(values, d_val, (size_t)total * 4, cudaMemcpyDeviceToHost,
+                                                g_ctx.stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(lengths, d_len, (size_t)total * 4, cudaMemcpyDeviceToHost,
+                                        g_ctx.stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+                if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "rle copy failed: %s", cudaGetErrorString(e));
+            }
+            dfree(d_val);
+            dfree(d_start);
+            dfree(d_len);
+        }
+    }
+    dfree(n_runs);
+    dfree(d_ptr);
     return rc;
 }
 

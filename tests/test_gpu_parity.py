@@ -514,3 +514,49 @@ def test_index_sort_pileups_and_recursion(gpu, monkeypatch, which):
     assert np.array_equal(_gpu_sort(same, 32), same)
     small_range = rng.integers(0, 3, size=500_000).astype(np.uint32)      # 2 significant bits
     assert np.array_equal(_gpu_sort(small_range, 2), np.sort(small_range))
+
+
+# ------------------------------------------------------------------------------------------------
+# $coverage as run-length encodings (contract T1: integer Rle per region)
+# ------------------------------------------------------------------------------------------------
+def _np_rle(x):
+    x = np.asarray(x)
+    heads = np.flatnonzero(np.concatenate([[True], x[1:] != x[:-1]]))
+    return x[heads].astype(np.int32), np.diff(np.concatenate([heads, [x.shape[0]]])).astype(np.int32)
+
+
+def test_coverage_rle_matches_the_oracle(gpu, fixture_data):
+    rb = gpu
+    rng = np.random.default_rng(41)
+    clen = [50000, 9000]
+    chrom, s, e, st = synth_reads(rng, 6000, clen, width=(1, 300))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    rc, rs, re_, rst = _regions(rng, 150, clen, [1, 2, 255, 256, 257, 1000, 1024, 5000, 20000])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    want = O.calc_coverage(o_reads, o_mask)
+    cov = rb.calcCoverage(g_reads, g_mask)
+    got = cov.rle()
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if w is None:
+            assert g is None
+            continue
+        wv, wl = _np_rle(w)
+        assert np.array_equal(g[0], wv) and np.array_equal(g[1], wl)
+        assert int(g[1].sum()) == w.shape[0] and (g[1] > 0).all()
+    # a sub-range, and the bundled fixture (long runs of zeros between reads)
+    sub = cov.rle(10, 25)
+    for g, w in zip(sub, want[10:35]):
+        assert (g is None) == (w is None)
+        if w is not None:
+            assert np.array_equal(np.repeat(g[0], g[1]), w)
+    o_reads, g_reads = fixture_reads(fixture_data, 0)
+    o_genes, g_genes = fixture_genes(fixture_data)
+    inp = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRef(inp, g_genes, "genebody", (2000, 2000))
+    want = O.coverage_ref(o_reads, o_genes, "genebody", (2000, 2000))
+    for g, w in zip(inp[0]["coverage"].rle(), want):
+        assert (g is None) == (w is None)
+        if w is not None:
+            wv, wl = _np_rle(w)
+            assert np.array_equal(g[0], wv) and np.array_equal(g[1], wl)
