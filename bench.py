@@ -42,6 +42,12 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(W.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fence", default="step", choices=["step", "end"],
+                    help="p2p exchange: all-reduce fence after every step, or only once after the "
+                         "timed steps (diagnostic: shows what the per-step fence costs)")
+    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
+                    help="N > 1: ranks store their rows straight into rank 0's matrix over NVLink "
+                         "(p2p) or the row blocks are gathered with NCCL and placed by a kernel (nccl)")
     ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets"],
                     help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
@@ -308,13 +314,21 @@ def run_b200(args):
                                            bp["regionBinSize"], C.byref(nc)))
             ncols_box["n"] = nc.value
             out_box["m"] = torch.empty((nc.value, R), dtype=torch.float64, device=dev)  # col-major R x nc
+            out_box["ptr"], out_box["ld"] = out_box["m"].data_ptr(), R
+            if world > 1 and args.exchange == "p2p":
+                # every rank writes its rows straight into rank 0's matrix (peer-mapped)
+                from recoup_b200.sharding import PeerMatrix
+                with torch.cuda.stream(stream):
+                    pm = PeerMatrix(R * world, nc.value, dev, dst=0)
+                out_box["peer"] = pm
+                out_box["ptr"], out_box["ld"] = pm.ptr_for(rank * R), R * world
             tl, nn = C.c_int64(0), C.c_int64(0)
             L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
             stats["total_len"], stats["n_null"] = tl.value, nn.value
         _lib.check(L.rcp_profile_matrix(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
                                         bp["regionBinSize"], _lib.STAT[bp["sumStat"]],
                                         _lib.INTERP[bp["interpolation"]], 42, 0,
-                                        vp(out_box["m"]), R, _lib.MEM_DEVICE))
+                                        C.c_void_p(out_box["ptr"]), out_box["ld"], _lib.MEM_DEVICE))
         L.rcp_coverage_free(cov.value)
         L.rcp_reads_free(h.value)
 
@@ -328,6 +342,11 @@ def run_b200(args):
         """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)),
         placed into the full column-major matrix by rcp_rows_scatter."""
         if world == 1:
+            return
+        if "peer" in out_box:               # the rows are already in place: order the stores
+            if args.fence == "step":
+                with torch.cuda.stream(stream):
+                    out_box["peer"].fence()
             return
         from recoup_b200.sharding import RowGather
         with torch.cuda.stream(stream):
@@ -447,6 +466,28 @@ def run_b200(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert mat.shape == (R, ncols)
 
+    # ---- N > 1: the exchanged matrix on rank 0 must hold every rank's rows ----
+    exchange_ok = None
+    if world > 1:
+        barrier()
+        saved = (out_box["ptr"], out_box["ld"])
+        out_box["ptr"], out_box["ld"] = out_box["m"].data_ptr(), R      # one more step, local output
+        device_step()
+        out_box["ptr"], out_box["ld"] = saved
+        barrier()
+        mine = out_box["m"].double().sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            full = out_box["peer"].as_tensor() if "peer" in out_box else gather_box["full"]
+            exchange_ok = True
+            for r in range(world):
+                got = float(full[:, r * R:(r + 1) * R].sum())
+                want = float(sums[r])
+                if not (abs(got - want) <= 1e-9 * max(abs(want), 1.0)) or want == 0.0:
+                    exchange_ok = False
+            assert exchange_ok, "rows of some rank did not arrive in rank 0's matrix"
+
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -523,7 +564,9 @@ def run_b200(args):
                        "l2": "inputs (%.0f MB) and coverage (%.0f MB) exceed the 126 MB L2"
                              % (13 * N / 1e6, 4 * total_len / 1e6),
                        "coverage_path": args.path,
-                       "parallelism": "regions sharded over %d GPU(s), NCCL row gather" % world},
+                       "parallelism": ("regions sharded over %d GPU(s), " % world) +
+                                      ("rows stored into rank 0's matrix over NVLink (peer-mapped)"
+                                       if world > 1 and args.exchange == "p2p" else "NCCL row gather")},
             "stage_ms_per_step": {k: v[0] * v[1] / args.steps for k, v in stage.items()},
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
             "roofline": roof,
@@ -532,10 +575,14 @@ def run_b200(args):
                     "phases_ms": {k: 1e3 * v / e2e_steps for k, v in phases.items()}},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if exchange_ok is not None:
+            out["exchange_verified"] = exchange_ok
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(out))
     if world > 1:
+        if "peer" in out_box:
+            out_box["peer"].close()
         dist.barrier()
         dist.destroy_process_group()
 

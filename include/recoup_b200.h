@@ -207,6 +207,19 @@ int rcp_sort_keys_u32(uint32_t* keys, int64_t n, int key_bits, int mem);
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
                      const int64_t* row_index, double* dst, int64_t ld_dst);
 
+/* Device memory that the other processes of this box (one per GPU) can map, so that every rank's
+ * rcp_profile_matrix / rcp_bin_matrix / rcp_base_matrix writes its row block STRAIGHT into the
+ * matrix of the gathering rank over NVLink (out = base + first_row, ld = total rows): the
+ * exchange is fused into the kernel's own stores and no gather / scatter pass runs.  The owner
+ * allocates and exports a 64-byte handle (CUDA IPC), peers open it; completion is ordered by any
+ * collective or barrier after the call.  rcp_shared_close undoes rcp_shared_open,
+ * rcp_shared_free undoes rcp_shared_alloc. */
+#define RCP_IPC_HANDLE_BYTES 64
+int rcp_shared_alloc(int64_t bytes, void** ptr_out, unsigned char* handle_out /* 64 */);
+int rcp_shared_open(const unsigned char* handle /* 64 */, void** ptr_out);
+int rcp_shared_close(void* ptr);
+int rcp_shared_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,10 @@ SIGNATURES = {
     "rcp_coverage_profile": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_double, _vp, C.c_int64, _vp, C.c_int]),
     "rcp_sort_keys_u32": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int]),
+    "rcp_shared_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "rcp_shared_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "rcp_shared_close": (C.c_int, [C.c_void_p]),
+    "rcp_shared_free": (C.c_int, [C.c_void_p]),
     "rcp_rows_scatter": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64]),
 }
 

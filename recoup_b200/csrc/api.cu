@@ -1,6 +1,7 @@
 // C ABI of librecoup_b200.so (include/recoup_b200.h): context, handle tables, argument checks.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <memory>
 
@@ -803,6 +804,46 @@ int rcp_sort_keys_u32(uint32_t* keys, int64_t n, int key_bits, int mem) {
     }
     dfree(d);
     return rc;
+}
+
+// ---- peer-mapped device memory (CUDA IPC) --------------------------------------------------
+int rcp_shared_alloc(int64_t bytes, void** ptr_out, unsigned char* handle_out) {
+    RCP_TRY(require_ready());
+    if (bytes <= 0 || ptr_out == nullptr || handle_out == nullptr)
+        return fail(RCP_ERR_ARG, "rcp_shared_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RCP_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    RCP_CUDA(cudaMalloc(&p, (size_t)bytes));      // not from the stream-ordered pool: exportable
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(RCP_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = p;
+    return RCP_OK;
+}
+
+int rcp_shared_open(const unsigned char* handle, void** ptr_out) {
+    RCP_TRY(require_ready());
+    if (handle == nullptr || ptr_out == nullptr) return fail(RCP_ERR_ARG, "rcp_shared_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    RCP_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RCP_OK;
+}
+
+int rcp_shared_close(void* ptr) {
+    if (ptr == nullptr) return RCP_OK;
+    RCP_CUDA(cudaIpcCloseMemHandle(ptr));
+    return RCP_OK;
+}
+
+int rcp_shared_free(void* ptr) {
+    if (ptr == nullptr) return RCP_OK;
+    RCP_CUDA(cudaFree(ptr));
+    return RCP_OK;
 }
 
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,

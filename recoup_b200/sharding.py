@@ -115,6 +115,78 @@ class RowGather:
         return self.full
 
 
+class PeerMatrix:
+    """The full profile matrix on rank `dst`, mapped into every rank of the box (CUDA IPC through
+    rcp_shared_alloc / rcp_shared_open): each rank's bin kernels store their row block straight
+    into it over NVLink (`out = ptr_for(first_row)`, `ld = n_total`), so the exchange is fused
+    into the kernel's own stores -- no gather, no scatter pass.  `fence()` (a tiny all-reduce on
+    the caller's stream) orders every rank's stores before the matrix is read on `dst`.
+
+    Contiguous row slices only (rank r owns rows [first_row, first_row + n_local)); arbitrary
+    row sets use RowGather."""
+
+    def __init__(self, n_total, n_cols, device, dst=0, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self._lib = _lib
+        self.group, self.dst = group, dst
+        self.rank = dist.get_rank(group)
+        self.n_total, self.n_cols = int(n_total), int(n_cols)
+        nbytes = self.n_total * self.n_cols * 8
+        handle = torch.zeros(_IPC_BYTES, dtype=torch.uint8)
+        ptr = C.c_void_p(0)
+        if self.rank == dst:
+            buf = (C.c_ubyte * _IPC_BYTES)()
+            _lib.check(_lib.lib.rcp_shared_alloc(nbytes, C.byref(ptr), buf))
+            handle = torch.tensor(list(buf), dtype=torch.uint8)
+        handle = handle.to(device)
+        dist.broadcast(handle, src=dst, group=group)
+        if self.rank != dst:
+            buf = (C.c_ubyte * _IPC_BYTES)(*handle.cpu().tolist())
+            _lib.check(_lib.lib.rcp_shared_open(buf, C.byref(ptr)))
+        self.base = ptr.value
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def ptr_for(self, first_row):
+        """device pointer of element (first_row, 0): pass it as `out` with ld = n_total"""
+        return self.base + 8 * int(first_row)
+
+    def fence(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def as_tensor(self):
+        """[n_cols, n_total] float64 view on rank `dst` (column-major n_total x n_cols)"""
+        import torch
+        assert self.rank == self.dst
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.n_cols, self.n_total), "typestr": "<f8",
+                                        "data": (self.base, False), "version": 2}
+        return torch.as_tensor(raw, device=self._flag.device)
+
+    def close(self):
+        import torch.distributed as dist
+        dist.barrier(group=self.group)
+        if self.base:
+            if self.rank == self.dst:
+                self._lib.lib.rcp_shared_free(self.base)
+            else:
+                self._lib.lib.rcp_shared_close(self.base)
+            self.base = 0
+
+
+_IPC_BYTES = 64
+
+
 def gather_rows(local, row_ids, n_total, dst=0, group=None, scatter=None, sizes=None):
     """One-shot form of RowGather (allocates per call)."""
     g = RowGather(int(local.shape[0]), row_ids, n_total, local.device, local.dtype, dst=dst,

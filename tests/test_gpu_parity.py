@@ -560,3 +560,90 @@ def test_coverage_rle_matches_the_oracle(gpu, fixture_data):
         if w is not None:
             wv, wl = _np_rle(w)
             assert np.array_equal(g[0], wv) and np.array_equal(g[1], wl)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's named configs (workloads.py generators): C2 at FULL size, C3-C5 scaled so that
+# the C oracle finishes in seconds.  Coverage bit-exact (compared as dense arrays), matrices
+# within 1e-6 relative, plus a checksum of checksums at full size.
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu_auto():
+    import recoup_b200 as rb
+    rb.init(0)
+    rb.set_coverage_path("auto")
+    return rb
+
+
+def _dense_equal(cov, dense):
+    """device CoverageList vs oracle DenseCoverage without python lists (large sizes)"""
+    lens = cov.lengths().astype(np.int64)
+    assert np.array_equal(lens, dense.len.astype(np.int64))
+    total = int(lens.sum())
+    buf = np.zeros(max(total, 1), dtype=np.int32)
+    from recoup_b200 import _lib
+    _lib.check(_lib.lib.rcp_coverage_fetch(cov.handle, 0, len(cov), buf.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           total))
+    pos = 0
+    off = dense.off
+    for r in range(len(cov)):
+        L = int(lens[r])
+        if L:
+            assert np.array_equal(buf[pos:pos + L], dense.cov[off[r]:off[r] + L]), "region %d" % r
+            pos += L
+
+
+@pytest.mark.parametrize("name,scale", [("C2", 1.0), ("C3", 0.05), ("C5", 0.02)])
+def test_named_config_against_c_oracle(gpu_auto, name, scale):
+    import workloads as W
+    rb = gpu_auto
+    w = W.CONFIGS[name](scale=scale, seed=4242)
+    reads = rb.GRanges(w["read_chrom"], w["read_start"], w["read_end"], strand=w["read_strand"],
+                       seqlevels=w["chrom_names"], seqlengths=w["chrom_len"])
+    s, e = O.get_regional_ranges(w["region_start"], w["region_end"], w["region_strand"], w["region"],
+                                 w["flank"])
+    mask = rb.GRanges(w["region_chrom"], s, e, strand=w["region_strand"], seqlevels=w["chrom_names"])
+    cov = rb.calcCoverage(reads, mask, frag_len=w["frag_len"])
+    ix = CO.Index(w["read_chrom"], w["read_start"], w["read_end"], w["read_strand"], w["chrom_len"],
+                  frag_len=w["frag_len"])
+    dense = CO.coverage(ix, w["region_chrom"], s, e, w["region_strand"])
+    assert cov.n_null == int((dense.len == 0).sum())
+    _dense_equal(cov, dense)
+    inp = [dict(id="s", name="s", coverage=cov)]
+    rb.profileMatrix(inp, w["flank"], w["bin_params"])
+    lens = dense.len[dense.len > 0]
+    equal = bool((lens == lens[0]).all()) if lens.size else True
+    want = CO.profile_matrix(dense, w["flank"], w["bin_params"], equal)
+    m = np.asarray(inp[0]["profile"])
+    assert_matrix_close(m, want)
+    if equal and w["bin_params"]["regionBinSize"] and lens.size:
+        # checksum of checksums: sum over the matrix * bases per bin == sum of all coverage
+        per_bin = int(lens[0]) // int(w["bin_params"]["regionBinSize"])
+        if per_bin * int(w["bin_params"]["regionBinSize"]) == int(lens[0]):
+            assert abs(m.sum() * per_bin - float(dense.cov.sum(dtype=np.int64))) <= 1e-9 * max(1.0, float(dense.cov.sum(dtype=np.int64)))
+
+
+def test_named_config_c4_rna_against_c_oracle(gpu_auto):
+    import workloads as W
+    rb = gpu_auto
+    w = W.CONFIGS["C4"](scale=0.02, seed=4244)
+    reads = rb.GRanges(w["read_chrom"], w["read_start"], w["read_end"], strand=w["read_strand"],
+                       seqlevels=w["chrom_names"], seqlengths=w["chrom_len"])
+    genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"], strand=w["region_strand"],
+                       seqlevels=w["chrom_names"])
+    grl = rb.GRangesList(rb.GRanges(w["exon_chrom"], w["exon_start"], w["exon_end"],
+                                    strand=w["exon_strand"], seqlevels=w["chrom_names"]), w["exon_ptr"])
+    inp = [dict(id="s", name="s", ranges=reads)]
+    rb.coverageRnaRef(inp, grl, genes, w["flank"])
+    ix = CO.Index(w["read_chrom"], w["read_start"], w["read_end"], w["read_strand"], w["chrom_len"])
+    f1, f2 = w["flank"]
+    ls, le = O.get_flanking_ranges(w["region_start"], w["region_end"], w["region_strand"], f1, "upstream")
+    rs, re_ = O.get_flanking_ranges(w["region_start"], w["region_end"], w["region_strand"], f2, "downstream")
+    center = CO.coverage_list(ix, w["exon_ptr"], w["exon_chrom"], w["exon_start"], w["exon_end"],
+                              w["exon_strand"])
+    left = CO.coverage(ix, w["region_chrom"], ls, le, w["region_strand"])
+    right = CO.coverage(ix, w["region_chrom"], rs, re_, w["region_strand"])
+    merged = CO.concat3(left.to_list(), center.to_list(), right.to_list())
+    assert_coverage_equal(inp[0]["coverage"].to_list(), merged)
+    rb.profileMatrix(inp, w["flank"], w["bin_params"])
+    assert_matrix_close(inp[0]["profile"], O.profile_matrix(merged, w["flank"], w["bin_params"]))
