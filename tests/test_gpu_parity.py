@@ -593,7 +593,7 @@ def _dense_equal(cov, dense):
             pos += L
 
 
-@pytest.mark.parametrize("name,scale", [("C2", 1.0), ("C3", 0.05), ("C5", 0.02)])
+@pytest.mark.parametrize("name,scale", [("C2", 1.0), ("C3", 0.2), ("C5", 0.1)])
 def test_named_config_against_c_oracle(gpu_auto, name, scale):
     import workloads as W
     rb = gpu_auto
@@ -626,7 +626,7 @@ def test_named_config_against_c_oracle(gpu_auto, name, scale):
 def test_named_config_c4_rna_against_c_oracle(gpu_auto):
     import workloads as W
     rb = gpu_auto
-    w = W.CONFIGS["C4"](scale=0.02, seed=4244)
+    w = W.CONFIGS["C4"](scale=0.1, seed=4244)
     reads = rb.GRanges(w["read_chrom"], w["read_start"], w["read_end"], strand=w["read_strand"],
                        seqlevels=w["chrom_names"], seqlengths=w["chrom_len"])
     genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"], strand=w["region_strand"],
