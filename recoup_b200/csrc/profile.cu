@@ -1,9 +1,10 @@
 // Profile-matrix kernels (sm_100a): binCoverageMatrix / baseCoverageMatrix / splitVector of the
 // reference (/root/reference/R/profile.R:100-212, R/util.R:15-85).
 //
-//   bin_matrix_kernel    1 CTA / region: bin edges from R's seed-42 rank table (util.R:74-80),
-//                        segmented integer sums with sub-warp groups sized to the bin width,
-//                        fp64 mean (or exact median by value bisection) written column-major
+//   bin_mean_kernel      persistent CTAs: bin edges from R's seed-42 rank table (util.R:74-80),
+//                        segment staged by cp.async (double-buffered) and prefix-summed in
+//                        place, bin sum = two shared-memory loads, fp64 mean, column-major
+//   bin_median_kernel    1 CTA / region: exact median by value bisection
 //   interp_kernel        regions shorter than the bin count (util.R:17-73): fmm spline or
 //                        neighbourhood fill, one warp per flagged region
 //   base_matrix_kernel   per-base matrix: int32 -> fp64 tiled transpose (profile.R:100-151)
@@ -79,9 +80,8 @@ __device__ __forceinline__ long long warp_range_sum(const int32_t* __restrict__ 
     return s;
 }
 
-// One CTA per region.  dynamic smem: edges[n + 1] (+ pad) then STAGE_INTS staging ints.
-template <bool MEDIAN>
-__global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
+// Median bins (sumStat = "median"): one CTA per region.  dynamic smem: edges[n + 1].
+__global__ void __launch_bounds__(CTA) bin_median_kernel(BinArgs p) {
     extern __shared__ __align__(16) int sh[];
     int* edges = sh;                    // n + 1
     __shared__ int wcount[WARPS];
@@ -133,93 +133,6 @@ __global__ void __launch_bounds__(CTA) bin_matrix_kernel(BinArgs p) {
         __syncthreads();
     }
     const int32_t* src = p.cov + p.off[r];
-    if (!MEDIAN && bsz < STAGE_MAX_BIN) {
-        // ---- narrow bins: a run of whole bins is staged in shared memory with coalesced 16-byte
-        // loads and turned IN PLACE into its inclusive prefix sum S (lane-serial: each thread
-        // scans an odd number of consecutive int4, one warp scan orders the threads); a bin sum
-        // is then S[last] - S[first - 1]: two shared-memory loads per bin instead of a walk.
-        // S is kept modulo 2^32; that is exact when max(coverage) * (bsz + 1) < 2^32, which
-        // the staging loop checks -- otherwise the run falls back to 64-bit walks.
-        uint32_t* stage = reinterpret_cast<uint32_t*>(sh + ((n + 1 + 3) & ~3));
-        const int bins_per_chunk = (STAGE_INTS - 4) / (bsz + 1);
-        for (int bin0 = 0; bin0 < n; bin0 += bins_per_chunk) {
-            const int bin1 = min(n, bin0 + bins_per_chunk);
-            const int lo_al = edges[bin0] & ~3;
-            const int nvec = (edges[bin1] - lo_al + 3) >> 2;    // <= STAGE_INTS / 4, inside the padded region
-            __syncthreads();
-            const int4* gsrc = reinterpret_cast<const int4*>(src + lo_al);
-            int vmax = 0;
-            for (int i = tid; i < nvec; i += CTA) {
-                const int4 x = __ldg(gsrc + i);
-                reinterpret_cast<int4*>(stage)[i] = x;
-                vmax = max(max(vmax, x.x), max(max(x.y, x.z), x.w));
-            }
-            vmax = __reduce_max_sync(0xffffffffu, vmax);
-            if (lane == 0) wcount[warp] = vmax;
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < WARPS; w++) vmax = max(vmax, wcount[w]);
-            if ((unsigned long long)vmax * (unsigned long long)(bsz + 1) < (1ull << 32)) {
-                const int K = ((nvec + CTA - 1) / CTA) | 1;        // odd: conflict-free LDS.128
-                const int v0 = tid * K, v1 = min(v0 + K, nvec);
-                uint32_t sum = 0;
-                for (int i = v0; i < v1; i++) {
-                    const uint4 x = reinterpret_cast<const uint4*>(stage)[i];
-                    sum += (x.x + x.y) + (x.z + x.w);
-                }
-                uint32_t inc = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                __syncthreads();                                   // wcount (max) fully read
-                if (lane == 31) wcount[warp] = (int)inc;
-                __syncthreads();
-                uint32_t run = inc - sum;
-#pragma unroll
-                for (int w = 0; w < WARPS - 1; w++)
-                    if (w < warp) run += (uint32_t)wcount[w];
-                for (int i = v0; i < v1; i++) {
-                    uint4 x = reinterpret_cast<const uint4*>(stage)[i];
-                    x.x = (run += x.x);
-                    x.y = (run += x.y);
-                    x.z = (run += x.z);
-                    x.w = (run += x.w);
-                    reinterpret_cast<uint4*>(stage)[i] = x;
-                }
-                __syncthreads();
-                for (int b = bin0 + tid; b < bin1; b += CTA) {
-                    const int e0 = edges[b] - lo_al, e1 = edges[b + 1] - lo_al;
-                    const uint32_t sum_b = stage[e1 - 1] - (e0 > 0 ? stage[e0 - 1] : 0u);
-                    out[(int64_t)b * p.ld] = p.scale * ((double)sum_b / (double)(e1 - e0));
-                }
-            } else {
-                const bool rotate = (bsz & 1) == 0;     // even stride: offset the lanes by one each
-                for (int b = bin0 + tid; b < bin1; b += CTA) {
-                    const int e0 = edges[b], len = edges[b + 1] - e0;
-                    const uint32_t* x = stage + (e0 - lo_al);
-                    int q = rotate ? (tid % len) : 0;
-                    long long sum = 0;
-                    for (int it = 0; it < len; it++) {
-                        sum += (long long)x[q];
-                        q = (q + 1 == len) ? 0 : q + 1;
-                    }
-                    out[(int64_t)b * p.ld] = p.scale * ((double)sum / (double)len);
-                }
-            }
-        }
-        return;
-    }
-    if (!MEDIAN) {
-        // ---- wide bins: one warp per bin, coalesced 16-byte global loads ----
-        for (int i = warp; i < n; i += WARPS) {
-            const int lo = edges[i], hi = edges[i + 1];
-            const long long sum = warp_range_sum(src, lo, hi);
-            if (lane == 0) out[(int64_t)i * p.ld] = p.scale * ((double)sum / (double)(hi - lo));
-        }
-        return;
-    }
     // ---- median: groups of g lanes per bin, exact order statistics by value bisection ----
     int g = 1;
     while (g < 32 && g < bsz) g <<= 1;
@@ -689,6 +602,73 @@ __global__ void __launch_bounds__(256) base_matrix_kernel(BaseArgs p) {
     }
 }
 
+// Wide-tile version of the same transpose: 32 regions x 256 columns per CTA.  Rows are read with
+// 16-byte loads when the segment start is 4-aligned (always for whole windows), columns leave as
+// 256-byte runs of 32 consecutive regions, two doubles per lane when the output allows 16-byte
+// stores.  The tile index runs along x (linear, no 65535 limit).
+constexpr int BW_ROWS = 32, BW_COLS = 256;
+
+__global__ void __launch_bounds__(256) base_matrix_wide_kernel(BaseArgs p, int64_t col_tiles,
+                                                               int vec_store) {
+    __shared__ int tile[BW_ROWS][BW_COLS + 1];
+    __shared__ int64_t r_off[BW_ROWS];
+    __shared__ int r_a[BW_ROWS], r_b[BW_ROWS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x / col_tiles) * BW_ROWS;
+    const int64_t k0 = ((int64_t)blockIdx.x % col_tiles) * BW_COLS;
+    if (tid < BW_ROWS) {
+        const int64_t r = r0 + tid;
+        int a = 0, b = 0;
+        int64_t o = 0;
+        if (r < p.R && !p.is_null[r]) {
+            const Seg sg = segment_of(p.len[r], p.where, p.f1, p.f2);
+            a = sg.a;
+            b = sg.b;
+            o = p.off[r];
+        }
+        r_off[tid] = o;
+        r_a[tid] = a;
+        r_b[tid] = b;
+    }
+    __syncthreads();
+    for (int jj = warp; jj < BW_ROWS; jj += 8) {
+        const int a = r_a[jj], b = r_b[jj];
+        const int32_t* src = p.cov + r_off[jj] + a + k0;       // column k0 of this region
+        const int avail = (int)min((int64_t)(b - a) - k0, (int64_t)BW_COLS);   // columns with data
+#pragma unroll
+        for (int h = 0; h < BW_COLS / 128; h++) {
+            const int c = h * 128 + lane * 4;
+            int4 v = make_int4(0, 0, 0, 0);
+            if ((a & 3) == 0 && c + 3 < avail) {
+                v = __ldg(reinterpret_cast<const int4*>(src + c));
+            } else {
+                if (c < avail) v.x = __ldg(src + c);
+                if (c + 1 < avail) v.y = __ldg(src + c + 1);
+                if (c + 2 < avail) v.z = __ldg(src + c + 2);
+                if (c + 3 < avail) v.w = __ldg(src + c + 3);
+            }
+            tile[jj][c] = v.x;
+            tile[jj][c + 1] = v.y;
+            tile[jj][c + 2] = v.z;
+            tile[jj][c + 3] = v.w;
+        }
+    }
+    __syncthreads();
+    const int ncol = (int)min((int64_t)BW_COLS, p.n_cols - k0);
+    if (vec_store && r0 + BW_ROWS <= p.R) {
+        // lanes 0..15 write column c, lanes 16..31 column c + 1; each lane two regions (16 bytes)
+        const int rr = (lane & 15) * 2, dc = lane >> 4;
+        for (int c = warp * 2 + dc; c < ncol; c += 16) {
+            const double2 v = make_double2(p.scale * (double)tile[rr][c], p.scale * (double)tile[rr + 1][c]);
+            *reinterpret_cast<double2*>(p.out + (k0 + c) * p.ld + r0 + rr) = v;
+        }
+    } else {
+        const int64_t r = r0 + lane;
+        if (r < p.R)
+            for (int c = warp; c < ncol; c += 8) p.out[(k0 + c) * p.ld + r] = p.scale * (double)tile[lane][c];
+    }
+}
+
 }  // namespace
 
 // out points to DEVICE memory here; the api layer stages host outputs.
@@ -738,9 +718,9 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         StageTimer t(ST_PROF_BIN);
         const size_t smem = edge_bytes;
         if (smem > 48 * 1024)
-            RCP_CUDA(cudaFuncSetAttribute(bin_matrix_kernel<true>,
+            RCP_CUDA(cudaFuncSetAttribute(bin_median_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bin_matrix_kernel<true><<<(unsigned)R, CTA, smem, g_ctx.stream>>>(a);
+        bin_median_kernel<<<(unsigned)R, CTA, smem, g_ctx.stream>>>(a);
         RCP_LAUNCHED();
     } else {
         // two staging buffers per CTA; the kernel is persistent (one resident wave of CTAs)
@@ -819,6 +799,17 @@ int base_matrix_device(const Coverage& cv, int where, int f1, int f2, int64_t n_
     a.out = d_out;
     a.ld = ld;
     StageTimer t(ST_PROF_BASE);
+    if (n_cols >= 128) {
+        // wide tiles; 16-byte stores need an even leading dimension and a 16-byte aligned matrix
+        const int64_t col_tiles = (n_cols + BW_COLS - 1) / BW_COLS, row_tiles = (R + BW_ROWS - 1) / BW_ROWS;
+        if (col_tiles * row_tiles <= 0x7fffffff) {
+            const int vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);
+            base_matrix_wide_kernel<<<(unsigned)(col_tiles * row_tiles), 256, 0, g_ctx.stream>>>(
+                a, col_tiles, vec);
+            RCP_LAUNCHED();
+            return RCP_OK;
+        }
+    }
     const int64_t gy = (R + 31) / 32, gx = (n_cols + 31) / 32;
     if (gy > 65535) {
         // grid.y is limited to 65535: walk the rows in slabs
