@@ -327,12 +327,25 @@ bkt_find_kernel(int64_t n, const uint32_t* __restrict__ g_start,
 __global__ void __launch_bounds__(CTA)
 bkt_place_kernel(unsigned long long n_hits, const uint2* __restrict__ hits,
                  unsigned long long* __restrict__ cursor, uint32_t* __restrict__ bucket) {
+    // four hits per thread and trip: four independent load -> ATOM -> store chains in flight
     const unsigned long long stride = (unsigned long long)gridDim.x * CTA;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * CTA + threadIdx.x; i < n_hits;
+    const unsigned long long n4 = n_hits >> 2;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * CTA + threadIdx.x; v < n4; v += stride) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(hits) + 2 * v);
+        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(hits) + 2 * v + 1);
+        const unsigned long long s0 = atomicAdd(cursor + a.x, 1ull);
+        const unsigned long long s1 = atomicAdd(cursor + a.z, 1ull);
+        const unsigned long long s2 = atomicAdd(cursor + b.x, 1ull);
+        const unsigned long long s3 = atomicAdd(cursor + b.z, 1ull);
+        bucket[s0] = a.y;
+        bucket[s1] = a.w;
+        bucket[s2] = b.y;
+        bucket[s3] = b.w;
+    }
+    for (unsigned long long i = n4 * 4 + (unsigned long long)blockIdx.x * CTA + threadIdx.x; i < n_hits;
          i += stride) {
         const uint2 h = __ldcs(hits + i);
-        const unsigned long long slot = atomicAdd(cursor + h.x, 1ull);
-        bucket[slot] = h.y;
+        bucket[atomicAdd(cursor + h.x, 1ull)] = h.y;
     }
 }
 
@@ -791,7 +804,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         RCP_CUDA(cudaMemcpyAsync(w.tile_cnt, w.boff, (size_t)T * 8, cudaMemcpyDeviceToDevice,
                                  g_ctx.stream));
         if (h.listed <= hit_cap) {
-            const int64_t blocks = ((int64_t)h.listed + CTA - 1) / CTA;
+            const int64_t blocks = ((int64_t)h.listed / 4 + CTA - 1) / CTA + 1;
             bkt_place_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)g_ctx.sm_count * 16), CTA,
                                0, g_ctx.stream>>>(h.listed, w.hits, w.tile_cnt, w.bucket);
             RCP_LAUNCHED();
