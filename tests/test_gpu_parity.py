@@ -495,9 +495,9 @@ def test_index_sort_uniform_keys(gpu, monkeypatch, n, bits, which):
 
 @pytest.mark.parametrize("which", ["cub", "hand"])
 def test_index_sort_pileups_and_recursion(gpu, monkeypatch, which):
-    monkeypatch.setenv("RCP_SORT", which)
     """Buckets far over the 32 K-key capacity: one value repeated 400 K times, 150 K keys inside a
     512-wide window, 90 K inside a 40 K-wide window, sorted / reversed inputs, all-equal input."""
+    monkeypatch.setenv("RCP_SORT", which)
     rng = np.random.default_rng(5)
     parts = [np.full(400_000, 2_000_000_123, dtype=np.uint32),
              (3_000_000_000 + rng.integers(0, 512, size=150_000)).astype(np.uint32),
