@@ -287,7 +287,7 @@ def run_b200(args):
     out_box = {}
     stats = {}
 
-    def device_step():
+    def device_step(k=0):
         """reads (HBM) -> index -> coverage -> matrix (HBM)."""
         h = C.c_int(0)
         _lib.check(L.rcp_reads_load(N, vp(d_reads[0]), vp(d_reads[1]), vp(d_reads[2]), vp(d_reads[3]),
@@ -313,8 +313,11 @@ def run_b200(args):
             _lib.check(L.rcp_profile_ncols(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
                                            bp["regionBinSize"], C.byref(nc)))
             ncols_box["n"] = nc.value
-            out_box["m"] = torch.empty((nc.value, R), dtype=torch.float64, device=dev)  # col-major R x nc
-            out_box["ptr"], out_box["ld"] = out_box["m"].data_ptr(), R
+            # col-major R x nc, double buffered (N > 1: the gather of step k overlaps step k + 1)
+            out_box["bufs"] = [torch.empty((nc.value, R), dtype=torch.float64, device=dev)
+                               for _ in range(2 if world > 1 else 1)]
+            out_box["m"] = out_box["bufs"][0]
+            out_box["ptr"], out_box["ld"] = None, R
             if world > 1 and args.exchange == "p2p":
                 # every rank writes its rows straight into rank 0's matrix (peer-mapped)
                 from recoup_b200.sharding import PeerMatrix
@@ -325,22 +328,31 @@ def run_b200(args):
             tl, nn = C.c_int64(0), C.c_int64(0)
             L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
             stats["total_len"], stats["n_null"] = tl.value, nn.value
+        if out_box["ptr"] is not None:      # peer-mapped matrix of rank 0 / verification buffer
+            out_ptr = out_box["ptr"]
+        else:
+            buf = out_box["bufs"][k % len(out_box["bufs"])]
+            if world > 1 and gdone[k % 2] is not None:
+                stream.wait_event(gdone[k % 2])     # the gather that read this buffer two steps ago
+            out_ptr = buf.data_ptr()
         _lib.check(L.rcp_profile_matrix(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
                                         bp["regionBinSize"], _lib.STAT[bp["sumStat"]],
                                         _lib.INTERP[bp["interpolation"]], 42, 0,
-                                        C.c_void_p(out_box["ptr"]), out_box["ld"], _lib.MEM_DEVICE))
+                                        C.c_void_p(out_ptr), out_box["ld"], _lib.MEM_DEVICE))
         L.rcp_coverage_free(cov.value)
         L.rcp_reads_free(h.value)
 
     gather_box = {}
 
-    def rows_scatter(block, ids, k, full):
-        _lib.check(L.rcp_rows_scatter(vp(block), block.shape[1], k, block.shape[0], vp(ids),
-                                      vp(full), full.shape[1]))
+    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gdone = [None, None]
 
-    def gather_step():
-        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)),
-        placed into the full column-major matrix by rcp_rows_scatter."""
+    def gather_step(k=0):
+        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) and their
+        placement into the full column-major matrix.  It runs on its own stream, behind the bin
+        kernel of this step and beside the next step's kernels: the output matrix is double
+        buffered (step k writes buffer k % 2), so only the gather of step k - 2 must have finished
+        before step k may overwrite its buffer."""
         if world == 1:
             return
         if "peer" in out_box:               # the rows are already in place: order the stores
@@ -349,12 +361,18 @@ def run_b200(args):
                     out_box["peer"].fence()
             return
         from recoup_b200.sharding import RowGather
-        with torch.cuda.stream(stream):
+        ready = torch.cuda.Event()
+        ready.record(stream)                # the bin kernel of this step (library stream)
+        gstream.wait_event(ready)
+        with torch.cuda.stream(gstream):
             if "g" not in gather_box:       # buffers and row indices are set up once
-                gather_box["g"] = RowGather(out_box["m"].shape[0], np.arange(rank * R, (rank + 1) * R),
-                                            R * world, dev, out_box["m"].dtype, dst=0,
-                                            sizes=[R] * world)
-            gather_box["full"] = gather_box["g"].gather(out_box["m"], scatter=rows_scatter)
+                gather_box["g"] = RowGather(out_box["bufs"][0].shape[0],
+                                            np.arange(rank * R, (rank + 1) * R), R * world, dev,
+                                            out_box["bufs"][0].dtype, dst=0, sizes=[R] * world)
+            gather_box["full"] = gather_box["g"].gather(out_box["bufs"][k % 2])
+            done = torch.cuda.Event()
+            done.record(gstream)
+        gdone[k % 2] = done
 
     def barrier():
         torch.cuda.synchronize()
@@ -365,9 +383,9 @@ def run_b200(args):
     # ---- warm-up ----
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-        gather_step()
+    for k in range(max(args.warmup, 3)):
+        device_step(k)
+        gather_step(k)
     barrier()
 
     # ---- timed: device-resident ----
@@ -379,9 +397,13 @@ def run_b200(args):
     barrier()
     t_begin = time.time()
     ev0.record(stream)
-    for _ in range(args.steps):
-        device_step()
-        gather_step()
+    for k in range(args.steps):
+        device_step(k)
+        gather_step(k)
+    if world > 1:
+        for ev in gdone:                    # the timed region ends when the last gathers have landed
+            if ev is not None:
+                stream.wait_event(ev)
     ev1.record(stream)
     barrier()
     t_end = time.time()
@@ -474,6 +496,8 @@ def run_b200(args):
         out_box["ptr"], out_box["ld"] = out_box["m"].data_ptr(), R      # one more step, local output
         device_step()
         out_box["ptr"], out_box["ld"] = saved
+        if "peer" not in out_box:           # and one more gather of exactly that block
+            gather_step(0)
         barrier()
         mine = out_box["m"].double().sum().reshape(1)
         sums = [torch.zeros_like(mine) for _ in range(world)]
@@ -566,7 +590,9 @@ def run_b200(args):
                        "coverage_path": args.path,
                        "parallelism": ("regions sharded over %d GPU(s), " % world) +
                                       ("rows stored into rank 0's matrix over NVLink (peer-mapped)"
-                                       if world > 1 and args.exchange == "p2p" else "NCCL row gather")},
+                                       if world > 1 and args.exchange == "p2p" else
+                                       "NCCL row gather on its own stream (double-buffered matrix: "
+                                       "the gather of step k runs beside step k + 1)")},
             "stage_ms_per_step": {k: v[0] * v[1] / args.steps for k, v in stage.items()},
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
             "roofline": roof,

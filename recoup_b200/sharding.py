@@ -83,13 +83,18 @@ class RowGather:
         self.block = None if self.equal else torch.zeros((self.n_cols, self.n_max), dtype=dtype,
                                                          device=device)
         if self.rank == dst:
-            self.blocks = [torch.empty((self.n_cols, self.n_max), dtype=dtype, device=device)
-                           for _ in range(self.world)]
+            self.stack = torch.empty((self.world, self.n_cols, self.n_max), dtype=dtype, device=device)
+            self.blocks = [self.stack[r] for r in range(self.world)]
             self.id_list = [torch.empty_like(ids) for _ in range(self.world)]
             self.full = torch.zeros((self.n_cols, self.n_total), dtype=dtype, device=device)
         else:
-            self.blocks = self.id_list = self.full = None
+            self.stack = self.blocks = self.id_list = self.full = None
         dist.gather(ids, self.id_list, dst=dst, group=group)      # once
+        # rank r owns rows [r * n, (r + 1) * n): the blocks drop into place with ONE strided copy
+        self.in_order = False
+        if self.rank == dst and self.equal and self.n_max * self.world == self.n_total:
+            want = torch.arange(self.n_total, dtype=torch.int64, device=device)
+            self.in_order = bool(torch.equal(torch.cat(self.id_list), want))
 
     def gather(self, local, scatter=None):
         """returns on `dst` a torch tensor [n_cols, n_total] (column-major n_total x n_cols, reused
@@ -104,6 +109,9 @@ class RowGather:
         dist.gather(send, self.blocks, dst=self.dst, group=self.group)
         if self.rank != self.dst:
             return None
+        if self.in_order and scatter is None:
+            self.full.view(self.n_cols, self.world, self.n_max).copy_(self.stack.permute(1, 0, 2))
+            return self.full
         for r in range(self.world):
             k = self.sizes[r]
             if k == 0:

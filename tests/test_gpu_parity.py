@@ -647,3 +647,23 @@ def test_named_config_c4_rna_against_c_oracle(gpu_auto):
     assert_coverage_equal(inp[0]["coverage"].to_list(), merged)
     rb.profileMatrix(inp, w["flank"], w["bin_params"])
     assert_matrix_close(inp[0]["profile"], O.profile_matrix(merged, w["flank"], w["bin_params"]))
+
+
+def test_rows_scatter_places_a_row_block(gpu):
+    """rcp_rows_scatter (multi-GPU helper): dst[row_index[i], c] = src[i, c], column-major."""
+    import torch
+    from recoup_b200 import _lib
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    n_rows, n_cols, total = 1000, 37, 5000
+    src = torch.from_numpy(rng.random((n_cols, n_rows + 11)))[:, :].to(dev)     # ld_src = n_rows + 11
+    ids_np = rng.permutation(total)[:n_rows].astype(np.int64)
+    ids = torch.from_numpy(ids_np).to(dev)
+    dst = torch.zeros((n_cols, total), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib.rcp_rows_scatter(C.c_void_p(src.data_ptr()), n_rows + 11, n_rows, n_cols,
+                                         C.c_void_p(ids.data_ptr()), C.c_void_p(dst.data_ptr()), total))
+    _lib.check(_lib.lib.rcp_sync())
+    want = np.zeros((n_cols, total))
+    want[:, ids_np] = src.cpu().numpy()[:, :n_rows]
+    assert np.array_equal(dst.cpu().numpy(), want)
