@@ -96,7 +96,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t_begin, t_end):
+    def stop(self, t_begin, t_end, label="timed region"):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -123,7 +123,7 @@ class ClockSampler:
             return sm, mx, reasons
 
         inside = [r for r in self.rows if t_begin <= r[0] <= t_end]
-        window = "timed region"
+        window = label
         if len(inside) < 3:
             inside = self.rows          # timed region shorter than the sampling period
             window = "warm-up + timed region (timed region < 3 samples long)"
@@ -418,9 +418,18 @@ def run_b200(args):
     _lib.check(L.rcp_timing_enable(0))
     stage = {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
              for i in range(n_st) if cnt[i] > 0}
-    # the sampler polls nvidia-smi (a driver-lock heavy call): it covers warm-up + the timed
-    # device region only and is stopped before the host-API (e2e) loop
-    clocks = sampler.stop(t_begin, t_end)
+    # The timed region is a few tens of milliseconds, shorter than one nvidia-smi period: keep
+    # the same steps running (untimed) for a second so that the clock record is taken UNDER THIS
+    # LOAD.  The sampler polls nvidia-smi (a driver-lock heavy call), so it is stopped before the
+    # host-API (e2e) loop.
+    t_probe = time.time()
+    k = args.steps
+    while time.time() - t_probe < 1.0:
+        device_step(k)
+        gather_step(k)
+        k += 1
+    barrier()
+    clocks = sampler.stop(t_begin, time.time(), "timed region + 1 s of the same steps (untimed)")
 
     # ---- timed: end to end through the public host API (pinned host buffers) ----
     def pinned(a):
