@@ -80,7 +80,9 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         *gs = 0;
         *ge1 = 0;
         if (map_read(c, s, e, st, n_chrom, chrom_off, chrom_len, frag_len, gs, ge1, &my_err)) {
-            if (*ge1 - *gs != w) {
+            // reads of another width: recorded until the buffer overflows (then uniform-width
+            // mode is abandoned anyway and the single counter must not become a hot spot)
+            if (*ge1 - *gs != w && *reinterpret_cast<volatile unsigned int*>(exc.count) <= exc.cap) {
                 const unsigned int k = atomicAdd(exc.count, 1u);
                 if (k < exc.cap) {
                     exc.xw[k] = *gs + w;
@@ -334,6 +336,7 @@ void reads_release(ReadsIdx& r) {
         dfree(r.cls[c].cxs);
         dfree(r.cls[c].cye);
         r.cls[c].built = false;
+        r.cls[c].xs_sorted = false;
     }
     dfree(r.exc_xw);
     dfree(r.exc_e1);
@@ -348,9 +351,10 @@ int reads_build_class(ReadsIdx& r, int cls) {
     SortedClass& sc = r.cls[cls];
     if (sc.built) return RCP_OK;
     const bool uni = r.uniform_w != 0;   // ye == xs + w: no second array, no second sort
+    const bool xs_done = sc.xs_sorted;   // the pair sort of the GRangesList path already made xs
     if (cls == CLS_ALL) {
         sc.n = r.n;
-        if (sc.xs == nullptr) {    // normally pre-filled by the map kernel (reads_load_impl)
+        if (sc.xs == nullptr) {    // pre-filled by the map kernel under RCP_PATH_INDEX
             RCP_TRY(dalloc(&sc.xs, (size_t)r.n));
             RCP_CUDA(cudaMemcpyAsync(sc.xs, r.g_start, (size_t)r.n * 4, cudaMemcpyDeviceToDevice,
                                      g_ctx.stream));
@@ -396,7 +400,8 @@ int reads_build_class(ReadsIdx& r, int cls) {
     }
     {
         StageTimer t(ST_INDEX_SORT);
-        RCP_TRY(sort_keys_u32(sc.xs, sc.n, r.key_bits));
+        if (!xs_done) RCP_TRY(sort_keys_u32(sc.xs, sc.n, r.key_bits));
+        sc.xs_sorted = true;
         if (!uni) RCP_TRY(sort_keys_u32(sc.ye, sc.n, r.key_bits));
         if (sc.cn > 0) {
             RCP_TRY(sort_keys_u32(sc.cxs, sc.cn, 32));
@@ -410,7 +415,10 @@ int reads_build_class(ReadsIdx& r, int cls) {
 
 int reads_build_pairs(ReadsIdx& r) {
     if (r.pairs_built) return RCP_OK;
-    RCP_TRY(reads_build_class(r, CLS_ALL));
+    // One (start, read id) pair sort gives both the permutation and the sorted starts the list
+    // kernels search (the xs of the ALL class); the independently sorted ends of that class are
+    // only needed by the rank method and stay unbuilt until a GRanges mask asks for them.
+    SortedClass& all = r.cls[CLS_ALL];
     uint32_t *keys = nullptr, *perm = nullptr;
     RCP_TRY(dalloc(&keys, (size_t)r.n));
     RCP_TRY(dalloc(&perm, (size_t)r.n));
@@ -422,6 +430,13 @@ int reads_build_pairs(ReadsIdx& r) {
         StageTimer t(ST_INDEX_SORT);
         RCP_TRY(sort_pairs_u32(keys, perm, r.n, r.key_bits));
     }
+    if (!all.xs_sorted) {           // hand the sorted keys to the ALL class
+        dfree(all.xs);
+        all.xs = keys;
+        all.n = r.n;
+        all.xs_sorted = true;
+        keys = nullptr;
+    }
     RCP_TRY(dalloc(&r.p_end1, (size_t)r.n));
     if (r.has_strand) RCP_TRY(dalloc(&r.p_strand, (size_t)r.n));
     gather_pairs_kernel<<<grid_for(r.n), TPB, 0, g_ctx.stream>>>(r.n, perm, r.g_end1, r.d_strand,
@@ -429,7 +444,7 @@ int reads_build_pairs(ReadsIdx& r) {
     RCP_LAUNCHED();
     RCP_TRY(dalloc(&r.p_maxend1, (size_t)r.n));
     RCP_TRY(running_max_u32(r.p_end1, r.p_maxend1, r.n));
-    dfree(keys);
+    if (keys) dfree(keys);
     dfree(perm);
     r.device_bytes += (size_t)r.n * (8 + (r.has_strand ? 1 : 0));
     r.pairs_built = true;

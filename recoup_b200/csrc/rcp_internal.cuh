@@ -117,7 +117,8 @@ struct DevIn {
 enum { CLS_ALL = 0, CLS_PLUS = 1, CLS_MINUS = 2, CLS_STAR = 3, CLS_N = 4 };
 
 struct SortedClass {
-    bool built = false;
+    bool built = false;       // xs and ye (or the uniform-width stand-ins) sorted
+    bool xs_sorted = false;   // xs alone is sorted (enough for the GRangesList path)
     int64_t n = 0;
     uint32_t* xs = nullptr;   // sorted global start coordinates
     uint32_t* ye = nullptr;   // sorted global (end + 1) coordinates, sorted independently;
