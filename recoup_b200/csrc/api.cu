@@ -183,7 +183,7 @@ int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t
                     int strand_filter, int mem, Coverage* cv);
 int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                              const int32_t* end, const int8_t* strand, int ignore_strand,
-                             int strand_filter, int mem, Coverage* cv);
+                             int strand_filter, int mem, bool may_switch, Coverage* cv);
 int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_ranges,
                   const int32_t* chrom, const int32_t* start, const int32_t* end,
                   const int8_t* strand, int ignore_strand, int strand_filter, int mem,
@@ -557,10 +557,15 @@ int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32
                                : (r->cls[CLS_PLUS].built && r->cls[CLS_MINUS].built &&
                                   r->cls[CLS_STAR].built);
     }
-    int rc = use_index ? coverage_ranges(*r, n_regions, chrom, start, end, strand,
-                                         ignore_strand != 0, strand_filter, mem, cv)
-                       : coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand,
-                                                  ignore_strand != 0, strand_filter, mem, cv);
+    int rc = RCP_SWITCH_TO_INDEX;
+    if (!use_index) {
+        rc = coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                      strand_filter, mem, g_ctx.coverage_path == RCP_PATH_AUTO, cv);
+        if (rc == RCP_SWITCH_TO_INDEX) coverage_release(*cv);      // dense mask, very many reads
+    }
+    if (rc == RCP_SWITCH_TO_INDEX)
+        rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                             strand_filter, mem, cv);
     if (rc != RCP_OK) {
         drop_coverage(h);
         return rc;

@@ -667,9 +667,13 @@ int launch_rescatter(const ReadsIdx& rd, const Work& w) {
 
 }  // namespace
 
+// may_switch: under RCP_PATH_AUTO the call gives up right after the plan (RCP_SWITCH_TO_INDEX) when
+// the mask is dense AND the read set is very large: there the random accesses of the two read
+// passes leave L2 (C5 at full size: 200 M reads, 10^6 windows: 12.3 ms against 10.6 ms through
+// the sorted index), while for sparse masks or fewer reads the buckets win (C2, C3, C5 / 4).
 int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                              const int32_t* end, const int8_t* strand, int ignore_strand,
-                             int strand_filter, int mem, Coverage* cv) {
+                             int strand_filter, int mem, bool may_switch, Coverage* cv) {
     DevIn<int32_t> d_chrom, d_start, d_end;
     DevIn<int8_t> d_strand;
     RCP_TRY(d_chrom.init(chrom, (size_t)R, mem));
@@ -725,6 +729,11 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
     const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
     if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
+    int64_t switch_reads = 120000000;
+    if (const char* e = getenv("RCP_BKT_SWITCH_READS")) switch_reads = strtoll(e, nullptr, 10);   // tests
+    if (may_switch && rd.n >= switch_reads &&
+        (double)Tb * TILE + (double)Ts * SMALL_MAX >= 0.25 * (double)rd.chrom_off[(size_t)rd.n_chrom])
+        return RCP_SWITCH_TO_INDEX;
 
     // ---- 2. tiles, cell table, block bitmap -------------------------------------------------
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];

@@ -24,6 +24,7 @@ struct Ctx {
 extern Ctx g_ctx;
 
 int fail(int code, const char* fmt, ...);   // records the message, returns code
+constexpr int RCP_SWITCH_TO_INDEX = -1000;   // internal: the bucket path hands the call to the index path
 int require_ready();                         // RCP_OK or RCP_ERR_NOGPU
 
 #define RCP_CUDA(call)                                                                         \

@@ -137,6 +137,11 @@ def test_bucket_path_overlapping_regions_and_hit_list_overflow(gpu, monkeypatch)
         monkeypatch.setenv("RCP_BKT_HIT_CAP", "100")
         got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
         assert_coverage_equal(got.to_list(), want)
+        # dense mask + "very many" reads: the automatic path hands the call to the sorted index
+        monkeypatch.setenv("RCP_BKT_SWITCH_READS", "1000")
+        got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+        assert_coverage_equal(got.to_list(), want)
+        monkeypatch.delenv("RCP_BKT_SWITCH_READS", raising=False)
         monkeypatch.delenv("RCP_BKT_HIT_CAP", raising=False)
     monkeypatch.delenv("RCP_BKT_HIT_CAP", raising=False)
 
