@@ -278,20 +278,35 @@ bkt_find_kernel(int64_t n, const uint32_t* __restrict__ g_start,
     // one read per lane (invalid lanes pass e1 = 0)
     auto slot = [&](uint32_t s, uint32_t e1, int st) {
         bool cand = e1 > s;
-        uint32_t cur = s >> CELL_SHIFT, c1 = 0;
+        const uint32_t c0 = s >> CELL_SHIFT;
+        uint32_t c1 = c0;
         if (cand) {
             const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
-            cand = (b1 > b0 + 1u) || (((bm[b0 >> 5] >> (b0 & 31u)) | (bm[b1 >> 5] >> (b1 & 31u))) & 1u);
+            uint32_t w = bm[b0 >> 5] >> (b0 & 31u);
+            if (b1 != b0) w |= bm[b1 >> 5] >> (b1 & 31u);          // rare: one load for most reads
+            cand = (b1 > b0 + 1u) || (w & 1u);
             c1 = (e1 - 1u) >> CELL_SHIFT;
         }
         const uint32_t tag = (st > 0 ? 0u : (st < 0 ? 1u : 2u)) << 30;
-        for (;;) {
-            const bool has = cand && cur <= c1;
+        // first cell of every candidate, last cell of those that touch two, then (reads longer
+        // than a cell: rare) the cells in between
+        const unsigned m1 = __ballot_sync(0xffffffffu, cand);
+        if (m1 == 0u) return;
+        if (cand) q[qn + __popc(m1 & lt)] = make_uint4(s, e1, c0 | tag, 0u);
+        qn += __popc(m1);
+        while (qn >= 32) round(32);     // a round may re-queue up to 32 items: keep qn < 32
+        const bool two = cand && c1 != c0;
+        const unsigned m2 = __ballot_sync(0xffffffffu, two);
+        if (m2 == 0u) return;
+        if (two) q[qn + __popc(m2 & lt)] = make_uint4(s, e1, c1 | tag, 0u);
+        qn += __popc(m2);
+        while (qn >= 32) round(32);     // a round may re-queue up to 32 items: keep qn < 32
+        for (uint32_t cur = c0 + 1u;; cur++) {
+            const bool has = two && cur < c1;
             const unsigned m = __ballot_sync(0xffffffffu, has);
             if (m == 0u) break;
             if (has) q[qn + __popc(m & lt)] = make_uint4(s, e1, cur | tag, 0u);
             qn += __popc(m);
-            cur++;
             while (qn >= 32) round(32);
         }
     };
