@@ -8,7 +8,6 @@
 //   interp_kernel        regions shorter than the bin count (util.R:17-73): fmm spline or
 //                        neighbourhood fill, one warp per flagged region
 //   base_matrix_kernel   per-base matrix: int32 -> fp64 tiled transpose (profile.R:100-151)
-#include <cuda_pipeline.h>
 
 #include <algorithm>
 
@@ -182,6 +181,44 @@ __global__ void __launch_bounds__(CTA) bin_median_kernel(BinArgs p) {
     }
 }
 
+// ---- TMA (1-D bulk copy) + mbarrier helpers for the staging of bin_mean_kernel ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy by the TMA unit (one thread issues it; `bytes` a multiple of 16,
+// both addresses 16-byte aligned); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ---- mean bins: persistent, double-buffered ----------------------------------------------------
 // One 32-byte descriptor per region (written by bin_desc_kernel), so that the main kernel does
 // no divisions and loads nothing else per region:
@@ -240,8 +277,10 @@ __device__ __forceinline__ BinDesc load_bin_desc(const BinDesc* __restrict__ p) 
 // sum S (lane-serial: each thread scans consecutive int4, one warp scan orders the threads); a
 // bin sum is then S[last] - S[first - 1], two shared-memory loads per bin.  S is kept modulo
 // 2^32, exact while max(coverage) * (bsz + 1) < 2^32 (checked; else 64-bit walks).  The staging
-// copy of the NEXT region (cp.async, second buffer) and the descriptor of the one after it are
-// issued before the current region is processed, so HBM latency hides behind the arithmetic.
+// copy of the NEXT region -- one TMA bulk copy (cp.async.bulk, up to 48 KB) issued by a single
+// thread into the second buffer, completion on an mbarrier -- and the descriptor of the region
+// after it are issued before the current region is processed, so HBM latency hides behind the
+// arithmetic and no thread spends instructions on the copy.
 // Wide bins: one warp per bin, 16-byte global loads.  Segments shorter than the bin count go
 // to the interpolation list (util.R:17).
 __global__ void __launch_bounds__(BT)
@@ -252,33 +291,50 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
     __shared__ int wcount[BWARPS];
     __shared__ int wmaxs[BWARPS];
     __shared__ int chunk_carry;
+    __shared__ __align__(8) uint64_t full_bar[2];            // one per staging buffer
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n;
     const int64_t step = gridDim.x;
     int64_t r = blockIdx.x;
     if (r >= R) return;
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        fence_proxy_async();                // make the initialised barriers visible to the TMA unit
+    }
+    __syncthreads();
     BinDesc none;
     none.off_lo = none.off_hi = none.a = none.b = none.bsz = none.dif = none.lo_al = none.nvec = 0;
 
     auto src_of = [&](const BinDesc& d) {
         return p.cov + (int64_t)(((uint64_t)(uint32_t)d.off_hi << 32) | (uint32_t)d.off_lo);
     };
-    auto issue = [&](const BinDesc& d, uint32_t* buf) {
-        const int32_t* g = src_of(d) + d.lo_al;
-        for (int i = tid; i < d.nvec; i += BT) __pipeline_memcpy_async(buf + 4 * i, g + 4 * i, 16);
-        __pipeline_commit();
+    // thread 0 starts the copy of one region into buffer `which` (regions that are not one staged
+    // run just complete the barrier phase)
+    auto issue = [&](const BinDesc& d, int which) {
+        if (tid != 0) return;
+        uint64_t* bar = &full_bar[which];
+        if (d.nvec > 0) {
+            const uint32_t bytes = (uint32_t)d.nvec * 16u;
+            fence_proxy_async();            // earlier generic reads of this buffer are ordered first
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_1d(bufs + (size_t)which * buf_ints, src_of(d) + d.lo_al, bytes, bar);
+        } else {
+            mbar_arrive(bar);
+        }
     };
 
     BinDesc d = load_bin_desc(desc + r);
     BinDesc dn = (r + step < R) ? load_bin_desc(desc + r + step) : none;
     int cur = 0;
-    issue(d, bufs);
+    uint32_t parity[2] = {0u, 0u};          // phase of each buffer's barrier
+    issue(d, 0);
     for (;;) {
         const BinDesc dnn = (r + 2 * step < R) ? load_bin_desc(desc + r + 2 * step) : none;
         uint32_t* stage = bufs + (size_t)cur * buf_ints;
-        issue(dn, bufs + (size_t)(cur ^ 1) * buf_ints);
-        __pipeline_wait_prior(1);           // everything but the copy just issued has landed
-        __syncthreads();
+        issue(dn, cur ^ 1);
+        mbar_wait(&full_bar[cur], parity[cur]);     // this region's copy has landed
+        parity[cur] ^= 1u;
         double* out = p.out + r;
         const int Ls = d.b - d.a;
         if (Ls <= 0) {                      // NULL coverage -> zero row (profile.R:191-197)
@@ -401,7 +457,7 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
         dn = dnn;
         cur ^= 1;
     }
-    __pipeline_wait_prior(0);
+    // the copy issued for the (non-existent) region after the last one carries no bytes
 }
 
 // ---- interpolation of short segments (util.R:17-73) ------------------------------------------
