@@ -153,6 +153,23 @@ __device__ __forceinline__ void block_scan_store(const int* diff, int tlen, int 
 // third of the instructions of the row-by-row scan above (one shuffle scan per RPW * 128
 // outputs instead of per 128).
 // --------------------------------------------------------------------------------------------
+// ---- TMA 1-D bulk store (shared -> global), bulk-group completion ------------------------------
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the bulk stores issued by this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // rows [row0, row0 + RPW) of the scanned tile -> dst, fully unrolled
 template <int RPW>
 __device__ __forceinline__ void warp_rows_out_n(const int* tile, int row0, int tlen,
@@ -177,7 +194,7 @@ __device__ __forceinline__ void warp_rows_out_n(const int* tile, int row0, int t
 
 // Whole CTA, RPW rows per warp (compile-time: every loop unrolls, no predicates).  `diff` must be
 // zero-padded up to WARPS * RPW rows.  wtot needs WARPS ints.
-template <int RPW>
+template <int RPW, bool TMA_OUT>
 __device__ __forceinline__ void block_scan_store_fwd(int* diff, int tlen, int* wtot,
                                                      int32_t* __restrict__ dst) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,7 +223,23 @@ __device__ __forceinline__ void block_scan_store_fwd(int* diff, int tlen, int* w
         *(reinterpret_cast<int4*>(mine) + k) = o;
     }
     __syncwarp();
-    warp_rows_out_n<RPW>(diff, warp * RPW, tlen, dst);
+    if (TMA_OUT) {
+        // the warp's rows are contiguous in shared memory and in the output: one bulk store by
+        // the TMA unit (16-byte granules; a ragged tail spills <= 3 ints into the region's own
+        // padding).  The caller waits for the store to have read shared memory
+        // (tma_store_wait_read) before the tile buffer is reused.
+        if (lane == 0) {
+            const int c0 = warp * RPW * ROW;
+            const int valid = min(RPW * ROW, tlen - c0);
+            if (valid > 0) {
+                fence_proxy_async_smem();
+                tma_store_1d(dst + c0, diff + c0, (uint32_t)((valid + 3) & ~3) * 4u);
+                tma_store_commit();
+            }
+        }
+    } else {
+        warp_rows_out_n<RPW>(diff, warp * RPW, tlen, dst);
+    }
 }
 
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }

@@ -505,7 +505,7 @@ __device__ __forceinline__ void tile_body(int* diff, int* wtot, int tlen, uint32
     if (e1 != NONE) add(e1);
     for (uint32_t i = 2 * CTA + tid; i < n; i += CTA) add(__ldcs(entries + i));
     __syncthreads();
-    block_scan_store_fwd<RPW>(diff, tlen, wtot, dst);
+    block_scan_store_fwd<RPW, true>(diff, tlen, wtot, dst);
 }
 
 // Long regions: persistent CTAs walk the tiles.  Nothing the current tile needs is loaded in
@@ -551,6 +551,7 @@ bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* _
             }
         }
         t += step;
+        if ((tid & 31u) == 0) tma_store_wait_read();    // this warp's bulk store has read `diff`
         if (t >= Tb) break;
         __syncthreads();            // diff and wtot are reused
         d = dn;
