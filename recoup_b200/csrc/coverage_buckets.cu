@@ -205,7 +205,7 @@ constexpr int HB_CAP = HB_FLUSH + 32;
 constexpr size_t FIND_SMEM_FIXED = (size_t)RWARPS * (QCAP * sizeof(uint4) + HB_CAP * sizeof(uint2));
 
 struct FindOut {
-    unsigned long long* tile_cnt;
+    uint32_t* tile_cnt;             // 32-bit: the total number of hits is checked to be < 2^32
     uint2* hits;                    // (tile, event pair)
     unsigned long long cap;         // entries available in `hits`
     unsigned long long* hit_n;      // entries reserved so far (> cap: the list is incomplete)
@@ -269,7 +269,7 @@ bkt_find_kernel(int64_t n, const uint32_t* __restrict__ g_start,
         qn += __popc(mm);
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hit) {
-            atomicAdd(out.tile_cnt + tile, 1ull);
+            atomicAdd(out.tile_cnt + tile, 1u);
             hb[hn + __popc(hm & lt)] = make_uint2(tile, packed);
         }
         hn += __popc(hm);
@@ -341,17 +341,17 @@ bkt_find_kernel(int64_t n, const uint32_t* __restrict__ g_start,
 // hit list -> per-tile buckets.  `cursor` starts at the tile's bucket offset.
 __global__ void __launch_bounds__(CTA)
 bkt_place_kernel(unsigned long long n_hits, const uint2* __restrict__ hits,
-                 unsigned long long* __restrict__ cursor, uint32_t* __restrict__ bucket) {
+                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ bucket) {
     // four hits per thread and trip: four independent load -> ATOM -> store chains in flight
     const unsigned long long stride = (unsigned long long)gridDim.x * CTA;
     const unsigned long long n4 = n_hits >> 2;
     for (unsigned long long v = (unsigned long long)blockIdx.x * CTA + threadIdx.x; v < n4; v += stride) {
         const uint4 a = __ldcs(reinterpret_cast<const uint4*>(hits) + 2 * v);
         const uint4 b = __ldcs(reinterpret_cast<const uint4*>(hits) + 2 * v + 1);
-        const unsigned long long s0 = atomicAdd(cursor + a.x, 1ull);
-        const unsigned long long s1 = atomicAdd(cursor + a.z, 1ull);
-        const unsigned long long s2 = atomicAdd(cursor + b.x, 1ull);
-        const unsigned long long s3 = atomicAdd(cursor + b.z, 1ull);
+        const uint32_t s0 = atomicAdd(cursor + a.x, 1u);
+        const uint32_t s1 = atomicAdd(cursor + a.z, 1u);
+        const uint32_t s2 = atomicAdd(cursor + b.x, 1u);
+        const uint32_t s3 = atomicAdd(cursor + b.z, 1u);
         bucket[s0] = a.y;
         bucket[s1] = a.w;
         bucket[s2] = b.y;
@@ -360,7 +360,7 @@ bkt_place_kernel(unsigned long long n_hits, const uint2* __restrict__ hits,
     for (unsigned long long i = n4 * 4 + (unsigned long long)blockIdx.x * CTA + threadIdx.x; i < n_hits;
          i += stride) {
         const uint2 h = __ldcs(hits + i);
-        bucket[atomicAdd(cursor + h.x, 1ull)] = h.y;
+        bucket[atomicAdd(cursor + h.x, 1u)] = h.y;
     }
 }
 
@@ -370,7 +370,7 @@ __device__ __forceinline__ void rescatter_read(uint32_t s, uint32_t e1, int st,
                                                const uint32_t* __restrict__ bm,
                                                const uint4* __restrict__ cell_rec,
                                                const uint4* __restrict__ ovf,
-                                               unsigned long long* __restrict__ cursor,
+                                               uint32_t* __restrict__ cursor,
                                                uint32_t* __restrict__ bucket) {
     if (e1 <= s) return;
     const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void rescatter_read(uint32_t s, uint32_t e1, int st,
         uint32_t p = rec.w, packed;
         for (;;) {
             if (record_hit<STRANDED>(rec, c, s, e1, bit, &packed))
-                bucket[atomicAdd(cursor + rec.z, 1ull)] = packed;
+                bucket[atomicAdd(cursor + rec.z, 1u)] = packed;
             if (p == NONE) break;
             rec = __ldg(ovf + p++);
             if (rec.y == 0u) break;
@@ -397,7 +397,7 @@ bkt_rescatter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
                      const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
                      const uint32_t* __restrict__ bitmap, int bm_words,
                      const uint4* __restrict__ cell_rec, const uint4* __restrict__ ovf,
-                     unsigned long long* __restrict__ cursor, uint32_t* __restrict__ bucket) {
+                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ bucket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
     for (int i = threadIdx.x; i < bm_words; i += RTPB) bm[i] = bitmap[i];
@@ -413,16 +413,16 @@ bkt_rescatter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
 __global__ void __launch_bounds__(CTA)
 bkt_null_kernel(int64_t R, int64_t Tb, const int64_t* __restrict__ off_big,
                 const int64_t* __restrict__ off_small, const int32_t* __restrict__ plen,
-                const unsigned long long* __restrict__ tile_cnt, int32_t* __restrict__ len,
+                const uint32_t* __restrict__ tile_cnt, int32_t* __restrict__ len,
                 uint8_t* __restrict__ is_null, int64_t* __restrict__ padded,
                 unsigned long long* __restrict__ stats /* [0] n_null, [1] total_len */) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
     unsigned long long my_null = 0, my_len = 0;
     if (r < R) {
         const int32_t L = plen[r];
-        unsigned long long hits = 0;
+        uint32_t hits = 0;          // only zero / non-zero matters
         if (L > SMALL_MAX) {
-            for (int64_t t = off_big[r]; t < off_big[r + 1]; t++) hits += tile_cnt[t];
+            for (int64_t t = off_big[r]; t < off_big[r + 1]; t++) hits |= tile_cnt[t];
         } else if (L > 0) {
             hits = tile_cnt[Tb + off_small[r]];
         }
@@ -450,14 +450,14 @@ bkt_null_kernel(int64_t R, int64_t Tb, const int64_t* __restrict__ off_big,
 // Everything a tile kernel needs, in one 32-byte record (one dependent load instead of five).
 struct __align__(16) TileDesc {
     int64_t out;         // offset of the tile's first output in the dense coverage
-    int64_t b0;          // first bucket entry
+    uint32_t b0;         // first bucket entry
     uint32_t n;          // bucket entries
     int32_t tlen;        // outputs; 0 = the region is NULL, nothing to write
-    int32_t pad[2];
+    int32_t pad[3];
 };
 
 __global__ void __launch_bounds__(CTA)
-bkt_desc_kernel(int64_t T, Tiles tiles, const int64_t* __restrict__ boff,
+bkt_desc_kernel(int64_t T, Tiles tiles, const uint32_t* __restrict__ boff,
                 const uint8_t* __restrict__ is_null, const int64_t* __restrict__ off,
                 TileDesc* __restrict__ desc) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
@@ -466,9 +466,9 @@ bkt_desc_kernel(int64_t T, Tiles tiles, const int64_t* __restrict__ boff,
     TileDesc d;
     d.out = off[b.x] + b.y;
     d.b0 = boff[t];
-    d.n = (uint32_t)(boff[t + 1] - boff[t]);
+    d.n = boff[t + 1] - boff[t];
     d.tlen = is_null[b.x] ? 0 : (int32_t)(tiles.a[t].y & 0xffffu);
-    d.pad[0] = d.pad[1] = 0;
+    d.pad[0] = d.pad[1] = d.pad[2] = 0;
     desc[t] = d;
 }
 
@@ -477,10 +477,10 @@ __device__ __forceinline__ TileDesc load_desc(const TileDesc* __restrict__ p) {
     const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
     TileDesc d;
     d.out = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
-    d.b0 = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
-    d.n = (uint32_t)b.x;
-    d.tlen = b.y;
-    d.pad[0] = d.pad[1] = 0;
+    d.b0 = (uint32_t)a.z;
+    d.n = (uint32_t)a.w;
+    d.tlen = b.x;
+    d.pad[0] = d.pad[1] = d.pad[2] = 0;
     return d;
 }
 
@@ -521,7 +521,8 @@ bkt_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, const uint32_t* _
     int64_t t = blockIdx.x;
     if (t >= Tb) return;
     TileDesc none;
-    none.out = none.b0 = 0;
+    none.out = 0;
+    none.b0 = 0;
     none.n = 0;
     none.tlen = 0;
     none.pad[0] = none.pad[1] = 0;
@@ -617,10 +618,10 @@ struct Work {
     Tiles tiles = {nullptr, nullptr};
     Cells cells = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int bm_words = 0;
-    unsigned long long* tile_cnt = nullptr;   // counts, then (pass 2) bucket cursors
+    uint32_t* tile_cnt = nullptr;             // counts, then (pass 2) bucket cursors
     uint2* hits = nullptr;
     unsigned long long* hit_n = nullptr;
-    int64_t* boff = nullptr;
+    uint32_t* boff = nullptr;
     uint32_t* bucket = nullptr;
     TileDesc* desc = nullptr;
     ~Work() {
@@ -771,7 +772,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         RCP_CUDA(cudaMemsetAsync(w.cells.rec, 0, (size_t)n_cell * sizeof(uint4), g_ctx.stream));
         RCP_CUDA(cudaMemsetAsync(w.cells.cnt, 0, ((size_t)n_cell + 1) * 4, g_ctx.stream));
         RCP_CUDA(cudaMemsetAsync(w.cells.bitmap, 0, (size_t)w.bm_words * 4, g_ctx.stream));
-        RCP_CUDA(cudaMemsetAsync(w.tile_cnt, 0, ((size_t)T + 1) * 8, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(w.tile_cnt, 0, ((size_t)T + 1) * 4, g_ctx.stream));
         if (T > 0) {
             bkt_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(
                 R, Tb, Ts, w.off_big, w.off_small, w.gs, w.plen, w.flags, w.tiles, w.cells.cnt,
@@ -807,11 +808,9 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
             RCP_LAUNCHED();
         }
         RCP_TRY(exclusive_scan_i64(w.padded, cv->off, R, cv->off + R));
-        RCP_TRY(exclusive_scan_i64(reinterpret_cast<const int64_t*>(w.tile_cnt), w.boff, T,
-                                   w.boff + T));
+        RCP_TRY(exclusive_scan_u32(w.tile_cnt, w.boff, T, w.boff + T));
     }
     RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.hits, w.boff + T, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h.listed, w.hit_n, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
@@ -820,13 +819,18 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     cv->total_len = (int64_t)h.stats[1];
     cv->max_len = (int32_t)h.stats[2];
     RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
+    // the find pass counted every hit exactly (64-bit); the per-tile counters and offsets are 32-bit
+    if (h.listed > 0xfffffff0ull)
+        return fail(RCP_ERR_UNSUPPORTED,
+                    "more than 2^32 (read, tile) overlaps: use RCP_PATH_INDEX for this mask");
+    h.hits = (int64_t)h.listed;
     if (h.hits == 0) return RCP_OK;                 // every region is NULL
     RCP_TRY(dalloc(&w.bucket, (size_t)h.hits));
     RCP_TRY(dalloc(&w.desc, (size_t)T));
     // ---- 5. pass 2: hits -> buckets (the counters become cursors starting at the offsets) -----
     {
         StageTimer t(ST_BKT_SCATTER);
-        RCP_CUDA(cudaMemcpyAsync(w.tile_cnt, w.boff, (size_t)T * 8, cudaMemcpyDeviceToDevice,
+        RCP_CUDA(cudaMemcpyAsync(w.tile_cnt, w.boff, (size_t)T * 4, cudaMemcpyDeviceToDevice,
                                  g_ctx.stream));
         if (h.listed <= hit_cap) {
             const int64_t blocks = ((int64_t)h.listed / 4 + CTA - 1) / CTA + 1;
