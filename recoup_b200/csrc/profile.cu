@@ -273,10 +273,8 @@ __device__ __forceinline__ BinDesc load_bin_desc(const BinDesc* __restrict__ p) 
 }
 
 // Persistent CTAs walk the regions.  Narrow bins (< 128 bases, the usual case: TSS windows,
-// flanks): the segment is staged in shared memory and turned IN PLACE into its inclusive prefix
-// sum S (lane-serial: each thread scans consecutive int4, one warp scan orders the threads); a
-// bin sum is then S[last] - S[first - 1], two shared-memory loads per bin.  S is kept modulo
-// 2^32, exact while max(coverage) * (bsz + 1) < 2^32 (checked; else 64-bit walks).  The staging
+// flanks): the segment is staged in shared memory and every bin is summed from there by a small
+// group of threads with 16-byte shared-memory loads and 64-bit sums.  The staging
 // copy of the NEXT region -- one TMA bulk copy (cp.async.bulk, up to 48 KB) issued by a single
 // thread into the second buffer, completion on an mbarrier -- and the descriptor of the region
 // after it are issued before the current region is processed, so HBM latency hides behind the
@@ -381,64 +379,35 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
                             reinterpret_cast<int4*>(stage)[i] = __ldg(gsrc + i);
                         __syncthreads();
                     }
-                    // pass 1: per-thread sum and max of K consecutive int4 (K odd: the 16-byte
-                    // shared-memory accesses of a warp then fall into distinct banks)
-                    const int K = ((nvec + BT - 1) / BT) | 1;
-                    const int v0 = min(tid * K, nvec), v1 = min(v0 + K, nvec);
-                    const uint4* sv = reinterpret_cast<const uint4*>(stage) + v0;
-                    const int kn = v1 - v0;
-                    uint32_t sum = 0;
-                    int vmax = 0;
-                    for (int i = 0; i < kn; i++) {
-                        const uint4 x = sv[i];
-                        sum += (x.x + x.y) + (x.z + x.w);
-                        vmax = max(max(vmax, (int)x.x), max(max((int)x.y, (int)x.z), (int)x.w));
-                    }
-                    uint32_t inc = sum;
-#pragma unroll
-                    for (int dd = 1; dd < 32; dd <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
-                        if (lane >= dd) inc += o;
-                    }
-                    vmax = __reduce_max_sync(0xffffffffu, vmax);
-                    if (lane == 31) wcount[warp] = (int)inc;
-                    if (lane == 0) wmaxs[warp] = vmax;
-                    __syncthreads();
-#pragma unroll
-                    for (int w = 0; w < BWARPS; w++) vmax = max(vmax, wmaxs[w]);
-                    if ((unsigned long long)vmax * (unsigned long long)(bsz + 1) < (1ull << 32)) {
-                        uint32_t run = inc - sum;
-#pragma unroll
-                        for (int w = 0; w < BWARPS - 1; w++)
-                            if (w < warp) run += (uint32_t)wcount[w];
-                        uint4* wv = reinterpret_cast<uint4*>(stage) + v0;
-                        for (int i = 0; i < kn; i++) {
-                            uint4 x = wv[i];
-                            x.x = (run += x.x);
-                            x.y = (run += x.y);
-                            x.z = (run += x.z);
-                            x.w = (run += x.w);
-                            wv[i] = x;
-                        }
-                        __syncthreads();
-                        for (int b = bin0 + tid; b < bin1; b += BT) {
-                            const int e0 = edge(b) - lo_al, e1 = edge(b + 1) - lo_al;
-                            const uint32_t sum_b = stage[e1 - 1] - (e0 > 0 ? stage[e0 - 1] : 0u);
-                            out[(int64_t)b * p.ld] = p.scale * ((double)sum_b / (double)(e1 - e0));
-                        }
-                    } else {
-                        const bool rotate = (bsz & 1) == 0;
-                        for (int b = bin0 + tid; b < bin1; b += BT) {
-                            const int e0 = edge(b), blen = edge(b + 1) - e0;
-                            const uint32_t* x = stage + (e0 - lo_al);
-                            int q = rotate ? (tid % blen) : 0;
-                            long long s64 = 0;
-                            for (int it = 0; it < blen; it++) {
-                                s64 += (long long)x[q];
-                                q = (q + 1 == blen) ? 0 : q + 1;
+                    // g threads per bin (a power of two that divides the warp): each walks its
+                    // share of the bin in the staged data -- scalar up to the first 16-byte
+                    // boundary, 16-byte loads after it, scalar tail -- with 64-bit sums; the g
+                    // parts meet by shuffles.  About 1.5 instructions per base.
+                    const int nb = bin1 - bin0;
+                    int g = 1;
+                    while (g < 32 && 2 * g * nb <= BT) g <<= 1;
+                    const int part = tid & (g - 1);
+                    for (int b0 = bin0; b0 < bin1; b0 += BT / g) {      // whole warps stay together
+                        const int b = b0 + tid / g;
+                        long long s64 = 0;
+                        int eb0 = 0, eb1 = 1;
+                        if (b < bin1) {
+                            eb0 = edge(b);
+                            eb1 = edge(b + 1);
+                            const int blen = eb1 - eb0;
+                            const int share = (blen + g - 1) / g;
+                            int q = eb0 - lo_al + part * share;
+                            const int qe = min(q + share, eb1 - lo_al);
+                            while (q < qe && (q & 3)) s64 += (long long)stage[q++];
+                            for (; q + 4 <= qe; q += 4) {
+                                const uint4 x = *reinterpret_cast<const uint4*>(stage + q);
+                                s64 += ((long long)x.x + x.y) + ((long long)x.z + x.w);
                             }
-                            out[(int64_t)b * p.ld] = p.scale * ((double)s64 / (double)blen);
+                            while (q < qe) s64 += (long long)stage[q++];
                         }
+                        for (int dd = g >> 1; dd > 0; dd >>= 1) s64 += __shfl_xor_sync(0xffffffffu, s64, dd);
+                        if (b < bin1 && part == 0)
+                            out[(int64_t)b * p.ld] = p.scale * ((double)s64 / (double)(eb1 - eb0));
                     }
                 }
             } else {
