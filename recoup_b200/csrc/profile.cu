@@ -10,6 +10,7 @@
 //   base_matrix_kernel   per-base matrix: int32 -> fp64 tiled transpose (profile.R:100-151)
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "r_rng.cuh"
 #include "rcp_internal.cuh"
@@ -233,7 +234,7 @@ struct __align__(16) BinDesc {
     int bsz, dif, lo_al, nvec;
 };
 
-constexpr int BT = 512;                // threads of bin_mean_kernel
+constexpr int BT = 256;                // threads of bin_mean_kernel
 constexpr int BWARPS = BT / 32;
 
 __global__ void __launch_bounds__(CTA)
@@ -281,23 +282,24 @@ __device__ __forceinline__ BinDesc load_bin_desc(const BinDesc* __restrict__ p) 
 // arithmetic and no thread spends instructions on the copy.
 // Wide bins: one warp per bin, 16-byte global loads.  Segments shorter than the bin count go
 // to the interpolation list (util.R:17).
+constexpr int NBUF_MAX = 8;
+
 __global__ void __launch_bounds__(BT)
-bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_ints) {
+bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_ints, int nbuf) {
     extern __shared__ __align__(16) int sh[];
     int* edges = sh;                                         // n + 1 (unequal bins only)
     uint32_t* bufs = reinterpret_cast<uint32_t*>(sh + ((p.n + 1 + 3) & ~3));
     __shared__ int wcount[BWARPS];
-    __shared__ int wmaxs[BWARPS];
     __shared__ int chunk_carry;
-    __shared__ __align__(8) uint64_t full_bar[2];            // one per staging buffer
+    __shared__ __align__(8) uint64_t full_bar[NBUF_MAX];     // one per staging buffer
+    __shared__ BinDesc ring[NBUF_MAX];                       // descriptor of the region in each buffer
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n;
     const int64_t step = gridDim.x;
     int64_t r = blockIdx.x;
     if (r >= R) return;
     if (tid == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+        for (int k = 0; k < nbuf; k++) mbar_init(&full_bar[k], 1);
         fence_proxy_async();                // make the initialised barriers visible to the TMA unit
     }
     __syncthreads();
@@ -308,9 +310,10 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
         return p.cov + (int64_t)(((uint64_t)(uint32_t)d.off_hi << 32) | (uint32_t)d.off_lo);
     };
     // thread 0 starts the copy of one region into buffer `which` (regions that are not one staged
-    // run just complete the barrier phase)
+    // run just complete the barrier phase) and publishes its descriptor beside it
     auto issue = [&](const BinDesc& d, int which) {
         if (tid != 0) return;
+        ring[which] = d;
         uint64_t* bar = &full_bar[which];
         if (d.nvec > 0) {
             const uint32_t bytes = (uint32_t)d.nvec * 16u;
@@ -322,17 +325,24 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
         }
     };
 
-    BinDesc d = load_bin_desc(desc + r);
-    BinDesc dn = (r + step < R) ? load_bin_desc(desc + r + step) : none;
-    int cur = 0;
-    uint32_t parity[2] = {0u, 0u};          // phase of each buffer's barrier
-    issue(d, 0);
-    for (;;) {
-        const BinDesc dnn = (r + 2 * step < R) ? load_bin_desc(desc + r + 2 * step) : none;
+    // The staging buffers form a ring of nbuf: the copies of the next nbuf - 1 regions are in
+    // flight while one region is processed (HBM latency is hidden by DEPTH: the per-region work
+    // is light), and the descriptor of the region after those is already in registers.
+    auto desc_at = [&](int64_t k) {         // descriptor of this CTA's k-th region
+        const int64_t rr = blockIdx.x + k * step;
+        return rr < R ? load_bin_desc(desc + rr) : none;
+    };
+    for (int k = 0; k < nbuf - 1; k++) issue(desc_at(k), k);
+    BinDesc dq = desc_at(nbuf - 1);         // next to be issued
+    uint32_t parity = 0;                    // bit k: phase of buffer k's barrier
+    for (int64_t it = 0;; it++) {
+        const int cur = (int)(it % nbuf);
+        issue(dq, (int)((it + nbuf - 1) % nbuf));
+        dq = desc_at(it + nbuf);
         uint32_t* stage = bufs + (size_t)cur * buf_ints;
-        issue(dn, cur ^ 1);
-        mbar_wait(&full_bar[cur], parity[cur]);     // this region's copy has landed
-        parity[cur] ^= 1u;
+        mbar_wait(&full_bar[cur], (parity >> cur) & 1u);    // this region's copy has landed
+        parity ^= 1u << cur;
+        const BinDesc d = ring[cur];
         double* out = p.out + r;
         const int Ls = d.b - d.a;
         if (Ls <= 0) {                      // NULL coverage -> zero row (profile.R:191-197)
@@ -421,10 +431,7 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
         }
         r += step;
         if (r >= R) break;
-        __syncthreads();                    // edges, wcount and the stage buffer are reused
-        d = dn;
-        dn = dnn;
-        cur ^= 1;
+        __syncthreads();                    // edges, wcount, the ring slot and the buffer are reused
     }
     // the copy issued for the (non-existent) region after the last one carries no bytes
 }
@@ -760,14 +767,20 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
             R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc);
         RCP_LAUNCHED();
-        const size_t smem = edge_bytes + 2 * (size_t)buf_ints * sizeof(int);
+        // CTAs per SM and buffers per CTA: as much shared memory as possible in flight
+        int per_sm = 4, nbuf = 2;
+        if (const char* e = getenv("RCP_BIN_CTAS")) per_sm = std::max(1, atoi(e));     // tuning
+        const size_t budget = 220u * 1024u / (size_t)per_sm - 1024u;
+        nbuf = (int)((budget - edge_bytes) / ((size_t)buf_ints * sizeof(int)));
+        nbuf = std::max(1, std::min(nbuf, NBUF_MAX));
+        const size_t smem = edge_bytes + (size_t)nbuf * buf_ints * sizeof(int);
         RCP_CUDA(cudaFuncSetAttribute(bin_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        int per_sm = 0;
-        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_mean_kernel, BT, smem));
-        if (per_sm < 1) return fail(RCP_ERR_UNSUPPORTED, "bin kernel does not fit (%zu bytes of shared memory)", smem);
-        const int64_t grid = std::min<int64_t>(R, (int64_t)g_ctx.sm_count * per_sm);
-        bin_mean_kernel<<<(unsigned)grid, BT, smem, g_ctx.stream>>>(a, d_desc, R, buf_ints);
+        int fit = 0;
+        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bin_mean_kernel, BT, smem));
+        if (fit < 1) return fail(RCP_ERR_UNSUPPORTED, "bin kernel does not fit (%zu bytes of shared memory)", smem);
+        const int64_t grid = std::min<int64_t>(R, (int64_t)g_ctx.sm_count * std::min(fit, per_sm));
+        bin_mean_kernel<<<(unsigned)grid, BT, smem, g_ctx.stream>>>(a, d_desc, R, buf_ints, nbuf);
         RCP_LAUNCHED();
     }
     InterpArgs ia;
