@@ -603,8 +603,32 @@ inline unsigned reads_grid(int64_t n, size_t smem) {
     return (unsigned)b;
 }
 
-// every device array of one call; freed on every exit path
+// Device scratch of one call.  Three arenas (one allocation each: the host is on the critical
+// path right after the two synchronisation points, and ~30 stream-ordered allocations plus as
+// many frees cost more than the small kernels between them): A sized by the regions, B by the
+// tiles / cells / reads, C by the hits.  Sub-buffers are 256-byte aligned.
+struct Arena {
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    int reserve(size_t bytes) {
+        cap = bytes;
+        used = 0;
+        return device_alloc(reinterpret_cast<void**>(&base), bytes > 0 ? bytes : 1);
+    }
+    template <class T>
+    T* take(size_t n) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += pad(n * sizeof(T));
+        return p;
+    }
+    ~Arena() {
+        if (base) device_free(base);
+    }
+};
+
 struct Work {
+    Arena A, B, C;
     uint32_t* gs = nullptr;
     int32_t* plen = nullptr;
     uint8_t* flags = nullptr;
@@ -624,32 +648,6 @@ struct Work {
     uint32_t* boff = nullptr;
     uint32_t* bucket = nullptr;
     TileDesc* desc = nullptr;
-    ~Work() {
-        dfree(hits);
-        dfree(hit_n);
-        dfree(desc);
-        dfree(gs);
-        dfree(plen);
-        dfree(flags);
-        dfree(nbig);
-        dfree(nsmall);
-        dfree(off_big);
-        dfree(off_small);
-        dfree(padded);
-        dfree(err);
-        dfree(stats);
-        dfree(tiles.a);
-        dfree(tiles.b);
-        dfree(cells.rec);
-        dfree(cells.ovf);
-        dfree(cells.cnt);
-        dfree(cells.ovf_n);
-        dfree(cells.ovf_ptr);
-        dfree(cells.bitmap);
-        dfree(tile_cnt);
-        dfree(boff);
-        dfree(bucket);
-    }
 };
 
 template <bool STRANDED>
@@ -706,18 +704,22 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     RCP_TRY(dalloc(&cv->len, (size_t)R));
     RCP_TRY(dalloc(&cv->is_null, (size_t)R));
     Work w;
-    RCP_TRY(dalloc(&w.gs, (size_t)R));
-    RCP_TRY(dalloc(&w.plen, (size_t)R));
-    RCP_TRY(dalloc(&w.flags, (size_t)R));
-    RCP_TRY(dalloc(&w.nbig, (size_t)R));
-    RCP_TRY(dalloc(&w.nsmall, (size_t)R));
-    RCP_TRY(dalloc(&w.off_big, (size_t)R + 1));
-    RCP_TRY(dalloc(&w.off_small, (size_t)R + 1));
-    RCP_TRY(dalloc(&w.padded, (size_t)R));
-    RCP_TRY(dalloc(&w.err, 1));
-    RCP_TRY(dalloc(&w.stats, 3));
-    RCP_CUDA(cudaMemsetAsync(w.err, 0, sizeof(unsigned int), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(w.stats, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
+    {
+        const size_t r = (size_t)R;
+        RCP_TRY(w.A.reserve(Arena::pad(r * 4) * 2 + Arena::pad(r) + Arena::pad(r * 8) * 3 +
+                            Arena::pad((r + 1) * 8) * 2 + Arena::pad(4) + Arena::pad(24)));
+        w.err = w.A.take<unsigned int>(1);            // err and stats first: one memset clears both
+        w.stats = w.A.take<unsigned long long>(3);
+        w.gs = w.A.take<uint32_t>(r);
+        w.plen = w.A.take<int32_t>(r);
+        w.flags = w.A.take<uint8_t>(r);
+        w.nbig = w.A.take<int64_t>(r);
+        w.nsmall = w.A.take<int64_t>(r);
+        w.padded = w.A.take<int64_t>(r);
+        w.off_big = w.A.take<int64_t>(r + 1);
+        w.off_small = w.A.take<int64_t>(r + 1);
+    }
+    RCP_CUDA(cudaMemsetAsync(w.err, 0, 512, g_ctx.stream));       // err (256 B slot) + stats
 
     struct Host {
         int64_t Tb, Ts, total_padded, hits;
@@ -757,22 +759,35 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     const int64_t n_cell = (span >> CELL_SHIFT) + 2;
     const int64_t pairs = Tb * CELLS_PER_BIG + Ts * CELLS_PER_SMALL;      // (tile, cell) bound
     w.bm_words = (int)(((span >> BM_SHIFT) + 32) / 32);
-    RCP_TRY(dalloc(&w.tiles.a, (size_t)T));
-    RCP_TRY(dalloc(&w.tiles.b, (size_t)T));
-    RCP_TRY(dalloc(&w.tile_cnt, (size_t)T + 1));
-    RCP_TRY(dalloc(&w.boff, (size_t)T + 1));
-    RCP_TRY(dalloc(&w.cells.rec, (size_t)n_cell));
-    RCP_TRY(dalloc(&w.cells.cnt, (size_t)n_cell + 1));
-    RCP_TRY(dalloc(&w.cells.ovf_n, (size_t)n_cell + 1));
-    RCP_TRY(dalloc(&w.cells.ovf_ptr, (size_t)n_cell + 1));
-    RCP_TRY(dalloc(&w.cells.ovf, (size_t)(pairs + pairs / 2 + 1)));
-    RCP_TRY(dalloc(&w.cells.bitmap, (size_t)w.bm_words));
+    // The hit list holds one entry per read by default: enough unless regions overlap heavily
+    // (then pass 2 walks the reads again instead).  RCP_BKT_HIT_CAP overrides it (tests).
+    unsigned long long hit_cap = (unsigned long long)std::max<int64_t>(rd.n, 4096);
+    if (const char* e = getenv("RCP_BKT_HIT_CAP")) hit_cap = strtoull(e, nullptr, 10);
+    size_t zero_bytes = 0;
+    {
+        const size_t t = (size_t)T, c = (size_t)n_cell, ovf_cap = (size_t)(pairs + pairs / 2 + 1);
+        RCP_TRY(w.B.reserve(Arena::pad(c * 16) + Arena::pad((c + 1) * 4) * 3 + Arena::pad((size_t)w.bm_words * 4) +
+                            Arena::pad((t + 1) * 4) * 2 + Arena::pad(16) + Arena::pad(t * 8) * 2 +
+                            Arena::pad(ovf_cap * 16) + Arena::pad((size_t)hit_cap * 8)));
+        // zero-initialised block first (ONE memset): cell records, cell counts, bitmap, tile counters,
+        // hit counter
+        w.cells.rec = w.B.take<uint4>(c);
+        w.cells.cnt = w.B.take<uint32_t>(c + 1);
+        w.cells.bitmap = w.B.take<uint32_t>((size_t)w.bm_words);
+        w.tile_cnt = w.B.take<uint32_t>(t + 1);
+        w.hit_n = w.B.take<unsigned long long>(2);
+        zero_bytes = w.B.used;
+        w.cells.ovf_n = w.B.take<uint32_t>(c + 1);
+        w.cells.ovf_ptr = w.B.take<uint32_t>(c + 1);
+        w.boff = w.B.take<uint32_t>(t + 1);
+        w.tiles.a = w.B.take<uint2>(t);
+        w.tiles.b = w.B.take<uint2>(t);
+        w.cells.ovf = w.B.take<uint4>(ovf_cap);
+        w.hits = w.B.take<uint2>((size_t)hit_cap);
+    }
     {
         StageTimer t(ST_BKT_PLAN);
-        RCP_CUDA(cudaMemsetAsync(w.cells.rec, 0, (size_t)n_cell * sizeof(uint4), g_ctx.stream));
-        RCP_CUDA(cudaMemsetAsync(w.cells.cnt, 0, ((size_t)n_cell + 1) * 4, g_ctx.stream));
-        RCP_CUDA(cudaMemsetAsync(w.cells.bitmap, 0, (size_t)w.bm_words * 4, g_ctx.stream));
-        RCP_CUDA(cudaMemsetAsync(w.tile_cnt, 0, ((size_t)T + 1) * 4, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(w.B.base, 0, zero_bytes, g_ctx.stream));
         if (T > 0) {
             bkt_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(
                 R, Tb, Ts, w.off_big, w.off_small, w.gs, w.plen, w.flags, w.tiles, w.cells.cnt,
@@ -787,13 +802,6 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         }
     }
     // ---- 3. pass 1: find the (read, tile) hits; count them per tile -------------------------
-    // The hit list holds one entry per read by default: enough unless regions overlap heavily
-    // (then pass 2 walks the reads again instead).  RCP_BKT_HIT_CAP overrides it (tests).
-    unsigned long long hit_cap = (unsigned long long)std::max<int64_t>(rd.n, 4096);
-    if (const char* e = getenv("RCP_BKT_HIT_CAP")) hit_cap = strtoull(e, nullptr, 10);
-    RCP_TRY(dalloc(&w.hits, (size_t)hit_cap));
-    RCP_TRY(dalloc(&w.hit_n, 1));
-    RCP_CUDA(cudaMemsetAsync(w.hit_n, 0, 8, g_ctx.stream));
     if (T > 0 && rd.n > 0) {
         StageTimer t(ST_BKT_COUNT);
         RCP_TRY(stranded ? launch_find<true>(rd, w, hit_cap) : launch_find<false>(rd, w, hit_cap));
@@ -825,8 +833,9 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
                     "more than 2^32 (read, tile) overlaps: use RCP_PATH_INDEX for this mask");
     h.hits = (int64_t)h.listed;
     if (h.hits == 0) return RCP_OK;                 // every region is NULL
-    RCP_TRY(dalloc(&w.bucket, (size_t)h.hits));
-    RCP_TRY(dalloc(&w.desc, (size_t)T));
+    RCP_TRY(w.C.reserve(Arena::pad((size_t)h.hits * 4) + Arena::pad((size_t)T * sizeof(TileDesc))));
+    w.bucket = w.C.take<uint32_t>((size_t)h.hits);
+    w.desc = w.C.take<TileDesc>((size_t)T);
     // ---- 5. pass 2: hits -> buckets (the counters become cursors starting at the offsets) -----
     {
         StageTimer t(ST_BKT_SCATTER);
