@@ -718,6 +718,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         w.padded = w.A.take<int64_t>(r);
         w.off_big = w.A.take<int64_t>(r + 1);
         w.off_small = w.A.take<int64_t>(r + 1);
+        if (w.A.used > w.A.cap) return fail(RCP_ERR_CUDA, "internal: region arena overrun");
     }
     RCP_CUDA(cudaMemsetAsync(w.err, 0, 512, g_ctx.stream));       // err (256 B slot) + stats
 
@@ -784,6 +785,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         w.tiles.b = w.B.take<uint2>(t);
         w.cells.ovf = w.B.take<uint4>(ovf_cap);
         w.hits = w.B.take<uint2>((size_t)hit_cap);
+        if (w.B.used > w.B.cap) return fail(RCP_ERR_CUDA, "internal: tile arena overrun");
     }
     {
         StageTimer t(ST_BKT_PLAN);
