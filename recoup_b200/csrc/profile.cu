@@ -257,7 +257,7 @@ bin_desc_kernel(int64_t R, const int64_t* __restrict__ off, const int32_t* __res
     d.dif = Ls >= n ? Ls - d.bsz * n : 0;
     d.lo_al = sg.a & ~3;
     d.nvec = 0;
-    if (d.bsz > 0 && d.bsz < STAGE_MAX_BIN && n <= (STAGE_INTS - 4) / (d.bsz + 1)) {
+    if (d.bsz > 0 && d.bsz < STAGE_MAX_BIN) {
         const int nvec = (sg.b - d.lo_al + 3) >> 2;
         if (nvec * 4 <= buf_ints) d.nvec = nvec;
     }
@@ -377,7 +377,7 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
             const int32_t* src = src_of(d);
             if (bsz < STAGE_MAX_BIN) {
                 const bool preloaded = d.nvec > 0;
-                const int bins_per_chunk = preloaded ? n : (STAGE_INTS - 4) / (bsz + 1);
+                const int bins_per_chunk = preloaded ? n : max(1, (buf_ints - 4) / (bsz + 1));
                 for (int bin0 = 0; bin0 < n; bin0 += bins_per_chunk) {
                     const int bin1 = min(n, bin0 + bins_per_chunk);
                     const int lo_al = preloaded ? d.lo_al : (edge(bin0) & ~3);
@@ -763,12 +763,28 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         if (where == RCP_WHERE_UPSTREAM) seg_max = std::min<int64_t>(seg_max, f1);
         else if (where == RCP_WHERE_DOWNSTREAM) seg_max = std::min<int64_t>(seg_max, f2);
         else if (where == RCP_WHERE_CENTER) seg_max = std::max<int64_t>(seg_max - f1 - f2, 0);
-        const int buf_ints = (int)std::min<int64_t>(STAGE_INTS, ((seg_max + 10) & ~(int64_t)3));
+        int buf_ints = (int)std::min<int64_t>(STAGE_INTS, ((seg_max + 10) & ~(int64_t)3));
+        // CTAs per SM: four, unless the typical bin is wide (mean segment / bins >= 128 bases:
+        // gene bodies).  Wide bins are summed straight from global memory by one warp each and
+        // are bound by the loads in flight, so they want all 64 warps of the SM; the staging
+        // buffers (used by the shorter regions only) shrink to make room.
+        int per_sm = 4;
+        {
+            const int64_t live = std::max<int64_t>(R - cv.n_null, 1);
+            int64_t seg_mean = cv.total_len / live;
+            if (where == RCP_WHERE_UPSTREAM) seg_mean = std::min<int64_t>(seg_mean, f1);
+            else if (where == RCP_WHERE_DOWNSTREAM) seg_mean = std::min<int64_t>(seg_mean, f2);
+            else if (where == RCP_WHERE_CENTER) seg_mean = std::max<int64_t>(seg_mean - f1 - f2, 0);
+            if (seg_mean / n_bins >= 128) {
+                per_sm = 8;
+                buf_ints = std::min(buf_ints, 6144);
+            }
+        }
         bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
             R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc);
         RCP_LAUNCHED();
         // CTAs per SM and buffers per CTA: as much shared memory as possible in flight
-        int per_sm = 4, nbuf = 2;
+        int nbuf = 2;
         if (const char* e = getenv("RCP_BIN_CTAS")) per_sm = std::max(1, atoi(e));     // tuning
         const size_t budget = 220u * 1024u / (size_t)per_sm - 1024u;
         nbuf = (int)((budget - edge_bytes) / ((size_t)buf_ints * sizeof(int)));
