@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="N > 1: ranks store their rows straight into rank 0's matrix over NVLink "
                          "(p2p) or the row blocks are gathered with NCCL and placed by a kernel (nccl)")
-    ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets"],
+    ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets", "blocks"],
                     help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
 

@@ -105,6 +105,7 @@ const char* rcp_timing_stage_name(int stage);
 #define RCP_PATH_AUTO 0
 #define RCP_PATH_INDEX 1
 #define RCP_PATH_BUCKETS 2
+#define RCP_PATH_BLOCKS 3      /* experimental: filter + two multisplit passes by 64-kb block */
 int rcp_set_coverage_path(int path);
 
 /* ---------------------------------------------------------------- base-R RNG -------------- */

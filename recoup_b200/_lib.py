@@ -17,7 +17,7 @@ WHERE = {"whole": 0, "center": 1, "upstream": 2, "downstream": 3}
 STAT = {"mean": 0, "median": 1}
 INTERP = {"auto": 0, "spline": 1, "linear": 2, "neighborhood": 3}
 SAMPLE_KIND = {"Rejection": 0, "Rounding": 1}
-COVERAGE_PATH = {"auto": 0, "index": 1, "buckets": 2}
+COVERAGE_PATH = {"auto": 0, "index": 1, "buckets": 2, "blocks": 3}
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)

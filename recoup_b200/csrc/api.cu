@@ -188,6 +188,9 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
                   const int32_t* chrom, const int32_t* start, const int32_t* end,
                   const int8_t* strand, int ignore_strand, int strand_filter, int mem,
                   Coverage* cv);
+int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, int ignore_strand,
+                           int strand_filter, int mem, Coverage* cv);
 int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv);
 int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
                    int64_t capacity);
@@ -459,7 +462,8 @@ const char* rcp_timing_stage_name(int stage) {
 }
 
 int rcp_set_coverage_path(int path) {
-    if (path != RCP_PATH_AUTO && path != RCP_PATH_INDEX && path != RCP_PATH_BUCKETS)
+    if (path != RCP_PATH_AUTO && path != RCP_PATH_INDEX && path != RCP_PATH_BUCKETS &&
+        path != RCP_PATH_BLOCKS)
         return fail(RCP_ERR_ARG, "unknown coverage path %d", path);
     g_ctx.coverage_path = path;
     return RCP_OK;
@@ -558,7 +562,10 @@ int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32
                                   r->cls[CLS_STAR].built);
     }
     int rc = RCP_SWITCH_TO_INDEX;
-    if (!use_index) {
+    if (g_ctx.coverage_path == RCP_PATH_BLOCKS) {
+        rc = coverage_ranges_blocks(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                    strand_filter, mem, cv);
+    } else if (!use_index) {
         rc = coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
                                       strand_filter, mem, g_ctx.coverage_path == RCP_PATH_AUTO, cv);
         if (rc == RCP_SWITCH_TO_INDEX) coverage_release(*cv);      // dense mask, very many reads

@@ -603,6 +603,398 @@ inline unsigned reads_grid(int64_t n, size_t smem) {
     return (unsigned)b;
 }
 
+// ================================================================================================
+// BLOCKS mode: the same coverage without the cell table, the hit list and the place pass.
+//   filter     reads that pass the block bitmap, compacted per 4096-read chunk (no atomics)
+//   partition  the survivors are grouped by 64-kb genome block (start >> 16) with two 8-bit
+//              multisplit passes: per-chunk histograms in shared memory, one prefix sum over
+//              (digit, chunk), then a scatter whose ranks come from shared-memory counters --
+//              no global atomic per element, every pass is a streaming pass
+//   tiles      a tile scans the candidates of the 1-2 blocks under it (those that can reach it:
+//              start >= tile start - widest read) and clips them itself
+// The NULL rule ("no read in any tile") is a warp-per-tile any-hit scan of the same candidates.
+// ================================================================================================
+constexpr int BLK_SHIFT = 16;
+constexpr int PCH = 4096;            // elements per partition chunk (one CTA)
+constexpr int PT = 256;              // threads of the partition kernels (= digits of a pass)
+
+struct Cands {
+    uint32_t* s;
+    uint32_t* e;         // end + 1
+    int8_t* st;          // strand (stranded calls only)
+};
+
+template <bool STRANDED>
+__global__ void __launch_bounds__(RTPB)
+blk_filter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
+                  const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
+                  const uint32_t* __restrict__ bitmap, int bm_words, Cands out,
+                  uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int i = threadIdx.x; i < bm_words; i += RTPB) bm[i] = bitmap[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t n_vec = n >> 2;
+    constexpr int SUBV = PCH / 4;
+    const int64_t n_sub = (n_vec + SUBV - 1) / SUBV;          // + one chunk for the n % 4 tail
+    const int64_t warps_total = (int64_t)gridDim.x * (RTPB / 32);
+    for (int64_t sc = (int64_t)blockIdx.x * (RTPB / 32) + (threadIdx.x >> 5); sc <= n_sub;
+         sc += warps_total) {
+        const int64_t o0 = sc * PCH;
+        uint32_t kept = 0;
+        auto keep = [&](uint32_t s, uint32_t e1, int st) {
+            bool ok = e1 > s;
+            if (ok) {
+                const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
+                uint32_t w = bm[b0 >> 5] >> (b0 & 31u);
+                if (b1 != b0) w |= bm[b1 >> 5] >> (b1 & 31u);
+                ok = (b1 > b0 + 1u) || (w & 1u);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int64_t o = o0 + kept + __popc(m & lt);
+                out.s[o] = s;
+                out.e[o] = e1;
+                if (STRANDED) out.st[o] = (int8_t)st;
+            }
+            kept += __popc(m);
+        };
+        if (sc < n_sub) {
+            const int64_t v_end = min(n_vec, (sc + 1) * SUBV);
+            for (int64_t v0 = sc * SUBV; v0 < v_end; v0 += 32) {
+                const int64_t v = v0 + lane;
+                uint4 s4 = make_uint4(0, 0, 0, 0), e4 = make_uint4(0, 0, 0, 0);
+                char4 t4 = make_char4(0, 0, 0, 0);
+                if (v < v_end) {
+                    s4 = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
+                    e4 = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
+                    if (STRANDED && strand) t4 = __ldcs(reinterpret_cast<const char4*>(strand) + v);
+                }
+                keep(s4.x, e4.x, t4.x);
+                keep(s4.y, e4.y, t4.y);
+                keep(s4.z, e4.z, t4.z);
+                keep(s4.w, e4.w, t4.w);
+            }
+        } else {
+            const int64_t i = n_vec * 4 + lane;
+            const bool ok = i < n;
+            keep(ok ? g_start[i] : 0u, ok ? g_end1[i] : 0u, (ok && STRANDED && strand) ? (int)strand[i] : 0);
+        }
+        if (lane == 0) counts[sc] = kept;
+    }
+}
+
+// pass 1, histogram: one CTA per filter chunk, digit = top 8 bits of the coordinate;
+// hist is digit-major: hist[digit * n_chunks + chunk]
+__global__ void __launch_bounds__(PT)
+blk_hist1_kernel(int64_t n_chunks, const uint32_t* __restrict__ keys,
+                 const uint32_t* __restrict__ counts, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[256];
+    const int64_t c = blockIdx.x;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t cnt = counts[c];
+    const uint32_t* k = keys + c * PCH;
+    for (uint32_t i = threadIdx.x; i < cnt; i += PT) atomicAdd(&h[__ldg(k + i) >> 24], 1u);
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * n_chunks + c] = h[threadIdx.x];
+}
+
+// pass 1, scatter: ranks from shared-memory cursors that start at the scanned offsets
+template <bool STRANDED>
+__global__ void __launch_bounds__(PT)
+blk_scatter1_kernel(int64_t n_chunks, Cands in, const uint32_t* __restrict__ counts,
+                    const uint32_t* __restrict__ pos, Cands out) {
+    __shared__ uint32_t cur[256];
+    const int64_t c = blockIdx.x;
+    cur[threadIdx.x] = pos[(int64_t)threadIdx.x * n_chunks + c];
+    __syncthreads();
+    const uint32_t cnt = counts[c];
+    const int64_t base = c * PCH;
+    for (uint32_t i = threadIdx.x; i < cnt; i += PT) {
+        const uint32_t s = __ldcs(in.s + base + i), e = __ldcs(in.e + base + i);
+        const uint32_t p = atomicAdd(&cur[s >> 24], 1u);
+        out.s[p] = s;
+        out.e[p] = e;
+        if (STRANDED) out.st[p] = __ldcs(in.st + base + i);
+    }
+}
+
+// After pass 1: start of each top-digit run (S1[257]) and the prefix of the chunk counts of
+// pass 2 (CP[257]): run d is cut into ceil(size / PCH) chunks.  One CTA of 256 threads.
+__global__ void __launch_bounds__(PT)
+blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hist1, [256*n_chunks] + total */,
+                uint32_t* __restrict__ S1, uint32_t* __restrict__ CP) {
+    __shared__ uint32_t w[PT / 32];
+    const int d = threadIdx.x;
+    const uint32_t total = pos[256 * n_chunks];
+    const uint32_t s = pos[(int64_t)d * n_chunks];
+    const uint32_t e = d == 255 ? total : pos[(int64_t)(d + 1) * n_chunks];
+    S1[d] = s;
+    if (d == 255) S1[256] = total;
+    const uint32_t nch = (e - s + PCH - 1) / PCH;
+    uint32_t inc = nch;
+    const unsigned lane = d & 31;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (lane >= (unsigned)dd) inc += o;
+    }
+    if (lane == 31) w[d >> 5] = inc;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int k = 0; k < (d >> 5); k++) pre += w[k];
+    CP[d] = pre + inc - nch;
+    if (d == 255) CP[256] = pre + inc;
+}
+
+// which (run, chunk) a pass-2 CTA owns; false past the last chunk
+__device__ __forceinline__ bool blk_chunk_of(uint32_t g, const uint32_t* __restrict__ CP,
+                                             const uint32_t* __restrict__ S1, int* d_out,
+                                             uint32_t* lo, uint32_t* hi, uint32_t* nch, uint32_t* j) {
+    if (g >= CP[256]) return false;
+    int a = 0, b = 256;                 // largest d with CP[d] <= g
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (CP[mid] <= g) a = mid;
+        else b = mid;
+    }
+    *d_out = a;
+    *nch = CP[a + 1] - CP[a];
+    *j = g - CP[a];
+    *lo = S1[a] + *j * PCH;
+    *hi = min(*lo + (uint32_t)PCH, S1[a + 1]);
+    return true;
+}
+
+// pass 2, histogram: digit = bits 16..23; hist2[CP[d] * 256 + digit * nch_d + j]
+__global__ void __launch_bounds__(PT)
+blk_hist2_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ CP,
+                 const uint32_t* __restrict__ S1, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[256];
+    int d;
+    uint32_t lo, hi, nch, j;
+    if (!blk_chunk_of(blockIdx.x, CP, S1, &d, &lo, &hi, &nch, &j)) return;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += PT) atomicAdd(&h[(__ldg(keys + i) >> 16) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)CP[d] * 256 + (size_t)threadIdx.x * nch + j] = h[threadIdx.x];
+}
+
+template <bool STRANDED>
+__global__ void __launch_bounds__(PT)
+blk_scatter2_kernel(Cands in, const uint32_t* __restrict__ CP, const uint32_t* __restrict__ S1,
+                    const uint32_t* __restrict__ pos, Cands out) {
+    __shared__ uint32_t cur[256];
+    int d;
+    uint32_t lo, hi, nch, j;
+    if (!blk_chunk_of(blockIdx.x, CP, S1, &d, &lo, &hi, &nch, &j)) return;
+    cur[threadIdx.x] = pos[(size_t)CP[d] * 256 + (size_t)threadIdx.x * nch + j];
+    __syncthreads();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += PT) {
+        const uint32_t s = __ldcs(in.s + i), e = __ldcs(in.e + i);
+        const uint32_t p = atomicAdd(&cur[(s >> 16) & 255u], 1u);
+        out.s[p] = s;
+        out.e[p] = e;
+        if (STRANDED) out.st[p] = __ldcs(in.st + i);
+    }
+}
+
+// first candidate of every 64-kb block (65537 entries) from the scanned pass-2 histogram
+__global__ void __launch_bounds__(PT)
+blk_offsets_kernel(const uint32_t* __restrict__ CP, const uint32_t* __restrict__ S1,
+                   const uint32_t* __restrict__ pos2, uint32_t* __restrict__ boff) {
+    const uint32_t b = blockIdx.x * PT + threadIdx.x;
+    if (b > 65536u) return;
+    if (b == 65536u) {
+        boff[b] = S1[256];
+        return;
+    }
+    const uint32_t d = b >> 8, low = b & 255u;
+    const uint32_t nch = CP[d + 1] - CP[d];
+    boff[b] = nch ? pos2[(size_t)CP[d] * 256 + (size_t)low * nch] : S1[d];
+}
+
+// candidates that can reach the tile [ts, ts + tl): those of the blocks from (ts - widest + 1)
+// to the tile's last base
+__device__ __forceinline__ void blk_range(uint32_t ts, uint32_t tl, uint32_t max_w,
+                                          const uint32_t* __restrict__ boff, uint32_t* c0,
+                                          uint32_t* c1) {
+    const uint32_t first = ts >= max_w ? ts - max_w + 1u : 0u;
+    *c0 = __ldg(boff + (first >> BLK_SHIFT));
+    *c1 = __ldg(boff + ((ts + tl - 1u) >> BLK_SHIFT) + 1u);
+}
+
+__device__ __forceinline__ bool blk_hit(uint32_t s, uint32_t e1, int st, uint32_t ts, uint32_t tl,
+                                        uint32_t flags, bool stranded, uint32_t* packed) {
+    if (!(s < ts + tl && e1 > ts)) return false;
+    if (stranded) {
+        const unsigned bit = st > 0 ? 0u : (st < 0 ? 1u : 2u);
+        if (!((flags >> (1 + bit)) & 1u)) return false;       // flags: bit0 reverse, bits1..3 classes
+    }
+    uint32_t lo = max(s, ts) - ts, hi = min(e1, ts + tl) - ts;
+    if (flags & 1u) {
+        const uint32_t l2 = tl - hi;
+        hi = tl - lo;
+        lo = l2;
+    }
+    *packed = lo | (hi << 16);
+    return true;
+}
+
+// NULL rule: does any candidate overlap the tile?  One warp per tile, early exit.
+__global__ void __launch_bounds__(CTA)
+blk_any_kernel(int64_t T, Tiles tiles, Cands c, const uint32_t* __restrict__ boff, uint32_t max_w,
+               int stranded, uint32_t* __restrict__ tile_any) {
+    const int64_t t = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint2 a = tiles.a[t];
+    const uint32_t ts = a.x, tl = a.y & 0xffffu, flags = a.y >> 16;
+    uint32_t c0, c1, packed;
+    blk_range(ts, tl, max_w, boff, &c0, &c1);
+    bool any = false;
+    for (uint32_t i0 = c0; i0 < c1 && !any; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool hit = false;
+        if (i < c1) hit = blk_hit(__ldg(c.s + i), __ldg(c.e + i), stranded ? (int)__ldg(c.st + i) : 0, ts, tl,
+                                  flags, stranded != 0, &packed);
+        any = __any_sync(0xffffffffu, hit);
+    }
+    if (lane == 0) tile_any[t] = any ? 1u : 0u;
+}
+
+// descriptors of blocks mode: b0 / n = the candidate range, pad[0] = tile start, pad[1] = flags
+__global__ void __launch_bounds__(CTA)
+blk_desc_kernel(int64_t T, Tiles tiles, const uint32_t* __restrict__ boff, uint32_t max_w,
+                const uint8_t* __restrict__ is_null, const int64_t* __restrict__ off,
+                TileDesc* __restrict__ desc) {
+    const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (t >= T) return;
+    const uint2 a = tiles.a[t], b = tiles.b[t];
+    const uint32_t tl = a.y & 0xffffu;
+    uint32_t c0, c1;
+    blk_range(a.x, tl, max_w, boff, &c0, &c1);
+    TileDesc d;
+    d.out = off[b.x] + b.y;
+    d.b0 = c0;
+    d.n = c1 - c0;
+    d.tlen = is_null[b.x] ? 0 : (int32_t)tl;
+    d.pad[0] = (int32_t)a.x;
+    d.pad[1] = (int32_t)(a.y >> 16);
+    d.pad[2] = 0;
+    desc[t] = d;
+}
+
+__device__ __forceinline__ TileDesc load_desc_full(const TileDesc* __restrict__ p) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    TileDesc d;
+    d.out = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
+    d.b0 = (uint32_t)a.z;
+    d.n = (uint32_t)a.w;
+    d.tlen = b.x;
+    d.pad[0] = b.y;
+    d.pad[1] = b.z;
+    d.pad[2] = b.w;
+    return d;
+}
+
+template <int RPW>
+__device__ __forceinline__ void blk_tile_body(int* diff, int* wtot, const TileDesc& d, Cands c,
+                                              bool stranded, int32_t* __restrict__ dst) {
+    const int tid = threadIdx.x;
+    const int tlen = d.tlen;
+#pragma unroll
+    for (int k = 0; k < RPW; k++)
+        reinterpret_cast<int4*>(diff)[k * CTA + tid] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t ts = (uint32_t)d.pad[0], flags = (uint32_t)d.pad[1];
+    for (uint32_t i = tid; i < d.n; i += CTA) {
+        const uint32_t s = __ldg(c.s + d.b0 + i), e1 = __ldg(c.e + d.b0 + i);
+        uint32_t packed;
+        if (blk_hit(s, e1, stranded ? (int)__ldg(c.st + d.b0 + i) : 0, ts, (uint32_t)tlen, flags, stranded,
+                    &packed)) {
+            const int lo = (int)(packed & 0xffffu), hi = (int)(packed >> 16);
+            atomicAdd(diff + lo, 1);
+            if (hi < tlen) atomicSub(diff + hi, 1);
+        }
+    }
+    __syncthreads();
+    block_scan_store_fwd<RPW, true>(diff, tlen, wtot, dst);
+}
+
+__global__ void __launch_bounds__(CTA, 5)
+blk_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, Cands c, int stranded,
+                int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int diff[TILE];
+    __shared__ int wtot[WARPS];
+    const uint32_t tid = threadIdx.x;
+    const int64_t step = gridDim.x;
+    int64_t t = blockIdx.x;
+    if (t >= Tb) return;
+    TileDesc d = load_desc_full(desc + t);
+    for (;;) {
+        TileDesc dn;
+        dn.tlen = 0;
+        if (t + step < Tb) dn = load_desc_full(desc + t + step);
+        if (d.tlen > 0) {
+            const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
+            int32_t* dst = cov + d.out;
+            switch (rpw) {
+                case 1: blk_tile_body<1>(diff, wtot, d, c, stranded != 0, dst); break;
+                case 2: blk_tile_body<2>(diff, wtot, d, c, stranded != 0, dst); break;
+                case 3: blk_tile_body<3>(diff, wtot, d, c, stranded != 0, dst); break;
+                case 4: blk_tile_body<4>(diff, wtot, d, c, stranded != 0, dst); break;
+                case 5: blk_tile_body<5>(diff, wtot, d, c, stranded != 0, dst); break;
+                case 6: blk_tile_body<6>(diff, wtot, d, c, stranded != 0, dst); break;
+                default: blk_tile_body<7>(diff, wtot, d, c, stranded != 0, dst); break;
+            }
+        }
+        t += step;
+        if ((tid & 31u) == 0) tma_store_wait_read();
+        if (t >= Tb) break;
+        __syncthreads();
+        d = dn;
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+blk_small_kernel(int64_t Ts, const TileDesc* __restrict__ desc, Cands c, int stranded,
+                 int32_t* __restrict__ cov) {
+    __shared__ __align__(16) int sm[WARPS][SMALL_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ts_i = (int64_t)blockIdx.x * WARPS + warp;
+    if (ts_i >= Ts) return;
+    const TileDesc d = load_desc_full(desc + ts_i);
+    const int L = d.tlen;
+    if (L == 0) return;
+    int* diff = sm[warp];
+    const int nrows = (L + ROW - 1) / ROW;
+    for (int i = lane; i < nrows * (ROW / 4); i += 32)
+        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t ts = (uint32_t)d.pad[0], flags = (uint32_t)d.pad[1];
+    for (uint32_t i = lane; i < d.n; i += 32) {
+        const uint32_t s = __ldg(c.s + d.b0 + i), e1 = __ldg(c.e + d.b0 + i);
+        uint32_t packed;
+        if (blk_hit(s, e1, stranded ? (int)__ldg(c.st + d.b0 + i) : 0, ts, (uint32_t)L, flags, stranded != 0,
+                    &packed)) {
+            const int lo = (int)(packed & 0xffffu), hi = (int)(packed >> 16);
+            atomicAdd(diff + lo, 1);
+            if (hi < L) atomicSub(diff + hi, 1);
+        }
+    }
+    __syncwarp();
+    int32_t* dst = cov + d.out;
+    int pre = 0;
+    for (int row = 0; row < nrows; row++)
+        pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, L - row * ROW, dst + row * ROW);
+}
+
 // Device scratch of one call.  Three arenas (one allocation each: the host is on the critical
 // path right after the two synchronisation points, and ~30 stream-ordered allocations plus as
 // many frees cost more than the small kernels between them): A sized by the regions, B by the
@@ -869,6 +1261,199 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         StageTimer t(ST_BKT_SMALL);
         bkt_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, w.desc + Tb, w.bucket,
                                                                          cv->cov);
+        RCP_LAUNCHED();
+    }
+    return RCP_OK;
+}
+
+// BLOCKS mode (see the kernels above): same contract as coverage_ranges_bucketed.
+int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, int ignore_strand,
+                           int strand_filter, int mem, Coverage* cv) {
+    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_chrom.init(chrom, (size_t)R, mem));
+    RCP_TRY(d_start.init(start, (size_t)R, mem));
+    RCP_TRY(d_end.init(end, (size_t)R, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)R, mem));
+    const bool stranded = !((strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr));
+    const bool st_arr = stranded && rd.d_strand != nullptr;      // strandless reads are all '*'
+    if (rd.n >= 0xfffff000ll) return fail(RCP_ERR_UNSUPPORTED, "blocks mode: more than 2^32 reads");
+
+    cv->n_regions = R;
+    RCP_TRY(dalloc(&cv->off, (size_t)R + 1));
+    RCP_TRY(dalloc(&cv->len, (size_t)R));
+    RCP_TRY(dalloc(&cv->is_null, (size_t)R));
+    Work w;
+    {
+        const size_t r = (size_t)R;
+        RCP_TRY(w.A.reserve(Arena::pad(r * 4) * 2 + Arena::pad(r) + Arena::pad(r * 8) * 3 +
+                            Arena::pad((r + 1) * 8) * 2 + Arena::pad(4) + Arena::pad(24)));
+        w.err = w.A.take<unsigned int>(1);
+        w.stats = w.A.take<unsigned long long>(3);
+        w.gs = w.A.take<uint32_t>(r);
+        w.plen = w.A.take<int32_t>(r);
+        w.flags = w.A.take<uint8_t>(r);
+        w.nbig = w.A.take<int64_t>(r);
+        w.nsmall = w.A.take<int64_t>(r);
+        w.padded = w.A.take<int64_t>(r);
+        w.off_big = w.A.take<int64_t>(r + 1);
+        w.off_small = w.A.take<int64_t>(r + 1);
+        if (w.A.used > w.A.cap) return fail(RCP_ERR_CUDA, "internal: region arena overrun");
+    }
+    RCP_CUDA(cudaMemsetAsync(w.err, 0, 512, g_ctx.stream));
+    struct Host {
+        int64_t Tb, Ts, total_padded;
+        unsigned long long stats[3];
+        unsigned int err;
+    } h = {0, 0, 0, {0, 0, 0}, 0};
+    {
+        StageTimer t(ST_BKT_PLAN);
+        if (R > 0) {
+            bkt_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
+                R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, rd.d_chrom_off,
+                rd.d_chrom_len, rd.n_chrom, ignore_strand, strand_filter, w.gs, w.plen, w.flags,
+                w.nbig, w.nsmall, w.err);
+            RCP_LAUNCHED();
+        }
+        RCP_TRY(exclusive_scan2_i64(w.nbig, w.off_big, w.off_big + R, w.nsmall, w.off_small,
+                                    w.off_small + R, R));
+    }
+    RCP_CUDA(cudaMemcpyAsync(&h.Tb, w.off_big + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.Ts, w.off_small + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(&h.err, w.err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (h.err & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
+    if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
+    const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
+    if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
+
+    // ---- tiles + block bitmap; filter; two multisplit passes ---------------------------------
+    const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
+    const int64_t n_cell = (span >> CELL_SHIFT) + 2;
+    w.bm_words = (int)(((span >> BM_SHIFT) + 32) / 32);
+    const int64_t n_chunks = ((rd.n >> 2) + PCH / 4 - 1) / (PCH / 4) + 1;      // filter chunks
+    const int64_t tc_upper = (rd.n + PCH - 1) / PCH + 256;                     // pass-2 chunks
+    Cands ca, cb;
+    uint32_t *counts, *hist1, *hist2, *S1, *CP, *blk_off;
+    size_t zero_bytes = 0;
+    {
+        const size_t t = (size_t)T, c = (size_t)n_cell, nc = (size_t)n_chunks, cap = nc * PCH;
+        const size_t st_bytes = st_arr ? Arena::pad(cap) : 0;
+        RCP_TRY(w.B.reserve(Arena::pad((c + 1) * 4) + Arena::pad((size_t)w.bm_words * 4) +
+                            Arena::pad((t + 1) * 4) + Arena::pad(256 * (size_t)tc_upper * 4 + 4) +
+                            Arena::pad(t * 8) * 2 + Arena::pad(cap * 4) * 4 + st_bytes * 2 +
+                            Arena::pad(nc * 4) + Arena::pad((256 * nc + 1) * 4) + Arena::pad(257 * 4) * 2 +
+                            Arena::pad(65537 * 4)));
+        // zero-initialised block first: cell counts (unused here, but bkt_tiles_kernel bumps them),
+        // bitmap, tile flags, pass-2 histogram
+        w.cells.cnt = w.B.take<uint32_t>(c + 1);
+        w.cells.bitmap = w.B.take<uint32_t>((size_t)w.bm_words);
+        w.tile_cnt = w.B.take<uint32_t>(t + 1);
+        hist2 = w.B.take<uint32_t>(256 * (size_t)tc_upper + 1);
+        zero_bytes = w.B.used;
+        w.tiles.a = w.B.take<uint2>(t);
+        w.tiles.b = w.B.take<uint2>(t);
+        ca.s = w.B.take<uint32_t>(cap);
+        ca.e = w.B.take<uint32_t>(cap);
+        cb.s = w.B.take<uint32_t>(cap);
+        cb.e = w.B.take<uint32_t>(cap);
+        ca.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
+        cb.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
+        counts = w.B.take<uint32_t>(nc);
+        hist1 = w.B.take<uint32_t>(256 * nc + 1);
+        S1 = w.B.take<uint32_t>(257);
+        CP = w.B.take<uint32_t>(257);
+        blk_off = w.B.take<uint32_t>(65537);
+        if (w.B.used > w.B.cap) return fail(RCP_ERR_CUDA, "internal: blocks arena overrun");
+    }
+    {
+        StageTimer t(ST_BKT_PLAN);
+        RCP_CUDA(cudaMemsetAsync(w.B.base, 0, zero_bytes, g_ctx.stream));
+        if (T > 0) {
+            bkt_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(
+                R, Tb, Ts, w.off_big, w.off_small, w.gs, w.plen, w.flags, w.tiles, w.cells.cnt,
+                w.cells.bitmap);
+            RCP_LAUNCHED();
+        }
+    }
+    {
+        StageTimer t(ST_BKT_COUNT);         // filter + pass 1
+        const size_t smem = (size_t)w.bm_words * 4;
+        if (st_arr) {
+            RCP_CUDA(cudaFuncSetAttribute(blk_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blk_filter_kernel<true><<<reads_grid(rd.n, smem), RTPB, smem, g_ctx.stream>>>(
+                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, counts);
+        } else {
+            RCP_CUDA(cudaFuncSetAttribute(blk_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blk_filter_kernel<false><<<reads_grid(rd.n, smem), RTPB, smem, g_ctx.stream>>>(
+                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, counts);
+        }
+        RCP_LAUNCHED();
+        blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, counts, hist1);
+        RCP_LAUNCHED();
+        RCP_TRY(exclusive_scan_u32(hist1, hist1, 256 * n_chunks, hist1 + 256 * n_chunks));
+        if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
+        else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
+        RCP_LAUNCHED();
+    }
+    {
+        StageTimer t(ST_BKT_SCATTER);       // pass 2 + block offsets
+        blk_runs_kernel<<<1, PT, 0, g_ctx.stream>>>(n_chunks, hist1, S1, CP);
+        RCP_LAUNCHED();
+        blk_hist2_kernel<<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb.s, CP, S1, hist2);
+        RCP_LAUNCHED();
+        RCP_TRY(exclusive_scan_u32(hist2, hist2, 256 * tc_upper, hist2 + 256 * tc_upper));
+        if (st_arr) blk_scatter2_kernel<true><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
+        else blk_scatter2_kernel<false><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
+        RCP_LAUNCHED();
+        blk_offsets_kernel<<<(65537 + PT - 1) / PT, PT, 0, g_ctx.stream>>>(CP, S1, hist2, blk_off);
+        RCP_LAUNCHED();
+    }
+    // ---- NULL rule, offsets ---------------------------------------------------------------------
+    const uint32_t max_w = rd.max_width > 0 ? rd.max_width : 1u;
+    {
+        StageTimer t(ST_BKT_PLAN);
+        if (T > 0) {
+            blk_any_kernel<<<blocks_for(T, WARPS), CTA, 0, g_ctx.stream>>>(T, w.tiles, ca, blk_off, max_w,
+                                                                           st_arr ? 1 : 0, w.tile_cnt);
+            RCP_LAUNCHED();
+        }
+        if (R > 0) {
+            bkt_null_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
+                R, Tb, w.off_big, w.off_small, w.plen, w.tile_cnt, cv->len, cv->is_null, w.padded,
+                w.stats);
+            RCP_LAUNCHED();
+        }
+        RCP_TRY(exclusive_scan_i64(w.padded, cv->off, R, cv->off + R));
+    }
+    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    cv->total_padded = h.total_padded;
+    cv->n_null = (int64_t)h.stats[0];
+    cv->total_len = (int64_t)h.stats[1];
+    cv->max_len = (int32_t)h.stats[2];
+    RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
+    if (T == 0 || cv->n_null == R) return RCP_OK;
+    RCP_TRY(w.C.reserve(Arena::pad((size_t)T * sizeof(TileDesc))));
+    w.desc = w.C.take<TileDesc>((size_t)T);
+    blk_desc_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, w.tiles, blk_off, max_w, cv->is_null,
+                                                                 cv->off, w.desc);
+    RCP_LAUNCHED();
+    if (Tb > 0) {
+        StageTimer t(ST_BKT_TILE);
+        int per_sm = 0;
+        RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blk_tile_kernel, CTA, 0));
+        if (per_sm < 1) per_sm = 1;
+        blk_tile_kernel<<<(unsigned)std::min<int64_t>(Tb, (int64_t)g_ctx.sm_count * per_sm), CTA, 0,
+                          g_ctx.stream>>>(Tb, w.desc, ca, st_arr ? 1 : 0, cv->cov);
+        RCP_LAUNCHED();
+    }
+    if (Ts > 0) {
+        StageTimer t(ST_BKT_SMALL);
+        blk_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, w.desc + Tb, ca,
+                                                                         st_arr ? 1 : 0, cv->cov);
         RCP_LAUNCHED();
     }
     return RCP_OK;

@@ -64,7 +64,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        unsigned int* __restrict__ err, unsigned long long* __restrict__ cls_count,
                        ExcBuf exc) {
     unsigned int my_err = 0;
-    unsigned int np = 0, nm = 0, ns = 0;
+    unsigned int np = 0, nm = 0, ns = 0, wmax = 0;
     // candidate common width: the fragment length, else the width of read 0
     uint32_t w = (uint32_t)frag_len;
     if (frag_len <= 0) {
@@ -80,6 +80,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         *gs = 0;
         *ge1 = 0;
         if (map_read(c, s, e, st, n_chrom, chrom_off, chrom_len, frag_len, gs, ge1, &my_err)) {
+            wmax = max(wmax, *ge1 - *gs);
             // reads of another width: recorded until the buffer overflows (then uniform-width
             // mode is abandoned anyway and the single counter must not become a hot spot)
             if (*ge1 - *gs != w && *reinterpret_cast<volatile unsigned int*>(exc.count) <= exc.cap) {
@@ -126,20 +127,22 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         if (strand_out) strand_out[i] = sgn(st);
     }
     // block-level reduction of the three strand counters and the error mask
-    __shared__ unsigned int sh[4];
-    if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+    __shared__ unsigned int sh[5];
+    if (threadIdx.x < 5) sh[threadIdx.x] = 0;
     __syncthreads();
     for (int d = 16; d > 0; d >>= 1) {
         np += __shfl_xor_sync(0xffffffffu, np, d);
         nm += __shfl_xor_sync(0xffffffffu, nm, d);
         ns += __shfl_xor_sync(0xffffffffu, ns, d);
         my_err |= __shfl_xor_sync(0xffffffffu, my_err, d);
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&sh[0], np);
         atomicAdd(&sh[1], nm);
         atomicAdd(&sh[2], ns);
         atomicOr(&sh[3], my_err);
+        atomicMax(&sh[4], wmax);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -147,6 +150,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         if (sh[1]) atomicAdd(&cls_count[1], (unsigned long long)sh[1]);
         if (sh[2]) atomicAdd(&cls_count[2], (unsigned long long)sh[2]);
         if (sh[3]) atomicOr(err, sh[3]);
+        if (sh[4]) atomicMax(&cls_count[3], (unsigned long long)sh[4]);
     }
 }
 
@@ -508,10 +512,10 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     unsigned long long* d_cnt = nullptr;
     unsigned int* d_w = nullptr;    // [0] exception count, [1] candidate width
     RCP_TRY(dalloc(&d_err, 1));
-    RCP_TRY(dalloc(&d_cnt, 3));
+    RCP_TRY(dalloc(&d_cnt, 4));
     RCP_TRY(dalloc(&d_w, 2));
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(unsigned int), g_ctx.stream));
     ExcBuf exc;
     exc.cap = (uint32_t)((n / 64 > 4096) ? (n / 64) : 4096);
@@ -545,7 +549,7 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
         RCP_LAUNCHED();
     }
     unsigned int h_err = 0, h_w[2] = {0, 0};
-    unsigned long long h_cnt[3] = {0, 0, 0};
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
     RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_w, d_w, sizeof(h_w), cudaMemcpyDeviceToHost, g_ctx.stream));
@@ -576,6 +580,7 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     r.cls[CLS_PLUS].n = (int64_t)h_cnt[0];
     r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
     r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
+    r.max_width = (uint32_t)h_cnt[3];
     if (eager_index) {
         RCP_TRY(reads_build_class(r, CLS_ALL));
         lap("class ALL enqueued");

@@ -134,6 +134,7 @@ struct ReadsIdx {
     int64_t n = 0;
     int n_chrom = 0;
     bool has_strand = false;
+    uint32_t max_width = 0;             // widest read (after extension and trimming)
     uint32_t uniform_w = 0;             // > 0: reads are this wide (ye == xs + w) except n_exc
     int64_t n_exc = 0;                  // reads of another width (uniform-width mode)
     uint32_t* exc_xw = nullptr;         // their start + w, true end + 1 and strand (unsorted)
