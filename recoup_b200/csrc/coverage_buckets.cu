@@ -606,7 +606,7 @@ inline unsigned reads_grid(int64_t n, size_t smem) {
 // ================================================================================================
 // BLOCKS mode: the same coverage without the cell table, the hit list and the place pass.
 //   filter     reads that pass the block bitmap, compacted per 4096-read chunk (no atomics)
-//   partition  the survivors are grouped by 64-kb genome block (start >> 16) with two 8-bit
+//   partition  the survivors are grouped by 16-kb genome block (start >> 14) with two 9-bit
 //              multisplit passes: per-chunk histograms in shared memory, one prefix sum over
 //              (digit, chunk), then a scatter whose ranks come from shared-memory counters --
 //              no global atomic per element, every pass is a streaming pass
@@ -614,9 +614,14 @@ inline unsigned reads_grid(int64_t n, size_t smem) {
 //              start >= tile start - widest read) and clips them itself
 // The NULL rule ("no read in any tile") is a warp-per-tile any-hit scan of the same candidates.
 // ================================================================================================
-constexpr int BLK_SHIFT = 16;
+constexpr int DIG_BITS = 9;                      // bits per multisplit pass
+constexpr int ND = 1 << DIG_BITS;                // digits per pass
+constexpr int BLK_SHIFT = 32 - 2 * DIG_BITS;     // 16-kb blocks (the granule of the bitmap)
+constexpr int N_BLOCKS = 1 << (2 * DIG_BITS);
+constexpr int SHIFT1 = 32 - DIG_BITS, SHIFT2 = BLK_SHIFT;
 constexpr int PCH = 4096;            // elements per partition chunk (one CTA)
-constexpr int PT = 256;              // threads of the partition kernels (= digits of a pass)
+constexpr int PT = 256;              // threads of the partition kernels
+static_assert(BLK_SHIFT == BM_SHIFT, "the filter bitmap and the partition use the same blocks");
 
 struct Cands {
     uint32_t* s;
@@ -686,54 +691,122 @@ blk_filter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
     }
 }
 
-// pass 1, histogram: one CTA per filter chunk, digit = top 8 bits of the coordinate;
-// hist is digit-major: hist[digit * n_chunks + chunk]
+// Histogram of one chunk (<= PCH keys at keys[lo, hi)) over the digit (key >> shift) & (ND - 1);
+// written digit-major: hist[digit * stride + column]
+__device__ __forceinline__ void blk_hist_chunk(const uint32_t* __restrict__ keys, uint32_t lo,
+                                               uint32_t hi, int shift, uint32_t* __restrict__ hist,
+                                               size_t stride, size_t column) {
+    __shared__ uint32_t h[ND];
+    for (int d = threadIdx.x; d < ND; d += PT) h[d] = 0;
+    __syncthreads();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += PT)
+        atomicAdd(&h[(__ldg(keys + i) >> shift) & (ND - 1)], 1u);
+    __syncthreads();
+    for (int d = threadIdx.x; d < ND; d += PT) hist[(size_t)d * stride + column] = h[d];
+}
+
+// Scatter of one chunk by the same digit: ranks from shared-memory counters, elements regrouped
+// by digit in shared memory, then written out so that consecutive threads write consecutive
+// addresses of a digit's run (whole sectors instead of one partial sector per element).
+// gbase[digit * stride + column] = global position of this chunk's first element with that digit.
+template <bool STRANDED>
+__device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, uint32_t hi, int shift,
+                                                  const uint32_t* __restrict__ gbase, size_t stride,
+                                                  size_t column, const Cands& out) {
+    __shared__ uint32_t cnt[ND];            // count, then local offset of each digit
+    __shared__ uint32_t gb[ND];
+    __shared__ uint32_t wsum[PT / 32];
+    __shared__ uint2 stage[PCH];
+    __shared__ int8_t stage_st[STRANDED ? PCH : 1];
+    const int tid = threadIdx.x;
+    for (int d = tid; d < ND; d += PT) cnt[d] = 0;
+    __syncthreads();
+    constexpr int PER = PCH / PT;           // 16 elements per thread
+    uint16_t rk[PER];                       // rank of the element inside its digit in this chunk
+    const uint32_t n = hi - lo;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = (uint32_t)k * PT + tid;
+        if (i < n) rk[k] = (uint16_t)atomicAdd(&cnt[(__ldg(in.s + lo + i) >> shift) & (ND - 1)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the ND digit counts (ND / PT consecutive digits per thread)
+    constexpr int DPT = ND / PT;
+    uint32_t c[DPT], mine = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        c[q] = cnt[tid * DPT + q];
+        mine += c[q];
+    }
+    uint32_t inc = mine;
+    const unsigned lane = tid & 31;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (lane >= (unsigned)dd) inc += o;
+    }
+    if (lane == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t run = inc - mine;
+    for (int k = 0; k < (tid >> 5); k++) run += wsum[k];
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        const int d = tid * DPT + q;
+        cnt[d] = run;                                       // local offset of digit d
+        gb[d] = gbase[(size_t)d * stride + column] - run;   // global position = gb[d] + local position
+        run += c[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = (uint32_t)k * PT + tid;
+        if (i < n) {
+            const uint32_t sv = __ldg(in.s + lo + i);       // second read: L1 / L2 hit
+            const uint32_t p = cnt[(sv >> shift) & (ND - 1)] + rk[k];
+            stage[p] = make_uint2(sv, __ldcs(in.e + lo + i));
+            if (STRANDED) stage_st[p] = __ldcs(in.st + lo + i);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += PT) {
+        const uint2 x = stage[i];
+        const uint32_t g = gb[(x.x >> shift) & (ND - 1)] + i;
+        out.s[g] = x.x;
+        out.e[g] = x.y;
+        if (STRANDED) out.st[g] = stage_st[i];
+    }
+}
+
+// pass 1: one CTA per filter chunk; hist1[digit * n_chunks + chunk]
 __global__ void __launch_bounds__(PT)
 blk_hist1_kernel(int64_t n_chunks, const uint32_t* __restrict__ keys,
                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t h[256];
     const int64_t c = blockIdx.x;
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t cnt = counts[c];
-    const uint32_t* k = keys + c * PCH;
-    for (uint32_t i = threadIdx.x; i < cnt; i += PT) atomicAdd(&h[__ldg(k + i) >> 24], 1u);
-    __syncthreads();
-    hist[(int64_t)threadIdx.x * n_chunks + c] = h[threadIdx.x];
+    const uint32_t lo = (uint32_t)(c * PCH);
+    blk_hist_chunk(keys, lo, lo + counts[c], SHIFT1, hist, (size_t)n_chunks, (size_t)c);
 }
 
-// pass 1, scatter: ranks from shared-memory cursors that start at the scanned offsets
 template <bool STRANDED>
 __global__ void __launch_bounds__(PT)
 blk_scatter1_kernel(int64_t n_chunks, Cands in, const uint32_t* __restrict__ counts,
                     const uint32_t* __restrict__ pos, Cands out) {
-    __shared__ uint32_t cur[256];
     const int64_t c = blockIdx.x;
-    cur[threadIdx.x] = pos[(int64_t)threadIdx.x * n_chunks + c];
-    __syncthreads();
-    const uint32_t cnt = counts[c];
-    const int64_t base = c * PCH;
-    for (uint32_t i = threadIdx.x; i < cnt; i += PT) {
-        const uint32_t s = __ldcs(in.s + base + i), e = __ldcs(in.e + base + i);
-        const uint32_t p = atomicAdd(&cur[s >> 24], 1u);
-        out.s[p] = s;
-        out.e[p] = e;
-        if (STRANDED) out.st[p] = __ldcs(in.st + base + i);
-    }
+    const uint32_t lo = (uint32_t)(c * PCH);
+    blk_scatter_chunk<STRANDED>(in, lo, lo + counts[c], SHIFT1, pos, (size_t)n_chunks, (size_t)c, out);
 }
 
-// After pass 1: start of each top-digit run (S1[257]) and the prefix of the chunk counts of
-// pass 2 (CP[257]): run d is cut into ceil(size / PCH) chunks.  One CTA of 256 threads.
-__global__ void __launch_bounds__(PT)
-blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hist1, [256*n_chunks] + total */,
+// After pass 1: start of each top-digit run (S1[ND + 1]) and the prefix of the chunk counts of
+// pass 2 (CP[ND + 1]): run d is cut into ceil(size / PCH) chunks.  One CTA of ND threads.
+__global__ void __launch_bounds__(ND)
+blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hist1 + total */,
                 uint32_t* __restrict__ S1, uint32_t* __restrict__ CP) {
-    __shared__ uint32_t w[PT / 32];
+    __shared__ uint32_t w[ND / 32];
     const int d = threadIdx.x;
-    const uint32_t total = pos[256 * n_chunks];
-    const uint32_t s = pos[(int64_t)d * n_chunks];
-    const uint32_t e = d == 255 ? total : pos[(int64_t)(d + 1) * n_chunks];
+    const uint32_t total = pos[(size_t)ND * n_chunks];
+    const uint32_t s = pos[(size_t)d * n_chunks];
+    const uint32_t e = d == ND - 1 ? total : pos[(size_t)(d + 1) * n_chunks];
     S1[d] = s;
-    if (d == 255) S1[256] = total;
+    if (d == ND - 1) S1[ND] = total;
     const uint32_t nch = (e - s + PCH - 1) / PCH;
     uint32_t inc = nch;
     const unsigned lane = d & 31;
@@ -747,15 +820,15 @@ blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hi
     uint32_t pre = 0;
     for (int k = 0; k < (d >> 5); k++) pre += w[k];
     CP[d] = pre + inc - nch;
-    if (d == 255) CP[256] = pre + inc;
+    if (d == ND - 1) CP[ND] = pre + inc;
 }
 
 // which (run, chunk) a pass-2 CTA owns; false past the last chunk
 __device__ __forceinline__ bool blk_chunk_of(uint32_t g, const uint32_t* __restrict__ CP,
                                              const uint32_t* __restrict__ S1, int* d_out,
                                              uint32_t* lo, uint32_t* hi, uint32_t* nch, uint32_t* j) {
-    if (g >= CP[256]) return false;
-    int a = 0, b = 256;                 // largest d with CP[d] <= g
+    if (g >= CP[ND]) return false;
+    int a = 0, b = ND;                  // largest d with CP[d] <= g
     while (b - a > 1) {
         const int mid = (a + b) >> 1;
         if (CP[mid] <= g) a = mid;
@@ -769,53 +842,39 @@ __device__ __forceinline__ bool blk_chunk_of(uint32_t g, const uint32_t* __restr
     return true;
 }
 
-// pass 2, histogram: digit = bits 16..23; hist2[CP[d] * 256 + digit * nch_d + j]
+// pass 2 inside the runs of pass 1; hist2[CP[d] * ND + digit * nch_d + j]
 __global__ void __launch_bounds__(PT)
 blk_hist2_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ CP,
                  const uint32_t* __restrict__ S1, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t h[256];
     int d;
     uint32_t lo, hi, nch, j;
     if (!blk_chunk_of(blockIdx.x, CP, S1, &d, &lo, &hi, &nch, &j)) return;
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += PT) atomicAdd(&h[(__ldg(keys + i) >> 16) & 255u], 1u);
-    __syncthreads();
-    hist[(size_t)CP[d] * 256 + (size_t)threadIdx.x * nch + j] = h[threadIdx.x];
+    blk_hist_chunk(keys, lo, hi, SHIFT2, hist + (size_t)CP[d] * ND, (size_t)nch, (size_t)j);
 }
 
 template <bool STRANDED>
 __global__ void __launch_bounds__(PT)
 blk_scatter2_kernel(Cands in, const uint32_t* __restrict__ CP, const uint32_t* __restrict__ S1,
                     const uint32_t* __restrict__ pos, Cands out) {
-    __shared__ uint32_t cur[256];
     int d;
     uint32_t lo, hi, nch, j;
     if (!blk_chunk_of(blockIdx.x, CP, S1, &d, &lo, &hi, &nch, &j)) return;
-    cur[threadIdx.x] = pos[(size_t)CP[d] * 256 + (size_t)threadIdx.x * nch + j];
-    __syncthreads();
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += PT) {
-        const uint32_t s = __ldcs(in.s + i), e = __ldcs(in.e + i);
-        const uint32_t p = atomicAdd(&cur[(s >> 16) & 255u], 1u);
-        out.s[p] = s;
-        out.e[p] = e;
-        if (STRANDED) out.st[p] = __ldcs(in.st + i);
-    }
+    blk_scatter_chunk<STRANDED>(in, lo, hi, SHIFT2, pos + (size_t)CP[d] * ND, (size_t)nch, (size_t)j, out);
 }
 
-// first candidate of every 64-kb block (65537 entries) from the scanned pass-2 histogram
+// first candidate of every block (N_BLOCKS + 1 entries) from the scanned pass-2 histogram
 __global__ void __launch_bounds__(PT)
 blk_offsets_kernel(const uint32_t* __restrict__ CP, const uint32_t* __restrict__ S1,
                    const uint32_t* __restrict__ pos2, uint32_t* __restrict__ boff) {
     const uint32_t b = blockIdx.x * PT + threadIdx.x;
-    if (b > 65536u) return;
-    if (b == 65536u) {
-        boff[b] = S1[256];
+    if (b > (uint32_t)N_BLOCKS) return;
+    if (b == (uint32_t)N_BLOCKS) {
+        boff[b] = S1[ND];
         return;
     }
-    const uint32_t d = b >> 8, low = b & 255u;
+    const uint32_t d = b >> DIG_BITS, low = b & (ND - 1);
     const uint32_t nch = CP[d + 1] - CP[d];
-    boff[b] = nch ? pos2[(size_t)CP[d] * 256 + (size_t)low * nch] : S1[d];
+    boff[b] = nch ? pos2[(size_t)CP[d] * ND + (size_t)low * nch] : S1[d];
 }
 
 // candidates that can reach the tile [ts, ts + tl): those of the blocks from (ts - widest + 1)
@@ -1333,7 +1392,7 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
     const int64_t n_cell = (span >> CELL_SHIFT) + 2;
     w.bm_words = (int)(((span >> BM_SHIFT) + 32) / 32);
     const int64_t n_chunks = ((rd.n >> 2) + PCH / 4 - 1) / (PCH / 4) + 1;      // filter chunks
-    const int64_t tc_upper = (rd.n + PCH - 1) / PCH + 256;                     // pass-2 chunks
+    const int64_t tc_upper = (rd.n + PCH - 1) / PCH + ND;                      // pass-2 chunks
     Cands ca, cb;
     uint32_t *counts, *hist1, *hist2, *S1, *CP, *blk_off;
     size_t zero_bytes = 0;
@@ -1341,16 +1400,16 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         const size_t t = (size_t)T, c = (size_t)n_cell, nc = (size_t)n_chunks, cap = nc * PCH;
         const size_t st_bytes = st_arr ? Arena::pad(cap) : 0;
         RCP_TRY(w.B.reserve(Arena::pad((c + 1) * 4) + Arena::pad((size_t)w.bm_words * 4) +
-                            Arena::pad((t + 1) * 4) + Arena::pad(256 * (size_t)tc_upper * 4 + 4) +
+                            Arena::pad((t + 1) * 4) + Arena::pad((size_t)ND * (size_t)tc_upper * 4 + 4) +
                             Arena::pad(t * 8) * 2 + Arena::pad(cap * 4) * 4 + st_bytes * 2 +
-                            Arena::pad(nc * 4) + Arena::pad((256 * nc + 1) * 4) + Arena::pad(257 * 4) * 2 +
-                            Arena::pad(65537 * 4)));
+                            Arena::pad(nc * 4) + Arena::pad(((size_t)ND * nc + 1) * 4) + Arena::pad((ND + 1) * 4) * 2 +
+                            Arena::pad(((size_t)N_BLOCKS + 1) * 4)));
         // zero-initialised block first: cell counts (unused here, but bkt_tiles_kernel bumps them),
         // bitmap, tile flags, pass-2 histogram
         w.cells.cnt = w.B.take<uint32_t>(c + 1);
         w.cells.bitmap = w.B.take<uint32_t>((size_t)w.bm_words);
         w.tile_cnt = w.B.take<uint32_t>(t + 1);
-        hist2 = w.B.take<uint32_t>(256 * (size_t)tc_upper + 1);
+        hist2 = w.B.take<uint32_t>((size_t)ND * (size_t)tc_upper + 1);
         zero_bytes = w.B.used;
         w.tiles.a = w.B.take<uint2>(t);
         w.tiles.b = w.B.take<uint2>(t);
@@ -1361,10 +1420,10 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         ca.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
         cb.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
         counts = w.B.take<uint32_t>(nc);
-        hist1 = w.B.take<uint32_t>(256 * nc + 1);
-        S1 = w.B.take<uint32_t>(257);
-        CP = w.B.take<uint32_t>(257);
-        blk_off = w.B.take<uint32_t>(65537);
+        hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
+        S1 = w.B.take<uint32_t>(ND + 1);
+        CP = w.B.take<uint32_t>(ND + 1);
+        blk_off = w.B.take<uint32_t>((size_t)N_BLOCKS + 1);
         if (w.B.used > w.B.cap) return fail(RCP_ERR_CUDA, "internal: blocks arena overrun");
     }
     {
@@ -1392,22 +1451,22 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         RCP_LAUNCHED();
         blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, counts, hist1);
         RCP_LAUNCHED();
-        RCP_TRY(exclusive_scan_u32(hist1, hist1, 256 * n_chunks, hist1 + 256 * n_chunks));
+        RCP_TRY(exclusive_scan_u32(hist1, hist1, (int64_t)ND * n_chunks, hist1 + (int64_t)ND * n_chunks));
         if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
         else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
         RCP_LAUNCHED();
     }
     {
         StageTimer t(ST_BKT_SCATTER);       // pass 2 + block offsets
-        blk_runs_kernel<<<1, PT, 0, g_ctx.stream>>>(n_chunks, hist1, S1, CP);
+        blk_runs_kernel<<<1, ND, 0, g_ctx.stream>>>(n_chunks, hist1, S1, CP);
         RCP_LAUNCHED();
         blk_hist2_kernel<<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb.s, CP, S1, hist2);
         RCP_LAUNCHED();
-        RCP_TRY(exclusive_scan_u32(hist2, hist2, 256 * tc_upper, hist2 + 256 * tc_upper));
+        RCP_TRY(exclusive_scan_u32(hist2, hist2, (int64_t)ND * tc_upper, hist2 + (int64_t)ND * tc_upper));
         if (st_arr) blk_scatter2_kernel<true><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
         else blk_scatter2_kernel<false><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
         RCP_LAUNCHED();
-        blk_offsets_kernel<<<(65537 + PT - 1) / PT, PT, 0, g_ctx.stream>>>(CP, S1, hist2, blk_off);
+        blk_offsets_kernel<<<(N_BLOCKS + 1 + PT - 1) / PT, PT, 0, g_ctx.stream>>>(CP, S1, hist2, blk_off);
         RCP_LAUNCHED();
     }
     // ---- NULL rule, offsets ---------------------------------------------------------------------
