@@ -452,11 +452,13 @@ def run_b200(args):
     e2e_steps = max(2, min(args.steps, 5))
 
     phases = {"upload+index": 0.0, "coverage": 0.0, "profile+download": 0.0}
+    e2e_in = {"seqnames": host_views[0], "views": host_views}
 
     def e2e_step():
         """The calls a user of the reference API makes, on pinned HOST arrays."""
         t_a = time.perf_counter()
-        reads = rb.GRanges(host_views[0], host_views[1], host_views[2], strand=host_views[3],
+        hv = e2e_in["views"]
+        reads = rb.GRanges(e2e_in["seqnames"], hv[1], hv[2], strand=hv[3],
                            seqlevels=w["chrom_names"], seqlengths=clen)
         sample = [dict(id="s", name="s", ranges=reads)]
         rb.device_reads(reads, w["frag_len"])
@@ -496,6 +498,33 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert mat.shape == (R, ncols)
+    main_phases = dict(phases)
+
+    # ---- the same, with the reads grouped by chromosome as a coordinate-sorted BAM delivers
+    # them (random order inside a chromosome: nothing on the device assumes an order).  A GRanges
+    # holds such seqnames as ~25 runs (Rle), and rcp_reads_load_rle sends the runs instead of
+    # 4 bytes per read.  Reported beside `e2e`, which stays on the randomly ordered arrays.
+    order = np.argsort(host_views[0].astype(np.uint8), kind="stable")
+    for p in pins:
+        p.numpy()[...] = p.numpy()[order]
+    del order
+    seq_rle = rb.Rle.encode(host_views[0])
+    e2e_in["seqnames"] = seq_rle
+    h2d_bam = h2d - host_views[0].nbytes + 8 * seq_rle.nrun
+    want_sum = float(mat.sum())
+    keep = [e2e_step(), e2e_step()]
+    assert abs(float(keep[0].sum()) - want_sum) <= 1e-9 * max(abs(want_sum), 1.0)
+    del keep
+    for k in phases:
+        phases[k] = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mat = e2e_step()
+    torch.cuda.synchronize()
+    e2e_bam_s = (time.perf_counter() - t0) / e2e_steps
+    bam_phases = dict(phases)
+    phases = main_phases
 
     # ---- N > 1: the exchanged matrix on rank 0 must hold every rank's rows ----
     exchange_ok = None
@@ -522,10 +551,10 @@ def run_b200(args):
             assert exchange_ok, "rows of some rank did not arrive in rank 0's matrix"
 
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, e2e_bam_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    elapsed_ms, e2e_ms, e2e_bam_ms = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = elapsed_ms / args.steps
     value = world * N / (ms_per_step * 1e-3)
     e2e_value = world * N / (e2e_ms * 1e-3)
@@ -607,7 +636,15 @@ def run_b200(args):
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "phases_ms": {k: 1e3 * v / e2e_steps for k, v in phases.items()}},
+                    "phases_ms": {k: 1e3 * v / e2e_steps for k, v in phases.items()},
+                    "inputs": "reads in random order; seqnames, start, end int32 + strand int8"},
+            "e2e_bam_order": {"value": world * N / (e2e_bam_ms * 1e-3), "unit": UNIT,
+                              "h2d_bytes_per_step": int(h2d_bam), "d2h_bytes_per_step": int(d2h),
+                              "ms_per_step": e2e_bam_ms, "steps": e2e_steps,
+                              "phases_ms": {k: 1e3 * v / e2e_steps for k, v in bam_phases.items()},
+                              "inputs": "the same reads grouped by chromosome (BAM order); seqnames "
+                                        "as the Rle a GRanges holds (%d runs), start, end int32 + "
+                                        "strand int8" % seq_rle.nrun},
             "gpu_launches": launches, "clocks": clocks,
         }
         if exchange_ok is not None:

@@ -105,7 +105,7 @@ const char* rcp_timing_stage_name(int stage);
 #define RCP_PATH_AUTO 0
 #define RCP_PATH_INDEX 1
 #define RCP_PATH_BUCKETS 2
-#define RCP_PATH_BLOCKS 3      /* experimental: filter + two multisplit passes by 64-kb block */
+#define RCP_PATH_BLOCKS 3      /* experimental: filter + two multisplit passes by 16-kb block */
 int rcp_set_coverage_path(int path);
 
 /* ---------------------------------------------------------------- base-R RNG -------------- */
@@ -126,6 +126,14 @@ int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out /* n */);
 int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                    const int8_t* strand, int n_chrom, const int64_t* chrom_len, int frag_len,
                    int mem, int* reads_out);
+/* The same with the chromosome ids as runs -- the form a GRanges holds them in (`seqnames(x)` is
+ * a factor-Rle: run_chrom = as.integer(runValue(seqnames(x))) - 1L, run_len = runLength(...));
+ * coordinate-sorted reads have one run per chromosome, so 4 of the 13 bytes per read never cross
+ * PCIe.  The run lengths must be >= 0 and sum to n (< 2^32).  Same result as rcp_reads_load on the
+ * expanded ids. */
+int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, const int32_t* run_len,
+                       const int32_t* start, const int32_t* end, const int8_t* strand, int n_chrom,
+                       const int64_t* chrom_len, int frag_len, int mem, int* reads_out);
 int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes);
 int rcp_reads_free(int reads);
 

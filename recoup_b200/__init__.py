@@ -11,10 +11,10 @@ from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, cov
                        device_reads, set_verbose)
 from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, haveEqualLengths,
                       profileMatrix)
-from .ranges import GRanges, GRangesList, getFlankingRanges, getRegionalRanges
+from .ranges import GRanges, GRangesList, Rle, getFlankingRanges, getRegionalRanges
 
 __all__ = [
-    "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "getRegionalRanges",
+    "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "Rle", "getRegionalRanges",
     "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
     "haveEqualLengths", "ProfileMatrix", "set_verbose",

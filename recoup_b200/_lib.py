@@ -46,6 +46,8 @@ SIGNATURES = {
     "rcp_r_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "rcp_r_rank_table": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip]),
     "rcp_reads_load": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, _ip]),
+    "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
+                                     C.c_int, C.c_int, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),
     "rcp_reads_free": (C.c_int, [C.c_int]),
     "rcp_coverage": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _ip]),

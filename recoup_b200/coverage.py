@@ -46,20 +46,34 @@ def set_verbose(flag):
 class DeviceReads:
     """Device index of one sample's reads (rcp_reads_load)."""
 
-    def __init__(self, gr, frag_len=0):
+    def __init__(self, gr, frag_len=0, use_runs=None):
+        """use_runs: send the seqnames as runs (rcp_reads_load_rle); default: when the GRanges
+        holds them as an Rle with fewer than n / 2 runs."""
         if gr.seqlengths is None:
             raise ValueError("reads need seqlengths (the length of the per-chromosome coverage "
                              "vector, coverage.R:201)")
         _lib.ensure_init()
         h = C.c_int(0)
-        chrom = np.ascontiguousarray(gr.seqnames, dtype=np.int32)
         start = np.ascontiguousarray(gr.start, dtype=np.int32)
         end = np.ascontiguousarray(gr.end, dtype=np.int32)
         strand = np.ascontiguousarray(gr.strand, dtype=np.int8)
         clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
-        _lib_check(_lib.lib.rcp_reads_load(len(gr), _ptr(chrom), _ptr(start), _ptr(end), _ptr(strand),
-                                           clen.shape[0], clen.ctypes.data_as(C.POINTER(C.c_int64)),
-                                           int(frag_len), _lib.MEM_HOST, C.byref(h)))
+        clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
+        rle = gr.seqnames_rle
+        if use_runs is None:
+            use_runs = rle is not None and len(gr) < 2**32 - 16 and rle.nrun * 2 < len(gr)
+        if use_runs:
+            # seqnames held as runs: only the runs cross PCIe
+            run_chrom = np.ascontiguousarray(rle.values, dtype=np.int32)
+            run_len = np.ascontiguousarray(rle.lengths, dtype=np.int32)
+            _lib_check(_lib.lib.rcp_reads_load_rle(len(gr), rle.nrun, _ptr(run_chrom), _ptr(run_len),
+                                                   _ptr(start), _ptr(end), _ptr(strand), clen.shape[0],
+                                                   clen_p, int(frag_len), _lib.MEM_HOST, C.byref(h)))
+        else:
+            chrom = np.ascontiguousarray(gr.seqnames, dtype=np.int32)
+            _lib_check(_lib.lib.rcp_reads_load(len(gr), _ptr(chrom), _ptr(start), _ptr(end),
+                                               _ptr(strand), clen.shape[0], clen_p, int(frag_len),
+                                               _lib.MEM_HOST, C.byref(h)))
         self.handle = h.value
         self.n = len(gr)
         self.seqlevels = list(gr.seqlevels)

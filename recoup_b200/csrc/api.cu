@@ -175,7 +175,8 @@ static void drop_coverage(int h) {
 }
 
 // implemented in the other translation units
-int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs,
+                    const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
                     const int64_t* chrom_len, int frag_len, int mem);
 int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
@@ -508,7 +509,33 @@ int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const 
         return fail(RCP_ERR_ARG, "rcp_reads_load: NULL array");
     if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
     std::unique_ptr<ReadsIdx> r(new ReadsIdx());
-    int rc = reads_load_impl(*r, n, chrom, start, end, strand, n_chrom, chrom_len, frag_len, mem);
+    int rc = reads_load_impl(*r, n, chrom, 0, nullptr, nullptr, start, end, strand, n_chrom, chrom_len,
+                             frag_len, mem);
+    if (rc != RCP_OK) {
+        reads_release(*r);
+        return rc;
+    }
+    const int h = g_next_handle++;
+    g_reads[h] = std::move(r);
+    *reads_out = h;
+    return RCP_OK;
+}
+
+int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, const int32_t* run_len,
+                       const int32_t* start, const int32_t* end, const int8_t* strand, int n_chrom,
+                       const int64_t* chrom_len, int frag_len, int mem, int* reads_out) {
+    RCP_TRY(require_ready());
+    if (n < 0 || n_runs < 0 || n_chrom < 1 || chrom_len == nullptr || reads_out == nullptr ||
+        frag_len < 0)
+        return fail(RCP_ERR_ARG, "rcp_reads_load_rle: bad scalar argument");
+    if (n > 0 && (n_runs < 1 || run_chrom == nullptr || run_len == nullptr || start == nullptr ||
+                  end == nullptr))
+        return fail(RCP_ERR_ARG, "rcp_reads_load_rle: NULL array");
+    if (n >= 0xfffffff0ll) return fail(RCP_ERR_UNSUPPORTED, "rcp_reads_load_rle: n >= 2^32");
+    if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
+    std::unique_ptr<ReadsIdx> r(new ReadsIdx());
+    int rc = reads_load_impl(*r, n, nullptr, n_runs, run_chrom, run_len, start, end, strand, n_chrom,
+                             chrom_len, frag_len, mem);
     if (rc != RCP_OK) {
         reads_release(*r);
         return rc;

@@ -455,9 +455,52 @@ int reads_build_pairs(ReadsIdx& r) {
     return RCP_OK;
 }
 
+// seqnames given as runs (GRanges keeps them as an Rle): run r covers reads
+// [run_first[r], run_first[r + 1]).  Every thread writes four consecutive reads: a binary search
+// places the first one, the others walk forward.  Reads beyond the runs' total get -1 (flagged by
+// the map kernel as a bad chromosome id).
+__global__ void __launch_bounds__(TPB)
+rle_expand_kernel(int64_t n, int64_t n_runs, const int32_t* __restrict__ run_value,
+                  const uint32_t* __restrict__ run_first /* n_runs + 1 */,
+                  int32_t* __restrict__ dense /* padded to a multiple of 4 */) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    const int64_t n_vec = (n + 3) >> 2;
+    for (int64_t v = (int64_t)blockIdx.x * TPB + threadIdx.x; v < n_vec; v += stride) {
+        const uint32_t i0 = (uint32_t)(v * 4);
+        int64_t a = 0, b = n_runs;              // largest run with run_first <= i0
+        while (b - a > 1) {
+            const int64_t mid = (a + b) >> 1;
+            if (__ldg(run_first + mid) <= i0) a = mid;
+            else b = mid;
+        }
+        int64_t r = a;
+        uint32_t next = __ldg(run_first + r + 1);
+        int32_t val = __ldg(run_value + r);
+        int32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            while (i0 + k >= next && r + 1 < n_runs) {
+                r++;
+                next = __ldg(run_first + r + 1);
+                val = __ldg(run_value + r);
+            }
+            o[k] = (i0 + k < next) ? val : -1;
+        }
+        reinterpret_cast<int4*>(dense)[v] = make_int4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+rle_check_kernel(int64_t n_runs, const int32_t* __restrict__ run_len, unsigned int* __restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n_runs && run_len[i] < 0) atomicOr(err, 8u);
+}
+
 // Builds the raw global-coordinate arrays (and, under RCP_PATH_INDEX, the ALL class at once; it
 // is otherwise built by the first call that needs it).  Synchronises once to validate.
-int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+// chrom == nullptr: the chromosome ids come as n_runs runs (run_chrom, run_len).
+int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs,
+                    const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
                     const int64_t* chrom_len, int frag_len, int mem) {
     const bool dbg = getenv("RCP_DEBUG_TIMING") != nullptr;
@@ -497,9 +540,15 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     RCP_CUDA(cudaMemcpyAsync(r.d_chrom_off, r.chrom_off.data(), ((size_t)n_chrom + 1) * 4,
                              cudaMemcpyHostToDevice, g_ctx.stream));
 
-    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int32_t> d_chrom, d_start, d_end, d_run_chrom, d_run_len;
     DevIn<int8_t> d_strand;
-    RCP_TRY(d_chrom.init(chrom, (size_t)n, mem));
+    const bool rle = chrom == nullptr && n > 0;
+    if (rle) {
+        RCP_TRY(d_run_chrom.init(run_chrom, (size_t)n_runs, mem));
+        RCP_TRY(d_run_len.init(run_len, (size_t)n_runs, mem));
+    } else {
+        RCP_TRY(d_chrom.init(chrom, (size_t)n, mem));
+    }
     RCP_TRY(d_start.init(start, (size_t)n, mem));
     RCP_TRY(d_end.init(end, (size_t)n, mem));
     RCP_TRY(d_strand.init(strand, (size_t)n, mem));
@@ -517,6 +566,20 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(unsigned int), g_ctx.stream));
+    uint32_t* run_first = nullptr;      // exclusive scan of the run lengths + their total
+    if (rle) {
+        StageTimer t(ST_INDEX_MAP);
+        RCP_TRY(dalloc(&run_first, (size_t)n_runs + 1));
+        RCP_TRY(dalloc(&d_chrom.owned, ((size_t)n + 3) & ~(size_t)3));
+        d_chrom.ptr = d_chrom.owned;
+        rle_check_kernel<<<grid_for(n_runs), TPB, 0, g_ctx.stream>>>(n_runs, d_run_len.ptr, d_err);
+        RCP_LAUNCHED();
+        RCP_TRY(exclusive_scan_u32(reinterpret_cast<const uint32_t*>(d_run_len.ptr), run_first, n_runs,
+                                   run_first + n_runs));
+        rle_expand_kernel<<<grid_for((n + 3) / 4), TPB, 0, g_ctx.stream>>>(
+            n, n_runs, d_run_chrom.ptr, run_first, d_chrom.owned);
+        RCP_LAUNCHED();
+    }
     ExcBuf exc;
     exc.cap = (uint32_t)((n / 64 > 4096) ? (n / 64) : 4096);
     RCP_TRY(dalloc(&r.exc_xw, (size_t)exc.cap));
@@ -548,8 +611,11 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
                 exc);
         RCP_LAUNCHED();
     }
-    unsigned int h_err = 0, h_w[2] = {0, 0};
+    unsigned int h_err = 0, h_w[2] = {0, 0}, h_total = 0;
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    if (rle)
+        RCP_CUDA(cudaMemcpyAsync(&h_total, run_first + n_runs, sizeof(h_total), cudaMemcpyDeviceToHost,
+                                 g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
     RCP_CUDA(cudaMemcpyAsync(h_w, d_w, sizeof(h_w), cudaMemcpyDeviceToHost, g_ctx.stream));
@@ -559,6 +625,11 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t*
     dfree(d_err);
     dfree(d_cnt);
     dfree(d_w);
+    dfree(run_first);
+    if (h_err & 8u) return fail(RCP_ERR_DATA, "a seqnames run has a negative length");
+    if (rle && (int64_t)h_total != n)
+        return fail(RCP_ERR_DATA, "the seqnames run lengths sum to %u, not to the %lld reads", h_total,
+                    (long long)n);
     // (nearly) every read has the same width w -- fixed-length or fragment-extended libraries;
     // the few that do not (trimmed at a chromosome end) live in a correction source.  Then the
     // sorted ends are the sorted starts shifted by w: one array, one sort.

@@ -35,10 +35,44 @@ def strand_to_code(strand, n=None):
     return np.sign(arr).astype(np.int8)
 
 
+class Rle:
+    """Run-length encoded vector (S4Vectors::Rle) -- how a GRanges holds its seqnames.  `values[r]`
+    repeated `lengths[r]` times."""
+
+    def __init__(self, values, lengths):
+        self.values = np.asarray(values)
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        if self.values.shape[0] != self.lengths.shape[0]:
+            raise ValueError("values and lengths must have the same length")
+        if self.lengths.shape[0] and int(self.lengths.min()) < 0:
+            raise ValueError("negative run length")
+        self._n = int(self.lengths.astype(np.int64).sum())
+
+    def __len__(self):
+        return self._n
+
+    @property
+    def nrun(self):
+        return self.lengths.shape[0]
+
+    def decode(self):
+        return np.repeat(self.values, self.lengths)
+
+    @staticmethod
+    def encode(x):
+        x = np.asarray(x)
+        if x.shape[0] == 0:
+            return Rle(x, np.zeros(0, dtype=np.int32))
+        cut = np.flatnonzero(x[1:] != x[:-1]) + 1
+        first = np.concatenate(([0], cut))
+        return Rle(x[first], np.diff(np.concatenate((first, [x.shape[0]]))))
+
+
 class GRanges:
-    """seqnames are stored as int32 ids into `seqlevels`; `seqlengths[i]` is the length of
-    seqlevels[i] (required for reads: the coverage vector of a chromosome has that length,
-    coverage.R:201)."""
+    """seqnames are stored as int32 ids into `seqlevels` (dense, or as an `Rle` when given as
+    one: `seqnames_rle`; the dense `seqnames` is then decoded on first use); `seqlengths[i]` is
+    the length of seqlevels[i] (required for reads: the coverage vector of a chromosome has that
+    length, coverage.R:201)."""
 
     def __init__(self, seqnames, start, end=None, width=None, strand=None, seqlevels=None,
                  seqlengths=None, names=None):
@@ -49,6 +83,12 @@ class GRanges:
                 raise ValueError("give end or width")
             end = start.astype(np.int64) + np.asarray(width, dtype=np.int64) - 1
         end = np.ascontiguousarray(end, dtype=np.int32)
+        run_len = None
+        if isinstance(seqnames, Rle):
+            if len(seqnames) != n:
+                raise ValueError("seqnames, start, end and strand must have the same length")
+            run_len = seqnames.lengths
+            seqnames = seqnames.values
         sn = np.asarray(seqnames)
         if sn.dtype.kind in "US":
             if seqlevels is None:
@@ -62,14 +102,19 @@ class GRanges:
             ids = np.ascontiguousarray(sn, dtype=np.int32)
             if seqlevels is None:
                 seqlevels = ["chr%d" % (i + 1) for i in range(int(ids.max()) + 1 if n else 0)]
-        if ids.shape[0] == 1 and n != 1:
+        if run_len is None and ids.shape[0] == 1 and n != 1:
             ids = np.full(n, ids[0], dtype=np.int32)
         st = strand_to_code(strand, n) if strand is not None else np.zeros(n, dtype=np.int8)
         if st.shape[0] == 1 and n != 1:
             st = np.full(n, st[0], dtype=np.int8)
-        if not (ids.shape[0] == end.shape[0] == st.shape[0] == n):
+        if not ((run_len is not None or ids.shape[0] == n) and end.shape[0] == st.shape[0] == n):
             raise ValueError("seqnames, start, end and strand must have the same length")
-        self.seqnames = ids
+        if run_len is None:
+            self.seqnames_rle = None
+            self._seqnames = ids
+        else:
+            self.seqnames_rle = Rle(ids, run_len)
+            self._seqnames = None
         self.start = start
         self.end = end
         self.strand = np.ascontiguousarray(st, dtype=np.int8)
@@ -81,6 +126,12 @@ class GRanges:
 
     def __len__(self):
         return self.start.shape[0]
+
+    @property
+    def seqnames(self):
+        if self._seqnames is None:
+            self._seqnames = np.ascontiguousarray(self.seqnames_rle.decode(), dtype=np.int32)
+        return self._seqnames
 
     @property
     def width(self):

@@ -478,6 +478,72 @@ def test_handles_and_errors(gpu):
     assert _lib.lib.rcp_launch_count(0) > 0 and before >= 0
 
 
+@pytest.mark.parametrize("n_reads,runs", [(20000, "sorted"), (1, "sorted"), (4099, "many"),
+                                          (5000, "empty_runs")])
+def test_seqnames_as_runs_give_the_same_coverage(gpu, n_reads, runs):
+    """rcp_reads_load_rle (seqnames as the Rle a GRanges holds) == the dense upload == oracle"""
+    rb = gpu
+    rng = np.random.default_rng(5)
+    clen = [30000, 70000, 900, 15000]
+    chrom, s, e, st = synth_reads(rng, n_reads, clen, width=(1, 300))
+    if runs != "many":                       # grouped by chromosome, like a sorted BAM
+        order = np.argsort(chrom, kind="stable")
+        chrom, s, e, st = chrom[order], s[order], e[order], st[order]
+    rle = rb.Rle.encode(chrom)
+    if runs == "empty_runs":                 # zero-length runs between and around the real ones
+        vals = np.repeat(rle.values, 3)
+        lens = np.zeros(vals.shape[0], dtype=np.int32)
+        lens[1::3] = rle.lengths
+        vals[0::3] = 3 - vals[0::3]
+        rle = rb.Rle(vals, lens)
+    o_reads, g_dense = both_reads(chrom, s, e, st, clen)
+    g_rle = rb.GRanges(rle, s, e, strand=st, seqlevels=g_dense.seqlevels, seqlengths=clen)
+    assert np.array_equal(g_rle.seqnames, chrom)
+    rc, rs, re_, rst = _regions(rng, 120, clen, [1, 33, 128, 1024, 1025, 5000, 9000])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    want = O.calc_coverage(o_reads, o_mask, None, False)
+    # force the runs entry (the wrapper picks it by itself only when it pays)
+    from recoup_b200.coverage import DeviceReads
+    dr = DeviceReads(g_rle, 0, use_runs=True)
+    g_rle._device[0] = dr
+    got = rb.calcCoverage(g_rle, g_mask, ignore_strand=False)
+    assert_coverage_equal(got.to_list(), want)
+    assert_coverage_equal(rb.calcCoverage(g_dense, g_mask, ignore_strand=False).to_list(), want)
+    dr.free()
+    g_rle._device.clear()
+    if runs == "sorted" and n_reads > 1:     # and through the wrapper, which now takes the runs
+        assert g_rle.seqnames_rle.nrun * 2 < len(g_rle)
+        assert_coverage_equal(rb.calcCoverage(g_rle, g_mask, ignore_strand=False).to_list(), want)
+
+
+def test_seqnames_runs_errors(gpu):
+    rb = gpu
+    from recoup_b200 import _lib
+    s = np.arange(1, 9, dtype=np.int32)
+    e = s + 5
+    cl = np.asarray([100, 100], dtype=np.int64)
+
+    def load(vals, lens):
+        h = C.c_int(0)
+        rv = np.asarray(vals, dtype=np.int32)
+        rl = np.asarray(lens, dtype=np.int32)
+        rc = _lib.lib.rcp_reads_load_rle(8, rv.shape[0], rv.ctypes.data_as(C.c_void_p),
+                                         rl.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                                         e.ctypes.data_as(C.c_void_p), None, 2,
+                                         cl.ctypes.data_as(C.POINTER(C.c_int64)), 0, _lib.MEM_HOST,
+                                         C.byref(h))
+        if rc == 0:
+            _lib.lib.rcp_reads_free(h.value)
+        return rc
+
+    assert load([0, 1], [5, 3]) == 0
+    assert load([0, 1], [5, 2]) == _lib.RCP_ERR_DATA        # runs shorter than the reads
+    assert load([0, 1], [5, 4]) == _lib.RCP_ERR_DATA        # ... longer
+    assert load([0, 1], [9, -1]) == _lib.RCP_ERR_DATA       # negative run
+    assert load([0, 2], [5, 3]) == _lib.RCP_ERR_DATA        # chromosome id out of range
+    assert load([], []) == _lib.RCP_ERR_ARG
+
+
 # ------------------------------------------------------------------------------------------------
 # the hand-written index sort, directly
 # ------------------------------------------------------------------------------------------------

@@ -81,3 +81,23 @@ def test_granges_container():
     assert len(sub) == 2 and sub.start.tolist() == [5, 9]
     with pytest.raises(ValueError):
         rb.GRangesList(gr, [0, 2])
+
+
+def test_rle_seqnames_round_trip():
+    from recoup_b200 import GRanges, Rle
+    x = np.array([0, 0, 0, 2, 2, 1, 1, 1, 1], dtype=np.int32)
+    r = Rle.encode(x)
+    assert r.values.tolist() == [0, 2, 1] and r.lengths.tolist() == [3, 2, 4] and len(r) == 9
+    assert np.array_equal(r.decode(), x)
+    assert len(Rle.encode(np.zeros(0, np.int32))) == 0
+    g = GRanges(r, np.arange(1, 10), np.arange(1, 10) + 5, seqlevels=["a", "b", "c"])
+    assert g.seqnames_rle.nrun == 3 and np.array_equal(g.seqnames, x)
+    g2 = GRanges(Rle(["a", "c", "b"], [3, 2, 4]), np.arange(1, 10), width=np.full(9, 6),
+                 seqlevels=["a", "b", "c"])
+    assert np.array_equal(g2.seqnames, x) and np.array_equal(g2.end, g.end)
+    sub = g2.subset(np.array([0, 4, 8]))
+    assert sub.seqnames.tolist() == [0, 2, 1] and sub.seqnames_rle is None
+    with pytest.raises(ValueError):
+        GRanges(Rle([0], [8]), np.arange(1, 10), np.arange(1, 10))
+    with pytest.raises(ValueError):
+        Rle([0, 1], [3, -1])
