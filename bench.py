@@ -332,6 +332,8 @@ def run_b200(args):
             out_ptr = out_box["ptr"]
         else:
             buf = out_box["bufs"][k % len(out_box["bufs"])]
+            if world > 1:
+                gissued[k % 2].wait()       # the helper thread has issued that gather
             if world > 1 and gdone[k % 2] is not None:
                 stream.wait_event(gdone[k % 2])     # the gather that read this buffer two steps ago
             out_ptr = buf.data_ptr()
@@ -347,22 +349,8 @@ def run_b200(args):
     gstream = torch.cuda.Stream(device=dev) if world > 1 else None
     gdone = [None, None]
 
-    def gather_step(k=0):
-        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) and their
-        placement into the full column-major matrix.  It runs on its own stream, behind the bin
-        kernel of this step and beside the next step's kernels: the output matrix is double
-        buffered (step k writes buffer k % 2), so only the gather of step k - 2 must have finished
-        before step k may overwrite its buffer."""
-        if world == 1:
-            return
-        if "peer" in out_box:               # the rows are already in place: order the stores
-            if args.fence == "step":
-                with torch.cuda.stream(stream):
-                    out_box["peer"].fence()
-            return
+    def gather_issue(k, ready):
         from recoup_b200.sharding import RowGather
-        ready = torch.cuda.Event()
-        ready.record(stream)                # the bin kernel of this step (library stream)
         gstream.wait_event(ready)
         with torch.cuda.stream(gstream):
             if "g" not in gather_box:       # buffers and row indices are set up once
@@ -372,9 +360,60 @@ def run_b200(args):
             gather_box["full"] = gather_box["g"].gather(out_box["bufs"][k % 2])
             done = torch.cuda.Event()
             done.record(gstream)
-        gdone[k % 2] = done
+        return done
+
+    # The host is on the critical path of a step (the library synchronises to validate the reads
+    # and to size the hit list), so the NCCL call is issued by a helper thread while the main
+    # thread is already launching the next step; ctypes releases the GIL inside the library.
+    import queue
+    import threading
+    gq = queue.Queue()
+    gissued = [threading.Event(), threading.Event()]
+    for e in gissued:
+        e.set()
+
+    def gather_worker():
+        torch.cuda.set_device(dev)
+        while True:
+            item = gq.get()
+            if item is None:
+                return
+            k, ready = item
+            gdone[k % 2] = gather_issue(k, ready)
+            gissued[k % 2].set()
+
+    gthread = None
+    if world > 1 and args.exchange == "nccl" and not os.environ.get("RCP_BENCH_INLINE_GATHER"):
+        gthread = threading.Thread(target=gather_worker, daemon=True)
+        gthread.start()
+
+    def gather_drain():
+        for e in gissued:
+            e.wait()
+
+    def gather_step(k=0):
+        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) and their
+        placement into the full column-major matrix.  It runs on its own stream, behind the bin
+        kernel of this step and beside the next step's kernels: the output matrix is double
+        buffered (step k writes buffer k % 2), so only the gather of step k - 2 must have finished
+        before step k may overwrite its buffer."""
+        if world == 1 or os.environ.get("RCP_BENCH_NO_GATHER"):
+            return
+        if "peer" in out_box:               # the rows are already in place: order the stores
+            if args.fence == "step":
+                with torch.cuda.stream(stream):
+                    out_box["peer"].fence()
+            return
+        ready = torch.cuda.Event()
+        ready.record(stream)                # the bin kernel of this step (library stream)
+        if gthread is None:
+            gdone[k % 2] = gather_issue(k, ready)
+        else:
+            gissued[k % 2].clear()
+            gq.put((k, ready))
 
     def barrier():
+        gather_drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -401,6 +440,7 @@ def run_b200(args):
         device_step(k)
         gather_step(k)
     if world > 1:
+        gather_drain()
         for ev in gdone:                    # the timed region ends when the last gathers have landed
             if ev is not None:
                 stream.wait_event(ev)
@@ -653,6 +693,9 @@ def run_b200(args):
             out["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(out))
     if world > 1:
+        if gthread is not None:
+            gq.put(None)
+            gthread.join()
         if "peer" in out_box:
             out_box["peer"].close()
         dist.barrier()

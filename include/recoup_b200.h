@@ -209,6 +209,36 @@ int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom,
  * Exposed so the hand-written sort can be tested directly against a host sort. */
 int rcp_sort_keys_u32(uint32_t* keys, int64_t n, int key_bits, int mem);
 
+/* ---------------------------------------------------------------- matrix consumers -------- */
+/* The reductions recoup's plotting side runs over a finished `$profile`, on the
+ * matrix where rcp_profile_matrix left it: column-major n_rows x n_cols, leading dimension ld,
+ * `mem` says where m AND the outputs live (rcp_matrix_quantile's probs/out are always host).
+ *
+ * rcp_matrix_col_profile: the average curve and its band of calcPlotProfiles (plot.R:949-990):
+ *   center = apply(x, 2, mean)   spread = apply(x, 2, sd)     (stat = RCP_STAT_MEAN)
+ *   center = apply(x, 2, median) spread = apply(x, 2, mad)    (stat = RCP_STAT_MEDIAN; mad's
+ *   constant 1.4826); log2_scale != 0 first maps x <- log2(x + 1) (plot.R:953-956).  The caller
+ *   forms upper/lower = center +- spread.  sd of a single row is NaN (R: NA).
+ * rcp_matrix_row_stat: apply(x, 1, sum | max | mean), the ordering values of orderProfiles
+ *   (plot.R:1076-1081, 1110-1131, 1135-1146; the max variant's sample() among tied maxima
+ *   returns the same value whichever it picks).
+ * rcp_order: sort(v, decreasing, index.return=TRUE)$ix (plot.R:1038-1041,1100-1103): 1-based,
+ *   ties keep their input order in both directions (R's default radix method), NaN/NA dropped:
+ *   *n_out entries of ix are valid (R drops them: na.last = NA).
+ * rcp_matrix_quantile: quantile(x, probs), type 7, over every cell (plot.R:519,536); a NaN
+ *   anywhere is RCP_ERR_DATA like R's error without na.rm. */
+#define RCP_ROW_SUM 0
+#define RCP_ROW_MAX 1
+#define RCP_ROW_MEAN 2
+int rcp_matrix_col_profile(const double* m, int64_t n_rows, int64_t n_cols, int64_t ld, int stat,
+                           int log2_scale, int mem, double* center /* n_cols */,
+                           double* spread /* n_cols */);
+int rcp_matrix_row_stat(const double* m, int64_t n_rows, int64_t n_cols, int64_t ld, int what, int mem,
+                        double* out /* n_rows */);
+int rcp_order(const double* v, int64_t n, int decreasing, int mem, int32_t* ix /* n */, int64_t* n_out);
+int rcp_matrix_quantile(const double* m, int64_t n_rows, int64_t n_cols, int64_t ld, const double* probs,
+                        int k, int mem, double* out /* k, host */);
+
 /* ---------------------------------------------------------------- multi-GPU helper -------- */
 /* Scatter a row block into the gathered matrix: dst[row_index[i] + c*ld_dst] =
  * src[i + c*ld_src] for i < n_rows, c < n_cols (all pointers on the device).  Used after the

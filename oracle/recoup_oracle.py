@@ -516,6 +516,90 @@ def linear_factors(lib_sizes, normalize="linear", sample_to=None):
 # --------------------------------------------------------------------------------------------
 # Brute-force definition used as the property-test ground truth
 # --------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# Consumers of the profile matrix                                  R/plot.R:513-545,949-1150
+# --------------------------------------------------------------------------------------------
+def r_mean(x):
+    """base R mean(): long-double sum / n, then one refinement pass (summary.c, real_mean)."""
+    x = np.asarray(x, dtype=np.longdouble)
+    n = x.shape[0]
+    s = x.sum() / n
+    s += (x - s).sum() / n
+    return float(s)
+
+
+def r_median(x):
+    x = np.sort(np.asarray(x, dtype=np.float64))
+    n = x.shape[0]
+    if n and np.isnan(x[-1]):
+        return float("nan")
+    return float(x[(n - 1) // 2]) if n % 2 else float((x[n // 2 - 1] + x[n // 2]) / 2.0)
+
+
+def plot_profile(profile, avgfun="mean", scale="natural"):
+    """calcPlotProfiles without smoothing (plot.R:976-990): apply(x$profile, 2, avgfun) and the
+    band  profile +- sd  (mean) or  +- mad  (median; stats::mad constant 1.4826), after
+    x <- log2(x + 1) when signalScale is "log2" (plot.R:978-981)."""
+    x = np.asarray(profile, dtype=np.float64)
+    if scale == "log2":
+        x = np.log2(x + 1.0)
+    n = x.shape[0]
+    center = np.empty(x.shape[1])
+    spread = np.empty(x.shape[1])
+    for j in range(x.shape[1]):
+        col = x[:, j]
+        if avgfun == "mean":
+            m = r_mean(col)
+            center[j] = m
+            d = col.astype(np.longdouble) - np.longdouble(m)
+            spread[j] = float(np.sqrt((d * d).sum() / (n - 1))) if n > 1 else float("nan")
+        else:
+            m = r_median(col)
+            center[j] = m
+            spread[j] = 1.4826 * r_median(np.abs(col - m))
+    return {"profile": center, "upper": center + spread, "lower": center - spread}
+
+
+def row_order_values(profile, what):
+    """apply(x$profile, 1, sum | max | mean) (plot.R:1080, 1122-1129, 1144); `what` is the
+    prefix of orderBy$what ("sum", "max", "avg")."""
+    x = np.asarray(profile, dtype=np.float64)
+    if what == "sum":
+        return np.array([float(np.asarray(r, dtype=np.longdouble).sum()) for r in x])
+    if what == "max":
+        return x.max(axis=1)
+    if what == "avg":
+        return np.array([r_mean(r) for r in x])
+    raise ValueError(what)
+
+
+def r_sort_index(v, decreasing=False):
+    """sort(v, decreasing, index.return=TRUE)$ix (plot.R:1100-1103): 1-based, NA dropped, ties in
+    input order both ways (order(method = "radix"), the default since R 3.3)."""
+    v = np.asarray(v, dtype=np.float64)
+    keep = np.flatnonzero(~np.isnan(v))
+    key = -v[keep] if decreasing else v[keep]
+    return keep[np.argsort(key + 0.0, kind="stable")] + 1
+
+
+def r_quantile7(x, probs):
+    """stats::quantile(x, probs, type = 7) (plot.R:519,536)."""
+    x = np.sort(np.asarray(x, dtype=np.float64).ravel())
+    if x.shape[0] and np.isnan(x[-1]):
+        raise ValueError("missing values and NaN's not allowed if 'na.rm' is FALSE")
+    n = x.shape[0]
+    out = []
+    for p in np.atleast_1d(probs):
+        index = (n - 1) * float(p)
+        lo, hi = int(math.floor(index)), int(math.ceil(index))
+        q = x[lo]
+        h = index - lo
+        if index > lo and x[hi] != q:
+            q = (1.0 - h) * q + h * x[hi]
+        out.append(float(q))
+    return np.array(out)
+
+
 def brute_coverage(read_start, read_end, lo, hi):
     """cov[p] = #{reads: start <= p <= end} for p in [lo, hi] -- O(N * L), tiny inputs only."""
     out = np.zeros(hi - lo + 1, dtype=np.int64)

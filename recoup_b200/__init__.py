@@ -7,6 +7,8 @@ compute call requires a B200 -- there is no CPU fallback.
 """
 from . import _lib
 from ._lib import RecoupError, init, set_coverage_path, shutdown
+from .consumers import (calcPlotProfiles, colProfile, heatmapScale, matrixQuantile, orderProfiles,
+                        rowStat, sortIndex)
 from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, coverageRnaRef,
                        device_reads, set_verbose)
 from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, haveEqualLengths,
@@ -14,8 +16,9 @@ from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, have
 from .ranges import GRanges, GRangesList, Rle, getFlankingRanges, getRegionalRanges
 
 __all__ = [
-    "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "Rle", "getRegionalRanges",
-    "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
+    "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "Rle",
+    "getRegionalRanges", "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
-    "haveEqualLengths", "ProfileMatrix", "set_verbose",
+    "haveEqualLengths", "ProfileMatrix", "set_verbose", "calcPlotProfiles", "orderProfiles",
+    "heatmapScale", "colProfile", "rowStat", "sortIndex", "matrixQuantile",
 ]

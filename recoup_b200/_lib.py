@@ -46,6 +46,11 @@ SIGNATURES = {
     "rcp_r_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "rcp_r_rank_table": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip]),
     "rcp_reads_load": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, _ip]),
+    "rcp_matrix_col_profile": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                         _vp, _vp]),
+    "rcp_matrix_row_stat": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp]),
+    "rcp_order": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
+    "rcp_matrix_quantile": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, C.c_int, _vp]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
                                      C.c_int, C.c_int, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),

@@ -545,6 +545,126 @@ def test_seqnames_runs_errors(gpu):
 
 
 # ------------------------------------------------------------------------------------------------
+# consumers of the matrix
+# ------------------------------------------------------------------------------------------------
+def _consumer_matrices():
+    rng = np.random.default_rng(77)
+    a = rng.gamma(0.6, 3.0, size=(2001, 37))
+    a[rng.random(a.shape) < 0.3] = 0.0                    # many ties at zero
+    a[5] = 0.0
+    b = np.round(rng.normal(0.0, 2.0, size=(64, 5)), 1)   # negatives, ties, even row count
+    b[3, 2] = -0.0
+    return [a, b, rng.random((1, 4)), rng.random((7, 1))]
+
+
+@pytest.mark.parametrize("avgfun", ["mean", "median"])
+@pytest.mark.parametrize("scale", ["natural", "log2"])
+def test_plot_profiles_match_the_oracle(gpu_auto, avgfun, scale):
+    rb = gpu_auto
+    mats = [m for m in _consumer_matrices() if scale == "natural" or m.min() >= 0]
+    opts = {"plotParams": {"sumStat": avgfun, "signalScale": scale, "smooth": False}}
+    got = rb.calcPlotProfiles([{"profile": m} for m in mats], opts)
+    for m, g in zip(mats, got):
+        want = O.plot_profile(m, avgfun, scale)
+        for k in ("profile", "upper", "lower"):
+            assert np.allclose(g[k], want[k], rtol=1e-12, atol=1e-12, equal_nan=True), (k, m.shape)
+    with pytest.raises(NotImplementedError):
+        rb.calcPlotProfiles([{"profile": mats[0]}], {"plotParams": {"smooth": True}})
+
+
+@pytest.mark.parametrize("what", ["sum1", "max2", "avg1", "suma", "maxa", "avga", "none"])
+@pytest.mark.parametrize("order", ["descending", "ascending"])
+def test_order_profiles_match_the_oracle(gpu_auto, what, order):
+    rb = gpu_auto
+    rng = np.random.default_rng(78)
+    a = _consumer_matrices()[0]
+    b = a[rng.permutation(a.shape[0])] * 1.5
+    inp = [{"profile": a}, {"profile": b}]
+    got = rb.orderProfiles(inp, {"orderBy": {"what": what, "order": order}})
+    if what == "none":
+        assert got["ix"].tolist() == list(range(1, a.shape[0] + 1))
+        return
+    kind, ref = what[:3], what[-1]
+    if ref == "a":
+        per = np.stack([O.row_order_values(x["profile"], kind) for x in inp], axis=1)
+        val = O.row_order_values(per, kind)
+    else:
+        val = O.row_order_values(inp[int(ref) - 1]["profile"], kind)
+    want = O.r_sort_index(val, order == "descending")
+    # the ordering values agree to rounding; exact ties (zero rows) must come out in input order
+    assert np.allclose(rb.rowStat(inp[0]["profile"], kind), O.row_order_values(a, kind), rtol=1e-13)
+    gv = val[got["ix"] - 1]
+    assert np.allclose(gv, val[want - 1], rtol=1e-12)
+    zero = np.flatnonzero(val == 0) + 1
+    assert [i for i in got["ix"] if val[i - 1] == 0] == zero.tolist()
+    assert sorted(got["ix"].tolist()) == list(range(1, a.shape[0] + 1))
+
+
+def test_sort_index_ties_nan_and_custom_order(gpu_auto):
+    rb = gpu_auto
+    v = np.array([3, 1, 2, 1, np.nan, 3.0, -0.0, 0.0, -np.inf, np.inf])
+    for dec in (False, True):
+        got = rb.sortIndex(v, dec)
+        assert got["ix"].tolist() == O.r_sort_index(v, dec).tolist()
+        assert np.array_equal(got["x"], v[got["ix"] - 1])
+    got = rb.orderProfiles([], {"orderBy": {"custom": [5.0, 7.0, 5.0], "order": "descending"}})
+    assert got["ix"].tolist() == [2, 1, 3]
+    assert rb.sortIndex(np.zeros(0))["ix"].shape == (0,)
+    rng = np.random.default_rng(3)
+    big = np.round(rng.normal(size=300001), 2)
+    assert np.array_equal(rb.sortIndex(big, True)["ix"], O.r_sort_index(big, True))
+
+
+def test_matrix_quantile_and_heatmap_scale(gpu_auto):
+    rb = gpu_auto
+    from recoup_b200 import _lib
+    mats = _consumer_matrices()
+    probs = [0.0, 0.1, 0.5, 0.95, 0.96, 0.999, 1.0]
+    for m in mats:
+        assert np.allclose(rb.matrixQuantile(m, probs), O.r_quantile7(m, probs), rtol=1e-14, atol=0)
+    inp = [{"profile": mats[0]}, {"profile": mats[0] * 2.0}]
+    q95 = float(O.r_quantile7(mats[0], [0.95])[0])
+    assert np.allclose(rb.heatmapScale(inp, "common", 0.5), [q95, q95])
+    assert np.allclose(rb.heatmapScale(inp, "each", 1.0), [q95, 2 * q95])
+    sparse = np.zeros((100, 10))
+    sparse[0, :3] = [4.0, 5.0, 6.0]                      # 0.95 .. 0.99 quantiles are 0: ladder climbs
+    want = [q for q in O.r_quantile7(sparse, [0.95, 0.96, 0.97, 0.98, 0.99, 0.995, 0.999]) if q != 0][0]
+    assert np.allclose(rb.heatmapScale([{"profile": sparse}], "each"), [want])
+    bad = mats[1].copy()
+    bad[0, 0] = np.nan
+    with pytest.raises(rb.RecoupError) as ei:
+        rb.matrixQuantile(bad, [0.5])
+    assert ei.value.code == _lib.RCP_ERR_DATA
+    # a row block of a wider matrix: leading dimension > rows, straight through the C ABI
+    big = np.asfortranarray(mats[0])
+    n = 500
+    out = np.empty(big.shape[1])
+    sp = np.empty(big.shape[1])
+    _lib.check(_lib.lib.rcp_matrix_col_profile(big.ctypes.data_as(C.c_void_p), n, big.shape[1],
+                                               big.shape[0], 0, 0, _lib.MEM_HOST,
+                                               out.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p)))
+    want = O.plot_profile(big[:n], "mean")
+    assert np.allclose(out, want["profile"], rtol=1e-12) and np.allclose(out + sp, want["upper"], rtol=1e-12)
+
+
+def test_consumers_on_the_fixture_profile(gpu_auto, fixture_data):
+    """end to end: fixture reads -> coverage -> profile -> curve, order, colour limit"""
+    rb = gpu_auto
+    _, g_reads = fixture_reads(fixture_data, 0)
+    _, g_genes = fixture_genes(fixture_data)
+    sample = [dict(id="s", name="s", ranges=g_reads)]
+    rb.coverageRef(sample, g_genes, "tss", (2000, 2000))
+    rb.profileMatrix(sample, (2000, 2000), dict(flankBinSize=0, regionBinSize=100, sumStat="mean",
+                                                 interpolation="auto"))
+    m = np.asarray(sample[0]["profile"])
+    curve = rb.calcPlotProfiles(sample, {"plotParams": {"sumStat": "mean", "signalScale": "natural"}})[0]
+    assert np.allclose(curve["profile"], O.plot_profile(m)["profile"], rtol=1e-12)
+    got = rb.orderProfiles(sample, {"orderBy": {"what": "sum1", "order": "descending"}})
+    assert got["ix"].tolist() == O.r_sort_index(O.row_order_values(m, "sum"), True).tolist()
+    assert np.allclose(rb.heatmapScale(sample, "common"), O.r_quantile7(m, [0.95]))
+
+
+# ------------------------------------------------------------------------------------------------
 # the hand-written index sort, directly
 # ------------------------------------------------------------------------------------------------
 def _gpu_sort(keys, bits):

@@ -171,3 +171,30 @@ def test_profile_matrix_paths():
     assert u2.shape == (3, 5 + 4 + 5) and (u2[0, :5] == np.arange(5)).all()
     assert (u2[1, -5:] == np.arange(21, 26)).all() and (u2[2] == 0).all()
     assert O.r_round(2.5) == 2 and O.r_round(3.5) == 4 and O.r_round(33.33) == 33
+
+
+def test_consumer_restatements_known_answers():
+    """R known answers (base R semantics): sort(index.return) is stable and drops NA; quantile is
+    type 7; mad uses the constant 1.4826; mean refines its first pass."""
+    v = np.array([3, 1, 2, 1, np.nan, 3.0])
+    assert O.r_sort_index(v).tolist() == [2, 4, 3, 1, 6]
+    assert O.r_sort_index(v, decreasing=True).tolist() == [1, 6, 3, 2, 4]
+    # quantile(1:10, c(.1,.5,.95)) = 1.90 5.50 9.55;  quantile(c(0,0,0,4), .95) = 3.4
+    assert np.allclose(O.r_quantile7(np.arange(1, 11), [0.1, 0.5, 0.95]), [1.9, 5.5, 9.55])
+    assert np.allclose(O.r_quantile7([0, 0, 0, 4], [0.95]), [3.4])
+    with pytest.raises(ValueError):
+        O.r_quantile7([1.0, np.nan], [0.5])
+    # x = matrix(c(1,2,3,4, 10,20,30,50), 4): colMeans 2.5 27.5; sd 1.290994 17.07825;
+    # median 2.5 25; mad 1.4826 14.826
+    x = np.array([[1, 10], [2, 20], [3, 30], [4, 50.0]])
+    p = O.plot_profile(x, "mean")
+    assert np.allclose(p["profile"], [2.5, 27.5])
+    assert np.allclose(p["upper"] - p["profile"], [1.2909944487, 17.0782512766])
+    p = O.plot_profile(x, "median")
+    assert np.allclose(p["profile"], [2.5, 25.0]) and np.allclose(p["profile"] - p["lower"], [1.4826, 14.826])
+    p = O.plot_profile(x, "mean", "log2")
+    assert np.allclose(p["profile"], np.log2(x + 1).mean(0))
+    assert O.row_order_values(x, "sum").tolist() == [11, 22, 33, 54]
+    assert O.row_order_values(x, "max").tolist() == [10, 20, 30, 50]
+    assert np.allclose(O.row_order_values(x, "avg"), [5.5, 11, 16.5, 27])
+    assert O.r_median([5, 1, 3]) == 3 and O.r_median([4, 1, 3, 2]) == 2.5
