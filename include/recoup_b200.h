@@ -134,6 +134,29 @@ int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const 
 int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, const int32_t* run_len,
                        const int32_t* start, const int32_t* end, const int8_t* strand, int n_chrom,
                        const int64_t* chrom_len, int frag_len, int mem, int* reads_out);
+/* The read-import step right before the path (preprocessRanges / readBam, ranges.R:1-65,
+ * 111-134), for reads that are already decoded:
+ *
+ * rcp_reads_width_quantile  quantile(width(reads), prob), type 7 -- the cut of spliceAction =
+ *   "remove" (ranges.R:126-127) -- and how many reads are not wider than it (the library size
+ *   that "downsample" / "sampleto" then draw from).
+ * rcp_r_sample_sorted  set.seed(seed) ONCE, then sort(sample(n[c], k[c])) for c = 0..n_calls-1
+ *   from the one RNG stream, as the lapply over samples does (ranges.R:38-41, 55-58); sample()
+ *   dispatches like base R's sample.int: the hash variant (redraw duplicates, at most 100
+ *   tries) when n > 1e7 and k <= n/2, else the partial Fisher-Yates loop.  Serial by nature
+ *   (one Mersenne-Twister stream): host code.  out = the blocks one after the other, 1-based.
+ * rcp_reads_load_select  reads[-which(width > max_width)][idx] (ranges.R:128-130 then 43,62) and
+ *   rcp_reads_load of the result, the selection done on the device.  max_width < 0: no width
+ *   filter; idx NULL: keep every surviving read, else k 1-based positions among the SURVIVING
+ *   reads in their original order.  *n_kept_out = reads that survive the width filter. */
+int rcp_reads_width_quantile(int64_t n, const int32_t* start, const int32_t* end, double prob, int mem,
+                             double* quantile_out /* host */, int64_t* n_le_out /* host */);
+int rcp_r_sample_sorted(int seed, int sample_kind, int n_calls, const int64_t* n, const int64_t* k,
+                        int32_t* out /* host, sum(k) */);
+int rcp_reads_load_select(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                          const int8_t* strand, double max_width, int64_t k, const int32_t* idx,
+                          int n_chrom, const int64_t* chrom_len, int frag_len, int mem,
+                          int64_t* n_kept_out, int* reads_out);
 int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes);
 int rcp_reads_free(int reads);
 

@@ -109,6 +109,19 @@ class RRandom:
             raise ValueError("cannot take a sample larger than the population")
         if k < 0:
             raise ValueError("invalid 'size' argument")
+        if n > 1e7 and k <= n / 2:
+            # sample.int's hash variant (R: .Internal(sample2(n, size)), do_sample2 in
+            # src/main/unique.c): draw, redraw on a duplicate, at most 100 tries
+            seen = set()
+            out = []
+            for _ in range(k):
+                for _try in range(100):
+                    v = self.unif_index(n) + 1
+                    if v not in seen:
+                        break
+                seen.add(v)
+                out.append(v)
+            return out
         x = list(range(n))
         out = []
         for _ in range(k):

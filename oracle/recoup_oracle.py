@@ -517,6 +517,28 @@ def linear_factors(lib_sizes, normalize="linear", sample_to=None):
 # Brute-force definition used as the property-test ground truth
 # --------------------------------------------------------------------------------------------
 # --------------------------------------------------------------------------------------------
+# Read import after decoding                                        R/ranges.R:1-65,111-134
+# --------------------------------------------------------------------------------------------
+def splice_remove(start, end, sq=0.75):
+    """readBam(sa = "remove") (ranges.R:125-133): qu = quantile(width(reads), sq); the reads wider
+    than qu are excluded.  Returns the boolean keep mask and qu."""
+    width = np.asarray(end, dtype=np.int64) - np.asarray(start, dtype=np.int64) + 1
+    qu = float(r_quantile7(width, [sq])[0])
+    return ~(width > qu), qu
+
+
+def downsample_indices(lib_sizes, normalize, seed=42, sample_to=1000000, sample_kind="Rejection"):
+    """preprocessRanges normalize = "downsample" / "sampleto" (ranges.R:31-63): ONE set.seed, then
+    sort(sample(libSize, s)) per sample, s = min(libSizes) or sampleTo.  1-based indices;
+    None for "none" / "linear"."""
+    if normalize in ("none", "linear"):
+        return [None for _ in lib_sizes]
+    s = min(lib_sizes) if normalize == "downsample" else int(sample_to)
+    rng = RRandom(seed, sample_kind)
+    return [np.sort(np.asarray(rng.sample_int(int(n), s), dtype=np.int64)) for n in lib_sizes]
+
+
+# --------------------------------------------------------------------------------------------
 # Consumers of the profile matrix                                  R/plot.R:513-545,949-1150
 # --------------------------------------------------------------------------------------------
 def r_mean(x):

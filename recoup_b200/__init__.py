@@ -11,6 +11,7 @@ from .consumers import (calcPlotProfiles, colProfile, heatmapScale, matrixQuanti
                         rowStat, sortIndex)
 from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, coverageRnaRef,
                        device_reads, set_verbose)
+from .preprocess import SelectedGRanges, preprocessRanges, readRanges, sampleSorted, widthQuantile
 from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, haveEqualLengths,
                       profileMatrix)
 from .ranges import GRanges, GRangesList, Rle, getFlankingRanges, getRegionalRanges
@@ -20,5 +21,6 @@ __all__ = [
     "getRegionalRanges", "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
     "haveEqualLengths", "ProfileMatrix", "set_verbose", "calcPlotProfiles", "orderProfiles",
-    "heatmapScale", "colProfile", "rowStat", "sortIndex", "matrixQuantile",
+    "heatmapScale", "colProfile", "rowStat", "sortIndex", "matrixQuantile", "preprocessRanges",
+    "readRanges", "SelectedGRanges", "sampleSorted", "widthQuantile",
 ]

@@ -51,6 +51,10 @@ SIGNATURES = {
     "rcp_matrix_row_stat": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp]),
     "rcp_order": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
     "rcp_matrix_quantile": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, C.c_int, _vp]),
+    "rcp_reads_width_quantile": (C.c_int, [C.c_int64, _vp, _vp, C.c_double, C.c_int, _f64p, _i64p]),
+    "rcp_r_sample_sorted": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p, _i64p, _vp]),
+    "rcp_reads_load_select": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_double, C.c_int64, _vp, C.c_int,
+                                        _i64p, C.c_int, C.c_int, _i64p, _ip]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
                                      C.c_int, C.c_int, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),

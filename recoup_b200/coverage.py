@@ -54,6 +54,25 @@ class DeviceReads:
                              "vector, coverage.R:201)")
         _lib.ensure_init()
         h = C.c_int(0)
+        if getattr(gr, "parent", None) is not None:
+            # a selection of another GRanges (preprocess.SelectedGRanges): the device applies it
+            p = gr.parent
+            arr = [np.ascontiguousarray(a, dtype=t) for a, t in
+                   ((p.seqnames, np.int32), (p.start, np.int32), (p.end, np.int32), (p.strand, np.int8))]
+            clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+            n_kept = C.c_int64(0)
+            k = 0 if gr.idx is None else gr.idx.shape[0]
+            _lib_check(_lib.lib.rcp_reads_load_select(
+                len(p), _ptr(arr[0]), _ptr(arr[1]), _ptr(arr[2]), _ptr(arr[3]),
+                -1.0 if gr.max_width is None else float(gr.max_width), k,
+                None if gr.idx is None else _ptr(gr.idx), clen.shape[0],
+                clen.ctypes.data_as(C.POINTER(C.c_int64)), int(frag_len), _lib.MEM_HOST,
+                C.byref(n_kept), C.byref(h)))
+            self.handle = h.value
+            self.n = len(gr)
+            self.seqlevels = list(gr.seqlevels)
+            self._fin = weakref.finalize(self, _free_reads, self.handle)
+            return
         start = np.ascontiguousarray(gr.start, dtype=np.int32)
         end = np.ascontiguousarray(gr.end, dtype=np.int32)
         strand = np.ascontiguousarray(gr.strand, dtype=np.int8)

@@ -1,4 +1,5 @@
 // C ABI of librecoup_b200.so (include/recoup_b200.h): context, handle tables, argument checks.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -179,6 +180,10 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
                     const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
                     const int64_t* chrom_len, int frag_len, int mem);
+int reads_load_select_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, double max_width, int64_t k,
+                           const int32_t* idx, int n_chrom, const int64_t* chrom_len, int frag_len,
+                           int mem, int64_t* n_kept_out);
 int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int ignore_strand,
                     int strand_filter, int mem, Coverage* cv);
@@ -490,6 +495,47 @@ int rcp_r_sample(int n, int k, int seed, int sample_kind, int* out) {
     return RCP_OK;
 }
 
+// sample.int(n, k) as base R dispatches it: the hash variant (do_sample2: draw, redraw on a
+// duplicate, at most 100 tries) when n > 1e7 and k <= n/2, else the partial Fisher-Yates loop.
+static void r_sample_int(RRng& rng, int64_t n, int64_t k, int32_t* out) {
+    if (n > 10000000 && k <= n / 2) {
+        std::vector<uint64_t> seen((size_t)((n + 63) / 64), 0);
+        for (int64_t i = 0; i < k; i++) {
+            uint32_t v = 0;
+            for (int j = 0; j < 100; j++) {
+                v = rng.index((uint32_t)n);
+                if (!((seen[v >> 6] >> (v & 63)) & 1ull)) break;
+            }
+            seen[v >> 6] |= 1ull << (v & 63);
+            out[i] = (int32_t)(v + 1);
+        }
+        return;
+    }
+    std::vector<int> x((size_t)n);
+    rng.sample((int)n, (int)k, x.data(), out);
+}
+
+int rcp_r_sample_sorted(int seed, int sample_kind, int n_calls, const int64_t* n, const int64_t* k,
+                        int32_t* out) {
+    if (sample_kind != RCP_SAMPLE_REJECTION && sample_kind != RCP_SAMPLE_ROUNDING)
+        return fail(RCP_ERR_ARG, "unknown sample kind %d", sample_kind);
+    if (n_calls < 0 || (n_calls > 0 && (n == nullptr || k == nullptr)))
+        return fail(RCP_ERR_ARG, "rcp_r_sample_sorted: bad argument");
+    std::unique_ptr<RRng> rng(new RRng);
+    rng->seed((uint32_t)seed, sample_kind);
+    int64_t at = 0;
+    for (int c = 0; c < n_calls; c++) {
+        if (n[c] < 0 || k[c] < 0 || k[c] > n[c] || n[c] > 0x7fffffff)
+            return fail(RCP_ERR_ARG, "cannot take a sample of %lld from a population of %lld",
+                        (long long)k[c], (long long)n[c]);
+        if (k[c] > 0 && out == nullptr) return fail(RCP_ERR_ARG, "out is NULL");
+        r_sample_int(*rng, n[c], k[c], out + at);
+        std::sort(out + at, out + at + k[c]);
+        at += k[c];
+    }
+    return RCP_OK;
+}
+
 int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out) {
     if (n < 0) return fail(RCP_ERR_ARG, "n < 0");
     std::vector<int> perm((size_t)n);
@@ -536,6 +582,30 @@ int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, cons
     std::unique_ptr<ReadsIdx> r(new ReadsIdx());
     int rc = reads_load_impl(*r, n, nullptr, n_runs, run_chrom, run_len, start, end, strand, n_chrom,
                              chrom_len, frag_len, mem);
+    if (rc != RCP_OK) {
+        reads_release(*r);
+        return rc;
+    }
+    const int h = g_next_handle++;
+    g_reads[h] = std::move(r);
+    *reads_out = h;
+    return RCP_OK;
+}
+
+int rcp_reads_load_select(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                          const int8_t* strand, double max_width, int64_t k, const int32_t* idx,
+                          int n_chrom, const int64_t* chrom_len, int frag_len, int mem,
+                          int64_t* n_kept_out, int* reads_out) {
+    RCP_TRY(require_ready());
+    if (n < 0 || k < 0 || n_chrom < 1 || chrom_len == nullptr || reads_out == nullptr || frag_len < 0)
+        return fail(RCP_ERR_ARG, "rcp_reads_load_select: bad scalar argument");
+    if (n > 0 && (chrom == nullptr || start == nullptr || end == nullptr))
+        return fail(RCP_ERR_ARG, "rcp_reads_load_select: NULL array");
+    if (n >= 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "rcp_reads_load_select: n >= 2^31 - 1");
+    if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
+    std::unique_ptr<ReadsIdx> r(new ReadsIdx());
+    int rc = reads_load_select_impl(*r, n, chrom, start, end, strand, max_width, k, idx, n_chrom,
+                                    chrom_len, frag_len, mem, n_kept_out);
     if (rc != RCP_OK) {
         reads_release(*r);
         return rc;

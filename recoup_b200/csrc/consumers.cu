@@ -157,6 +157,22 @@ cell_keys_kernel(const double* __restrict__ m, int64_t n_rows, int64_t n_cols, i
     if (col_id) col_id[i] = (uint32_t)c;
 }
 
+// widths of reads as keys; also used to count the reads not wider than a limit
+__global__ void __launch_bounds__(TPB)
+width_keys_kernel(int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                  unsigned long long* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) keys[i] = ordered_key((double)end[i] - (double)start[i] + 1.0);
+}
+__global__ void __launch_bounds__(TPB)
+count_le_kernel(int64_t n, const unsigned long long* __restrict__ keys, const double* __restrict__ limit,
+                unsigned long long* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    const bool le = i < n && !(key_value(keys[i]) > *limit);
+    const unsigned m = __ballot_sync(0xffffffffu, le);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 // median of every sorted column segment (R: mean of the two middle values for even n)
 __global__ void __launch_bounds__(TPB)
 col_median_kernel(const unsigned long long* __restrict__ sorted, int64_t n_rows, int64_t n_cols,
@@ -400,6 +416,49 @@ int rcp_order(const double* v, int64_t n, int decreasing, int mem, int32_t* ix, 
     dfree(idx);
     dfree(n_nan);
     if (rc == RCP_OK && n_out) *n_out = n - (int64_t)h_nan;
+    return rc;
+}
+
+int rcp_reads_width_quantile(int64_t n, const int32_t* start, const int32_t* end, double prob, int mem,
+                             double* quantile_out, int64_t* n_le_out) {
+    RCP_TRY(require_ready());
+    if (n <= 0 || start == nullptr || end == nullptr || quantile_out == nullptr ||
+        (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE))
+        return fail(RCP_ERR_ARG, "width_quantile: bad argument");
+    if (!(prob >= 0.0 && prob <= 1.0)) return fail(RCP_ERR_ARG, "width_quantile: 'probs' outside [0,1]");
+    if (n > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "width_quantile: more than 2^31-1 reads");
+    DevIn<int32_t> d_start, d_end;
+    RCP_TRY(d_start.init(start, (size_t)n, mem));
+    RCP_TRY(d_end.init(end, (size_t)n, mem));
+    unsigned long long* keys = nullptr;
+    unsigned long long* count = nullptr;
+    double *d_prob = nullptr, *d_out = nullptr;
+    RCP_TRY(dalloc(&keys, (size_t)n));
+    RCP_TRY(dalloc(&count, 1));
+    RCP_TRY(dalloc(&d_prob, 1));
+    RCP_TRY(dalloc(&d_out, 1));
+    RCP_CUDA(cudaMemsetAsync(count, 0, 8, g_ctx.stream));
+    RCP_CUDA(cudaMemcpyAsync(d_prob, &prob, 8, cudaMemcpyHostToDevice, g_ctx.stream));
+    const unsigned blocks = (unsigned)((n + TPB - 1) / TPB);
+    width_keys_kernel<<<blocks, TPB, 0, g_ctx.stream>>>(n, d_start.ptr, d_end.ptr, keys);
+    RCP_LAUNCHED();
+    int rc = sort_keys_u64(keys, n);
+    unsigned long long h_count = 0;
+    if (rc == RCP_OK) {
+        quantile_kernel<<<1, 64, 0, g_ctx.stream>>>(keys, n, d_prob, 1, d_out);
+        count_le_kernel<<<blocks, TPB, 0, g_ctx.stream>>>(n, keys, d_out, count);
+        g_ctx.launches += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(quantile_out, d_out, 8, cudaMemcpyDeviceToHost, g_ctx.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_count, count, 8, cudaMemcpyDeviceToHost, g_ctx.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+        if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "width_quantile failed: %s", cudaGetErrorString(e));
+    }
+    dfree(keys);
+    dfree(count);
+    dfree(d_prob);
+    dfree(d_out);
+    if (rc == RCP_OK && n_le_out) *n_le_out = (int64_t)h_count;
     return rc;
 }
 

@@ -572,7 +572,7 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
         RCP_TRY(dalloc(&run_first, (size_t)n_runs + 1));
         RCP_TRY(dalloc(&d_chrom.owned, ((size_t)n + 3) & ~(size_t)3));
         d_chrom.ptr = d_chrom.owned;
-        rle_check_kernel<<<grid_for(n_runs), TPB, 0, g_ctx.stream>>>(n_runs, d_run_len.ptr, d_err);
+        rle_check_kernel<<<(unsigned)((n_runs + TPB - 1) / TPB), TPB, 0, g_ctx.stream>>>(n_runs, d_run_len.ptr, d_err);
         RCP_LAUNCHED();
         RCP_TRY(exclusive_scan_u32(reinterpret_cast<const uint32_t*>(d_run_len.ptr), run_first, n_runs,
                                    run_first + n_runs));
@@ -658,6 +658,129 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     }
     r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
     return RCP_OK;
+}
+
+// ---- ranges[-which(width > qu)][idx] followed by the load ----------------------
+namespace {
+
+__global__ void __launch_bounds__(TPB)
+keep_flags_kernel(int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                  double max_width, uint32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const double w = (double)end[i] - (double)start[i] + 1.0;
+    flag[i] = !(w > max_width);
+}
+
+// kept_pos[rank of read i among the kept] = i
+__global__ void __launch_bounds__(TPB)
+kept_positions_kernel(int64_t n, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank,
+                      uint32_t* __restrict__ kept_pos) {
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n && flag[i]) kept_pos[rank[i]] = (uint32_t)i;
+}
+
+// out[j] = in[ kept_pos[ idx[j] - 1 ] ]   (either level of indirection may be absent)
+__global__ void __launch_bounds__(TPB)
+select_gather_kernel(int64_t k, int64_t n_kept, const int32_t* __restrict__ idx,
+                     const uint32_t* __restrict__ kept_pos, const int32_t* __restrict__ chrom,
+                     const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                     const int8_t* __restrict__ strand, int32_t* __restrict__ o_chrom,
+                     int32_t* __restrict__ o_start, int32_t* __restrict__ o_end,
+                     int8_t* __restrict__ o_strand, unsigned int* __restrict__ err) {
+    const int64_t j = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (j >= k) return;
+    int64_t p = idx ? (int64_t)idx[j] - 1 : j;
+    if (p < 0 || p >= n_kept) {
+        atomicOr(err, 1u);
+        p = 0;
+    }
+    const int64_t i = kept_pos ? (int64_t)kept_pos[p] : p;
+    o_chrom[j] = chrom[i];
+    o_start[j] = start[i];
+    o_end[j] = end[i];
+    if (o_strand) o_strand[j] = strand[i];
+}
+
+}  // namespace
+
+int reads_load_select_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, double max_width, int64_t k,
+                           const int32_t* idx, int n_chrom, const int64_t* chrom_len, int frag_len,
+                           int mem, int64_t* n_kept_out) {
+    DevIn<int32_t> d_chrom, d_start, d_end, d_idx;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_chrom.init(chrom, (size_t)n, mem));
+    RCP_TRY(d_start.init(start, (size_t)n, mem));
+    RCP_TRY(d_end.init(end, (size_t)n, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)n, mem));
+    RCP_TRY(d_idx.init(idx, (size_t)k, mem));
+    const bool filter = max_width >= 0.0 && n > 0;
+    int64_t n_kept = n;
+    uint32_t *flag = nullptr, *rank = nullptr, *kept_pos = nullptr;
+    unsigned int* d_err = nullptr;
+    RCP_TRY(dalloc(&d_err, 1));
+    RCP_CUDA(cudaMemsetAsync(d_err, 0, 4, g_ctx.stream));
+    int rc = RCP_OK;
+    if (filter) {
+        StageTimer t(ST_INDEX_MAP);
+        rc = dalloc(&flag, (size_t)n);
+        if (rc == RCP_OK) rc = dalloc(&rank, (size_t)n + 1);
+        if (rc == RCP_OK) {
+            keep_flags_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, g_ctx.stream>>>(n, d_start.ptr, d_end.ptr, max_width, flag);
+            g_ctx.launches++;
+            rc = exclusive_scan_u32(flag, rank, n, rank + n);
+        }
+        uint32_t h_kept = 0;
+        if (rc == RCP_OK) {
+            cudaError_t e = cudaMemcpyAsync(&h_kept, rank + n, 4, cudaMemcpyDeviceToHost, g_ctx.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+            if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "width filter failed: %s", cudaGetErrorString(e));
+        }
+        n_kept = (int64_t)h_kept;
+        if (rc == RCP_OK) rc = dalloc(&kept_pos, (size_t)n_kept);
+        if (rc == RCP_OK && n_kept > 0) {
+            kept_positions_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, g_ctx.stream>>>(n, flag, rank, kept_pos);
+            g_ctx.launches++;
+        }
+    }
+    if (n_kept_out) *n_kept_out = n_kept;
+    const int64_t m = idx ? k : n_kept;                 // reads that reach the load
+    int32_t *o_chrom = nullptr, *o_start = nullptr, *o_end = nullptr;
+    int8_t* o_strand = nullptr;
+    if (rc == RCP_OK) rc = dalloc(&o_chrom, (size_t)m);
+    if (rc == RCP_OK) rc = dalloc(&o_start, (size_t)m);
+    if (rc == RCP_OK) rc = dalloc(&o_end, (size_t)m);
+    if (rc == RCP_OK && strand) rc = dalloc(&o_strand, (size_t)m);
+    unsigned int h_err = 0;
+    if (rc == RCP_OK && m > 0) {
+        if (n_kept == 0) {
+            rc = fail(RCP_ERR_DATA, "an index selects from an empty set of reads");
+        } else {
+            StageTimer t(ST_INDEX_MAP);
+            select_gather_kernel<<<(unsigned)((m + TPB - 1) / TPB), TPB, 0, g_ctx.stream>>>(
+                m, n_kept, d_idx.ptr, kept_pos, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, o_chrom,
+                o_start, o_end, o_strand, d_err);
+            g_ctx.launches++;
+            cudaError_t e = cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+            if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "read selection failed: %s", cudaGetErrorString(e));
+            if (rc == RCP_OK && h_err)
+                rc = fail(RCP_ERR_DATA, "a selection index is outside 1..%lld", (long long)n_kept);
+        }
+    }
+    if (rc == RCP_OK)
+        rc = reads_load_impl(r, m, o_chrom, 0, nullptr, nullptr, o_start, o_end, o_strand, n_chrom, chrom_len,
+                             frag_len, RCP_MEM_DEVICE);
+    dfree(flag);
+    dfree(rank);
+    dfree(kept_pos);
+    dfree(d_err);
+    dfree(o_chrom);
+    dfree(o_start);
+    dfree(o_end);
+    dfree(o_strand);
+    return rc;
 }
 
 }  // namespace rcp

@@ -545,6 +545,71 @@ def test_seqnames_runs_errors(gpu):
 
 
 # ------------------------------------------------------------------------------------------------
+# read import after the decode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("normalize", ["none", "downsample", "sampleto"])
+@pytest.mark.parametrize("splice", ["keep", "remove"])
+def test_preprocess_ranges_selection_on_the_device(gpu_auto, normalize, splice):
+    rb = gpu_auto
+    rng = np.random.default_rng(21)
+    clen = [40000, 9000]
+    libs = []
+    for n in (6000, 4500, 5200):
+        chrom, s, e, st = synth_reads(rng, n, clen, width=(20, 60))
+        long_ = rng.random(n) < 0.2                       # "spliced" reads: much wider
+        e = np.where(long_, np.minimum(e + rng.integers(200, 3000, size=n), np.asarray(clen)[chrom]), e)
+        libs.append((chrom, s, e.astype(s.dtype), st))
+    pp = {"normalize": normalize, "spliceAction": splice, "spliceRemoveQ": 0.75, "seed": 11,
+          "sampleTo": 3000}
+    inp = [{"name": "s%d" % i, "file": "s%d.bam" % i} for i in range(3)]
+
+    def reader(x):
+        c, s, e, st = libs[int(x["name"][1:])]
+        return rb.GRanges(c, s, e, strand=st, seqlevels=["c0", "c1"], seqlengths=clen)
+
+    rb.preprocessRanges(inp, pp, reader=reader)
+    # oracle: the same steps on numpy arrays
+    kept = []
+    for c, s, e, st in libs:
+        keep = O.splice_remove(s, e, 0.75)[0] if splice == "remove" else np.ones(len(s), bool)
+        kept.append([a[keep] for a in (c, s, e, st)])
+    idx = O.downsample_indices([len(k[0]) for k in kept], normalize, seed=11, sample_to=3000)
+    rc, rs, re_, rst = _regions(rng, 60, clen, [1, 100, 1024, 1025, 5000])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    for x, k, ix in zip(inp, kept, idx):
+        sel = k if ix is None else [a[ix - 1] for a in k]
+        assert len(x["ranges"]) == len(sel[0])
+        o_reads = O.Reads(sel[0], sel[1], sel[2], sel[3], np.asarray(clen))
+        want = O.calc_coverage(o_reads, o_mask, None, False)
+        got = rb.calcCoverage(x["ranges"], g_mask, ignore_strand=False)
+        assert_coverage_equal(got.to_list(), want)
+        if normalize != "none" or splice == "remove":
+            assert np.array_equal(x["ranges"].start, sel[1]) and np.array_equal(x["ranges"].end, sel[2])
+    if normalize == "downsample":
+        assert len({len(x["ranges"]) for x in inp}) == 1
+
+
+def test_width_quantile_and_selection_errors(gpu_auto):
+    rb = gpu_auto
+    from recoup_b200 import _lib
+    rng = np.random.default_rng(22)
+    s = rng.integers(1, 1000, size=5001).astype(np.int32)
+    e = (s + rng.integers(0, 300, size=5001)).astype(np.int32)
+    gr = rb.GRanges(np.zeros(5001, np.int32), s, e, seqlevels=["c"], seqlengths=[2000])
+    for q in (0.0, 0.5, 0.75, 0.999, 1.0):
+        keep, qu = O.splice_remove(s, e, q)
+        got_q, got_n = rb.widthQuantile(gr, q)
+        assert got_q == qu and got_n == int(keep.sum())
+    bad = rb.SelectedGRanges(gr, 5001, idx=[1, 5002])
+    with pytest.raises(rb.RecoupError) as ei:
+        rb.device_reads(bad)
+    assert ei.value.code == _lib.RCP_ERR_DATA
+    none_left = rb.SelectedGRanges(gr, 0, max_width=0.5)
+    mask = rb.GRanges(np.zeros(1, np.int32), [1], [50], seqlevels=["c"])
+    assert rb.calcCoverage(none_left, mask)[0] is None          # no reads: NULL
+
+
+# ------------------------------------------------------------------------------------------------
 # consumers of the matrix
 # ------------------------------------------------------------------------------------------------
 def _consumer_matrices():

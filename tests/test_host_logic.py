@@ -101,3 +101,39 @@ def test_rle_seqnames_round_trip():
         GRanges(Rle([0], [8]), np.arange(1, 10), np.arange(1, 10))
     with pytest.raises(ValueError):
         Rle([0, 1], [3, -1])
+
+
+def test_downsampling_indices_follow_one_r_stream():
+    """sort(sample(libSize, s)) per sample after ONE set.seed (ranges.R:38-41): the library's
+    host RNG against the oracle's, including sample.int's hash variant for n > 1e7"""
+    from oracle.r_rng import RRandom
+    for kind in ("Rejection", "Rounding"):
+        r = RRandom(7, kind)
+        want = [np.sort(r.sample_int(n, 400)) for n in (1000, 20000001, 400)]
+        got = rb.sampleSorted([1000, 20000001, 400], 400, 7, kind)
+        for w_, g_ in zip(want, got):
+            assert np.array_equal(w_, g_)
+    assert [a.tolist() for a in rb.sampleSorted([10, 10], 3, 42)] == [[1, 5, 10], [2, 4, 9]]
+    idx = O.downsample_indices([1000, 600], "downsample", seed=7)
+    assert np.array_equal(idx[0], rb.sampleSorted([1000, 600], 600, 7)[0]) and len(idx[1]) == 600
+    assert O.downsample_indices([5, 6], "linear") == [None, None]
+    with pytest.raises(rb.RecoupError):
+        rb.sampleSorted([10], 11, 42)
+
+
+def test_selected_granges_and_preprocess_host_logic():
+    gr = rb.GRanges(np.zeros(6, np.int32), [1, 10, 20, 30, 40, 50], [5, 29, 24, 34, 90, 54],
+                    strand=[1, -1, 1, 0, 1, -1], seqlevels=["c"], seqlengths=[100])
+    sel = rb.SelectedGRanges(gr, 4, max_width=5.0, idx=[1, 3, 4])     # widths 5 20 5 5 51 5
+    assert len(sel) == 3 and sel.start.tolist() == [1, 30, 50] and sel.strand.tolist() == [1, 0, -1]
+    assert sel.seqlengths.tolist() == [100] and sel.width.tolist() == [5, 5, 5]
+    keep, qu = O.splice_remove(gr.start, gr.end, 0.75)
+    assert qu == 16.25 and keep.tolist() == [True, False, True, True, False, True]
+    done = [{"ranges": gr}]
+    assert rb.preprocessRanges(done, {"normalize": "downsample"}) is done     # ranges.R:2-4
+    with pytest.raises(ValueError):
+        rb.preprocessRanges([{"name": "a"}], {"normalize": "none"})
+    with pytest.raises(ValueError):
+        rb.preprocessRanges([{"name": "a"}], {"normalize": "bogus"}, reader=lambda x: gr)
+    out = rb.preprocessRanges([{"name": "a"}], {"normalize": "none"}, reader=lambda x: gr)
+    assert out[0]["ranges"] is gr
