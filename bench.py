@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
                     help="N > 1: ranks store their rows straight into rank 0's matrix over NVLink "
                          "(p2p) or the row blocks are gathered with NCCL and placed by a kernel (nccl)")
+    ap.add_argument("--read-order", default="random", choices=["random", "coordinate"],
+                    help="order of the synthetic reads: as generated (random; the default and the "
+                         "harder case) or sorted by chromosome and start like a coordinate-sorted BAM")
     ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets", "blocks"],
                     help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
@@ -252,6 +255,12 @@ def run_b200(args):
     w = W.CONFIGS[args.workload](scale=args.scale, seed={"C2": 1001, "C3": 1003, "C4": 1004,
                                                           "C5": 1005}[args.workload] + 7919 * rank)
     N = len(w["read_start"])
+    if args.read_order == "coordinate":
+        order = np.lexsort((w["read_start"], w["read_chrom"]))
+        for key in ("read_chrom", "read_start", "read_end", "read_strand"):
+            w[key] = np.ascontiguousarray(w[key][order])
+        del order
+        w["name"] += " (reads coordinate-sorted)"
     is_rna = w["region"] == "rna"
     genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"],
                        strand=w["region_strand"], seqlevels=w["chrom_names"])

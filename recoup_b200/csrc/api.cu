@@ -146,6 +146,53 @@ static void drain_timers() {
     g_pending.clear();
 }
 
+// ---- fetch_and_sync ------------------------------------------------------------------------
+namespace {
+struct FetchArgs {
+    const uint32_t* src[8];
+    int words[8];
+    int n;
+};
+__global__ void fetch_pack_kernel(FetchArgs a, uint32_t* __restrict__ out) {
+    int at = 0;
+    for (int i = 0; i < a.n; i++)
+        for (int k = 0; k < a.words[i]; k++) out[at++] = a.src[i][k];
+}
+uint32_t* g_fetch_dev = nullptr;
+uint32_t* g_fetch_host = nullptr;       // page-locked
+}  // namespace
+
+int fetch_and_sync(const FetchItem* items, int n) {
+    if (n < 0 || n > 8) return fail(RCP_ERR_ARG, "internal: fetch_and_sync of %d items", n);
+    if (g_fetch_dev == nullptr) {
+        RCP_CUDA(cudaMalloc((void**)&g_fetch_dev, 8 * 32));
+        RCP_CUDA(cudaHostAlloc((void**)&g_fetch_host, 8 * 32, cudaHostAllocDefault));
+    }
+    FetchArgs a;
+    a.n = n;
+    int words = 0;
+    for (int i = 0; i < n; i++) {
+        if (items[i].bytes <= 0 || items[i].bytes > 32 || (items[i].bytes & 3))
+            return fail(RCP_ERR_ARG, "internal: fetch_and_sync item of %d bytes", items[i].bytes);
+        a.src[i] = static_cast<const uint32_t*>(items[i].dev);
+        a.words[i] = items[i].bytes / 4;
+        words += a.words[i];
+    }
+    if (n > 0) {
+        fetch_pack_kernel<<<1, 1, 0, g_ctx.stream>>>(a, g_fetch_dev);
+        RCP_LAUNCHED();
+        RCP_CUDA(cudaMemcpyAsync(g_fetch_host, g_fetch_dev, (size_t)words * 4, cudaMemcpyDeviceToHost,
+                                 g_ctx.stream));
+    }
+    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    int at = 0;
+    for (int i = 0; i < n; i++) {
+        memcpy(items[i].host, g_fetch_host + at, (size_t)items[i].bytes);
+        at += a.words[i];
+    }
+    return RCP_OK;
+}
+
 int require_ready() {
     if (!g_ctx.ready)
         return fail(RCP_ERR_NOGPU, "rcp_init() has not bound a CUDA device (no CPU fallback exists)");
@@ -379,6 +426,9 @@ int rcp_shutdown(void) {
     for (cudaEvent_t e : g_free_events) cudaEventDestroy(e);
     g_free_events.clear();
     cudaStreamSynchronize(g_ctx.stream);
+    if (g_fetch_dev) cudaFree(g_fetch_dev);
+    if (g_fetch_host) cudaFreeHost(g_fetch_host);
+    g_fetch_dev = g_fetch_host = nullptr;
     cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
     return RCP_OK;

@@ -690,11 +690,11 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
         RCP_TRY(exclusive_scan2_i64(ra.padded, cv->off, cv->off + R, ra.ntiles, tile_off,
                                     tile_off + R, R));
     }
-    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[4] = {{cv->off + R, &h.total_padded, 8}, {tile_off + R, &h.total_tiles, 8},
+                                    {d_stats, h.stats, 24}, {d_err, &h.err, 4}};
+        RCP_TRY(fetch_and_sync(items, 4));
+    }
     int rc = RCP_OK;
     if (h.err & 1u) rc = fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
     else if (h.err & 2u) rc = fail(RCP_ERR_DATA, "a region has end < start - 1");
@@ -861,11 +861,11 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
     }
     RCP_TRY(exclusive_scan2_i64(la.padded, cv->off, cv->off + G, la.ntiles, tile_off,
                                 tile_off + G, G));
-    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.total_tiles, tile_off + G, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, d_stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[4] = {{cv->off + G, &h.total_padded, 8}, {tile_off + G, &h.total_tiles, 8},
+                                    {d_stats, h.stats, 24}, {d_err, &h.err, 4}};
+        RCP_TRY(fetch_and_sync(items, 4));
+    }
     int rc = RCP_OK;
     if (h.err & 1u) rc = fail(RCP_ERR_DATA, "a range has a chromosome id outside [0, n_chrom)");
     else if (h.err & 2u) rc = fail(RCP_ERR_DATA, "a range has end < start - 1");

@@ -1192,10 +1192,10 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         RCP_TRY(exclusive_scan2_i64(w.nbig, w.off_big, w.off_big + R, w.nsmall, w.off_small,
                                     w.off_small + R, R));
     }
-    RCP_CUDA(cudaMemcpyAsync(&h.Tb, w.off_big + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.Ts, w.off_small + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.err, w.err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[3] = {{w.off_big + R, &h.Tb, 8}, {w.off_small + R, &h.Ts, 8}, {w.err, &h.err, 4}};
+        RCP_TRY(fetch_and_sync(items, 3));
+    }
     if (h.err & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
     if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
     const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
@@ -1271,10 +1271,10 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         RCP_TRY(exclusive_scan_i64(w.padded, cv->off, R, cv->off + R));
         RCP_TRY(exclusive_scan_u32(w.tile_cnt, w.boff, T, w.boff + T));
     }
-    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.listed, w.hit_n, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[3] = {{cv->off + R, &h.total_padded, 8}, {w.stats, h.stats, 24}, {w.hit_n, &h.listed, 8}};
+        RCP_TRY(fetch_and_sync(items, 3));
+    }
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
     cv->total_len = (int64_t)h.stats[1];
@@ -1378,10 +1378,10 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         RCP_TRY(exclusive_scan2_i64(w.nbig, w.off_big, w.off_big + R, w.nsmall, w.off_small,
                                     w.off_small + R, R));
     }
-    RCP_CUDA(cudaMemcpyAsync(&h.Tb, w.off_big + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.Ts, w.off_small + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h.err, w.err, 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[3] = {{w.off_big + R, &h.Tb, 8}, {w.off_small + R, &h.Ts, 8}, {w.err, &h.err, 4}};
+        RCP_TRY(fetch_and_sync(items, 3));
+    }
     if (h.err & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
     if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
     const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
@@ -1486,9 +1486,10 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         }
         RCP_TRY(exclusive_scan_i64(w.padded, cv->off, R, cv->off + R));
     }
-    RCP_CUDA(cudaMemcpyAsync(&h.total_padded, cv->off + R, 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h.stats, w.stats, 24, cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        const FetchItem items[2] = {{cv->off + R, &h.total_padded, 8}, {w.stats, h.stats, 24}};
+        RCP_TRY(fetch_and_sync(items, 2));
+    }
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
     cv->total_len = (int64_t)h.stats[1];

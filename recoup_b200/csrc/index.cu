@@ -613,14 +613,12 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     }
     unsigned int h_err = 0, h_w[2] = {0, 0}, h_total = 0;
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
-    if (rle)
-        RCP_CUDA(cudaMemcpyAsync(&h_total, run_first + n_runs, sizeof(h_total), cudaMemcpyDeviceToHost,
-                                 g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(h_w, d_w, sizeof(h_w), cudaMemcpyDeviceToHost, g_ctx.stream));
     lap("map kernel enqueued");
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    {
+        FetchItem items[4] = {{d_err, &h_err, 4}, {d_cnt, h_cnt, 32}, {d_w, h_w, 8}, {nullptr, &h_total, 4}};
+        if (rle) items[3].dev = run_first + n_runs;
+        RCP_TRY(fetch_and_sync(items, rle ? 4 : 3));
+    }
     lap("sync (copies + map kernel)");
     dfree(d_err);
     dfree(d_cnt);

@@ -94,6 +94,17 @@ inline void dfree(T*& p) {
     p = nullptr;
 }
 
+// Several small device values -> host in ONE transfer, then a stream synchronisation: a
+// one-thread kernel packs them into a device block, one copy brings the block into page-locked
+// host memory.  (A cudaMemcpyAsync into pageable memory is a blocking round trip of its own, and
+// the sync points of a step used to pay three of them each.)
+struct FetchItem {
+    const void* dev;
+    void* host;
+    int bytes;      // <= 32, a multiple of 4
+};
+int fetch_and_sync(const FetchItem* items, int n);      // n <= 8
+
 // A caller array that must be readable on the device: either the caller's own device pointer or
 // a stream-ordered staging copy of host memory.
 template <class T>
