@@ -605,7 +605,8 @@ inline unsigned reads_grid(int64_t n, size_t smem) {
 
 // ================================================================================================
 // BLOCKS mode: the same coverage without the cell table, the hit list and the place pass.
-//   filter     reads that pass the block bitmap, compacted per 4096-read chunk (no atomics)
+//   filter     reads that pass the block bitmap, compacted into one dense candidate array (one
+//              atomic reservation per 256+ survivors of a warp)
 //   partition  the survivors are grouped by 16-kb genome block (start >> 14) with two 9-bit
 //              multisplit passes: per-chunk histograms in shared memory, one prefix sum over
 //              (digit, chunk), then a scatter whose ranks come from shared-memory counters --
@@ -629,66 +630,86 @@ struct Cands {
     int8_t* st;          // strand (stranded calls only)
 };
 
+// The survivors leave through a per-warp shared-memory buffer that is flushed 256+ at a time with
+// ONE atomic reservation in the dense candidate array and coalesced stores (their order is not
+// deterministic; the coverage, a sum of integers, is).
+constexpr int FB_FLUSH = 256;
+constexpr int FB_CAP = FB_FLUSH + 128;
+template <bool STRANDED>
+__host__ __device__ constexpr size_t filter_smem_fixed() {
+    return (size_t)RWARPS * FB_CAP * (sizeof(uint2) + (STRANDED ? 1 : 0));
+}
+
 template <bool STRANDED>
 __global__ void __launch_bounds__(RTPB)
 blk_filter_kernel(int64_t n, const uint32_t* __restrict__ g_start,
                   const uint32_t* __restrict__ g_end1, const int8_t* __restrict__ strand,
                   const uint32_t* __restrict__ bitmap, int bm_words, Cands out,
-                  uint32_t* __restrict__ counts) {
+                  uint32_t* __restrict__ total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
+    uint2* fb = reinterpret_cast<uint2*>(smem_raw) + (threadIdx.x >> 5) * FB_CAP;
+    int8_t* fst = reinterpret_cast<int8_t*>(smem_raw + (size_t)RWARPS * FB_CAP * sizeof(uint2)) +
+                  (threadIdx.x >> 5) * FB_CAP;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw + filter_smem_fixed<STRANDED>());
     for (int i = threadIdx.x; i < bm_words; i += RTPB) bm[i] = bitmap[i];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int64_t n_vec = n >> 2;
-    constexpr int SUBV = PCH / 4;
-    const int64_t n_sub = (n_vec + SUBV - 1) / SUBV;          // + one chunk for the n % 4 tail
-    const int64_t warps_total = (int64_t)gridDim.x * (RTPB / 32);
-    for (int64_t sc = (int64_t)blockIdx.x * (RTPB / 32) + (threadIdx.x >> 5); sc <= n_sub;
-         sc += warps_total) {
-        const int64_t o0 = sc * PCH;
-        uint32_t kept = 0;
-        auto keep = [&](uint32_t s, uint32_t e1, int st) {
-            bool ok = e1 > s;
-            if (ok) {
-                const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
-                uint32_t w = bm[b0 >> 5] >> (b0 & 31u);
-                if (b1 != b0) w |= bm[b1 >> 5] >> (b1 & 31u);
-                ok = (b1 > b0 + 1u) || (w & 1u);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const int64_t o = o0 + kept + __popc(m & lt);
-                out.s[o] = s;
-                out.e[o] = e1;
-                if (STRANDED) out.st[o] = (int8_t)st;
-            }
-            kept += __popc(m);
-        };
-        if (sc < n_sub) {
-            const int64_t v_end = min(n_vec, (sc + 1) * SUBV);
-            for (int64_t v0 = sc * SUBV; v0 < v_end; v0 += 32) {
-                const int64_t v = v0 + lane;
-                uint4 s4 = make_uint4(0, 0, 0, 0), e4 = make_uint4(0, 0, 0, 0);
-                char4 t4 = make_char4(0, 0, 0, 0);
-                if (v < v_end) {
-                    s4 = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
-                    e4 = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
-                    if (STRANDED && strand) t4 = __ldcs(reinterpret_cast<const char4*>(strand) + v);
-                }
-                keep(s4.x, e4.x, t4.x);
-                keep(s4.y, e4.y, t4.y);
-                keep(s4.z, e4.z, t4.z);
-                keep(s4.w, e4.w, t4.w);
-            }
-        } else {
-            const int64_t i = n_vec * 4 + lane;
-            const bool ok = i < n;
-            keep(ok ? g_start[i] : 0u, ok ? g_end1[i] : 0u, (ok && STRANDED && strand) ? (int)strand[i] : 0);
+    int fill = 0;                   // warp-uniform
+    auto flush = [&]() {
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(total, (uint32_t)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < fill; i += 32) {
+            const uint2 x = fb[i];
+            out.s[base + i] = x.x;
+            out.e[base + i] = x.y;
+            if (STRANDED) out.st[base + i] = fst[i];
         }
-        if (lane == 0) counts[sc] = kept;
+        fill = 0;
+        __syncwarp();
+    };
+    auto keep = [&](uint32_t s, uint32_t e1, int st) {
+        bool ok = e1 > s;
+        if (ok) {
+            const uint32_t b0 = s >> BM_SHIFT, b1 = (e1 - 1u) >> BM_SHIFT;
+            uint32_t w = bm[b0 >> 5] >> (b0 & 31u);
+            if (b1 != b0) w |= bm[b1 >> 5] >> (b1 & 31u);
+            ok = (b1 > b0 + 1u) || (w & 1u);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int p = fill + __popc(m & lt);
+            fb[p] = make_uint2(s, e1);
+            if (STRANDED) fst[p] = (int8_t)st;
+        }
+        fill += __popc(m);
+    };
+    const int64_t n_vec = n >> 2;
+    const int64_t warps_total = (int64_t)gridDim.x * RWARPS;
+    const int64_t gw = (int64_t)blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    for (int64_t base = gw * 32; base < n_vec; base += warps_total * 32) {
+        const int64_t v = base + lane;
+        uint4 s4 = make_uint4(0, 0, 0, 0), e4 = make_uint4(0, 0, 0, 0);
+        char4 t4 = make_char4(0, 0, 0, 0);
+        if (v < n_vec) {
+            s4 = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
+            e4 = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
+            if (STRANDED && strand) t4 = __ldcs(reinterpret_cast<const char4*>(strand) + v);
+        }
+        keep(s4.x, e4.x, t4.x);
+        keep(s4.y, e4.y, t4.y);
+        keep(s4.z, e4.z, t4.z);
+        keep(s4.w, e4.w, t4.w);
+        if (fill >= FB_FLUSH) flush();
     }
+    if (gw == 0) {                  // the n % 4 tail
+        const int64_t i = n_vec * 4 + lane;
+        const bool ok = i < n;
+        keep(ok ? g_start[i] : 0u, ok ? g_end1[i] : 0u, (ok && STRANDED && strand) ? (int)strand[i] : 0);
+    }
+    if (fill > 0) flush();
 }
 
 // Histogram of one chunk (<= PCH keys at keys[lo, hi)) over the digit (key >> shift) & (ND - 1);
@@ -780,19 +801,20 @@ __device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, 
 // pass 1: one CTA per filter chunk; hist1[digit * n_chunks + chunk]
 __global__ void __launch_bounds__(PT)
 blk_hist1_kernel(int64_t n_chunks, const uint32_t* __restrict__ keys,
-                 const uint32_t* __restrict__ counts, uint32_t* __restrict__ hist) {
+                 const uint32_t* __restrict__ total, uint32_t* __restrict__ hist) {
     const int64_t c = blockIdx.x;
-    const uint32_t lo = (uint32_t)(c * PCH);
-    blk_hist_chunk(keys, lo, lo + counts[c], SHIFT1, hist, (size_t)n_chunks, (size_t)c);
+    const uint32_t tot = *total, lo = min((uint32_t)(c * PCH), tot);
+    blk_hist_chunk(keys, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, hist, (size_t)n_chunks, (size_t)c);
 }
 
 template <bool STRANDED>
 __global__ void __launch_bounds__(PT)
-blk_scatter1_kernel(int64_t n_chunks, Cands in, const uint32_t* __restrict__ counts,
+blk_scatter1_kernel(int64_t n_chunks, Cands in, const uint32_t* __restrict__ total,
                     const uint32_t* __restrict__ pos, Cands out) {
     const int64_t c = blockIdx.x;
-    const uint32_t lo = (uint32_t)(c * PCH);
-    blk_scatter_chunk<STRANDED>(in, lo, lo + counts[c], SHIFT1, pos, (size_t)n_chunks, (size_t)c, out);
+    const uint32_t tot = *total, lo = min((uint32_t)(c * PCH), tot);
+    if (lo >= tot) return;          // (its histogram column is all zero)
+    blk_scatter_chunk<STRANDED>(in, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, pos, (size_t)n_chunks, (size_t)c, out);
 }
 
 // After pass 1: start of each top-digit run (S1[ND + 1]) and the prefix of the chunk counts of
@@ -1391,10 +1413,10 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
     const int64_t n_cell = (span >> CELL_SHIFT) + 2;
     w.bm_words = (int)(((span >> BM_SHIFT) + 32) / 32);
-    const int64_t n_chunks = ((rd.n >> 2) + PCH / 4 - 1) / (PCH / 4) + 1;      // filter chunks
+    const int64_t n_chunks = (rd.n + PCH - 1) / PCH + 1;                       // pass-1 chunks (upper bound)
     const int64_t tc_upper = (rd.n + PCH - 1) / PCH + ND;                      // pass-2 chunks
     Cands ca, cb;
-    uint32_t *counts, *hist1, *hist2, *S1, *CP, *blk_off;
+    uint32_t *cand_total, *hist1, *hist2, *S1, *CP, *blk_off;
     size_t zero_bytes = 0;
     {
         const size_t t = (size_t)T, c = (size_t)n_cell, nc = (size_t)n_chunks, cap = nc * PCH;
@@ -1410,6 +1432,7 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         w.cells.bitmap = w.B.take<uint32_t>((size_t)w.bm_words);
         w.tile_cnt = w.B.take<uint32_t>(t + 1);
         hist2 = w.B.take<uint32_t>((size_t)ND * (size_t)tc_upper + 1);
+        cand_total = w.B.take<uint32_t>(nc);          // [0] = number of candidates
         zero_bytes = w.B.used;
         w.tiles.a = w.B.take<uint2>(t);
         w.tiles.b = w.B.take<uint2>(t);
@@ -1419,7 +1442,6 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
         cb.e = w.B.take<uint32_t>(cap);
         ca.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
         cb.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
-        counts = w.B.take<uint32_t>(nc);
         hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
         S1 = w.B.take<uint32_t>(ND + 1);
         CP = w.B.take<uint32_t>(ND + 1);
@@ -1438,22 +1460,23 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
     }
     {
         StageTimer t(ST_BKT_COUNT);         // filter + pass 1
-        const size_t smem = (size_t)w.bm_words * 4;
         if (st_arr) {
+            const size_t smem = filter_smem_fixed<true>() + (size_t)w.bm_words * 4;
             RCP_CUDA(cudaFuncSetAttribute(blk_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             blk_filter_kernel<true><<<reads_grid(rd.n, smem), RTPB, smem, g_ctx.stream>>>(
-                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, counts);
+                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, cand_total);
         } else {
+            const size_t smem = filter_smem_fixed<false>() + (size_t)w.bm_words * 4;
             RCP_CUDA(cudaFuncSetAttribute(blk_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             blk_filter_kernel<false><<<reads_grid(rd.n, smem), RTPB, smem, g_ctx.stream>>>(
-                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, counts);
+                rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, cand_total);
         }
         RCP_LAUNCHED();
-        blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, counts, hist1);
+        blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, cand_total, hist1);
         RCP_LAUNCHED();
         RCP_TRY(exclusive_scan_u32(hist1, hist1, (int64_t)ND * n_chunks, hist1 + (int64_t)ND * n_chunks));
-        if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
-        else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, counts, hist1, cb);
+        if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
+        else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
         RCP_LAUNCHED();
     }
     {
