@@ -984,28 +984,66 @@ __device__ __forceinline__ TileDesc load_desc_full(const TileDesc* __restrict__ 
     return d;
 }
 
-template <int RPW>
+// The candidate loads are issued four per thread at a time (the first batch before the tile is
+// cleared): a tile has ~10^3 candidates, so one batch usually covers it and the loop pays the
+// L2 / HBM latency once instead of once per candidate.
+template <int RPW, bool STRANDED>
 __device__ __forceinline__ void blk_tile_body(int* diff, int* wtot, const TileDesc& d, Cands c,
-                                              bool stranded, int32_t* __restrict__ dst) {
-    const int tid = threadIdx.x;
+                                              int32_t* __restrict__ dst) {
+    constexpr int B = 4;
+    const uint32_t tid = threadIdx.x;
     const int tlen = d.tlen;
+    const uint32_t n = d.n;
+    const uint32_t* cs = c.s + d.b0;
+    const uint32_t* ce = c.e + d.b0;
+    const int8_t* ct = STRANDED ? c.st + d.b0 : nullptr;
+    uint32_t s[B], e[B];
+    int st[B];
+    auto load = [&](uint32_t i0) {
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            const uint32_t i = i0 + (uint32_t)k * CTA + tid;
+            const bool ok = i < n;
+            s[k] = ok ? __ldg(cs + i) : 0u;
+            e[k] = ok ? __ldg(ce + i) : 0u;            // end 0: never a hit
+            st[k] = (STRANDED && ok) ? (int)__ldg(ct + i) : 0;
+        }
+    };
+    load(0);
 #pragma unroll
     for (int k = 0; k < RPW; k++)
         reinterpret_cast<int4*>(diff)[k * CTA + tid] = make_int4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t ts = (uint32_t)d.pad[0], flags = (uint32_t)d.pad[1];
-    for (uint32_t i = tid; i < d.n; i += CTA) {
-        const uint32_t s = __ldg(c.s + d.b0 + i), e1 = __ldg(c.e + d.b0 + i);
-        uint32_t packed;
-        if (blk_hit(s, e1, stranded ? (int)__ldg(c.st + d.b0 + i) : 0, ts, (uint32_t)tlen, flags, stranded,
-                    &packed)) {
-            const int lo = (int)(packed & 0xffffu), hi = (int)(packed >> 16);
-            atomicAdd(diff + lo, 1);
-            if (hi < tlen) atomicSub(diff + hi, 1);
+    for (uint32_t i0 = 0; i0 < n; i0 += B * CTA) {
+        if (i0) load(i0);
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            uint32_t packed;
+            if (blk_hit(s[k], e[k], st[k], ts, (uint32_t)tlen, flags, STRANDED, &packed)) {
+                const int lo = (int)(packed & 0xffffu), hi = (int)(packed >> 16);
+                atomicAdd(diff + lo, 1);
+                if (hi < tlen) atomicSub(diff + hi, 1);
+            }
         }
     }
     __syncthreads();
     block_scan_store_fwd<RPW, true>(diff, tlen, wtot, dst);
+}
+
+template <bool STRANDED>
+__device__ __forceinline__ void blk_tile_dispatch(int* diff, int* wtot, const TileDesc& d, Cands c,
+                                                  int32_t* __restrict__ dst) {
+    const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
+    switch (rpw) {
+        case 1: blk_tile_body<1, STRANDED>(diff, wtot, d, c, dst); break;
+        case 2: blk_tile_body<2, STRANDED>(diff, wtot, d, c, dst); break;
+        case 3: blk_tile_body<3, STRANDED>(diff, wtot, d, c, dst); break;
+        case 4: blk_tile_body<4, STRANDED>(diff, wtot, d, c, dst); break;
+        case 5: blk_tile_body<5, STRANDED>(diff, wtot, d, c, dst); break;
+        case 6: blk_tile_body<6, STRANDED>(diff, wtot, d, c, dst); break;
+        default: blk_tile_body<7, STRANDED>(diff, wtot, d, c, dst); break;
+    }
 }
 
 __global__ void __launch_bounds__(CTA, 5)
@@ -1023,17 +1061,8 @@ blk_tile_kernel(int64_t Tb, const TileDesc* __restrict__ desc, Cands c, int stra
         dn.tlen = 0;
         if (t + step < Tb) dn = load_desc_full(desc + t + step);
         if (d.tlen > 0) {
-            const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
-            int32_t* dst = cov + d.out;
-            switch (rpw) {
-                case 1: blk_tile_body<1>(diff, wtot, d, c, stranded != 0, dst); break;
-                case 2: blk_tile_body<2>(diff, wtot, d, c, stranded != 0, dst); break;
-                case 3: blk_tile_body<3>(diff, wtot, d, c, stranded != 0, dst); break;
-                case 4: blk_tile_body<4>(diff, wtot, d, c, stranded != 0, dst); break;
-                case 5: blk_tile_body<5>(diff, wtot, d, c, stranded != 0, dst); break;
-                case 6: blk_tile_body<6>(diff, wtot, d, c, stranded != 0, dst); break;
-                default: blk_tile_body<7>(diff, wtot, d, c, stranded != 0, dst); break;
-            }
+            if (stranded) blk_tile_dispatch<true>(diff, wtot, d, c, cov + d.out);
+            else blk_tile_dispatch<false>(diff, wtot, d, c, cov + d.out);
         }
         t += step;
         if ((tid & 31u) == 0) tma_store_wait_read();
