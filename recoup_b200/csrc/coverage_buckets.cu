@@ -741,6 +741,11 @@ __device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, 
     __shared__ int8_t stage_st[STRANDED ? PCH : 1];
     const int tid = threadIdx.x;
     for (int d = tid; d < ND; d += PT) cnt[d] = 0;
+    constexpr int DPT = ND / PT;
+    // the global bases of this thread's digits: issued first, needed only after the local scan
+    uint32_t gbv[DPT];
+#pragma unroll
+    for (int q = 0; q < DPT; q++) gbv[q] = __ldg(gbase + (size_t)(tid * DPT + q) * stride + column);
     __syncthreads();
     constexpr int PER = PCH / PT;           // 16 elements per thread
     uint16_t rk[PER];                       // rank of the element inside its digit in this chunk
@@ -748,11 +753,14 @@ __device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, 
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const uint32_t i = (uint32_t)k * PT + tid;
-        if (i < n) rk[k] = (uint16_t)atomicAdd(&cnt[(__ldg(in.s + lo + i) >> shift) & (ND - 1)], 1u);
+        if (i < n) {
+            rk[k] = (uint16_t)atomicAdd(&cnt[(__ldg(in.s + lo + i) >> shift) & (ND - 1)], 1u);
+            // the ends are read in the staging phase: start them towards L2 now (one per sector)
+            if ((tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.e + lo + i));
+        }
     }
     __syncthreads();
     // exclusive scan of the ND digit counts (ND / PT consecutive digits per thread)
-    constexpr int DPT = ND / PT;
     uint32_t c[DPT], mine = 0;
 #pragma unroll
     for (int q = 0; q < DPT; q++) {
@@ -774,7 +782,7 @@ __device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, 
     for (int q = 0; q < DPT; q++) {
         const int d = tid * DPT + q;
         cnt[d] = run;                                       // local offset of digit d
-        gb[d] = gbase[(size_t)d * stride + column] - run;   // global position = gb[d] + local position
+        gb[d] = gbv[q] - run;                               // global position = gb[d] + local position
         run += c[q];
     }
     __syncthreads();
