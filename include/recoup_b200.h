@@ -94,18 +94,23 @@ int rcp_timing_enable(int on);
 int rcp_timing_read(int reset, int capacity, double* ms_out, int64_t* count_out);
 const char* rcp_timing_stage_name(int stage);
 
-/* How rcp_coverage (GRanges masks) finds the reads of each region.  Both give identical results.
+/* How rcp_coverage (GRanges masks) finds the reads of each region.  All give identical results.
  *   RCP_PATH_BUCKETS  two passes over the unsorted reads drop each read into the buckets of the
- *                     output tiles it overlaps (no sort);
+ *                     output tiles it overlaps (cell table + hit list, no sort);
+ *   RCP_PATH_BLOCKS   the reads that pass a block bitmap are partitioned by 16-kb genome block
+ *                     (two multisplit passes, no per-read random access) and every output tile
+ *                     scans the candidates of the blocks under it;
  *   RCP_PATH_INDEX    the reads are radix-sorted once per handle and every region is served by
  *                     rank searches (cheaper when one handle serves many masks);
- *   RCP_PATH_AUTO     (default) the index when the handle already has one, else buckets.
+ *   RCP_PATH_AUTO     (default) the index when the handle already has one or the mask is dense
+ *                     and the reads many; else blocks for masks made of tiled regions (> 1024 bp:
+ *                     TSS windows, gene bodies), buckets for masks dominated by short regions.
  * The reference has one path (findOverlaps per region, coverage.R:189-193); this is a tuning
  * knob with no counterpart there. */
 #define RCP_PATH_AUTO 0
 #define RCP_PATH_INDEX 1
 #define RCP_PATH_BUCKETS 2
-#define RCP_PATH_BLOCKS 3      /* experimental: filter + two multisplit passes by 16-kb block */
+#define RCP_PATH_BLOCKS 3
 int rcp_set_coverage_path(int path);
 
 /* ---------------------------------------------------------------- base-R RNG -------------- */
