@@ -337,6 +337,10 @@ def run_b200(args):
             tl, nn = C.c_int64(0), C.c_int64(0)
             L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
             stats["total_len"], stats["n_null"] = tl.value, nn.value
+            pth, cand = C.c_int(0), C.c_int64(0)
+            L.rcp_coverage_path_info(cov.value, C.byref(pth), C.byref(cand))
+            stats["path"] = {0: "list", 1: "index", 2: "buckets", 3: "blocks"}[pth.value]
+            stats["candidates"] = cand.value
         if out_box["ptr"] is not None:      # peer-mapped matrix of rank 0 / verification buffer
             out_ptr = out_box["ptr"]
         else:
@@ -621,8 +625,16 @@ def run_b200(args):
         # Per KERNEL (the `roofline` object, dominant kernel of the step): the bytes that kernel
         # cannot avoid moving -- a pass over the reads 8 B/read (+1 with strand), the tile
         # kernels 4 B/covered base written (+ 8 B/read on the index path, which reads the sorted
-        # arrays there), the bin kernel 4 B/covered base + 8 B/cell, the sort 8 B/key.
+        # arrays there), the bin kernel 4 B/covered base + 8 B/cell, the sort 8 B/key.  Block path:
+        # the filter reads 8 B/read (its output, 8 B/candidate, is not counted); a scatter pass
+        # reads and writes 8 B/candidate; the tile kernel writes 4 B/covered base and reads the
+        # candidates once (8 B each; the re-reads of a block by its second tile are not counted).
+        cand = stats.get("candidates", 0)
         alg_kernel = {
+            "blk_filter": 8 * N,
+            "blk_scatter": 16 * cand,
+            "blk_tile": 4 * total_len + 8 * cand,
+            "blk_small": 4 * total_len + 8 * cand,
             "index_map": 22 * N,
             "index_sort": 8 * N,
             "cov_tile": 8 * N + 4 * total_len + 16 * R,
@@ -637,7 +649,8 @@ def run_b200(args):
         groups = {
             "reads_map": (["index_map"], 22 * N),
             "coverage": (["index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
-                          "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small"],
+                          "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small",
+                          "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small"],
                          8 * N + 4 * total_len + 16 * R),
             "profile": (["prof_bin", "prof_interp", "prof_base"], 4 * total_len + 8 * R * ncols),
         }
@@ -659,11 +672,18 @@ def run_b200(args):
         roof = None
         if dom:
             per_step_ms = per_step[dom]
-            ach = alg_kernel[dom] / (per_step_ms * 1e-3) / 1e9
+            per_launch_ms = own[dom][0]         # average over the launches of the timed region
+            ach = alg_kernel[dom] / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-                    "ms_per_step": per_step_ms, "launches_per_step": own[dom][1] / args.steps,
-                    "algorithmic_bytes": alg_kernel[dom], "stages": stage_roof}
+                    "ms_per_step": per_step_ms, "ms_per_launch": per_launch_ms,
+                    "launches_per_step": own[dom][1] / args.steps,
+                    "algorithmic_bytes": alg_kernel[dom],
+                    "kernels": {k: {"ms_per_launch": own[k][0], "launches_per_step": own[k][1] / args.steps,
+                                    "algorithmic_bytes": alg_kernel[k],
+                                    "frac": alg_kernel[k] / (own[k][0] * 1e-3) / 1e9 / peak}
+                                for k in own},
+                    "stages": stage_roof}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -674,7 +694,8 @@ def run_b200(args):
                        "null_regions": stats["n_null"],
                        "l2": "inputs (%.0f MB) and coverage (%.0f MB) exceed the 126 MB L2"
                              % (13 * N / 1e6, 4 * total_len / 1e6),
-                       "coverage_path": args.path,
+                       "coverage_path": args.path, "coverage_path_used": stats.get("path"),
+                       "filter_candidates_per_gpu": stats.get("candidates"),
                        "parallelism": ("regions sharded over %d GPU(s), " % world) +
                                       ("rows stored into rank 0's matrix over NVLink (peer-mapped)"
                                        if world > 1 and args.exchange == "p2p" else

@@ -112,6 +112,10 @@ const char* rcp_timing_stage_name(int stage);
 #define RCP_PATH_BUCKETS 2
 #define RCP_PATH_BLOCKS 3
 int rcp_set_coverage_path(int path);
+/* Which path produced a coverage (RCP_PATH_INDEX / BUCKETS / BLOCKS; 0 for GRangesList and
+ * concatenated coverages) and, for the block path, how many reads passed its bitmap filter
+ * (bench.py derives that path's algorithmic bytes from it). */
+int rcp_coverage_path_info(int cov, int* path, int64_t* candidates);
 
 /* ---------------------------------------------------------------- base-R RNG -------------- */
 /* `set.seed(seed); sample(1:n, k)` -- the bin layout of splitVector (util.R:78-79). */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "rcp_r_sample_sorted": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p, _i64p, _vp]),
     "rcp_reads_load_select": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_double, C.c_int64, _vp, C.c_int,
                                         _i64p, C.c_int, C.c_int, _i64p, _ip]),
+    "rcp_coverage_path_info": (C.c_int, [C.c_int, _ip, _i64p]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
                                      C.c_int, C.c_int, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),

@@ -104,7 +104,7 @@ static int64_t g_stage_count[ST_N];
 static const char* const g_stage_names[ST_N] = {
     "index_map", "index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
     "prof_bin", "prof_interp", "prof_base", "fused", "bkt_plan", "bkt_count", "bkt_scatter",
-    "bkt_tile", "bkt_small"};
+    "bkt_tile", "bkt_small", "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small"};
 
 static cudaEvent_t take_event() {
     if (!g_free_events.empty()) {
@@ -790,6 +790,14 @@ int rcp_coverage_info(int cov, int64_t* n_regions, int64_t* total_len, int64_t* 
     if (total_len) *total_len = cv->total_len;
     if (n_null) *n_null = cv->n_null;
     if (scale) *scale = cv->scale;
+    return RCP_OK;
+}
+
+int rcp_coverage_path_info(int cov, int* path, int64_t* candidates) {
+    Coverage* cv = get_coverage(cov);
+    if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (path) *path = cv->path;
+    if (candidates) *candidates = cv->candidates;
     return RCP_OK;
 }
 

@@ -699,6 +699,7 @@ int coverage_ranges_impl(ReadsIdx& rd, Sources<NS> src, int64_t R, const int32_t
     if (h.err & 1u) rc = fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
     else if (h.err & 2u) rc = fail(RCP_ERR_DATA, "a region has end < start - 1");
     if (rc == RCP_OK) {
+        cv->path = RCP_PATH_INDEX;
         cv->total_padded = h.total_padded;
         cv->n_null = (int64_t)h.stats[0];
         cv->total_len = (int64_t)h.stats[1];

@@ -812,6 +812,7 @@ blk_hist1_kernel(int64_t n_chunks, const uint32_t* __restrict__ keys,
                  const uint32_t* __restrict__ total, uint32_t* __restrict__ hist) {
     const int64_t c = blockIdx.x;
     const uint32_t tot = *total, lo = min((uint32_t)(c * PCH), tot);
+    if (lo >= tot) return;          // the histogram is cleared beforehand: nothing to write
     blk_hist_chunk(keys, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, hist, (size_t)n_chunks, (size_t)c);
 }
 
@@ -1346,6 +1347,7 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
         const FetchItem items[3] = {{cv->off + R, &h.total_padded, 8}, {w.stats, h.stats, 24}, {w.hit_n, &h.listed, 8}};
         RCP_TRY(fetch_and_sync(items, 3));
     }
+    cv->path = RCP_PATH_BUCKETS;
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
     cv->total_len = (int64_t)h.stats[1];
@@ -1487,6 +1489,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         w.tile_cnt = w.B.take<uint32_t>(t + 1);
         hist2 = w.B.take<uint32_t>((size_t)ND * (size_t)tc_upper + 1);
         cand_total = w.B.take<uint32_t>(nc);          // [0] = number of candidates
+        hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
         zero_bytes = w.B.used;
         w.tiles.a = w.B.take<uint2>(t);
         w.tiles.b = w.B.take<uint2>(t);
@@ -1496,7 +1499,6 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         cb.e = w.B.take<uint32_t>(cap);
         ca.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
         cb.st = st_arr ? w.B.take<int8_t>(cap) : nullptr;
-        hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
         S1 = w.B.take<uint32_t>(ND + 1);
         CP = w.B.take<uint32_t>(ND + 1);
         blk_off = w.B.take<uint32_t>((size_t)N_BLOCKS + 1);
@@ -1513,7 +1515,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         }
     }
     {
-        StageTimer t(ST_BKT_COUNT);         // filter + pass 1
+        StageTimer t(ST_BLK_FILTER);
         if (st_arr) {
             const size_t smem = filter_smem_fixed<true>() + (size_t)w.bm_words * 4;
             RCP_CUDA(cudaFuncSetAttribute(blk_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1526,30 +1528,39 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
                 rd.n, rd.g_start, rd.g_end1, rd.d_strand, w.cells.bitmap, w.bm_words, ca, cand_total);
         }
         RCP_LAUNCHED();
+    }
+    {
+        StageTimer t(ST_BLK_HIST);          // pass 1
         blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, cand_total, hist1);
         RCP_LAUNCHED();
         RCP_TRY(exclusive_scan_u32(hist1, hist1, (int64_t)ND * n_chunks, hist1 + (int64_t)ND * n_chunks));
+    }
+    {
+        StageTimer t(ST_BLK_SCATTER);
         if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
         else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
         RCP_LAUNCHED();
     }
     {
-        StageTimer t(ST_BKT_SCATTER);       // pass 2 + block offsets
+        StageTimer t(ST_BLK_HIST);          // pass 2
         blk_runs_kernel<<<1, ND, 0, g_ctx.stream>>>(n_chunks, hist1, S1, CP);
         RCP_LAUNCHED();
         blk_hist2_kernel<<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb.s, CP, S1, hist2);
         RCP_LAUNCHED();
         RCP_TRY(exclusive_scan_u32(hist2, hist2, (int64_t)ND * tc_upper, hist2 + (int64_t)ND * tc_upper));
+    }
+    {
+        StageTimer t(ST_BLK_SCATTER);
         if (st_arr) blk_scatter2_kernel<true><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
         else blk_scatter2_kernel<false><<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb, CP, S1, hist2, ca);
-        RCP_LAUNCHED();
-        blk_offsets_kernel<<<(N_BLOCKS + 1 + PT - 1) / PT, PT, 0, g_ctx.stream>>>(CP, S1, hist2, blk_off);
         RCP_LAUNCHED();
     }
     // ---- NULL rule, offsets ---------------------------------------------------------------------
     const uint32_t max_w = rd.max_width > 0 ? rd.max_width : 1u;
     {
         StageTimer t(ST_BKT_PLAN);
+        blk_offsets_kernel<<<(N_BLOCKS + 1 + PT - 1) / PT, PT, 0, g_ctx.stream>>>(CP, S1, hist2, blk_off);
+        RCP_LAUNCHED();
         if (T > 0) {
             blk_any_kernel<<<blocks_for(T, WARPS), CTA, 0, g_ctx.stream>>>(T, w.tiles, ca, blk_off, max_w,
                                                                            st_arr ? 1 : 0, w.tile_cnt);
@@ -1563,10 +1574,14 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         }
         RCP_TRY(exclusive_scan_i64(w.padded, cv->off, R, cv->off + R));
     }
+    uint32_t h_cand = 0;
     {
-        const FetchItem items[2] = {{cv->off + R, &h.total_padded, 8}, {w.stats, h.stats, 24}};
-        RCP_TRY(fetch_and_sync(items, 2));
+        const FetchItem items[3] = {{cv->off + R, &h.total_padded, 8}, {w.stats, h.stats, 24},
+                                    {cand_total, &h_cand, 4}};
+        RCP_TRY(fetch_and_sync(items, 3));
     }
+    cv->path = RCP_PATH_BLOCKS;
+    cv->candidates = (int64_t)h_cand;
     cv->total_padded = h.total_padded;
     cv->n_null = (int64_t)h.stats[0];
     cv->total_len = (int64_t)h.stats[1];
@@ -1579,7 +1594,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
                                                                  cv->off, w.desc);
     RCP_LAUNCHED();
     if (Tb > 0) {
-        StageTimer t(ST_BKT_TILE);
+        StageTimer t(ST_BLK_TILE);
         int per_sm = 0;
         RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blk_tile_kernel, CTA, 0));
         if (per_sm < 1) per_sm = 1;
@@ -1588,7 +1603,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         RCP_LAUNCHED();
     }
     if (Ts > 0) {
-        StageTimer t(ST_BKT_SMALL);
+        StageTimer t(ST_BLK_SMALL);
         blk_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, w.desc + Tb, ca,
                                                                          st_arr ? 1 : 0, cv->cov);
         RCP_LAUNCHED();

@@ -67,6 +67,11 @@ enum Stage {
     ST_BKT_SCATTER,     // bucket path: scatter pass over the reads
     ST_BKT_TILE,        // bucket path: bkt_tile_kernel
     ST_BKT_SMALL,       // bucket path: bkt_small_kernel
+    ST_BLK_FILTER,      // block path: blk_filter_kernel (one launch)
+    ST_BLK_HIST,        // block path: per-chunk digit histograms + their prefix sums (two passes)
+    ST_BLK_SCATTER,     // block path: blk_scatter1/2_kernel (one launch per pass)
+    ST_BLK_TILE,        // block path: blk_tile_kernel
+    ST_BLK_SMALL,       // block path: blk_small_kernel
     ST_N
 };
 struct StageTimer {
@@ -180,6 +185,8 @@ struct Coverage {
     int64_t total_len = 0;       // sum of len
     int64_t n_null = 0;
     int32_t max_len = 0;         // longest region (sizes the staging buffers of the bin kernel)
+    int path = 0;                // RCP_PATH_* that produced it (0: list / concat)
+    int64_t candidates = 0;      // block path: reads that passed the bitmap filter
     double scale = 1.0;
     int32_t* cov = nullptr;      // dense int32, region r at [off[r], off[r] + len[r])
     int64_t* off = nullptr;      // n_regions + 1, multiples of 32 ints
