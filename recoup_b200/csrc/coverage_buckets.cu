@@ -806,36 +806,45 @@ __device__ __forceinline__ void blk_scatter_chunk(const Cands& in, uint32_t lo, 
     }
 }
 
-// pass 1: one CTA per filter chunk; hist1[digit * n_chunks + chunk]
+// pass 1: one CTA per chunk of the dense candidate array.  The number of chunks is only known on
+// the device (nc1 = ceil(candidates / PCH)); the launches are sized for the upper bound and the
+// histogram is laid out compactly, hist1[digit * nc1 + chunk], so that its prefix sum runs over
+// ND * nc1 entries (sizes[0], written here) instead of the upper bound.
+__device__ __forceinline__ uint32_t blk_nc1(uint32_t total) { return (total + PCH - 1) / PCH; }
+
 __global__ void __launch_bounds__(PT)
-blk_hist1_kernel(int64_t n_chunks, const uint32_t* __restrict__ keys,
-                 const uint32_t* __restrict__ total, uint32_t* __restrict__ hist) {
-    const int64_t c = blockIdx.x;
-    const uint32_t tot = *total, lo = min((uint32_t)(c * PCH), tot);
-    if (lo >= tot) return;          // the histogram is cleared beforehand: nothing to write
-    blk_hist_chunk(keys, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, hist, (size_t)n_chunks, (size_t)c);
+blk_hist1_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ total,
+                 uint32_t* __restrict__ hist, uint32_t* __restrict__ sizes) {
+    const uint32_t c = blockIdx.x;
+    const uint32_t tot = *total, nc1 = blk_nc1(tot);
+    if (c == 0 && threadIdx.x == 0) sizes[0] = (uint32_t)ND * nc1;
+    if (c >= nc1) return;
+    const uint32_t lo = c * PCH;
+    blk_hist_chunk(keys, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, hist, (size_t)nc1, (size_t)c);
 }
 
 template <bool STRANDED>
 __global__ void __launch_bounds__(PT, 5)
-blk_scatter1_kernel(int64_t n_chunks, Cands in, const uint32_t* __restrict__ total,
-                    const uint32_t* __restrict__ pos, Cands out) {
-    const int64_t c = blockIdx.x;
-    const uint32_t tot = *total, lo = min((uint32_t)(c * PCH), tot);
-    if (lo >= tot) return;          // (its histogram column is all zero)
-    blk_scatter_chunk<STRANDED>(in, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, pos, (size_t)n_chunks, (size_t)c, out);
+blk_scatter1_kernel(Cands in, const uint32_t* __restrict__ total, const uint32_t* __restrict__ pos,
+                    Cands out) {
+    const uint32_t c = blockIdx.x;
+    const uint32_t tot = *total, nc1 = blk_nc1(tot);
+    if (c >= nc1) return;
+    const uint32_t lo = c * PCH;
+    blk_scatter_chunk<STRANDED>(in, lo, min(lo + (uint32_t)PCH, tot), SHIFT1, pos, (size_t)nc1, (size_t)c, out);
 }
 
 // After pass 1: start of each top-digit run (S1[ND + 1]) and the prefix of the chunk counts of
-// pass 2 (CP[ND + 1]): run d is cut into ceil(size / PCH) chunks.  One CTA of ND threads.
+// pass 2 (CP[ND + 1]): run d is cut into ceil(size / PCH) chunks; sizes[1] = entries of the
+// pass-2 histogram.  One CTA of ND threads.
 __global__ void __launch_bounds__(ND)
-blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hist1 + total */,
-                uint32_t* __restrict__ S1, uint32_t* __restrict__ CP) {
+blk_runs_kernel(const uint32_t* __restrict__ cand_total, const uint32_t* __restrict__ pos /* scan of hist1 */,
+                uint32_t* __restrict__ S1, uint32_t* __restrict__ CP, uint32_t* __restrict__ sizes) {
     __shared__ uint32_t w[ND / 32];
     const int d = threadIdx.x;
-    const uint32_t total = pos[(size_t)ND * n_chunks];
-    const uint32_t s = pos[(size_t)d * n_chunks];
-    const uint32_t e = d == ND - 1 ? total : pos[(size_t)(d + 1) * n_chunks];
+    const uint32_t total = *cand_total, nc1 = blk_nc1(total);
+    const uint32_t s = total ? pos[(size_t)d * nc1] : 0u;
+    const uint32_t e = (d == ND - 1 || total == 0u) ? total : pos[(size_t)(d + 1) * nc1];
     S1[d] = s;
     if (d == ND - 1) S1[ND] = total;
     const uint32_t nch = (e - s + PCH - 1) / PCH;
@@ -851,7 +860,10 @@ blk_runs_kernel(int64_t n_chunks, const uint32_t* __restrict__ pos /* scan of hi
     uint32_t pre = 0;
     for (int k = 0; k < (d >> 5); k++) pre += w[k];
     CP[d] = pre + inc - nch;
-    if (d == ND - 1) CP[ND] = pre + inc;
+    if (d == ND - 1) {
+        CP[ND] = pre + inc;
+        sizes[1] = (uint32_t)ND * (pre + inc);
+    }
 }
 
 // which (run, chunk) a pass-2 CTA owns; false past the last chunk
@@ -1472,7 +1484,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
     const int64_t n_chunks = (rd.n + PCH - 1) / PCH + 1;                       // pass-1 chunks (upper bound)
     const int64_t tc_upper = (rd.n + PCH - 1) / PCH + ND;                      // pass-2 chunks
     Cands ca, cb;
-    uint32_t *cand_total, *hist1, *hist2, *S1, *CP, *blk_off;
+    uint32_t *cand_total, *scan_sizes, *hist1, *hist2, *S1, *CP, *blk_off;
     size_t zero_bytes = 0;
     {
         const size_t t = (size_t)T, c = (size_t)n_cell, nc = (size_t)n_chunks, cap = nc * PCH;
@@ -1480,17 +1492,18 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         RCP_TRY(w.B.reserve(Arena::pad((c + 1) * 4) + Arena::pad((size_t)w.bm_words * 4) +
                             Arena::pad((t + 1) * 4) + Arena::pad((size_t)ND * (size_t)tc_upper * 4 + 4) +
                             Arena::pad(t * 8) * 2 + Arena::pad(cap * 4) * 4 + st_bytes * 2 +
-                            Arena::pad(nc * 4) + Arena::pad(((size_t)ND * nc + 1) * 4) + Arena::pad((ND + 1) * 4) * 2 +
+                            Arena::pad(8) * 2 + Arena::pad(((size_t)ND * nc + 1) * 4) + Arena::pad((ND + 1) * 4) * 2 +
                             Arena::pad(((size_t)N_BLOCKS + 1) * 4)));
         // zero-initialised block first: cell counts (unused here, but bkt_tiles_kernel bumps them),
-        // bitmap, tile flags, pass-2 histogram
+        // bitmap, tile flags, candidate counter (the histograms are written in full by their kernels)
         w.cells.cnt = w.B.take<uint32_t>(c + 1);
         w.cells.bitmap = w.B.take<uint32_t>((size_t)w.bm_words);
         w.tile_cnt = w.B.take<uint32_t>(t + 1);
-        hist2 = w.B.take<uint32_t>((size_t)ND * (size_t)tc_upper + 1);
-        cand_total = w.B.take<uint32_t>(nc);          // [0] = number of candidates
-        hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
+        cand_total = w.B.take<uint32_t>(1);           // number of candidates
         zero_bytes = w.B.used;
+        scan_sizes = w.B.take<uint32_t>(2);           // entries of the pass-1 / pass-2 histograms
+        hist1 = w.B.take<uint32_t>((size_t)ND * nc + 1);
+        hist2 = w.B.take<uint32_t>((size_t)ND * (size_t)tc_upper + 1);
         w.tiles.a = w.B.take<uint2>(t);
         w.tiles.b = w.B.take<uint2>(t);
         ca.s = w.B.take<uint32_t>(cap);
@@ -1531,23 +1544,23 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
     }
     {
         StageTimer t(ST_BLK_HIST);          // pass 1
-        blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca.s, cand_total, hist1);
+        blk_hist1_kernel<<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(ca.s, cand_total, hist1, scan_sizes);
         RCP_LAUNCHED();
-        RCP_TRY(exclusive_scan_u32(hist1, hist1, (int64_t)ND * n_chunks, hist1 + (int64_t)ND * n_chunks));
+        RCP_TRY(exclusive_scan_u32_bounded(hist1, hist1, (int64_t)ND * n_chunks, scan_sizes, nullptr));
     }
     {
         StageTimer t(ST_BLK_SCATTER);
-        if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
-        else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(n_chunks, ca, cand_total, hist1, cb);
+        if (st_arr) blk_scatter1_kernel<true><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(ca, cand_total, hist1, cb);
+        else blk_scatter1_kernel<false><<<(unsigned)n_chunks, PT, 0, g_ctx.stream>>>(ca, cand_total, hist1, cb);
         RCP_LAUNCHED();
     }
     {
         StageTimer t(ST_BLK_HIST);          // pass 2
-        blk_runs_kernel<<<1, ND, 0, g_ctx.stream>>>(n_chunks, hist1, S1, CP);
+        blk_runs_kernel<<<1, ND, 0, g_ctx.stream>>>(cand_total, hist1, S1, CP, scan_sizes);
         RCP_LAUNCHED();
         blk_hist2_kernel<<<(unsigned)tc_upper, PT, 0, g_ctx.stream>>>(cb.s, CP, S1, hist2);
         RCP_LAUNCHED();
-        RCP_TRY(exclusive_scan_u32(hist2, hist2, (int64_t)ND * tc_upper, hist2 + (int64_t)ND * tc_upper));
+        RCP_TRY(exclusive_scan_u32_bounded(hist2, hist2, (int64_t)ND * tc_upper, scan_sizes + 1, nullptr));
     }
     {
         StageTimer t(ST_BLK_SCATTER);

@@ -207,6 +207,10 @@ int sort_pairs_u32(uint32_t* keys_in_out, uint32_t* vals_in_out, int64_t n, int 
 // on the DEVICE (d_total) -- nothing is synchronised.
 int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, int64_t* d_total);
 int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* d_total);
+// the same over the first min(n_upper, *n_dev) elements: the length lives on the device, the
+// launch is sized for n_upper and the blocks beyond the real length return at once
+int exclusive_scan_u32_bounded(const uint32_t* in, uint32_t* out, int64_t n_upper, const uint32_t* n_dev,
+                               uint32_t* d_total);
 int exclusive_scan2_i64(const int64_t* in0, int64_t* out0, int64_t* d_total0, const int64_t* in1,
                         int64_t* out1, int64_t* d_total1, int64_t n);
 

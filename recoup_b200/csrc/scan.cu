@@ -17,7 +17,15 @@ struct ScanArgs {
     V* out[NC];
     V* partial[NC];
     V* total[NC];   // device scalars, may be null
+    const uint32_t* n_dev = nullptr;   // optional device-side length (<= the host-side n)
 };
+
+template <class V, int NC>
+__device__ __forceinline__ int64_t scan_length(const ScanArgs<V, NC>& a, int64_t n) {
+    if (a.n_dev == nullptr) return n;
+    const int64_t m = (int64_t)*a.n_dev;
+    return m < n ? m : n;
+}
 
 template <class V>
 __device__ __forceinline__ V warp_inclusive(V v) {
@@ -53,6 +61,12 @@ __device__ __forceinline__ V block_exclusive(V v, V* total) {
 template <class V, int NC>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(ScanArgs<V, NC> a, int64_t n) {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    n = scan_length(a, n);
+    if (base >= n) {                // beyond the device-side length: contributes nothing
+        if (threadIdx.x == 0)
+            for (int c = 0; c < NC; c++) a.partial[c][blockIdx.x] = 0;
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         V s = 0;
@@ -88,6 +102,8 @@ template <class V, int NC>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(ScanArgs<V, NC> a, int64_t n) {
     // blocked arrangement: thread t owns SCAN_ITEMS consecutive elements
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    n = scan_length(a, n);
+    if ((int64_t)blockIdx.x * SCAN_TILE >= n) return;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         V v[SCAN_ITEMS];
@@ -147,6 +163,17 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* d
     a.partial[0] = nullptr;
     a.total[0] = d_total;
     return scan_impl<uint32_t, 1>(a, n);
+}
+
+int exclusive_scan_u32_bounded(const uint32_t* in, uint32_t* out, int64_t n_upper, const uint32_t* n_dev,
+                               uint32_t* d_total) {
+    ScanArgs<uint32_t, 1> a;
+    a.in[0] = in;
+    a.out[0] = out;
+    a.partial[0] = nullptr;
+    a.total[0] = d_total;
+    a.n_dev = n_dev;
+    return scan_impl<uint32_t, 1>(a, n_upper);
 }
 
 int exclusive_scan2_i64(const int64_t* in0, int64_t* out0, int64_t* d_total0, const int64_t* in1,
