@@ -1,5 +1,8 @@
 // Coverage without a sort (sm_100a): calcCoverage / coverageFromRanges of the reference
-// (/root/reference/R/coverage.R:126-226) straight from the UNSORTED reads.
+// (/root/reference/R/coverage.R:126-226) straight from the UNSORTED reads.  Two ways of doing it
+// live here and share the region plan, the tiles and the scan / store code (cov_common.cuh):
+// the BUCKET path (bkt_*, described next; default for masks of short regions) and the BLOCK path
+// (blk_*, described at "BLOCKS mode" below; default for masks made of tiled regions).
 //
 // Only reads that overlap a region contribute to that region's coverage, and a region's coverage
 // does not depend on the order of its reads.  So instead of sorting every read by coordinate
