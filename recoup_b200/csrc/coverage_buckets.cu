@@ -965,7 +965,7 @@ blk_any_kernel(int64_t T, Tiles tiles, Cands c, const uint32_t* __restrict__ bof
     for (uint32_t i0 = c0; i0 < c1 && !any; i0 += 32) {
         const uint32_t i = i0 + lane;
         bool hit = false;
-        if (i < c1) hit = blk_hit(__ldg(c.s + i), __ldg(c.e + i), stranded ? (int)__ldg(c.st + i) : 0, ts, tl,
+        if (i < c1) hit = blk_hit(__ldg(c.s + i), __ldg(c.e + i), (stranded && c.st) ? (int)__ldg(c.st + i) : 0, ts, tl,
                                   flags, stranded != 0, &packed);
         any = __any_sync(0xffffffffu, hit);
     }
@@ -1020,7 +1020,7 @@ __device__ __forceinline__ void blk_tile_body(int* diff, int* wtot, const TileDe
     const uint32_t n = d.n;
     const uint32_t* cs = c.s + d.b0;
     const uint32_t* ce = c.e + d.b0;
-    const int8_t* ct = STRANDED ? c.st + d.b0 : nullptr;
+    const int8_t* ct = (STRANDED && c.st) ? c.st + d.b0 : nullptr;    // no strand array: every read is '*'
     uint32_t s[B], e[B];
     int st[B];
     auto load = [&](uint32_t i0) {
@@ -1030,7 +1030,7 @@ __device__ __forceinline__ void blk_tile_body(int* diff, int* wtot, const TileDe
             const bool ok = i < n;
             s[k] = ok ? __ldg(cs + i) : 0u;
             e[k] = ok ? __ldg(ce + i) : 0u;            // end 0: never a hit
-            st[k] = (STRANDED && ok) ? (int)__ldg(ct + i) : 0;
+            st[k] = (STRANDED && ok && ct) ? (int)__ldg(ct + i) : 0;
         }
     };
     load(0);
@@ -1115,7 +1115,7 @@ blk_small_kernel(int64_t Ts, const TileDesc* __restrict__ desc, Cands c, int str
     for (uint32_t i = lane; i < d.n; i += 32) {
         const uint32_t s = __ldg(c.s + d.b0 + i), e1 = __ldg(c.e + d.b0 + i);
         uint32_t packed;
-        if (blk_hit(s, e1, stranded ? (int)__ldg(c.st + d.b0 + i) : 0, ts, (uint32_t)L, flags, stranded != 0,
+        if (blk_hit(s, e1, (stranded && c.st) ? (int)__ldg(c.st + d.b0 + i) : 0, ts, (uint32_t)L, flags, stranded != 0,
                     &packed)) {
             const int lo = (int)(packed & 0xffffu), hi = (int)(packed >> 16);
             atomicAdd(diff + lo, 1);
@@ -1579,7 +1579,7 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         RCP_LAUNCHED();
         if (T > 0) {
             blk_any_kernel<<<blocks_for(T, WARPS), CTA, 0, g_ctx.stream>>>(T, w.tiles, ca, blk_off, max_w,
-                                                                           st_arr ? 1 : 0, w.tile_cnt);
+                                                                           stranded ? 1 : 0, w.tile_cnt);
             RCP_LAUNCHED();
         }
         if (R > 0) {
@@ -1615,13 +1615,13 @@ static int blocks_ranges_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, con
         RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blk_tile_kernel, CTA, 0));
         if (per_sm < 1) per_sm = 1;
         blk_tile_kernel<<<(unsigned)std::min<int64_t>(Tb, (int64_t)g_ctx.sm_count * per_sm), CTA, 0,
-                          g_ctx.stream>>>(Tb, w.desc, ca, st_arr ? 1 : 0, cv->cov);
+                          g_ctx.stream>>>(Tb, w.desc, ca, stranded ? 1 : 0, cv->cov);
         RCP_LAUNCHED();
     }
     if (Ts > 0) {
         StageTimer t(ST_BLK_SMALL);
         blk_small_kernel<<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, w.desc + Tb, ca,
-                                                                         st_arr ? 1 : 0, cv->cov);
+                                                                         stranded ? 1 : 0, cv->cov);
         RCP_LAUNCHED();
     }
     return RCP_OK;

@@ -170,6 +170,12 @@ def test_pileups_long_reads_and_no_strand(gpu):
     # ignore.strand=FALSE with strandless reads: '*' reads match every region
     got2 = rb.calcCoverage(g_reads, g_mask, ignore_strand=False)
     assert_coverage_equal(got2.to_list(), want)
+    # a strand pre-filter sees only '*' reads: "+" keeps none (every region NULL), "*" keeps all
+    for filt, code in (("+", 1), ("-", -1), ("*", 0)):
+        want_f = O.calc_coverage(o_reads, o_mask, code, True)
+        got_f = rb.calcCoverage(g_reads, g_mask, strand=filt)
+        assert_coverage_equal(got_f.to_list(), want_f)
+        assert all(w is None for w in want_f) == (filt != "*")
 
 
 def test_empty_inputs(gpu):
