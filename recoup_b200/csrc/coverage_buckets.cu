@@ -1289,7 +1289,10 @@ int coverage_ranges_bucketed(ReadsIdx& rd, int64_t R, const int32_t* chrom, cons
     // has no per-read random access (C2 1.40 vs 1.54 ms, C3 7.7 vs 8.0 ms); masks dominated by
     // short regions keep the buckets: a short region would scan every candidate of its 16-kb block
     // (C5 at 1/4 scale: 2.84 vs 2.35 ms).
-    if (may_switch && Ts * 4 <= Tb && rd.n < 0xfffff000ll && getenv("RCP_AUTO_NO_BLOCKS") == nullptr)
+    // (a tile looks back by the widest read for its candidates: a sample with very long reads
+    // would make every tile scan many blocks, so those stay with the buckets too)
+    if (may_switch && Ts * 4 <= Tb && rd.n < 0xfffff000ll && rd.max_width <= (2u << BM_SHIFT) &&
+        getenv("RCP_AUTO_NO_BLOCKS") == nullptr)
         return blocks_ranges_impl(rd, R, chrom, start, end, strand, ignore_strand, strand_filter, mem, cv,
                                   &w, Tb, Ts);
 
