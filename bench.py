@@ -385,6 +385,8 @@ def run_b200(args):
     for e in gissued:
         e.set()
 
+    gfail = []
+
     def gather_worker():
         torch.cuda.set_device(dev)
         while True:
@@ -392,8 +394,12 @@ def run_b200(args):
             if item is None:
                 return
             k, ready = item
-            gdone[k % 2] = gather_issue(k, ready)
-            gissued[k % 2].set()
+            try:
+                gdone[k % 2] = gather_issue(k, ready)
+            except BaseException as exc:    # never leave the main thread waiting for this gather
+                gfail.append(exc)
+            finally:
+                gissued[k % 2].set()
 
     gthread = None
     if world > 1 and args.exchange == "nccl" and not os.environ.get("RCP_BENCH_INLINE_GATHER"):
@@ -403,6 +409,8 @@ def run_b200(args):
     def gather_drain():
         for e in gissued:
             e.wait()
+        if gfail:
+            raise gfail[0]
 
     def gather_step(k=0):
         """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) and their
