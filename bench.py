@@ -244,7 +244,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a mismatched collective must fail in a minute, not hang the box until the watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=90))
     rb.init(local)
     rb.set_coverage_path(args.path)
     L = _lib.lib
@@ -483,12 +486,15 @@ def run_b200(args):
     # the same steps running (untimed) for a second so that the clock record is taken UNDER THIS
     # LOAD.  The sampler polls nvidia-smi (a driver-lock heavy call), so it is stopped before the
     # host-API (e2e) loop.
-    t_probe = time.time()
-    k = args.steps
-    while time.time() - t_probe < 1.0:
+    # The number of extra steps is agreed by all ranks (rank 0 derives it from the max-over-ranks
+    # step time and broadcasts it): every rank issues the same number of gathers.
+    n_probe = torch.tensor([max(1, min(4000, int(1000.0 / max(elapsed_ms / args.steps, 1e-3))))],
+                           dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_probe, op=dist.ReduceOp.MIN)
+    for k in range(args.steps, args.steps + int(n_probe.item())):
         device_step(k)
         gather_step(k)
-        k += 1
     barrier()
     clocks = sampler.stop(t_begin, time.time(), "timed region + 1 s of the same steps (untimed)")
 
