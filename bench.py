@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--read-order", default="random", choices=["random", "coordinate"],
                     help="order of the synthetic reads: as generated (random; the default and the "
                          "harder case) or sorted by chromosome and start like a coordinate-sorted BAM")
-    ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets", "blocks"],
+    ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets", "blocks", "split"],
                     help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
 
@@ -342,7 +342,7 @@ def run_b200(args):
             stats["total_len"], stats["n_null"] = tl.value, nn.value
             pth, cand = C.c_int(0), C.c_int64(0)
             L.rcp_coverage_path_info(cov.value, C.byref(pth), C.byref(cand))
-            stats["path"] = {0: "list", 1: "index", 2: "buckets", 3: "blocks"}[pth.value]
+            stats["path"] = {0: "list", 1: "index", 2: "buckets", 3: "blocks", 4: "split"}[pth.value]
             stats["candidates"] = cand.value
         if out_box["ptr"] is not None:      # peer-mapped matrix of rank 0 / verification buffer
             out_ptr = out_box["ptr"]
@@ -649,6 +649,9 @@ def run_b200(args):
             "blk_scatter": 16 * cand,
             "blk_tile": 4 * total_len + 8 * cand,
             "blk_small": 4 * total_len + 8 * cand,
+            "sp_split": 8 * N,
+            "sp_tile": 4 * total_len + 4 * cand,
+            "sp_small": 4 * total_len + 4 * cand,
             "index_map": 22 * N,
             "index_sort": 8 * N,
             "cov_tile": 8 * N + 4 * total_len + 16 * R,
@@ -664,7 +667,8 @@ def run_b200(args):
             "reads_map": (["index_map"], 22 * N),
             "coverage": (["index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
                           "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small",
-                          "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small"],
+                          "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small",
+                          "sp_plan", "sp_split", "sp_sort", "sp_tile", "sp_small"],
                          8 * N + 4 * total_len + 16 * R),
             "profile": (["prof_bin", "prof_interp", "prof_base"], 4 * total_len + 8 * R * ncols),
         }

@@ -95,6 +95,14 @@ int rcp_timing_read(int reset, int capacity, double* ms_out, int64_t* count_out)
 const char* rcp_timing_stage_name(int stage);
 
 /* How rcp_coverage (GRanges masks) finds the reads of each region.  All give identical results.
+ *   RCP_PATH_SPLIT    ONE streaming pass over the unsorted reads: a block bitmap of the mask in
+ *                     shared memory filters them, the survivors are packed into 32-bit words and
+ *                     split into <= 1024 groups of the mask's blocks through shared-memory rings
+ *                     (64-byte chunks, no histogram pass, no prefix sum over the reads); each
+ *                     group is then sorted by 2-kb sub-bin and every output tile reads the
+ *                     sub-bins under it.  The host synchronises once, right after the plan.
+ *                     Needs reads narrower than the packed word allows (<= 8191 bp, less for
+ *                     dense masks / stranded calls); otherwise the call uses the paths below;
  *   RCP_PATH_BUCKETS  two passes over the unsorted reads drop each read into the buckets of the
  *                     output tiles it overlaps (cell table + hit list, no sort);
  *   RCP_PATH_BLOCKS   the reads that pass a block bitmap are partitioned by 16-kb genome block
@@ -102,20 +110,30 @@ const char* rcp_timing_stage_name(int stage);
  *                     scans the candidates of the blocks under it;
  *   RCP_PATH_INDEX    the reads are radix-sorted once per handle and every region is served by
  *                     rank searches (cheaper when one handle serves many masks);
- *   RCP_PATH_AUTO     (default) the index when the handle already has one or the mask is dense
- *                     and the reads many; else blocks for masks made of tiled regions (> 1024 bp:
- *                     TSS windows, gene bodies), buckets for masks dominated by short regions.
+ *   RCP_PATH_AUTO     (default) the index when the handle already has one; else split when the
+ *                     reads fit its packed word; else the index when the mask is dense and the
+ *                     reads many, blocks for masks made of tiled regions (> 1024 bp: TSS windows,
+ *                     gene bodies), buckets for masks dominated by short regions.
  * The reference has one path (findOverlaps per region, coverage.R:189-193); this is a tuning
  * knob with no counterpart there. */
 #define RCP_PATH_AUTO 0
 #define RCP_PATH_INDEX 1
 #define RCP_PATH_BUCKETS 2
 #define RCP_PATH_BLOCKS 3
+#define RCP_PATH_SPLIT 4
 int rcp_set_coverage_path(int path);
 /* Which path produced a coverage (RCP_PATH_INDEX / BUCKETS / BLOCKS; 0 for GRangesList and
  * concatenated coverages) and, for the block path, how many reads passed its bitmap filter
  * (bench.py derives that path's algorithmic bytes from it). */
 int rcp_coverage_path_info(int cov, int* path, int64_t* candidates);
+
+/* Deferred validation of the reads (default off).  When on, rcp_reads_load* return as soon as
+ * their work is enqueued -- no host synchronisation -- and a data error of the reads (bad
+ * chromosome id, start < 1, ...) is reported by the FIRST call that uses the reads handle
+ * (rcp_coverage, rcp_coverage_list) instead of by the load itself.  Host arrays passed to a
+ * deferred load must stay unchanged until that call returns.  The reference validates inside
+ * GRanges construction; which call raises is the only difference. */
+int rcp_set_deferred_validation(int on);
 
 /* ---------------------------------------------------------------- base-R RNG -------------- */
 /* `set.seed(seed); sample(1:n, k)` -- the bin layout of splitVector (util.R:78-79). */

@@ -17,7 +17,7 @@ WHERE = {"whole": 0, "center": 1, "upstream": 2, "downstream": 3}
 STAT = {"mean": 0, "median": 1}
 INTERP = {"auto": 0, "spline": 1, "linear": 2, "neighborhood": 3}
 SAMPLE_KIND = {"Rejection": 0, "Rounding": 1}
-COVERAGE_PATH = {"auto": 0, "index": 1, "buckets": 2, "blocks": 3}
+COVERAGE_PATH = {"auto": 0, "index": 1, "buckets": 2, "blocks": 3, "split": 4}
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -38,6 +38,7 @@ SIGNATURES = {
     "rcp_sync": (C.c_int, []),
     "rcp_launch_count": (C.c_int64, [C.c_int]),
     "rcp_set_coverage_path": (C.c_int, [C.c_int]),
+    "rcp_set_deferred_validation": (C.c_int, [C.c_int]),
     "rcp_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "rcp_host_free": (C.c_int, [C.c_void_p]),
     "rcp_timing_enable": (C.c_int, [C.c_int]),

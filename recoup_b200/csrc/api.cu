@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -104,7 +105,8 @@ static int64_t g_stage_count[ST_N];
 static const char* const g_stage_names[ST_N] = {
     "index_map", "index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
     "prof_bin", "prof_interp", "prof_base", "fused", "bkt_plan", "bkt_count", "bkt_scatter",
-    "bkt_tile", "bkt_small", "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small"};
+    "bkt_tile", "bkt_small", "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small",
+    "sp_plan", "sp_split", "sp_sort", "sp_tile", "sp_small"};
 
 static cudaEvent_t take_event() {
     if (!g_free_events.empty()) {
@@ -244,6 +246,9 @@ int coverage_list(ReadsIdx& rd, int64_t G, const int64_t* ptr, const int64_t n_r
 int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                            const int32_t* end, const int8_t* strand, int ignore_strand,
                            int strand_filter, int mem, Coverage* cv);
+int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                          const int32_t* end, const int8_t* strand, int ignore_strand,
+                          int strand_filter, int mem, Coverage* cv);
 int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv);
 int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
                    int64_t capacity);
@@ -519,9 +524,14 @@ const char* rcp_timing_stage_name(int stage) {
 
 int rcp_set_coverage_path(int path) {
     if (path != RCP_PATH_AUTO && path != RCP_PATH_INDEX && path != RCP_PATH_BUCKETS &&
-        path != RCP_PATH_BLOCKS)
+        path != RCP_PATH_BLOCKS && path != RCP_PATH_SPLIT)
         return fail(RCP_ERR_ARG, "unknown coverage path %d", path);
     g_ctx.coverage_path = path;
+    return RCP_OK;
+}
+
+int rcp_set_deferred_validation(int on) {
+    g_ctx.deferred_validation = on != 0;
     return RCP_OK;
 }
 
@@ -708,18 +718,33 @@ int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32
                                : (r->cls[CLS_PLUS].built && r->cls[CLS_MINUS].built &&
                                   r->cls[CLS_STAR].built);
     }
-    int rc = RCP_SWITCH_TO_INDEX;
-    if (g_ctx.coverage_path == RCP_PATH_BLOCKS) {
-        rc = coverage_ranges_blocks(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
-                                    strand_filter, mem, cv);
-    } else if (!use_index) {
-        rc = coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
-                                      strand_filter, mem, g_ctx.coverage_path == RCP_PATH_AUTO, cv);
-        if (rc == RCP_SWITCH_TO_INDEX) coverage_release(*cv);      // dense mask, very many reads
+    // The split path (one streaming pass over the unsorted reads) serves every GRanges mask it can
+    // (reads narrower than the packed candidate word allows); it also validates a deferred load.
+    int rc = RCP_SPLIT_NOT_APPLICABLE;
+    const bool try_split = g_ctx.coverage_path == RCP_PATH_SPLIT ||
+                           (g_ctx.coverage_path == RCP_PATH_AUTO && !use_index &&
+                            getenv("RCP_AUTO_NO_SPLIT") == nullptr);
+    if (try_split) {
+        rc = coverage_ranges_split(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                   strand_filter, mem, cv);
     }
-    if (rc == RCP_SWITCH_TO_INDEX)
-        rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
-                             strand_filter, mem, cv);
+    if (rc == RCP_SPLIT_NOT_APPLICABLE) {
+        rc = reads_resolve(*r);
+        if (rc == RCP_OK) rc = RCP_SWITCH_TO_INDEX;
+        if (rc == RCP_SWITCH_TO_INDEX && g_ctx.coverage_path == RCP_PATH_BLOCKS) {
+            rc = coverage_ranges_blocks(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                        strand_filter, mem, cv);
+        } else if (rc == RCP_SWITCH_TO_INDEX && !use_index) {
+            rc = coverage_ranges_bucketed(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                          strand_filter, mem,
+                                          g_ctx.coverage_path == RCP_PATH_AUTO ||
+                                              g_ctx.coverage_path == RCP_PATH_SPLIT, cv);
+            if (rc == RCP_SWITCH_TO_INDEX) coverage_release(*cv);      // dense mask, very many reads
+        }
+        if (rc == RCP_SWITCH_TO_INDEX)
+            rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                 strand_filter, mem, cv);
+    }
     if (rc != RCP_OK) {
         drop_coverage(h);
         return rc;
@@ -744,6 +769,7 @@ int rcp_coverage_list(int reads, int64_t n_elements, const int64_t* ptr, const i
     if (ptr[0] != 0) return fail(RCP_ERR_ARG, "ptr[0] must be 0");
     const int64_t n_ranges = ptr[n_elements];
     if (n_ranges > 0 && (!chrom || !start || !end)) return fail(RCP_ERR_ARG, "rcp_coverage_list: NULL array");
+    RCP_TRY(reads_resolve(*r));
     Coverage* cv;
     int h;
     RCP_TRY(new_coverage(&cv, &h));
@@ -786,6 +812,7 @@ int rcp_coverage_info(int cov, int64_t* n_regions, int64_t* total_len, int64_t* 
                       double* scale) {
     Coverage* cv = get_coverage(cov);
     if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (total_len || n_null) RCP_TRY(coverage_resolve_stats(*cv));
     if (n_regions) *n_regions = cv->n_regions;
     if (total_len) *total_len = cv->total_len;
     if (n_null) *n_null = cv->n_null;
@@ -796,6 +823,7 @@ int rcp_coverage_info(int cov, int64_t* n_regions, int64_t* total_len, int64_t* 
 int rcp_coverage_path_info(int cov, int* path, int64_t* candidates) {
     Coverage* cv = get_coverage(cov);
     if (!cv) return fail(RCP_ERR_HANDLE, "unknown coverage handle %d", cov);
+    if (candidates) RCP_TRY(coverage_resolve_stats(*cv));
     if (path) *path = cv->path;
     if (candidates) *candidates = cv->candidates;
     return RCP_OK;

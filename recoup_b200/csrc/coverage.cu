@@ -752,6 +752,22 @@ void coverage_release(Coverage& c) {
     dfree(c.off);
     dfree(c.len);
     dfree(c.is_null);
+    dfree(c.d_stats);
+    c.stats_pending = false;
+}
+
+// split path: n_null / total_len / max_len / candidates were produced after the call returned
+int coverage_resolve_stats(Coverage& c) {
+    if (!c.stats_pending) return RCP_OK;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    const FetchItem items[1] = {{c.d_stats, h, 32}};
+    RCP_TRY(fetch_and_sync(items, 1));
+    c.n_null = (int64_t)h[0];
+    c.total_len = (int64_t)h[1];
+    c.max_len = (int32_t)h[2];
+    c.candidates = (int64_t)h[3];
+    c.stats_pending = false;
+    return RCP_OK;
 }
 
 int coverage_ranges(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,

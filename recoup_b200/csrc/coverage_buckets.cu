@@ -1132,27 +1132,7 @@ blk_small_kernel(int64_t Ts, const TileDesc* __restrict__ desc, Cands c, int str
 // Device scratch of one call.  Three arenas (one allocation each: the host is on the critical
 // path right after the two synchronisation points, and ~30 stream-ordered allocations plus as
 // many frees cost more than the small kernels between them): A sized by the regions, B by the
-// tiles / cells / reads, C by the hits.  Sub-buffers are 256-byte aligned.
-struct Arena {
-    char* base = nullptr;
-    size_t used = 0, cap = 0;
-    static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
-    int reserve(size_t bytes) {
-        cap = bytes;
-        used = 0;
-        return device_alloc(reinterpret_cast<void**>(&base), bytes > 0 ? bytes : 1);
-    }
-    template <class T>
-    T* take(size_t n) {
-        T* p = reinterpret_cast<T*>(base + used);
-        used += pad(n * sizeof(T));
-        return p;
-    }
-    ~Arena() {
-        if (base) device_free(base);
-    }
-};
-
+// tiles / cells / reads, C by the hits.  (Arena: rcp_internal.cuh)
 struct Work {
     Arena A, B, C;
     uint32_t* gs = nullptr;

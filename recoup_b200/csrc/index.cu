@@ -329,6 +329,11 @@ inline unsigned grid_for(int64_t n) {
 }  // namespace
 
 void reads_release(ReadsIdx& r) {
+    dfree(r.pd_err);
+    dfree(r.pd_cnt);
+    dfree(r.pd_w);
+    dfree(r.pd_run_first);
+    r.pending = false;
     dfree(r.d_chrom_len);
     dfree(r.d_chrom_off);
     dfree(r.g_start);
@@ -611,29 +616,64 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
                 exc);
         RCP_LAUNCHED();
     }
-    unsigned int h_err = 0, h_w[2] = {0, 0}, h_total = 0;
-    unsigned long long h_cnt[4] = {0, 0, 0, 0};
     lap("map kernel enqueued");
-    {
-        FetchItem items[4] = {{d_err, &h_err, 4}, {d_cnt, h_cnt, 32}, {d_w, h_w, 8}, {nullptr, &h_total, 4}};
-        if (rle) items[3].dev = run_first + n_runs;
-        RCP_TRY(fetch_and_sync(items, rle ? 4 : 3));
-    }
+    r.pending = true;
+    r.pd_rle = rle;
+    r.pd_err = d_err;
+    r.pd_cnt = d_cnt;
+    r.pd_w = d_w;
+    r.pd_run_first = run_first;
+    r.pd_run_total = rle ? run_first + n_runs : nullptr;
+    r.pd_exc_cap = exc.cap;
+    r.pd_eager_index = eager_index;
+    r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
+    // Deferred validation: the status words stay on the device until the first call that uses
+    // the handle reads them (that call reports a data error of these reads).
+    if (g_ctx.deferred_validation && !eager_index) return RCP_OK;
+    RCP_TRY(reads_resolve(r));
     lap("sync (copies + map kernel)");
-    dfree(d_err);
-    dfree(d_cnt);
-    dfree(d_w);
-    dfree(run_first);
+    return RCP_OK;
+}
+
+int reads_pending_items(ReadsIdx& r, FetchItem* items, int* n) {
+    if (!r.pending) return RCP_OK;
+    items[(*n)++] = {r.pd_err, &r.h_err, 4};
+    items[(*n)++] = {r.pd_cnt, r.h_cnt, 32};
+    items[(*n)++] = {r.pd_w, r.h_w, 8};
+    if (r.pd_rle) items[(*n)++] = {r.pd_run_total, &r.h_total, 4};
+    return RCP_OK;
+}
+
+int reads_resolve(ReadsIdx& r) {
+    if (!r.pending) return RCP_OK;
+    FetchItem items[4];
+    int n = 0;
+    reads_pending_items(r, items, &n);
+    RCP_TRY(fetch_and_sync(items, n));
+    return reads_finish(r);
+}
+
+// what follows the fetch of the status words (the caller has synchronised)
+int reads_finish(ReadsIdx& r) {
+    if (!r.pending) return RCP_OK;
+    r.pending = false;
+    const int64_t n = r.n;
+    const unsigned int h_err = r.h_err;
+    dfree(r.pd_err);
+    dfree(r.pd_cnt);
+    dfree(r.pd_w);
+    dfree(r.pd_run_first);
+    r.pd_run_total = nullptr;
     if (h_err & 8u) return fail(RCP_ERR_DATA, "a seqnames run has a negative length");
-    if (rle && (int64_t)h_total != n)
-        return fail(RCP_ERR_DATA, "the seqnames run lengths sum to %u, not to the %lld reads", h_total,
+    if (r.pd_rle && (int64_t)r.h_total != n)
+        return fail(RCP_ERR_DATA, "the seqnames run lengths sum to %u, not to the %lld reads", r.h_total,
                     (long long)n);
     // (nearly) every read has the same width w -- fixed-length or fragment-extended libraries;
     // the few that do not (trimmed at a chromosome end) live in a correction source.  Then the
     // sorted ends are the sorted starts shifted by w: one array, one sort.
-    if (h_err == 0 && n > 0 && h_w[1] > 0 && h_w[0] <= exc.cap) {
-        r.uniform_w = h_w[1];
-        r.n_exc = (int64_t)h_w[0];
+    if (h_err == 0 && n > 0 && r.h_w[1] > 0 && r.h_w[0] <= r.pd_exc_cap) {
+        r.uniform_w = r.h_w[1];
+        r.n_exc = (int64_t)r.h_w[0];
     } else {
         r.uniform_w = 0;
         r.n_exc = 0;
@@ -646,15 +686,11 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     if (h_err & 1u) return fail(RCP_ERR_DATA, "a read has a chromosome id outside [0, n_chrom)");
     if (h_err & 2u) return fail(RCP_ERR_DATA, "a read violates 1 <= start <= end");
     if (h_err & 4u) return fail(RCP_ERR_DATA, "a read starts beyond the end of its chromosome");
-    r.cls[CLS_PLUS].n = (int64_t)h_cnt[0];
-    r.cls[CLS_MINUS].n = (int64_t)h_cnt[1];
-    r.cls[CLS_STAR].n = (int64_t)h_cnt[2];
-    r.max_width = (uint32_t)h_cnt[3];
-    if (eager_index) {
-        RCP_TRY(reads_build_class(r, CLS_ALL));
-        lap("class ALL enqueued");
-    }
-    r.device_bytes += (size_t)n * (8 + (r.has_strand ? 1 : 0));
+    r.cls[CLS_PLUS].n = (int64_t)r.h_cnt[0];
+    r.cls[CLS_MINUS].n = (int64_t)r.h_cnt[1];
+    r.cls[CLS_STAR].n = (int64_t)r.h_cnt[2];
+    r.max_width = (uint32_t)r.h_cnt[3];
+    if (r.pd_eager_index) RCP_TRY(reads_build_class(r, CLS_ALL));
     return RCP_OK;
 }
 

@@ -20,11 +20,13 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;      // kernels launched by this library
     int coverage_path = RCP_PATH_AUTO;
+    bool deferred_validation = false;   // rcp_set_deferred_validation
 };
 extern Ctx g_ctx;
 
 int fail(int code, const char* fmt, ...);   // records the message, returns code
 constexpr int RCP_SWITCH_TO_INDEX = -1000;   // internal: the bucket path hands the call to the index path
+constexpr int RCP_SPLIT_NOT_APPLICABLE = -1001;   // internal: the split path cannot serve this call
 int require_ready();                         // RCP_OK or RCP_ERR_NOGPU
 
 #define RCP_CUDA(call)                                                                         \
@@ -72,6 +74,11 @@ enum Stage {
     ST_BLK_SCATTER,     // block path: blk_scatter1/2_kernel (one launch per pass)
     ST_BLK_TILE,        // block path: blk_tile_kernel
     ST_BLK_SMALL,       // block path: blk_small_kernel
+    ST_SP_PLAN,         // split path: windows, bitmap + ranks, tiles, descriptors, NULL rule
+    ST_SP_SPLIT,        // split path: sp_split_kernel (filter + one-pass split into groups)
+    ST_SP_SORT,         // split path: chunk lists per group + sp_group_kernel (sub-bin sort)
+    ST_SP_TILE,         // split path: sp_tile_kernel
+    ST_SP_SMALL,        // split path: sp_small_kernel
     ST_N
 };
 struct StageTimer {
@@ -109,6 +116,27 @@ struct FetchItem {
     int bytes;      // <= 32, a multiple of 4
 };
 int fetch_and_sync(const FetchItem* items, int n);      // n <= 8
+
+// Device scratch of one call: one allocation, sub-buffers 256-byte aligned.
+struct Arena {
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    int reserve(size_t bytes) {
+        cap = bytes;
+        used = 0;
+        return device_alloc(reinterpret_cast<void**>(&base), bytes > 0 ? bytes : 1);
+    }
+    template <class T>
+    T* take(size_t n) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += pad(n * sizeof(T));
+        return p;
+    }
+    ~Arena() {
+        if (base) device_free(base);
+    }
+};
 
 // A caller array that must be readable on the device: either the caller's own device pointer or
 // a stream-ordered staging copy of host memory.
@@ -172,7 +200,26 @@ struct ReadsIdx {
     int8_t* p_strand = nullptr;         // strand in start-sorted order (nullptr when !has_strand)
     uint32_t* p_maxend1 = nullptr;      // running max of p_end1
     size_t device_bytes = 0;
+    // Deferred validation (rcp_set_deferred_validation): rcp_reads_load returned without waiting
+    // for the map kernel; its status words are still on the device and are read by the first
+    // call that uses the handle (reads_resolve, or the split path's own plan fetch).
+    bool pending = false;
+    bool pd_rle = false;
+    unsigned int* pd_err = nullptr;
+    unsigned long long* pd_cnt = nullptr;
+    unsigned int* pd_w = nullptr;
+    uint32_t* pd_run_total = nullptr;   // owner: pd_run_first
+    uint32_t* pd_run_first = nullptr;
+    uint32_t pd_exc_cap = 0;
+    bool pd_eager_index = false;
+    unsigned int h_err = 0, h_w[2] = {0, 0}, h_total = 0;
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
 };
+
+// deferred validation: the fetch items of a pending handle (appended), and what follows the fetch
+int reads_pending_items(ReadsIdx& r, FetchItem* items, int* n);
+int reads_finish(ReadsIdx& r);
+int reads_resolve(ReadsIdx& r);     // fetch + finish when pending
 
 int reads_build_class(ReadsIdx& r, int cls);   // lazily build a strand class
 int reads_build_pairs(ReadsIdx& r);            // lazily build the start-sorted pair arrays
@@ -186,7 +233,11 @@ struct Coverage {
     int64_t n_null = 0;
     int32_t max_len = 0;         // longest region (sizes the staging buffers of the bin kernel)
     int path = 0;                // RCP_PATH_* that produced it (0: list / concat)
-    int64_t candidates = 0;      // block path: reads that passed the bitmap filter
+    int64_t candidates = 0;      // block / split path: reads that passed the bitmap filter
+    // split path: n_null / total_len / candidates are produced on the device after the call has
+    // returned; they are fetched on first use (coverage_resolve_stats)
+    unsigned long long* d_stats = nullptr;   // [0] n_null [1] total_len [2] max_len [3] candidates
+    bool stats_pending = false;
     double scale = 1.0;
     int32_t* cov = nullptr;      // dense int32, region r at [off[r], off[r] + len[r])
     int64_t* off = nullptr;      // n_regions + 1, multiples of 32 ints
@@ -194,6 +245,7 @@ struct Coverage {
     uint8_t* is_null = nullptr;  // n_regions
 };
 void coverage_release(Coverage& c);
+int coverage_resolve_stats(Coverage& c);
 
 ReadsIdx* get_reads(int h);
 Coverage* get_coverage(int h);

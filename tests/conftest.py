@@ -18,11 +18,11 @@ def fixture_data():
     return np.load(os.path.join(ROOT, "tests", "golden", "recoup_test_data.npz"))
 
 
-@pytest.fixture(scope="session", params=["auto", "buckets", "index", "blocks"])
+@pytest.fixture(scope="session", params=["auto", "split", "buckets", "index", "blocks"])
 def gpu(request):
     """Binds the CUDA library to cuda:0; fails (never skips) when the GPU path is unusable.
     Every parity test runs once per coverage path (buckets / sorted index / the automatic choice
-    between them / the experimental block partition): all must match the oracle bit for bit."""
+    between them / the one-pass split / the block partition): all must match the oracle bit for bit."""
     import recoup_b200 as rb
     rb.init(0)
     rb.set_coverage_path(request.param)
