@@ -3,23 +3,21 @@
 // over the reads and no per-read random access outside shared memory.
 //
 //   plan     regions -> windows (geometry / NULL rules of coverage.R:209,217-222), tile counts,
-//            storage offsets, and a 1-bit-per-16-kb BLOCK BITMAP of the mask.  A rank table over
-//            the bitmap numbers the set blocks 0 .. n_set-1 ("compacted genome"): consecutive
-//            ranks are cut into <= 1024 GROUPS of 2^gshift blocks.
-//   split    every read is tested against the bitmap in shared memory; a survivor is clipped to
-//            the set blocks it touches, packed into ONE 32-bit word (position inside its group |
-//            strand class | width) and appended to its group's 32-entry ring in shared memory
-//            (one shared-memory atomic).  Full 16-entry chunks leave as 64-byte stores into a
-//            chunk pool; a chunk carries its group in a 2-byte tag.  No histogram pass, no global
-//            atomics per read, no prefix sum over the reads.
+//            storage offsets, and a 1-bit-per-16-kb BLOCK BITMAP of the mask.
+//   split    the genome is cut into <= 1024 GROUPS of 2^P positions (P from the genome length
+//            alone).  Every read is tested against the bitmap in shared memory; a survivor is
+//            packed into ONE 32-bit word (position inside its group | strand class | width) and
+//            appended to its group's 32-entry ring in shared memory (one shared-memory atomic).
+//            Full 16-entry chunks leave as 64-byte stores into a chunk pool; a chunk carries its
+//            group in a 2-byte tag.  No histogram pass, no global atomic per read, no prefix sum
+//            over the reads.
 //   sort     the chunk tags are counting-sorted by group (three tiny kernels over ~N/16 tags);
-//            then one CTA per group sorts the group's candidates by 2-kb sub-bin of the compacted
-//            genome (shared-memory histogram + cursors) into one dense candidate array and
-//            writes the sub-bin offsets.
-//   tiles    a tile (<= 7168 outputs of one region) reads the candidates of the sub-bins under
-//            it (reaching back by the widest read), clips them, builds the difference array in
-//            shared memory (atomics), scans it and writes the int32 coverage with TMA bulk
-//            stores; regions <= 1024 bp are handled by one warp each.
+//            then one CTA per group sorts the group's candidates by 1-kb sub-bin (shared-memory
+//            histogram + cursors) into one dense candidate array and writes the sub-bin offsets.
+//   tiles    one WARP per tile (<= 896 outputs of one region): the candidates of the sub-bins
+//            under it (reaching back by the widest read) are clipped into a warp-private
+//            difference array in shared memory (atomics), scanned, and written as int32 coverage
+//            by one TMA bulk store.  No block-wide barrier.
 //   NULL     a region none of whose tiles saw a read is NULL (coverage.R:198,224-225).  Its
 //            storage is allocated up front (offsets do not depend on the reads), so the host
 //            synchronises ONCE per call, right after the plan, and never in the read passes.
@@ -39,22 +37,28 @@ using namespace covk;
 namespace {
 
 constexpr int BLK_SHIFT = 14;                         // 16384-bp blocks of the bitmap
-constexpr uint32_t BLK_MASK = (1u << BLK_SHIFT) - 1u;
-constexpr int SUB_SHIFT = 11;                         // 2048-bp sub-bins of the candidate sort
-constexpr int SUBS = 1 << (BLK_SHIFT - SUB_SHIFT);    // sub-bins per block
+constexpr int SUB_SHIFT = 10;                         // 1024-bp sub-bins of the candidate sort
 constexpr int NG = 1024;                              // groups (at most)
 constexpr int RING = 32;                              // ring entries per group (power of two)
 constexpr int CH = 16;                                // entries per chunk (64 bytes)
 constexpr int ST = 1024;                              // threads of the split kernel (== NG)
 constexpr int SLAB = 64;                              // chunks a warp takes from the pool at a time
-constexpr int MAX_WORDS = 8192;                       // bitmap words (2^32 positions)
-constexpr int MIN_GSHIFT = 2;                         // >= 4 blocks per group: position field >= 16 bits
-constexpr int MAX_GSHIFT = 8;
-constexpr int GT = 512;                               // threads of the group kernel
+constexpr int MIN_P = 16, MAX_P = 22;                 // position bits of a candidate word
+constexpr int GT = 1024;                              // threads of the group kernel
 constexpr int CS = 1024;                              // threads of the chunk-sort kernels
+constexpr int WT = 7 * ROW;                           // outputs of a warp tile (896); regions <= 1024 bp are ONE tile
+constexpr int WT_ONE = SMALL_MAX;
 static_assert(ST == NG, "the flush phase maps thread t to group t");
 static_assert(RING == 2 * CH, "a ring holds two chunks");
 static_assert(SLAB >= 64, "one flush phase of a warp needs up to 64 chunks");
+
+// Block table: one 32-bit word per 16 blocks.  Bit k (k < 16): block 16 w + k is in the mask;
+// bit 16 + k: the block AFTER it is (so that one load also answers for a read that crosses into
+// the next block).
+__device__ __forceinline__ void sp_mark_block(uint32_t* __restrict__ tab, uint32_t b) {
+    atomicOr(tab + (b >> 4), 1u << (b & 15u));
+    if (b > 0) atomicOr(tab + ((b - 1u) >> 4), 0x10000u << ((b - 1u) & 15u));
+}
 
 // ---------------------------------------------------------------------------------- plan ------
 __global__ void __launch_bounds__(CTA)
@@ -62,9 +66,8 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
                const int32_t* __restrict__ end, const int8_t* __restrict__ strand,
                const uint32_t* __restrict__ chrom_off, const int64_t* __restrict__ chrom_len,
                int n_chrom, int ignore_strand, int strand_filter, uint32_t* __restrict__ gs_out,
-               int32_t* __restrict__ plen, uint8_t* __restrict__ flags, int64_t* __restrict__ nbig,
-               int64_t* __restrict__ nsmall, int64_t* __restrict__ padded,
-               uint32_t* __restrict__ bitmap, unsigned int* __restrict__ err,
+               int32_t* __restrict__ plen, uint8_t* __restrict__ flags, int64_t* __restrict__ ntile,
+               int64_t* __restrict__ padded, uint32_t* __restrict__ tab, unsigned int* __restrict__ err,
                unsigned long long* __restrict__ pstats /* [0] total len [1] max len */) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
     unsigned long long my_len = 0;
@@ -78,19 +81,12 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
         gs_out[r] = gs;
         plen[r] = len;
         flags[r] = (uint8_t)((st < 0 ? 1u : 0u) | (class_mask(st, ignore_strand, strand_filter) << 1));
-        nbig[r] = len > SMALL_MAX ? ((int64_t)len + TILE - 1) / TILE : 0;
-        nsmall[r] = (len > 0 && len <= SMALL_MAX) ? 1 : 0;
+        ntile[r] = len > WT_ONE ? ((int64_t)len + WT - 1) / WT : (len > 0 ? 1 : 0);
         padded[r] = ((int64_t)len + PAD - 1) / PAD * PAD;
         my_len = (unsigned long long)len;
         if (len > 0) {
-            const uint32_t b0 = gs >> BLK_SHIFT, b1 = (gs + (uint32_t)len - 1u) >> BLK_SHIFT;
-            for (uint32_t b = b0; b <= b1;) {
-                const uint32_t w = b >> 5, hi = min(b1, (w << 5) + 31u);
-                const uint32_t nb = hi - b + 1u;
-                const uint32_t m = (nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (b & 31u);
-                atomicOr(bitmap + w, m);
-                b = hi + 1u;
-            }
+            const uint32_t b1 = (gs + (uint32_t)len - 1u) >> BLK_SHIFT;
+            for (uint32_t b = gs >> BLK_SHIFT; b <= b1; b++) sp_mark_block(tab, b);
         }
     }
     unsigned long long my_max = my_len;
@@ -104,40 +100,6 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
     }
 }
 
-// bitmap -> (bits, set blocks before this word) per 32-block word; one CTA of 1024 threads
-__global__ void __launch_bounds__(1024)
-sp_rank_kernel(const uint32_t* __restrict__ bitmap, int words, uint2* __restrict__ tab,
-               uint32_t* __restrict__ n_set) {
-    __shared__ uint32_t wsum[32];
-    const int t = threadIdx.x;
-    constexpr int PER = MAX_WORDS / 1024;
-    uint32_t bits[PER], c = 0;
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int w = t * PER + k;
-        bits[k] = w < words ? bitmap[w] : 0u;
-        c += __popc(bits[k]);
-    }
-    uint32_t inc = c;
-    const unsigned lane = t & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= (unsigned)d) inc += o;
-    }
-    if (lane == 31) wsum[t >> 5] = inc;
-    __syncthreads();
-    uint32_t run = inc - c;
-    for (int k = 0; k < (t >> 5); k++) run += wsum[k];
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int w = t * PER + k;
-        if (w < words) tab[w] = make_uint2(bits[k], run);
-        run += __popc(bits[k]);
-    }
-    if (t == 1023) *n_set = run;
-}
-
 __device__ __forceinline__ int64_t sp_owner_of(const int64_t* __restrict__ off, int64_t R, int64_t t) {
     int64_t lo = 0, hi = R;
     while (hi - lo > 1) {
@@ -146,13 +108,6 @@ __device__ __forceinline__ int64_t sp_owner_of(const int64_t* __restrict__ off, 
         else hi = mid;
     }
     return lo;
-}
-
-// rank of block b among the set blocks (for an unset block: the rank of the next set one)
-__device__ __forceinline__ uint32_t sp_rank(const uint2* __restrict__ tab, uint32_t b, bool* set) {
-    const uint2 w = __ldg(tab + (b >> 5));
-    *set = (w.x >> (b & 31u)) & 1u;
-    return w.y + __popc(w.x & ((1u << (b & 31u)) - 1u));
 }
 
 // Everything a tile kernel needs in one 32-byte record.
@@ -166,50 +121,34 @@ struct __align__(16) SpDesc {
     uint32_t region;
 };
 
-// One thread per tile: where it lies (tiles are cut in OUTPUT space, as in the other paths) and
-// which candidates can reach it.  boff is read later (sp_range_kernel): it does not exist yet
-// when the tiles are laid out, so the record keeps the sub-bin indices in c0 / n meanwhile.
+// One thread per tile: where it lies (tiles are cut in OUTPUT space, as in the other paths: on a
+// '-' region tile j covers the mirrored positions) and which candidates can reach it: those that
+// start from (tile start - widest read + 1) on.  boff is read later (sp_range_kernel): it does
+// not exist yet when the tiles are laid out, so the record keeps the sub-bin indices in c0 / n
+// meanwhile.
 __global__ void __launch_bounds__(CTA)
-sp_tiles_kernel(int64_t R, int64_t Tb, int64_t Ts, const int64_t* __restrict__ off_big,
-                const int64_t* __restrict__ off_small, const uint32_t* __restrict__ gs,
+sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, const uint32_t* __restrict__ gs,
                 const int32_t* __restrict__ plen, const uint8_t* __restrict__ flags,
-                const int64_t* __restrict__ cov_off, const uint2* __restrict__ tab, uint32_t max_w,
-                uint32_t pmask, SpDesc* __restrict__ desc) {
+                const int64_t* __restrict__ cov_off, uint32_t max_w, uint32_t pmask,
+                SpDesc* __restrict__ desc) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
-    if (t >= Tb + Ts) return;
-    int64_t r;
-    uint32_t o_lo, tlen, tstart;
-    if (t < Tb) {
-        r = sp_owner_of(off_big, R, t);
-        const int j = (int)(t - off_big[r]);
-        const int L = plen[r];
-        const int m = (L + TILE - 1) / TILE;
-        const int tile_len = (((L + m - 1) / m) + ROW - 1) / ROW * ROW;
-        o_lo = (uint32_t)(j * tile_len);
-        tlen = (uint32_t)min(tile_len, L - (int)o_lo);
-        const uint32_t q0 = (flags[r] & 1u) ? (uint32_t)L - o_lo - tlen : o_lo;
-        tstart = gs[r] + q0;
-    } else {
-        r = sp_owner_of(off_small, R, t - Tb);
-        o_lo = 0;
-        tlen = (uint32_t)plen[r];
-        tstart = gs[r];
+    if (t >= T) return;
+    const int64_t r = sp_owner_of(off_tile, R, t);
+    const int L = plen[r];
+    uint32_t o_lo = 0, tlen = (uint32_t)L;
+    if (L > WT_ONE) {
+        o_lo = (uint32_t)(t - off_tile[r]) * WT;
+        tlen = (uint32_t)min(WT, L - (int)o_lo);
     }
-    // candidates that can reach [tstart, tstart + tlen): those homed from (tstart - widest + 1) on
+    const uint32_t q0 = (flags[r] & 1u) ? (uint32_t)L - o_lo - tlen : o_lo;
+    const uint32_t tstart = gs[r] + q0;
     const uint32_t first = tstart >= max_w ? tstart - max_w + 1u : 0u;
-    const uint32_t last = tstart + tlen - 1u;
-    bool set;
-    const uint32_t rf = sp_rank(tab, first >> BLK_SHIFT, &set);
-    const uint32_t bin_lo = rf * SUBS + (set ? ((first & BLK_MASK) >> SUB_SHIFT) : 0u);
-    const uint32_t rl = sp_rank(tab, last >> BLK_SHIFT, &set);          // a tile's own blocks are set
-    const uint32_t bin_hi = rl * SUBS + ((last & BLK_MASK) >> SUB_SHIFT);
-    const uint32_t rs = sp_rank(tab, tstart >> BLK_SHIFT, &set);
     SpDesc d;
     d.out = cov_off[r] + o_lo;
-    d.c0 = bin_lo;
-    d.n = bin_hi + 1u;
+    d.c0 = first >> SUB_SHIFT;
+    d.n = ((tstart + tlen - 1u) >> SUB_SHIFT) + 1u;
     d.tlen = (int32_t)tlen;
-    d.cts = ((rs << BLK_SHIFT) | (tstart & BLK_MASK)) & pmask;
+    d.cts = tstart & pmask;
     d.flags = flags[r];
     d.region = (uint32_t)r;
     desc[t] = d;
@@ -227,41 +166,40 @@ sp_range_kernel(int64_t T, const uint32_t* __restrict__ boff, SpDesc* __restrict
 }
 
 // --------------------------------------------------------------------------------- split ------
-// One read -> (group, packed word), or false when no block it touches is in the mask.  The read
-// is clipped to the set blocks it touches (the part inside an unset block cannot reach any
-// region), so that every candidate lies inside consecutive ranks of the compacted genome.
-template <bool STRANDED>
-__device__ __forceinline__ bool sp_classify(uint32_t s, uint32_t e1, int st, const uint2* tab,
-                                            int gshift, int P, uint32_t* g, uint32_t* packed) {
-    if (e1 <= s) return false;
-    const uint32_t b0 = s >> BLK_SHIFT, b1 = (e1 - 1u) >> BLK_SHIFT;
-    uint2 w = tab[b0 >> 5];
-    bool set0 = (w.x >> (b0 & 31u)) & 1u;
-    uint32_t home = b0;
-    if (b1 != b0) {                                   // at most two blocks: width < 16384
-        const uint2 w1 = tab[b1 >> 5];
-        const bool set1 = (w1.x >> (b1 & 31u)) & 1u;
-        if (set0) {
-            if (!set1) e1 = b1 << BLK_SHIFT;
-        } else {
-            if (!set1) return false;
-            s = b1 << BLK_SHIFT;
-            home = b1;
-            w = w1;
-            set0 = true;
-        }
-    }
-    if (!set0) return false;
-    const uint32_t rank = w.y + __popc(w.x & ((1u << (home & 31u)) - 1u));
-    *g = rank >> gshift;
-    uint32_t word = ((rank & ((1u << gshift) - 1u)) << BLK_SHIFT) | (s & BLK_MASK);
-    int sh = P;
-    if (STRANDED) {
-        word |= (st > 0 ? 0u : (st < 0 ? 1u : 2u)) << P;
-        sh += 2;
-    }
-    *packed = word | ((e1 - s) << sh);
-    return true;
+// shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loop)
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ int lds_s8(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts8(uint32_t a, int v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
 }
 
 struct SplitOut {
@@ -270,25 +208,66 @@ struct SplitOut {
     uint32_t* pool_next;     // chunks handed out so far (in SLABs)
 };
 
+// Shared memory of the split kernel: rings | ring counters | block table.
+constexpr size_t sp_split_smem(int words) {
+    return (size_t)NG * RING * 4 + (size_t)NG * 4 + (size_t)words * 4;
+}
+constexpr size_t SP_SMEM_MAX = 232448;                // 227 KB: the most one CTA can have on sm_100
+
+// A round = ST x RPT reads.  Per read: one table load answers "is any block it touches in the
+// mask"; a survivor takes a slot of its group's ring with ONE shared-memory atomic and stores its
+// packed word there.  Then the CTA meets, thread t flushes the complete chunks of ring t, and reads
+// that found their ring full go round again.  A warp that has seen a full ring (coordinate-sorted
+// input: everything goes to one group) sends whole 16-entry runs of one group straight to a pool
+// chunk from then on.
 template <bool STRANDED>
 __global__ void __launch_bounds__(ST, 1)
 sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t* __restrict__ g_end1,
-                const int8_t* __restrict__ strand, const uint2* __restrict__ tab_g, int words,
-                int gshift, int P, SplitOut out) {
+                const int8_t* __restrict__ strand, const uint32_t* __restrict__ tab_g, int words, int P,
+                SplitOut out) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
-    uint32_t* ring = reinterpret_cast<uint32_t*>(sp_smem);            // NG * RING
-    uint32_t* cnt = ring + NG * RING;                                 // NG: ring start << 16 | fill
-    uint2* tab = reinterpret_cast<uint2*>(cnt + NG);                  // words
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
-    for (int i = tid; i < words; i += ST) tab[i] = tab_g[i];
-    cnt[tid] = 0;
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(sp_smem);     // NG * RING words
+    const uint32_t cnt_a = ring_a + NG * RING * 4;                            // NG: ring start << 16 | fill
+    const uint32_t tab_a = cnt_a + NG * 4;                                    // block table
+    for (int i = tid; i < words; i += ST) sts32(tab_a + i * 4, tab_g[i]);
+    sts32(cnt_a + tid * 4, 0u);
     __syncthreads();
+    const uint32_t pmask = (1u << P) - 1u;
+    const int wsh = STRANDED ? P + 2 : P;
     uint32_t slab_next = 0, slab_end = 0;          // this warp's share of the chunk pool
+    uint32_t spare = 0;                            // lane 0: the next slab, requested ahead of need
+    bool have_spare = false;
+    bool hot = false;                              // this warp has met a full ring
+
+    // `total` chunks for this warp (warp-uniform); chunk i of them is chunk_at(i)
+    uint32_t a_rem = 0, a_old = 0, a_new = 0;
+    auto alloc = [&](uint32_t total) {
+        a_rem = slab_end - slab_next;
+        a_old = slab_next;
+        a_new = 0;
+        if (total > a_rem) {
+            if (!have_spare && lane == 0) spare = atomicAdd(out.pool_next, (uint32_t)SLAB);
+            a_new = __shfl_sync(0xffffffffu, spare, 0);
+            have_spare = false;
+            slab_next = a_new + (total - a_rem);
+            slab_end = a_new + SLAB;
+        } else {
+            slab_next += total;
+        }
+        // request the next slab well before this one runs out: the atomic's round trip then
+        // overlaps the following rounds instead of stalling the whole CTA at a barrier
+        if (!have_spare && slab_end - slab_next < (uint32_t)SLAB / 2) {
+            if (lane == 0) spare = atomicAdd(out.pool_next, (uint32_t)SLAB);
+            have_spare = true;
+        }
+    };
+    auto chunk_at = [&](uint32_t i) { return i < a_rem ? a_old + i : a_new + (i - a_rem); };
 
     // thread t owns group t here: every complete chunk of its ring leaves as one 64-byte store
     auto flush_phase = [&](bool final_pass) {
-        const uint32_t w = cnt[tid];
+        const uint32_t w = lds32(cnt_a + tid * 4);
         const uint32_t raw = w & 0xffffu, start = w >> 16;
         const uint32_t nn = min(raw, (uint32_t)RING);
         const uint32_t k = final_pass ? (nn > 0u ? 1u : 0u) : nn / CH;
@@ -296,49 +275,81 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
         const uint32_t total = __popc(m1) + __popc(m2);
         if (total) {                                // warp-uniform
             const uint32_t idx = __popc(m1 & lt) + __popc(m2 & lt);
-            const uint32_t rem = slab_end - slab_next;
-            uint32_t nb = 0;
-            if (total > rem) {
-                if (lane == 0) nb = atomicAdd(out.pool_next, (uint32_t)SLAB);
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-            }
+            alloc(total);
             for (uint32_t j = 0; j < k; j++) {
-                const uint32_t i = idx + j;
-                const uint32_t c = i < rem ? slab_next + i : nb + (i - rem);
-                const uint4* src = reinterpret_cast<const uint4*>(ring + tid * RING + ((start + CH * j) & (RING - 1)));
+                const uint32_t c = chunk_at(idx + j);
+                const uint32_t src = ring_a + (uint32_t)tid * RING * 4 + (((start + CH * j) & (RING - 1)) << 2);
                 uint4* dst = reinterpret_cast<uint4*>(out.pool + (size_t)c * CH);
-                const uint4 a = src[0], b = src[1], cc = src[2], d = src[3];
+                const uint4 a = lds128(src), b = lds128(src + 16), cc = lds128(src + 32), d = lds128(src + 48);
                 __stcs(dst, a);
                 __stcs(dst + 1, b);
                 __stcs(dst + 2, cc);
                 __stcs(dst + 3, d);
                 out.meta[c] = (uint16_t)(((uint32_t)tid << 5) | (final_pass ? nn : (uint32_t)CH));
             }
-            if (total > rem) {
-                slab_next = nb + (total - rem);
-                slab_end = nb + SLAB;
-            } else {
-                slab_next += total;
-            }
         }
         if (k || raw > (uint32_t)RING)
-            cnt[tid] = final_pass ? 0u : ((((start + CH * k) & (RING - 1)) << 16) | (nn - CH * k));
+            sts32(cnt_a + tid * 4, final_pass ? 0u : ((((start + CH * k) & (RING - 1)) << 16) | (nn - CH * k)));
     };
 
-    // up to four reads per thread and round; a read that finds its ring full waits for the flush
-    auto insert_round = [&](const uint32_t* gk, const uint32_t* pk, uint32_t pend) {
-        for (;;) {
+    // is any block the read touches in the mask?  (crossing reads look at the "next block" bit)
+    auto keep_read = [&](uint32_t s, uint32_t e1) -> bool {
+        const uint32_t t = lds32(tab_a + ((s >> (BLK_SHIFT + 2)) & 0xfffffffcu)) >> ((s >> BLK_SHIFT) & 15u);
+        const bool cross = ((e1 - 1u) >> BLK_SHIFT) != (s >> BLK_SHIFT);
+        return (t & 1u) | (cross & ((t >> 16) & 1u));
+    };
+    auto pack = [&](uint32_t s, uint32_t e1, int st) -> uint32_t {
+        uint32_t word = (s & pmask) | ((e1 - s) << wsh);
+        if (STRANDED) word |= (st > 0 ? 0u : (st < 0 ? 1u : 2u)) << P;
+        return word;
+    };
+    // one insertion attempt; false: the ring is full until the next flush
+    auto insert = [&](uint32_t g, uint32_t pk) -> bool {
+        const uint32_t old = atoms_add(cnt_a + g * 4, 1u);
+        const uint32_t slot = old & 0xffffu;
+        if (slot >= (uint32_t)RING) return false;
+        sts32(ring_a + g * (RING * 4) + ((((old >> 16) + slot) & (RING - 1)) << 2), pk);
+        return true;
+    };
+    // hot warps: when every pending read of this k is about ONE group, whole 16-entry runs go
+    // straight to pool chunks; the rest takes the ring
+    auto direct = [&](bool want, uint32_t g, uint32_t pk) -> bool {
+        const unsigned mo = __ballot_sync(0xffffffffu, want);
+        if (mo == 0u) return want;
+        const uint32_t g0 = __shfl_sync(0xffffffffu, g, __ffs(mo) - 1);
+        const uint32_t nact = __popc(mo);
+        if (nact < (uint32_t)CH || !__all_sync(0xffffffffu, !want || g == g0)) return want;
+        const uint32_t nfull = nact / CH;
+        alloc(nfull);
+        const uint32_t r = __popc(mo & lt);           // rank among the pending lanes
+        if (want && r < nfull * CH) {
+            const uint32_t c = chunk_at(r / CH);
+            out.pool[(size_t)c * CH + (r & (CH - 1))] = pk;
+            if ((r & (CH - 1)) == 0) out.meta[c] = (uint16_t)((g0 << 5) | (uint32_t)CH);
+            return false;
+        }
+        return want;
+    };
+
+    constexpr int RPT = 8;                          // reads per thread and round (two 16-byte loads per array)
+    auto do_round = [&](const uint32_t* sv, const uint32_t* ev, const int* tv) {
+        uint32_t gk[RPT], pk[RPT], pend = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if ((pend >> k) & 1u) {
-                    const uint32_t old = atomicAdd(&cnt[gk[k]], 1u);
-                    const uint32_t slot = old & 0xffffu;
-                    if (slot < (uint32_t)RING) {
-                        ring[gk[k] * RING + (((old >> 16) + slot) & (RING - 1))] = pk[k];
-                        pend &= ~(1u << k);
-                    }
-                }
+        for (int k = 0; k < RPT; k++) {
+            gk[k] = sv[k] >> P;
+            pk[k] = pack(sv[k], ev[k], tv[k]);
+            if (keep_read(sv[k], ev[k])) pend |= 1u << k;
+        }
+        for (;;) {
+            if (hot) {
+#pragma unroll
+                for (int k = 0; k < RPT; k++)
+                    if (!direct((pend >> k) & 1u, gk[k], pk[k])) pend &= ~(1u << k);
             }
+#pragma unroll
+            for (int k = 0; k < RPT; k++)
+                if (((pend >> k) & 1u) && insert(gk[k], pk[k])) pend &= ~(1u << k);
+            hot = hot || __any_sync(0xffffffffu, pend != 0u);
             const int any = __syncthreads_or(pend != 0u);
             flush_phase(false);
             __syncthreads();
@@ -346,48 +357,46 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
         }
     };
 
+    // round r covers the 16-byte vectors [r * 2 * ST, (r + 1) * 2 * ST): thread t takes vectors
+    // r * 2 * ST + t and + ST + t (both coalesced across the CTA)
     const int64_t n_vec = n >> 2;
-    const int64_t rounds = (n_vec + ST - 1) / ST;
-    int64_t round = blockIdx.x;
-    uint4 s4 = make_uint4(0, 0, 0, 0), e4 = make_uint4(0, 0, 0, 0);
-    char4 t4 = make_char4(0, 0, 0, 0);
-    auto load = [&](int64_t rd, uint4* s, uint4* e, char4* t) {
-        const int64_t v = rd * ST + tid;
-        *s = make_uint4(0, 0, 0, 0);
-        *e = make_uint4(0, 0, 0, 0);
-        *t = make_char4(0, 0, 0, 0);
-        if (v < n_vec) {
-            *s = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
-            *e = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
-            if (STRANDED && strand) *t = __ldcs(reinterpret_cast<const char4*>(strand) + v);
+    const int rounds = (int)((n_vec + 2 * ST - 1) / (2 * ST));
+    int round = blockIdx.x;
+    uint4 s4[2], e4[2];
+    char4 t4[2];
+    auto load = [&](int rd, uint4* s, uint4* e, char4* t) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int64_t v = ((int64_t)rd * 2 + h) * ST + tid;
+            s[h] = make_uint4(0, 0, 0, 0);
+            e[h] = make_uint4(0, 0, 0, 0);
+            t[h] = make_char4(0, 0, 0, 0);
+            if (v < n_vec) {
+                s[h] = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
+                e[h] = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
+                if (STRANDED && strand) t[h] = __ldcs(reinterpret_cast<const char4*>(strand) + v);
+            }
         }
     };
-    if (round < rounds) load(round, &s4, &e4, &t4);
+    if (round < rounds) load(round, s4, e4, t4);
     while (round < rounds) {
-        const int64_t nr = round + gridDim.x;
-        uint4 s4n, e4n;
-        char4 t4n;
-        if (nr < rounds) load(nr, &s4n, &e4n, &t4n);      // in flight while this round is split
-        uint32_t gk[4], pk[4], pend = 0;
-        if (sp_classify<STRANDED>(s4.x, e4.x, t4.x, tab, gshift, P, &gk[0], &pk[0])) pend |= 1u;
-        if (sp_classify<STRANDED>(s4.y, e4.y, t4.y, tab, gshift, P, &gk[1], &pk[1])) pend |= 2u;
-        if (sp_classify<STRANDED>(s4.z, e4.z, t4.z, tab, gshift, P, &gk[2], &pk[2])) pend |= 4u;
-        if (sp_classify<STRANDED>(s4.w, e4.w, t4.w, tab, gshift, P, &gk[3], &pk[3])) pend |= 8u;
-        insert_round(gk, pk, pend);
+        const int nr = round + (int)gridDim.x;
+        const uint32_t sv[RPT] = {s4[0].x, s4[0].y, s4[0].z, s4[0].w, s4[1].x, s4[1].y, s4[1].z, s4[1].w};
+        const uint32_t ev[RPT] = {e4[0].x, e4[0].y, e4[0].z, e4[0].w, e4[1].x, e4[1].y, e4[1].z, e4[1].w};
+        const int tv[RPT] = {t4[0].x, t4[0].y, t4[0].z, t4[0].w, t4[1].x, t4[1].y, t4[1].z, t4[1].w};
+        if (nr < rounds) load(nr, s4, e4, t4);            // in flight while this round is split
+        do_round(sv, ev, tv);
         round = nr;
-        if (round < rounds) {
-            s4 = s4n;
-            e4 = e4n;
-            t4 = t4n;
-        }
     }
     if (blockIdx.x == 0) {              // the n % 4 tail
-        uint32_t gk[4], pk[4], pend = 0;
         const int64_t i = n_vec * 4 + tid;
-        if (i < n && sp_classify<STRANDED>(g_start[i], g_end1[i], (STRANDED && strand) ? (int)strand[i] : 0,
-                                           tab, gshift, P, &gk[0], &pk[0]))
-            pend = 1u;
-        insert_round(gk, pk, pend);
+        const bool in = i < n;
+        uint32_t sv[RPT] = {0u}, ev[RPT] = {0u};
+        int tv[RPT] = {0};
+        sv[0] = in ? g_start[i] : 0u;
+        ev[0] = in ? g_end1[i] : 0u;
+        tv[0] = (in && STRANDED && strand) ? (int)strand[i] : 0;
+        do_round(sv, ev, tv);
     }
     flush_phase(true);                   // what is left in the rings: one partial chunk per group
 }
@@ -460,88 +469,113 @@ sp_chunk_place_kernel(const uint16_t* __restrict__ meta, const uint32_t* __restr
 }
 
 // ------------------------------------------------------------------- candidates by sub-bin -----
-// One CTA per group: histogram of the group's candidates over its sub-bins, prefix, placement.
-// The group's output starts at CH * cb[g] (its chunk capacity: the partial chunks leave a hole of
-// zero words -- width 0, never a hit -- at the end of the group's range).
-__global__ void __launch_bounds__(GT)
+// One CTA per group (2^P positions of the genome): histogram of the group's candidates over its
+// 1-kb sub-bins, prefix, placement.  The sorted group is assembled in SHARED MEMORY (cursors are
+// shared-memory atomics) and leaves with coalesced 16-byte stores: a 4-byte store per candidate
+// to a random place costs as much as a global atomic (~180 G/s for the whole chip).  A group too
+// large for shared memory scatters directly.  The group's output starts at CH * cb[g] (its chunk
+// capacity: the partial chunks leave a hole of zero words -- width 0, never a hit -- at the end
+// of the group's range).
+constexpr size_t GSMEM = 220 * 1024;      // dynamic shared memory of the group kernel (1 CTA per SM)
+
+__global__ void __launch_bounds__(GT, 1)
 sp_group_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ list,
-                const uint32_t* __restrict__ cb, int n_groups, int gshift, uint32_t pmask,
-                uint32_t* __restrict__ cand, uint32_t* __restrict__ boff) {
-    extern __shared__ uint32_t gsm[];
-    const int nb = SUBS << gshift;                 // sub-bins of a group
+                const uint32_t* __restrict__ cb, int n_groups, int nb /* sub-bins of a group */,
+                uint32_t pmask, uint32_t* __restrict__ cand, uint32_t* __restrict__ boff) {
+    extern __shared__ __align__(16) uint32_t gsm[];
     uint32_t* h = gsm;                             // nb counts, then cursors
+    uint32_t* out = gsm + nb;                      // the sorted group
+    const uint32_t cap = (uint32_t)(GSMEM / 4) - (uint32_t)nb;
     __shared__ uint32_t wsum[GT / 32];
     const int tid = threadIdx.x, g = blockIdx.x;
     for (int i = tid; i < nb; i += GT) h[i] = 0;
     __syncthreads();
     const uint32_t c0 = cb[g], c1 = cb[g + 1];
-    const uint32_t sub = tid & (CH - 1), hw = tid / CH;           // half-warp = one chunk
-    constexpr int HW = GT / CH, U = 4;                            // chunks in flight per half-warp
-    for (uint32_t i0 = c0 + hw; i0 < c1; i0 += HW * U) {
-        uint32_t le[U], e[U];
+    // four lanes per chunk (16 bytes each): a warp reads 8 chunks with one 16-byte load per lane
+    const uint32_t q4 = (tid & 3) * 4, cw = tid >> 2;
+    constexpr uint32_t CPS = GT / 4, U = 4;                       // chunks per CTA step, steps in flight
+    // list entries are fetched one iteration ahead of the chunks they name
+    auto stream = [&](auto&& use) {
+        uint32_t le[U], ln[U];
+        uint4 e[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + (uint32_t)u * HW;
-            le[u] = i < c1 ? __ldg(list + i) : 0u;
+        for (uint32_t u = 0; u < U; u++) {
+            const uint32_t i = c0 + cw + u * CPS;
+            ln[u] = i < c1 ? __ldg(list + i) : 0u;
         }
+        for (uint32_t i0 = c0 + cw; i0 < c1; i0 += CPS * U) {
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            e[u] = sub < (le[u] & 31u) ? __ldcs(pool + (size_t)(le[u] >> 5) * CH + sub) : 0xffffffffu;
+            for (uint32_t u = 0; u < U; u++) {
+                le[u] = ln[u];
+                e[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (q4 < (le[u] & 31u))
+                    e[u] = __ldg(reinterpret_cast<const uint4*>(pool + (size_t)(le[u] >> 5) * CH + q4));
+            }
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (sub < (le[u] & 31u)) atomicAdd(&h[(e[u] & pmask) >> SUB_SHIFT], 1u);
-    }
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t i = i0 + CPS * U + u * CPS;
+                ln[u] = i < c1 ? __ldg(list + i) : 0u;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t f = le[u] & 31u;
+                if (q4 < f) use(e[u].x);
+                if (q4 + 1 < f) use(e[u].y);
+                if (q4 + 2 < f) use(e[u].z);
+                if (q4 + 3 < f) use(e[u].w);
+            }
+        }
+    };
+    stream([&](uint32_t e) { atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u); });
     __syncthreads();
-    // exclusive prefix of the nb counts (nb / GT consecutive bins per thread, nb <= 2048)
-    const int per = (nb + GT - 1) / GT;
-    uint32_t c[4], mine = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int b = tid * per + q;
-        c[q] = (q < per && b < nb) ? h[b] : 0u;
-        mine += c[q];
-    }
-    uint32_t inc = mine;
+    // exclusive prefix of the nb counts: warp w owns the bins [w * pw, (w + 1) * pw) and walks them
+    // 32 at a time (consecutive lanes, consecutive bins: no bank conflicts); the warp bases follow
+    // from the warp totals
+    constexpr int NW = GT / 32;
+    const int pw = (nb + NW - 1) / NW;
     const unsigned lane = tid & 31;
+    const int wb0 = (tid >> 5) * pw, wb1 = min(nb, wb0 + pw);
+    uint32_t carry = 0;
+    for (int b = wb0 + (int)lane; b - (int)lane < wb1; b += 32) {
+        const uint32_t c = b < wb1 ? h[b] : 0u;
+        uint32_t inc = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= (unsigned)d) inc += o;
-    }
-    if (lane == 31) wsum[tid >> 5] = inc;
-    __syncthreads();
-    uint32_t run = inc - mine;
-    for (int k = 0; k < (tid >> 5); k++) run += wsum[k];
-    const uint32_t base = c0 * CH;
-    uint32_t total = 0;
-    for (int k = 0; k < GT / 32; k++) total += wsum[k];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int b = tid * per + q;
-        if (q < per && b < nb) {
-            h[b] = run;                                         // cursor
-            boff[(size_t)g * nb + b] = base + run;
-            run += c[q];
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += o;
         }
+        if (b < wb1) h[b] = carry + inc - c;                    // relative to the warp's first bin
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) wsum[tid >> 5] = carry;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (int k = 0; k < NW; k++) {
+        if (k < (tid >> 5)) wbase += wsum[k];
+        total += wsum[k];
+    }
+    const uint32_t base = c0 * CH;
+    for (int b = wb0 + (int)lane; b < wb1; b += 32) {
+        const uint32_t o = h[b] + wbase;
+        h[b] = o;                                               // cursor
+        boff[(size_t)g * nb + b] = base + o;
     }
     if (g == n_groups - 1 && tid == 0) boff[(size_t)n_groups * nb] = base + total;
-    // the hole between this group's candidates and the next group's first
-    for (uint32_t i = base + total + tid; i < c1 * CH; i += GT) cand[i] = 0u;
     __syncthreads();
-    for (uint32_t i0 = c0 + hw; i0 < c1; i0 += HW * U) {
-        uint32_t le[U], e[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + (uint32_t)u * HW;
-            le[u] = i < c1 ? __ldg(list + i) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            e[u] = sub < (le[u] & 31u) ? __ldcs(pool + (size_t)(le[u] >> 5) * CH + sub) : 0xffffffffu;
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (sub < (le[u] & 31u)) cand[base + atomicAdd(&h[(e[u] & pmask) >> SUB_SHIFT], 1u)] = e[u];
+    if (total > cap) {          // a huge group: plain scatter, then the hole
+        stream([&](uint32_t e) { cand[base + atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u)] = e; });
+        for (uint32_t i = base + total + tid; i < c1 * CH; i += GT) cand[i] = 0u;
+        return;
     }
+    stream([&](uint32_t e) { out[atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u)] = e; });
+    // zero words up to the group's chunk capacity (a multiple of CH, so of 4): the hole
+    const uint32_t full = (c1 - c0) * CH;
+    for (uint32_t i = total + tid; i < min(full, (total + 3u) & ~3u); i += GT) out[i] = 0u;
+    __syncthreads();
+    const uint32_t n4 = (total + 3u) >> 2;                       // 16-byte words holding candidates
+    uint4* dst = reinterpret_cast<uint4*>(cand + base);           // base is a multiple of CH words
+    for (uint32_t i = tid; i < n4; i += GT) dst[i] = reinterpret_cast<const uint4*>(out)[i];
+    for (uint32_t i = n4 * 4 + tid; i < full; i += GT) cand[base + i] = 0u;
 }
 
 // --------------------------------------------------------------------------------- tiles ------
@@ -579,103 +613,112 @@ __device__ __forceinline__ bool sp_apply(uint32_t e, const SpDesc& d, int P, int
     return true;
 }
 
-template <int RPW, bool STRANDED>
-__device__ __forceinline__ bool sp_tile_body(int* diff, int* wtot, const SpDesc& d,
-                                             const uint32_t* __restrict__ cand, int P,
-                                             int32_t* __restrict__ dst) {
+// Lane-serial forward scan of a warp-private tile of RPW rows (RPW * 128 ints, zero-padded): lane
+// l owns the RPW * 4 consecutive ints at l * RPW * 4 (16-byte loads with a lane stride of
+// RPW * 16 bytes: conflict-free for odd RPW); the lane sums its run, one warp scan orders the
+// lanes, the run is rescanned from the right start and written back in place; the TMA unit then
+// stores the tile as ONE bulk copy (cp.async.bulk.global.shared::cta), so no thread spends LSU
+// wavefronts on the 4 B / base output.
+template <int RPW>
+__device__ __forceinline__ void warp_scan_store_fwd(int* diff, int tlen, int32_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    int* mine = diff + lane * 4 * RPW;
+    int4 v[RPW];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        v[k] = *(reinterpret_cast<const int4*>(mine) + k);
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const int inc = warp_inclusive_scan(sum);
+    int run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        int4 o;
+        o.x = (run += v[k].x);
+        o.y = (run += v[k].y);
+        o.z = (run += v[k].z);
+        o.w = (run += v[k].w);
+        *(reinterpret_cast<int4*>(mine) + k) = o;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        fence_proxy_async_smem();
+        tma_store_1d(dst, diff, (uint32_t)((tlen + 3) & ~3) * 4u);
+        tma_store_commit();
+    }
+}
+
+// One WARP per tile (<= 896 outputs; a region <= 1024 bp is one tile): no block-wide barrier
+// anywhere.  Persistent warps; the next tile's descriptor and its first 128 candidates are in
+// flight while the current tile is scanned and stored; longer candidate lists are read 128 at a
+// time (four loads per lane in flight).
+template <bool STRANDED>
+__global__ void __launch_bounds__(CTA, 4)
+sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
+                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit) {
+    __shared__ __align__(16) int sm[WARPS][WT_ONE];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    int* diff = sm[warp];
+    const int64_t step = (int64_t)gridDim.x * WARPS;
+    int64_t t = (int64_t)blockIdx.x * WARPS + warp;
+    if (t >= T) return;
     constexpr int B = 4;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n = d.n;
-    const uint32_t* c = cand + d.c0;
-    uint32_t e[B];
-    auto load = [&](uint32_t i0) {
+    auto load4 = [&](const SpDesc& x, uint32_t i0, uint32_t* e) {
 #pragma unroll
         for (int k = 0; k < B; k++) {
-            const uint32_t i = i0 + (uint32_t)k * CTA + tid;
-            e[k] = i < n ? __ldg(c + i) : 0u;               // 0: width 0, never a hit
+            const uint32_t i = i0 + (uint32_t)k * 32u + lane;
+            e[k] = i < x.n ? __ldg(cand + x.c0 + i) : 0u;       // 0: width 0, never a hit
         }
     };
-    load(0);
-#pragma unroll
-    for (int k = 0; k < RPW; k++)
-        reinterpret_cast<int4*>(diff)[k * CTA + tid] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-    bool hit = false;
-    for (uint32_t i0 = 0; i0 < n; i0 += B * CTA) {
-        if (i0) load(i0);
-#pragma unroll
-        for (int k = 0; k < B; k++) hit |= sp_apply<STRANDED>(e[k], d, P, diff);
-    }
-    const bool any = __syncthreads_or(hit) != 0;
-    block_scan_store_fwd<RPW, true>(diff, d.tlen, wtot, dst);
-    return any;
-}
-
-template <bool STRANDED>
-__device__ __forceinline__ bool sp_tile_dispatch(int* diff, int* wtot, const SpDesc& d,
-                                                 const uint32_t* __restrict__ cand, int P,
-                                                 int32_t* __restrict__ dst) {
-    const int rpw = ((d.tlen + ROW - 1) / ROW + WARPS - 1) / WARPS;
-    switch (rpw) {
-        case 1: return sp_tile_body<1, STRANDED>(diff, wtot, d, cand, P, dst);
-        case 2: return sp_tile_body<2, STRANDED>(diff, wtot, d, cand, P, dst);
-        case 3: return sp_tile_body<3, STRANDED>(diff, wtot, d, cand, P, dst);
-        case 4: return sp_tile_body<4, STRANDED>(diff, wtot, d, cand, P, dst);
-        case 5: return sp_tile_body<5, STRANDED>(diff, wtot, d, cand, P, dst);
-        case 6: return sp_tile_body<6, STRANDED>(diff, wtot, d, cand, P, dst);
-        default: return sp_tile_body<7, STRANDED>(diff, wtot, d, cand, P, dst);
-    }
-}
-
-template <bool STRANDED>
-__global__ void __launch_bounds__(CTA, 5)
-sp_tile_kernel(int64_t Tb, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
-               int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit) {
-    __shared__ __align__(16) int diff[TILE];
-    __shared__ int wtot[WARPS];
-    const uint32_t tid = threadIdx.x;
-    const int64_t step = gridDim.x;
-    int64_t t = blockIdx.x;
-    if (t >= Tb) return;
     SpDesc d = sp_load_desc(desc + t);
+    SpDesc dn;
+    dn.n = 0;
+    if (t + step < T) dn = sp_load_desc(desc + t + step);
+    uint32_t e[B], f[B];
+    load4(d, 0, e);
     for (;;) {
-        SpDesc dn;
-        dn.tlen = 0;
-        if (t + step < Tb) dn = sp_load_desc(desc + t + step);
-        const bool any = sp_tile_dispatch<STRANDED>(diff, wtot, d, cand, P, cov + d.out);
-        if (any && tid == 0) region_hit[d.region] = 1;
+        const bool more = t + step < T;
+        if (more) load4(dn, 0, f);                  // next tile's first candidates
+        const int rows = (d.tlen + ROW - 1) / ROW;
+        for (int k = 0; k < rows; k++) reinterpret_cast<int4*>(diff)[k * 32 + lane] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        bool hit = false;
+        for (uint32_t i0 = 0;;) {
+#pragma unroll
+            for (int k = 0; k < B; k++) hit |= sp_apply<STRANDED>(e[k], d, P, diff);
+            i0 += B * 32;
+            if (i0 >= d.n) break;
+            load4(d, i0, e);
+        }
+        hit = __any_sync(0xffffffffu, hit);
+        __syncwarp();
+        int32_t* dst = cov + d.out;
+        switch (rows) {
+            case 1: warp_scan_store_fwd<1>(diff, d.tlen, dst); break;
+            case 2: warp_scan_store_fwd<2>(diff, d.tlen, dst); break;
+            case 3: warp_scan_store_fwd<3>(diff, d.tlen, dst); break;
+            case 4: warp_scan_store_fwd<4>(diff, d.tlen, dst); break;
+            case 5: warp_scan_store_fwd<5>(diff, d.tlen, dst); break;
+            case 6: warp_scan_store_fwd<6>(diff, d.tlen, dst); break;
+            case 7: warp_scan_store_fwd<7>(diff, d.tlen, dst); break;
+            default: {      // 8 rows (a whole region of 897..1024 bp): row by row, conflict-free
+                int pre = 0;
+                for (int row = 0; row < rows; row++)
+                    pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, d.tlen - row * ROW, dst + row * ROW);
+            }
+        }
+        if (hit && lane == 0) region_hit[d.region] = 1;
         t += step;
-        if ((tid & 31u) == 0) tma_store_wait_read();
-        if (t >= Tb) break;
-        __syncthreads();
+        if (lane == 0) tma_store_wait_read();       // the bulk store has read the tile
+        if (!more) break;
+        __syncwarp();
         d = dn;
+        if (t + step < T) dn = sp_load_desc(desc + t + step);
+#pragma unroll
+        for (int k = 0; k < B; k++) e[k] = f[k];
     }
-}
-
-template <bool STRANDED>
-__global__ void __launch_bounds__(CTA)
-sp_small_kernel(int64_t Ts, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
-                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit) {
-    __shared__ __align__(16) int sm[WARPS][SMALL_MAX];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ts_i = (int64_t)blockIdx.x * WARPS + warp;
-    if (ts_i >= Ts) return;
-    const SpDesc d = sp_load_desc(desc + ts_i);
-    const int L = d.tlen;
-    int* diff = sm[warp];
-    const int nrows = (L + ROW - 1) / ROW;
-    for (int i = lane; i < nrows * (ROW / 4); i += 32)
-        reinterpret_cast<int4*>(diff)[i] = make_int4(0, 0, 0, 0);
-    __syncwarp();
-    bool hit = false;
-    for (uint32_t i = lane; i < d.n; i += 32) hit |= sp_apply<STRANDED>(__ldg(cand + d.c0 + i), d, P, diff);
-    hit = __any_sync(0xffffffffu, hit);
-    __syncwarp();
-    if (hit && lane == 0) region_hit[d.region] = 1;
-    int32_t* dst = cov + d.out;
-    int pre = 0;
-    for (int row = 0; row < nrows; row++)
-        pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, L - row * ROW, dst + row * ROW);
 }
 
 // NULL rule (coverage.R:198,224-225): no overlapping read in any tile of the region.
@@ -710,7 +753,7 @@ sp_null_kernel(int64_t R, const int32_t* __restrict__ plen, const uint8_t* __res
 }  // namespace
 
 // Same contract as coverage_ranges_bucketed.  RCP_SPLIT_NOT_APPLICABLE: the reads are too wide for
-// the packed candidate word of this mask (or the genome too long for the shared-memory table);
+// the packed candidate word of this genome (or the genome too long for the shared-memory table);
 // nothing has been produced and the caller uses another path.
 int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                           const int32_t* end, const int8_t* strand, int ignore_strand,
@@ -718,8 +761,16 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
     const bool stranded = !((strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr));
     const bool st_arr = stranded && rd.d_strand != nullptr;      // strandless reads are all '*'
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
-    const int words = (int)(((span >> BLK_SHIFT) + 32) / 32);
-    if (words > MAX_WORDS || rd.n >= 0x7ffffff0ll) return RCP_SPLIT_NOT_APPLICABLE;
+    const int words = (int)((span >> (BLK_SHIFT + 4)) + 2);
+    int P = MIN_P;
+    while (P < MAX_P && ((span + (1ll << P) - 1) >> P) > NG) P++;
+    const int n_groups = (int)std::max<int64_t>(1, (span + (1ll << P) - 1) >> P);
+    const int wbits = 32 - P - (stranded ? 2 : 0);
+    if (n_groups > NG || rd.n >= 0x7ffffff0ll || sp_split_smem(words) > SP_SMEM_MAX)
+        return RCP_SPLIT_NOT_APPLICABLE;
+    if (!rd.pending && (rd.max_width > 8191u || rd.max_width >= (1u << wbits))) return RCP_SPLIT_NOT_APPLICABLE;
+    const uint32_t pmask = (1u << P) - 1u;
+    const int nb = 1 << (P - SUB_SHIFT);                // sub-bins of a group
 
     DevIn<int32_t> d_chrom, d_start, d_end;
     DevIn<int8_t> d_strand;
@@ -731,25 +782,20 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
     // ---- plan -------------------------------------------------------------------------------
     Arena A;
     const size_t r = (size_t)R;
-    RCP_TRY(A.reserve(Arena::pad(64) + Arena::pad((size_t)words * 4) + Arena::pad((size_t)words * 8) +
-                      Arena::pad(r * 4) * 2 + Arena::pad(r) * 2 + Arena::pad(r * 8) * 3 +
-                      Arena::pad((r + 1) * 8) * 2));
-    // zero-initialised block first (ONE memset): status words, bitmap, region hit flags
-    unsigned int* err = A.take<unsigned int>(16);         // [0] err [1] n_set; pstats at +8 bytes x2
+    RCP_TRY(A.reserve(Arena::pad(64) + Arena::pad((size_t)words * 4) + Arena::pad(r * 4) * 2 + Arena::pad(r) * 2 +
+                      Arena::pad(r * 8) * 2 + Arena::pad((r + 1) * 8)));
+    // zero-initialised block first (ONE memset): status words, block table, region hit flags
+    unsigned int* err = A.take<unsigned int>(16);         // [0] err; pstats at +16 bytes
     unsigned long long* pstats = reinterpret_cast<unsigned long long*>(err + 4);   // [0] total len [1] max len
-    uint32_t* n_set = err + 1;
-    uint32_t* bitmap = A.take<uint32_t>((size_t)words);
+    uint32_t* tab = A.take<uint32_t>((size_t)words);
     uint8_t* region_hit = A.take<uint8_t>(r);
     const size_t zero_bytes = A.used;
-    uint2* tab = A.take<uint2>((size_t)words);
     uint32_t* gs = A.take<uint32_t>(r);
     int32_t* plen = A.take<int32_t>(r);
     uint8_t* flags = A.take<uint8_t>(r);
-    int64_t* nbig = A.take<int64_t>(r);
-    int64_t* nsmall = A.take<int64_t>(r);
+    int64_t* ntile = A.take<int64_t>(r);
     int64_t* padded = A.take<int64_t>(r);
-    int64_t* off_big = A.take<int64_t>(r + 1);
-    int64_t* off_small = A.take<int64_t>(r + 1);
+    int64_t* off_tile = A.take<int64_t>(r + 1);
     if (A.used > A.cap) return fail(RCP_ERR_CUDA, "internal: split plan arena overrun");
 
     cv->n_regions = R;
@@ -757,6 +803,13 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
     RCP_TRY(dalloc(&cv->len, r));
     RCP_TRY(dalloc(&cv->is_null, r));
     RCP_TRY(dalloc(&cv->d_stats, 4));
+    auto give_up = [&]() {
+        dfree(cv->off);
+        dfree(cv->len);
+        dfree(cv->is_null);
+        dfree(cv->d_stats);
+        return RCP_SPLIT_NOT_APPLICABLE;
+    };
     {
         StageTimer t(ST_SP_PLAN);
         RCP_CUDA(cudaMemsetAsync(A.base, 0, zero_bytes, g_ctx.stream));
@@ -764,48 +817,31 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
         if (R > 0) {
             sp_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
                 R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, rd.d_chrom_off, rd.d_chrom_len,
-                rd.n_chrom, ignore_strand, strand_filter, gs, plen, flags, nbig, nsmall, padded, bitmap,
-                err, pstats);
+                rd.n_chrom, ignore_strand, strand_filter, gs, plen, flags, ntile, padded, tab, err,
+                pstats);
             RCP_LAUNCHED();
         }
-        RCP_TRY(exclusive_scan2_i64(nbig, off_big, off_big + R, nsmall, off_small, off_small + R, R));
-        RCP_TRY(exclusive_scan_i64(padded, cv->off, R, cv->off + R));
-        sp_rank_kernel<<<1, 1024, 0, g_ctx.stream>>>(bitmap, words, tab, n_set);
-        RCP_LAUNCHED();
+        RCP_TRY(exclusive_scan2_i64(ntile, off_tile, off_tile + R, padded, cv->off, cv->off + R, R));
     }
     struct Host {
-        int64_t Tb, Ts, total_padded;
+        int64_t T, total_padded;
         unsigned long long pstats[2];
-        unsigned int err[2];
-    } h = {0, 0, 0, {0, 0}, {0, 0}};
+        unsigned int err;
+    } h = {0, 0, {0, 0}, 0};
     {
-        FetchItem items[8] = {{off_big + R, &h.Tb, 8}, {off_small + R, &h.Ts, 8}, {cv->off + R, &h.total_padded, 8},
-                              {pstats, h.pstats, 16}, {err, h.err, 8}};
-        int n_items = 5;
+        FetchItem items[8] = {{off_tile + R, &h.T, 8}, {cv->off + R, &h.total_padded, 8}, {pstats, h.pstats, 16},
+                              {err, &h.err, 4}};
+        int n_items = 4;
         reads_pending_items(rd, items, &n_items);       // a deferred rcp_reads_load is validated here
         RCP_TRY(fetch_and_sync(items, n_items));
         RCP_TRY(reads_finish(rd));
     }
-    if (h.err[0] & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
-    if (h.err[0] & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
-    const int64_t Tb = h.Tb, Ts = h.Ts, T = Tb + Ts;
+    if (h.err & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
+    if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
+    const int64_t T = h.T;
     if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
-    const uint32_t set_blocks = h.err[1];
-    int gshift = MIN_GSHIFT;
-    while (gshift < MAX_GSHIFT && (((int64_t)set_blocks + (1ll << gshift) - 1) >> gshift) > NG) gshift++;
-    const int n_groups = (int)std::max<int64_t>(1, ((int64_t)set_blocks + (1ll << gshift) - 1) >> gshift);
-    const int P = gshift + BLK_SHIFT;
-    const int wbits = 32 - P - (stranded ? 2 : 0);
     const uint32_t max_w = rd.max_width > 0 ? rd.max_width : 1u;
-    if (n_groups > NG || max_w > 8191u || max_w >= (1u << wbits)) {
-        dfree(cv->off);
-        dfree(cv->len);
-        dfree(cv->is_null);
-        dfree(cv->d_stats);
-        return RCP_SPLIT_NOT_APPLICABLE;
-    }
-    const uint32_t pmask = (1u << P) - 1u;
-    const int nb = SUBS << gshift;
+    if (max_w > 8191u || max_w >= (1u << wbits)) return give_up();
 
     cv->path = RCP_PATH_SPLIT;
     cv->total_padded = h.total_padded;
@@ -817,9 +853,9 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
 
     // ---- scratch of the read passes ------------------------------------------------------------
     const int split_grid = g_ctx.sm_count;
-    const int sort_grid = g_ctx.sm_count;
+    const int sort_grid = 64;          // columns of the chunk-count table (one CTA each)
     const size_t pool_cap = (size_t)(rd.n / CH + 1) + (size_t)split_grid * NG +
-                            (size_t)split_grid * (ST / 32) * SLAB + SLAB;
+                            (size_t)split_grid * (ST / 32) * SLAB * 2 + SLAB;
     Arena B;
     RCP_TRY(B.reserve(Arena::pad(pool_cap * CH * 4) * 2 + Arena::pad(pool_cap * 2) + Arena::pad(pool_cap * 4) +
                       Arena::pad(16) + Arena::pad((size_t)sort_grid * NG * 4) + Arena::pad((NG + 1) * 4) +
@@ -839,27 +875,23 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
         StageTimer t(ST_SP_PLAN);
         RCP_CUDA(cudaMemsetAsync(B.base, 0, zero_b, g_ctx.stream));
         if (T > 0) {
-            sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(
-                R, Tb, Ts, off_big, off_small, gs, plen, flags, cv->off, tab, max_w, pmask, desc);
+            sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags, cv->off,
+                                                                         max_w, pmask, desc);
             RCP_LAUNCHED();
         }
     }
     {
         StageTimer t(ST_SP_SPLIT);
-        const size_t smem = (size_t)NG * RING * 4 + (size_t)NG * 4 + (size_t)words * 8;
+        const size_t smem = sp_split_smem(words);
         SplitOut out = {pool, meta, pool_next};
-        if (st_arr) {
+        if (stranded) {     // no strand array: every read is '*'
             RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, rd.d_strand,
-                                                                         tab, words, gshift, P, out);
-        } else if (stranded) {     // no strand array: every read is '*'
-            RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, nullptr, tab,
-                                                                         words, gshift, P, out);
+            sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1,
+                                                                         st_arr ? rd.d_strand : nullptr, tab, words, P, out);
         } else {
             RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             sp_split_kernel<false><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, nullptr, tab,
-                                                                          words, gshift, P, out);
+                                                                          words, P, out);
         }
         RCP_LAUNCHED();
     }
@@ -871,8 +903,8 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
         RCP_LAUNCHED();
         sp_chunk_place_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col, list);
         RCP_LAUNCHED();
-        sp_group_kernel<<<n_groups, GT, (size_t)nb * 4, g_ctx.stream>>>(pool, list, cb, n_groups, gshift, pmask,
-                                                                      cand, boff);
+        RCP_CUDA(cudaFuncSetAttribute(sp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM));
+        sp_group_kernel<<<n_groups, GT, GSMEM, g_ctx.stream>>>(pool, list, cb, n_groups, nb, pmask, cand, boff);
         RCP_LAUNCHED();
     }
     if (T > 0) {
@@ -881,30 +913,20 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
             sp_range_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, boff, desc);
             RCP_LAUNCHED();
         }
-        if (Tb > 0) {
+        {
             StageTimer t(ST_SP_TILE);
             int per_sm = 0;
             if (stranded) {
-                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_tile_kernel<true>, CTA, 0));
+                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_wtile_kernel<true>, CTA, 0));
                 per_sm = std::max(per_sm, 1);
-                sp_tile_kernel<true><<<(unsigned)std::min<int64_t>(Tb, (int64_t)g_ctx.sm_count * per_sm), CTA, 0,
-                                       g_ctx.stream>>>(Tb, desc, cand, P, cv->cov, region_hit);
+                sp_wtile_kernel<true><<<(unsigned)std::min<int64_t>(blocks_for(T, WARPS), (int64_t)g_ctx.sm_count * per_sm),
+                                        CTA, 0, g_ctx.stream>>>(T, desc, cand, P, cv->cov, region_hit);
             } else {
-                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_tile_kernel<false>, CTA, 0));
+                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_wtile_kernel<false>, CTA, 0));
                 per_sm = std::max(per_sm, 1);
-                sp_tile_kernel<false><<<(unsigned)std::min<int64_t>(Tb, (int64_t)g_ctx.sm_count * per_sm), CTA, 0,
-                                        g_ctx.stream>>>(Tb, desc, cand, P, cv->cov, region_hit);
+                sp_wtile_kernel<false><<<(unsigned)std::min<int64_t>(blocks_for(T, WARPS), (int64_t)g_ctx.sm_count * per_sm),
+                                         CTA, 0, g_ctx.stream>>>(T, desc, cand, P, cv->cov, region_hit);
             }
-            RCP_LAUNCHED();
-        }
-        if (Ts > 0) {
-            StageTimer t(ST_SP_SMALL);
-            if (stranded)
-                sp_small_kernel<true><<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, desc + Tb, cand, P, cv->cov,
-                                                                                      region_hit);
-            else
-                sp_small_kernel<false><<<blocks_for(Ts, WARPS), CTA, 0, g_ctx.stream>>>(Ts, desc + Tb, cand, P, cv->cov,
-                                                                                       region_hit);
             RCP_LAUNCHED();
         }
     }

@@ -49,6 +49,62 @@ def reads_for_slice(read_chrom, read_start, read_end, reg_chrom, reg_start, reg_
     return keep
 
 
+def slice_spans(reg_chrom, reg_start, reg_end, parts, n_chrom, pad=0):
+    """Per rank and chromosome, the span [lo, hi] of the rank's region slice (lo > hi: the slice
+    has no region on that chromosome), widened by `pad` (the fragment length when reads are
+    extended on load).  int64 array [world, n_chrom, 2]; the input of exchange_reads."""
+    reg_chrom = np.asarray(reg_chrom, dtype=np.int64)
+    reg_start = np.asarray(reg_start, dtype=np.int64)
+    reg_end = np.asarray(reg_end, dtype=np.int64)
+    out = np.empty((len(parts), int(n_chrom), 2), dtype=np.int64)
+    out[:, :, 0] = np.iinfo(np.int64).max // 4
+    out[:, :, 1] = -1
+    for r, idx in enumerate(parts):
+        if len(idx) == 0:
+            continue
+        c = reg_chrom[idx]
+        np.minimum.at(out[r, :, 0], c, reg_start[idx] - int(pad))
+        np.maximum.at(out[r, :, 1], c, reg_end[idx] + int(pad))
+    return out
+
+
+def exchange_reads(chrom, start, end, strand, spans, group=None):
+    """The data-path exchange of the region-sharded run: every rank holds an arbitrary share of
+    the reads (torch tensors on its device: chrom / start / end int32, strand int8 or None) and
+    receives the reads that can overlap ITS region slice -- per chromosome, those meeting
+    [lo, hi] of `spans` (slice_spans).  A read at a slice boundary goes to both neighbours.  One
+    all_to_all_single for the counts, one for the packed (chrom, start, end) triples, one for the
+    strands.  world == 1 (or no process group): a local filter.  Returns the four tensors."""
+    import torch
+    import torch.distributed as dist
+
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    dev = chrom.device
+    sp = torch.as_tensor(np.ascontiguousarray(spans), device=dev)        # [world, n_chrom, 2]
+    c64 = chrom.long()
+    picks = []
+    for r in range(world):
+        m = (end.long() >= sp[r, :, 0][c64]) & (start.long() <= sp[r, :, 1][c64])
+        picks.append(torch.nonzero(m, as_tuple=False).squeeze(1))
+    order = torch.cat(picks) if world > 1 else picks[0]
+    triples = torch.stack([chrom[order], start[order], end[order]], dim=1).contiguous()
+    st = strand[order].contiguous() if strand is not None else None
+    if world == 1:
+        return triples[:, 0].contiguous(), triples[:, 1].contiguous(), triples[:, 2].contiguous(), st
+    send_counts = torch.tensor([int(p.shape[0]) for p in picks], dtype=torch.int64, device=dev)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    got = torch.empty((sum(rc), 3), dtype=triples.dtype, device=dev)
+    dist.all_to_all_single(got, triples, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    got_st = None
+    if st is not None:
+        got_st = torch.empty((sum(rc),), dtype=st.dtype, device=dev)
+        dist.all_to_all_single(got_st, st, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return got[:, 0].contiguous(), got[:, 1].contiguous(), got[:, 2].contiguous(), got_st
+
+
 class RowGather:
     """Gathers per-rank row blocks into the full matrix on rank `dst`, step after step: every
     buffer (padded send block, receive blocks, row-index lists, the full matrix) is allocated and
@@ -101,8 +157,8 @@ class RowGather:
         by the next call), else None"""
         import torch.distributed as dist
 
-        if self.equal and local.is_contiguous():
-            send = local
+        if self.equal:
+            send = local if local.is_contiguous() else local.contiguous()
         else:
             self.block[:, :self.n_local] = local
             send = self.block

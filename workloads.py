@@ -192,4 +192,36 @@ def dnase_sites(scale=1.0, seed=1005, n_reads=200_000_000, n_regions=1_000_000, 
         bin_params=dict(flankBinSize=0, regionBinSize=0, sumStat="mean", interpolation="auto"))
 
 
+def dnase_sites_part(part, n_parts=8, scale=1.0, seed=1005, n_reads=200_000_000, n_regions=1_000_000,
+                     flank=500, read_len=50, chrom_len=HG19_LEN):
+    """C5 for the strong-scaling run: the SAME sites as dnase_sites (same seed), the reads drawn in
+    `n_parts` independent parts so that W ranks can each generate the parts {p : p % W == rank}
+    and the union is the same read set for every W (checksums comparable across W)."""
+    rng = np.random.default_rng(seed)
+    N = max(int(n_reads * scale), 1000) // n_parts
+    R = max(int(n_regions * scale), 50)
+    rchrom, site = _uniform_positions(rng, R, chrom_len)
+    site = np.clip(site, flank + 1, chrom_len[rchrom] - flank)
+    rstrand = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=R)
+    prng = np.random.default_rng([seed, part + 1])
+    n_cl = N // 2
+    chrom_bg, pos_bg = _uniform_positions(prng, N - n_cl, chrom_len)
+    which = prng.integers(0, R, size=n_cl)
+    pos_cl = site[which] + prng.integers(-100, 101, size=n_cl)
+    chrom = np.concatenate([chrom_bg, rchrom[which]])
+    pos = np.concatenate([pos_bg, pos_cl])
+    start = np.clip(pos, 1, chrom_len[chrom] - read_len + 1)
+    perm = prng.permutation(N)
+    strand = prng.choice(np.array([1, -1], dtype=np.int8), size=N)
+    return dict(
+        name="C5 synthetic DNase-seq: %d reads (part %d of %d) over %d sites +-%d bp, per-base"
+             % (N, part, n_parts, R, flank),
+        chrom_names=HG19_NAMES, chrom_len=np.asarray(chrom_len, dtype=np.int64),
+        read_chrom=chrom[perm].astype(np.int32), read_start=start[perm].astype(np.int32),
+        read_end=(start[perm] + read_len - 1).astype(np.int32), read_strand=strand, frag_len=0,
+        region_chrom=rchrom, region_start=site.astype(np.int32), region_end=site.astype(np.int32),
+        region_strand=rstrand, region="custom", flank=(flank, flank),
+        bin_params=dict(flankBinSize=0, regionBinSize=0, sumStat="mean", interpolation="auto"))
+
+
 CONFIGS = {"C2": chipseq_tss, "C3": gene_bodies, "C4": rnaseq, "C5": dnase_sites}
