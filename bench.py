@@ -5,18 +5,27 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      (CPU arm: the oracle's C port on the host cores)
 
-A "step" is one pass of the hot path over one sample: rcp_reads_load (global-coordinate map +
-index sort) -> rcp_coverage (exact per-base int32 coverage of every region) ->
-rcp_profile_matrix (regions x bins fp64, column-major) [-> NCCL gather of the row blocks to rank 0
-when N > 1].  `value` times that with the decoded reads/regions already resident in HBM;
-`e2e` times the same through the public host API with pinned HOST buffers, copies included.
-Regions shard across ranks with no data-path collective except the final row gather (weak
-scaling: every rank owns a full-size region slice and its overlapping reads).
+A "step" is one pass of the hot path over one sample: rcp_reads_load (global-coordinate map) ->
+rcp_coverage (exact per-base int32 coverage of every region) -> rcp_profile_matrix (regions x
+bins fp64, column-major) [-> NCCL gather of the row blocks to rank 0 when N > 1].  `value` times
+that with the decoded reads/regions already resident in HBM; `e2e` times the same through the
+public host API with pinned HOST buffers, copies included.
+
+The JSON line carries, beside the headline (C2):
+  configs   C1, C3 (all 8 samples), C4, C5 of BASELINE.json at full size, one GPU (N = 1 only)
+  fused     the C2 step through rcp_coverage_profile (coverage not materialised)
+  strong    ONE C5 problem sharded by region over the N ranks: reads exchanged with an NCCL
+            all-to-all inside the timed region, each rank's matrix block downloaded over its own
+            PCIe link; `checksum` is the same for every N
+For N > 1 the headline itself is N independent C2 replicas (weak scaling: every rank a full-size
+sample of its own) whose row blocks are gathered to rank 0.
 """
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -31,6 +40,8 @@ import workloads as W  # noqa: E402
 
 METRIC = "reads/s through coverage + profileMatrix (reads -> per-base coverage -> regions x bins)"
 UNIT = "reads/s"
+SEEDS = {"C2": 1001, "C3": 1003, "C4": 1004, "C5": 1005}
+PATHS = {0: "list", 1: "index", 2: "buckets", 3: "blocks", 4: "split"}
 
 
 def parse_args():
@@ -42,12 +53,12 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(W.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fence", default="step", choices=["step", "end"],
-                    help="p2p exchange: all-reduce fence after every step, or only once after the "
-                         "timed steps (diagnostic: shows what the per-step fence costs)")
-    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
-                    help="N > 1: ranks store their rows straight into rank 0's matrix over NVLink "
-                         "(p2p) or the row blocks are gathered with NCCL and placed by a kernel (nccl)")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="N = 1: also run C1, C3, C4 and C5 (device-resident) and report them in `configs`")
+    ap.add_argument("--configs-scale", type=float, default=1.0,
+                    help="scale of the extra configs and of the strong-scaling problem (1.0 = the named sizes)")
+    ap.add_argument("--strong", default="on", choices=["on", "off"],
+                    help="also run ONE C5 problem sharded by region over the N ranks (`strong` in the line)")
     ap.add_argument("--read-order", default="random", choices=["random", "coordinate"],
                     help="order of the synthetic reads: as generated (random; the default and the "
                          "harder case) or sorted by chromosome and start like a coordinate-sorted BAM")
@@ -227,13 +238,338 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Problem:
+    """One workload with its reads and regions resident on the device, and the step over it:
+    rcp_reads_load -> rcp_coverage[_list / x3 + concat] -> rcp_profile_matrix, all device memory."""
+
+    def __init__(self, env, w, reads=None, region_idx=None):
+        import torch
+        self.env, self.w = env, w
+        rb, dev = env["rb"], env["dev"]
+        from recoup_b200.ranges import getFlankingRanges, getRegionalRanges
+        self.is_rna = w["region"] == "rna"
+        sel = slice(None) if region_idx is None else region_idx
+        self.genes = rb.GRanges(w["region_chrom"][sel], w["region_start"][sel], w["region_end"][sel],
+                                strand=w["region_strand"][sel], seqlevels=w["chrom_names"])
+        self.f1, self.f2 = w["flank"]
+        self.bp = w["bin_params"]
+        self.clen = np.ascontiguousarray(w["chrom_len"], dtype=np.int64)
+
+        def to_dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        if self.is_rna:
+            left = getFlankingRanges(self.genes, self.f1, "upstream")
+            right = getFlankingRanges(self.genes, self.f2, "downstream")
+            self.R = len(self.genes)
+            self.d_left = [to_dev(x) for x in (left.seqnames, left.start, left.end, left.strand)]
+            self.d_right = [to_dev(x) for x in (right.seqnames, right.start, right.end, right.strand)]
+            self.ex = [np.ascontiguousarray(w[k]) for k in ("exon_chrom", "exon_start", "exon_end", "exon_strand")]
+            self.ex_ptr = np.ascontiguousarray(w["exon_ptr"], dtype=np.int64)
+        else:
+            self.win = getRegionalRanges(self.genes, w["region"], w["flank"])
+            self.R = len(self.win)
+            self.d_win = [to_dev(x) for x in (self.win.seqnames, self.win.start, self.win.end, self.win.strand)]
+        self.equal_lengths = 1 if w["region"] in ("tss", "tes", "custom") else 0
+        self.set_reads(reads if reads is not None else
+                       [to_dev(w[k]) for k in ("read_chrom", "read_start", "read_end", "read_strand")])
+        self.ncols = None
+        self.stats = {}
+        self.out = None
+
+    def set_reads(self, d_reads):
+        self.d_reads = d_reads
+        self.N = int(d_reads[1].shape[0])
+
+    def _load(self):
+        L, _lib = self.env["L"], self.env["_lib"]
+        vp = lambda t: C.c_void_p(t.data_ptr())                # noqa: E731
+        h = C.c_int(0)
+        r = self.d_reads
+        _lib.check(L.rcp_reads_load(self.N, vp(r[0]), vp(r[1]), vp(r[2]), vp(r[3]) if r[3] is not None else None,
+                                    self.clen.shape[0], self.clen.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    int(self.w["frag_len"]), _lib.MEM_DEVICE, C.byref(h)))
+        return h
+
+    def step(self, out_ptr=None, ld=None):
+        """reads (HBM) -> coverage -> matrix (HBM).  out_ptr / ld: where the matrix goes (default:
+        this problem's own buffer)."""
+        import torch
+        L, _lib = self.env["L"], self.env["_lib"]
+        vp = lambda t: C.c_void_p(t.data_ptr())                # noqa: E731
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)            # noqa: E731
+        R = self.R
+        h = self._load()
+        cov = C.c_int(0)
+        if self.is_rna:
+            hc, hl, hr = C.c_int(0), C.c_int(0), C.c_int(0)
+            _lib.check(L.rcp_coverage_list(h.value, R, self.ex_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           hp(self.ex[0]), hp(self.ex[1]), hp(self.ex[2]), hp(self.ex[3]), 1,
+                                           _lib.STRAND_ANY, _lib.MEM_HOST, C.byref(hc)))
+            dl, dr = self.d_left, self.d_right
+            _lib.check(L.rcp_coverage(h.value, R, vp(dl[0]), vp(dl[1]), vp(dl[2]), vp(dl[3]), 1,
+                                      _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hl)))
+            _lib.check(L.rcp_coverage(h.value, R, vp(dr[0]), vp(dr[1]), vp(dr[2]), vp(dr[3]), 1,
+                                      _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hr)))
+            _lib.check(L.rcp_coverage_concat3(hl.value, hc.value, hr.value, C.byref(cov)))
+            for x in (hc, hl, hr):
+                L.rcp_coverage_free(x.value)
+        else:
+            dw = self.d_win
+            _lib.check(L.rcp_coverage(h.value, R, vp(dw[0]), vp(dw[1]), vp(dw[2]), vp(dw[3]), 1,
+                                      _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(cov)))
+        if self.ncols is None:
+            nc = C.c_int64(0)
+            _lib.check(L.rcp_profile_ncols(cov.value, self.equal_lengths, self.f1, self.f2,
+                                           self.bp["flankBinSize"], self.bp["regionBinSize"], C.byref(nc)))
+            self.ncols = nc.value
+        if out_ptr is None:
+            if self.out is None:
+                self.out = torch.empty((self.ncols, R), dtype=torch.float64, device=self.env["dev"])
+            out_ptr, ld = self.out.data_ptr(), R
+        _lib.check(L.rcp_profile_matrix(cov.value, self.equal_lengths, self.f1, self.f2,
+                                        self.bp["flankBinSize"], self.bp["regionBinSize"],
+                                        _lib.STAT[self.bp["sumStat"]], _lib.INTERP[self.bp["interpolation"]],
+                                        42, 0, C.c_void_p(out_ptr), ld, _lib.MEM_DEVICE))
+        if not self.stats:
+            tl, nn = C.c_int64(0), C.c_int64(0)
+            L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
+            pth, cand = C.c_int(0), C.c_int64(0)
+            L.rcp_coverage_path_info(cov.value, C.byref(pth), C.byref(cand))
+            self.stats = {"total_len": tl.value, "n_null": nn.value, "path": PATHS[pth.value],
+                          "candidates": cand.value}
+        L.rcp_coverage_free(cov.value)
+        L.rcp_reads_free(h.value)
+
+    def fused_step(self):
+        """Equal-length windows only: rcp_coverage_profile (coverage not materialised)."""
+        L, _lib = self.env["L"], self.env["_lib"]
+        vp = lambda t: C.c_void_p(t.data_ptr())                # noqa: E731
+        h = self._load()
+        dw = self.d_win
+        _lib.check(L.rcp_coverage_profile(h.value, self.R, vp(dw[0]), vp(dw[1]), vp(dw[2]), vp(dw[3]), 1,
+                                          _lib.STRAND_ANY, self.bp["regionBinSize"], 42, 0, 1.0,
+                                          C.c_void_p(self.out.data_ptr()), self.R, None, _lib.MEM_DEVICE))
+        L.rcp_reads_free(h.value)
+
+
+def stage_table(L, _lib):
+    n_st = 0
+    while L.rcp_timing_stage_name(n_st):
+        n_st += 1
+    ms = (C.c_double * n_st)()
+    cnt = (C.c_int64 * n_st)()
+    _lib.check(L.rcp_timing_read(1, n_st, ms, cnt))
+    return {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
+            for i in range(n_st) if cnt[i] > 0}
+
+
+STAGE_GROUPS = {
+    "reads_map": ["index_map"],
+    "coverage": ["index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
+                 "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small",
+                 "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small",
+                 "sp_plan", "sp_split", "sp_sort", "sp_tile", "sp_small"],
+    "profile": ["prof_bin", "prof_interp", "prof_base"],
+}
+
+
+def stage_roofline(stage, steps, N, R, ncols, total_len, peak):
+    """SURVEY 8d algorithmic bytes per STAGE / the stage's whole time (sort / bucketing / planning
+    included in the TIME, not in the bytes):
+      reads_map  13 B/read in (chrom, start, end, strand) + 9 B/read out
+      coverage   8 B/read + 4 B/covered base + 16 B/region
+      profile    4 B/covered base + 8 B/matrix cell"""
+    nbytes = {"reads_map": 22 * N, "coverage": 8 * N + 4 * total_len + 16 * R,
+              "profile": 4 * total_len + 8 * R * ncols}
+    per_step = {k: v[0] * v[1] / steps for k, v in stage.items()}
+    out = {}
+    for g, members in STAGE_GROUPS.items():
+        ms_g = sum(per_step.get(m, 0.0) for m in members)
+        if ms_g > 0:
+            ach = nbytes[g] / (ms_g * 1e-3) / 1e9
+            out[g] = {"ms_per_step": ms_g, "algorithmic_bytes": nbytes[g], "achieved": ach, "frac": ach / peak}
+    return out, per_step
+
+
+def time_problem(env, prob, steps, warmup, step_fn=None):
+    """W untimed + K timed steps of one problem on the library stream; returns (ms/step, stages)."""
+    import torch
+    L, _lib, stream = env["L"], env["_lib"], env["stream"]
+    fn = step_fn or prob.step
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    _lib.check(L.rcp_timing_enable(1))
+    _lib.check(L.rcp_timing_read(1, 0, None, None))
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        fn()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    stage = stage_table(L, _lib)
+    _lib.check(L.rcp_timing_enable(0))
+    return ms, stage
+
+
+def config_entry(env, w, steps, peak, samples=1, note=None):
+    """One extra config, device-resident: ms per sample step, stage times and roofline fractions."""
+    prob = Problem(env, w)
+    ms, stage = time_problem(env, prob, steps, 3)
+    roof, per_step = stage_roofline(stage, steps, prob.N, prob.R, prob.ncols, prob.stats["total_len"], peak)
+    out = {"workload": w["name"], "reads_per_sample": prob.N, "regions": prob.R, "matrix_cols": prob.ncols,
+           "covered_bases": prob.stats["total_len"], "null_regions": prob.stats["n_null"],
+           "coverage_path_used": prob.stats["path"], "samples": samples, "steps_per_sample": steps,
+           "ms_per_sample": ms, "reads_per_s": prob.N / (ms * 1e-3),
+           "region_bins_per_s": prob.R * prob.ncols / (ms * 1e-3),
+           "stage_ms": per_step, "stages": roof}
+    if note:
+        out["note"] = note
+    return out
+
+
+def run_c1(env):
+    """C1: the reference's bundled ChIP-seq data (both samples), TSS +-2 kb, 100 bins, through the
+    HOST API (the fixture is tiny: latency-bound; parity config)."""
+    import torch
+    rb = env["rb"]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "recoup_test_data.npz"))
+    n = z["gene_start"].shape[0]
+    genes = rb.GRanges(np.zeros(n, dtype=np.int32), z["gene_start"], z["gene_end"], strand=z["gene_strand"],
+                       seqlevels=["chr12"], names=list(z["gene_names"]))
+    bp = dict(flankBinSize=0, regionBinSize=100, sumStat="mean", interpolation="auto")
+    reads = []
+    for k in range(2):
+        s = z["reads_%d_start" % k].astype(np.int64)
+        wd = z["reads_%d_width" % k].astype(np.int64)
+        reads.append(rb.GRanges(np.zeros(s.shape[0], dtype=np.int32), s, s + wd - 1, strand=z["reads_%d_strand" % k],
+                                seqlevels=["chr12"], seqlengths=z["chrom_len"]))
+
+    def one():
+        inp = [dict(id="s%d" % k, name="s%d" % k, ranges=reads[k]) for k in range(2)]
+        rb.coverageRef(inp, genes, "tss", (2000, 2000))
+        rb.profileMatrix(inp, (2000, 2000), bp)
+        for x in inp:
+            x["coverage"].free()
+        for g in reads:
+            for dr in g._device.values():
+                dr.free()
+            g._device.clear()
+        return inp
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        inp = one()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    nreads = sum(len(r) for r in reads)
+    return {"workload": "C1 recoup_test_data: 2 samples x 100000 reads over 100 genes, TSS +-2 kb, 100 bins",
+            "through": "host API (coverageRef + profileMatrix), host arrays, copies included",
+            "ms_per_pass": ms, "reads_per_s": nreads / (ms * 1e-3), "matrix": list(inp[0]["profile"].shape),
+            "note": "latency-bound (0.8 MB of reads): parity config, not a roofline config"}
+
+
+def run_strong(env, args, world, rank):
+    """ONE C5 problem sharded by region: every rank generates the read parts {p : p % W == rank}
+    (an arbitrary share of the reads), the timed step exchanges the reads (all-to-all by region
+    slice), runs the path on the rank's slice and downloads the rank's matrix block over its own
+    PCIe link.  checksum = sum of all matrix entries: the same for every W."""
+    import torch
+    import torch.distributed as dist
+    from recoup_b200.ranges import getRegionalRanges
+    from recoup_b200.sharding import exchange_reads, partition_regions, slice_spans
+    rb, dev, L = env["rb"], env["dev"], env["L"]
+    n_parts = 8
+    mine = [p for p in range(n_parts) if p % world == rank]
+    t_gen = time.time()
+    ws = [W.dnase_sites_part(p, n_parts=n_parts, scale=args.configs_scale) for p in mine]
+    w = dict(ws[0])
+    for key in ("read_chrom", "read_start", "read_end", "read_strand"):
+        w[key] = np.concatenate([x[key] for x in ws])
+    del ws
+    t_gen = time.time() - t_gen
+    genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"], strand=w["region_strand"],
+                       seqlevels=w["chrom_names"])
+    win = getRegionalRanges(genes, w["region"], w["flank"])
+    parts = partition_regions(win.seqnames, win.start, win.end, world)
+    spans = slice_spans(win.seqnames, win.start, win.end, parts, len(w["chrom_len"]))
+    my_idx = np.sort(parts[rank])
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)      # noqa: E731
+    share = [to_dev(w[k]) for k in ("read_chrom", "read_start", "read_end", "read_strand")]
+    n_share = int(share[1].shape[0])
+    for key in ("read_chrom", "read_start", "read_end", "read_strand"):
+        w[key] = w[key][:0]
+    prob = Problem(env, w, reads=share, region_idx=my_idx)
+    R_mine = prob.R
+    ncols = w["flank"][0] + w["flank"][1]          # per-base custom windows: f1 + f2 columns
+    block = torch.empty((ncols, R_mine), dtype=torch.float64, device=dev)
+    host = torch.empty((ncols, R_mine), dtype=torch.float64, pin_memory=True)
+    lib_stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        with torch.cuda.stream(lib_stream):
+            ev[0].record(lib_stream)
+            got = exchange_reads(share[0], share[1], share[2], share[3], spans)
+            ev[1].record(lib_stream)
+            prob.set_reads(list(got))
+            prob.step(out_ptr=block.data_ptr(), ld=R_mine)
+            ev[2].record(lib_stream)
+            host.copy_(block, non_blocking=True)
+            ev[3].record(lib_stream)
+        torch.cuda.synchronize()
+        return int(got[1].shape[0])
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    steps = max(2, min(args.steps, 3))
+    phases = np.zeros(3)
+    total_ms = 0.0
+    n_mine = 0
+    for _ in range(steps):
+        n_mine = step()
+        total_ms += ev[0].elapsed_time(ev[3])
+        phases += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
+        if world > 1:
+            dist.barrier()
+    ms = total_ms / steps
+    checksum = float(host.sum())
+    red = torch.tensor([ms, phases[0] / steps, phases[1] / steps, phases[2] / steps], dtype=torch.float64, device=dev)
+    tot = torch.tensor([checksum, float(n_share), float(n_mine), float(R_mine)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(red[0])
+    n_total = int(tot[1])
+    out = {"workload": "C5 synthetic DNase-seq: %d reads over %d sites +-%d bp, per-base, ONE problem "
+                       "sharded by region over %d GPU(s)" % (n_total, len(win), w["flank"][0], world),
+           "scaling": "strong", "n_gpus": world, "steps": steps,
+           "ms_per_step": ms, "reads_per_s": n_total / (ms * 1e-3),
+           "phases_ms_max_over_ranks": {"exchange_reads (classify + NCCL all-to-all)": float(red[1]),
+                                        "load + coverage + per-base matrix": float(red[2]),
+                                        "matrix block D2H (own PCIe link)": float(red[3])},
+           "reads_after_exchange": int(tot[2]), "regions": int(tot[3]), "matrix_cols": ncols,
+           "matrix_bytes_total": int(tot[3]) * ncols * 8,
+           "coverage_path_used": prob.stats.get("path"), "checksum": float(tot[0]),
+           "generation_s_this_rank": round(t_gen, 1)}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     import recoup_b200 as rb
     from recoup_b200 import _lib
-    from recoup_b200.ranges import getFlankingRanges, getRegionalRanges
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -244,151 +580,58 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        import datetime
-        # a mismatched collective must fail in a minute, not hang the box until the watchdog
+        # a mismatched collective must fail in minutes, not hang the box until the watchdog
         dist.init_process_group("nccl", device_id=torch.device("cuda", local),
-                                timeout=datetime.timedelta(seconds=90))
+                                timeout=datetime.timedelta(seconds=180))
     rb.init(local)
     rb.set_coverage_path(args.path)
     L = _lib.lib
+    _lib.check(L.rcp_set_deferred_validation(1))
     dev = torch.device("cuda", local)
     stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
+    env = {"rb": rb, "_lib": _lib, "L": L, "dev": dev, "stream": stream}
+    peak, peak_src = peaks()
 
-    # ---- this rank's slice: a full-size sample of the named workload (weak scaling) ----
-    w = W.CONFIGS[args.workload](scale=args.scale, seed={"C2": 1001, "C3": 1003, "C4": 1004,
-                                                          "C5": 1005}[args.workload] + 7919 * rank)
-    N = len(w["read_start"])
+    # ---- this rank's headline problem: a full-size sample of the named workload (N > 1: an
+    # independent replica per rank, weak scaling) ----
+    w = W.CONFIGS[args.workload](scale=args.scale, seed=SEEDS[args.workload] + 7919 * rank)
     if args.read_order == "coordinate":
         order = np.lexsort((w["read_start"], w["read_chrom"]))
         for key in ("read_chrom", "read_start", "read_end", "read_strand"):
             w[key] = np.ascontiguousarray(w[key][order])
         del order
         w["name"] += " (reads coordinate-sorted)"
-    is_rna = w["region"] == "rna"
-    genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"],
-                       strand=w["region_strand"], seqlevels=w["chrom_names"])
-    f1, f2 = w["flank"]
-    bp = w["bin_params"]
-    if is_rna:
-        left = getFlankingRanges(genes, f1, "upstream")
-        right = getFlankingRanges(genes, f2, "downstream")
-        R = len(genes)
-    else:
-        win = getRegionalRanges(genes, w["region"], w["flank"])
-        R = len(win)
-    clen = np.ascontiguousarray(w["chrom_len"], dtype=np.int64)
-    clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
-    n_chrom = clen.shape[0]
+    prob = Problem(env, w)
+    N, R = prob.N, prob.R
+    is_rna = prob.is_rna
 
-    def to_dev(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-
-    d_reads = [to_dev(w[k]) for k in ("read_chrom", "read_start", "read_end", "read_strand")]
-    if is_rna:
-        d_left = [to_dev(x) for x in (left.seqnames, left.start, left.end, left.strand)]
-        d_right = [to_dev(x) for x in (right.seqnames, right.start, right.end, right.strand)]
-        ex = [np.ascontiguousarray(w[k]) for k in ("exon_chrom", "exon_start", "exon_end", "exon_strand")]
-        ex_ptr = np.ascontiguousarray(w["exon_ptr"], dtype=np.int64)
-    else:
-        d_win = [to_dev(x) for x in (win.seqnames, win.start, win.end, win.strand)]
-    vp = lambda t: C.c_void_p(t.data_ptr())
-    hp = lambda a: a.ctypes.data_as(C.c_void_p)
-
-    equal_lengths = 1 if w["region"] in ("tss", "tes", "custom") else 0
-    ncols_box = {}
-    out_box = {}
-    stats = {}
-
-    def device_step(k=0):
-        """reads (HBM) -> index -> coverage -> matrix (HBM)."""
-        h = C.c_int(0)
-        _lib.check(L.rcp_reads_load(N, vp(d_reads[0]), vp(d_reads[1]), vp(d_reads[2]), vp(d_reads[3]),
-                                    n_chrom, clen_p, int(w["frag_len"]), _lib.MEM_DEVICE, C.byref(h)))
-        cov = C.c_int(0)
-        if is_rna:
-            hc, hl, hr = C.c_int(0), C.c_int(0), C.c_int(0)
-            _lib.check(L.rcp_coverage_list(h.value, R, ex_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
-                                           hp(ex[0]), hp(ex[1]), hp(ex[2]), hp(ex[3]), 1,
-                                           _lib.STRAND_ANY, _lib.MEM_HOST, C.byref(hc)))
-            _lib.check(L.rcp_coverage(h.value, R, vp(d_left[0]), vp(d_left[1]), vp(d_left[2]),
-                                      vp(d_left[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hl)))
-            _lib.check(L.rcp_coverage(h.value, R, vp(d_right[0]), vp(d_right[1]), vp(d_right[2]),
-                                      vp(d_right[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(hr)))
-            _lib.check(L.rcp_coverage_concat3(hl.value, hc.value, hr.value, C.byref(cov)))
-            for x in (hc, hl, hr):
-                L.rcp_coverage_free(x.value)
-        else:
-            _lib.check(L.rcp_coverage(h.value, R, vp(d_win[0]), vp(d_win[1]), vp(d_win[2]),
-                                      vp(d_win[3]), 1, _lib.STRAND_ANY, _lib.MEM_DEVICE, C.byref(cov)))
-        if "n" not in ncols_box:
-            nc = C.c_int64(0)
-            _lib.check(L.rcp_profile_ncols(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
-                                           bp["regionBinSize"], C.byref(nc)))
-            ncols_box["n"] = nc.value
-            # col-major R x nc, double buffered (N > 1: the gather of step k overlaps step k + 1)
-            out_box["bufs"] = [torch.empty((nc.value, R), dtype=torch.float64, device=dev)
-                               for _ in range(2 if world > 1 else 1)]
-            out_box["m"] = out_box["bufs"][0]
-            out_box["ptr"], out_box["ld"] = None, R
-            if world > 1 and args.exchange == "p2p":
-                # every rank writes its rows straight into rank 0's matrix (peer-mapped)
-                from recoup_b200.sharding import PeerMatrix
-                with torch.cuda.stream(stream):
-                    pm = PeerMatrix(R * world, nc.value, dev, dst=0)
-                out_box["peer"] = pm
-                out_box["ptr"], out_box["ld"] = pm.ptr_for(rank * R), R * world
-            tl, nn = C.c_int64(0), C.c_int64(0)
-            L.rcp_coverage_info(cov.value, None, C.byref(tl), C.byref(nn), None)
-            stats["total_len"], stats["n_null"] = tl.value, nn.value
-            pth, cand = C.c_int(0), C.c_int64(0)
-            L.rcp_coverage_path_info(cov.value, C.byref(pth), C.byref(cand))
-            stats["path"] = {0: "list", 1: "index", 2: "buckets", 3: "blocks", 4: "split"}[pth.value]
-            stats["candidates"] = cand.value
-        if out_box["ptr"] is not None:      # peer-mapped matrix of rank 0 / verification buffer
-            out_ptr = out_box["ptr"]
-        else:
-            buf = out_box["bufs"][k % len(out_box["bufs"])]
-            if world > 1:
-                gissued[k % 2].wait()       # the helper thread has issued that gather
-            if world > 1 and gdone[k % 2] is not None:
-                stream.wait_event(gdone[k % 2])     # the gather that read this buffer two steps ago
-            out_ptr = buf.data_ptr()
-        _lib.check(L.rcp_profile_matrix(cov.value, equal_lengths, f1, f2, bp["flankBinSize"],
-                                        bp["regionBinSize"], _lib.STAT[bp["sumStat"]],
-                                        _lib.INTERP[bp["interpolation"]], 42, 0,
-                                        C.c_void_p(out_ptr), out_box["ld"], _lib.MEM_DEVICE))
-        L.rcp_coverage_free(cov.value)
-        L.rcp_reads_free(h.value)
-
-    gather_box = {}
-
+    # ---- N > 1: NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) on
+    # its own stream; the output matrix is double buffered, so the gather of step k runs beside
+    # the kernels of step k + 1.  The NCCL call is issued by a helper thread (the host is on the
+    # critical path of a step; ctypes releases the GIL inside the library).
+    prob.step()                                             # sizes the matrix
+    ncols = prob.ncols
+    bufs = [prob.out] + ([torch.empty_like(prob.out)] if world > 1 else [])
     gstream = torch.cuda.Stream(device=dev) if world > 1 else None
     gdone = [None, None]
+    gather_box = {}
+    gq = queue.Queue()
+    gissued = [threading.Event(), threading.Event()]
+    for e in gissued:
+        e.set()
+    gfail = []
 
     def gather_issue(k, ready):
         from recoup_b200.sharding import RowGather
         gstream.wait_event(ready)
         with torch.cuda.stream(gstream):
             if "g" not in gather_box:       # buffers and row indices are set up once
-                gather_box["g"] = RowGather(out_box["bufs"][0].shape[0],
-                                            np.arange(rank * R, (rank + 1) * R), R * world, dev,
-                                            out_box["bufs"][0].dtype, dst=0, sizes=[R] * world)
-            gather_box["full"] = gather_box["g"].gather(out_box["bufs"][k % 2])
+                gather_box["g"] = RowGather(ncols, np.arange(rank * R, (rank + 1) * R), R * world, dev,
+                                            bufs[0].dtype, dst=0, sizes=[R] * world)
+            gather_box["full"] = gather_box["g"].gather(bufs[k % 2])
             done = torch.cuda.Event()
             done.record(gstream)
         return done
-
-    # The host is on the critical path of a step (the library synchronises to validate the reads
-    # and to size the hit list), so the NCCL call is issued by a helper thread while the main
-    # thread is already launching the next step; ctypes releases the GIL inside the library.
-    import queue
-    import threading
-    gq = queue.Queue()
-    gissued = [threading.Event(), threading.Event()]
-    for e in gissued:
-        e.set()
-
-    gfail = []
 
     def gather_worker():
         torch.cuda.set_device(dev)
@@ -405,7 +648,7 @@ def run_b200(args):
                 gissued[k % 2].set()
 
     gthread = None
-    if world > 1 and args.exchange == "nccl" and not os.environ.get("RCP_BENCH_INLINE_GATHER"):
+    if world > 1:
         gthread = threading.Thread(target=gather_worker, daemon=True)
         gthread.start()
 
@@ -415,24 +658,18 @@ def run_b200(args):
         if gfail:
             raise gfail[0]
 
-    def gather_step(k=0):
-        """NCCL gather of the row blocks to rank 0 (the reference's do.call(rbind, ...)) and their
-        placement into the full column-major matrix.  It runs on its own stream, behind the bin
-        kernel of this step and beside the next step's kernels: the output matrix is double
-        buffered (step k writes buffer k % 2), so only the gather of step k - 2 must have finished
-        before step k may overwrite its buffer."""
-        if world == 1 or os.environ.get("RCP_BENCH_NO_GATHER"):
-            return
-        if "peer" in out_box:               # the rows are already in place: order the stores
-            if args.fence == "step":
-                with torch.cuda.stream(stream):
-                    out_box["peer"].fence()
-            return
-        ready = torch.cuda.Event()
-        ready.record(stream)                # the bin kernel of this step (library stream)
-        if gthread is None:
-            gdone[k % 2] = gather_issue(k, ready)
-        else:
+    def full_step(k):
+        buf = bufs[k % len(bufs)]
+        if world > 1:
+            gissued[k % 2].wait()           # the helper thread has issued the gather two steps back
+            if gfail:
+                raise gfail[0]
+            if gdone[k % 2] is not None:
+                stream.wait_event(gdone[k % 2])     # ... and it has read this buffer
+        prob.step(out_ptr=buf.data_ptr(), ld=R)
+        if world > 1:
+            ready = torch.cuda.Event()
+            ready.record(stream)            # the bin kernel of this step (library stream)
             gissued[k % 2].clear()
             gq.put((k, ready))
 
@@ -447,8 +684,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     for k in range(max(args.warmup, 3)):
-        device_step(k)
-        gather_step(k)
+        full_step(k)
     barrier()
 
     # ---- timed: device-resident ----
@@ -461,8 +697,7 @@ def run_b200(args):
     t_begin = time.time()
     ev0.record(stream)
     for k in range(args.steps):
-        device_step(k)
-        gather_step(k)
+        full_step(k)
     if world > 1:
         gather_drain()
         for ev in gdone:                    # the timed region ends when the last gathers have landed
@@ -470,33 +705,57 @@ def run_b200(args):
                 stream.wait_event(ev)
     ev1.record(stream)
     barrier()
-    t_end = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = int(L.rcp_launch_count(0))
-    n_st = 0
-    while L.rcp_timing_stage_name(n_st):
-        n_st += 1
-    ms = (C.c_double * n_st)()
-    cnt = (C.c_int64 * n_st)()
-    _lib.check(L.rcp_timing_read(1, n_st, ms, cnt))
+    stage = stage_table(L, _lib)
     _lib.check(L.rcp_timing_enable(0))
-    stage = {L.rcp_timing_stage_name(i).decode(): (ms[i] / max(cnt[i], 1), int(cnt[i]))
-             for i in range(n_st) if cnt[i] > 0}
     # The timed region is a few tens of milliseconds, shorter than one nvidia-smi period: keep
-    # the same steps running (untimed) for a second so that the clock record is taken UNDER THIS
-    # LOAD.  The sampler polls nvidia-smi (a driver-lock heavy call), so it is stopped before the
-    # host-API (e2e) loop.
-    # The number of extra steps is agreed by all ranks (rank 0 derives it from the max-over-ranks
-    # step time and broadcasts it): every rank issues the same number of gathers.
+    # the same steps running (untimed) for about a second so that the clock record is taken UNDER
+    # THIS LOAD.  The number of extra steps is agreed by all ranks (never a rank-local wall
+    # clock around a collective).
     n_probe = torch.tensor([max(1, min(4000, int(1000.0 / max(elapsed_ms / args.steps, 1e-3))))],
                            dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(n_probe, op=dist.ReduceOp.MIN)
-    for k in range(args.steps, args.steps + int(n_probe.item())):
-        device_step(k)
-        gather_step(k)
+    n_probe = int(n_probe.item())
+    for k in range(args.steps, args.steps + n_probe):
+        full_step(k)
     barrier()
-    clocks = sampler.stop(t_begin, time.time(), "timed region + 1 s of the same steps (untimed)")
+    clocks = sampler.stop(t_begin, time.time(), "timed region + ~1 s of the same steps (untimed)")
+
+    # ---- N > 1: the exchanged matrix on rank 0 must hold every rank's rows ----
+    exchange_ok = None
+    if world > 1:
+        k_last = args.steps + n_probe - 1
+        mine = bufs[k_last % 2].double().sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            full = gather_box["full"]
+            exchange_ok = True
+            for r in range(world):
+                got = float(full[:, r * R:(r + 1) * R].sum())
+                want = float(sums[r])
+                if not (abs(got - want) <= 1e-9 * max(abs(want), 1.0)) or want == 0.0:
+                    exchange_ok = False
+        gq.put(None)
+        gthread.join()
+        gather_box.clear()
+        barrier()
+
+    # ---- the fused entry point (coverage not materialised), same problem ----
+    fused = None
+    if not is_rna and prob.equal_lengths and prob.bp["regionBinSize"] > 0:
+        prob.out = bufs[0]
+        prob.step()
+        want = prob.out.clone()
+        ms_f, stage_f = time_problem(env, prob, args.steps, 3, step_fn=prob.fused_step)
+        same = bool(torch.equal(want, prob.out))
+        del want
+        fused = {"ms_per_step": ms_f, "reads_per_s": N / (ms_f * 1e-3), "matrix_equals_two_stage": same,
+                 "algorithmic_bytes": 8 * N + 16 * R + 8 * R * ncols,
+                 "stage_ms": {k: v[0] * v[1] / args.steps for k, v in stage_f.items()}}
+        fused["frac_of_hbm_peak"] = fused["algorithmic_bytes"] / (ms_f * 1e-3) / 1e9 / peak
 
     # ---- timed: end to end through the public host API (pinned host buffers) ----
     def pinned(a):
@@ -511,15 +770,14 @@ def run_b200(args):
         grl = rb.GRangesList(rb.GRanges(w["exon_chrom"], w["exon_start"], w["exon_end"],
                                         strand=w["exon_strand"], seqlevels=w["chrom_names"]),
                              w["exon_ptr"])
-        h2d += sum(ex[i].nbytes for i in range(4)) + 2 * 13 * R
+        h2d += sum(prob.ex[i].nbytes for i in range(4)) + 2 * 13 * R
     else:
         h2d += 13 * R
-    ncols = ncols_box["n"]
     d2h = 8 * R * ncols + 4 * R
     e2e_steps = max(2, min(args.steps, 5))
-
-    phases = {"upload+index": 0.0, "coverage": 0.0, "profile+download": 0.0}
+    phases = {"upload+map": 0.0, "coverage": 0.0, "profile+download": 0.0}
     e2e_in = {"seqnames": host_views[0], "views": host_views}
+    clen = prob.clen
 
     def e2e_step():
         """The calls a user of the reference API makes, on pinned HOST arrays."""
@@ -529,25 +787,23 @@ def run_b200(args):
                            seqlevels=w["chrom_names"], seqlengths=clen)
         sample = [dict(id="s", name="s", ranges=reads)]
         rb.device_reads(reads, w["frag_len"])
-        L.rcp_sync()
         t_b = time.perf_counter()
         if is_rna:
-            rb.coverageRnaRef(sample, grl, genes, w["flank"])
+            rb.coverageRnaRef(sample, grl, prob.genes, w["flank"])
         else:
             if w["frag_len"]:
-                sample[0]["coverage"] = rb.calcCoverage(reads, win, frag_len=w["frag_len"])
+                sample[0]["coverage"] = rb.calcCoverage(reads, prob.win, frag_len=w["frag_len"])
             else:
-                rb.coverageRef(sample, genes, w["region"], w["flank"])
-        L.rcp_sync()
+                rb.coverageRef(sample, prob.genes, w["region"], w["flank"])
         t_c = time.perf_counter()
-        rb.profileMatrix(sample, w["flank"], bp)
+        rb.profileMatrix(sample, w["flank"], prob.bp)
         m = sample[0]["profile"]
         t_d = time.perf_counter()
         sample[0]["coverage"].free()
         for dr in reads._device.values():
             dr.free()
         reads._device.clear()
-        phases["upload+index"] += t_b - t_a
+        phases["upload+map"] += t_b - t_a
         phases["coverage"] += t_c - t_b
         phases["profile+download"] += t_d - t_c
         return m
@@ -592,30 +848,8 @@ def run_b200(args):
     e2e_bam_s = (time.perf_counter() - t0) / e2e_steps
     bam_phases = dict(phases)
     phases = main_phases
-
-    # ---- N > 1: the exchanged matrix on rank 0 must hold every rank's rows ----
-    exchange_ok = None
-    if world > 1:
-        barrier()
-        saved = (out_box["ptr"], out_box["ld"])
-        out_box["ptr"], out_box["ld"] = out_box["m"].data_ptr(), R      # one more step, local output
-        device_step()
-        out_box["ptr"], out_box["ld"] = saved
-        if "peer" not in out_box:           # and one more gather of exactly that block
-            gather_step(0)
-        barrier()
-        mine = out_box["m"].double().sum().reshape(1)
-        sums = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(sums, mine)
-        if rank == 0:
-            full = out_box["peer"].as_tensor() if "peer" in out_box else gather_box["full"]
-            exchange_ok = True
-            for r in range(world):
-                got = float(full[:, r * R:(r + 1) * R].sum())
-                want = float(sums[r])
-                if not (abs(got - want) <= 1e-9 * max(abs(want), 1.0)) or want == 0.0:
-                    exchange_ok = False
-            assert exchange_ok, "rows of some rank did not arrive in rank 0's matrix"
+    n_runs = seq_rle.nrun
+    del pins, host_views, mat, e2e_in
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([elapsed_ms, e2e_s * 1e3, e2e_bam_s * 1e3], dtype=torch.float64, device=dev)
@@ -625,76 +859,80 @@ def run_b200(args):
     ms_per_step = elapsed_ms / args.steps
     value = world * N / (ms_per_step * 1e-3)
     e2e_value = world * N / (e2e_ms * 1e-3)
+    stats = prob.stats
+    total_len = stats["total_len"]
+    headline_name = w["name"]
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(w)
+
+    # ---- the other configs (one GPU) and the region-sharded C5 ----
+    prob = None
+    bufs = None
+    w = None
+    torch.cuda.empty_cache()
+    configs = None
+    headline = args.workload == "C2" and args.scale == 1.0
+    if world == 1 and args.configs == "all" and headline:
+        cs = args.configs_scale
+        note = None if cs == 1.0 else "scaled by %.3g" % cs
+        configs = {"C1": run_c1(env)}
+        # C3: 8 samples over the same 60k genes; each sample is one step (per-sample numbers)
+        per = []
+        for smp in range(8):
+            w3 = W.gene_bodies(scale=cs, seed=SEEDS["C3"])
+            if smp:     # same genes, this sample's own reads
+                w3.update({k: v for k, v in W.gene_bodies(scale=cs, seed=SEEDS["C3"] + 101 * smp).items()
+                           if k.startswith("read_")})
+            per.append(config_entry(env, w3, max(2, min(args.steps, 3)), peak, samples=8, note=note))
+            del w3
+        c3 = dict(per[0])
+        c3["ms_per_sample"] = float(np.mean([e["ms_per_sample"] for e in per]))
+        c3["ms_all_8_samples"] = float(np.sum([e["ms_per_sample"] for e in per]))
+        c3["reads_per_s"] = float(np.sum([e["reads_per_sample"] for e in per]) / (c3["ms_all_8_samples"] * 1e-3))
+        c3["per_sample_ms"] = [e["ms_per_sample"] for e in per]
+        configs["C3"] = c3
+        w4 = W.rnaseq(scale=cs)
+        configs["C4"] = config_entry(env, w4, max(2, min(args.steps, 3)), peak, note=note)
+        del w4
+        torch.cuda.empty_cache()
+    strong = None
+    if args.strong == "on" and headline:
+        strong = run_strong(env, args, world, rank)
+        if configs is not None:
+            configs["C5"] = dict(strong, note="run through the region-sharded code path at W = 1; the matrix "
+                                              "block download (8 GB D2H) is inside ms_per_step")
 
     if rank == 0:
-        peak, peak_src = peaks()
-        total_len = stats["total_len"]
-        # Algorithmic bytes (SURVEY 8d / DESIGN.md 4).  Per STAGE:
-        #   reads_map  13 B/read in (chrom, start, end, strand) + 9 B/read out (global start,
-        #              end+1, strand)
-        #   coverage   8 B/read + 4 B/covered base + 16 B/region     (everything between the
-        #              mapped reads and the dense coverage: sort or bucketing included in the
-        #              TIME, not in the bytes)
-        #   profile    4 B/covered base + 8 B/matrix cell
-        # Per KERNEL (the `roofline` object, dominant kernel of the step): the bytes that kernel
-        # cannot avoid moving -- a pass over the reads 8 B/read (+1 with strand), the tile
-        # kernels 4 B/covered base written (+ 8 B/read on the index path, which reads the sorted
-        # arrays there), the bin kernel 4 B/covered base + 8 B/cell, the sort 8 B/key.  Block path:
-        # the filter reads 8 B/read (its output, 8 B/candidate, is not counted); a scatter pass
-        # reads and writes 8 B/candidate; the tile kernel writes 4 B/covered base and reads the
-        # candidates once (8 B each; the re-reads of a block by its second tile are not counted).
+        # Algorithmic bytes per KERNEL (the `roofline` object, dominant own kernel of the step): the
+        # bytes that kernel cannot avoid moving -- a pass over the reads 8 B/read, the tile kernels
+        # 4 B/covered base written + the candidates read once, the bin kernel 4 B/covered base +
+        # 8 B/cell, the sort 8 B/key.
         cand = stats.get("candidates", 0)
         alg_kernel = {
-            "blk_filter": 8 * N,
-            "blk_scatter": 16 * cand,
-            "blk_tile": 4 * total_len + 8 * cand,
+            "blk_filter": 8 * N, "blk_scatter": 16 * cand, "blk_tile": 4 * total_len + 8 * cand,
             "blk_small": 4 * total_len + 8 * cand,
-            "sp_split": 8 * N,
-            "sp_tile": 4 * total_len + 4 * cand,
-            "sp_small": 4 * total_len + 4 * cand,
-            "index_map": 22 * N,
-            "index_sort": 8 * N,
-            "cov_tile": 8 * N + 4 * total_len + 16 * R,
-            "cov_small": 8 * N + 4 * total_len + 16 * R,
-            "bkt_count": 8 * N,
-            "bkt_scatter": 8 * N,
-            "bkt_tile": 4 * total_len,
-            "bkt_small": 4 * total_len,
-            "prof_bin": 4 * total_len + 8 * R * ncols,
-            "prof_base": 4 * total_len + 8 * R * ncols,
+            "sp_split": 8 * N, "sp_sort": 8 * cand, "sp_tile": 4 * total_len + 4 * cand,
+            "index_map": 22 * N, "index_sort": 8 * N,
+            "cov_tile": 8 * N + 4 * total_len + 16 * R, "cov_small": 8 * N + 4 * total_len + 16 * R,
+            "bkt_count": 8 * N, "bkt_scatter": 8 * N, "bkt_tile": 4 * total_len, "bkt_small": 4 * total_len,
+            "prof_bin": 4 * total_len + 8 * R * ncols, "prof_base": 4 * total_len + 8 * R * ncols,
         }
-        groups = {
-            "reads_map": (["index_map"], 22 * N),
-            "coverage": (["index_sort", "cov_plan", "cov_tile", "cov_small", "cov_list", "cov_concat",
-                          "bkt_plan", "bkt_count", "bkt_scatter", "bkt_tile", "bkt_small",
-                          "blk_filter", "blk_hist", "blk_scatter", "blk_tile", "blk_small",
-                          "sp_plan", "sp_split", "sp_sort", "sp_tile", "sp_small"],
-                         8 * N + 4 * total_len + 16 * R),
-            "profile": (["prof_bin", "prof_interp", "prof_base"], 4 * total_len + 8 * R * ncols),
-        }
-        per_step = {k: v[0] * v[1] / args.steps for k, v in stage.items()}
-        stage_roof = {}
-        for g, (members, nbytes) in groups.items():
-            ms_g = sum(per_step.get(m, 0.0) for m in members)
-            if ms_g > 0:
-                ach = nbytes / (ms_g * 1e-3) / 1e9
-                stage_roof[g] = {"ms_per_step": ms_g, "algorithmic_bytes": nbytes, "achieved": ach,
-                                 "frac": ach / peak}
-        # measured DRAM traffic per launch (ncu --set full), available for the full-size C2 step
+        stage_roof, per_step = stage_roofline(stage, args.steps, N, R, ncols, total_len, peak)
+        # measured DRAM traffic per launch (ncu --set full of this round's kernels), keyed by stage
         traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic_C2.json")
-        if args.workload == "C2" and args.scale == 1.0 and os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic_C2.json")
+        if headline and os.path.exists(tpath):
             traffic = json.load(open(tpath))
         own = {k: v for k, v in stage.items() if k in alg_kernel}
         dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
         roof = None
         if dom:
-            per_step_ms = per_step[dom]
             per_launch_ms = own[dom][0]         # average over the launches of the timed region
             ach = alg_kernel[dom] / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-                    "ms_per_step": per_step_ms, "ms_per_launch": per_launch_ms,
+                    "ms_per_step": per_step[dom], "ms_per_launch": per_launch_ms,
                     "launches_per_step": own[dom][1] / args.steps,
                     "algorithmic_bytes": alg_kernel[dom],
                     "kernels": {k: {"ms_per_launch": own[k][0], "launches_per_step": own[k][1] / args.steps,
@@ -707,19 +945,19 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32 coverage / f64 matrix",
             "data": "synthetic",
-            "config": {"workload": w["name"], "regions_per_gpu": R, "reads_per_gpu": N,
+            "config": {"workload": headline_name, "regions_per_gpu": R, "reads_per_gpu": N,
                        "matrix_cols": ncols, "covered_bases_per_gpu": total_len,
                        "null_regions": stats["n_null"],
                        "l2": "inputs (%.0f MB) and coverage (%.0f MB) exceed the 126 MB L2"
                              % (13 * N / 1e6, 4 * total_len / 1e6),
                        "coverage_path": args.path, "coverage_path_used": stats.get("path"),
-                       "filter_candidates_per_gpu": stats.get("candidates"),
-                       "parallelism": ("regions sharded over %d GPU(s), " % world) +
-                                      ("rows stored into rank 0's matrix over NVLink (peer-mapped)"
-                                       if world > 1 and args.exchange == "p2p" else
-                                       "NCCL row gather on its own stream (double-buffered matrix: "
-                                       "the gather of step k runs beside step k + 1)")},
-            "stage_ms_per_step": {k: v[0] * v[1] / args.steps for k, v in stage.items()},
+                       "candidates_per_gpu": stats.get("candidates"),
+                       "parallelism": ("one GPU" if world == 1 else
+                                       "%d independent replicas of the workload, one per GPU (weak scaling; "
+                                       "every rank its own reads and regions), row blocks gathered to rank 0 "
+                                       "with NCCL on a second stream; the ONE-problem region-sharded run is "
+                                       "in `strong`" % world)},
+            "stage_ms_per_step": per_step,
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -732,20 +970,21 @@ def run_b200(args):
                               "phases_ms": {k: 1e3 * v / e2e_steps for k, v in bam_phases.items()},
                               "inputs": "the same reads grouped by chromosome (BAM order); seqnames "
                                         "as the Rle a GRanges holds (%d runs), start, end int32 + "
-                                        "strand int8" % seq_rle.nrun},
+                                        "strand int8" % n_runs},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if fused is not None:
+            out["fused"] = fused
+        if configs is not None:
+            out["configs"] = configs
+        if strong is not None:
+            out["strong"] = strong
         if exchange_ok is not None:
             out["exchange_verified"] = exchange_ok
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(w)
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
         print(json.dumps(out))
     if world > 1:
-        if gthread is not None:
-            gq.put(None)
-            gthread.join()
-        if "peer" in out_box:
-            out_box["peer"].close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -245,9 +245,14 @@ int rcp_profile_matrix(int cov, int equal_lengths, int f1, int f2, int flank_bin
                        double* out, int64_t ld, int mem);
 
 /* ---------------------------------------------------------------- fused path -------------- */
-/* coverageRef + profileMatrix for fixed-width windows WITHOUT materialising $coverage
- * (coverage.R:1-42 + profile.R:83-96): windows of equal length, n_bins bins (0 = per base).
- * is_null_out (n_regions, may be NULL) receives the NULL flags. */
+/* coverageRef + profileMatrix (mean) for fixed-width windows (coverage.R:1-42 + profile.R:83-96):
+ * windows of equal length (else RCP_ERR_ARG), n_bins bins (0 = per base), the matrix scaled by
+ * `scale`.  With n_bins >= 1, windows at least n_bins long and reads the split path accepts, the
+ * coverage is NEVER materialised: the tile kernel adds each tile's bin sums to 64-bit
+ * accumulators and a last kernel divides -- same integer sums, same fp64 divide, so the matrix
+ * equals rcp_coverage + rcp_profile_matrix bit for bit.  Otherwise the two stages are composed
+ * and the coverage is released at once.  is_null_out (n_regions, may be NULL) receives the NULL
+ * flags. */
 int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom,
                          const int32_t* start, const int32_t* end, const int8_t* strand,
                          int ignore_strand, int strand_filter, int n_bins, int seed,

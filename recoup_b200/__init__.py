@@ -12,15 +12,15 @@ from .consumers import (calcPlotProfiles, colProfile, heatmapScale, matrixQuanti
 from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, coverageRnaRef,
                        device_reads, set_verbose)
 from .preprocess import SelectedGRanges, preprocessRanges, readRanges, sampleSorted, widthQuantile
-from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, haveEqualLengths,
-                      profileMatrix)
+from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, coverageProfile,
+                      haveEqualLengths, profileMatrix)
 from .ranges import GRanges, GRangesList, Rle, getFlankingRanges, getRegionalRanges
 
 __all__ = [
     "RecoupError", "init", "shutdown", "set_coverage_path", "GRanges", "GRangesList", "Rle",
     "getRegionalRanges", "getFlankingRanges", "calcCoverage", "coverageRef", "coverageRnaRef", "CoverageList",
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
-    "haveEqualLengths", "ProfileMatrix", "set_verbose", "calcPlotProfiles", "orderProfiles",
+    "haveEqualLengths", "coverageProfile", "ProfileMatrix", "set_verbose", "calcPlotProfiles", "orderProfiles",
     "heatmapScale", "colProfile", "rowStat", "sortIndex", "matrixQuantile", "preprocessRanges",
     "readRanges", "SelectedGRanges", "sampleSorted", "widthQuantile",
 ]

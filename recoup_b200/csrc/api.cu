@@ -249,6 +249,10 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
 int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                           const int32_t* end, const int8_t* strand, int ignore_strand,
                           int strand_filter, int mem, Coverage* cv);
+int coverage_profile_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, int ignore_strand,
+                           int strand_filter, int mem, int n_bins, int seed, int sample_kind,
+                           double scale, double* d_out, int64_t ld, uint8_t* d_is_null);
 int coverage_concat3(const Coverage& a, const Coverage& b, const Coverage& c, Coverage* cv);
 int coverage_fetch(const Coverage& cv, int64_t first, int64_t count, int32_t* out,
                    int64_t capacity);
@@ -958,18 +962,79 @@ int rcp_profile_matrix(int cov, int equal_lengths, int f1, int f2, int flank_bin
     return m.finish(out, ld, R, ncols);
 }
 
-// ---- fused path (round 1: composed from the two stages; the coverage is released at once) ----
+// ---- fused path ----------------------------------------------------------------------------
+// Equal-length windows with n_bins >= 1 bins are served by the split path's fused tile kernel (the coverage never reaches HBM).  Everything else (per-base matrices, windows
+// shorter than the bin count, reads too wide for the split path) composes the two stages and
+// releases the coverage at once.  Windows of different lengths are an error either way.
 int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom, const int32_t* start,
                          const int32_t* end, const int8_t* strand, int ignore_strand,
                          int strand_filter, int n_bins, int seed, int sample_kind, double scale,
                          double* out, int64_t ld, uint8_t* is_null_out, int mem) {
+    RCP_TRY(require_ready());
+    ReadsIdx* r = get_reads(reads);
+    if (!r) return fail(RCP_ERR_HANDLE, "unknown reads handle %d", reads);
+    if (n_regions < 0 || n_bins < 0 || out == nullptr || ld < n_regions)
+        return fail(RCP_ERR_ARG, "rcp_coverage_profile: bad argument");
+    if (n_regions > 0 && (!chrom || !start || !end)) return fail(RCP_ERR_ARG, "rcp_coverage_profile: NULL array");
+    if (!valid_strand_filter(strand_filter)) return fail(RCP_ERR_ARG, "bad strand filter %d", strand_filter);
+    if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
+    if (n_regions > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 regions");
+    const bool may_split = g_ctx.coverage_path == RCP_PATH_SPLIT ||
+                           (g_ctx.coverage_path == RCP_PATH_AUTO && getenv("RCP_AUTO_NO_SPLIT") == nullptr);
+    if (n_bins >= 1 && may_split) {
+        MatrixOut m;
+        RCP_TRY(m.init(out, ld, n_regions, n_bins, mem));
+        uint8_t* d_null = nullptr;
+        bool own_null = false;
+        if (is_null_out) {
+            if (mem == RCP_MEM_DEVICE) d_null = is_null_out;
+            else {
+                RCP_TRY(dalloc(&d_null, (size_t)n_regions));
+                own_null = true;
+            }
+        }
+        int rc = coverage_profile_split(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
+                                        strand_filter, mem, n_bins, seed, sample_kind, scale, m.dev, m.ld_dev,
+                                        d_null);
+        if (rc == RCP_OK) {
+            if (own_null && n_regions > 0) {
+                cudaError_t e = cudaMemcpyAsync(is_null_out, d_null, (size_t)n_regions, cudaMemcpyDeviceToHost,
+                                                g_ctx.stream);
+                if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "null-flag copy failed: %s", cudaGetErrorString(e));
+            }
+            if (rc == RCP_OK) rc = m.finish(out, ld, n_regions, n_bins);     // synchronises for host output
+        }
+        if (own_null) dfree(d_null);
+        if (rc != RCP_SPLIT_NOT_APPLICABLE) return rc;
+    }
     int h = 0;
     RCP_TRY(rcp_coverage(reads, n_regions, chrom, start, end, strand, ignore_strand, strand_filter,
                          mem, &h));
     Coverage* cv = get_coverage(h);
     cv->scale = scale;
-    int rc = rcp_profile_matrix(h, 1, 0, 0, 0, n_bins, RCP_STAT_MEAN, RCP_INTERP_AUTO, seed,
-                                sample_kind, out, ld, mem);
+    int rc = RCP_OK;
+    {   // one common length (profile.R:86-96 is the equal-length branch)
+        std::vector<int32_t> len((size_t)n_regions);
+        if (n_regions > 0) {
+            cudaError_t e = cudaMemcpyAsync(len.data(), cv->len, (size_t)n_regions * 4, cudaMemcpyDeviceToHost,
+                                            g_ctx.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+            if (e != cudaSuccess) rc = fail(RCP_ERR_CUDA, "length copy failed: %s", cudaGetErrorString(e));
+        }
+        int32_t common = 0;
+        for (int32_t l : len) {
+            if (l == 0) continue;
+            if (common == 0) common = l;
+            else if (l != common) {
+                rc = fail(RCP_ERR_ARG, "rcp_coverage_profile: the windows have different lengths (%d and %d); "
+                                       "use rcp_coverage + rcp_profile_matrix", common, l);
+                break;
+            }
+        }
+    }
+    if (rc == RCP_OK)
+        rc = rcp_profile_matrix(h, 1, 0, 0, 0, n_bins, RCP_STAT_MEAN, RCP_INTERP_AUTO, seed, sample_kind, out,
+                                ld, mem);
     if (rc == RCP_OK && is_null_out && n_regions > 0) {
         cudaError_t e = cudaMemcpyAsync(is_null_out, cv->is_null, (size_t)n_regions,
                                         mem == RCP_MEM_DEVICE ? cudaMemcpyDeviceToDevice

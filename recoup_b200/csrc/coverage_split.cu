@@ -27,7 +27,10 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <vector>
+
 #include "cov_common.cuh"
+#include "r_rng.cuh"
 #include "rcp_internal.cuh"
 
 namespace rcp {
@@ -68,7 +71,7 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
                int n_chrom, int ignore_strand, int strand_filter, uint32_t* __restrict__ gs_out,
                int32_t* __restrict__ plen, uint8_t* __restrict__ flags, int64_t* __restrict__ ntile,
                int64_t* __restrict__ padded, uint32_t* __restrict__ tab, unsigned int* __restrict__ err,
-               unsigned long long* __restrict__ pstats /* [0] total len [1] max len */) {
+               unsigned long long* __restrict__ pstats /* [0] total len [1] max len [2] 2^32 - min len */) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
     unsigned long long my_len = 0;
     if (r < R) {
@@ -89,14 +92,16 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
             for (uint32_t b = gs >> BLK_SHIFT; b <= b1; b++) sp_mark_block(tab, b);
         }
     }
-    unsigned long long my_max = my_len;
+    unsigned long long my_max = my_len, my_inv = my_len ? 0x100000000ull - my_len : 0ull;
     for (int d = 16; d > 0; d >>= 1) {
         my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
         my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+        my_inv = max(my_inv, __shfl_xor_sync(0xffffffffu, my_inv, d));
     }
     if ((threadIdx.x & 31) == 0 && my_len) {
         atomicAdd(&pstats[0], my_len);
         atomicMax(&pstats[1], my_max);
+        atomicMax(&pstats[2], my_inv);
     }
 }
 
@@ -129,8 +134,8 @@ struct __align__(16) SpDesc {
 __global__ void __launch_bounds__(CTA)
 sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, const uint32_t* __restrict__ gs,
                 const int32_t* __restrict__ plen, const uint8_t* __restrict__ flags,
-                const int64_t* __restrict__ cov_off, uint32_t max_w, uint32_t pmask,
-                SpDesc* __restrict__ desc) {
+                const int64_t* __restrict__ cov_off /* nullptr: fused, `out` = offset inside the region */,
+                uint32_t max_w, uint32_t pmask, SpDesc* __restrict__ desc) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (t >= T) return;
     const int64_t r = sp_owner_of(off_tile, R, t);
@@ -144,7 +149,7 @@ sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, cons
     const uint32_t tstart = gs[r] + q0;
     const uint32_t first = tstart >= max_w ? tstart - max_w + 1u : 0u;
     SpDesc d;
-    d.out = cov_off[r] + o_lo;
+    d.out = cov_off ? cov_off[r] + o_lo : (int64_t)o_lo;
     d.c0 = first >> SUB_SHIFT;
     d.n = ((tstart + tlen - 1u) >> SUB_SHIFT) + 1u;
     d.tlen = (int32_t)tlen;
@@ -619,7 +624,7 @@ __device__ __forceinline__ bool sp_apply(uint32_t e, const SpDesc& d, int P, int
 // lanes, the run is rescanned from the right start and written back in place; the TMA unit then
 // stores the tile as ONE bulk copy (cp.async.bulk.global.shared::cta), so no thread spends LSU
 // wavefronts on the 4 B / base output.
-template <int RPW>
+template <int RPW, bool STORE = true>
 __device__ __forceinline__ void warp_scan_store_fwd(int* diff, int tlen, int32_t* __restrict__ dst) {
     const int lane = threadIdx.x & 31;
     int* mine = diff + lane * 4 * RPW;
@@ -642,21 +647,69 @@ __device__ __forceinline__ void warp_scan_store_fwd(int* diff, int tlen, int32_t
         *(reinterpret_cast<int4*>(mine) + k) = o;
     }
     __syncwarp();
-    if (lane == 0) {
+    if (STORE && lane == 0) {
         fence_proxy_async_smem();
         tma_store_1d(dst, diff, (uint32_t)((tlen + 3) & ~3) * 4u);
         tma_store_commit();
     }
 }
 
+// FUSED coverage -> bins: what a tile hands on instead of its coverage.  The regions have ONE
+// common length, so one edge table serves them all (edge[i] = first output of bin i, n + 1
+// entries; splitVector's seeded layout, util.R:74-80).  The tile adds, for every bin it meets,
+// the sum of its part of the bin to the bin's 64-bit accumulator (a bin may straddle tiles);
+// integer sums are exact, so the matrix equals the two-stage path's bit for bit.
+struct FusedBins {
+    const int32_t* edge;                 // n + 1
+    int n;
+    int64_t R;
+    unsigned long long* acc;             // [n][R]
+};
+
+__device__ __forceinline__ void tile_to_bins(const int* tile, const SpDesc& d, const FusedBins& fb) {
+    const int lane = threadIdx.x & 31;
+    const int o_lo = (int)d.out, o_hi = o_lo + d.tlen;
+    int a = 0, b = fb.n;                 // last bin with edge <= o_lo
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (__ldg(fb.edge + mid) <= o_lo) a = mid;
+        else b = mid;
+    }
+    for (int i = a + lane; i < fb.n; i += 32) {
+        const int e0 = __ldg(fb.edge + i);
+        if (e0 >= o_hi) break;
+        const int lo = max(e0, o_lo) - o_lo, hi = min(__ldg(fb.edge + i + 1), o_hi) - o_lo;
+        unsigned long long s = 0;
+        for (int k = lo; k < hi; k++) s += (unsigned long long)(unsigned int)tile[k];
+        if (s) atomicAdd(fb.acc + (size_t)i * fb.R + d.region, s);
+    }
+}
+
+// acc -> the matrix (column-major, like acc): mean of the bin, times the scale; NULL rows are zero
+__global__ void __launch_bounds__(CTA)
+sp_bins_finish_kernel(FusedBins fb, const int32_t* __restrict__ plen, const uint8_t* __restrict__ region_hit,
+                      double scale, double* __restrict__ out, int64_t ld, uint8_t* __restrict__ is_null) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (r >= fb.R) return;
+    const int i = blockIdx.y;
+    const bool null = plen[r] == 0 || region_hit[r] == 0;
+    double v = 0.0;
+    if (!null) {
+        const int w = __ldg(fb.edge + i + 1) - __ldg(fb.edge + i);
+        v = scale * ((double)(long long)fb.acc[(size_t)i * fb.R + r] / (double)w);
+    }
+    out[(size_t)i * ld + r] = v;
+    if (i == 0 && is_null) is_null[r] = null ? 1 : 0;
+}
+
 // One WARP per tile (<= 896 outputs; a region <= 1024 bp is one tile): no block-wide barrier
 // anywhere.  Persistent warps; the next tile's descriptor and its first 128 candidates are in
 // flight while the current tile is scanned and stored; longer candidate lists are read 128 at a
 // time (four loads per lane in flight).
-template <bool STRANDED>
+template <bool STRANDED, bool FUSED>
 __global__ void __launch_bounds__(CTA, 4)
 sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
-                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit) {
+                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, FusedBins fb) {
     __shared__ __align__(16) int sm[WARPS][WT_ONE];
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -694,24 +747,28 @@ sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __re
         }
         hit = __any_sync(0xffffffffu, hit);
         __syncwarp();
-        int32_t* dst = cov + d.out;
+        int32_t* dst = FUSED ? nullptr : cov + d.out;
         switch (rows) {
-            case 1: warp_scan_store_fwd<1>(diff, d.tlen, dst); break;
-            case 2: warp_scan_store_fwd<2>(diff, d.tlen, dst); break;
-            case 3: warp_scan_store_fwd<3>(diff, d.tlen, dst); break;
-            case 4: warp_scan_store_fwd<4>(diff, d.tlen, dst); break;
-            case 5: warp_scan_store_fwd<5>(diff, d.tlen, dst); break;
-            case 6: warp_scan_store_fwd<6>(diff, d.tlen, dst); break;
-            case 7: warp_scan_store_fwd<7>(diff, d.tlen, dst); break;
-            default: {      // 8 rows (a whole region of 897..1024 bp): row by row, conflict-free
-                int pre = 0;
-                for (int row = 0; row < rows; row++)
-                    pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, d.tlen - row * ROW, dst + row * ROW);
-            }
+            case 1: warp_scan_store_fwd<1, !FUSED>(diff, d.tlen, dst); break;
+            case 2: warp_scan_store_fwd<2, !FUSED>(diff, d.tlen, dst); break;
+            case 3: warp_scan_store_fwd<3, !FUSED>(diff, d.tlen, dst); break;
+            case 4: warp_scan_store_fwd<4, !FUSED>(diff, d.tlen, dst); break;
+            case 5: warp_scan_store_fwd<5, !FUSED>(diff, d.tlen, dst); break;
+            case 6: warp_scan_store_fwd<6, !FUSED>(diff, d.tlen, dst); break;
+            case 7: warp_scan_store_fwd<7, !FUSED>(diff, d.tlen, dst); break;
+            default:        // 8 rows (a whole region of 897..1024 bp)
+                if (FUSED) {
+                    warp_scan_store_fwd<8, false>(diff, d.tlen, dst);
+                } else {    // row by row, conflict-free
+                    int pre = 0;
+                    for (int row = 0; row < rows; row++)
+                        pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, d.tlen - row * ROW, dst + row * ROW);
+                }
         }
+        if (FUSED && hit) tile_to_bins(diff, d, fb);        // a tile without a read adds nothing
         if (hit && lane == 0) region_hit[d.region] = 1;
         t += step;
-        if (lane == 0) tma_store_wait_read();       // the bulk store has read the tile
+        if (!FUSED && lane == 0) tma_store_wait_read();     // the bulk store has read the tile
         if (!more) break;
         __syncwarp();
         d = dn;
@@ -755,9 +812,21 @@ sp_null_kernel(int64_t R, const int32_t* __restrict__ plen, const uint8_t* __res
 // Same contract as coverage_ranges_bucketed.  RCP_SPLIT_NOT_APPLICABLE: the reads are too wide for
 // the packed candidate word of this genome (or the genome too long for the shared-memory table);
 // nothing has been produced and the caller uses another path.
-int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
-                          const int32_t* end, const int8_t* strand, int ignore_strand,
-                          int strand_filter, int mem, Coverage* cv) {
+// fz != nullptr: the FUSED form (rcp_coverage_profile): no coverage is stored, the tiles add their
+// bin sums to accumulators and sp_bins_finish_kernel writes the matrix (cv is scratch then).
+// RCP_SPLIT_NOT_APPLICABLE there also when the windows differ in length or are shorter than the
+// bin count (interpolation): the caller composes the two stages instead.
+struct FusedReq {
+    int n_bins, seed, sample_kind;
+    double scale;
+    double* d_out;
+    int64_t ld;
+    uint8_t* d_is_null;      // may be nullptr
+};
+
+static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                      const int32_t* end, const int8_t* strand, int ignore_strand,
+                      int strand_filter, int mem, Coverage* cv, const FusedReq* fz) {
     const bool stranded = !((strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr));
     const bool st_arr = stranded && rd.d_strand != nullptr;      // strandless reads are all '*'
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
@@ -786,7 +855,7 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
                       Arena::pad(r * 8) * 2 + Arena::pad((r + 1) * 8)));
     // zero-initialised block first (ONE memset): status words, block table, region hit flags
     unsigned int* err = A.take<unsigned int>(16);         // [0] err; pstats at +16 bytes
-    unsigned long long* pstats = reinterpret_cast<unsigned long long*>(err + 4);   // [0] total len [1] max len
+    unsigned long long* pstats = reinterpret_cast<unsigned long long*>(err + 4);   // [0] total len [1] max len [2] 2^32 - min len
     uint32_t* tab = A.take<uint32_t>((size_t)words);
     uint8_t* region_hit = A.take<uint8_t>(r);
     const size_t zero_bytes = A.used;
@@ -825,11 +894,11 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
     }
     struct Host {
         int64_t T, total_padded;
-        unsigned long long pstats[2];
+        unsigned long long pstats[3];
         unsigned int err;
-    } h = {0, 0, {0, 0}, 0};
+    } h = {0, 0, {0, 0, 0}, 0};
     {
-        FetchItem items[8] = {{off_tile + R, &h.T, 8}, {cv->off + R, &h.total_padded, 8}, {pstats, h.pstats, 16},
+        FetchItem items[8] = {{off_tile + R, &h.T, 8}, {cv->off + R, &h.total_padded, 8}, {pstats, h.pstats, 24},
                               {err, &h.err, 4}};
         int n_items = 4;
         reads_pending_items(rd, items, &n_items);       // a deferred rcp_reads_load is validated here
@@ -843,13 +912,47 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
     const uint32_t max_w = rd.max_width > 0 ? rd.max_width : 1u;
     if (max_w > 8191u || max_w >= (1u << wbits)) return give_up();
 
-    cv->path = RCP_PATH_SPLIT;
-    cv->total_padded = h.total_padded;
-    cv->total_len = (int64_t)h.pstats[0];       // upper bounds until the NULL rule has run
-    cv->max_len = (int32_t)h.pstats[1];
-    cv->n_null = 0;
-    cv->stats_pending = true;
-    RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
+    // ---- fused: one common window length, bin edges of splitVector (util.R:74-80) -------------
+    FusedBins fb = {nullptr, 0, R, nullptr};
+    Arena F;
+    if (fz) {
+        const int64_t max_len = (int64_t)h.pstats[1];
+        const int64_t min_len = h.pstats[2] ? 0x100000000ll - (int64_t)h.pstats[2] : 0;
+        const int n = fz->n_bins;
+        if (max_len != min_len || (max_len > 0 && max_len < n)) return give_up();
+        const int64_t Lc = max_len > 0 ? max_len : n;       // no valid window at all: any layout
+        std::vector<int32_t> edge((size_t)n + 1);
+        {
+            std::vector<int> perm((size_t)n), scratch((size_t)n), rank((size_t)n);
+            RRng* rng = new RRng;
+            rng->seed((uint32_t)fz->seed, fz->sample_kind);
+            rng->sample(n, n, scratch.data(), perm.data());
+            delete rng;
+            for (int pos = 0; pos < n; pos++) rank[(size_t)perm[(size_t)pos] - 1] = pos + 1;
+            const int64_t b = Lc / n, d = Lc - b * n;
+            int64_t at = 0;
+            for (int i = 0; i < n; i++) {
+                edge[(size_t)i] = (int32_t)at;
+                at += b + (rank[(size_t)i] <= d ? 1 : 0);
+            }
+            edge[(size_t)n] = (int32_t)at;
+        }
+        RCP_TRY(F.reserve(Arena::pad(((size_t)n + 1) * 4) + Arena::pad((size_t)n * r * 8)));
+        int32_t* d_edge = F.take<int32_t>((size_t)n + 1);
+        fb.acc = F.take<unsigned long long>((size_t)n * r);
+        RCP_CUDA(cudaMemcpyAsync(d_edge, edge.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(fb.acc, 0, (size_t)n * r * 8, g_ctx.stream));
+        fb.edge = d_edge;
+        fb.n = n;
+    } else {
+        cv->path = RCP_PATH_SPLIT;
+        cv->total_padded = h.total_padded;
+        cv->total_len = (int64_t)h.pstats[0];       // upper bounds until the NULL rule has run
+        cv->max_len = (int32_t)h.pstats[1];
+        cv->n_null = 0;
+        cv->stats_pending = true;
+        RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
+    }
 
     // ---- scratch of the read passes ------------------------------------------------------------
     const int split_grid = g_ctx.sm_count;
@@ -875,8 +978,8 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
         StageTimer t(ST_SP_PLAN);
         RCP_CUDA(cudaMemsetAsync(B.base, 0, zero_b, g_ctx.stream));
         if (T > 0) {
-            sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags, cv->off,
-                                                                         max_w, pmask, desc);
+            sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags,
+                                                                         fz ? nullptr : cv->off, max_w, pmask, desc);
             RCP_LAUNCHED();
         }
     }
@@ -914,21 +1017,29 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
             RCP_LAUNCHED();
         }
         {
-            StageTimer t(ST_SP_TILE);
-            int per_sm = 0;
-            if (stranded) {
-                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_wtile_kernel<true>, CTA, 0));
+            StageTimer t(fz ? ST_FUSED : ST_SP_TILE);
+            const int64_t want = blocks_for(T, WARPS);
+            auto launch = [&](auto kern) -> int {
+                int per_sm = 0;
+                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA, 0));
                 per_sm = std::max(per_sm, 1);
-                sp_wtile_kernel<true><<<(unsigned)std::min<int64_t>(blocks_for(T, WARPS), (int64_t)g_ctx.sm_count * per_sm),
-                                        CTA, 0, g_ctx.stream>>>(T, desc, cand, P, cv->cov, region_hit);
-            } else {
-                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_wtile_kernel<false>, CTA, 0));
-                per_sm = std::max(per_sm, 1);
-                sp_wtile_kernel<false><<<(unsigned)std::min<int64_t>(blocks_for(T, WARPS), (int64_t)g_ctx.sm_count * per_sm),
-                                         CTA, 0, g_ctx.stream>>>(T, desc, cand, P, cv->cov, region_hit);
-            }
+                kern<<<(unsigned)std::min<int64_t>(want, (int64_t)g_ctx.sm_count * per_sm), CTA, 0, g_ctx.stream>>>(
+                    T, desc, cand, P, cv->cov, region_hit, fb);
+                RCP_LAUNCHED();
+                return RCP_OK;
+            };
+            if (fz) RCP_TRY(stranded ? launch(sp_wtile_kernel<true, true>) : launch(sp_wtile_kernel<false, true>));
+            else RCP_TRY(stranded ? launch(sp_wtile_kernel<true, false>) : launch(sp_wtile_kernel<false, false>));
+        }
+    }
+    if (fz) {
+        if (R > 0) {
+            StageTimer t(ST_FUSED);
+            sp_bins_finish_kernel<<<dim3(blocks_for(R, CTA), (unsigned)fb.n), CTA, 0, g_ctx.stream>>>(
+                fb, plen, region_hit, fz->scale, fz->d_out, fz->ld, fz->d_is_null);
             RCP_LAUNCHED();
         }
+        return RCP_OK;
     }
     if (R > 0) {
         StageTimer t(ST_SP_PLAN);
@@ -937,6 +1048,26 @@ int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const i
         RCP_LAUNCHED();
     }
     return RCP_OK;
+}
+
+int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                          const int32_t* end, const int8_t* strand, int ignore_strand,
+                          int strand_filter, int mem, Coverage* cv) {
+    return split_impl(rd, R, chrom, start, end, strand, ignore_strand, strand_filter, mem, cv, nullptr);
+}
+
+// coverageRef + profileMatrix of equal-length windows WITHOUT storing the coverage (d_out, d_is_null:
+// device memory).  RCP_SPLIT_NOT_APPLICABLE: compose rcp_coverage + rcp_profile_matrix instead.
+int coverage_profile_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
+                           const int32_t* end, const int8_t* strand, int ignore_strand,
+                           int strand_filter, int mem, int n_bins, int seed, int sample_kind,
+                           double scale, double* d_out, int64_t ld, uint8_t* d_is_null) {
+    if (n_bins < 1 || n_bins > 30000) return RCP_SPLIT_NOT_APPLICABLE;
+    Coverage scratch;
+    const FusedReq fz = {n_bins, seed, sample_kind, scale, d_out, ld, d_is_null};
+    const int rc = split_impl(rd, R, chrom, start, end, strand, ignore_strand, strand_filter, mem, &scratch, &fz);
+    coverage_release(scratch);
+    return rc;
 }
 
 }  // namespace rcp

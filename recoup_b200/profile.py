@@ -145,3 +145,43 @@ def profileMatrix(input, flank, binParams, rc=None, seed=R_SEED, sample_kind="Re
         _message("Calculating profile for ", x.get("name"))
         x["profile"] = _profile_one(x["coverage"], equal, flank, binParams, seed, sample_kind)
     return input
+
+
+def coverageProfile(input, mask, binSize, strand=None, ignore_strand=True, scale=1.0, frag_len=0,
+                    seed=R_SEED, sample_kind="Rejection"):
+    """coverageRef + profileMatrix of ONE sample over equal-length windows in one call
+    (coverage.R:1-42 followed by profile.R:83-96, sumStat = "mean"), through rcp_coverage_profile:
+    with binSize >= 1 the per-base coverage never reaches HBM (the tile kernel hands its bin sums
+    on); binSize = 0 gives the per-base matrix.  Returns (ProfileMatrix, is_null) -- the rows of
+    NULL coverages are zero, as in profile.R:191-197.  Windows of different lengths are an error
+    (use calcCoverage + profileMatrix, whose unequal-length branch this call does not have)."""
+    from .coverage import _as_reads, _map_chrom, _ptr, device_reads
+    from .ranges import GRanges, strand_to_code
+    reads = _as_reads(input)
+    if reads is None or not isinstance(mask, GRanges):
+        raise ValueError("coverageProfile takes decoded reads (GRanges) and a GRanges mask")
+    strand_filter = int(strand_to_code(strand)[0]) if strand is not None else _lib.STRAND_ANY
+    dr = device_reads(reads, frag_len)
+    chrom = np.ascontiguousarray(_map_chrom(mask, reads), dtype=np.int32)
+    start = np.ascontiguousarray(mask.start, dtype=np.int32)
+    end = np.ascontiguousarray(mask.end, dtype=np.int32)
+    bad = chrom < 0
+    if bad.any():
+        chrom = np.where(bad, 0, chrom).astype(np.int32)
+        start = np.where(bad, -1, start).astype(np.int32)
+        end = np.where(bad, -1, end).astype(np.int32)
+    R = len(mask)
+    if int(binSize) > 0:
+        ncols = int(binSize)
+    else:
+        w = (end.astype(np.int64) - start + 1)[~bad]
+        ncols = int(w[0]) if w.size else 0
+    out = _out(R, ncols)
+    is_null = np.zeros(R, dtype=np.uint8)
+    if R > 0 and ncols > 0:
+        _lib.check(_lib.lib.rcp_coverage_profile(
+            dr.handle, R, _ptr(chrom), _ptr(start), _ptr(end), _ptr(mask.strand), int(bool(ignore_strand)),
+            strand_filter, int(binSize), int(seed), _sample_kind(sample_kind), float(scale),
+            out.ctypes.data_as(C.c_void_p), _ld(out), is_null.ctypes.data_as(C.c_void_p), _lib.MEM_HOST))
+    cols = [str(i + 1) for i in range(ncols)] if int(binSize) > 0 else None
+    return ProfileMatrix(out, rownames=mask.names, colnames=cols), is_null.astype(bool)

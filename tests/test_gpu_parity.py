@@ -929,3 +929,145 @@ def test_rows_scatter_places_a_row_block(gpu):
     want = np.zeros((n_cols, total))
     want[:, ids_np] = src.cpu().numpy()[:, :n_rows]
     assert np.array_equal(dst.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# rcp_coverage_profile: coverage -> bins without materialising the coverage
+# ------------------------------------------------------------------------------------------------
+def _equal_windows(rng, n, clen, L):
+    chrom = rng.integers(0, len(clen), size=n).astype(np.int32)
+    start = (rng.random(n) * (np.asarray(clen)[chrom] + 200)).astype(np.int64) - 100
+    strand = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=n)
+    return chrom, start, start + L - 1, strand
+
+
+@pytest.mark.parametrize("L,n_bins", [(4000, 100), (10000, 200), (2999, 64), (900, 37), (1024, 1024),
+                                      (1025, 10), (5000, 3), (300, 0)])
+@pytest.mark.parametrize("ignore,filt", [(True, None), (False, None), (True, "-")])
+def test_fused_coverage_profile_matches_the_oracle(gpu, L, n_bins, ignore, filt):
+    """bit-exact integer sums + the same fp64 divide: the fused matrix equals profileMatrix of the
+    oracle's coverage within 1e-6 (and the two-stage CUDA path exactly); NULL rows are zero and
+    flagged; '-' windows are reversed; bins straddle the 896-output tiles for most sizes."""
+    rb = gpu
+    rng = np.random.default_rng(100 + L + n_bins)
+    clen = [60000, 25000, 8000]
+    chrom, s, e, st = synth_reads(rng, 30000, clen, width=(20, 300))
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    rc, rs, re_, rst = _equal_windows(rng, 400, clen, L)
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    filt_code = None if filt is None else {"+": 1, "-": -1, "*": 0}[filt]
+    want_cov = O.calc_coverage(o_reads, o_mask, filt_code, ignore)
+    bp = dict(flankBinSize=0, regionBinSize=n_bins, sumStat="mean", interpolation="auto")
+    want = 0.5 * O.profile_matrix(want_cov, (0, 0), bp)
+    got, is_null = rb.coverageProfile(g_reads, g_mask, n_bins, strand=filt, ignore_strand=ignore, scale=0.5)
+    assert [bool(x) for x in is_null] == [w is None for w in want_cov]
+    assert any(w is None for w in want_cov) and sum(w is not None for w in want_cov) > 100
+    assert_matrix_close(got, want)
+    # and exactly what the two stages give
+    cov = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+    cov.set_scale(0.5)
+    inp = [dict(id="s", name="s", ranges=g_reads, coverage=cov)]
+    rb.profileMatrix(inp, (0, 0), bp)
+    assert np.array_equal(np.asarray(got), np.asarray(inp[0]["profile"]))
+
+
+def test_fused_coverage_profile_device_memory_and_errors(gpu):
+    import torch
+    from recoup_b200 import _lib
+    rb = gpu
+    L = _lib.lib
+    rng = np.random.default_rng(5)
+    clen = [50000, 20000]
+    chrom, s, e, st = synth_reads(rng, 20000, clen, width=(30, 200))
+    _, g_reads = both_reads(chrom, s, e, st, clen)
+    rc, rs, re_, rst = _equal_windows(rng, 300, clen, 3000)
+    _, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    want, want_null = rb.coverageProfile(g_reads, g_mask, 60)
+    dr = rb.device_reads(g_reads)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)      # noqa: E731
+    d = [t(g_mask.seqnames, np.int32), t(g_mask.start, np.int32), t(g_mask.end, np.int32), t(g_mask.strand, np.int8)]
+    out = torch.full((60, 300 + 7), -1.0, dtype=torch.float64, device=dev)          # ld = 307 > n_regions
+    nul = torch.full((300,), 9, dtype=torch.uint8, device=dev)
+    vp = lambda x: C.c_void_p(x.data_ptr())                                          # noqa: E731
+    _lib.check(L.rcp_coverage_profile(dr.handle, 300, vp(d[0]), vp(d[1]), vp(d[2]), vp(d[3]), 1, _lib.STRAND_ANY,
+                                      60, 42, 0, 1.0, vp(out), 307, vp(nul), _lib.MEM_DEVICE))
+    L.rcp_sync()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, :300].T, np.asarray(want))
+    assert (got[:, 300:] == -1.0).all()                      # the padding rows of ld are untouched
+    assert np.array_equal(nul.cpu().numpy().astype(bool), want_null)
+    # windows of different lengths: an error, not a silently binned mixture
+    re2 = re_.copy()
+    re2[7] += 5
+    _, bad_mask = both_regions(rc, rs, re2, rst, len(clen))
+    with pytest.raises(rb.RecoupError):
+        rb.coverageProfile(g_reads, bad_mask, 60)
+    # windows shorter than the bin count take the composed path (spline / neighbourhood fill)
+    rc3, rs3, re3, rst3 = _equal_windows(rng, 50, clen, 40)
+    o3, m3 = both_regions(rc3, rs3, re3, rst3, len(clen))
+    o_reads, _ = both_reads(chrom, s, e, st, clen)
+    got3, _ = rb.coverageProfile(g_reads, m3, 64)
+    bp = dict(flankBinSize=0, regionBinSize=64, sumStat="mean", interpolation="auto")
+    assert_matrix_close(got3, O.profile_matrix(O.calc_coverage(o_reads, o3, None, True), (0, 0), bp))
+
+
+def test_auto_serves_ordinary_samples_through_the_split_path(gpu_auto):
+    """RCP_PATH_AUTO: short reads over a GRanges mask go through the one-pass split path; reads
+    wider than its packed word allows fall back (same results either way)."""
+    from recoup_b200 import _lib
+    rb = gpu_auto
+    rng = np.random.default_rng(8)
+    clen = [90000, 30000]
+    for width, want_path in (((30, 250), 4), ((9000, 12000), None)):
+        chrom, s, e, st = synth_reads(rng, 5000, clen, width=width)
+        o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+        rc, rs, re_, rst = _equal_windows(rng, 100, clen, 2500)
+        o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+        cov = rb.calcCoverage(g_reads, g_mask)
+        pth, cand = C.c_int(0), C.c_int64(0)
+        _lib.check(_lib.lib.rcp_coverage_path_info(cov.handle, C.byref(pth), C.byref(cand)))
+        if want_path is not None:
+            assert pth.value == want_path and cand.value > 0
+        else:
+            assert pth.value != 4
+        assert_coverage_equal(cov.to_list(), O.calc_coverage(o_reads, o_mask, None, True))
+
+
+def test_region_sharded_run_equals_the_single_gpu_matrix(gpu_auto):
+    """The multi-GPU path with the CUDA library behind every rank, emulated in one process (the
+    ranks of a box run the same code on their own GPUs): partition_regions + slice_spans +
+    exchange_reads (world 1: the local filter) per slice, the row blocks put back by row index --
+    bitwise equal to the one-GPU matrix, coverage included."""
+    import torch
+    import workloads as W
+    from recoup_b200.sharding import exchange_reads, partition_regions, slice_spans
+    rb = gpu_auto
+    w = W.dnase_sites(scale=0.002, seed=17)
+    genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"], strand=w["region_strand"],
+                       seqlevels=w["chrom_names"])
+    win = rb.getRegionalRanges(genes, "custom", w["flank"])
+    reads = rb.GRanges(w["read_chrom"], w["read_start"], w["read_end"], strand=w["read_strand"],
+                       seqlevels=w["chrom_names"], seqlengths=w["chrom_len"])
+    full, _ = rb.coverageProfile(reads, win, 0)
+    full_cov = rb.calcCoverage(reads, win).to_list()
+    world = 3
+    parts = partition_regions(win.seqnames, win.start, win.end, world)
+    spans = slice_spans(win.seqnames, win.start, win.end, parts, len(w["chrom_len"]))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))      # noqa: E731
+    got = np.full_like(np.asarray(full), -1.0)
+    for rank in range(world):
+        idx = np.sort(parts[rank])
+        # world 1 inside exchange_reads: the local filter against THIS rank's spans
+        c, s, e, st = exchange_reads(t(w["read_chrom"]), t(w["read_start"]), t(w["read_end"]), t(w["read_strand"]),
+                                     spans[rank:rank + 1])
+        assert 0 < c.shape[0] < len(w["read_start"])
+        mine = rb.GRanges(c.numpy(), s.numpy(), e.numpy(), strand=st.numpy(), seqlevels=w["chrom_names"],
+                          seqlengths=w["chrom_len"])
+        block, _ = rb.coverageProfile(mine, win.subset(idx), 0)
+        got[idx] = np.asarray(block)
+        cov = rb.calcCoverage(mine, win.subset(idx)).to_list()
+        for k, i in enumerate(idx):
+            a, b = cov[k], full_cov[int(i)]
+            assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
+    assert np.array_equal(got, np.asarray(full))
