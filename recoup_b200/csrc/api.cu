@@ -249,6 +249,9 @@ int coverage_ranges_blocks(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
 int coverage_ranges_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                           const int32_t* end, const int8_t* strand, int ignore_strand,
                           int strand_filter, int mem, Coverage* cv);
+int coverage_list_split(ReadsIdx& rd, int64_t G, const int64_t* ptr, int64_t n_ranges, const int32_t* chrom,
+                        const int32_t* start, const int32_t* end, const int8_t* strand, int ignore_strand,
+                        int strand_filter, int mem, Coverage* cv);
 int coverage_profile_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32_t* start,
                            const int32_t* end, const int8_t* strand, int ignore_strand,
                            int strand_filter, int mem, int n_bins, int seed, int sample_kind,
@@ -777,7 +780,17 @@ int rcp_coverage_list(int reads, int64_t n_elements, const int64_t* ptr, const i
     Coverage* cv;
     int h;
     RCP_TRY(new_coverage(&cv, &h));
-    int rc = coverage_list(*r, n_elements, ptr, n_ranges, chrom, start, end, strand,
+    // the handle's binned index (built on first use) serves the call when the reads fit its packed
+    // word; the start-sorted pairs (one radix sort of every read) otherwise or on request
+    int rc = RCP_SPLIT_NOT_APPLICABLE;
+    if ((g_ctx.coverage_path == RCP_PATH_AUTO || g_ctx.coverage_path == RCP_PATH_SPLIT) && !r->pairs_built &&
+        getenv("RCP_AUTO_NO_SPLIT") == nullptr) {
+        rc = coverage_list_split(*r, n_elements, ptr, n_ranges, chrom, start, end, strand, ignore_strand != 0,
+                                 strand_filter, mem, cv);
+        if (rc == RCP_SPLIT_NOT_APPLICABLE) coverage_release(*cv);
+    }
+    if (rc == RCP_SPLIT_NOT_APPLICABLE)
+        rc = coverage_list(*r, n_elements, ptr, n_ranges, chrom, start, end, strand,
                            ignore_strand != 0, strand_filter, mem, cv);
     if (rc != RCP_OK) {
         drop_coverage(h);

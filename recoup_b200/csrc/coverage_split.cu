@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(CTA)
 sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, const uint32_t* __restrict__ gs,
                 const int32_t* __restrict__ plen, const uint8_t* __restrict__ flags,
                 const int64_t* __restrict__ cov_off /* nullptr: fused, `out` = offset inside the region */,
-                uint32_t max_w, uint32_t pmask, SpDesc* __restrict__ desc) {
+                uint32_t max_w, uint32_t pmask, SpDesc* __restrict__ desc, uint32_t* __restrict__ tabs,
+                const uint32_t* __restrict__ lxs, const uint32_t* __restrict__ lmax, uint32_t ln,
+                uint2* __restrict__ lrange) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (t >= T) return;
     const int64_t r = sp_owner_of(off_tile, R, t);
@@ -157,6 +159,25 @@ sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, cons
     d.flags = flags[r];
     d.region = (uint32_t)r;
     desc[t] = d;
+    if (ln) {           // the handle keeps long reads aside: those that can meet this tile
+        tabs[t] = tstart;
+        const uint32_t hi = tstart + tlen - 1u;
+        uint32_t a = 0, b = ln;
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            if (__ldg(lxs + mid) < hi + 1u) a = mid + 1;
+            else b = mid;
+        }
+        const uint32_t c1 = a;
+        a = 0;
+        b = c1;
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            if (__ldg(lmax + mid) < tstart + 1u) a = mid + 1;
+            else b = mid;
+        }
+        lrange[t] = make_uint2(a, c1);
+    }
 }
 
 // sub-bin indices -> candidate range
@@ -229,7 +250,7 @@ template <bool STRANDED>
 __global__ void __launch_bounds__(ST, 1)
 sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t* __restrict__ g_end1,
                 const int8_t* __restrict__ strand, const uint32_t* __restrict__ tab_g, int words, int P,
-                SplitOut out) {
+                uint32_t max_pack_w, SplitOut out) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
@@ -301,7 +322,7 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
     auto keep_read = [&](uint32_t s, uint32_t e1) -> bool {
         const uint32_t t = lds32(tab_a + ((s >> (BLK_SHIFT + 2)) & 0xfffffffcu)) >> ((s >> BLK_SHIFT) & 15u);
         const bool cross = ((e1 - 1u) >> BLK_SHIFT) != (s >> BLK_SHIFT);
-        return (t & 1u) | (cross & ((t >> 16) & 1u));
+        return ((t & 1u) | (cross & ((t >> 16) & 1u))) & (e1 - s <= max_pack_w);    // wider: the long-read list
     };
     auto pack = [&](uint32_t s, uint32_t e1, int st) -> uint32_t {
         uint32_t word = (s & pmask) | ((e1 - s) << wsh);
@@ -583,6 +604,64 @@ sp_group_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ 
     for (uint32_t i = n4 * 4 + tid; i < full; i += GT) cand[base + i] = 0u;
 }
 
+// ------------------------------------------------------------------------ long reads ----------
+// Reads wider than the packed word allows stay out of the binned index: start-sorted, with the
+// running maximum of their ends, they are looked up per tile (GRanges masks) or per element
+// (GRangesList masks) and applied whole.
+struct LongIdx {
+    uint32_t n;
+    const uint32_t* xs;      // sorted starts
+    const uint32_t* e1;      // end + 1
+    const int8_t* st;        // strand (nullptr: '*')
+    const uint32_t* maxe1;   // running max of e1
+};
+
+__global__ void __launch_bounds__(CTA)
+sp_long_count_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1, uint32_t max_pack_w,
+                     unsigned long long* __restrict__ count) {
+    unsigned c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * CTA + threadIdx.x; i < n; i += (int64_t)gridDim.x * CTA)
+        c += (e1[i] - s[i] > max_pack_w) && (e1[i] > s[i]);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(CTA)
+sp_long_collect_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
+                       uint32_t max_pack_w, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ keys,
+                       uint32_t* __restrict__ idx) {
+    for (int64_t i = (int64_t)blockIdx.x * CTA + threadIdx.x; i < n; i += (int64_t)gridDim.x * CTA)
+        if (e1[i] - s[i] > max_pack_w && e1[i] > s[i]) {
+            const unsigned long long k = atomicAdd(cursor, 1ull);
+            keys[k] = s[i];
+            idx[k] = (uint32_t)i;
+        }
+}
+
+__global__ void __launch_bounds__(CTA)
+sp_long_gather_kernel(uint32_t n, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ e1,
+                      const int8_t* __restrict__ st, uint32_t* __restrict__ o_e1, int8_t* __restrict__ o_st) {
+    const uint32_t i = blockIdx.x * CTA + threadIdx.x;
+    if (i >= n) return;
+    o_e1[i] = e1[idx[i]];
+    if (st) o_st[i] = st[idx[i]];
+}
+
+__device__ __forceinline__ uint32_t sp_lower_bound(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {
+    while (lo < hi) {               // first index with a[i] >= v
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// long reads that can meet [lo, hi] (global, closed): start <= hi and the running max of end + 1 > lo
+__device__ __forceinline__ uint2 sp_long_range(const LongIdx& lg, uint32_t lo, uint32_t hi) {
+    const uint32_t c1 = sp_lower_bound(lg.xs, 0, lg.n, hi + 1u);
+    const uint32_t c0 = sp_lower_bound(lg.maxe1, 0, c1, lo + 1u);
+    return make_uint2(c0, c1);
+}
+
 // --------------------------------------------------------------------------------- tiles ------
 __device__ __forceinline__ SpDesc sp_load_desc(const SpDesc* __restrict__ p) {
     const int4 a = __ldg(reinterpret_cast<const int4*>(p));
@@ -709,7 +788,8 @@ sp_bins_finish_kernel(FusedBins fb, const int32_t* __restrict__ plen, const uint
 template <bool STRANDED, bool FUSED>
 __global__ void __launch_bounds__(CTA, 4)
 sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
-                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, FusedBins fb) {
+                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, FusedBins fb, LongIdx lg,
+                const uint32_t* __restrict__ tabs, const uint2* __restrict__ lrange) {
     __shared__ __align__(16) int sm[WARPS][WT_ONE];
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -745,6 +825,26 @@ sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __re
             if (i0 >= d.n) break;
             load4(d, i0, e);
         }
+        if (lg.n) {             // the reads kept out of the binned index
+            const uint2 lr = lrange[t];
+            const uint32_t ts = tabs[t];
+            for (uint32_t i = lr.x + lane; i < lr.y; i += 32) {
+                const uint32_t rs = __ldg(lg.xs + i), re1 = __ldg(lg.e1 + i);
+                const int st = lg.st ? (int)__ldg(lg.st + i) : 0;
+                const uint32_t cls = st > 0 ? 0u : (st < 0 ? 1u : 2u);
+                if (!((d.flags >> (1u + cls)) & 1u)) continue;
+                if (rs >= ts + (uint32_t)d.tlen || re1 <= ts) continue;
+                int lo = (int)(max(rs, ts) - ts), hi = (int)(min(re1, ts + (uint32_t)d.tlen) - ts);
+                if (d.flags & 1u) {
+                    const int l2 = d.tlen - hi;
+                    hi = d.tlen - lo;
+                    lo = l2;
+                }
+                atomicAdd(diff + lo, 1);
+                if (hi < d.tlen) atomicSub(diff + hi, 1);
+                hit = true;
+            }
+        }
         hit = __any_sync(0xffffffffu, hit);
         __syncwarp();
         int32_t* dst = FUSED ? nullptr : cov + d.out;
@@ -775,6 +875,241 @@ sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __re
         if (t + step < T) dn = sp_load_desc(desc + t + step);
 #pragma unroll
         for (int k = 0; k < B; k++) e[k] = f[k];
+    }
+}
+
+// ---------------------------------------------------------------------- GRangesList masks -----
+// coverageFromRanges on a GRangesList element (coverage.R:177-178,202-207): all ranges (exons) of
+// the element stitched into one vector; a read overlapping k ranges of the element counts k times
+// on every range it touches (coverage.R:190-192).
+struct ListPlan {
+    const int64_t* ptr;      // G + 1
+    const int8_t* rstrand;   // per range (may be nullptr)
+    uint32_t* xgs;           // per range: global start (after the zero-index drop)
+    uint32_t* xge;           //            global end; xge + 1 == xgs marks a zero-width range
+    int32_t* xoff;           //            offset of the range inside the stitched element
+    uint2* lrange;           // per element: the long reads that can meet its span
+};
+
+// err bits: 1 chrom id, 2 end < start-1, 4 ranges of one element on different chromosomes
+__global__ void __launch_bounds__(CTA)
+sp_list_plan_kernel(int64_t G, ListPlan lp, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
+                    const int32_t* __restrict__ end, const uint32_t* __restrict__ chrom_off,
+                    const int64_t* __restrict__ chrom_len, int n_chrom, int32_t* __restrict__ plen,
+                    uint8_t* __restrict__ flags, int64_t* __restrict__ ntile, int64_t* __restrict__ padded,
+                    unsigned int* __restrict__ err, unsigned long long* __restrict__ pstats, LongIdx lg) {
+    const int64_t g = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    unsigned long long my_len = 0;
+    if (g < G) {
+        const int64_t a = lp.ptr[g], b = lp.ptr[g + 1];
+        bool null = (b <= a);
+        int64_t L = 0;
+        int st0 = 0;
+        uint32_t lo = 0xffffffffu, hi = 0;
+        if (!null) {
+            const int c = chrom[a];
+            st0 = lp.rstrand ? (int)lp.rstrand[a] : 0;       // strand of the FIRST range (coverage.R:185)
+            if (c < 0 || c >= n_chrom) {
+                atomicOr(err, 1u);
+                null = true;
+            } else {
+                const int64_t clen = chrom_len[c];
+                const uint32_t coff = chrom_off[c];
+                for (int64_t i = a; i < b; i++) {
+                    int64_t s = start[i], e = end[i];
+                    if (chrom[i] != c) atomicOr(err, 4u);
+                    if (e < s - 1) { atomicOr(err, 2u); null = true; }
+                    if (s < 0 || e > clen) null = true;      // coverage.R:206 inside the tryCatch
+                    if (s == 0) s = 1;
+                    int64_t w = e - s + 1;
+                    if (w < 0) w = 0;
+                    const uint32_t gs = coff + (uint32_t)(s > 0 ? s : 0);
+                    lp.xgs[i] = gs;
+                    lp.xge[i] = gs + (uint32_t)w - 1u;
+                    lp.xoff[i] = (int32_t)L;
+                    L += w;
+                    if (w > 0) {
+                        lo = min(lo, gs);
+                        hi = max(hi, gs + (uint32_t)w - 1u);
+                    }
+                }
+                if (L == 0 || L > 0x7fffffff) null = true;
+            }
+        }
+        const int32_t len = null ? 0 : (int32_t)L;
+        lp.lrange[g] = (lg.n && !null) ? sp_long_range(lg, lo, hi) : make_uint2(0u, 0u);
+        plen[g] = len;
+        flags[g] = (uint8_t)(st0 < 0 ? 1u : 0u);
+        ntile[g] = len > WT_ONE ? ((int64_t)len + WT - 1) / WT : (len > 0 ? 1 : 0);
+        padded[g] = ((int64_t)len + PAD - 1) / PAD * PAD;
+        my_len = (unsigned long long)len;
+    }
+    unsigned long long my_max = my_len;
+    for (int d = 16; d > 0; d >>= 1) {
+        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+    }
+    if ((threadIdx.x & 31) == 0 && my_len) {
+        atomicAdd(&pstats[0], my_len);
+        atomicMax(&pstats[1], my_max);
+    }
+}
+
+// tiles of the stitched vectors: `cts` holds the tile's first STITCHED position
+__global__ void __launch_bounds__(CTA)
+sp_list_tiles_kernel(int64_t G, int64_t T, const int64_t* __restrict__ off_tile, const int32_t* __restrict__ plen,
+                     const uint8_t* __restrict__ flags, const int64_t* __restrict__ cov_off,
+                     SpDesc* __restrict__ desc) {
+    const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (t >= T) return;
+    const int64_t g = sp_owner_of(off_tile, G, t);
+    const int L = plen[g];
+    uint32_t o_lo = 0, tlen = (uint32_t)L;
+    if (L > WT_ONE) {
+        o_lo = (uint32_t)(t - off_tile[g]) * WT;
+        tlen = (uint32_t)min(WT, L - (int)o_lo);
+    }
+    SpDesc d;
+    d.out = cov_off[g] + o_lo;
+    d.c0 = d.n = 0;
+    d.tlen = (int32_t)tlen;
+    d.cts = (flags[g] & 1u) ? (uint32_t)L - o_lo - tlen : o_lo;
+    d.flags = flags[g];
+    d.region = (uint32_t)g;
+    desc[t] = d;
+}
+
+// One warp per tile of a stitched vector.  For every range piece under the tile the warp reads the
+// candidates of the sub-bins that can reach it; a candidate that overlaps the range adds its
+// multiplicity (the number of ranges of the element it hits under the strand rules) on the piece.
+template <bool STRANDED>
+__global__ void __launch_bounds__(CTA, 4)
+sp_ltile_kernel(int64_t T, const SpDesc* __restrict__ desc, ListPlan lp, const uint32_t* __restrict__ cand,
+                const uint32_t* __restrict__ boff, int P, uint32_t max_w, int ignore_strand, int strand_filter,
+                int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, LongIdx lg) {
+    __shared__ __align__(16) int sm[WARPS][WT_ONE];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    int* diff = sm[warp];
+    const int64_t step = (int64_t)gridDim.x * WARPS;
+    const int sh = 32 - P;
+    const uint32_t pmask = (1u << P) - 1u;
+    for (int64_t t = (int64_t)blockIdx.x * WARPS + warp; t < T; t += step) {
+        const SpDesc d = sp_load_desc(desc + t);
+        const int64_t a = lp.ptr[d.region], b = lp.ptr[d.region + 1];
+        const int tlen = d.tlen, t0 = (int)d.cts, t1 = t0 + tlen;
+        const bool rev = d.flags & 1u;
+        const int rows = (tlen + ROW - 1) / ROW;
+        for (int k = 0; k < rows; k++) reinterpret_cast<int4*>(diff)[k * 32 + lane] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        int64_t qa = a, qb = b;              // last range with xoff <= t0
+        while (qb - qa > 1) {
+            const int64_t mid = (qa + qb) >> 1;
+            if (__ldg(lp.xoff + mid) <= t0) qa = mid;
+            else qb = mid;
+        }
+        bool hit = false;
+        for (int64_t q = qa; q < b; q++) {
+            const int xo = __ldg(lp.xoff + q);
+            if (xo >= t1) break;
+            const uint32_t s = __ldg(lp.xgs + q), e = __ldg(lp.xge + q);
+            if (e + 1u == s) continue;
+            const int w = (int)(e - s) + 1;
+            const int k0 = max(xo, t0), k1 = min(xo + w, t1);              // stitched [k0, k1)
+            if (k0 >= k1) continue;
+            const uint32_t ps = s + (uint32_t)(k0 - xo), pe = s + (uint32_t)(k1 - 1 - xo);   // genomic piece
+            const uint32_t first = ps >= max_w ? ps - max_w + 1u : 0u;
+            const uint32_t c0 = __ldg(boff + (first >> SUB_SHIFT)), c1 = __ldg(boff + (pe >> SUB_SHIFT) + 1);
+            for (uint32_t i = c0 + lane; i < c1; i += 32) {
+                const uint32_t word = __ldg(cand + i);
+                const int rel = ((int)((word - (ps & pmask)) << sh)) >> sh;
+                const uint32_t wd = word >> (STRANDED ? P + 2 : P);
+                if (wd == 0u) continue;
+                const int64_t rs64 = (int64_t)ps + rel;
+                const uint32_t rs = (uint32_t)rs64, re1 = rs + wd;
+                if (!(rs <= pe && re1 > ps)) continue;                     // does not reach the piece
+                int rst = 0;
+                if (STRANDED) {
+                    const uint32_t cls = (word >> P) & 3u;
+                    rst = cls == 0u ? 1 : (cls == 1u ? -1 : 0);
+                }
+                if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
+                int mult = 0;
+                for (int64_t z = a; z < b; z++) {
+                    const uint32_t zs = __ldg(lp.xgs + z), ze = __ldg(lp.xge + z);
+                    if (ze + 1u == zs) continue;
+                    if (rs <= ze && re1 > zs &&
+                        strand_ok(rst, lp.rstrand ? (int)__ldg(lp.rstrand + z) : 0, ignore_strand, strand_filter))
+                        mult++;
+                }
+                if (mult == 0) continue;
+                hit = true;
+                // +mult on the covered part of the piece, in output order
+                const int ka = k0 + (int)(max(rs, ps) - ps) - t0;
+                const int kb1 = k0 + (int)(min(re1 - 1u, pe) - ps) + 1 - t0;    // may equal tlen
+                if (!rev) {
+                    atomicAdd(diff + ka, mult);
+                    if (kb1 < tlen) atomicSub(diff + kb1, mult);
+                } else {
+                    atomicAdd(diff + (tlen - kb1), mult);
+                    if (ka > 0) atomicSub(diff + (tlen - ka), mult);
+                }
+            }
+        }
+        if (lg.n) {             // the reads kept out of the binned index: whole reads against the element
+            const uint2 lr = lp.lrange[d.region];
+            for (uint32_t i = lr.x + lane; i < lr.y; i += 32) {
+                const uint32_t rs = __ldg(lg.xs + i), re1 = __ldg(lg.e1 + i);
+                const int rst = lg.st ? (int)__ldg(lg.st + i) : 0;
+                if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
+                int mult = 0;
+                for (int64_t z = a; z < b; z++) {
+                    const uint32_t zs = __ldg(lp.xgs + z), ze = __ldg(lp.xge + z);
+                    if (ze + 1u == zs) continue;
+                    if (rs <= ze && re1 > zs &&
+                        strand_ok(rst, lp.rstrand ? (int)__ldg(lp.rstrand + z) : 0, ignore_strand, strand_filter))
+                        mult++;
+                }
+                if (mult == 0) continue;
+                for (int64_t q = qa; q < b; q++) {
+                    const int xo = __ldg(lp.xoff + q);
+                    if (xo >= t1) break;
+                    const uint32_t s = __ldg(lp.xgs + q), e = __ldg(lp.xge + q);
+                    if (e + 1u == s || !(rs <= e && re1 > s)) continue;
+                    const int pa = xo + (int)(max(rs, s) - s), pb = xo + (int)(min(re1 - 1u, e) - s);   // stitched, closed
+                    if (pb < t0 || pa >= t1) continue;
+                    const int ka = max(pa, t0) - t0, kb1 = min(pb, t1 - 1) + 1 - t0;
+                    hit = true;
+                    if (!rev) {
+                        atomicAdd(diff + ka, mult);
+                        if (kb1 < tlen) atomicSub(diff + kb1, mult);
+                    } else {
+                        atomicAdd(diff + (tlen - kb1), mult);
+                        if (ka > 0) atomicSub(diff + (tlen - ka), mult);
+                    }
+                }
+            }
+        }
+        hit = __any_sync(0xffffffffu, hit);
+        __syncwarp();
+        int32_t* dst = cov + d.out;
+        switch (rows) {
+            case 1: warp_scan_store_fwd<1>(diff, tlen, dst); break;
+            case 2: warp_scan_store_fwd<2>(diff, tlen, dst); break;
+            case 3: warp_scan_store_fwd<3>(diff, tlen, dst); break;
+            case 4: warp_scan_store_fwd<4>(diff, tlen, dst); break;
+            case 5: warp_scan_store_fwd<5>(diff, tlen, dst); break;
+            case 6: warp_scan_store_fwd<6>(diff, tlen, dst); break;
+            case 7: warp_scan_store_fwd<7>(diff, tlen, dst); break;
+            default: {
+                int pre = 0;
+                for (int row = 0; row < rows; row++)
+                    pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, tlen - row * ROW, dst + row * ROW);
+            }
+        }
+        if (hit && lane == 0) region_hit[d.region] = 1;
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
     }
 }
 
@@ -812,6 +1147,162 @@ sp_null_kernel(int64_t R, const int32_t* __restrict__ plen, const uint8_t* __res
 // Same contract as coverage_ranges_bucketed.  RCP_SPLIT_NOT_APPLICABLE: the reads are too wide for
 // the packed candidate word of this genome (or the genome too long for the shared-memory table);
 // nothing has been produced and the caller uses another path.
+struct SortedCands {
+    uint32_t* cand = nullptr;     // packed candidate words, sorted by 1-kb sub-bin
+    uint32_t* boff = nullptr;     // n_groups * nb + 1 sub-bin offsets into cand
+    uint32_t* cb = nullptr;       // NG + 1: chunk-list offsets per group (cb[NG] * CH >= candidates)
+};
+
+// split kernel + chunk lists + group sort.  tab: the mask's block table on the device.  The
+// result lives in arena K (the caller keeps or drops it); B is scratch of the passes.
+static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, int n_groups, bool stranded,
+                          bool st_arr, uint32_t max_pack_w, Arena& K, Arena& B, SortedCands* sc) {
+    const int nb = 1 << (P - SUB_SHIFT);
+    const uint32_t pmask = (1u << P) - 1u;
+    const int split_grid = g_ctx.sm_count;
+    const int sort_grid = 64;          // columns of the chunk-count table (one CTA each)
+    const size_t pool_cap = (size_t)(rd.n / CH + 1) + (size_t)split_grid * NG +
+                            (size_t)split_grid * (ST / 32) * SLAB * 2 + SLAB;
+    RCP_TRY(K.reserve(Arena::pad(pool_cap * CH * 4) + Arena::pad((NG + 1) * 4) +
+                      Arena::pad(((size_t)n_groups * nb + 1) * 4)));
+    sc->cand = K.take<uint32_t>(pool_cap * CH);
+    sc->cb = K.take<uint32_t>(NG + 1);
+    sc->boff = K.take<uint32_t>((size_t)n_groups * nb + 1);
+    RCP_TRY(B.reserve(Arena::pad(pool_cap * CH * 4) + Arena::pad(pool_cap * 2) + Arena::pad(pool_cap * 4) +
+                      Arena::pad(16) + Arena::pad((size_t)sort_grid * NG * 4)));
+    uint32_t* pool_next = B.take<uint32_t>(4);
+    uint16_t* meta = B.take<uint16_t>(pool_cap);
+    const size_t zero_b = B.used;
+    uint32_t* pool = B.take<uint32_t>(pool_cap * CH);
+    uint32_t* list = B.take<uint32_t>(pool_cap);
+    uint32_t* col = B.take<uint32_t>((size_t)sort_grid * NG);
+    if (B.used > B.cap || K.used > K.cap) return fail(RCP_ERR_CUDA, "internal: split arena overrun");
+    {
+        StageTimer t(ST_SP_SPLIT);
+        RCP_CUDA(cudaMemsetAsync(B.base, 0, zero_b, g_ctx.stream));
+        const size_t smem = sp_split_smem(words);
+        SplitOut out = {pool, meta, pool_next};
+        if (stranded) {     // no strand array: every read is '*'
+            RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1,
+                                                                         st_arr ? rd.d_strand : nullptr, tab, words, P,
+                                                                         max_pack_w, out);
+        } else {
+            RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sp_split_kernel<false><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, nullptr, tab,
+                                                                          words, P, max_pack_w, out);
+        }
+        RCP_LAUNCHED();
+    }
+    {
+        StageTimer t(ST_SP_SORT);
+        sp_chunk_hist_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col);
+        RCP_LAUNCHED();
+        sp_chunk_scan_kernel<<<1, NG, 0, g_ctx.stream>>>(col, sort_grid, sc->cb);
+        RCP_LAUNCHED();
+        sp_chunk_place_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col, list);
+        RCP_LAUNCHED();
+        RCP_CUDA(cudaFuncSetAttribute(sp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM));
+        sp_group_kernel<<<n_groups, GT, GSMEM, g_ctx.stream>>>(pool, list, sc->cb, n_groups, nb, pmask, sc->cand,
+                                                               sc->boff);
+        RCP_LAUNCHED();
+    }
+    return RCP_OK;
+}
+
+// The genome's split geometry: position bits of a candidate word, groups, table words.
+struct SplitGeom {
+    int words, P, n_groups, nb;
+    uint32_t pmask;
+    bool ok;
+};
+static SplitGeom split_geometry(const ReadsIdx& rd) {
+    SplitGeom g;
+    const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
+    g.words = (int)((span >> (BLK_SHIFT + 4)) + 2);
+    g.P = MIN_P;
+    while (g.P < MAX_P && ((span + (1ll << g.P) - 1) >> g.P) > NG) g.P++;
+    g.n_groups = (int)std::max<int64_t>(1, (span + (1ll << g.P) - 1) >> g.P);
+    g.nb = 1 << (g.P - SUB_SHIFT);
+    g.pmask = (1u << g.P) - 1u;
+    g.ok = g.n_groups <= NG && rd.n < 0x7ffffff0ll && sp_split_smem(g.words) <= SP_SMEM_MAX;
+    return g;
+}
+
+// Builds the handle's binned index (every read, sorted by 1-kb bin).  RCP_SPLIT_NOT_APPLICABLE when
+// the reads do not fit the packed word.  The words carry the strand class when the reads have one.
+static LongIdx long_index(const ReadsIdx& rd) {
+    LongIdx lg;
+    lg.n = (uint32_t)rd.ln_n;
+    lg.xs = rd.ln_xs;
+    lg.e1 = rd.ln_e1;
+    lg.st = rd.ln_st;
+    lg.maxe1 = rd.ln_maxe1;
+    return lg;
+}
+
+static int reads_build_binned(ReadsIdx& rd) {
+    if (rd.bn_cand) return RCP_OK;
+    RCP_TRY(reads_resolve(rd));
+    const SplitGeom g = split_geometry(rd);
+    const bool stranded = rd.d_strand != nullptr;
+    const int wbits = 32 - g.P - (stranded ? 2 : 0);
+    if (!g.ok || wbits < 7) return RCP_SPLIT_NOT_APPLICABLE;
+    // the words hold reads up to max_pack_w wide; wider ones go to the long-read list
+    const uint32_t max_pack_w = std::min<uint32_t>((1u << wbits) - 1u, 8191u);
+    rd.bn_max_pack_w = max_pack_w;
+    if (rd.max_width > max_pack_w) {
+        unsigned long long* d_cnt = nullptr;
+        RCP_TRY(dalloc(&d_cnt, 2));
+        RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 16, g_ctx.stream));
+        const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(rd.n, CTA), (int64_t)g_ctx.sm_count * 8);
+        sp_long_count_kernel<<<grid, CTA, 0, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, max_pack_w, d_cnt);
+        RCP_LAUNCHED();
+        unsigned long long h_cnt = 0;
+        const FetchItem it[1] = {{d_cnt, &h_cnt, 8}};
+        RCP_TRY(fetch_and_sync(it, 1));
+        // a sample made of long reads is not what this index is for
+        if (h_cnt > (unsigned long long)rd.n / 8 || h_cnt >= 0x7fffffffull) {
+            dfree(d_cnt);
+            return RCP_SPLIT_NOT_APPLICABLE;
+        }
+        const size_t n = (size_t)h_cnt;
+        uint32_t* idx = nullptr;
+        RCP_TRY(dalloc(&rd.ln_xs, n));
+        RCP_TRY(dalloc(&rd.ln_e1, n));
+        RCP_TRY(dalloc(&rd.ln_maxe1, n));
+        if (rd.d_strand) RCP_TRY(dalloc(&rd.ln_st, n));
+        RCP_TRY(dalloc(&idx, n));
+        sp_long_collect_kernel<<<grid, CTA, 0, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, max_pack_w, d_cnt + 1,
+                                                               rd.ln_xs, idx);
+        RCP_LAUNCHED();
+        RCP_TRY(sort_pairs_u32(rd.ln_xs, idx, (int64_t)n, rd.key_bits));
+        if (n > 0) {
+            sp_long_gather_kernel<<<blocks_for((int64_t)n, CTA), CTA, 0, g_ctx.stream>>>((uint32_t)n, idx, rd.g_end1,
+                                                                                        rd.d_strand, rd.ln_e1, rd.ln_st);
+            RCP_LAUNCHED();
+        }
+        RCP_TRY(running_max_u32_device(rd.ln_e1, rd.ln_maxe1, (int64_t)n));
+        rd.ln_n = (int64_t)n;
+        dfree(idx);
+        dfree(d_cnt);
+    }
+    Arena K, B, Tb;
+    RCP_TRY(Tb.reserve(Arena::pad((size_t)g.words * 4)));
+    uint32_t* tab = Tb.take<uint32_t>((size_t)g.words);
+    RCP_CUDA(cudaMemsetAsync(tab, 0xff, (size_t)g.words * 4, g_ctx.stream));      // the mask "everything"
+    SortedCands sc;
+    RCP_TRY(split_and_sort(rd, tab, g.words, g.P, g.n_groups, stranded, stranded, max_pack_w, K, B, &sc));
+    rd.bn_base = K.base;
+    K.base = nullptr;                   // the handle owns it now
+    rd.bn_cand = sc.cand;
+    rd.bn_boff = sc.boff;
+    rd.bn_cb = sc.cb;
+    rd.bn_P = g.P;
+    rd.bn_stranded = stranded;
+    return RCP_OK;
+}
+
 // fz != nullptr: the FUSED form (rcp_coverage_profile): no coverage is stored, the tiles add their
 // bin sums to accumulators and sp_bins_finish_kernel writes the matrix (cv is scratch then).
 // RCP_SPLIT_NOT_APPLICABLE there also when the windows differ in length or are shorter than the
@@ -837,7 +1328,9 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     const int wbits = 32 - P - (stranded ? 2 : 0);
     if (n_groups > NG || rd.n >= 0x7ffffff0ll || sp_split_smem(words) > SP_SMEM_MAX)
         return RCP_SPLIT_NOT_APPLICABLE;
-    if (!rd.pending && (rd.max_width > 8191u || rd.max_width >= (1u << wbits))) return RCP_SPLIT_NOT_APPLICABLE;
+    const bool have_index = rd.bn_cand && rd.bn_P == P && (rd.bn_stranded || !stranded);
+    if (!have_index && !rd.pending && (rd.max_width > 8191u || rd.max_width >= (1u << wbits)))
+        return RCP_SPLIT_NOT_APPLICABLE;
     const uint32_t pmask = (1u << P) - 1u;
     const int nb = 1 << (P - SUB_SHIFT);                // sub-bins of a group
 
@@ -909,8 +1402,11 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     if (h.err & 2u) return fail(RCP_ERR_DATA, "a region has end < start - 1");
     const int64_t T = h.T;
     if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
-    const uint32_t max_w = rd.max_width > 0 ? rd.max_width : 1u;
-    if (max_w > 8191u || max_w >= (1u << wbits)) return give_up();
+    // (with the handle's binned index the words hold the reads up to bn_max_pack_w; wider ones
+    // come from the long-read list)
+    const uint32_t max_w = have_index ? std::max(1u, std::min(rd.max_width, rd.bn_max_pack_w))
+                                      : (rd.max_width > 0 ? rd.max_width : 1u);
+    if (!have_index && (max_w > 8191u || max_w >= (1u << wbits))) return give_up();
 
     // ---- fused: one common window length, bin edges of splitVector (util.R:74-80) -------------
     FusedBins fb = {nullptr, 0, R, nullptr};
@@ -954,60 +1450,34 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
         RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
     }
 
-    // ---- scratch of the read passes ------------------------------------------------------------
-    const int split_grid = g_ctx.sm_count;
-    const int sort_grid = 64;          // columns of the chunk-count table (one CTA each)
-    const size_t pool_cap = (size_t)(rd.n / CH + 1) + (size_t)split_grid * NG +
-                            (size_t)split_grid * (ST / 32) * SLAB * 2 + SLAB;
-    Arena B;
-    RCP_TRY(B.reserve(Arena::pad(pool_cap * CH * 4) * 2 + Arena::pad(pool_cap * 2) + Arena::pad(pool_cap * 4) +
-                      Arena::pad(16) + Arena::pad((size_t)sort_grid * NG * 4) + Arena::pad((NG + 1) * 4) +
-                      Arena::pad(((size_t)n_groups * nb + 1) * 4) + Arena::pad((size_t)(T + 1) * sizeof(SpDesc))));
-    uint32_t* pool_next = B.take<uint32_t>(4);
-    uint16_t* meta = B.take<uint16_t>(pool_cap);
-    const size_t zero_b = B.used;
-    uint32_t* pool = B.take<uint32_t>(pool_cap * CH);
-    uint32_t* cand = B.take<uint32_t>(pool_cap * CH);
-    uint32_t* list = B.take<uint32_t>(pool_cap);
-    uint32_t* col = B.take<uint32_t>((size_t)sort_grid * NG);
-    uint32_t* cb = B.take<uint32_t>(NG + 1);
-    uint32_t* boff = B.take<uint32_t>((size_t)n_groups * nb + 1);
-    SpDesc* desc = B.take<SpDesc>((size_t)T + 1);
-    if (B.used > B.cap) return fail(RCP_ERR_CUDA, "internal: split arena overrun");
-    {
+    // ---- the sorted candidates: the handle's binned index when it has one, else this mask's ----
+    Arena K, B;
+    SortedCands sc;
+    bool words_stranded = stranded;
+    if (have_index) {
+        sc.cand = rd.bn_cand;
+        sc.boff = rd.bn_boff;
+        sc.cb = rd.bn_cb;
+        words_stranded = rd.bn_stranded;
+    } else {
+        RCP_TRY(split_and_sort(rd, tab, words, P, n_groups, stranded, st_arr, 0xffffffffu, K, B, &sc));
+    }
+    uint32_t* cand = sc.cand;
+    uint32_t* boff = sc.boff;
+    uint32_t* cb = sc.cb;
+    LongIdx lg = long_index(rd);
+    if (!have_index) lg.n = 0;
+    Arena D;
+    RCP_TRY(D.reserve(Arena::pad((size_t)(T + 1) * sizeof(SpDesc)) + (lg.n ? Arena::pad((size_t)(T + 1) * 4) +
+                                                                            Arena::pad((size_t)(T + 1) * 8) : 0)));
+    SpDesc* desc = D.take<SpDesc>((size_t)T + 1);
+    uint32_t* tabs = lg.n ? D.take<uint32_t>((size_t)T + 1) : nullptr;
+    uint2* lrange = lg.n ? D.take<uint2>((size_t)T + 1) : nullptr;
+    if (T > 0) {
         StageTimer t(ST_SP_PLAN);
-        RCP_CUDA(cudaMemsetAsync(B.base, 0, zero_b, g_ctx.stream));
-        if (T > 0) {
-            sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags,
-                                                                         fz ? nullptr : cv->off, max_w, pmask, desc);
-            RCP_LAUNCHED();
-        }
-    }
-    {
-        StageTimer t(ST_SP_SPLIT);
-        const size_t smem = sp_split_smem(words);
-        SplitOut out = {pool, meta, pool_next};
-        if (stranded) {     // no strand array: every read is '*'
-            RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1,
-                                                                         st_arr ? rd.d_strand : nullptr, tab, words, P, out);
-        } else {
-            RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sp_split_kernel<false><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, nullptr, tab,
-                                                                          words, P, out);
-        }
-        RCP_LAUNCHED();
-    }
-    {
-        StageTimer t(ST_SP_SORT);
-        sp_chunk_hist_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col);
-        RCP_LAUNCHED();
-        sp_chunk_scan_kernel<<<1, NG, 0, g_ctx.stream>>>(col, sort_grid, cb);
-        RCP_LAUNCHED();
-        sp_chunk_place_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col, list);
-        RCP_LAUNCHED();
-        RCP_CUDA(cudaFuncSetAttribute(sp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM));
-        sp_group_kernel<<<n_groups, GT, GSMEM, g_ctx.stream>>>(pool, list, cb, n_groups, nb, pmask, cand, boff);
+        sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags,
+                                                                     fz ? nullptr : cv->off, max_w, pmask, desc, tabs,
+                                                                     lg.xs, lg.maxe1, lg.n, lrange);
         RCP_LAUNCHED();
     }
     if (T > 0) {
@@ -1024,12 +1494,12 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
                 RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA, 0));
                 per_sm = std::max(per_sm, 1);
                 kern<<<(unsigned)std::min<int64_t>(want, (int64_t)g_ctx.sm_count * per_sm), CTA, 0, g_ctx.stream>>>(
-                    T, desc, cand, P, cv->cov, region_hit, fb);
+                    T, desc, cand, P, cv->cov, region_hit, fb, lg, tabs, lrange);
                 RCP_LAUNCHED();
                 return RCP_OK;
             };
-            if (fz) RCP_TRY(stranded ? launch(sp_wtile_kernel<true, true>) : launch(sp_wtile_kernel<false, true>));
-            else RCP_TRY(stranded ? launch(sp_wtile_kernel<true, false>) : launch(sp_wtile_kernel<false, false>));
+            if (fz) RCP_TRY(words_stranded ? launch(sp_wtile_kernel<true, true>) : launch(sp_wtile_kernel<false, true>));
+            else RCP_TRY(words_stranded ? launch(sp_wtile_kernel<true, false>) : launch(sp_wtile_kernel<false, false>));
         }
     }
     if (fz) {
@@ -1068,6 +1538,109 @@ int coverage_profile_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
     const int rc = split_impl(rd, R, chrom, start, end, strand, ignore_strand, strand_filter, mem, &scratch, &fz);
     coverage_release(scratch);
     return rc;
+}
+
+// rcp_coverage_list through the handle's binned index (built here on first use: coverageRnaRef
+// makes three coverage calls per sample on the same reads).  RCP_SPLIT_NOT_APPLICABLE: the reads do
+// not fit the packed word; the caller uses the sorted-pair path.
+int coverage_list_split(ReadsIdx& rd, int64_t G, const int64_t* ptr, int64_t n_ranges, const int32_t* chrom,
+                        const int32_t* start, const int32_t* end, const int8_t* strand, int ignore_strand,
+                        int strand_filter, int mem, Coverage* cv) {
+    {
+        const int rc = reads_build_binned(rd);
+        if (rc != RCP_OK) return rc;
+    }
+    const SplitGeom g = split_geometry(rd);
+    const uint32_t max_w = std::max(1u, std::min(rd.max_width, rd.bn_max_pack_w));
+    const LongIdx lg = long_index(rd);
+    DevIn<int64_t> d_ptr;
+    DevIn<int32_t> d_chrom, d_start, d_end;
+    DevIn<int8_t> d_strand;
+    RCP_TRY(d_ptr.init(ptr, (size_t)G + 1, mem));
+    RCP_TRY(d_chrom.init(chrom, (size_t)n_ranges, mem));
+    RCP_TRY(d_start.init(start, (size_t)n_ranges, mem));
+    RCP_TRY(d_end.init(end, (size_t)n_ranges, mem));
+    RCP_TRY(d_strand.init(strand, (size_t)n_ranges, mem));
+    Arena A;
+    const size_t r = (size_t)G, nr = (size_t)n_ranges;
+    RCP_TRY(A.reserve(Arena::pad(64) + Arena::pad(r) * 2 + Arena::pad(r * 4) + Arena::pad(r * 8) * 3 +
+                      Arena::pad((r + 1) * 8) + Arena::pad(nr * 4) * 3));
+    unsigned int* err = A.take<unsigned int>(16);
+    unsigned long long* pstats = reinterpret_cast<unsigned long long*>(err + 4);
+    uint8_t* region_hit = A.take<uint8_t>(r);
+    const size_t zero_bytes = A.used;
+    uint8_t* flags = A.take<uint8_t>(r);
+    int32_t* plen = A.take<int32_t>(r);
+    int64_t* ntile = A.take<int64_t>(r);
+    int64_t* padded = A.take<int64_t>(r);
+    int64_t* off_tile = A.take<int64_t>(r + 1);
+    ListPlan lp;
+    lp.ptr = d_ptr.ptr;
+    lp.rstrand = d_strand.ptr;
+    lp.xgs = A.take<uint32_t>(nr);
+    lp.xge = A.take<uint32_t>(nr);
+    lp.xoff = A.take<int32_t>(nr);
+    lp.lrange = A.take<uint2>(r);
+    if (A.used > A.cap) return fail(RCP_ERR_CUDA, "internal: list plan arena overrun");
+    cv->n_regions = G;
+    RCP_TRY(dalloc(&cv->off, r + 1));
+    RCP_TRY(dalloc(&cv->len, r));
+    RCP_TRY(dalloc(&cv->is_null, r));
+    RCP_TRY(dalloc(&cv->d_stats, 4));
+    struct Host {
+        int64_t T, total_padded;
+        unsigned long long pstats[2];
+        unsigned int err;
+    } h = {0, 0, {0, 0}, 0};
+    {
+        StageTimer t(ST_COV_LIST);
+        RCP_CUDA(cudaMemsetAsync(A.base, 0, zero_bytes, g_ctx.stream));
+        RCP_CUDA(cudaMemsetAsync(cv->d_stats, 0, 32, g_ctx.stream));
+        if (G > 0) {
+            sp_list_plan_kernel<<<blocks_for(G, CTA), CTA, 0, g_ctx.stream>>>(
+                G, lp, d_chrom.ptr, d_start.ptr, d_end.ptr, rd.d_chrom_off, rd.d_chrom_len, rd.n_chrom, plen, flags,
+                ntile, padded, err, pstats, lg);
+            RCP_LAUNCHED();
+        }
+        RCP_TRY(exclusive_scan2_i64(ntile, off_tile, off_tile + G, padded, cv->off, cv->off + G, G));
+        const FetchItem items[4] = {{off_tile + G, &h.T, 8}, {cv->off + G, &h.total_padded, 8}, {pstats, h.pstats, 16},
+                                    {err, &h.err, 4}};
+        RCP_TRY(fetch_and_sync(items, 4));
+    }
+    if (h.err & 1u) return fail(RCP_ERR_DATA, "a range has a chromosome id outside [0, n_chrom)");
+    if (h.err & 2u) return fail(RCP_ERR_DATA, "a range has end < start - 1");
+    if (h.err & 4u) return fail(RCP_ERR_DATA, "the ranges of one list element lie on different chromosomes");
+    const int64_t T = h.T;
+    if (T > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 coverage tiles");
+    cv->path = 0;
+    cv->total_padded = h.total_padded;
+    cv->total_len = (int64_t)h.pstats[0];
+    cv->max_len = (int32_t)h.pstats[1];
+    cv->n_null = 0;
+    cv->stats_pending = true;
+    RCP_TRY(dalloc(&cv->cov, (size_t)h.total_padded));
+    Arena D;
+    RCP_TRY(D.reserve(Arena::pad((size_t)(T + 1) * sizeof(SpDesc))));
+    SpDesc* desc = D.take<SpDesc>((size_t)T + 1);
+    StageTimer t(ST_COV_LIST);
+    if (T > 0) {
+        sp_list_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(G, T, off_tile, plen, flags, cv->off, desc);
+        RCP_LAUNCHED();
+        const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(T, WARPS), (int64_t)g_ctx.sm_count * 4);
+        if (rd.bn_stranded)
+            sp_ltile_kernel<true><<<grid, CTA, 0, g_ctx.stream>>>(T, desc, lp, rd.bn_cand, rd.bn_boff, g.P, max_w,
+                                                                 ignore_strand, strand_filter, cv->cov, region_hit, lg);
+        else
+            sp_ltile_kernel<false><<<grid, CTA, 0, g_ctx.stream>>>(T, desc, lp, rd.bn_cand, rd.bn_boff, g.P, max_w,
+                                                                  ignore_strand, strand_filter, cv->cov, region_hit, lg);
+        RCP_LAUNCHED();
+    }
+    if (G > 0) {
+        sp_null_kernel<<<blocks_for(G, CTA), CTA, 0, g_ctx.stream>>>(G, plen, region_hit, rd.bn_cb, cv->len, cv->is_null,
+                                                                    cv->d_stats);
+        RCP_LAUNCHED();
+    }
+    return RCP_OK;
 }
 
 }  // namespace rcp

@@ -328,7 +328,17 @@ inline unsigned grid_for(int64_t n) {
 
 }  // namespace
 
+int running_max_u32_device(const uint32_t* in, uint32_t* out, int64_t n) { return running_max_u32(in, out, n); }
+
 void reads_release(ReadsIdx& r) {
+    if (r.bn_base) device_free(r.bn_base);
+    r.bn_base = nullptr;
+    r.bn_cand = r.bn_boff = r.bn_cb = nullptr;
+    dfree(r.ln_xs);
+    dfree(r.ln_e1);
+    dfree(r.ln_st);
+    dfree(r.ln_maxe1);
+    r.ln_n = 0;
     dfree(r.pd_err);
     dfree(r.pd_cnt);
     dfree(r.pd_w);

@@ -200,6 +200,23 @@ struct ReadsIdx {
     int8_t* p_strand = nullptr;         // strand in start-sorted order (nullptr when !has_strand)
     uint32_t* p_maxend1 = nullptr;      // running max of p_end1
     size_t device_bytes = 0;
+    // Binned index: EVERY read as a packed candidate word, sorted by 1-kb bin of the genome (the
+    // split path run with the mask "everything").  Built by the first GRangesList call of the
+    // handle (coverageRnaRef makes three coverage calls on it) and reused by every later call.
+    char* bn_base = nullptr;            // owner of the three arrays below
+    uint32_t* bn_cand = nullptr;
+    uint32_t* bn_boff = nullptr;
+    uint32_t* bn_cb = nullptr;
+    int bn_P = 0;
+    bool bn_stranded = false;           // the words carry the strand class
+    // reads too wide for the packed word (unspliced / long reads) are kept OUT of the binned
+    // index, start-sorted with the running maximum of their ends (a few per cent at most)
+    int64_t ln_n = 0;
+    uint32_t bn_max_pack_w = 0;         // widest read the words hold
+    uint32_t* ln_xs = nullptr;          // sorted global starts
+    uint32_t* ln_e1 = nullptr;          // end + 1 in that order
+    int8_t* ln_st = nullptr;            // strand in that order (nullptr: all '*')
+    uint32_t* ln_maxe1 = nullptr;       // running maximum of ln_e1
     // Deferred validation (rcp_set_deferred_validation): rcp_reads_load returned without waiting
     // for the map kernel; its status words are still on the device and are read by the first
     // call that uses the handle (reads_resolve, or the split path's own plan fetch).
@@ -255,6 +272,7 @@ int new_coverage(Coverage** out, int* handle);
 // radix sort (sort.cu)
 int sort_keys_u32(uint32_t* keys_in_out, int64_t n, int end_bit);
 int sort_pairs_u32(uint32_t* keys_in_out, uint32_t* vals_in_out, int64_t n, int end_bit);
+int running_max_u32_device(const uint32_t* in, uint32_t* out, int64_t n);
 // exclusive prefix sum of int64 (scan.cu); out may alias in; total (optional) receives the sum
 // on the DEVICE (d_total) -- nothing is synchronised.
 int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, int64_t* d_total);

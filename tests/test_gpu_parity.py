@@ -1071,3 +1071,50 @@ def test_region_sharded_run_equals_the_single_gpu_matrix(gpu_auto):
             a, b = cov[k], full_cov[int(i)]
             assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
     assert np.array_equal(got, np.asarray(full))
+
+
+@pytest.mark.parametrize("ignore,filt", [(True, None), (False, None), (False, "+")])
+def test_list_masks_with_long_reads_and_the_cached_binned_index(gpu, ignore, filt):
+    """GRangesList elements over a sample that mixes short reads with reads far wider than the
+    packed candidate word (unspliced / long reads, 2 %): the first list call builds the handle's
+    binned index (short reads) + long-read list, and the GRanges calls that follow on the SAME
+    handle (coverageRnaRef's flank passes) reuse both.  Multiplicity of long reads spanning
+    several exons included."""
+    rb = gpu
+    rng = np.random.default_rng(77)
+    clen = [150000, 40000]
+    chrom, s, e, st = synth_reads(rng, 30000, clen, width=(30, 300))
+    lc, ls, le, lst = synth_reads(rng, 600, clen, width=(9000, 30000))
+    chrom, s, e, st = (np.concatenate([chrom, lc]), np.concatenate([s, ls]), np.concatenate([e, le]),
+                       np.concatenate([st, lst]))
+    perm = rng.permutation(chrom.shape[0])
+    chrom, s, e, st = chrom[perm], s[perm], e[perm], st[perm]
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    ptr, xc, xs, xe, xst = [0], [], [], [], []
+    for g in range(120):
+        c = int(rng.integers(0, 2))
+        pos = int(rng.integers(1, clen[c] - 30000))
+        gst = int(rng.choice([1, -1, 0]))
+        for _ in range(int(rng.integers(1, 14))):
+            w = int(rng.integers(20, 900))
+            xc.append(c); xs.append(pos); xe.append(pos + w - 1); xst.append(gst)
+            pos += w + int(rng.integers(50, 2500))
+        ptr.append(len(xs))
+    o_mask = dict(ptr=ptr, chrom=xc, start=xs, end=xe, strand=xst)
+    u = rb.GRanges(np.asarray(xc, np.int32), xs, xe, strand=np.asarray(xst, np.int8), seqlevels=["c0", "c1"])
+    g_mask = rb.GRangesList(u, ptr)
+    filt_code = None if filt is None else {"+": 1, "-": -1, "*": 0}[filt]
+    want = O.calc_coverage(o_reads, o_mask, filt_code, ignore)
+    got = rb.calcCoverage(g_reads, g_mask, strand=filt, ignore_strand=ignore)
+    assert_coverage_equal(got.to_list(), want)
+    # the GRanges passes that follow on the same handle
+    rc, rs, re_, rst = _regions(rng, 200, clen, [1, 90, 1000, 1024, 1025, 3000, 9000, 20011])
+    o2, g2 = both_regions(rc, rs, re_, rst, len(clen))
+    want2 = O.calc_coverage(o_reads, o2, filt_code, ignore)
+    got2 = rb.calcCoverage(g_reads, g2, strand=filt, ignore_strand=ignore)
+    assert_coverage_equal(got2.to_list(), want2)
+    m, is_null = rb.coverageProfile(g_reads, g2.subset(np.flatnonzero(np.asarray(re_) - np.asarray(rs) == 2999)), 30,
+                                    strand=filt, ignore_strand=ignore)
+    sel = [w for w, L in zip(want2, np.asarray(re_) - np.asarray(rs)) if L == 2999]
+    bp = dict(flankBinSize=0, regionBinSize=30, sumStat="mean", interpolation="auto")
+    assert_matrix_close(m, O.profile_matrix(sel, (0, 0), bp))
