@@ -517,7 +517,7 @@ def run_strong(env, args, world, rank):
     def step():
         with torch.cuda.stream(lib_stream):
             ev[0].record(lib_stream)
-            got = exchange_reads(share[0], share[1], share[2], share[3], spans)
+            got = exchange_reads(share[0], share[1], share[2], share[3], spans, filter_single=False)
             ev[1].record(lib_stream)
             prob.set_reads(list(got))
             prob.step(out_ptr=block.data_ptr(), ld=R_mine)
@@ -535,6 +535,9 @@ def run_strong(env, args, world, rank):
     phases = np.zeros(3)
     total_ms = 0.0
     n_mine = 0
+    _lib = env["_lib"]
+    _lib.check(L.rcp_timing_enable(1))
+    _lib.check(L.rcp_timing_read(1, 0, None, None))
     for _ in range(steps):
         n_mine = step()
         total_ms += ev[0].elapsed_time(ev[3])
@@ -542,6 +545,8 @@ def run_strong(env, args, world, rank):
         if world > 1:
             dist.barrier()
     ms = total_ms / steps
+    stage = stage_table(L, _lib)
+    _lib.check(L.rcp_timing_enable(0))
     checksum = float(host.sum())
     red = torch.tensor([ms, phases[0] / steps, phases[1] / steps, phases[2] / steps], dtype=torch.float64, device=dev)
     tot = torch.tensor([checksum, float(n_share), float(n_mine), float(R_mine)], dtype=torch.float64, device=dev)
@@ -554,12 +559,15 @@ def run_strong(env, args, world, rank):
                        "sharded by region over %d GPU(s)" % (n_total, len(win), w["flank"][0], world),
            "scaling": "strong", "n_gpus": world, "steps": steps,
            "ms_per_step": ms, "reads_per_s": n_total / (ms * 1e-3),
+           "ms_device_resident": float(red[1]) + float(red[2]),
+           "reads_per_s_device_resident": n_total / ((float(red[1]) + float(red[2])) * 1e-3),
            "phases_ms_max_over_ranks": {"exchange_reads (classify + NCCL all-to-all)": float(red[1]),
                                         "load + coverage + per-base matrix": float(red[2]),
                                         "matrix block D2H (own PCIe link)": float(red[3])},
            "reads_after_exchange": int(tot[2]), "regions": int(tot[3]), "matrix_cols": ncols,
            "matrix_bytes_total": int(tot[3]) * ncols * 8,
            "coverage_path_used": prob.stats.get("path"), "checksum": float(tot[0]),
+           "stage_ms_rank0": {k: v[0] * v[1] / steps for k, v in stage.items()},
            "generation_s_this_rank": round(t_gen, 1)}
     return out
 

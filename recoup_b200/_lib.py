@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librecoup_b200.so")
+LIB_PATH = os.environ.get("RCP_LIB_PATH") or os.path.join(_HERE, "librecoup_b200.so")     # RCP_LIB_PATH: A/B builds
 
 RCP_OK, RCP_ERR_CUDA, RCP_ERR_ARG, RCP_ERR_HANDLE, RCP_ERR_NOGPU, RCP_ERR_UNSUPPORTED, RCP_ERR_DATA = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1

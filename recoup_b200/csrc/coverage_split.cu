@@ -26,6 +26,8 @@
 // L2), 4 B per covered base written once.
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 
 #include <vector>
 
@@ -630,12 +632,21 @@ __global__ void __launch_bounds__(CTA)
 sp_long_collect_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
                        uint32_t max_pack_w, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ keys,
                        uint32_t* __restrict__ idx) {
-    for (int64_t i = (int64_t)blockIdx.x * CTA + threadIdx.x; i < n; i += (int64_t)gridDim.x * CTA)
-        if (e1[i] - s[i] > max_pack_w && e1[i] > s[i]) {
-            const unsigned long long k = atomicAdd(cursor, 1ull);
+    const unsigned lane = threadIdx.x & 31;
+    // warp-uniform trip count; one atomic per warp and round (the cursor is a single address)
+    for (int64_t base = (int64_t)blockIdx.x * CTA + (threadIdx.x & ~31u); base < n; base += (int64_t)gridDim.x * CTA) {
+        const int64_t i = base + lane;
+        const bool is = i < n && e1[i] - s[i] > max_pack_w && e1[i] > s[i];
+        const unsigned m = __ballot_sync(0xffffffffu, is);
+        if (m == 0u) continue;
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(cursor, (unsigned long long)__popc(m));
+        k = __shfl_sync(0xffffffffu, k, 0) + __popc(m & ((1u << lane) - 1u));
+        if (is) {
             keys[k] = s[i];
             idx[k] = (uint32_t)i;
         }
+    }
 }
 
 __global__ void __launch_bounds__(CTA)
@@ -785,8 +796,11 @@ sp_bins_finish_kernel(FusedBins fb, const int32_t* __restrict__ plen, const uint
 // anywhere.  Persistent warps; the next tile's descriptor and its first 128 candidates are in
 // flight while the current tile is scanned and stored; longer candidate lists are read 128 at a
 // time (four loads per lane in flight).
+#ifndef RCP_WTILE_OCC
+#define RCP_WTILE_OCC 4
+#endif
 template <bool STRANDED, bool FUSED>
-__global__ void __launch_bounds__(CTA, 4)
+__global__ void __launch_bounds__(CTA, RCP_WTILE_OCC)
 sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
                 int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, FusedBins fb, LongIdx lg,
                 const uint32_t* __restrict__ tabs, const uint2* __restrict__ lrange) {
@@ -1241,9 +1255,24 @@ static LongIdx long_index(const ReadsIdx& rd) {
     return lg;
 }
 
+struct DebugLap {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit DebugLap() : on(getenv("RCP_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(g_ctx.stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rcp split] %-32s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    }
+};
+
 static int reads_build_binned(ReadsIdx& rd) {
     if (rd.bn_cand) return RCP_OK;
+    DebugLap dbg;
     RCP_TRY(reads_resolve(rd));
+    dbg.lap("binned: resolve reads");
     const SplitGeom g = split_geometry(rd);
     const bool stranded = rd.d_strand != nullptr;
     const int wbits = 32 - g.P - (stranded ? 2 : 0);
@@ -1286,6 +1315,7 @@ static int reads_build_binned(ReadsIdx& rd) {
         rd.ln_n = (int64_t)n;
         dfree(idx);
         dfree(d_cnt);
+        dbg.lap("binned: long-read list");
     }
     Arena K, B, Tb;
     RCP_TRY(Tb.reserve(Arena::pad((size_t)g.words * 4)));
@@ -1300,6 +1330,7 @@ static int reads_build_binned(ReadsIdx& rd) {
     rd.bn_cb = sc.cb;
     rd.bn_P = g.P;
     rd.bn_stranded = stranded;
+    dbg.lap("binned: split + sort");
     return RCP_OK;
 }
 
@@ -1546,10 +1577,12 @@ int coverage_profile_split(ReadsIdx& rd, int64_t R, const int32_t* chrom, const 
 int coverage_list_split(ReadsIdx& rd, int64_t G, const int64_t* ptr, int64_t n_ranges, const int32_t* chrom,
                         const int32_t* start, const int32_t* end, const int8_t* strand, int ignore_strand,
                         int strand_filter, int mem, Coverage* cv) {
+    DebugLap dbg;
     {
         const int rc = reads_build_binned(rd);
         if (rc != RCP_OK) return rc;
     }
+    dbg.lap("list: binned index");
     const SplitGeom g = split_geometry(rd);
     const uint32_t max_w = std::max(1u, std::min(rd.max_width, rd.bn_max_pack_w));
     const LongIdx lg = long_index(rd);
@@ -1607,6 +1640,7 @@ int coverage_list_split(ReadsIdx& rd, int64_t G, const int64_t* ptr, int64_t n_r
                                     {err, &h.err, 4}};
         RCP_TRY(fetch_and_sync(items, 4));
     }
+    dbg.lap("list: plan + fetch");
     if (h.err & 1u) return fail(RCP_ERR_DATA, "a range has a chromosome id outside [0, n_chrom)");
     if (h.err & 2u) return fail(RCP_ERR_DATA, "a range has end < start - 1");
     if (h.err & 4u) return fail(RCP_ERR_DATA, "the ranges of one list element lie on different chromosomes");
@@ -1640,6 +1674,7 @@ int coverage_list_split(ReadsIdx& rd, int64_t G, const int64_t* ptr, int64_t n_r
                                                                     cv->d_stats);
         RCP_LAUNCHED();
     }
+    dbg.lap("list: tiles");
     return RCP_OK;
 }
 

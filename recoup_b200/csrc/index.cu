@@ -9,6 +9,7 @@
 // cut any region into tiles without carrying state between tiles (coverage.cu).
 // Replaces splitBySeqname + the per-region findOverlaps/coverage of the reference
 // (/root/reference/R/util.R:1-13, R/coverage.R:189-201).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -596,7 +597,9 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
         RCP_LAUNCHED();
     }
     ExcBuf exc;
-    exc.cap = (uint32_t)((n / 64 > 4096) ? (n / 64) : 4096);
+    // (the exception counter is ONE address: a sample whose widths vary hits it once per read
+    // until the buffer is full, so the buffer stays small)
+    exc.cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(n / 64, 4096), 65536);
     RCP_TRY(dalloc(&r.exc_xw, (size_t)exc.cap));
     RCP_TRY(dalloc(&r.exc_e1, (size_t)exc.cap));
     RCP_TRY(dalloc(&r.exc_st, (size_t)exc.cap));

@@ -56,6 +56,7 @@ struct BinArgs {
 
 constexpr int STAGE_INTS = 12288;      // ints of one region staged in shared memory (48 KB)
 constexpr int STAGE_MAX_BIN = 128;     // bins narrower than this use the staged path
+constexpr int LONG_REGION_MIN = 16384; // wide-bin segments from this length on: bin_wide_kernel
 
 // Sum of src[lo, hi) by one warp with 16-byte loads where the index is 4-aligned (src itself is
 // 128-byte aligned: region offsets are multiples of 32 ints).
@@ -240,7 +241,8 @@ constexpr int BWARPS = BT / 32;
 __global__ void __launch_bounds__(CTA)
 bin_desc_kernel(int64_t R, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
                 const uint8_t* __restrict__ is_null, int where, int f1, int f2, int n,
-                int buf_ints, BinDesc* __restrict__ desc) {
+                int buf_ints, BinDesc* __restrict__ desc, int32_t* __restrict__ long_list,
+                unsigned int* __restrict__ long_count) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
     if (r >= R) return;
     Seg sg;
@@ -260,6 +262,13 @@ bin_desc_kernel(int64_t R, const int64_t* __restrict__ off, const int32_t* __res
     if (d.bsz > 0 && d.bsz < STAGE_MAX_BIN) {
         const int nvec = (sg.b - d.lo_al + 3) >> 2;
         if (nvec * 4 <= buf_ints) d.nvec = nvec;
+    }
+    // a long region with wide bins (gene bodies run to megabases) would keep ONE CTA busy long
+    // after the others have finished: its bins go to bin_wide_kernel, one warp per bin, spread
+    // over the whole grid
+    if (d.bsz >= STAGE_MAX_BIN && Ls >= LONG_REGION_MIN) {
+        d.nvec = -1;
+        long_list[atomicAdd(long_count, 1u)] = (int32_t)r;
     }
     desc[r] = d;
 }
@@ -349,6 +358,7 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
             for (int i = tid; i < n; i += BT) out[(int64_t)i * p.ld] = 0.0;
         } else if (d.bsz == 0) {            // util.R:17: interpolation path, handled separately
             if (tid == 0) p.short_list[atomicAdd(p.short_count, 1u)] = (int32_t)r;
+        } else if (d.nvec < 0) {            // long region, wide bins: bin_wide_kernel
         } else {
             // ---- bin edges: bin i has bsz + [rank[i] <= dif] elements (util.R:74-80) ----
             const int bsz = d.bsz, dif = d.dif;
@@ -421,11 +431,56 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
                     }
                 }
             } else {
-                // ---- wide bins: one warp per bin, coalesced 16-byte global loads ----
-                for (int i = warp; i < n; i += BWARPS) {
-                    const int lo = edge(i), hi = edge(i + 1);
-                    const long long s64 = warp_range_sum(src, lo, hi);
-                    if (lane == 0) out[(int64_t)i * p.ld] = p.scale * ((double)s64 / (double)(hi - lo));
+                // ---- wide bins (>= 128 bases): every warp STREAMS a contiguous run of bins -- the
+                // bins of a region are one contiguous stretch of coverage -- with 16-byte loads,
+                // four 512-byte rows in flight per warp.  A row (128 bases) meets at most one
+                // bin edge: the lanes keep a running partial sum for the current bin and one for
+                // the bin after the edge, and the warp reduces once per BIN, not per row.
+                const int per = (n + BWARPS - 1) / BWARPS;
+                const int i0 = warp * per, i1 = min(n, i0 + per);
+                if (i0 < i1) {
+                    const int lo = edge(i0), hi = edge(i1);
+                    int k = i0, nxt = edge(i0 + 1);
+                    long long acc = 0;
+                    constexpr int UW = 4;
+                    for (int q0 = lo & ~3; q0 < hi; q0 += 128 * UW) {
+                        int4 x[UW];
+#pragma unroll
+                        for (int u = 0; u < UW; u++) {
+                            const int q = q0 + u * 128 + lane * 4;
+                            x[u] = make_int4(0, 0, 0, 0);
+                            if (q < hi) x[u] = __ldcs(reinterpret_cast<const int4*>(src + q));
+                        }
+#pragma unroll
+                        for (int u = 0; u < UW; u++) {
+                            const int row = q0 + u * 128;
+                            if (row >= hi) break;
+                            const int q = row + lane * 4;
+                            int a0 = x[u].x, a1 = x[u].y, a2 = x[u].z, a3 = x[u].w;
+                            if (row < lo || row + 128 > hi) {           // first / last row of the run
+                                a0 = (q >= lo && q < hi) ? a0 : 0;
+                                a1 = (q + 1 >= lo && q + 1 < hi) ? a1 : 0;
+                                a2 = (q + 2 >= lo && q + 2 < hi) ? a2 : 0;
+                                a3 = (q + 3 >= lo && q + 3 < hi) ? a3 : 0;
+                            }
+                            const long long tot = ((long long)a0 + a1) + ((long long)a2 + a3);
+                            if (row + 128 >= nxt) {                     // this row ends the current bin
+                                const int c = nxt - q;                  // this lane's elements before the edge
+                                const long long before = (long long)(c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) +
+                                                         (c > 2 ? a2 : 0) + (c > 3 ? a3 : 0);
+                                long long t = acc + before;
+#pragma unroll
+                                for (int dd = 16; dd > 0; dd >>= 1) t += __shfl_xor_sync(0xffffffffu, t, dd);
+                                const int b0 = edge(k);
+                                if (lane == 0) out[(int64_t)k * p.ld] = p.scale * ((double)t / (double)(nxt - b0));
+                                acc = tot - before;
+                                k++;
+                                nxt = k < i1 ? edge(k + 1) : 0x7fffffff;
+                            } else {
+                                acc += tot;
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -434,6 +489,83 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
         __syncthreads();                    // edges, wcount, the ring slot and the buffer are reused
     }
     // the copy issued for the (non-existent) region after the last one carries no bytes
+}
+
+// ---- long regions with wide bins: runs of WIDE_RUN bins of all such regions in one pool --------
+// One warp STREAMS a run of consecutive bins -- one contiguous stretch of coverage -- with
+// 16-byte loads, four 512-byte rows in flight.  A row (128 bases) meets at most one bin edge
+// (bins are >= 128 wide): the lanes keep a partial sum for the current bin, the warp reduces
+// once per bin.  Bin i has bsz + [rank[i] <= dif] elements (util.R:74-80).
+constexpr int WIDE_RUN = 16;
+
+__global__ void __launch_bounds__(BT)
+bin_wide_kernel(BinArgs p, const BinDesc* __restrict__ desc, const int32_t* __restrict__ long_list,
+                const unsigned int* __restrict__ long_count) {
+    const int lane = threadIdx.x & 31;
+    const int n = p.n;
+    const int runs = (n + WIDE_RUN - 1) / WIDE_RUN;
+    const int64_t units = (int64_t)(*long_count) * runs;
+    const int64_t wstep = (int64_t)gridDim.x * BWARPS;
+    for (int64_t u = (int64_t)blockIdx.x * BWARPS + (threadIdx.x >> 5); u < units; u += wstep) {
+        const int64_t r = long_list[u / runs];
+        const int i0 = (int)(u % runs) * WIDE_RUN, i1 = min(n, i0 + WIDE_RUN);
+        const BinDesc d = load_bin_desc(desc + r);
+        const int bsz = d.bsz, dif = d.dif;
+        // lane l knows whether bin i0 + l is one base wider; the start of bin i0 needs the count before it
+        int pre = 0;
+        unsigned extra = 0;
+        if (dif > 0) {
+            for (int j = lane; j < i0; j += 32) pre += (__ldg(p.rank + j) <= dif);
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, dd);
+            extra = __ballot_sync(0xffffffffu, i0 + lane < i1 && __ldg(p.rank + i0 + lane) <= dif);
+        }
+        const int lo = d.a + i0 * bsz + pre;
+        const int hi = lo + (i1 - i0) * bsz + __popc(extra);
+        const int32_t* src = p.cov + (int64_t)(((uint64_t)(uint32_t)d.off_hi << 32) | (uint32_t)d.off_lo);
+        double* out = p.out + r;
+        int k = i0, b0 = lo, nxt = lo + bsz + (int)(extra & 1u);
+        long long acc = 0;
+        constexpr int UW = 4;
+        for (int q0 = lo & ~3; q0 < hi; q0 += 128 * UW) {
+            int4 x[UW];
+#pragma unroll
+            for (int v = 0; v < UW; v++) {
+                const int q = q0 + v * 128 + lane * 4;
+                x[v] = make_int4(0, 0, 0, 0);
+                if (q < hi) x[v] = __ldcs(reinterpret_cast<const int4*>(src + q));
+            }
+#pragma unroll
+            for (int v = 0; v < UW; v++) {
+                const int row = q0 + v * 128;
+                if (row >= hi) break;
+                const int q = row + lane * 4;
+                int a0 = x[v].x, a1 = x[v].y, a2 = x[v].z, a3 = x[v].w;
+                if (row < lo || row + 128 > hi) {           // first / last row of the run
+                    a0 = (q >= lo && q < hi) ? a0 : 0;
+                    a1 = (q + 1 >= lo && q + 1 < hi) ? a1 : 0;
+                    a2 = (q + 2 >= lo && q + 2 < hi) ? a2 : 0;
+                    a3 = (q + 3 >= lo && q + 3 < hi) ? a3 : 0;
+                }
+                const long long tot = ((long long)a0 + a1) + ((long long)a2 + a3);
+                if (row + 128 >= nxt) {                     // this row ends the current bin
+                    const int c = nxt - q;                  // this lane's elements before the edge
+                    const long long before = (long long)(c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) +
+                                             (c > 2 ? a2 : 0) + (c > 3 ? a3 : 0);
+                    long long t = acc + before;
+#pragma unroll
+                    for (int dd = 16; dd > 0; dd >>= 1) t += __shfl_xor_sync(0xffffffffu, t, dd);
+                    if (lane == 0) out[(int64_t)k * p.ld] = p.scale * ((double)t / (double)(nxt - b0));
+                    acc = tot - before;
+                    k++;
+                    b0 = nxt;
+                    nxt = k < i1 ? nxt + bsz + (int)((extra >> (k - i0)) & 1u) : 0x7fffffff;
+                } else {
+                    acc += tot;
+                }
+            }
+        }
+    }
 }
 
 // ---- interpolation of short segments (util.R:17-73) ------------------------------------------
@@ -746,6 +878,8 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
     const size_t edge_bytes = (((size_t)n_bins + 1 + 3) & ~(size_t)3) * sizeof(int);
     if (edge_bytes > 150 * 1024) return fail(RCP_ERR_UNSUPPORTED, "more than ~38000 bins per segment");
     BinDesc* d_desc = nullptr;
+    int32_t* long_list = nullptr;
+    unsigned int* long_count = nullptr;
     if (stat == RCP_STAT_MEDIAN) {
         StageTimer t(ST_PROF_BIN);
         const size_t smem = edge_bytes;
@@ -780,8 +914,11 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
                 buf_ints = std::min(buf_ints, 6144);
             }
         }
+        RCP_TRY(dalloc(&long_list, (size_t)R));
+        RCP_TRY(dalloc(&long_count, 1));
+        RCP_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned int), g_ctx.stream));
         bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
-            R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc);
+            R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc, long_list, long_count);
         RCP_LAUNCHED();
         // CTAs per SM and buffers per CTA: as much shared memory as possible in flight
         int nbuf = 2;
@@ -797,6 +934,9 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         if (fit < 1) return fail(RCP_ERR_UNSUPPORTED, "bin kernel does not fit (%zu bytes of shared memory)", smem);
         const int64_t grid = std::min<int64_t>(R, (int64_t)g_ctx.sm_count * std::min(fit, per_sm));
         bin_mean_kernel<<<(unsigned)grid, BT, smem, g_ctx.stream>>>(a, d_desc, R, buf_ints, nbuf);
+        RCP_LAUNCHED();
+        // (nothing to do when no region is long: the warps find zero units)
+        bin_wide_kernel<<<(unsigned)(g_ctx.sm_count * 8), BT, 0, g_ctx.stream>>>(a, d_desc, long_list, long_count);
         RCP_LAUNCHED();
     }
     InterpArgs ia;
@@ -829,6 +969,8 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
         RCP_LAUNCHED();
     }
     dfree(d_desc);
+    dfree(long_list);
+    dfree(long_count);
     dfree(d_rank);
     dfree(short_list);
     dfree(short_count);

@@ -68,18 +68,22 @@ def slice_spans(reg_chrom, reg_start, reg_end, parts, n_chrom, pad=0):
     return out
 
 
-def exchange_reads(chrom, start, end, strand, spans, group=None):
+def exchange_reads(chrom, start, end, strand, spans, group=None, filter_single=True):
     """The data-path exchange of the region-sharded run: every rank holds an arbitrary share of
     the reads (torch tensors on its device: chrom / start / end int32, strand int8 or None) and
     receives the reads that can overlap ITS region slice -- per chromosome, those meeting
     [lo, hi] of `spans` (slice_spans).  A read at a slice boundary goes to both neighbours.  One
     all_to_all_single for the counts, one for the packed (chrom, start, end) triples, one for the
-    strands.  world == 1 (or no process group): a local filter.  Returns the four tensors."""
+    strands.  world == 1 (or no process group): a local filter against spans[0] (skipped with
+    filter_single=False: the coverage call drops the reads its mask does not touch anyway).
+    Returns the four tensors."""
     import torch
     import torch.distributed as dist
 
     on = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if on else 1
+    if world == 1 and len(spans) == 1 and not filter_single:
+        return chrom, start, end, strand       # one rank owns every region: nothing to send or drop
     dev = chrom.device
     sp = torch.as_tensor(np.ascontiguousarray(spans), device=dev)        # [world, n_chrom, 2]
     c64 = chrom.long()
