@@ -618,29 +618,41 @@ struct LongIdx {
     const uint32_t* maxe1;   // running max of e1
 };
 
+// CTA c owns the reads [c * per, (c + 1) * per): it counts its long reads, and (after an exclusive
+// prefix over the CTAs) writes them from its own base -- no global atomic, deterministic order.
 __global__ void __launch_bounds__(CTA)
-sp_long_count_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1, uint32_t max_pack_w,
-                     unsigned long long* __restrict__ count) {
+sp_long_count_kernel(int64_t n, int64_t per, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
+                     uint32_t max_pack_w, uint32_t* __restrict__ per_cta) {
+    __shared__ unsigned wsum[WARPS];
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
     unsigned c = 0;
-    for (int64_t i = (int64_t)blockIdx.x * CTA + threadIdx.x; i < n; i += (int64_t)gridDim.x * CTA)
-        c += (e1[i] - s[i] > max_pack_w) && (e1[i] > s[i]);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += CTA) c += (e1[i] - s[i] > max_pack_w) && (e1[i] > s[i]);
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < WARPS; w++) t += wsum[w];
+        per_cta[blockIdx.x] = t;
+    }
 }
 
 __global__ void __launch_bounds__(CTA)
-sp_long_collect_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
-                       uint32_t max_pack_w, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ keys,
+sp_long_collect_kernel(int64_t n, int64_t per, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
+                       uint32_t max_pack_w, const uint32_t* __restrict__ base, uint32_t* __restrict__ keys,
                        uint32_t* __restrict__ idx) {
+    __shared__ unsigned cursor;
+    if (threadIdx.x == 0) cursor = base[blockIdx.x];
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    // warp-uniform trip count; one atomic per warp and round (the cursor is a single address)
-    for (int64_t base = (int64_t)blockIdx.x * CTA + (threadIdx.x & ~31u); base < n; base += (int64_t)gridDim.x * CTA) {
-        const int64_t i = base + lane;
-        const bool is = i < n && e1[i] - s[i] > max_pack_w && e1[i] > s[i];
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t b0 = lo + (threadIdx.x & ~31u); b0 < hi; b0 += CTA) {        // warp-uniform trip count
+        const int64_t i = b0 + lane;
+        const bool is = i < hi && e1[i] - s[i] > max_pack_w && e1[i] > s[i];
         const unsigned m = __ballot_sync(0xffffffffu, is);
         if (m == 0u) continue;
-        unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(cursor, (unsigned long long)__popc(m));
+        unsigned k = 0;
+        if (lane == 0) k = atomicAdd(&cursor, (unsigned)__popc(m));        // shared memory
         k = __shfl_sync(0xffffffffu, k, 0) + __popc(m & ((1u << lane) - 1u));
         if (is) {
             keys[k] = s[i];
@@ -917,6 +929,7 @@ sp_list_plan_kernel(int64_t G, ListPlan lp, const int32_t* __restrict__ chrom, c
     if (g < G) {
         const int64_t a = lp.ptr[g], b = lp.ptr[g + 1];
         bool null = (b <= a);
+        bool simple = true;
         int64_t L = 0;
         int st0 = 0;
         uint32_t lo = 0xffffffffu, hi = 0;
@@ -929,8 +942,13 @@ sp_list_plan_kernel(int64_t G, ListPlan lp, const int32_t* __restrict__ chrom, c
             } else {
                 const int64_t clen = chrom_len[c];
                 const uint32_t coff = chrom_off[c];
+                int64_t prev_end = -1;
                 for (int64_t i = a; i < b; i++) {
                     int64_t s = start[i], e = end[i];
+                    // ascending, disjoint, non-empty ranges of one strand: the multiplicity of a read
+                    // follows from its neighbours in the list alone (sp_ltile_kernel)
+                    if (s <= prev_end || e < s || (lp.rstrand && lp.rstrand[i] != lp.rstrand[a])) simple = false;
+                    prev_end = e;
                     if (chrom[i] != c) atomicOr(err, 4u);
                     if (e < s - 1) { atomicOr(err, 2u); null = true; }
                     if (s < 0 || e > clen) null = true;      // coverage.R:206 inside the tryCatch
@@ -953,7 +971,7 @@ sp_list_plan_kernel(int64_t G, ListPlan lp, const int32_t* __restrict__ chrom, c
         const int32_t len = null ? 0 : (int32_t)L;
         lp.lrange[g] = (lg.n && !null) ? sp_long_range(lg, lo, hi) : make_uint2(0u, 0u);
         plen[g] = len;
-        flags[g] = (uint8_t)(st0 < 0 ? 1u : 0u);
+        flags[g] = (uint8_t)((st0 < 0 ? 1u : 0u) | (simple ? 2u : 0u));
         ntile[g] = len > WT_ONE ? ((int64_t)len + WT - 1) / WT : (len > 0 ? 1 : 0);
         padded[g] = ((int64_t)len + PAD - 1) / PAD * PAD;
         my_len = (unsigned long long)len;
@@ -967,6 +985,30 @@ sp_list_plan_kernel(int64_t G, ListPlan lp, const int32_t* __restrict__ chrom, c
         atomicAdd(&pstats[0], my_len);
         atomicMax(&pstats[1], my_max);
     }
+}
+
+// Number of ranges of the element [a, b) the read [rs, re1) hits under the strand rules
+// (coverage.R:190-192).  `simple` elements (ascending, disjoint, one strand): the read is known to
+// overlap range q, the other hits are q's neighbours.  Otherwise every range is tested.
+__device__ __forceinline__ int sp_multiplicity(const ListPlan& lp, int64_t a, int64_t b, int64_t q, bool simple,
+                                               uint32_t rs, uint32_t re1, int rst, int ignore_strand,
+                                               int strand_filter) {
+    if (simple) {
+        if (!strand_ok(rst, lp.rstrand ? (int)__ldg(lp.rstrand + a) : 0, ignore_strand, strand_filter)) return 0;
+        int mult = 1;
+        for (int64_t z = q + 1; z < b && __ldg(lp.xgs + z) < re1; z++) mult++;
+        for (int64_t z = q - 1; z >= a && __ldg(lp.xge + z) >= rs; z--) mult++;
+        return mult;
+    }
+    int mult = 0;
+    for (int64_t z = a; z < b; z++) {
+        const uint32_t zs = __ldg(lp.xgs + z), ze = __ldg(lp.xge + z);
+        if (ze + 1u == zs) continue;
+        if (rs <= ze && re1 > zs &&
+            strand_ok(rst, lp.rstrand ? (int)__ldg(lp.rstrand + z) : 0, ignore_strand, strand_filter))
+            mult++;
+    }
+    return mult;
 }
 
 // tiles of the stitched vectors: `cts` holds the tile's first STITCHED position
@@ -1012,7 +1054,7 @@ sp_ltile_kernel(int64_t T, const SpDesc* __restrict__ desc, ListPlan lp, const u
         const SpDesc d = sp_load_desc(desc + t);
         const int64_t a = lp.ptr[d.region], b = lp.ptr[d.region + 1];
         const int tlen = d.tlen, t0 = (int)d.cts, t1 = t0 + tlen;
-        const bool rev = d.flags & 1u;
+        const bool rev = d.flags & 1u, simple = (d.flags & 2u) != 0;
         const int rows = (tlen + ROW - 1) / ROW;
         for (int k = 0; k < rows; k++) reinterpret_cast<int4*>(diff)[k * 32 + lane] = make_int4(0, 0, 0, 0);
         __syncwarp();
@@ -1048,14 +1090,7 @@ sp_ltile_kernel(int64_t T, const SpDesc* __restrict__ desc, ListPlan lp, const u
                     rst = cls == 0u ? 1 : (cls == 1u ? -1 : 0);
                 }
                 if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
-                int mult = 0;
-                for (int64_t z = a; z < b; z++) {
-                    const uint32_t zs = __ldg(lp.xgs + z), ze = __ldg(lp.xge + z);
-                    if (ze + 1u == zs) continue;
-                    if (rs <= ze && re1 > zs &&
-                        strand_ok(rst, lp.rstrand ? (int)__ldg(lp.rstrand + z) : 0, ignore_strand, strand_filter))
-                        mult++;
-                }
+                const int mult = sp_multiplicity(lp, a, b, q, simple, rs, re1, rst, ignore_strand, strand_filter);
                 if (mult == 0) continue;
                 hit = true;
                 // +mult on the covered part of the piece, in output order
@@ -1161,6 +1196,19 @@ sp_null_kernel(int64_t R, const int32_t* __restrict__ plen, const uint8_t* __res
 // Same contract as coverage_ranges_bucketed.  RCP_SPLIT_NOT_APPLICABLE: the reads are too wide for
 // the packed candidate word of this genome (or the genome too long for the shared-memory table);
 // nothing has been produced and the caller uses another path.
+struct DebugLap {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit DebugLap() : on(getenv("RCP_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(g_ctx.stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rcp split] %-32s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    }
+};
+
 struct SortedCands {
     uint32_t* cand = nullptr;     // packed candidate words, sorted by 1-kb sub-bin
     uint32_t* boff = nullptr;     // n_groups * nb + 1 sub-bin offsets into cand
@@ -1191,6 +1239,8 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, i
     uint32_t* list = B.take<uint32_t>(pool_cap);
     uint32_t* col = B.take<uint32_t>((size_t)sort_grid * NG);
     if (B.used > B.cap || K.used > K.cap) return fail(RCP_ERR_CUDA, "internal: split arena overrun");
+    DebugLap dbg;
+    dbg.lap("  split_and_sort: arenas");
     {
         StageTimer t(ST_SP_SPLIT);
         RCP_CUDA(cudaMemsetAsync(B.base, 0, zero_b, g_ctx.stream));
@@ -1208,6 +1258,7 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, i
         }
         RCP_LAUNCHED();
     }
+    dbg.lap("  split_and_sort: split kernel");
     {
         StageTimer t(ST_SP_SORT);
         sp_chunk_hist_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col);
@@ -1216,11 +1267,13 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, i
         RCP_LAUNCHED();
         sp_chunk_place_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col, list);
         RCP_LAUNCHED();
+        dbg.lap("  split_and_sort: chunk lists");
         RCP_CUDA(cudaFuncSetAttribute(sp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM));
         sp_group_kernel<<<n_groups, GT, GSMEM, g_ctx.stream>>>(pool, list, sc->cb, n_groups, nb, pmask, sc->cand,
                                                                sc->boff);
         RCP_LAUNCHED();
     }
+    dbg.lap("  split_and_sort: group sort");
     return RCP_OK;
 }
 
@@ -1255,19 +1308,6 @@ static LongIdx long_index(const ReadsIdx& rd) {
     return lg;
 }
 
-struct DebugLap {
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    explicit DebugLap() : on(getenv("RCP_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
-    void lap(const char* what) {
-        if (!on) return;
-        cudaStreamSynchronize(g_ctx.stream);
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[rcp split] %-32s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
-        t0 = now;
-    }
-};
-
 static int reads_build_binned(ReadsIdx& rd) {
     if (rd.bn_cand) return RCP_OK;
     DebugLap dbg;
@@ -1281,17 +1321,19 @@ static int reads_build_binned(ReadsIdx& rd) {
     const uint32_t max_pack_w = std::min<uint32_t>((1u << wbits) - 1u, 8191u);
     rd.bn_max_pack_w = max_pack_w;
     if (rd.max_width > max_pack_w) {
-        unsigned long long* d_cnt = nullptr;
-        RCP_TRY(dalloc(&d_cnt, 2));
-        RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 16, g_ctx.stream));
-        const unsigned grid = (unsigned)std::min<int64_t>(blocks_for(rd.n, CTA), (int64_t)g_ctx.sm_count * 8);
-        sp_long_count_kernel<<<grid, CTA, 0, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, max_pack_w, d_cnt);
+        const int n_cta = g_ctx.sm_count * 8;
+        const int64_t per = (rd.n + n_cta - 1) / n_cta;
+        uint32_t* d_cnt = nullptr;          // per-CTA counts, then their exclusive prefix (+ the total)
+        RCP_TRY(dalloc(&d_cnt, (size_t)n_cta + 1));
+        sp_long_count_kernel<<<n_cta, CTA, 0, g_ctx.stream>>>(rd.n, per, rd.g_start, rd.g_end1, max_pack_w, d_cnt);
         RCP_LAUNCHED();
-        unsigned long long h_cnt = 0;
-        const FetchItem it[1] = {{d_cnt, &h_cnt, 8}};
+        RCP_TRY(exclusive_scan_u32(d_cnt, d_cnt, n_cta, d_cnt + n_cta));
+        uint32_t h_cnt = 0;
+        const FetchItem it[1] = {{d_cnt + n_cta, &h_cnt, 4}};
         RCP_TRY(fetch_and_sync(it, 1));
+        dbg.lap("  long: count");
         // a sample made of long reads is not what this index is for
-        if (h_cnt > (unsigned long long)rd.n / 8 || h_cnt >= 0x7fffffffull) {
+        if ((int64_t)h_cnt > rd.n / 8) {
             dfree(d_cnt);
             return RCP_SPLIT_NOT_APPLICABLE;
         }
@@ -1302,10 +1344,12 @@ static int reads_build_binned(ReadsIdx& rd) {
         RCP_TRY(dalloc(&rd.ln_maxe1, n));
         if (rd.d_strand) RCP_TRY(dalloc(&rd.ln_st, n));
         RCP_TRY(dalloc(&idx, n));
-        sp_long_collect_kernel<<<grid, CTA, 0, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, max_pack_w, d_cnt + 1,
-                                                               rd.ln_xs, idx);
+        sp_long_collect_kernel<<<n_cta, CTA, 0, g_ctx.stream>>>(rd.n, per, rd.g_start, rd.g_end1, max_pack_w, d_cnt,
+                                                                rd.ln_xs, idx);
         RCP_LAUNCHED();
+        dbg.lap("  long: collect");
         RCP_TRY(sort_pairs_u32(rd.ln_xs, idx, (int64_t)n, rd.key_bits));
+        dbg.lap("  long: sort");
         if (n > 0) {
             sp_long_gather_kernel<<<blocks_for((int64_t)n, CTA), CTA, 0, g_ctx.stream>>>((uint32_t)n, idx, rd.g_end1,
                                                                                         rd.d_strand, rd.ln_e1, rd.ln_st);

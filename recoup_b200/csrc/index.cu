@@ -66,6 +66,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        ExcBuf exc) {
     unsigned int my_err = 0;
     unsigned int np = 0, nm = 0, ns = 0, wmax = 0;
+    bool exc_full = false;
     // candidate common width: the fragment length, else the width of read 0
     uint32_t w = (uint32_t)frag_len;
     if (frag_len <= 0) {
@@ -84,12 +85,17 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
             wmax = max(wmax, *ge1 - *gs);
             // reads of another width: recorded until the buffer overflows (then uniform-width
             // mode is abandoned anyway and the single counter must not become a hot spot)
-            if (*ge1 - *gs != w && *reinterpret_cast<volatile unsigned int*>(exc.count) <= exc.cap) {
-                const unsigned int k = atomicAdd(exc.count, 1u);
-                if (k < exc.cap) {
-                    exc.xw[k] = *gs + w;
-                    exc.e1[k] = *ge1;
-                    exc.st[k] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
+            if (*ge1 - *gs != w && !exc_full) {
+                // (one look at the counter per thread once it is full: it is a single address)
+                if (*reinterpret_cast<volatile unsigned int*>(exc.count) > exc.cap) {
+                    exc_full = true;
+                } else {
+                    const unsigned int k = atomicAdd(exc.count, 1u);
+                    if (k < exc.cap) {
+                        exc.xw[k] = *gs + w;
+                        exc.e1[k] = *ge1;
+                        exc.st[k] = (int8_t)(st > 0 ? 1 : (st < 0 ? -1 : 0));
+                    }
                 }
             }
         }
