@@ -160,39 +160,54 @@ __global__ void fetch_pack_kernel(FetchArgs a, uint32_t* __restrict__ out) {
     for (int i = 0; i < a.n; i++)
         for (int k = 0; k < a.words[i]; k++) out[at++] = a.src[i][k];
 }
-uint32_t* g_fetch_dev = nullptr;
 uint32_t* g_fetch_host = nullptr;       // page-locked
 }  // namespace
 
-int fetch_and_sync(const FetchItem* items, int n) {
-    if (n < 0 || n > 8) return fail(RCP_ERR_ARG, "internal: fetch_and_sync of %d items", n);
-    if (g_fetch_dev == nullptr) {
-        RCP_CUDA(cudaMalloc((void**)&g_fetch_dev, 8 * 32));
-        RCP_CUDA(cudaHostAlloc((void**)&g_fetch_host, 8 * 32, cudaHostAllocDefault));
+// fetch_begin queues the packing kernel (it writes straight into mapped page-locked host memory)
+// and records an event; fetch_end waits for that event only, so kernels queued in between keep
+// the GPU busy while the host wakes up and plans the next launches.
+namespace {
+FetchArgs g_fetch_args;
+cudaEvent_t g_fetch_event = nullptr;
+uint32_t* g_fetch_host_dev = nullptr;   // device-side address of g_fetch_host
+}  // namespace
+
+int fetch_begin(const FetchItem* items, int n) {
+    if (n < 0 || n > 8) return fail(RCP_ERR_ARG, "internal: fetch of %d items", n);
+    if (g_fetch_host == nullptr) {
+        RCP_CUDA(cudaHostAlloc((void**)&g_fetch_host, 8 * 32, cudaHostAllocMapped));
+        RCP_CUDA(cudaHostGetDevicePointer((void**)&g_fetch_host_dev, g_fetch_host, 0));
+        RCP_CUDA(cudaEventCreateWithFlags(&g_fetch_event, cudaEventDisableTiming));
     }
-    FetchArgs a;
+    FetchArgs& a = g_fetch_args;
     a.n = n;
-    int words = 0;
     for (int i = 0; i < n; i++) {
         if (items[i].bytes <= 0 || items[i].bytes > 32 || (items[i].bytes & 3))
-            return fail(RCP_ERR_ARG, "internal: fetch_and_sync item of %d bytes", items[i].bytes);
+            return fail(RCP_ERR_ARG, "internal: fetch item of %d bytes", items[i].bytes);
         a.src[i] = static_cast<const uint32_t*>(items[i].dev);
         a.words[i] = items[i].bytes / 4;
-        words += a.words[i];
     }
     if (n > 0) {
-        fetch_pack_kernel<<<1, 1, 0, g_ctx.stream>>>(a, g_fetch_dev);
+        fetch_pack_kernel<<<1, 1, 0, g_ctx.stream>>>(a, g_fetch_host_dev);
         RCP_LAUNCHED();
-        RCP_CUDA(cudaMemcpyAsync(g_fetch_host, g_fetch_dev, (size_t)words * 4, cudaMemcpyDeviceToHost,
-                                 g_ctx.stream));
     }
-    RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    RCP_CUDA(cudaEventRecord(g_fetch_event, g_ctx.stream));
+    return RCP_OK;
+}
+
+int fetch_end(const FetchItem* items, int n) {
+    RCP_CUDA(cudaEventSynchronize(g_fetch_event));
     int at = 0;
     for (int i = 0; i < n; i++) {
         memcpy(items[i].host, g_fetch_host + at, (size_t)items[i].bytes);
-        at += a.words[i];
+        at += g_fetch_args.words[i];
     }
     return RCP_OK;
+}
+
+int fetch_and_sync(const FetchItem* items, int n) {
+    RCP_TRY(fetch_begin(items, n));
+    return fetch_end(items, n);     // the event is the last thing in the stream: the stream has drained
 }
 
 int require_ready() {
@@ -438,9 +453,10 @@ int rcp_shutdown(void) {
     for (cudaEvent_t e : g_free_events) cudaEventDestroy(e);
     g_free_events.clear();
     cudaStreamSynchronize(g_ctx.stream);
-    if (g_fetch_dev) cudaFree(g_fetch_dev);
     if (g_fetch_host) cudaFreeHost(g_fetch_host);
-    g_fetch_dev = g_fetch_host = nullptr;
+    if (g_fetch_event) cudaEventDestroy(g_fetch_event);
+    g_fetch_host = g_fetch_host_dev = nullptr;
+    g_fetch_event = nullptr;
     cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
     return RCP_OK;

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <cstdio>
 
+#include <type_traits>
 #include <vector>
 
 #include "cov_common.cuh"
@@ -42,18 +43,26 @@ using namespace covk;
 namespace {
 
 constexpr int BLK_SHIFT = 14;                         // 16384-bp blocks of the bitmap
-constexpr int SUB_SHIFT = 10;                         // 1024-bp sub-bins of the candidate sort
+#ifndef RCP_SUB_SHIFT
+#define RCP_SUB_SHIFT 10
+#endif
+constexpr int SUB_SHIFT = RCP_SUB_SHIFT;              // sub-bins of the candidate sort (2^SUB_SHIFT bp)
 constexpr int NG = 1024;                              // groups (at most)
 constexpr int RING = 32;                              // ring entries per group (power of two)
 constexpr int CH = 16;                                // entries per chunk (64 bytes)
-constexpr int ST = 1024;                              // threads of the split kernel (== NG)
+#ifndef RCP_SPLIT_ST
+#define RCP_SPLIT_ST 1024
+#endif
+constexpr int ST = RCP_SPLIT_ST;                      // threads of the split kernel
+constexpr int ROUND_VEC = 2048;                       // 16-byte vectors (of 4 reads) per CTA round
+constexpr int VPT = ROUND_VEC / ST;                   // vectors per thread and round
 constexpr int SLAB = 64;                              // chunks a warp takes from the pool at a time
 constexpr int MIN_P = 16, MAX_P = 22;                 // position bits of a candidate word
 constexpr int GT = 1024;                              // threads of the group kernel
 constexpr int CS = 1024;                              // threads of the chunk-sort kernels
 constexpr int WT = 7 * ROW;                           // outputs of a warp tile (896); regions <= 1024 bp are ONE tile
 constexpr int WT_ONE = SMALL_MAX;
-static_assert(ST == NG, "the flush phase maps thread t to group t");
+static_assert(NG % ST == 0 && ROUND_VEC % ST == 0, "the flush phase maps thread t to the groups t, t + ST, ...");
 static_assert(RING == 2 * CH, "a ring holds two chunks");
 static_assert(SLAB >= 64, "one flush phase of a warp needs up to 64 chunks");
 
@@ -260,7 +269,7 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
     const uint32_t cnt_a = ring_a + NG * RING * 4;                            // NG: ring start << 16 | fill
     const uint32_t tab_a = cnt_a + NG * 4;                                    // block table
     for (int i = tid; i < words; i += ST) sts32(tab_a + i * 4, tab_g[i]);
-    sts32(cnt_a + tid * 4, 0u);
+    for (int i = tid; i < NG; i += ST) sts32(cnt_a + i * 4, 0u);
     __syncthreads();
     const uint32_t pmask = (1u << P) - 1u;
     const int wsh = STRANDED ? P + 2 : P;
@@ -293,31 +302,35 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
     };
     auto chunk_at = [&](uint32_t i) { return i < a_rem ? a_old + i : a_new + (i - a_rem); };
 
-    // thread t owns group t here: every complete chunk of its ring leaves as one 64-byte store
+    // thread t owns the groups t, t + ST, ... here: every complete chunk of a ring leaves as one
+    // 64-byte store
     auto flush_phase = [&](bool final_pass) {
-        const uint32_t w = lds32(cnt_a + tid * 4);
-        const uint32_t raw = w & 0xffffu, start = w >> 16;
-        const uint32_t nn = min(raw, (uint32_t)RING);
-        const uint32_t k = final_pass ? (nn > 0u ? 1u : 0u) : nn / CH;
-        const unsigned m1 = __ballot_sync(0xffffffffu, k >= 1u), m2 = __ballot_sync(0xffffffffu, k >= 2u);
-        const uint32_t total = __popc(m1) + __popc(m2);
-        if (total) {                                // warp-uniform
-            const uint32_t idx = __popc(m1 & lt) + __popc(m2 & lt);
-            alloc(total);
-            for (uint32_t j = 0; j < k; j++) {
-                const uint32_t c = chunk_at(idx + j);
-                const uint32_t src = ring_a + (uint32_t)tid * RING * 4 + (((start + CH * j) & (RING - 1)) << 2);
-                uint4* dst = reinterpret_cast<uint4*>(out.pool + (size_t)c * CH);
-                const uint4 a = lds128(src), b = lds128(src + 16), cc = lds128(src + 32), d = lds128(src + 48);
-                __stcs(dst, a);
-                __stcs(dst + 1, b);
-                __stcs(dst + 2, cc);
-                __stcs(dst + 3, d);
-                out.meta[c] = (uint16_t)(((uint32_t)tid << 5) | (final_pass ? nn : (uint32_t)CH));
+#pragma unroll 1
+        for (int grp = tid; grp < NG; grp += ST) {
+            const uint32_t w = lds32(cnt_a + grp * 4);
+            const uint32_t raw = w & 0xffffu, start = w >> 16;
+            const uint32_t nn = min(raw, (uint32_t)RING);
+            const uint32_t k = final_pass ? (nn > 0u ? 1u : 0u) : nn / CH;
+            const unsigned m1 = __ballot_sync(0xffffffffu, k >= 1u), m2 = __ballot_sync(0xffffffffu, k >= 2u);
+            const uint32_t total = __popc(m1) + __popc(m2);
+            if (total) {                                // warp-uniform
+                const uint32_t idx = __popc(m1 & lt) + __popc(m2 & lt);
+                alloc(total);
+                for (uint32_t j = 0; j < k; j++) {
+                    const uint32_t c = chunk_at(idx + j);
+                    const uint32_t src = ring_a + (uint32_t)grp * RING * 4 + (((start + CH * j) & (RING - 1)) << 2);
+                    uint4* dst = reinterpret_cast<uint4*>(out.pool + (size_t)c * CH);
+                    const uint4 a = lds128(src), b = lds128(src + 16), cc = lds128(src + 32), d = lds128(src + 48);
+                    __stcs(dst, a);
+                    __stcs(dst + 1, b);
+                    __stcs(dst + 2, cc);
+                    __stcs(dst + 3, d);
+                    out.meta[c] = (uint16_t)(((uint32_t)grp << 5) | (final_pass ? nn : (uint32_t)CH));
+                }
             }
+            if (k || raw > (uint32_t)RING)
+                sts32(cnt_a + grp * 4, final_pass ? 0u : ((((start + CH * k) & (RING - 1)) << 16) | (nn - CH * k)));
         }
-        if (k || raw > (uint32_t)RING)
-            sts32(cnt_a + tid * 4, final_pass ? 0u : ((((start + CH * k) & (RING - 1)) << 16) | (nn - CH * k)));
     };
 
     // is any block the read touches in the mask?  (crossing reads look at the "next block" bit)
@@ -359,72 +372,87 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
         return want;
     };
 
-    constexpr int RPT = 8;                          // reads per thread and round (two 16-byte loads per array)
-    auto do_round = [&](const uint32_t* sv, const uint32_t* ev, const int* tv) {
-        uint32_t gk[RPT], pk[RPT], pend = 0;
-#pragma unroll
-        for (int k = 0; k < RPT; k++) {
-            gk[k] = sv[k] >> P;
-            pk[k] = pack(sv[k], ev[k], tv[k]);
-            if (keep_read(sv[k], ev[k])) pend |= 1u << k;
+    constexpr int RPT = 4 * VPT;                    // reads per thread and round
+    // Reads whose ring was full wait here (thread-local memory: a rare path, so that the common one
+    // keeps no per-read registers and the next round's loads can stay in flight).
+    uint32_t fg[RPT], fp[RPT];
+    uint32_t nf = 0;
+    auto take = [&](uint32_t sv, uint32_t ev, int tv) {
+        const uint32_t g = sv >> P, pk = pack(sv, ev, tv);
+        bool want = keep_read(sv, ev);
+        if (hot) want = direct(want, g, pk);
+        if (want && !insert(g, pk)) {
+            fg[nf] = g;
+            fp[nf] = pk;
+            nf++;
         }
+    };
+    // barrier, flush, barrier; then the reads that found their ring full go round again
+    auto finish_round = [&]() {
         for (;;) {
-            if (hot) {
-#pragma unroll
-                for (int k = 0; k < RPT; k++)
-                    if (!direct((pend >> k) & 1u, gk[k], pk[k])) pend &= ~(1u << k);
-            }
-#pragma unroll
-            for (int k = 0; k < RPT; k++)
-                if (((pend >> k) & 1u) && insert(gk[k], pk[k])) pend &= ~(1u << k);
-            hot = hot || __any_sync(0xffffffffu, pend != 0u);
-            const int any = __syncthreads_or(pend != 0u);
+            hot = hot || __any_sync(0xffffffffu, nf != 0u);
+            const int any = __syncthreads_or(nf != 0u);
             flush_phase(false);
             __syncthreads();
             if (!any) break;
+            uint32_t mx = nf;                                   // warp-uniform trip count (direct votes)
+            for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            uint32_t kept = 0;
+            for (uint32_t i = 0; i < mx; i++) {
+                const bool mine = i < nf;
+                const uint32_t g = mine ? fg[i] : 0u, pk = mine ? fp[i] : 0u;
+                bool want = mine;
+                if (hot) want = direct(want, g, pk);
+                if (want && !insert(g, pk)) {
+                    fg[kept] = g;
+                    fp[kept] = pk;
+                    kept++;
+                }
+            }
+            nf = kept;
         }
     };
 
-    // round r covers the 16-byte vectors [r * 2 * ST, (r + 1) * 2 * ST): thread t takes vectors
-    // r * 2 * ST + t and + ST + t (both coalesced across the CTA)
+    // round r covers the 16-byte vectors [r * ROUND_VEC, (r + 1) * ROUND_VEC): thread t takes the
+    // vectors r * ROUND_VEC + h * ST + t (coalesced across the CTA).  The loads of the NEXT round are
+    // issued vector by vector as this round's reads are consumed, and stay in flight through the
+    // rest of the insertions, both barriers and the flush.
     const int64_t n_vec = n >> 2;
-    const int rounds = (int)((n_vec + 2 * ST - 1) / (2 * ST));
+    const int rounds = (int)((n_vec + ROUND_VEC - 1) / ROUND_VEC);
     int round = blockIdx.x;
-    uint4 s4[2], e4[2];
-    char4 t4[2];
-    auto load = [&](int rd, uint4* s, uint4* e, char4* t) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int64_t v = ((int64_t)rd * 2 + h) * ST + tid;
-            s[h] = make_uint4(0, 0, 0, 0);
-            e[h] = make_uint4(0, 0, 0, 0);
-            t[h] = make_char4(0, 0, 0, 0);
-            if (v < n_vec) {
-                s[h] = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
-                e[h] = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
-                if (STRANDED && strand) t[h] = __ldcs(reinterpret_cast<const char4*>(strand) + v);
-            }
+    uint4 s4[VPT], e4[VPT];
+    char4 t4[VPT];
+    auto load = [&](int rd, int h) {
+        const int64_t v = (int64_t)rd * ROUND_VEC + h * ST + tid;
+        s4[h] = e4[h] = make_uint4(0, 0, 0, 0);
+        t4[h] = make_char4(0, 0, 0, 0);
+        if (rd < rounds && v < n_vec) {
+            s4[h] = __ldcs(reinterpret_cast<const uint4*>(g_start) + v);
+            e4[h] = __ldcs(reinterpret_cast<const uint4*>(g_end1) + v);
+            if (STRANDED && strand) t4[h] = __ldcs(reinterpret_cast<const char4*>(strand) + v);
         }
     };
-    if (round < rounds) load(round, s4, e4, t4);
+#pragma unroll
+    for (int h = 0; h < VPT; h++) load(round, h);
     while (round < rounds) {
         const int nr = round + (int)gridDim.x;
-        const uint32_t sv[RPT] = {s4[0].x, s4[0].y, s4[0].z, s4[0].w, s4[1].x, s4[1].y, s4[1].z, s4[1].w};
-        const uint32_t ev[RPT] = {e4[0].x, e4[0].y, e4[0].z, e4[0].w, e4[1].x, e4[1].y, e4[1].z, e4[1].w};
-        const int tv[RPT] = {t4[0].x, t4[0].y, t4[0].z, t4[0].w, t4[1].x, t4[1].y, t4[1].z, t4[1].w};
-        if (nr < rounds) load(nr, s4, e4, t4);            // in flight while this round is split
-        do_round(sv, ev, tv);
+#pragma unroll
+        for (int h = 0; h < VPT; h++) {
+            take(s4[h].x, e4[h].x, t4[h].x);
+            take(s4[h].y, e4[h].y, t4[h].y);
+            take(s4[h].z, e4[h].z, t4[h].z);
+            take(s4[h].w, e4[h].w, t4[h].w);
+            load(nr, h);                    // into the registers just consumed
+        }
+        finish_round();
         round = nr;
     }
     if (blockIdx.x == 0) {              // the n % 4 tail
         const int64_t i = n_vec * 4 + tid;
         const bool in = i < n;
-        uint32_t sv[RPT] = {0u}, ev[RPT] = {0u};
-        int tv[RPT] = {0};
-        sv[0] = in ? g_start[i] : 0u;
-        ev[0] = in ? g_end1[i] : 0u;
-        tv[0] = (in && STRANDED && strand) ? (int)strand[i] : 0;
-        do_round(sv, ev, tv);
+        const uint32_t sv = in ? g_start[i] : 0u, ev = in ? g_end1[i] : 0u;
+        take(sv, ev, (in && STRANDED && strand) ? (int)strand[i] : 0);
+        finish_round();
     }
     flush_phase(true);                   // what is left in the rings: one partial chunk per group
 }
@@ -720,6 +748,32 @@ __device__ __forceinline__ bool sp_apply(uint32_t e, const SpDesc& d, int P, int
     return true;
 }
 
+// The same for the hot loop of the warp-tile kernel: `rev` is a template parameter (the caller
+// branches once per tile, warp-uniformly), both events are PREDICATED shared-memory reductions (no
+// divergent branch around them), addresses are 32-bit shared addresses.  cls = the region's strand
+// classes (flags >> 1).
+template <bool STRANDED, bool REV>
+__device__ __forceinline__ bool sp_apply_fast(uint32_t e, uint32_t cts, int tlen, uint32_t cls, int P,
+                                              uint32_t diff_a) {
+    const int sh = 32 - P;
+    const int rel = ((int)((e - cts) << sh)) >> sh;                // candidate start - tile start
+    int w = (int)(e >> (STRANDED ? P + 2 : P));
+    if (STRANDED) w = ((cls >> ((e >> P) & 3u)) & 1u) ? w : 0;
+    const int lo = max(rel, 0), hi = min(rel + w, tlen);
+    const int a = REV ? tlen - hi : lo;                            // +1 here
+    const int b = REV ? tlen - lo : hi;                            // -1 here unless it is the tile's end
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.lt.s32 p, %0, %1;\n\t"
+        "setp.lt.and.s32 q, %2, %3, p;\n\t"
+        "@p red.shared.add.s32 [%4], 1;\n\t"
+        "@q red.shared.add.s32 [%5], -1;\n\t"
+        "}" ::"r"(lo), "r"(hi), "r"(b), "r"(tlen), "r"(diff_a + (uint32_t)a * 4u), "r"(diff_a + (uint32_t)b * 4u)
+        : "memory");
+    return lo < hi;
+}
+
 // Lane-serial forward scan of a warp-private tile of RPW rows (RPW * 128 ints, zero-padded): lane
 // l owns the RPW * 4 consecutive ints at l * RPW * 4 (16-byte loads with a lane stride of
 // RPW * 16 bytes: conflict-free for odd RPW); the lane sums its run, one warp scan orders the
@@ -804,53 +858,117 @@ sp_bins_finish_kernel(FusedBins fb, const int32_t* __restrict__ plen, const uint
     if (i == 0 && is_null) is_null[r] = null ? 1 : 0;
 }
 
+// 16-byte asynchronous copies global -> shared memory (no register staging): the candidates of the
+// NEXT tile land in a warp-private buffer while the current tile is built, scanned and stored.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // One WARP per tile (<= 896 outputs; a region <= 1024 bp is one tile): no block-wide barrier
-// anywhere.  Persistent warps; the next tile's descriptor and its first 128 candidates are in
-// flight while the current tile is scanned and stored; longer candidate lists are read 128 at a
-// time (four loads per lane in flight).
+// anywhere.  Persistent warps; descriptors are fetched two tiles ahead, and the first CBUF candidate
+// words of the next tile are copied into shared memory (cp.async) during the current tile.  The
+// staged range starts at the 16-byte boundary below the tile's first candidate and ends at the one
+// above its last: the extra words belong to neighbouring sub-bins (or are the zero words of a
+// hole), start before the reach of the widest read or after the tile, and clip to nothing.
+// Longer candidate lists continue from global memory, 128 at a time.
 #ifndef RCP_WTILE_OCC
 #define RCP_WTILE_OCC 4
 #endif
+constexpr int CBUF = 256;                   // staged candidate words per tile and buffer
+constexpr size_t WTILE_SMEM = (size_t)WARPS * (WT_ONE * 4 + 2 * CBUF * 4 + 4 * sizeof(SpDesc));
 template <bool STRANDED, bool FUSED>
 __global__ void __launch_bounds__(CTA, RCP_WTILE_OCC)
 sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __restrict__ cand, int P,
                 int32_t* __restrict__ cov, uint8_t* __restrict__ region_hit, FusedBins fb, LongIdx lg,
                 const uint32_t* __restrict__ tabs, const uint2* __restrict__ lrange) {
-    __shared__ __align__(16) int sm[WARPS][WT_ONE];
+    extern __shared__ __align__(16) unsigned char wt_smem[];
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    int* diff = sm[warp];
+    int* diff = reinterpret_cast<int*>(wt_smem) + warp * WT_ONE;
+    const uint32_t* cs = reinterpret_cast<const uint32_t*>(wt_smem + (size_t)WARPS * WT_ONE * 4) + warp * 2 * CBUF;
+    const SpDesc* ring = reinterpret_cast<const SpDesc*>(wt_smem + (size_t)WARPS * (WT_ONE * 4 + 2 * CBUF * 4)) + warp * 4;
+    const uint32_t cs_a = (uint32_t)__cvta_generic_to_shared(cs);
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(ring);
     const int64_t step = (int64_t)gridDim.x * WARPS;
     int64_t t = (int64_t)blockIdx.x * WARPS + warp;
     if (t >= T) return;
-    constexpr int B = 4;
-    auto load4 = [&](const SpDesc& x, uint32_t i0, uint32_t* e) {
+    // descriptor of this warp's tile number j (tile t0 + j * step) -> ring slot j & 3, by two lanes
+    auto stage_desc = [&](int64_t tile, int j) {
+        if (lane < 2 && tile < T)
+            cp_async16(ring_a + (uint32_t)(j & 3) * (uint32_t)sizeof(SpDesc) + lane * 16u,
+                       reinterpret_cast<const int4*>(desc + tile) + lane);
+    };
+    // the 16-byte units of [c0 & ~3, ...) that hold the first candidates of a tile
+    auto stage_cands = [&](uint32_t c0, uint32_t n, int buf) {
+        const uint32_t a0 = c0 & ~3u;
+        const uint32_t units = min(((c0 - a0) + n + 3u) >> 2, (uint32_t)(CBUF / 4));
 #pragma unroll
-        for (int k = 0; k < B; k++) {
-            const uint32_t i = i0 + (uint32_t)k * 32u + lane;
-            e[k] = i < x.n ? __ldg(cand + x.c0 + i) : 0u;       // 0: width 0, never a hit
+        for (int k = 0; k < CBUF / 128; k++) {
+            const uint32_t u = (uint32_t)k * 32u + lane;
+            if (u < units) cp_async16(cs_a + (uint32_t)buf * (CBUF * 4) + u * 16u, cand + a0 + u * 4u);
         }
     };
-    SpDesc d = sp_load_desc(desc + t);
-    SpDesc dn;
-    dn.n = 0;
-    if (t + step < T) dn = sp_load_desc(desc + t + step);
-    uint32_t e[B], f[B];
-    load4(d, 0, e);
-    for (;;) {
+    stage_desc(t, 0);
+    stage_desc(t + step, 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    stage_cands(ring[0].c0, ring[0].n, 0);
+    cp_async_commit();
+    int buf = 0;
+    constexpr int B = 4;
+    // iteration j: the group committed one iteration ago (candidates of tile j, descriptor of tile
+    // j + 1) has had a whole tile's time to land; the next group (candidates of j + 1, descriptor
+    // of j + 2) is issued before tile j is built
+    for (int j = 0;; j++) {
+        cp_async_wait<0>();
+        __syncwarp();
+        const SpDesc d = ring[j & 3];
         const bool more = t + step < T;
-        if (more) load4(dn, 0, f);                  // next tile's first candidates
+        if (more) {
+            const SpDesc* nx = ring + ((j + 1) & 3);
+            stage_cands(nx->c0, nx->n, buf ^ 1);
+        }
+        stage_desc(t + 2 * step, j + 2);
+        cp_async_commit();
         const int rows = (d.tlen + ROW - 1) / ROW;
         for (int k = 0; k < rows; k++) reinterpret_cast<int4*>(diff)[k * 32 + lane] = make_int4(0, 0, 0, 0);
         __syncwarp();
         bool hit = false;
-        for (uint32_t i0 = 0;;) {
+        const uint32_t a0 = d.c0 & ~3u;
+        const uint32_t words = (d.c0 - a0) + d.n;                       // from a0 on
+        const uint32_t staged = min((words + 3u) & ~3u, (uint32_t)CBUF);
+        const uint32_t mine_a = cs_a + (uint32_t)buf * (CBUF * 4) + lane * 4u;
+        const uint32_t diff_a = (uint32_t)__cvta_generic_to_shared(diff);
+        const uint32_t cls = d.flags >> 1;
+        auto apply_all = [&](auto rev_tag) {
+            constexpr bool REV = decltype(rev_tag)::value;
+#pragma unroll 4
+            for (uint32_t i = lane; i < staged; i += 32)
+                hit |= sp_apply_fast<STRANDED, REV>(lds32(mine_a + (i - lane) * 4u), d.cts, d.tlen, cls, P, diff_a);
+#if defined(RCP_EXP_MODE) && RCP_EXP_MODE == 2     // timing experiment: staged candidates only (wrong results)
+            if (d.tlen >= 0) return;
+#endif
+            for (uint32_t i0 = CBUF; i0 < words; i0 += B * 32) {       // a long list: the rest from global memory
+                uint32_t e[B];
 #pragma unroll
-            for (int k = 0; k < B; k++) hit |= sp_apply<STRANDED>(e[k], d, P, diff);
-            i0 += B * 32;
-            if (i0 >= d.n) break;
-            load4(d, i0, e);
-        }
+                for (int k = 0; k < B; k++) {
+                    const uint32_t i = i0 + (uint32_t)k * 32u + lane;
+                    e[k] = i < words ? __ldg(cand + a0 + i) : 0u;       // 0: width 0, never a hit
+                }
+#pragma unroll
+                for (int k = 0; k < B; k++) hit |= sp_apply_fast<STRANDED, REV>(e[k], d.cts, d.tlen, cls, P, diff_a);
+            }
+        };
+#if defined(RCP_EXP_MODE) && RCP_EXP_MODE == 1     // timing experiment: no candidates applied (wrong results)
+        if (d.tlen < 0) apply_all(std::true_type{});
+#else
+        if (d.flags & 1u) apply_all(std::true_type{});
+        else apply_all(std::false_type{});
+#endif
         if (lg.n) {             // the reads kept out of the binned index
             const uint2 lr = lrange[t];
             const uint32_t ts = tabs[t];
@@ -897,10 +1015,7 @@ sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __re
         if (!FUSED && lane == 0) tma_store_wait_read();     // the bulk store has read the tile
         if (!more) break;
         __syncwarp();
-        d = dn;
-        if (t + step < T) dn = sp_load_desc(desc + t + step);
-#pragma unroll
-        for (int k = 0; k < B; k++) e[k] = f[k];
+        buf ^= 1;
     }
 }
 
@@ -1465,12 +1580,20 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
         unsigned long long pstats[3];
         unsigned int err;
     } h = {0, 0, {0, 0, 0}, 0};
+    // The read passes do not depend on anything the host is about to learn: they are queued
+    // BEFORE the host waits for the plan's numbers, so the GPU works through the round trip.  (A
+    // sample whose reads turn out not to fit the packed word is caught below; the passes have
+    // written into their own arenas only.)
+    Arena K, B;
+    SortedCands sc;
     {
         FetchItem items[8] = {{off_tile + R, &h.T, 8}, {cv->off + R, &h.total_padded, 8}, {pstats, h.pstats, 24},
                               {err, &h.err, 4}};
         int n_items = 4;
         reads_pending_items(rd, items, &n_items);       // a deferred rcp_reads_load is validated here
-        RCP_TRY(fetch_and_sync(items, n_items));
+        RCP_TRY(fetch_begin(items, n_items));
+        if (!have_index) RCP_TRY(split_and_sort(rd, tab, words, P, n_groups, stranded, st_arr, 0xffffffffu, K, B, &sc));
+        RCP_TRY(fetch_end(items, n_items));
         RCP_TRY(reads_finish(rd));
     }
     if (h.err & 1u) return fail(RCP_ERR_DATA, "a region has a chromosome id outside [0, n_chrom)");
@@ -1526,16 +1649,12 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     }
 
     // ---- the sorted candidates: the handle's binned index when it has one, else this mask's ----
-    Arena K, B;
-    SortedCands sc;
     bool words_stranded = stranded;
     if (have_index) {
         sc.cand = rd.bn_cand;
         sc.boff = rd.bn_boff;
         sc.cb = rd.bn_cb;
         words_stranded = rd.bn_stranded;
-    } else {
-        RCP_TRY(split_and_sort(rd, tab, words, P, n_groups, stranded, st_arr, 0xffffffffu, K, B, &sc));
     }
     uint32_t* cand = sc.cand;
     uint32_t* boff = sc.boff;
@@ -1566,9 +1685,11 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
             const int64_t want = blocks_for(T, WARPS);
             auto launch = [&](auto kern) -> int {
                 int per_sm = 0;
-                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA, 0));
+                RCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WTILE_SMEM));
+                RCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA, WTILE_SMEM));
                 per_sm = std::max(per_sm, 1);
-                kern<<<(unsigned)std::min<int64_t>(want, (int64_t)g_ctx.sm_count * per_sm), CTA, 0, g_ctx.stream>>>(
+                kern<<<(unsigned)std::min<int64_t>(want, (int64_t)g_ctx.sm_count * per_sm), CTA, WTILE_SMEM,
+                       g_ctx.stream>>>(
                     T, desc, cand, P, cv->cov, region_hit, fb, lg, tabs, lrange);
                 RCP_LAUNCHED();
                 return RCP_OK;

@@ -116,6 +116,9 @@ struct FetchItem {
     int bytes;      // <= 32, a multiple of 4
 };
 int fetch_and_sync(const FetchItem* items, int n);      // n <= 8
+// the same in two halves: kernels queued between them run while the host waits for the values
+int fetch_begin(const FetchItem* items, int n);
+int fetch_end(const FetchItem* items, int n);
 
 // Device scratch of one call: one allocation, sub-buffers 256-byte aligned.
 struct Arena {
