@@ -161,6 +161,16 @@ int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const 
 int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, const int32_t* run_len,
                        const int32_t* start, const int32_t* end, const int8_t* strand, int n_chrom,
                        const int64_t* chrom_len, int frag_len, int mem, int* reads_out);
+/* The same for a library whose reads all have ONE width -- fixed-length single-end reads, or a
+ * GRanges after `resize(x, w)`: an IRanges holds (start, width), and a constant width is one number
+ * (`w <- width(x)[1L]` when `S4Vectors::isConstant(width(x))`, checked once at import).  Every read
+ * is [start, start + width - 1]; the `end` array never crosses PCIe (9 -> 5 bytes per read with the
+ * seqnames as runs).  chrom == NULL: the seqnames come as runs (n_runs, run_chrom, run_len, as in
+ * rcp_reads_load_rle); otherwise dense ids and the run arguments are ignored.  Same result as
+ * rcp_reads_load with end = start + width - 1. */
+int rcp_reads_load_width(int64_t n, const int32_t* chrom, int64_t n_runs, const int32_t* run_chrom,
+                         const int32_t* run_len, const int32_t* start, int width, const int8_t* strand,
+                         int n_chrom, const int64_t* chrom_len, int frag_len, int mem, int* reads_out);
 /* The read-import step right before the path (preprocessRanges / readBam, ranges.R:1-65,
  * 111-134), for reads that are already decoded:
  *

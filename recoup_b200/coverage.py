@@ -74,13 +74,32 @@ class DeviceReads:
             self._fin = weakref.finalize(self, _free_reads, self.handle)
             return
         start = np.ascontiguousarray(gr.start, dtype=np.int32)
-        end = np.ascontiguousarray(gr.end, dtype=np.int32)
         strand = np.ascontiguousarray(gr.strand, dtype=np.int8)
         clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
         clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
         rle = gr.seqnames_rle
         if use_runs is None:
             use_runs = rle is not None and len(gr) < 2**32 - 16 and rle.nrun * 2 < len(gr)
+        fixed = getattr(gr, "fixed_width", None)
+        if fixed is not None:
+            # one width for every read: start (+ strand) only cross PCIe
+            if use_runs:
+                run_chrom = np.ascontiguousarray(rle.values, dtype=np.int32)
+                run_len = np.ascontiguousarray(rle.lengths, dtype=np.int32)
+                _lib_check(_lib.lib.rcp_reads_load_width(len(gr), None, rle.nrun, _ptr(run_chrom), _ptr(run_len),
+                                                         _ptr(start), int(fixed), _ptr(strand), clen.shape[0],
+                                                         clen_p, int(frag_len), _lib.MEM_HOST, C.byref(h)))
+            else:
+                chrom = np.ascontiguousarray(gr.seqnames, dtype=np.int32)
+                _lib_check(_lib.lib.rcp_reads_load_width(len(gr), _ptr(chrom), 0, None, None, _ptr(start),
+                                                         int(fixed), _ptr(strand), clen.shape[0], clen_p,
+                                                         int(frag_len), _lib.MEM_HOST, C.byref(h)))
+            self.handle = h.value
+            self.n = len(gr)
+            self.seqlevels = list(gr.seqlevels)
+            self._fin = weakref.finalize(self, _free_reads, self.handle)
+            return
+        end = np.ascontiguousarray(gr.end, dtype=np.int32)
         if use_runs:
             # seqnames held as runs: only the runs cross PCIe
             run_chrom = np.ascontiguousarray(rle.values, dtype=np.int32)

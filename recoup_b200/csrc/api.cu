@@ -243,7 +243,7 @@ static void drop_coverage(int h) {
 int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs,
                     const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
-                    const int64_t* chrom_len, int frag_len, int mem);
+                    const int64_t* chrom_len, int frag_len, int mem, int fixed_width);
 int reads_load_select_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const int32_t* start,
                            const int32_t* end, const int8_t* strand, double max_width, int64_t k,
                            const int32_t* idx, int n_chrom, const int64_t* chrom_len, int frag_len,
@@ -639,7 +639,7 @@ int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const 
     if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
     std::unique_ptr<ReadsIdx> r(new ReadsIdx());
     int rc = reads_load_impl(*r, n, chrom, 0, nullptr, nullptr, start, end, strand, n_chrom, chrom_len,
-                             frag_len, mem);
+                             frag_len, mem, 0);
     if (rc != RCP_OK) {
         reads_release(*r);
         return rc;
@@ -664,7 +664,33 @@ int rcp_reads_load_rle(int64_t n, int64_t n_runs, const int32_t* run_chrom, cons
     if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
     std::unique_ptr<ReadsIdx> r(new ReadsIdx());
     int rc = reads_load_impl(*r, n, nullptr, n_runs, run_chrom, run_len, start, end, strand, n_chrom,
-                             chrom_len, frag_len, mem);
+                             chrom_len, frag_len, mem, 0);
+    if (rc != RCP_OK) {
+        reads_release(*r);
+        return rc;
+    }
+    const int h = g_next_handle++;
+    g_reads[h] = std::move(r);
+    *reads_out = h;
+    return RCP_OK;
+}
+
+int rcp_reads_load_width(int64_t n, const int32_t* chrom, int64_t n_runs, const int32_t* run_chrom,
+                         const int32_t* run_len, const int32_t* start, int width, const int8_t* strand,
+                         int n_chrom, const int64_t* chrom_len, int frag_len, int mem, int* reads_out) {
+    RCP_TRY(require_ready());
+    if (n < 0 || n_runs < 0 || n_chrom < 1 || chrom_len == nullptr || reads_out == nullptr || frag_len < 0)
+        return fail(RCP_ERR_ARG, "rcp_reads_load_width: bad scalar argument");
+    if (width < 1) return fail(RCP_ERR_ARG, "rcp_reads_load_width: width must be >= 1");
+    const bool runs = chrom == nullptr;
+    if (n > 0 && (start == nullptr || (runs && (n_runs < 1 || run_chrom == nullptr || run_len == nullptr))))
+        return fail(RCP_ERR_ARG, "rcp_reads_load_width: NULL array");
+    if (runs && n >= 0xfffffff0ll) return fail(RCP_ERR_UNSUPPORTED, "rcp_reads_load_width: n >= 2^32");
+    if (mem != RCP_MEM_HOST && mem != RCP_MEM_DEVICE) return fail(RCP_ERR_ARG, "bad mem kind");
+    std::unique_ptr<ReadsIdx> r(new ReadsIdx());
+    int rc = reads_load_impl(*r, n, chrom, runs ? n_runs : 0, runs ? run_chrom : nullptr,
+                             runs ? run_len : nullptr, start, nullptr, strand, n_chrom, chrom_len, frag_len,
+                             mem, width);
     if (rc != RCP_OK) {
         reads_release(*r);
         return rc;

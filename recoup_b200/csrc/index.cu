@@ -54,12 +54,13 @@ __device__ __forceinline__ bool map_read(int c, int64_t s, int64_t e, int st, in
 
 // VEC = 4: every thread maps four consecutive reads with 16-byte loads/stores (all arrays
 // 16-byte aligned, checked on the host); the n % 4 tail and VEC = 1 use scalar accesses.
-template <int VEC>
+template <int VEC, bool HAS_END>
 __global__ void __launch_bounds__(TPB)
 reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                        const int8_t* __restrict__ strand, const uint32_t* __restrict__ chrom_off,
                        const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
+                       int fixed_width /* end == nullptr: every read is [start, start + fixed_width - 1] */,
                        uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
                        uint32_t* __restrict__ xs_out, int8_t* __restrict__ strand_out,
                        unsigned int* __restrict__ err, unsigned long long* __restrict__ cls_count,
@@ -72,13 +73,14 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
     if (frag_len <= 0) {
         uint32_t a = 0, b = 0;
         unsigned int e0 = 0;
-        if (map_read(chrom[0], start[0], end[0], strand ? (int)strand[0] : 0, n_chrom, chrom_off,
+        if (map_read(chrom[0], start[0], HAS_END ? (int64_t)end[0] : (int64_t)start[0] + fixed_width - 1,
+                     strand ? (int)strand[0] : 0, n_chrom, chrom_off,
                      chrom_len, 0, &a, &b, &e0))
             w = b - a;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *exc.w_out = w;
 
-    auto one = [&](int c, int s, int e, int st, uint32_t* gs, uint32_t* ge1) {
+    auto one = [&](int c, int s, int64_t e, int st, uint32_t* gs, uint32_t* ge1) {
         *gs = 0;
         *ge1 = 0;
         if (map_read(c, s, e, st, n_chrom, chrom_off, chrom_len, frag_len, gs, ge1, &my_err)) {
@@ -110,14 +112,16 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
     for (int64_t v = (int64_t)blockIdx.x * TPB + threadIdx.x; v < n_vec; v += stride) {
         const int4 c4 = __ldg(reinterpret_cast<const int4*>(chrom) + v);
         const int4 s4 = __ldg(reinterpret_cast<const int4*>(start) + v);
-        const int4 e4 = __ldg(reinterpret_cast<const int4*>(end) + v);
+        int4 e4 = make_int4(0, 0, 0, 0);
+        if (HAS_END) e4 = __ldg(reinterpret_cast<const int4*>(end) + v);
+        const int64_t wm1 = (int64_t)fixed_width - 1;
         char4 t4 = make_char4(0, 0, 0, 0);
         if (strand) t4 = __ldg(reinterpret_cast<const char4*>(strand) + v);
         uint4 gs, ge;
-        one(c4.x, s4.x, e4.x, t4.x, &gs.x, &ge.x);
-        one(c4.y, s4.y, e4.y, t4.y, &gs.y, &ge.y);
-        one(c4.z, s4.z, e4.z, t4.z, &gs.z, &ge.z);
-        one(c4.w, s4.w, e4.w, t4.w, &gs.w, &ge.w);
+        one(c4.x, s4.x, HAS_END ? (int64_t)e4.x : s4.x + wm1, t4.x, &gs.x, &ge.x);
+        one(c4.y, s4.y, HAS_END ? (int64_t)e4.y : s4.y + wm1, t4.y, &gs.y, &ge.y);
+        one(c4.z, s4.z, HAS_END ? (int64_t)e4.z : s4.z + wm1, t4.z, &gs.z, &ge.z);
+        one(c4.w, s4.w, HAS_END ? (int64_t)e4.w : s4.w + wm1, t4.w, &gs.w, &ge.w);
         reinterpret_cast<uint4*>(g_start)[v] = gs;
         reinterpret_cast<uint4*>(g_end1)[v] = ge;
         if (xs_out) reinterpret_cast<uint4*>(xs_out)[v] = gs;
@@ -127,7 +131,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
     for (int64_t i = n_vec * 4 + (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
         const int st = strand ? (int)strand[i] : 0;
         uint32_t gs, ge1;
-        one(chrom[i], start[i], end[i], st, &gs, &ge1);
+        one(chrom[i], start[i], HAS_END ? (int64_t)end[i] : (int64_t)start[i] + fixed_width - 1, st, &gs, &ge1);
         g_start[i] = gs;
         g_end1[i] = ge1;
         if (xs_out) xs_out[i] = gs;
@@ -524,7 +528,7 @@ rle_check_kernel(int64_t n_runs, const int32_t* __restrict__ run_len, unsigned i
 int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs,
                     const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
-                    const int64_t* chrom_len, int frag_len, int mem) {
+                    const int64_t* chrom_len, int frag_len, int mem, int fixed_width) {
     const bool dbg = getenv("RCP_DEBUG_TIMING") != nullptr;
     auto t_start = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -572,7 +576,7 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
         RCP_TRY(d_chrom.init(chrom, (size_t)n, mem));
     }
     RCP_TRY(d_start.init(start, (size_t)n, mem));
-    RCP_TRY(d_end.init(end, (size_t)n, mem));
+    RCP_TRY(d_end.init(end, (size_t)n, mem));            // nullptr with fixed_width: nothing to copy
     RCP_TRY(d_strand.init(strand, (size_t)n, mem));
     lap("staging copies enqueued");
 
@@ -620,19 +624,21 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     if (n > 0) {
         StageTimer t(ST_INDEX_MAP);
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-        const bool vec = al16(d_chrom.ptr) && al16(d_start.ptr) && al16(d_end.ptr) &&
+        const bool vec = al16(d_chrom.ptr) && al16(d_start.ptr) && (d_end.ptr == nullptr || al16(d_end.ptr)) &&
                          (d_strand.ptr == nullptr || (reinterpret_cast<uintptr_t>(d_strand.ptr) & 3u) == 0);
         const unsigned grid = grid_for(vec ? (n + 3) / 4 : n);
-        if (vec)
-            reads_to_global_kernel<4><<<grid, TPB, 0, g_ctx.stream>>>(
-                n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
-                n_chrom, frag_len, r.g_start, r.g_end1, r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt,
-                exc);
-        else
-            reads_to_global_kernel<1><<<grid, TPB, 0, g_ctx.stream>>>(
-                n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off, r.d_chrom_len,
-                n_chrom, frag_len, r.g_start, r.g_end1, r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt,
-                exc);
+        auto launch = [&](auto kern) {
+            kern<<<grid, TPB, 0, g_ctx.stream>>>(n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off,
+                                                 r.d_chrom_len, n_chrom, frag_len, fixed_width, r.g_start, r.g_end1,
+                                                 r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt, exc);
+        };
+        if (d_end.ptr) {
+            if (vec) launch(reads_to_global_kernel<4, true>);
+            else launch(reads_to_global_kernel<1, true>);
+        } else {
+            if (vec) launch(reads_to_global_kernel<4, false>);
+            else launch(reads_to_global_kernel<1, false>);
+        }
         RCP_LAUNCHED();
     }
     lap("map kernel enqueued");
@@ -824,7 +830,7 @@ int reads_load_select_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, const i
     }
     if (rc == RCP_OK)
         rc = reads_load_impl(r, m, o_chrom, 0, nullptr, nullptr, o_start, o_end, o_strand, n_chrom, chrom_len,
-                             frag_len, RCP_MEM_DEVICE);
+                             frag_len, RCP_MEM_DEVICE, 0);
     dfree(flag);
     dfree(rank);
     dfree(kept_pos);

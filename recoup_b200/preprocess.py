@@ -34,6 +34,7 @@ class SelectedGRanges(GRanges):
         self.seqlengths = parent.seqlengths
         self.names = None
         self.seqnames_rle = None
+        self.fixed_width = None
         self._device = {}
         self._host = None
 

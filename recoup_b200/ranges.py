@@ -78,11 +78,21 @@ class GRanges:
                  seqlengths=None, names=None):
         start = np.ascontiguousarray(start, dtype=np.int32)
         n = start.shape[0]
+        # ONE width for every range (fixed-length reads, or a GRanges after resize()): kept as a
+        # number, as a constant-width IRanges is known to be; `end` is materialised only on demand
+        # and the reads upload sends start + width (rcp_reads_load_width)
+        self.fixed_width = None
         if end is None:
             if width is None:
                 raise ValueError("give end or width")
-            end = start.astype(np.int64) + np.asarray(width, dtype=np.int64) - 1
-        end = np.ascontiguousarray(end, dtype=np.int32)
+            if np.ndim(width) == 0:
+                if int(width) < 1:
+                    raise ValueError("width must be >= 1")
+                self.fixed_width = int(width)
+            else:
+                end = start.astype(np.int64) + np.asarray(width, dtype=np.int64) - 1
+        if end is not None:
+            end = np.ascontiguousarray(end, dtype=np.int32)
         run_len = None
         if isinstance(seqnames, Rle):
             if len(seqnames) != n:
@@ -107,7 +117,8 @@ class GRanges:
         st = strand_to_code(strand, n) if strand is not None else np.zeros(n, dtype=np.int8)
         if st.shape[0] == 1 and n != 1:
             st = np.full(n, st[0], dtype=np.int8)
-        if not ((run_len is not None or ids.shape[0] == n) and end.shape[0] == st.shape[0] == n):
+        if not ((run_len is not None or ids.shape[0] == n) and st.shape[0] == n
+                and (end is None or end.shape[0] == n)):
             raise ValueError("seqnames, start, end and strand must have the same length")
         if run_len is None:
             self.seqnames_rle = None
@@ -116,7 +127,7 @@ class GRanges:
             self.seqnames_rle = Rle(ids, run_len)
             self._seqnames = None
         self.start = start
-        self.end = end
+        self._end = end
         self.strand = np.ascontiguousarray(st, dtype=np.int8)
         self.seqlevels = list(seqlevels)
         self.seqlengths = (None if seqlengths is None
@@ -134,7 +145,18 @@ class GRanges:
         return self._seqnames
 
     @property
+    def end(self):
+        if self._end is None:
+            e = self.start.astype(np.int64) + (self.fixed_width - 1)
+            if e.size and int(e.max()) > np.iinfo(np.int32).max:
+                raise OverflowError("start + width - 1 leaves the int32 range")
+            self._end = np.ascontiguousarray(e, dtype=np.int32)
+        return self._end
+
+    @property
     def width(self):
+        if self.fixed_width is not None:
+            return np.full(len(self), self.fixed_width, dtype=np.int64)
         return self.end.astype(np.int64) - self.start.astype(np.int64) + 1
 
     def subset(self, idx):

@@ -522,6 +522,44 @@ def test_seqnames_as_runs_give_the_same_coverage(gpu, n_reads, runs):
         assert_coverage_equal(rb.calcCoverage(g_rle, g_mask, ignore_strand=False).to_list(), want)
 
 
+@pytest.mark.parametrize("frag_len", [0, 200])
+@pytest.mark.parametrize("runs", [False, True])
+def test_one_width_reads_upload_start_only(gpu, runs, frag_len):
+    """rcp_reads_load_width (start + ONE width; the ends never cross PCIe) == the dense upload ==
+    oracle, with and without the fragment extension, seqnames dense or as runs"""
+    rb = gpu
+    rng = np.random.default_rng(11)
+    clen = [30000, 70000, 900, 15000]
+    n, w = 6001, 36
+    chrom, s, _, st = synth_reads(rng, n, clen, width=(w, w))
+    s = np.minimum(s, np.asarray(clen)[chrom] - w + 1).astype(np.int32)
+    if runs:
+        order = np.argsort(chrom, kind="stable")
+        chrom, s, st = chrom[order], s[order], st[order]
+    e = (s + w - 1).astype(np.int32)
+    o_reads, g_dense = both_reads(chrom, s, e, st, clen)
+    g_w = rb.GRanges(rb.Rle.encode(chrom) if runs else chrom, s, width=w, strand=st,
+                     seqlevels=g_dense.seqlevels, seqlengths=clen)
+    rc, rs, re_, rst = _regions(rng, 150, clen, [1, 33, 128, 1024, 1025, 5000, 9000])
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, len(clen))
+    got = rb.calcCoverage(g_w, g_mask, ignore_strand=False, frag_len=frag_len)
+    assert g_w._end is None                     # the host never built the ends
+    ref = rb.calcCoverage(g_dense, g_mask, ignore_strand=False, frag_len=frag_len)
+    assert_coverage_equal(got.to_list(), ref.to_list())
+    if frag_len:
+        es, ee = O.extend_fragments(s, e, st, frag_len, chrom, clen)
+        o_reads = O.Reads(chrom, es, ee, st, clen)
+    assert_coverage_equal(got.to_list(), O.calc_coverage(o_reads, o_mask, None, False))
+    # argument errors
+    from recoup_b200 import _lib
+    h = C.c_int(0)
+    cl = np.asarray(clen, dtype=np.int64)
+    rc_ = _lib.lib.rcp_reads_load_width(n, chrom.ctypes.data_as(C.c_void_p), 0, None, None,
+                                        s.ctypes.data_as(C.c_void_p), 0, None, len(clen),
+                                        cl.ctypes.data_as(C.POINTER(C.c_int64)), 0, _lib.MEM_HOST, C.byref(h))
+    assert rc_ == _lib.RCP_ERR_ARG
+
+
 def test_seqnames_runs_errors(gpu):
     rb = gpu
     from recoup_b200 import _lib

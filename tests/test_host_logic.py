@@ -83,6 +83,20 @@ def test_granges_container():
         rb.GRangesList(gr, [0, 2])
 
 
+def test_granges_with_one_width_keeps_it_as_a_number():
+    gr = rb.GRanges([0, 0, 1], [5, 1, 9], width=36, strand=["+", "-", "*"], seqlevels=["a", "b"])
+    assert gr.fixed_width == 36 and gr._end is None          # nothing materialised
+    assert gr.width.tolist() == [36, 36, 36]
+    assert gr.end.tolist() == [40, 36, 44]
+    sub = gr.subset(np.array([0, 2]))
+    assert sub.end.tolist() == [40, 44] and sub.fixed_width is None
+    assert rb.GRanges([0], [5], width=[7]).fixed_width is None
+    with pytest.raises(ValueError):
+        rb.GRanges([0], [5], width=0)
+    with pytest.raises(OverflowError):
+        rb.GRanges([0], [2**31 - 5], width=36).end
+
+
 def test_rle_seqnames_round_trip():
     from recoup_b200 import GRanges, Rle
     x = np.array([0, 0, 0, 2, 2, 1, 1, 1, 1], dtype=np.int32)
