@@ -242,7 +242,7 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
 struct SplitOut {
     uint32_t* pool;          // chunks of CH entries
     uint16_t* meta;          // per chunk: group << 5 | entries (0: unused slot)
-    uint32_t* pool_next;     // chunks handed out so far (in SLABs)
+    uint32_t* pool_next;     // chunks handed out so far (in SLABs); [1]: rounds handed out so far
 };
 
 // Shared memory of the split kernel: rings | ring counters | block table.
@@ -417,9 +417,21 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
     // vectors r * ROUND_VEC + h * ST + t (coalesced across the CTA).  The loads of the NEXT round are
     // issued vector by vector as this round's reads are consumed, and stay in flight through the
     // rest of the insertions, both barriers and the flush.
+    // Rounds are handed out by a global counter, not by a fixed stride: when the kernel shares the
+    // GPU (the NCCL gather of the previous step holds a few SMs) the CTAs that start late simply
+    // take fewer rounds, instead of running a second wave that doubles the kernel's time.  The
+    // index of the round after next is fetched by thread 0 during a round and published through
+    // shared memory at that round's barriers.
+    __shared__ int next_round[2];
     const int64_t n_vec = n >> 2;
     const int rounds = (int)((n_vec + ROUND_VEC - 1) / ROUND_VEC);
-    int round = blockIdx.x;
+    if (tid == 0) {
+        next_round[0] = (int)atomicAdd(out.pool_next + 1, 1u);
+        next_round[1] = (int)atomicAdd(out.pool_next + 1, 1u);
+    }
+    __syncthreads();
+    int round = next_round[0], nr = next_round[1];
+    __syncthreads();
     uint4 s4[VPT], e4[VPT];
     char4 t4[VPT];
     auto load = [&](int rd, int h) {
@@ -434,8 +446,9 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
     };
 #pragma unroll
     for (int h = 0; h < VPT; h++) load(round, h);
-    while (round < rounds) {
-        const int nr = round + (int)gridDim.x;
+    for (int it = 0; round < rounds; it++) {
+        unsigned after = 0;
+        if (tid == 0) after = atomicAdd(out.pool_next + 1, 1u);     // in flight during the round
 #pragma unroll
         for (int h = 0; h < VPT; h++) {
             take(s4[h].x, e4[h].x, t4[h].x);
@@ -444,8 +457,10 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
             take(s4[h].w, e4[h].w, t4[h].w);
             load(nr, h);                    // into the registers just consumed
         }
-        finish_round();
+        if (tid == 0) next_round[it & 1] = (int)min(after, 0x7fffffffu);
+        finish_round();                     // (its barriers publish next_round[it & 1])
         round = nr;
+        nr = next_round[it & 1];
     }
     if (blockIdx.x == 0) {              // the n % 4 tail
         const int64_t i = n_vec * 4 + tid;
