@@ -1,4 +1,5 @@
 // C ABI of librecoup_b200.so (include/recoup_b200.h): context, handle tables, argument checks.
+#include <climits>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -282,6 +283,91 @@ int base_matrix_device(const Coverage& cv, int where, int f1, int f2, int64_t n_
                        double* d_out, int64_t ld);
 
 namespace {
+
+// ---- region-sharded runs: which rank(s) needs a read ("each GPU owns a region slice
+// plus its overlapping reads") ----------------------------------------------------------------
+constexpr int ROUTE_MAXW = 64;          // ranks
+constexpr int ROUTE_CTA = 256;
+constexpr int ROUTE_PER = 8;            // reads per thread: a CTA owns ROUTE_CTA * ROUTE_PER consecutive reads
+
+// span[(r * n_chrom + c) * 2 + {0, 1}] = [lo, hi] of rank r's slice on chromosome c (lo > hi: none).
+// A read with a chromosome id outside the table goes to rank 0, whose load reports it.
+__device__ __forceinline__ bool route_hit(const int32_t* sp, int n_chrom, int r, int c, int s, int e) {
+    if (c < 0 || c >= n_chrom) return r == 0;
+    const int lo = sp[(r * n_chrom + c) * 2], hi = sp[(r * n_chrom + c) * 2 + 1];
+    return e >= lo && s <= hi;
+}
+
+// PACK = false: counts[r] += reads for rank r.  PACK = true: the reads leave as (chrom, start, end)
+// triples + strand bytes, rank r's run starting at base[r]; a CTA reserves its share of every run
+// with one atomic per rank, so a run is written in CTA-sized contiguous pieces.
+template <bool PACK>
+__global__ void __launch_bounds__(ROUTE_CTA)
+route_kernel(int64_t n, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
+             const int32_t* __restrict__ end, const int8_t* __restrict__ strand, int world, int n_chrom,
+             const int32_t* __restrict__ span, unsigned long long* __restrict__ counts /* [world] */,
+             const int64_t* __restrict__ base /* [world] */, int32_t* __restrict__ triples,
+             int8_t* __restrict__ strand_out) {
+    extern __shared__ int32_t route_sp[];                   // the span table
+    __shared__ unsigned int cnt[ROUTE_MAXW];
+    __shared__ unsigned long long at[ROUTE_MAXW];
+    for (int i = threadIdx.x; i < world * n_chrom * 2; i += ROUTE_CTA) route_sp[i] = span[i];
+    if (threadIdx.x < ROUTE_MAXW) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * (ROUTE_CTA * ROUTE_PER);
+    const unsigned lane = threadIdx.x & 31;
+    int c[ROUTE_PER], s[ROUTE_PER], e[ROUTE_PER];
+#pragma unroll
+    for (int k = 0; k < ROUTE_PER; k++) {
+        const int64_t i = first + (int64_t)k * ROUTE_CTA + threadIdx.x;
+        const bool in = i < n;
+        c[k] = in ? chrom[i] : 0;
+        s[k] = in ? start[i] : 1;
+        e[k] = in ? end[i] : 0;
+        if (!in) c[k] = INT_MIN;                            // beyond the reads: nowhere
+    }
+    // warp-uniform loops: every lane walks the same (k, r) pairs, the ballots see whole warps
+    for (int r = 0; r < world; r++) {
+        unsigned mine = 0;
+#pragma unroll
+        for (int k = 0; k < ROUTE_PER; k++)
+            mine += (c[k] != INT_MIN && route_hit(route_sp, n_chrom, r, c[k], s[k], e[k])) ? 1u : 0u;
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if (lane == 0 && mine) atomicAdd(&cnt[r], mine);
+    }
+    __syncthreads();
+    if (!PACK) {
+        if ((int)threadIdx.x < world && cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+        return;
+    }
+    if ((int)threadIdx.x < world) {
+        at[threadIdx.x] = (unsigned long long)base[threadIdx.x] +
+                          (cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], (unsigned long long)cnt[threadIdx.x]) : 0ull);
+        cnt[threadIdx.x] = 0;                               // now the cursor inside the CTA's piece
+    }
+    __syncthreads();
+    for (int r = 0; r < world; r++) {
+#pragma unroll
+        for (int k = 0; k < ROUTE_PER; k++) {
+            const bool hit = c[k] != INT_MIN && route_hit(route_sp, n_chrom, r, c[k], s[k], e[k]);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            unsigned w0 = 0;
+            if (lane == 0) w0 = atomicAdd(&cnt[r], (unsigned)__popc(m));
+            w0 = __shfl_sync(0xffffffffu, w0, 0);
+            if (hit) {
+                const unsigned long long p = at[r] + w0 + __popc(m & ((1u << lane) - 1u));
+                triples[p * 3] = c[k];
+                triples[p * 3 + 1] = s[k];
+                triples[p * 3 + 2] = e[k];
+                if (strand_out) {
+                    const int64_t i = first + (int64_t)k * ROUTE_CTA + threadIdx.x;
+                    strand_out[p] = strand ? strand[i] : (int8_t)0;
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 rows_scatter_kernel(const double* __restrict__ src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
@@ -1159,6 +1245,64 @@ int rcp_shared_free(void* ptr) {
     if (ptr == nullptr) return RCP_OK;
     RCP_CUDA(cudaFree(ptr));
     return RCP_OK;
+}
+
+static int route_impl(bool pack, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                      const int8_t* strand, int world, int n_chrom, const int32_t* spans, int64_t* counts_host,
+                      const int64_t* offsets_host, int32_t* triples_out, int8_t* strand_out) {
+    RCP_TRY(require_ready());
+    if (n < 0 || world < 1 || world > ROUTE_MAXW || n_chrom < 1 || spans == nullptr)
+        return fail(RCP_ERR_ARG, "rcp_reads_route: bad scalar argument (1 <= world <= %d)", ROUTE_MAXW);
+    if (n > 0 && (!chrom || !start || !end)) return fail(RCP_ERR_ARG, "rcp_reads_route: NULL array");
+    const size_t sp_ints = (size_t)world * n_chrom * 2;
+    if (sp_ints * 4 > 40 * 1024) return fail(RCP_ERR_UNSUPPORTED, "rcp_reads_route: span table over 40 KB");
+    int32_t* d_span = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    int64_t* d_base = nullptr;
+    RCP_TRY(dalloc(&d_span, sp_ints));
+    RCP_TRY(dalloc(&d_cnt, (size_t)world));
+    RCP_TRY(dalloc(&d_base, (size_t)world));
+    RCP_CUDA(cudaMemcpyAsync(d_span, spans, sp_ints * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)world * 8, g_ctx.stream));
+    if (pack)
+        RCP_CUDA(cudaMemcpyAsync(d_base, offsets_host, (size_t)world * 8, cudaMemcpyHostToDevice, g_ctx.stream));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, (n + ROUTE_CTA * ROUTE_PER - 1) / (ROUTE_CTA * ROUTE_PER));
+    if (n > 0) {
+        if (pack)
+            route_kernel<true><<<grid, ROUTE_CTA, sp_ints * 4, g_ctx.stream>>>(n, chrom, start, end, strand, world,
+                                                                             n_chrom, d_span, d_cnt, d_base,
+                                                                             triples_out, strand_out);
+        else
+            route_kernel<false><<<grid, ROUTE_CTA, sp_ints * 4, g_ctx.stream>>>(n, chrom, start, end, strand, world,
+                                                                              n_chrom, d_span, d_cnt, nullptr,
+                                                                              nullptr, nullptr);
+        RCP_LAUNCHED();
+    }
+    int rc = RCP_OK;
+    if (!pack) {
+        RCP_CUDA(cudaMemcpyAsync(counts_host, d_cnt, (size_t)world * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+        RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    }
+    dfree(d_span);
+    dfree(d_cnt);
+    dfree(d_base);
+    return rc;
+}
+
+int rcp_reads_route_count(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, int world,
+                          int n_chrom, const int32_t* spans, int64_t* counts_out) {
+    if (counts_out == nullptr) return fail(RCP_ERR_ARG, "rcp_reads_route_count: counts_out is NULL");
+    return route_impl(false, n, chrom, start, end, nullptr, world, n_chrom, spans, counts_out, nullptr, nullptr,
+                      nullptr);
+}
+
+int rcp_reads_route_pack(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
+                         const int8_t* strand, int world, int n_chrom, const int32_t* spans,
+                         const int64_t* offsets, int32_t* triples_out, int8_t* strand_out) {
+    if (offsets == nullptr || (n > 0 && triples_out == nullptr))
+        return fail(RCP_ERR_ARG, "rcp_reads_route_pack: NULL argument");
+    return route_impl(true, n, chrom, start, end, strand, world, n_chrom, spans, nullptr, offsets, triples_out,
+                      strand_out);
 }
 
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,

@@ -85,6 +85,9 @@ def exchange_reads(chrom, start, end, strand, spans, group=None, filter_single=T
     if world == 1 and len(spans) == 1 and not filter_single:
         return chrom, start, end, strand       # one rank owns every region: nothing to send or drop
     dev = chrom.device
+    if dev.type == "cuda":
+        return _exchange_reads_device(chrom, start, end, strand, spans, world, group)
+    # host tensors (the gloo tests of the N > 1 logic): the same routing with torch operations
     sp = torch.as_tensor(np.ascontiguousarray(spans), device=dev)        # [world, n_chrom, 2]
     c64 = chrom.long()
     picks = []
@@ -106,6 +109,52 @@ def exchange_reads(chrom, start, end, strand, spans, group=None, filter_single=T
     if st is not None:
         got_st = torch.empty((sum(rc),), dtype=st.dtype, device=dev)
         dist.all_to_all_single(got_st, st, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return got[:, 0].contiguous(), got[:, 1].contiguous(), got[:, 2].contiguous(), got_st
+
+
+def _exchange_reads_device(chrom, start, end, strand, spans, world, group):
+    """exchange_reads on CUDA tensors: the library's routing kernels (rcp_reads_route_count /
+    _pack) count and pack the reads per destination rank -- two streaming passes over the share,
+    one host synchronisation -- then one all-to-all for the counts, one for the triples, one for
+    the strands.  The torch stream current at the call must be the library's stream."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    _lib.ensure_init()
+    L = _lib.lib
+    dev = chrom.device
+    n = int(chrom.shape[0])
+    sp = np.ascontiguousarray(np.clip(np.asarray(spans, dtype=np.int64), -2**31 + 1, 2**31 - 1), dtype=np.int32)
+    n_chrom = int(sp.shape[1])
+    chrom, start, end = chrom.contiguous(), start.contiguous(), end.contiguous()
+    strand = None if strand is None else strand.contiguous()
+    vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())      # noqa: E731
+    sp_p = sp.ctypes.data_as(C.POINTER(C.c_int32))
+    counts = np.zeros(world, dtype=np.int64)
+    _lib.check(L.rcp_reads_route_count(n, vp(chrom), vp(start), vp(end), world, n_chrom, sp_p,
+                                       counts.ctypes.data_as(C.POINTER(C.c_int64))))
+    offsets = np.ascontiguousarray(np.concatenate(([0], np.cumsum(counts)[:-1])), dtype=np.int64)
+    total = int(counts.sum())
+    triples = torch.empty((total, 3), dtype=torch.int32, device=dev)
+    st = torch.empty((total,), dtype=torch.int8, device=dev) if strand is not None else None
+    _lib.check(L.rcp_reads_route_pack(n, vp(chrom), vp(start), vp(end), vp(strand), world, n_chrom, sp_p,
+                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(triples), vp(st)))
+    if world == 1:
+        got, got_st = triples, st
+    else:
+        send_counts = torch.from_numpy(counts).to(dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        sc, rc = counts.tolist(), recv_counts.tolist()
+        got = torch.empty((sum(rc), 3), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(got, triples, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        got_st = None
+        if st is not None:
+            got_st = torch.empty((sum(rc),), dtype=torch.int8, device=dev)
+            dist.all_to_all_single(got_st, st, output_split_sizes=rc, input_split_sizes=sc, group=group)
     return got[:, 0].contiguous(), got[:, 1].contiguous(), got[:, 2].contiguous(), got_st
 
 

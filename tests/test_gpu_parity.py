@@ -1111,6 +1111,68 @@ def test_region_sharded_run_equals_the_single_gpu_matrix(gpu_auto):
     assert np.array_equal(got, np.asarray(full))
 
 
+@pytest.mark.parametrize("n_reads", [1, 2047, 50000])
+def test_read_routing_kernels_match_the_span_rule(gpu_auto, n_reads):
+    """rcp_reads_route_count / _pack (the send side of the region-sharded exchange): rank r's run
+    holds exactly the reads that meet r's spans (a boundary read goes to both neighbours, a read
+    with a bad chromosome id to rank 0), strands travel with their reads; and exchange_reads on
+    device tensors (world 1) returns the same reads as on host tensors."""
+    import torch
+    from recoup_b200 import _lib
+    from recoup_b200.sharding import exchange_reads, partition_regions, slice_spans
+    rng = np.random.default_rng(23)
+    clen = [90000, 30000, 5000]
+    chrom, s, e, st = synth_reads(rng, n_reads, clen, width=(20, 400))
+    if n_reads > 10:
+        chrom[3] = 7                                         # outside the table: rank 0 reports it
+    rc, rs, re_, rst = _regions(rng, 90, clen, [100, 1000, 3000])
+    world = 3
+    parts = partition_regions(rc, rs, re_, world)
+    spans = slice_spans(rc, rs, re_, parts, len(clen))
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (chrom, s.astype(np.int32), e.astype(np.int32), st)]
+    vp = lambda t: C.c_void_p(t.data_ptr())                  # noqa: E731
+    sp = np.ascontiguousarray(np.clip(spans, -2**31 + 1, 2**31 - 1), dtype=np.int32)
+    sp_p = sp.ctypes.data_as(C.POINTER(C.c_int32))
+    counts = np.zeros(world, dtype=np.int64)
+    L = _lib.lib
+    _lib.check(L.rcp_reads_route_count(n_reads, vp(d[0]), vp(d[1]), vp(d[2]), world, len(clen), sp_p,
+                                       counts.ctypes.data_as(C.POINTER(C.c_int64))))
+    ok = (chrom >= 0) & (chrom < len(clen))
+    cc = np.where(ok, chrom, 0)
+    want = []
+    for r in range(world):
+        m = ok & (e >= spans[r, cc, 0]) & (s <= spans[r, cc, 1])
+        if r == 0:
+            m |= ~ok
+        want.append(np.flatnonzero(m))
+    assert counts.tolist() == [len(x) for x in want]
+    offsets = np.concatenate(([0], np.cumsum(counts)[:-1])).astype(np.int64)
+    total = int(counts.sum())
+    tri = torch.full((max(total, 1), 3), -9, dtype=torch.int32, device=dev)
+    so = torch.full((max(total, 1),), -9, dtype=torch.int8, device=dev)
+    _lib.check(L.rcp_reads_route_pack(n_reads, vp(d[0]), vp(d[1]), vp(d[2]), vp(d[3]), world, len(clen), sp_p,
+                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(tri), vp(so)))
+    L.rcp_sync()
+    tri, so = tri.cpu().numpy(), so.cpu().numpy()
+    for r in range(world):
+        got = np.column_stack([tri[offsets[r]:offsets[r] + counts[r]], so[offsets[r]:offsets[r] + counts[r]]])
+        exp = np.column_stack([chrom[want[r]], s[want[r]], e[want[r]], st[want[r]]])
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], exp[np.lexsort(exp.T[::-1])])
+    # the wrapper, device tensors against host tensors (world 1: the local filter against rank 1's spans)
+    if n_reads > 10:
+        keep = ok
+        dk = [torch.from_numpy(np.ascontiguousarray(a[keep])) for a in (chrom, s.astype(np.int32), e.astype(np.int32), st)]
+        host = exchange_reads(*dk, spans[1:2])
+        stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
+        with torch.cuda.stream(stream):
+            devr = exchange_reads(*[t.to(dev) for t in dk], spans[1:2])
+        L.rcp_sync()
+        a = np.column_stack([t.cpu().numpy() for t in devr])
+        b = np.column_stack([t.numpy() for t in host])
+        assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+
+
 @pytest.mark.parametrize("ignore,filt", [(True, None), (False, None), (False, "+")])
 def test_list_masks_with_long_reads_and_the_cached_binned_index(gpu, ignore, filt):
     """GRangesList elements over a sample that mixes short reads with reads far wider than the
