@@ -62,6 +62,10 @@ def parse_args():
     ap.add_argument("--read-order", default="random", choices=["random", "coordinate"],
                     help="order of the synthetic reads: as generated (random; the default and the "
                          "harder case) or sorted by chromosome and start like a coordinate-sorted BAM")
+    ap.add_argument("--exchange", default="ce", choices=["ce", "nccl"],
+                    help="N > 1: how the row blocks reach rank 0 -- ce: every rank puts its block "
+                         "straight into rank 0's matrix (CUDA IPC mapping) with the copy engine over "
+                         "NVLink + a one-word NCCL all-reduce as the fence; nccl: dist.gather + placement")
     ap.add_argument("--path", default="auto", choices=["auto", "index", "buckets", "blocks", "split"],
                     help="rcp_set_coverage_path: how rcp_coverage finds each region's reads")
     return ap.parse_args()
@@ -629,14 +633,26 @@ def run_b200(args):
         e.set()
     gfail = []
 
+    if world > 1 and args.exchange == "ce":
+        from recoup_b200.sharding import PeerMatrix
+        # rank 0's matrix (double buffered like the blocks), mapped into every rank of the box
+        gather_box["peer"] = [PeerMatrix(R * world, ncols, dev, dst=0) for _ in range(2)]
+
     def gather_issue(k, ready):
         from recoup_b200.sharding import RowGather
         gstream.wait_event(ready)
         with torch.cuda.stream(gstream):
-            if "g" not in gather_box:       # buffers and row indices are set up once
-                gather_box["g"] = RowGather(ncols, np.arange(rank * R, (rank + 1) * R), R * world, dev,
-                                            bufs[0].dtype, dst=0, sizes=[R] * world)
-            gather_box["full"] = gather_box["g"].gather(bufs[k % 2])
+            if args.exchange == "ce":
+                pm = gather_box["peer"][k % 2]
+                pm.put(bufs[k % 2], rank * R, stream=gstream)     # copy engine, straight into place
+                pm.fence()                                          # one-word all-reduce on gstream
+                if rank == 0:
+                    gather_box["full"] = pm.as_tensor()
+            else:
+                if "g" not in gather_box:       # buffers and row indices are set up once
+                    gather_box["g"] = RowGather(ncols, np.arange(rank * R, (rank + 1) * R), R * world, dev,
+                                                bufs[0].dtype, dst=0, sizes=[R] * world)
+                gather_box["full"] = gather_box["g"].gather(bufs[k % 2])
             done = torch.cuda.Event()
             done.record(gstream)
         return done
@@ -748,6 +764,9 @@ def run_b200(args):
                     exchange_ok = False
         gq.put(None)
         gthread.join()
+        barrier()
+        for pm in gather_box.get("peer", []):
+            pm.close()
         gather_box.clear()
         barrier()
 
@@ -981,9 +1000,12 @@ def run_b200(args):
                        "candidates_per_gpu": stats.get("candidates"),
                        "parallelism": ("one GPU" if world == 1 else
                                        "%d independent replicas of the workload, one per GPU (weak scaling; "
-                                       "every rank its own reads and regions), row blocks gathered to rank 0 "
-                                       "with NCCL on a second stream; the ONE-problem region-sharded run is "
-                                       "in `strong`" % world)},
+                                       "every rank its own reads and regions), row blocks %s on a second "
+                                       "stream; the ONE-problem region-sharded run is in `strong`"
+                                       % (world, "put straight into rank 0's matrix by the copy engine over "
+                                                 "NVLink (CUDA IPC mapping), fenced by a one-word NCCL all-reduce"
+                                          if args.exchange == "ce" else
+                                          "gathered to rank 0 with NCCL (dist.gather + placement)"))},
             "stage_ms_per_step": per_step,
             "region_bins_per_s": world * R * ncols / (ms_per_step * 1e-3),
             "roofline": roof,

@@ -311,6 +311,15 @@ int rcp_matrix_quantile(const double* m, int64_t n_rows, int64_t n_cols, int64_t
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,
                      const int64_t* row_index, double* dst, int64_t ld_dst);
 
+/* Place a row block into a matrix with the COPY ENGINE (one strided 2-D copy, no SM is used):
+ * dst[i + c*ld_dst] = src[i + c*ld_src] for i < n_rows, c < n_cols.  `dst` may lie in another
+ * GPU's memory mapped with rcp_shared_open (the block then crosses NVLink straight into its place
+ * in the gathering rank's matrix -- the reference's do.call(rbind, ...), profile.R:150,208, without a
+ * gather buffer or a placement pass) or in page-locked host memory.  `stream`: a cudaStream_t, or
+ * NULL for the library's stream. */
+int rcp_rows_put(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols, double* dst,
+                 int64_t ld_dst, void* stream);
+
 /* Region-sharded runs (every GPU owns a region slice plus its overlapping reads; the
  * reference's analogue is the split of the regions over mclapply workers, coverage.R:148-154,
  * each of which subsets the reads with findOverlaps).  A rank holds an arbitrary share of the

@@ -1247,6 +1247,18 @@ int rcp_shared_free(void* ptr) {
     return RCP_OK;
 }
 
+int rcp_rows_put(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols, double* dst,
+                 int64_t ld_dst, void* stream) {
+    RCP_TRY(require_ready());
+    if (n_rows <= 0 || n_cols <= 0) return RCP_OK;
+    if (src == nullptr || dst == nullptr || ld_src < n_rows || ld_dst < n_rows)
+        return fail(RCP_ERR_ARG, "rcp_rows_put: bad argument");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
+    RCP_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)n_rows * 8, (size_t)n_cols,
+                               cudaMemcpyDefault, st));
+    return RCP_OK;
+}
+
 static int route_impl(bool pack, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                       const int8_t* strand, int world, int n_chrom, const int32_t* spans, int64_t* counts_host,
                       const int64_t* offsets_host, int32_t* triples_out, int8_t* strand_out) {

@@ -274,7 +274,24 @@ class PeerMatrix:
         """device pointer of element (first_row, 0): pass it as `out` with ld = n_total"""
         return self.base + 8 * int(first_row)
 
+    def put(self, local, first_row, stream=None):
+        """Copy-engine exchange: the block `local` ([n_cols, n_local] torch tensor = column-major
+        n_local x n_cols) goes to rows [first_row, first_row + n_local) of the matrix on `dst` with
+        one strided copy over NVLink (rcp_rows_put) on `stream` (a torch stream; default: the
+        current one).  No SM of either GPU is used; follow with fence()."""
+        import ctypes as C
+
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(local.device)
+        n_cols, n_local = int(local.shape[0]), int(local.shape[1])
+        assert n_cols == self.n_cols and local.stride(1) == 1
+        self._lib.check(self._lib.lib.rcp_rows_put(C.c_void_p(local.data_ptr()), int(local.stride(0)), n_local,
+                                                   n_cols, C.c_void_p(self.ptr_for(first_row)), self.n_total,
+                                                   C.c_void_p(st.cuda_stream)))
+
     def fence(self):
+        """Orders every rank's stores / puts before the matrix is read on `dst` (a one-word
+        all-reduce on the current torch stream)."""
         import torch.distributed as dist
         dist.all_reduce(self._flag, group=self.group)
 
