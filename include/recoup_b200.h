@@ -327,15 +327,16 @@ int rcp_rows_put(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_co
  * [lo, hi] that rank r's slice covers on chromosome c (lo > hi: nothing).  A read goes to every
  * rank whose interval it overlaps; a read with a chromosome id outside [0, n_chrom) goes to rank
  * 0, whose rcp_reads_load reports it.  _count: counts_out[r] (host) = reads bound for rank r (one
- * host synchronisation).  _pack: writes them as (chrom, start, end) int32 triples and strand bytes
- * (device; strand / strand_out may be NULL), rank r's run starting at triple offsets[r] (host:
- * the exclusive prefix sum of the counts) -- the send buffer of one all-to-all.  The order inside
- * a run is unspecified (coverage does not depend on it). */
+ * host synchronisation).  _pack: writes them into four device arrays (chrom, start, end int32,
+ * strand int8; strand / strand_out may be NULL), rank r's run starting at offsets[r] (host: the
+ * exclusive prefix sum of the counts) in each -- the send buffers of the all-to-all.  The order
+ * inside a run is unspecified (coverage does not depend on it). */
 int rcp_reads_route_count(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, int world,
                           int n_chrom, const int32_t* spans, int64_t* counts_out /* world, host */);
 int rcp_reads_route_pack(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                          const int8_t* strand, int world, int n_chrom, const int32_t* spans,
-                         const int64_t* offsets /* world, host */, int32_t* triples_out, int8_t* strand_out);
+                         const int64_t* offsets /* world, host */, int32_t* chrom_out, int32_t* start_out,
+                         int32_t* end_out, int8_t* strand_out);
 
 /* Device memory that the other processes of this box (one per GPU) can map, so that every rank's
  * rcp_profile_matrix / rcp_bin_matrix / rcp_base_matrix writes its row block STRAIGHT into the

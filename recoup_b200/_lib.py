@@ -59,7 +59,8 @@ SIGNATURES = {
     "rcp_coverage_path_info": (C.c_int, [C.c_int, _ip, _i64p]),
     "rcp_rows_put": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _vp]),
     "rcp_reads_route_count": (C.c_int, [C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int, _i32p, _i64p]),
-    "rcp_reads_route_pack": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _i32p, _i64p, _vp, _vp]),
+    "rcp_reads_route_pack": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _i32p, _i64p, _vp, _vp, _vp,
+                                       _vp]),
     "rcp_reads_load_width": (C.c_int, [C.c_int64, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _i64p,
                                        C.c_int, C.c_int, _ip]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,

@@ -298,16 +298,16 @@ __device__ __forceinline__ bool route_hit(const int32_t* sp, int n_chrom, int r,
     return e >= lo && s <= hi;
 }
 
-// PACK = false: counts[r] += reads for rank r.  PACK = true: the reads leave as (chrom, start, end)
-// triples + strand bytes, rank r's run starting at base[r]; a CTA reserves its share of every run
+// PACK = false: counts[r] += reads for rank r.  PACK = true: the reads leave as four arrays (chrom,
+// start, end, strand), rank r's run starting at base[r] in each; a CTA reserves its share of every run
 // with one atomic per rank, so a run is written in CTA-sized contiguous pieces.
 template <bool PACK>
 __global__ void __launch_bounds__(ROUTE_CTA)
 route_kernel(int64_t n, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
              const int32_t* __restrict__ end, const int8_t* __restrict__ strand, int world, int n_chrom,
              const int32_t* __restrict__ span, unsigned long long* __restrict__ counts /* [world] */,
-             const int64_t* __restrict__ base /* [world] */, int32_t* __restrict__ triples,
-             int8_t* __restrict__ strand_out) {
+             const int64_t* __restrict__ base /* [world] */, int32_t* __restrict__ chrom_out,
+             int32_t* __restrict__ start_out, int32_t* __restrict__ end_out, int8_t* __restrict__ strand_out) {
     extern __shared__ int32_t route_sp[];                   // the span table
     __shared__ unsigned int cnt[ROUTE_MAXW];
     __shared__ unsigned long long at[ROUTE_MAXW];
@@ -357,9 +357,9 @@ route_kernel(int64_t n, const int32_t* __restrict__ chrom, const int32_t* __rest
             w0 = __shfl_sync(0xffffffffu, w0, 0);
             if (hit) {
                 const unsigned long long p = at[r] + w0 + __popc(m & ((1u << lane) - 1u));
-                triples[p * 3] = c[k];
-                triples[p * 3 + 1] = s[k];
-                triples[p * 3 + 2] = e[k];
+                chrom_out[p] = c[k];
+                start_out[p] = s[k];
+                end_out[p] = e[k];
                 if (strand_out) {
                     const int64_t i = first + (int64_t)k * ROUTE_CTA + threadIdx.x;
                     strand_out[p] = strand ? strand[i] : (int8_t)0;
@@ -1261,7 +1261,8 @@ int rcp_rows_put(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_co
 
 static int route_impl(bool pack, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                       const int8_t* strand, int world, int n_chrom, const int32_t* spans, int64_t* counts_host,
-                      const int64_t* offsets_host, int32_t* triples_out, int8_t* strand_out) {
+                      const int64_t* offsets_host, int32_t* chrom_out, int32_t* start_out, int32_t* end_out,
+                      int8_t* strand_out) {
     RCP_TRY(require_ready());
     if (n < 0 || world < 1 || world > ROUTE_MAXW || n_chrom < 1 || spans == nullptr)
         return fail(RCP_ERR_ARG, "rcp_reads_route: bad scalar argument (1 <= world <= %d)", ROUTE_MAXW);
@@ -1282,12 +1283,12 @@ static int route_impl(bool pack, int64_t n, const int32_t* chrom, const int32_t*
     if (n > 0) {
         if (pack)
             route_kernel<true><<<grid, ROUTE_CTA, sp_ints * 4, g_ctx.stream>>>(n, chrom, start, end, strand, world,
-                                                                             n_chrom, d_span, d_cnt, d_base,
-                                                                             triples_out, strand_out);
+                                                                             n_chrom, d_span, d_cnt, d_base, chrom_out,
+                                                                             start_out, end_out, strand_out);
         else
             route_kernel<false><<<grid, ROUTE_CTA, sp_ints * 4, g_ctx.stream>>>(n, chrom, start, end, strand, world,
                                                                               n_chrom, d_span, d_cnt, nullptr,
-                                                                              nullptr, nullptr);
+                                                                              nullptr, nullptr, nullptr, nullptr);
         RCP_LAUNCHED();
     }
     int rc = RCP_OK;
@@ -1305,16 +1306,17 @@ int rcp_reads_route_count(int64_t n, const int32_t* chrom, const int32_t* start,
                           int n_chrom, const int32_t* spans, int64_t* counts_out) {
     if (counts_out == nullptr) return fail(RCP_ERR_ARG, "rcp_reads_route_count: counts_out is NULL");
     return route_impl(false, n, chrom, start, end, nullptr, world, n_chrom, spans, counts_out, nullptr, nullptr,
-                      nullptr);
+                      nullptr, nullptr, nullptr);
 }
 
 int rcp_reads_route_pack(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                          const int8_t* strand, int world, int n_chrom, const int32_t* spans,
-                         const int64_t* offsets, int32_t* triples_out, int8_t* strand_out) {
-    if (offsets == nullptr || (n > 0 && triples_out == nullptr))
+                         const int64_t* offsets, int32_t* chrom_out, int32_t* start_out, int32_t* end_out,
+                         int8_t* strand_out) {
+    if (offsets == nullptr || (n > 0 && (chrom_out == nullptr || start_out == nullptr || end_out == nullptr)))
         return fail(RCP_ERR_ARG, "rcp_reads_route_pack: NULL argument");
-    return route_impl(true, n, chrom, start, end, strand, world, n_chrom, spans, nullptr, offsets, triples_out,
-                      strand_out);
+    return route_impl(true, n, chrom, start, end, strand, world, n_chrom, spans, nullptr, offsets, chrom_out,
+                      start_out, end_out, strand_out);
 }
 
 int rcp_rows_scatter(const double* src, int64_t ld_src, int64_t n_rows, int64_t n_cols,

@@ -1206,33 +1206,50 @@ sp_ltile_kernel(int64_t T, const SpDesc* __restrict__ desc, ListPlan lp, const u
             const uint32_t ps = s + (uint32_t)(k0 - xo), pe = s + (uint32_t)(k1 - 1 - xo);   // genomic piece
             const uint32_t first = ps >= max_w ? ps - max_w + 1u : 0u;
             const uint32_t c0 = __ldg(boff + (first >> SUB_SHIFT)), c1 = __ldg(boff + (pe >> SUB_SHIFT) + 1);
-            for (uint32_t i = c0 + lane; i < c1; i += 32) {
-                const uint32_t word = __ldg(cand + i);
-                const int rel = ((int)((word - (ps & pmask)) << sh)) >> sh;
-                const uint32_t wd = word >> (STRANDED ? P + 2 : P);
-                if (wd == 0u) continue;
-                const int64_t rs64 = (int64_t)ps + rel;
-                const uint32_t rs = (uint32_t)rs64, re1 = rs + wd;
-                if (!(rs <= pe && re1 > ps)) continue;                     // does not reach the piece
-                int rst = 0;
-                if (STRANDED) {
-                    const uint32_t cls = (word >> P) & 3u;
-                    rst = cls == 0u ? 1 : (cls == 1u ? -1 : 0);
+            // candidates 128 at a time: the four loads of a lane are in flight together, and the
+            // next batch is requested before this one is used
+            auto fetch = [&](uint32_t i0, uint32_t* wv) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t i = i0 + (uint32_t)k * 32u + lane;
+                    wv[k] = i < c1 ? __ldg(cand + i) : 0u;          // 0: width 0, skipped below
                 }
-                if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
-                const int mult = sp_multiplicity(lp, a, b, q, simple, rs, re1, rst, ignore_strand, strand_filter);
-                if (mult == 0) continue;
-                hit = true;
-                // +mult on the covered part of the piece, in output order
-                const int ka = k0 + (int)(max(rs, ps) - ps) - t0;
-                const int kb1 = k0 + (int)(min(re1 - 1u, pe) - ps) + 1 - t0;    // may equal tlen
-                if (!rev) {
-                    atomicAdd(diff + ka, mult);
-                    if (kb1 < tlen) atomicSub(diff + kb1, mult);
-                } else {
-                    atomicAdd(diff + (tlen - kb1), mult);
-                    if (ka > 0) atomicSub(diff + (tlen - ka), mult);
+            };
+            uint32_t wv[4], wn[4];
+            if (c0 < c1) fetch(c0, wv);
+            for (uint32_t i0 = c0; i0 < c1; i0 += 128) {
+                if (i0 + 128 < c1) fetch(i0 + 128, wn);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t word = wv[k];
+                    const int rel = ((int)((word - (ps & pmask)) << sh)) >> sh;
+                    const uint32_t wd = word >> (STRANDED ? P + 2 : P);
+                    if (wd == 0u) continue;
+                    const int64_t rs64 = (int64_t)ps + rel;
+                    const uint32_t rs = (uint32_t)rs64, re1 = rs + wd;
+                    if (!(rs <= pe && re1 > ps)) continue;                     // does not reach the piece
+                    int rst = 0;
+                    if (STRANDED) {
+                        const uint32_t cls = (word >> P) & 3u;
+                        rst = cls == 0u ? 1 : (cls == 1u ? -1 : 0);
+                    }
+                    if (strand_filter != RCP_STRAND_ANY && rst != strand_filter) continue;
+                    const int mult = sp_multiplicity(lp, a, b, q, simple, rs, re1, rst, ignore_strand, strand_filter);
+                    if (mult == 0) continue;
+                    hit = true;
+                    // +mult on the covered part of the piece, in output order
+                    const int ka = k0 + (int)(max(rs, ps) - ps) - t0;
+                    const int kb1 = k0 + (int)(min(re1 - 1u, pe) - ps) + 1 - t0;    // may equal tlen
+                    if (!rev) {
+                        atomicAdd(diff + ka, mult);
+                        if (kb1 < tlen) atomicSub(diff + kb1, mult);
+                    } else {
+                        atomicAdd(diff + (tlen - kb1), mult);
+                        if (ka > 0) atomicSub(diff + (tlen - ka), mult);
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < 4; k++) wv[k] = wn[k];
             }
         }
         if (lg.n) {             // the reads kept out of the binned index: whole reads against the element

@@ -498,15 +498,20 @@ bin_mean_kernel(BinArgs p, const BinDesc* __restrict__ desc, int64_t R, int buf_
 // once per bin.  Bin i has bsz + [rank[i] <= dif] elements (util.R:74-80).
 constexpr int WIDE_RUN = 16;
 
-__global__ void __launch_bounds__(BT)
+__global__ void __launch_bounds__(BT, 3)
 bin_wide_kernel(BinArgs p, const BinDesc* __restrict__ desc, const int32_t* __restrict__ long_list,
-                const unsigned int* __restrict__ long_count) {
+                unsigned int* __restrict__ long_count) {
     const int lane = threadIdx.x & 31;
     const int n = p.n;
     const int runs = (n + WIDE_RUN - 1) / WIDE_RUN;
     const int64_t units = (int64_t)(*long_count) * runs;
-    const int64_t wstep = (int64_t)gridDim.x * BWARPS;
-    for (int64_t u = (int64_t)blockIdx.x * BWARPS + (threadIdx.x >> 5); u < units; u += wstep) {
+    // units are handed out by a counter (long_count[1]): gene lengths are heavy-tailed, and a fixed
+    // stride would leave the kernel waiting for the warp that drew the longest regions
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(reinterpret_cast<unsigned long long*>(long_count + 2), 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if ((int64_t)u >= units) break;
         const int64_t r = long_list[u / runs];
         const int i0 = (int)(u % runs) * WIDE_RUN, i1 = min(n, i0 + WIDE_RUN);
         const BinDesc d = load_bin_desc(desc + r);
@@ -527,14 +532,19 @@ bin_wide_kernel(BinArgs p, const BinDesc* __restrict__ desc, const int32_t* __re
         int k = i0, b0 = lo, nxt = lo + bsz + (int)(extra & 1u);
         long long acc = 0;
         constexpr int UW = 4;
-        for (int q0 = lo & ~3; q0 < hi; q0 += 128 * UW) {
-            int4 x[UW];
+        // the rows of the NEXT trip are requested before this trip's rows are summed
+        auto fetch = [&](int q0, int4* x) {
 #pragma unroll
             for (int v = 0; v < UW; v++) {
                 const int q = q0 + v * 128 + lane * 4;
                 x[v] = make_int4(0, 0, 0, 0);
                 if (q < hi) x[v] = __ldcs(reinterpret_cast<const int4*>(src + q));
             }
+        };
+        int4 x[UW], y[UW];
+        fetch(lo & ~3, x);
+        for (int q0 = lo & ~3; q0 < hi; q0 += 128 * UW) {
+            if (q0 + 128 * UW < hi) fetch(q0 + 128 * UW, y);
 #pragma unroll
             for (int v = 0; v < UW; v++) {
                 const int row = q0 + v * 128;
@@ -564,6 +574,8 @@ bin_wide_kernel(BinArgs p, const BinDesc* __restrict__ desc, const int32_t* __re
                     acc += tot;
                 }
             }
+#pragma unroll
+            for (int v = 0; v < UW; v++) x[v] = y[v];
         }
     }
 }
@@ -915,8 +927,8 @@ int bin_matrix_device(const Coverage& cv, int where, int f1, int f2, int n_bins,
             }
         }
         RCP_TRY(dalloc(&long_list, (size_t)R));
-        RCP_TRY(dalloc(&long_count, 1));
-        RCP_CUDA(cudaMemsetAsync(long_count, 0, sizeof(unsigned int), g_ctx.stream));
+        RCP_TRY(dalloc(&long_count, 4));        // [0] regions in the list, [2..3] unit counter of bin_wide_kernel
+        RCP_CUDA(cudaMemsetAsync(long_count, 0, 4 * sizeof(unsigned int), g_ctx.stream));
         bin_desc_kernel<<<(unsigned)((R + CTA - 1) / CTA), CTA, 0, g_ctx.stream>>>(
             R, cv.off, cv.len, cv.is_null, where, f1, f2, n_bins, buf_ints, d_desc, long_list, long_count);
         RCP_LAUNCHED();

@@ -115,8 +115,8 @@ def exchange_reads(chrom, start, end, strand, spans, group=None, filter_single=T
 def _exchange_reads_device(chrom, start, end, strand, spans, world, group):
     """exchange_reads on CUDA tensors: the library's routing kernels (rcp_reads_route_count /
     _pack) count and pack the reads per destination rank -- two streaming passes over the share,
-    one host synchronisation -- then one all-to-all for the counts, one for the triples, one for
-    the strands.  The torch stream current at the call must be the library's stream."""
+    one host synchronisation -- then one all-to-all for the counts and one per array (no
+    interleaving on the send side, nothing to take apart on the receive side).  The torch stream current at the call must be the library's stream."""
     import ctypes as C
 
     import torch
@@ -138,24 +138,23 @@ def _exchange_reads_device(chrom, start, end, strand, spans, world, group):
                                        counts.ctypes.data_as(C.POINTER(C.c_int64))))
     offsets = np.ascontiguousarray(np.concatenate(([0], np.cumsum(counts)[:-1])), dtype=np.int64)
     total = int(counts.sum())
-    triples = torch.empty((total, 3), dtype=torch.int32, device=dev)
+    send = [torch.empty((total,), dtype=torch.int32, device=dev) for _ in range(3)]
     st = torch.empty((total,), dtype=torch.int8, device=dev) if strand is not None else None
     _lib.check(L.rcp_reads_route_pack(n, vp(chrom), vp(start), vp(end), vp(strand), world, n_chrom, sp_p,
-                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(triples), vp(st)))
+                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(send[0]), vp(send[1]),
+                                      vp(send[2]), vp(st)))
     if world == 1:
-        got, got_st = triples, st
-    else:
-        send_counts = torch.from_numpy(counts).to(dev)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=group)
-        sc, rc = counts.tolist(), recv_counts.tolist()
-        got = torch.empty((sum(rc), 3), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(got, triples, output_split_sizes=rc, input_split_sizes=sc, group=group)
-        got_st = None
-        if st is not None:
-            got_st = torch.empty((sum(rc),), dtype=torch.int8, device=dev)
-            dist.all_to_all_single(got_st, st, output_split_sizes=rc, input_split_sizes=sc, group=group)
-    return got[:, 0].contiguous(), got[:, 1].contiguous(), got[:, 2].contiguous(), got_st
+        return send[0], send[1], send[2], st
+    send_counts = torch.from_numpy(counts).to(dev)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = counts.tolist(), recv_counts.tolist()
+    got = []
+    for t in send + ([st] if st is not None else []):
+        r = torch.empty((sum(rc),), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(r, t, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        got.append(r)
+    return got[0], got[1], got[2], (got[3] if st is not None else None)
 
 
 class RowGather:

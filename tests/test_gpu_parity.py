@@ -1149,12 +1149,13 @@ def test_read_routing_kernels_match_the_span_rule(gpu_auto, n_reads):
     assert counts.tolist() == [len(x) for x in want]
     offsets = np.concatenate(([0], np.cumsum(counts)[:-1])).astype(np.int64)
     total = int(counts.sum())
-    tri = torch.full((max(total, 1), 3), -9, dtype=torch.int32, device=dev)
+    outs = [torch.full((max(total, 1),), -9, dtype=torch.int32, device=dev) for _ in range(3)]
     so = torch.full((max(total, 1),), -9, dtype=torch.int8, device=dev)
     _lib.check(L.rcp_reads_route_pack(n_reads, vp(d[0]), vp(d[1]), vp(d[2]), vp(d[3]), world, len(clen), sp_p,
-                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(tri), vp(so)))
+                                      offsets.ctypes.data_as(C.POINTER(C.c_int64)), vp(outs[0]), vp(outs[1]),
+                                      vp(outs[2]), vp(so)))
     L.rcp_sync()
-    tri, so = tri.cpu().numpy(), so.cpu().numpy()
+    tri, so = np.column_stack([o.cpu().numpy() for o in outs]), so.cpu().numpy()
     for r in range(world):
         got = np.column_stack([tri[offsets[r]:offsets[r] + counts[r]], so[offsets[r]:offsets[r] + counts[r]]])
         exp = np.column_stack([chrom[want[r]], s[want[r]], e[want[r]], st[want[r]]])
