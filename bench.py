@@ -966,10 +966,18 @@ def run_b200(args):
         }
         stage_roof, per_step = stage_roofline(stage, args.steps, N, R, ncols, total_len, peak)
         # measured DRAM traffic per launch (ncu --set full of this round's kernels), keyed by stage
+        # (a figure is used only while the source file of its kernel still has the hash recorded
+        # with the capture -- tools/make_traffic.py; a stale file reads as null, never as a number)
         traffic = {}
         tpath = os.path.join(ROOT, "profiles", "r02_traffic_C2.json")
         if headline and os.path.exists(tpath):
-            traffic = json.load(open(tpath))
+            import hashlib
+            tj = json.load(open(tpath))
+            for stage_name, fname in tj.get("file_of", {}).items():
+                src = os.path.join(ROOT, "recoup_b200", "csrc", fname)
+                if (stage_name in tj and os.path.exists(src) and
+                        hashlib.sha256(open(src, "rb").read()).hexdigest() == tj["source_hash"].get(fname)):
+                    traffic[stage_name] = tj[stage_name]
         own = {k: v for k, v in stage.items() if k in alg_kernel}
         dom = max(own, key=lambda k: own[k][0] * own[k][1]) if own else None
         roof = None

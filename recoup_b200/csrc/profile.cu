@@ -505,6 +505,7 @@ bin_wide_kernel(BinArgs p, const BinDesc* __restrict__ desc, const int32_t* __re
     const int n = p.n;
     const int runs = (n + WIDE_RUN - 1) / WIDE_RUN;
     const int64_t units = (int64_t)(*long_count) * runs;
+    if (units == 0) return;                 // no such region: not a single atomic
     // units are handed out by a counter (long_count[1]): gene lengths are heavy-tailed, and a fixed
     // stride would leave the kernel waiting for the warp that drew the longest regions
     for (;;) {

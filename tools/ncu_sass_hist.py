@@ -30,5 +30,5 @@ for r in rows:
     tots += s
     n += 1
 print("SASS instructions %d, executed %d, stall samples %d" % (n, tot, tots))
-for op, k in c.most_common(28):
+for op, k in c.most_common(int(sys.argv[3]) if len(sys.argv) > 3 else 28):
     print("%-10s %12d %5.1f%%   stall %5.1f%%" % (op, k, 100.0 * k / tot, 100.0 * cs[op] / max(tots, 1)))
