@@ -661,34 +661,27 @@ struct LongIdx {
     const uint32_t* maxe1;   // running max of e1
 };
 
-// CTA c owns the reads [c * per, (c + 1) * per): it counts its long reads, and (after an exclusive
-// prefix over the CTAs) writes them from its own base -- no global atomic, deterministic order.
+// CTA c owns LONG_PER consecutive reads: it counts its long reads, reserves their places with ONE
+// global atomic, and writes them (the second look at the reads comes from L1 / L2).  The total is
+// known beforehand (the map kernel counts them), the order is settled by the sort that follows.
+constexpr int LONG_PER = CTA * 16;
 __global__ void __launch_bounds__(CTA)
-sp_long_count_kernel(int64_t n, int64_t per, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
-                     uint32_t max_pack_w, uint32_t* __restrict__ per_cta) {
-    __shared__ unsigned wsum[WARPS];
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+sp_long_collect_kernel(int64_t n, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
+                       uint32_t max_pack_w, unsigned int* __restrict__ cursor_g, uint32_t cap,
+                       uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    __shared__ unsigned cnt, cursor;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t lo = (int64_t)blockIdx.x * LONG_PER, hi = min(n, lo + LONG_PER);
     unsigned c = 0;
     for (int64_t i = lo + threadIdx.x; i < hi; i += CTA) c += (e1[i] - s[i] > max_pack_w) && (e1[i] > s[i]);
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    if (lane == 0 && c) atomicAdd(&cnt, c);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = 0;
-        for (int w = 0; w < WARPS; w++) t += wsum[w];
-        per_cta[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(CTA)
-sp_long_collect_kernel(int64_t n, int64_t per, const uint32_t* __restrict__ s, const uint32_t* __restrict__ e1,
-                       uint32_t max_pack_w, const uint32_t* __restrict__ base, uint32_t* __restrict__ keys,
-                       uint32_t* __restrict__ idx) {
-    __shared__ unsigned cursor;
-    if (threadIdx.x == 0) cursor = base[blockIdx.x];
+    if (cnt == 0) return;                                   // (uniform: read after the barrier)
+    if (threadIdx.x == 0) cursor = atomicAdd(cursor_g, cnt);
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
     for (int64_t b0 = lo + (threadIdx.x & ~31u); b0 < hi; b0 += CTA) {        // warp-uniform trip count
         const int64_t i = b0 + lane;
         const bool is = i < hi && e1[i] - s[i] > max_pack_w && e1[i] > s[i];
@@ -697,7 +690,7 @@ sp_long_collect_kernel(int64_t n, int64_t per, const uint32_t* __restrict__ s, c
         unsigned k = 0;
         if (lane == 0) k = atomicAdd(&cursor, (unsigned)__popc(m));        // shared memory
         k = __shfl_sync(0xffffffffu, k, 0) + __popc(m & ((1u << lane) - 1u));
-        if (is) {
+        if (is && k < cap) {
             keys[k] = s[i];
             idx[k] = (uint32_t)i;
         }
@@ -1468,32 +1461,25 @@ static int reads_build_binned(ReadsIdx& rd) {
     const uint32_t max_pack_w = std::min<uint32_t>((1u << wbits) - 1u, 8191u);
     rd.bn_max_pack_w = max_pack_w;
     if (rd.max_width > max_pack_w) {
-        const int n_cta = g_ctx.sm_count * 8;
-        const int64_t per = (rd.n + n_cta - 1) / n_cta;
-        uint32_t* d_cnt = nullptr;          // per-CTA counts, then their exclusive prefix (+ the total)
-        RCP_TRY(dalloc(&d_cnt, (size_t)n_cta + 1));
-        sp_long_count_kernel<<<n_cta, CTA, 0, g_ctx.stream>>>(rd.n, per, rd.g_start, rd.g_end1, max_pack_w, d_cnt);
-        RCP_LAUNCHED();
-        RCP_TRY(exclusive_scan_u32(d_cnt, d_cnt, n_cta, d_cnt + n_cta));
-        uint32_t h_cnt = 0;
-        const FetchItem it[1] = {{d_cnt + n_cta, &h_cnt, 4}};
-        RCP_TRY(fetch_and_sync(it, 1));
-        dbg.lap("  long: count");
+        // how many: counted by the map kernel when the threshold it was given is this one
+        // (a stranded handle, or a strandless one: the same rule on both sides)
+        if (rd.long_thr != max_pack_w) return RCP_SPLIT_NOT_APPLICABLE;
         // a sample made of long reads is not what this index is for
-        if ((int64_t)h_cnt > rd.n / 8) {
-            dfree(d_cnt);
-            return RCP_SPLIT_NOT_APPLICABLE;
-        }
-        const size_t n = (size_t)h_cnt;
+        if (rd.n_long > rd.n / 8) return RCP_SPLIT_NOT_APPLICABLE;
+        const size_t n = (size_t)rd.n_long;
         uint32_t* idx = nullptr;
+        unsigned int* d_cur = nullptr;
+        RCP_TRY(dalloc(&d_cur, 1));
+        RCP_CUDA(cudaMemsetAsync(d_cur, 0, 4, g_ctx.stream));
         RCP_TRY(dalloc(&rd.ln_xs, n));
         RCP_TRY(dalloc(&rd.ln_e1, n));
         RCP_TRY(dalloc(&rd.ln_maxe1, n));
         if (rd.d_strand) RCP_TRY(dalloc(&rd.ln_st, n));
         RCP_TRY(dalloc(&idx, n));
-        sp_long_collect_kernel<<<n_cta, CTA, 0, g_ctx.stream>>>(rd.n, per, rd.g_start, rd.g_end1, max_pack_w, d_cnt,
-                                                                rd.ln_xs, idx);
+        sp_long_collect_kernel<<<(unsigned)blocks_for(rd.n, LONG_PER), CTA, 0, g_ctx.stream>>>(
+            rd.n, rd.g_start, rd.g_end1, max_pack_w, d_cur, (uint32_t)n, rd.ln_xs, idx);
         RCP_LAUNCHED();
+        dfree(d_cur);
         dbg.lap("  long: collect");
         RCP_TRY(sort_pairs_u32(rd.ln_xs, idx, (int64_t)n, rd.key_bits));
         dbg.lap("  long: sort");
@@ -1505,7 +1491,6 @@ static int reads_build_binned(ReadsIdx& rd) {
         RCP_TRY(running_max_u32_device(rd.ln_e1, rd.ln_maxe1, (int64_t)n));
         rd.ln_n = (int64_t)n;
         dfree(idx);
-        dfree(d_cnt);
         dbg.lap("binned: long-read list");
     }
     Arena K, B, Tb;

@@ -61,12 +61,13 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
                        const int8_t* __restrict__ strand, const uint32_t* __restrict__ chrom_off,
                        const int64_t* __restrict__ chrom_len, int n_chrom, int frag_len,
                        int fixed_width /* end == nullptr: every read is [start, start + fixed_width - 1] */,
+                       uint32_t long_thr /* reads wider than this are counted in exc.count[2] */,
                        uint32_t* __restrict__ g_start, uint32_t* __restrict__ g_end1,
                        uint32_t* __restrict__ xs_out, int8_t* __restrict__ strand_out,
                        unsigned int* __restrict__ err, unsigned long long* __restrict__ cls_count,
                        ExcBuf exc) {
     unsigned int my_err = 0;
-    unsigned int np = 0, nm = 0, ns = 0, wmax = 0;
+    unsigned int np = 0, nm = 0, ns = 0, wmax = 0, nlong = 0;
     bool exc_full = false;
     // candidate common width: the fragment length, else the width of read 0
     uint32_t w = (uint32_t)frag_len;
@@ -85,6 +86,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         *ge1 = 0;
         if (map_read(c, s, e, st, n_chrom, chrom_off, chrom_len, frag_len, gs, ge1, &my_err)) {
             wmax = max(wmax, *ge1 - *gs);
+            nlong += (*ge1 - *gs > long_thr);
             // reads of another width: recorded until the buffer overflows (then uniform-width
             // mode is abandoned anyway and the single counter must not become a hot spot)
             if (*ge1 - *gs != w && !exc_full) {
@@ -138,8 +140,8 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         if (strand_out) strand_out[i] = sgn(st);
     }
     // block-level reduction of the three strand counters and the error mask
-    __shared__ unsigned int sh[5];
-    if (threadIdx.x < 5) sh[threadIdx.x] = 0;
+    __shared__ unsigned int sh[6];
+    if (threadIdx.x < 6) sh[threadIdx.x] = 0;
     __syncthreads();
     for (int d = 16; d > 0; d >>= 1) {
         np += __shfl_xor_sync(0xffffffffu, np, d);
@@ -147,8 +149,10 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         ns += __shfl_xor_sync(0xffffffffu, ns, d);
         my_err |= __shfl_xor_sync(0xffffffffu, my_err, d);
         wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+        nlong += __shfl_xor_sync(0xffffffffu, nlong, d);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (nlong) atomicAdd(&sh[5], nlong);
         atomicAdd(&sh[0], np);
         atomicAdd(&sh[1], nm);
         atomicAdd(&sh[2], ns);
@@ -162,6 +166,7 @@ reads_to_global_kernel(int64_t n, const int32_t* __restrict__ chrom,
         if (sh[2]) atomicAdd(&cls_count[2], (unsigned long long)sh[2]);
         if (sh[3]) atomicOr(err, sh[3]);
         if (sh[4]) atomicMax(&cls_count[3], (unsigned long long)sh[4]);
+        if (sh[5]) atomicAdd(exc.count + 2, sh[5]);
     }
 }
 
@@ -585,13 +590,17 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     if (r.has_strand) RCP_TRY(dalloc(&r.d_strand, (size_t)n));
     unsigned int* d_err = nullptr;
     unsigned long long* d_cnt = nullptr;
-    unsigned int* d_w = nullptr;    // [0] exception count, [1] candidate width
+    unsigned int* d_w = nullptr;    // [0] exception count, [1] candidate width, [2] reads wider than long_thr
     RCP_TRY(dalloc(&d_err, 1));
     RCP_TRY(dalloc(&d_cnt, 4));
-    RCP_TRY(dalloc(&d_w, 2));
+    RCP_TRY(dalloc(&d_w, 4));
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), g_ctx.stream));
-    RCP_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(unsigned int), g_ctx.stream));
+    RCP_CUDA(cudaMemsetAsync(d_w, 0, 4 * sizeof(unsigned int), g_ctx.stream));
+    {   // the widest read the split path's packed word holds for this genome (coverage_split.cu)
+        const int wbits = 32 - split_position_bits((int64_t)r.chrom_off[(size_t)n_chrom]) - (r.has_strand ? 2 : 0);
+        r.long_thr = wbits >= 7 ? std::min<uint32_t>((1u << wbits) - 1u, 8191u) : 0xffffffffu;
+    }
     uint32_t* run_first = nullptr;      // exclusive scan of the run lengths + their total
     if (rle) {
         StageTimer t(ST_INDEX_MAP);
@@ -629,7 +638,8 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
         const unsigned grid = grid_for(vec ? (n + 3) / 4 : n);
         auto launch = [&](auto kern) {
             kern<<<grid, TPB, 0, g_ctx.stream>>>(n, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, r.d_chrom_off,
-                                                 r.d_chrom_len, n_chrom, frag_len, fixed_width, r.g_start, r.g_end1,
+                                                 r.d_chrom_len, n_chrom, frag_len, fixed_width, r.long_thr, r.g_start,
+                                                 r.g_end1,
                                                  r.cls[CLS_ALL].xs, r.d_strand, d_err, d_cnt, exc);
         };
         if (d_end.ptr) {
@@ -664,7 +674,7 @@ int reads_pending_items(ReadsIdx& r, FetchItem* items, int* n) {
     if (!r.pending) return RCP_OK;
     items[(*n)++] = {r.pd_err, &r.h_err, 4};
     items[(*n)++] = {r.pd_cnt, r.h_cnt, 32};
-    items[(*n)++] = {r.pd_w, r.h_w, 8};
+    items[(*n)++] = {r.pd_w, r.h_w, 16};
     if (r.pd_rle) items[(*n)++] = {r.pd_run_total, &r.h_total, 4};
     return RCP_OK;
 }
@@ -715,6 +725,7 @@ int reads_finish(ReadsIdx& r) {
     r.cls[CLS_MINUS].n = (int64_t)r.h_cnt[1];
     r.cls[CLS_STAR].n = (int64_t)r.h_cnt[2];
     r.max_width = (uint32_t)r.h_cnt[3];
+    r.n_long = (int64_t)r.h_w[2];
     if (r.pd_eager_index) RCP_TRY(reads_build_class(r, CLS_ALL));
     return RCP_OK;
 }

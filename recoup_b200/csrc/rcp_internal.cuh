@@ -232,9 +232,21 @@ struct ReadsIdx {
     uint32_t* pd_run_first = nullptr;
     uint32_t pd_exc_cap = 0;
     bool pd_eager_index = false;
-    unsigned int h_err = 0, h_w[2] = {0, 0}, h_total = 0;
+    unsigned int h_err = 0, h_w[4] = {0, 0, 0, 0}, h_total = 0;   // h_w: exceptions, width, reads wider than long_thr
+    // reads wider than the packed candidate word of the split path (counted by the map kernel, so
+    // that the handle's long-read list needs no counting pass and no host synchronisation)
+    uint32_t long_thr = 0;
+    int64_t n_long = 0;
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
 };
+
+// Split path geometry: position bits of a candidate word for a genome of `span` global positions
+// (<= 1024 groups of 2^P positions, 16 <= P <= 22).
+inline int split_position_bits(int64_t span) {
+    int P = 16;
+    while (P < 22 && ((span + (1ll << P) - 1) >> P) > 1024) P++;
+    return P;
+}
 
 // deferred validation: the fetch items of a pending handle (appended), and what follows the fetch
 int reads_pending_items(ReadsIdx& r, FetchItem* items, int* n);
