@@ -194,6 +194,38 @@ int rcp_reads_load_select(int64_t n, const int32_t* chrom, const int32_t* start,
                           const int8_t* strand, double max_width, int64_t k, const int32_t* idx,
                           int n_chrom, const int64_t* chrom_len, int frag_len, int mem,
                           int64_t* n_kept_out, int* reads_out);
+/* The decode itself (readBam / readBed, ranges.R:111-146), on the device.  The
+ * result is a `decoded` handle: chrom id, start, end (1-based, closed), strand (+1 / -1 / 0) in
+ * FILE ORDER, resident in HBM.
+ *
+ * rcp_bam_index   walks the length-prefixed alignment records of an INFLATED BAM (the bytes after
+ *   the header and the reference list; the BGZF inflate is zlib's job on the host): *n_records_out
+ *   = records; offsets_out (may be NULL; capacity >= records + 1) = byte offset of every record
+ *   and of the end.  Host code: the chain is serial.
+ * rcp_bam_decode  readGAlignments(file) with its default flag filter (unmapped records dropped),
+ *   then as(., "GRanges") (splice_split = 0: one range per alignment, start = pos + 1, width =
+ *   the CIGAR's extent on the reference, M D N = X) or unlist(grglist(.)) (splice_split = 1,
+ *   spliceAction "split": the runs of M D = X between N operations, empty ones dropped), strand
+ *   from flag 0x10, then trim() against ref_len.  rec / offsets: host or device memory (`mem`);
+ *   ref_len: host, the header's reference lengths.
+ * rcp_bed_decode  import.bed(file, trackLine = FALSE): lines of chrom, chromStart, chromEnd
+ *   [, name, score, strand] separated by tabs or blanks; start = chromStart + 1; strand '.' or
+ *   absent = '*'; empty lines, '#' comments, "track" and "browser" lines skipped.  names: the
+ *   seqlevels (host), chrom id = index into them; a name not among them is RCP_ERR_DATA.
+ * rcp_decoded_fetch  the arrays -> host (any pointer may be NULL).
+ * rcp_reads_load_decoded  rcp_reads_load of the decoded reads without a host round trip. */
+int rcp_bam_index(const uint8_t* rec /* host */, int64_t n_bytes, int64_t* n_records_out,
+                  int64_t* offsets_out /* host */, int64_t capacity);
+int rcp_bam_decode(const uint8_t* rec, int64_t n_bytes, const int64_t* offsets, int64_t n_records,
+                   int n_ref, const int64_t* ref_len /* host */, int splice_split, int mem,
+                   int* decoded_out, int64_t* n_out);
+int rcp_bed_decode(const char* text, int64_t n_bytes, int n_names, const char* const* names /* host */,
+                   int mem, int* decoded_out, int64_t* n_out);
+int rcp_decoded_fetch(int decoded, int32_t* chrom, int32_t* start, int32_t* end, int8_t* strand,
+                      int64_t capacity);
+int rcp_decoded_free(int decoded);
+int rcp_reads_load_decoded(int decoded, int n_chrom, const int64_t* chrom_len, int frag_len,
+                           int* reads_out);
 int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes);
 int rcp_reads_free(int reads);
 

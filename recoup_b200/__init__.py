@@ -14,6 +14,7 @@ from .coverage import (CoverageList, DeviceReads, calcCoverage, coverageRef, cov
 from .preprocess import SelectedGRanges, preprocessRanges, readRanges, sampleSorted, widthQuantile
 from .profile import (ProfileMatrix, baseCoverageMatrix, binCoverageMatrix, coverageProfile,
                       haveEqualLengths, profileMatrix)
+from .readers import DecodedGRanges, decodeBam, readBam, readBed, readRangesFile
 from .ranges import GRanges, GRangesList, Rle, getFlankingRanges, getRegionalRanges
 
 __all__ = [
@@ -22,5 +23,6 @@ __all__ = [
     "DeviceReads", "device_reads", "profileMatrix", "binCoverageMatrix", "baseCoverageMatrix",
     "haveEqualLengths", "coverageProfile", "ProfileMatrix", "set_verbose", "calcPlotProfiles", "orderProfiles",
     "heatmapScale", "colProfile", "rowStat", "sortIndex", "matrixQuantile", "preprocessRanges",
-    "readRanges", "SelectedGRanges", "sampleSorted", "widthQuantile",
+    "readRanges", "SelectedGRanges", "sampleSorted", "widthQuantile", "readBam", "readBed", "readRangesFile",
+    "decodeBam", "DecodedGRanges",
 ]

@@ -65,6 +65,12 @@ SIGNATURES = {
                                        C.c_int, C.c_int, _ip]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
                                      C.c_int, C.c_int, _ip]),
+    "rcp_bam_index": (C.c_int, [_vp, C.c_int64, _i64p, _vp, C.c_int64]),
+    "rcp_bam_decode": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _i64p, C.c_int, C.c_int, _ip, _i64p]),
+    "rcp_bed_decode": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_char_p), C.c_int, _ip, _i64p]),
+    "rcp_decoded_fetch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int64]),
+    "rcp_decoded_free": (C.c_int, [C.c_int]),
+    "rcp_reads_load_decoded": (C.c_int, [C.c_int, C.c_int, _i64p, C.c_int, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),
     "rcp_reads_free": (C.c_int, [C.c_int]),
     "rcp_coverage": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _ip]),

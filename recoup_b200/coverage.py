@@ -54,6 +54,17 @@ class DeviceReads:
                              "vector, coverage.R:201)")
         _lib.ensure_init()
         h = C.c_int(0)
+        if getattr(gr, "decoded_handle", None) is not None:
+            # decoded on the device (readers.DecodedGRanges): no host round trip
+            clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+            _lib_check(_lib.lib.rcp_reads_load_decoded(gr.decoded_handle, clen.shape[0],
+                                                       clen.ctypes.data_as(C.POINTER(C.c_int64)), int(frag_len),
+                                                       C.byref(h)))
+            self.handle = h.value
+            self.n = len(gr)
+            self.seqlevels = list(gr.seqlevels)
+            self._fin = weakref.finalize(self, _free_reads, self.handle)
+            return
         if getattr(gr, "parent", None) is not None:
             # a selection of another GRanges (preprocess.SelectedGRanges): the device applies it
             p = gr.parent

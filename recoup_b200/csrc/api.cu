@@ -241,6 +241,7 @@ static void drop_coverage(int h) {
 }
 
 // implemented in the other translation units
+void decoded_release_all();     // import.cu
 int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs,
                     const int32_t* run_chrom, const int32_t* run_len, const int32_t* start,
                     const int32_t* end, const int8_t* strand, int n_chrom,
@@ -531,6 +532,7 @@ int rcp_shutdown(void) {
     g_reads.clear();
     for (auto& kv : g_covs) coverage_release(*kv.second);
     g_covs.clear();
+    decoded_release_all();
     cache_release_all();
     g_big_live.clear();
     host_cache_release_all();

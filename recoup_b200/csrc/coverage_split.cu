@@ -139,14 +139,16 @@ struct __align__(16) SpDesc {
 
 // One thread per tile: where it lies (tiles are cut in OUTPUT space, as in the other paths: on a
 // '-' region tile j covers the mirrored positions) and which candidates can reach it: those that
-// start from (tile start - widest read + 1) on.  boff is read later (sp_range_kernel): it does
-// not exist yet when the tiles are laid out, so the record keeps the sub-bin indices in c0 / n
-// meanwhile.
+// start from (tile start - widest read + 1) on: the run of the sub-bins [first, last] in boff (the
+// group sort is queued before this kernel: the host learns the tile count while it runs).
 __global__ void __launch_bounds__(CTA)
 sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, const uint32_t* __restrict__ gs,
                 const int32_t* __restrict__ plen, const uint8_t* __restrict__ flags,
-                const int64_t* __restrict__ cov_off /* nullptr: fused, `out` = offset inside the region */,
-                uint32_t max_w, uint32_t pmask, SpDesc* __restrict__ desc, uint32_t* __restrict__ tabs,
+                const int64_t* __restrict__ cov_off /* nullptr: fused, `out` = offset inside the region
+                                                       | first bin the tile meets << 32 */,
+                const int32_t* __restrict__ edge, int n_bins,
+                uint32_t max_w, uint32_t pmask, const uint32_t* __restrict__ boff, SpDesc* __restrict__ desc,
+                uint32_t* __restrict__ tabs,
                 const uint32_t* __restrict__ lxs, const uint32_t* __restrict__ lmax, uint32_t ln,
                 uint2* __restrict__ lrange) {
     const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
@@ -163,8 +165,17 @@ sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, cons
     const uint32_t first = tstart >= max_w ? tstart - max_w + 1u : 0u;
     SpDesc d;
     d.out = cov_off ? cov_off[r] + o_lo : (int64_t)o_lo;
-    d.c0 = first >> SUB_SHIFT;
-    d.n = ((tstart + tlen - 1u) >> SUB_SHIFT) + 1u;
+    if (!cov_off) {                         // last bin with edge <= o_lo
+        int a = 0, b = n_bins;
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (__ldg(edge + mid) <= (int)o_lo) a = mid;
+            else b = mid;
+        }
+        d.out |= (int64_t)a << 32;
+    }
+    d.c0 = __ldg(boff + (first >> SUB_SHIFT));
+    d.n = __ldg(boff + ((tstart + tlen - 1u) >> SUB_SHIFT) + 1u) - d.c0;
     d.tlen = (int32_t)tlen;
     d.cts = tstart & pmask;
     d.flags = flags[r];
@@ -189,17 +200,6 @@ sp_tiles_kernel(int64_t R, int64_t T, const int64_t* __restrict__ off_tile, cons
         }
         lrange[t] = make_uint2(a, c1);
     }
-}
-
-// sub-bin indices -> candidate range
-__global__ void __launch_bounds__(CTA)
-sp_range_kernel(int64_t T, const uint32_t* __restrict__ boff, SpDesc* __restrict__ desc) {
-    const int64_t t = (int64_t)blockIdx.x * CTA + threadIdx.x;
-    if (t >= T) return;
-    const uint32_t lo = desc[t].c0, hi1 = desc[t].n;
-    const uint32_t c0 = __ldg(boff + lo), c1 = __ldg(boff + hi1);
-    desc[t].c0 = c0;
-    desc[t].n = c1 - c0;
 }
 
 // --------------------------------------------------------------------------------- split ------
@@ -633,7 +633,9 @@ sp_group_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ 
     }
     if (g == n_groups - 1 && tid == 0) boff[(size_t)n_groups * nb] = base + total;
     __syncthreads();
-    if (total > cap) {          // a huge group: plain scatter, then the hole
+    if (total > cap) {          // a huge group: plain scatter, then the hole.  (Sorting it in slices of
+                                // sub-bins that fit shared memory was tried: every slice is one more
+                                // pass over the group's chunks, C4 1.32 -> 1.74 ms.)
         stream([&](uint32_t e) { cand[base + atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u)] = e; });
         for (uint32_t i = base + total + tid; i < c1 * CH; i += GT) cand[i] = 0u;
         return;
@@ -830,21 +832,74 @@ struct FusedBins {
     unsigned long long* acc;             // [n][R]
 };
 
-__device__ __forceinline__ void tile_to_bins(const int* tile, const SpDesc& d, const FusedBins& fb) {
+// Scan of a FUSED tile: the lane-serial scan of warp_scan_store_fwd run TWICE in registers, so that
+// the tile holds S[k] = c[0] + ... + c[k] (the running sum of the COVERAGE, modulo 2^32) instead of
+// the coverage: a bin's part of the tile is then S[hi - 1] - S[lo - 1], two shared-memory loads
+// instead of a serial sum of its bases.  Exact as long as the true sum fits 32 bits, which the
+// warp checks (coverage below 2^22 everywhere in the tile, <= 1024 bases); otherwise (returns
+// false) the tile holds the coverage itself and the bins are summed base by base.
+template <int RPW>
+__device__ __forceinline__ bool warp_scan_prefix2(int* diff) {
     const int lane = threadIdx.x & 31;
-    const int o_lo = (int)d.out, o_hi = o_lo + d.tlen;
-    int a = 0, b = fb.n;                 // last bin with edge <= o_lo
-    while (b - a > 1) {
-        const int mid = (a + b) >> 1;
-        if (__ldg(fb.edge + mid) <= o_lo) a = mid;
-        else b = mid;
+    int* mine = diff + lane * 4 * RPW;
+    int4 v[RPW];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        v[k] = *(reinterpret_cast<const int4*>(mine) + k);
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
+    const int inc = warp_inclusive_scan(sum);
+    const int run0 = inc - sum;
+    int run = run0, cmax = 0;
+    uint32_t tot = 0;                       // sum of this lane's coverage values
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        run += v[k].x; tot += (uint32_t)run; cmax = max(cmax, run);
+        run += v[k].y; tot += (uint32_t)run; cmax = max(cmax, run);
+        run += v[k].z; tot += (uint32_t)run; cmax = max(cmax, run);
+        run += v[k].w; tot += (uint32_t)run; cmax = max(cmax, run);
+    }
+    const bool small = __reduce_max_sync(0xffffffffu, cmax) < (1 << 22);
+    uint32_t acc = 0;
+    if (small) {
+        uint32_t incs = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incs, d);
+            if (lane >= d) incs += o;
+        }
+        acc = incs - tot;
+    }
+    run = run0;
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+        int4 o;
+        run += v[k].x; acc += (uint32_t)run; o.x = small ? (int)acc : run;
+        run += v[k].y; acc += (uint32_t)run; o.y = small ? (int)acc : run;
+        run += v[k].z; acc += (uint32_t)run; o.z = small ? (int)acc : run;
+        run += v[k].w; acc += (uint32_t)run; o.w = small ? (int)acc : run;
+        *(reinterpret_cast<int4*>(mine) + k) = o;
+    }
+    __syncwarp();
+    return small;
+}
+
+// prefixed: the tile holds S (warp_scan_prefix2 returned true), else the coverage
+__device__ __forceinline__ void tile_to_bins(const int* tile, const SpDesc& d, const FusedBins& fb, bool prefixed) {
+    const int lane = threadIdx.x & 31;
+    const int o_lo = (int)(uint32_t)d.out, o_hi = o_lo + d.tlen;
+    const int a = (int)(d.out >> 32);    // last bin with edge <= o_lo (sp_tiles_kernel)
     for (int i = a + lane; i < fb.n; i += 32) {
         const int e0 = __ldg(fb.edge + i);
         if (e0 >= o_hi) break;
         const int lo = max(e0, o_lo) - o_lo, hi = min(__ldg(fb.edge + i + 1), o_hi) - o_lo;
         unsigned long long s = 0;
-        for (int k = lo; k < hi; k++) s += (unsigned long long)(unsigned int)tile[k];
+        if (prefixed) {
+            if (hi > lo) s = (uint32_t)tile[hi - 1] - (lo > 0 ? (uint32_t)tile[lo - 1] : 0u);
+        } else {
+            for (int k = lo; k < hi; k++) s += (unsigned long long)(unsigned int)tile[k];
+        }
         if (s) atomicAdd(fb.acc + (size_t)i * fb.R + d.region, s);
     }
 }
@@ -999,25 +1054,38 @@ sp_wtile_kernel(int64_t T, const SpDesc* __restrict__ desc, const uint32_t* __re
         }
         hit = __any_sync(0xffffffffu, hit);
         __syncwarp();
-        int32_t* dst = FUSED ? nullptr : cov + d.out;
-        switch (rows) {
-            case 1: warp_scan_store_fwd<1, !FUSED>(diff, d.tlen, dst); break;
-            case 2: warp_scan_store_fwd<2, !FUSED>(diff, d.tlen, dst); break;
-            case 3: warp_scan_store_fwd<3, !FUSED>(diff, d.tlen, dst); break;
-            case 4: warp_scan_store_fwd<4, !FUSED>(diff, d.tlen, dst); break;
-            case 5: warp_scan_store_fwd<5, !FUSED>(diff, d.tlen, dst); break;
-            case 6: warp_scan_store_fwd<6, !FUSED>(diff, d.tlen, dst); break;
-            case 7: warp_scan_store_fwd<7, !FUSED>(diff, d.tlen, dst); break;
-            default:        // 8 rows (a whole region of 897..1024 bp)
-                if (FUSED) {
-                    warp_scan_store_fwd<8, false>(diff, d.tlen, dst);
-                } else {    // row by row, conflict-free
+        if (FUSED) {
+            if (hit) {                                          // a tile without a read adds nothing
+                bool prefixed = false;
+                switch (rows) {
+                    case 1: prefixed = warp_scan_prefix2<1>(diff); break;
+                    case 2: prefixed = warp_scan_prefix2<2>(diff); break;
+                    case 3: prefixed = warp_scan_prefix2<3>(diff); break;
+                    case 4: prefixed = warp_scan_prefix2<4>(diff); break;
+                    case 5: prefixed = warp_scan_prefix2<5>(diff); break;
+                    case 6: prefixed = warp_scan_prefix2<6>(diff); break;
+                    case 7: prefixed = warp_scan_prefix2<7>(diff); break;
+                    default: prefixed = warp_scan_prefix2<8>(diff); break;
+                }
+                tile_to_bins(diff, d, fb, prefixed);
+            }
+        } else {
+            int32_t* dst = cov + d.out;
+            switch (rows) {
+                case 1: warp_scan_store_fwd<1>(diff, d.tlen, dst); break;
+                case 2: warp_scan_store_fwd<2>(diff, d.tlen, dst); break;
+                case 3: warp_scan_store_fwd<3>(diff, d.tlen, dst); break;
+                case 4: warp_scan_store_fwd<4>(diff, d.tlen, dst); break;
+                case 5: warp_scan_store_fwd<5>(diff, d.tlen, dst); break;
+                case 6: warp_scan_store_fwd<6>(diff, d.tlen, dst); break;
+                case 7: warp_scan_store_fwd<7>(diff, d.tlen, dst); break;
+                default: {      // 8 rows (a whole region of 897..1024 bp): row by row, conflict-free
                     int pre = 0;
                     for (int row = 0; row < rows; row++)
                         pre += warp_row_scan_store(diff + row * ROW, pre, 0, false, d.tlen - row * ROW, dst + row * ROW);
                 }
+            }
         }
-        if (FUSED && hit) tile_to_bins(diff, d, fb);        // a tile without a read adds nothing
         if (hit && lane == 0) region_hit[d.region] = 1;
         t += step;
         if (!FUSED && lane == 0) tma_store_wait_read();     // the bulk store has read the tile
@@ -1539,7 +1607,6 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     if (!have_index && !rd.pending && (rd.max_width > 8191u || rd.max_width >= (1u << wbits)))
         return RCP_SPLIT_NOT_APPLICABLE;
     const uint32_t pmask = (1u << P) - 1u;
-    const int nb = 1 << (P - SUB_SHIFT);                // sub-bins of a group
 
     DevIn<int32_t> d_chrom, d_start, d_end;
     DevIn<int8_t> d_strand;
@@ -1687,16 +1754,12 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     if (T > 0) {
         StageTimer t(ST_SP_PLAN);
         sp_tiles_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(R, T, off_tile, gs, plen, flags,
-                                                                     fz ? nullptr : cv->off, max_w, pmask, desc, tabs,
+                                                                     fz ? nullptr : cv->off, fb.edge, fb.n, max_w, pmask, boff,
+                                                                     desc, tabs,
                                                                      lg.xs, lg.maxe1, lg.n, lrange);
         RCP_LAUNCHED();
     }
     if (T > 0) {
-        {
-            StageTimer t(ST_SP_PLAN);
-            sp_range_kernel<<<blocks_for(T, CTA), CTA, 0, g_ctx.stream>>>(T, boff, desc);
-            RCP_LAUNCHED();
-        }
         {
             StageTimer t(fz ? ST_FUSED : ST_SP_TILE);
             const int64_t want = blocks_for(T, WARPS);

@@ -4,10 +4,10 @@ decoded:
     preprocessRanges(input, preprocessParams, bamParams, rc)            ranges.R:1-65
     readBam(..., sa = "remove", sq)                                     ranges.R:125-133
 
-Decoding BAM / BED files stays outside the library (the north star: reads arrive decoded), so the
-caller passes `reader`, a callable that returns the decoded GRanges of one sample -- what
-readBam / readBed would return for spliceAction "keep" or "split".  Everything after the decode
-runs here: the width cut of spliceAction "remove" (a type-7 quantile, on the device), the seeded
+The decode itself: `reader`, a callable that returns the decoded GRanges of one sample (what
+readBam / readBed would return for spliceAction "keep" or "split"), or -- reader None -- the
+sample's own `file` / `format` through the device decoders of readers.py (BAM records and BED text
+parsed on the device after the host's BGZF inflate).  Everything after the decode runs here: the width cut of spliceAction "remove" (a type-7 quantile, on the device), the seeded
 down-sampling indices (base R's sample() stream, serial by nature: host code inside the library)
 and the selection itself, which the device applies while it loads the reads
 (rcp_reads_load_select) -- the selected reads are never gathered on the host unless somebody
@@ -91,7 +91,15 @@ def readRanges(x, reader, spliceAction="keep", spliceRemoveQ=0.75):
         raise ValueError("sa must be one of keep, remove, split")
     if not 0 <= spliceRemoveQ <= 1:
         raise ValueError("sq must be in [0, 1]")
-    gr = reader(x)
+    if reader is None:
+        # the file itself: decoded on the device (readers.py); "split" is the decoder's business
+        from .readers import readRangesFile
+        if x.get("file") is None or x.get("format") is None:
+            raise ValueError("One or more input files cannot be read: no file / format and no reader")
+        gr = readRangesFile(x["file"], x["format"], "split" if spliceAction == "split" else "keep",
+                            seqlevels=x.get("seqlevels"), seqlengths=x.get("seqlengths"))
+    else:
+        gr = reader(x)
     if spliceAction != "remove" or len(gr) == 0:
         return gr
     qu, n_kept = widthQuantile(gr, spliceRemoveQ)
@@ -108,8 +116,6 @@ def preprocessRanges(input, preprocessParams, bamParams=None, rc=None, reader=No
     preprocessParams$sampleTo, both with ONE set.seed(preprocessParams$seed)."""
     if not any(x.get("ranges") is None for x in input):
         return input
-    if reader is None:
-        raise ValueError("One or more input files cannot be read: no reader was given")
     pp = preprocessParams
     normalize = pp.get("normalize", "none")
     if normalize not in ("none", "linear", "downsample", "sampleto"):

@@ -178,6 +178,38 @@ def test_pileups_long_reads_and_no_strand(gpu):
         assert all(w is None for w in want_f) == (filt != "*")
 
 
+def test_groups_denser_than_shared_memory(gpu):
+    """Split path: a 64-kb group holding more candidates than its CTA's shared memory (the group
+    kernel scatters it directly), one of them with 70 000 reads in ONE 1-kb sub-bin."""
+    rb = gpu
+    rng = np.random.default_rng(33)
+    clen = [400000]
+    n_bg, n_pile = 170000, 70000
+    chrom = np.zeros(n_bg + n_pile, dtype=np.int32)
+    w = rng.integers(20, 90, size=n_bg + n_pile)
+    s = np.empty(n_bg + n_pile, dtype=np.int64)
+    s[:n_bg] = rng.integers(1, 130000, size=n_bg)                  # two groups, ~85 000 candidates each
+    s[n_bg:] = rng.integers(262144 + 5 * 1024, 262144 + 6 * 1024 - 100, size=n_pile)   # one sub-bin
+    e = s + w - 1
+    st = rng.choice(np.array([1, -1, 0], dtype=np.int8), size=n_bg + n_pile)
+    o_reads, g_reads = both_reads(chrom, s, e, st, clen)
+    rc, rs, re_, rst = _regions(rng, 60, clen, [500, 3000, 20000])
+    rs[0], re_[0] = 1, 135000
+    rs[1], re_[1] = 262144, 262144 + 9000
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 1)
+    for ignore in (True, False):
+        want = O.calc_coverage(o_reads, o_mask, None, ignore)
+        got = rb.calcCoverage(g_reads, g_mask, ignore_strand=ignore)
+        assert_coverage_equal(got.to_list(), want)
+    # the same reads through the handle's binned index (GRangesList mask)
+    ptr = np.arange(0, 61, 3, dtype=np.int64)
+    o_list = dict(ptr=ptr, **o_mask)
+    grl = rb.GRangesList(g_mask, ptr)
+    want = O.calc_coverage(o_reads, o_list)
+    got = rb.calcCoverage(g_reads, grl)
+    assert_coverage_equal(got.to_list(), want)
+
+
 def test_empty_inputs(gpu):
     rb = gpu
     clen = [1000]
