@@ -480,24 +480,128 @@ def run_c1(env):
             "note": "latency-bound (0.8 MB of reads): parity config, not a roofline config"}
 
 
-def run_strong(env, args, world, rank):
-    """ONE C5 problem sharded by region: every rank generates the read parts {p : p % W == rank}
-    (an arbitrary share of the reads), the timed step exchanges the reads (all-to-all by region
-    slice), runs the path on the rank's slice and downloads the rank's matrix block over its own
-    PCIe link.  checksum = sum of all matrix entries: the same for every W."""
+def run_import(env, n_records=2_000_000):
+    """Read import: rcp_bam_decode / rcp_bed_decode on synthetic files with the record
+    and text bytes already in HBM (device-timed) and from pinned-free host memory (wall clock, copies
+    included).  Records: 36-byte core + 12-byte name + 3 CIGAR operations (40M 1000N 35M: spliced
+    reads, two ranges each under spliceAction split) + 38 bytes of sequence / qualities."""
+    import ctypes as C
+
+    import torch
+    _lib = env["_lib"]
+    L = _lib.lib
+    rng = np.random.default_rng(9)
+    clen = np.asarray([249250621, 243199373, 198022430], dtype=np.int64)
+    n = int(n_records)
+    name_len, n_cig, tail = 12, 3, 38
+    body = 32 + name_len + 4 * n_cig + tail
+    rec = np.zeros((n, 4 + body), dtype=np.uint8)
+    v32 = lambda col, arr: rec.__setitem__((slice(None), slice(col, col + 4)),
+                                           np.ascontiguousarray(arr, dtype="<i4").view(np.uint8).reshape(n, 4))
+    ref = rng.integers(0, 3, size=n)
+    v32(0, np.full(n, body))
+    v32(4, ref)
+    v32(8, (rng.random(n) * (clen[ref] - 2000)).astype(np.int64))
+    rec[:, 12] = name_len
+    rec[:, 16] = n_cig
+    flag = rng.choice(np.asarray([0, 16, 4], dtype=np.int64), size=n, p=[0.49, 0.49, 0.02])
+    rec[:, 18] = flag
+    cig0 = 36 + name_len
+    for k, (ln, op) in enumerate(((40, 0), (1000, 3), (35, 0))):
+        v32(cig0 + 4 * k, np.full(n, (ln << 4) | op))
+    rec = rec.reshape(-1)
+    n_bytes = rec.shape[0]
+    off = np.arange(n + 1, dtype=np.int64) * (4 + body)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_rec = torch.from_numpy(rec).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
+    out = {"records": n, "record_bytes": n_bytes}
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        L.rcp_sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        L.rcp_sync()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    def bam(mem, split):
+        h, no = C.c_int(0), C.c_int64(0)
+        if mem == _lib.MEM_DEVICE:
+            _lib.check(L.rcp_bam_decode(vp(d_rec), n_bytes, vp(d_off), n, 3, clen_p, split, mem, C.byref(h), C.byref(no)))
+        else:
+            _lib.check(L.rcp_bam_decode(hp(rec), n_bytes, hp(off), n, 3, clen_p, split, mem, C.byref(h), C.byref(no)))
+        L.rcp_decoded_free(h.value)
+        return no.value
+
+    for split in (0, 1):
+        key = "bam_split" if split else "bam_keep"
+        ms = timed(lambda: bam(_lib.MEM_DEVICE, split))
+        out[key] = {"ranges_out": bam(_lib.MEM_DEVICE, split), "ms_device_resident": ms,
+                    "records_per_s": n / (ms * 1e-3), "GB_per_s": n_bytes / (ms * 1e6)}
+    ms = timed(lambda: bam(_lib.MEM_HOST, 0), reps=3)
+    out["bam_keep"]["ms_from_host"] = ms
+    t0 = time.perf_counter()
+    cnt = C.c_int64(0)
+    _lib.check(L.rcp_bam_index(hp(rec), n_bytes, C.byref(cnt), hp(off), n + 1))
+    out["bam_index_host_ms"] = 1e3 * (time.perf_counter() - t0)
+    del d_rec, d_off
+    # BED: six columns, ~33 bytes per line
+    m = n
+    names = ["chr1", "chr2", "chr3"]
+    a = (rng.random(m) * 1.9e8).astype(np.int64)
+    cols = [np.asarray(names)[rng.integers(0, 3, size=m)], a.astype(str), (a + 36).astype(str),
+            np.full(m, "r"), np.full(m, "0"), np.where(rng.random(m) < 0.5, "+", "-")]
+    text = "\n".join(map("\t".join, zip(*cols))).encode() + b"\n"
+    t_host = np.frombuffer(text, dtype=np.uint8)
+    d_text = torch.from_numpy(t_host.copy()).to(dev)
+    arr = (C.c_char_p * 3)(*[s.encode() for s in names])
+
+    def bed(mem):
+        h, no = C.c_int(0), C.c_int64(0)
+        src = vp(d_text) if mem == _lib.MEM_DEVICE else hp(t_host)
+        _lib.check(L.rcp_bed_decode(src, t_host.shape[0], 3, arr, mem, C.byref(h), C.byref(no)))
+        L.rcp_decoded_free(h.value)
+        return no.value
+
+    ms = timed(lambda: bed(_lib.MEM_DEVICE))
+    out["bed"] = {"lines": m, "text_bytes": int(t_host.shape[0]), "ranges_out": bed(_lib.MEM_DEVICE),
+                  "ms_device_resident": ms, "lines_per_s": m / (ms * 1e-3), "GB_per_s": t_host.shape[0] / (ms * 1e6),
+                  "ms_from_host": timed(lambda: bed(_lib.MEM_HOST), reps=3)}
+    out["note"] = ("decode only: the BGZF inflate (host zlib) and the host walk of the record chain "
+                   "(bam_index_host_ms) come before it")
+    return out
+
+
+def run_strong(env, args, world, rank, which="C5"):
+    """ONE problem sharded by region -- C5 (every rank generates the read parts {p : p % W == rank})
+    or C3 (every rank keeps the reads rank, rank + W, ... of the one seeded sample): an arbitrary
+    share of the reads per rank; the timed step exchanges the reads (all-to-all by region slice),
+    runs the path on the rank's slice and downloads the rank's matrix block over its own PCIe
+    link.  checksum = sum of all matrix entries: the same for every W."""
     import torch
     import torch.distributed as dist
     from recoup_b200.ranges import getRegionalRanges
     from recoup_b200.sharding import exchange_reads, partition_regions, slice_spans
     rb, dev, L = env["rb"], env["dev"], env["L"]
-    n_parts = 8
-    mine = [p for p in range(n_parts) if p % world == rank]
     t_gen = time.time()
-    ws = [W.dnase_sites_part(p, n_parts=n_parts, scale=args.configs_scale) for p in mine]
-    w = dict(ws[0])
-    for key in ("read_chrom", "read_start", "read_end", "read_strand"):
-        w[key] = np.concatenate([x[key] for x in ws])
-    del ws
+    if which == "C5":
+        n_parts = 8
+        mine = [p for p in range(n_parts) if p % world == rank]
+        ws = [W.dnase_sites_part(p, n_parts=n_parts, scale=args.configs_scale) for p in mine]
+        w = dict(ws[0])
+        for key in ("read_chrom", "read_start", "read_end", "read_strand"):
+            w[key] = np.concatenate([x[key] for x in ws])
+        del ws
+    else:
+        w = W.gene_bodies(scale=args.configs_scale, seed=SEEDS["C3"])
+        for key in ("read_chrom", "read_start", "read_end", "read_strand"):
+            w[key] = np.ascontiguousarray(w[key][rank::world])
     t_gen = time.time() - t_gen
     genes = rb.GRanges(w["region_chrom"], w["region_start"], w["region_end"], strand=w["region_strand"],
                        seqlevels=w["chrom_names"])
@@ -512,7 +616,10 @@ def run_strong(env, args, world, rank):
         w[key] = w[key][:0]
     prob = Problem(env, w, reads=share, region_idx=my_idx)
     R_mine = prob.R
-    ncols = w["flank"][0] + w["flank"][1]          # per-base custom windows: f1 + f2 columns
+    if which == "C5":
+        ncols = w["flank"][0] + w["flank"][1]      # per-base custom windows: f1 + f2 columns
+    else:
+        ncols = 2 * w["bin_params"]["flankBinSize"] + w["bin_params"]["regionBinSize"]
     block = torch.empty((ncols, R_mine), dtype=torch.float64, device=dev)
     host = torch.empty((ncols, R_mine), dtype=torch.float64, pin_memory=True)
     lib_stream = torch.cuda.ExternalStream(L.rcp_stream(), device=dev)
@@ -559,8 +666,10 @@ def run_strong(env, args, world, rank):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms = float(red[0])
     n_total = int(tot[1])
-    out = {"workload": "C5 synthetic DNase-seq: %d reads over %d sites +-%d bp, per-base, ONE problem "
-                       "sharded by region over %d GPU(s)" % (n_total, len(win), w["flank"][0], world),
+    label = ("C5 synthetic DNase-seq: %d reads over %d sites +-%d bp, per-base" if which == "C5" else
+             "C3 synthetic gene bodies (one sample): %d reads over %d genes +-%d bp, 50+150+50 bins")
+    out = {"workload": (label + ", ONE problem sharded by region over %d GPU(s)") % (n_total, len(win), w["flank"][0],
+                                                                                    world),
            "scaling": "strong", "n_gpus": world, "steps": steps,
            "ms_per_step": ms, "reads_per_s": n_total / (ms * 1e-3),
            "ms_device_resident": float(red[1]) + float(red[2]),
@@ -942,9 +1051,14 @@ def run_b200(args):
         configs["C4"] = config_entry(env, w4, max(2, min(args.steps, 3)), peak, note=note)
         del w4
         torch.cuda.empty_cache()
-    strong = None
+        configs["import"] = run_import(env, 2_000_000)
+        torch.cuda.empty_cache()
+    strong = strong_c3 = None
     if args.strong == "on" and headline:
         strong = run_strong(env, args, world, rank)
+        torch.cuda.empty_cache()
+        strong_c3 = run_strong(env, args, world, rank, "C3")
+        torch.cuda.empty_cache()
         if configs is not None:
             configs["C5"] = dict(strong, note="run through the region-sharded code path at W = 1; the matrix "
                                               "block download (8 GB D2H) is inside ms_per_step")
@@ -1041,6 +1155,8 @@ def run_b200(args):
             out["configs"] = configs
         if strong is not None:
             out["strong"] = strong
+        if strong_c3 is not None:
+            out["strong_C3"] = strong_c3
         if exchange_ok is not None:
             out["exchange_verified"] = exchange_ok
         if cpu is not None:

@@ -226,6 +226,11 @@ int rcp_decoded_fetch(int decoded, int32_t* chrom, int32_t* start, int32_t* end,
 int rcp_decoded_free(int decoded);
 int rcp_reads_load_decoded(int decoded, int n_chrom, const int64_t* chrom_len, int frag_len,
                            int* reads_out);
+/* rcp_reads_width_quantile / rcp_reads_load_select on a decoded handle (idx: host memory). */
+int rcp_decoded_width_quantile(int decoded, double prob, double* quantile_out, int64_t* n_le_out);
+int rcp_reads_load_decoded_select(int decoded, double max_width, int64_t k, const int32_t* idx /* host */,
+                                  int n_chrom, const int64_t* chrom_len, int frag_len,
+                                  int64_t* n_kept_out, int* reads_out);
 int rcp_reads_info(int reads, int64_t* n, int* n_chrom, int64_t* device_bytes);
 int rcp_reads_free(int reads);
 

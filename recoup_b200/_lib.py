@@ -71,6 +71,9 @@ SIGNATURES = {
     "rcp_decoded_fetch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int64]),
     "rcp_decoded_free": (C.c_int, [C.c_int]),
     "rcp_reads_load_decoded": (C.c_int, [C.c_int, C.c_int, _i64p, C.c_int, _ip]),
+    "rcp_decoded_width_quantile": (C.c_int, [C.c_int, C.c_double, _f64p, _i64p]),
+    "rcp_reads_load_decoded_select": (C.c_int, [C.c_int, C.c_double, C.c_int64, _vp, C.c_int, _i64p, C.c_int,
+                                                _i64p, _ip]),
     "rcp_reads_info": (C.c_int, [C.c_int, _i64p, _ip, _i64p]),
     "rcp_reads_free": (C.c_int, [C.c_int]),
     "rcp_coverage": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _ip]),

@@ -68,6 +68,20 @@ class DeviceReads:
         if getattr(gr, "parent", None) is not None:
             # a selection of another GRanges (preprocess.SelectedGRanges): the device applies it
             p = gr.parent
+            if getattr(p, "decoded_handle", None) is not None:
+                # a selection of reads decoded on the device: nothing but the index crosses PCIe
+                clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+                n_kept = C.c_int64(0)
+                k = 0 if gr.idx is None else gr.idx.shape[0]
+                _lib_check(_lib.lib.rcp_reads_load_decoded_select(
+                    p.decoded_handle, -1.0 if gr.max_width is None else float(gr.max_width), k,
+                    None if gr.idx is None else _ptr(gr.idx), clen.shape[0],
+                    clen.ctypes.data_as(C.POINTER(C.c_int64)), int(frag_len), C.byref(n_kept), C.byref(h)))
+                self.handle = h.value
+                self.n = len(gr)
+                self.seqlevels = list(gr.seqlevels)
+                self._fin = weakref.finalize(self, _free_reads, self.handle)
+                return
             arr = [np.ascontiguousarray(a, dtype=t) for a, t in
                    ((p.seqnames, np.int32), (p.start, np.int32), (p.end, np.int32), (p.strand, np.int8))]
             clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)

@@ -11,7 +11,7 @@
 //            Full 16-entry chunks leave as 64-byte stores into a chunk pool; a chunk carries its
 //            group in a 2-byte tag.  No histogram pass, no global atomic per read, no prefix sum
 //            over the reads.
-//   sort     the chunk tags are counting-sorted by group (three tiny kernels over ~N/16 tags);
+//   sort     the chunk tags are counting-sorted by group (one cooperative launch over ~N/16 tags);
 //            then one CTA per group sorts the group's candidates by 1-kb sub-bin (shared-memory
 //            histogram + cursors) into one dense candidate array and writes the sub-bin offsets.
 //   tiles    one WARP per tile (<= 896 outputs of one region): the candidates of the sub-bins
@@ -31,6 +31,8 @@
 
 #include <type_traits>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "cov_common.cuh"
 #include "r_rng.cuh"
@@ -82,8 +84,10 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
                int n_chrom, int ignore_strand, int strand_filter, uint32_t* __restrict__ gs_out,
                int32_t* __restrict__ plen, uint8_t* __restrict__ flags, int64_t* __restrict__ ntile,
                int64_t* __restrict__ padded, uint32_t* __restrict__ tab, unsigned int* __restrict__ err,
-               unsigned long long* __restrict__ pstats /* [0] total len [1] max len [2] 2^32 - min len */) {
+               unsigned long long* __restrict__ pstats /* [0] total len [1] max len [2] 2^32 - min len */,
+               unsigned long long* __restrict__ zero4 /* the coverage's stats words: cleared here */) {
     const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (r < 4) zero4[r] = 0ull;
     unsigned long long my_len = 0;
     if (r < R) {
         const int st = strand ? (int)strand[r] : 0;
@@ -474,18 +478,26 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
 
 // ---------------------------------------------------------------------- chunks by group -------
 // Counting sort of the chunk tags: per-CTA histograms over a contiguous range of pool slots, a
-// column-wise prefix by one CTA, then the placement with shared-memory cursors.
+// column-wise prefix, then the placement with shared-memory cursors.
 __device__ __forceinline__ void sp_slot_range(uint32_t n_slots, uint32_t* lo, uint32_t* hi) {
     const uint32_t per = ((n_slots + gridDim.x - 1) / gridDim.x + CS - 1) / CS * CS;
     *lo = min(n_slots, blockIdx.x * per);
     *hi = min(n_slots, *lo + per);
 }
 
+// One cooperative launch (64 CTAs, all resident): histogram of this CTA's slot range, grid barrier,
+// every CTA works out its own cursors from the whole count table (64 x 1024 words from L2: cheaper
+// than a second barrier around a one-CTA prefix), placement.  CTA 0 also writes cb[g] = first
+// chunk-list entry of group g (cb[NG] = chunks in all).
 __global__ void __launch_bounds__(CS)
-sp_chunk_hist_kernel(const uint16_t* __restrict__ meta, const uint32_t* __restrict__ pool_next,
-                     uint32_t* __restrict__ col /* [gridDim.x][NG] */) {
+sp_chunk_lists_kernel(const uint16_t* __restrict__ meta, const uint32_t* __restrict__ pool_next,
+                      uint32_t* __restrict__ col /* [gridDim.x][NG] */, uint32_t* __restrict__ cb,
+                      uint32_t* __restrict__ list /* slot << 5 | entries */) {
+    static_assert(CS == NG, "thread g of a CTA owns group g");
     __shared__ uint32_t h[NG];
-    h[threadIdx.x] = 0;
+    __shared__ uint32_t wsum[NG / 32];
+    const int g = threadIdx.x;
+    h[g] = 0;
     __syncthreads();
     uint32_t lo, hi;
     sp_slot_range(*pool_next, &lo, &hi);
@@ -494,17 +506,14 @@ sp_chunk_hist_kernel(const uint16_t* __restrict__ meta, const uint32_t* __restri
         if (m & 31u) atomicAdd(&h[m >> 5], 1u);
     }
     __syncthreads();
-    col[(size_t)blockIdx.x * NG + threadIdx.x] = h[threadIdx.x];
-}
-
-// one CTA, thread g = group g: cb[g] = first chunk-list entry of group g (cb[NG] = chunks in all);
-// col[c][g] becomes the first entry CTA c writes for group g
-__global__ void __launch_bounds__(NG)
-sp_chunk_scan_kernel(uint32_t* __restrict__ col, int n_cols, uint32_t* __restrict__ cb) {
-    __shared__ uint32_t wsum[NG / 32];
-    const int g = threadIdx.x;
-    uint32_t tot = 0;
-    for (int c = 0; c < n_cols; c++) tot += col[(size_t)c * NG + g];
+    col[(size_t)blockIdx.x * NG + g] = h[g];
+    cooperative_groups::this_grid().sync();
+    uint32_t tot = 0, before = 0;
+    for (unsigned c = 0; c < gridDim.x; c++) {
+        const uint32_t v = __ldcg(col + (size_t)c * NG + g);
+        tot += v;
+        if (c < blockIdx.x) before += v;
+    }
     uint32_t inc = tot;
     const unsigned lane = g & 31;
 #pragma unroll
@@ -516,26 +525,15 @@ sp_chunk_scan_kernel(uint32_t* __restrict__ col, int n_cols, uint32_t* __restric
     __syncthreads();
     uint32_t run = inc - tot;
     for (int k = 0; k < (g >> 5); k++) run += wsum[k];
-    cb[g] = run;
-    if (g == NG - 1) cb[NG] = run + tot;
-    for (int c = 0; c < n_cols; c++) {
-        const uint32_t v = col[(size_t)c * NG + g];
-        col[(size_t)c * NG + g] = run;
-        run += v;
+    if (blockIdx.x == 0) {
+        cb[g] = run;
+        if (g == NG - 1) cb[NG] = run + tot;
     }
-}
-
-__global__ void __launch_bounds__(CS)
-sp_chunk_place_kernel(const uint16_t* __restrict__ meta, const uint32_t* __restrict__ pool_next,
-                      const uint32_t* __restrict__ col, uint32_t* __restrict__ list /* slot << 5 | entries */) {
-    __shared__ uint32_t cur[NG];
-    cur[threadIdx.x] = col[(size_t)blockIdx.x * NG + threadIdx.x];
+    h[g] = run + before;                // cursor of this CTA for group g
     __syncthreads();
-    uint32_t lo, hi;
-    sp_slot_range(*pool_next, &lo, &hi);
     for (uint32_t i = lo + threadIdx.x; i < hi; i += CS) {
         const uint32_t m = meta[i];
-        if (m & 31u) list[atomicAdd(&cur[m >> 5], 1u)] = (i << 5) | (m & 31u);
+        if (m & 31u) list[atomicAdd(&h[m >> 5], 1u)] = (i << 5) | (m & 31u);
     }
 }
 
@@ -590,14 +588,32 @@ sp_group_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ 
 #pragma unroll
             for (uint32_t u = 0; u < U; u++) {
                 const uint32_t f = le[u] & 31u;
-                if (q4 < f) use(e[u].x);
-                if (q4 + 1 < f) use(e[u].y);
-                if (q4 + 2 < f) use(e[u].z);
-                if (q4 + 3 < f) use(e[u].w);
+                use(e[u], q4 < f, q4 + 1 < f, q4 + 2 < f, q4 + 3 < f);
             }
         }
     };
-    stream([&](uint32_t e) { atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u); });
+    auto sub = [&](uint32_t e) { return (e & pmask) >> SUB_SHIFT; };
+    stream([&](uint4 e, bool v0, bool v1, bool v2, bool v3) {
+        if (v0) atomicAdd(&h[sub(e.x)], 1u);
+        if (v1) atomicAdd(&h[sub(e.y)], 1u);
+        if (v2) atomicAdd(&h[sub(e.z)], 1u);
+        if (v3) atomicAdd(&h[sub(e.w)], 1u);
+    });
+    // placement: the four cursor atomics of a 16-byte word are issued back to back and the four
+    // stores follow, so that a thread waits for ONE shared-memory round trip per word, not four
+    auto place = [&](uint32_t* dst) {
+        stream([&](uint4 e, bool v0, bool v1, bool v2, bool v3) {
+            uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+            if (v0) p0 = atomicAdd(&h[sub(e.x)], 1u);
+            if (v1) p1 = atomicAdd(&h[sub(e.y)], 1u);
+            if (v2) p2 = atomicAdd(&h[sub(e.z)], 1u);
+            if (v3) p3 = atomicAdd(&h[sub(e.w)], 1u);
+            if (v0) dst[p0] = e.x;
+            if (v1) dst[p1] = e.y;
+            if (v2) dst[p2] = e.z;
+            if (v3) dst[p3] = e.w;
+        });
+    };
     __syncthreads();
     // exclusive prefix of the nb counts: warp w owns the bins [w * pw, (w + 1) * pw) and walks them
     // 32 at a time (consecutive lanes, consecutive bins: no bank conflicts); the warp bases follow
@@ -636,11 +652,11 @@ sp_group_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ 
     if (total > cap) {          // a huge group: plain scatter, then the hole.  (Sorting it in slices of
                                 // sub-bins that fit shared memory was tried: every slice is one more
                                 // pass over the group's chunks, C4 1.32 -> 1.74 ms.)
-        stream([&](uint32_t e) { cand[base + atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u)] = e; });
+        place(cand + base);
         for (uint32_t i = base + total + tid; i < c1 * CH; i += GT) cand[i] = 0u;
         return;
     }
-    stream([&](uint32_t e) { out[atomicAdd(&h[(e & pmask) >> SUB_SHIFT], 1u)] = e; });
+    place(out);
     // zero words up to the group's chunk capacity (a multiple of CH, so of 4): the hole
     const uint32_t full = (c1 - c0) * CH;
     for (uint32_t i = total + tid; i < min(full, (total + 3u) & ~3u); i += GT) out[i] = 0u;
@@ -1469,12 +1485,14 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, i
     dbg.lap("  split_and_sort: split kernel");
     {
         StageTimer t(ST_SP_SORT);
-        sp_chunk_hist_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col);
-        RCP_LAUNCHED();
-        sp_chunk_scan_kernel<<<1, NG, 0, g_ctx.stream>>>(col, sort_grid, sc->cb);
-        RCP_LAUNCHED();
-        sp_chunk_place_kernel<<<sort_grid, CS, 0, g_ctx.stream>>>(meta, pool_next, col, list);
-        RCP_LAUNCHED();
+        {
+            const uint16_t* a_meta = meta;
+            const uint32_t* a_next = pool_next;
+            void* args[] = {(void*)&a_meta, (void*)&a_next, (void*)&col, (void*)&sc->cb, (void*)&list};
+            RCP_CUDA(cudaLaunchCooperativeKernel((const void*)sp_chunk_lists_kernel, dim3((unsigned)sort_grid), dim3(CS),
+                                                 args, 0, g_ctx.stream));
+            RCP_LAUNCHED();
+        }
         dbg.lap("  split_and_sort: chunk lists");
         RCP_CUDA(cudaFuncSetAttribute(sp_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM));
         sp_group_kernel<<<n_groups, GT, GSMEM, g_ctx.stream>>>(pool, list, sc->cb, n_groups, nb, pmask, sc->cand,
@@ -1649,12 +1667,12 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     {
         StageTimer t(ST_SP_PLAN);
         RCP_CUDA(cudaMemsetAsync(A.base, 0, zero_bytes, g_ctx.stream));
-        RCP_CUDA(cudaMemsetAsync(cv->d_stats, 0, 32, g_ctx.stream));
+        if (R == 0) RCP_CUDA(cudaMemsetAsync(cv->d_stats, 0, 32, g_ctx.stream));     // else: sp_plan_kernel
         if (R > 0) {
             sp_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
                 R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, rd.d_chrom_off, rd.d_chrom_len,
                 rd.n_chrom, ignore_strand, strand_filter, gs, plen, flags, ntile, padded, tab, err,
-                pstats);
+                pstats, cv->d_stats);
             RCP_LAUNCHED();
         }
         RCP_TRY(exclusive_scan2_i64(ntile, off_tile, off_tile + R, padded, cv->off, cv->off + R, R));

@@ -572,4 +572,25 @@ int rcp_reads_load_decoded(int decoded, int n_chrom, const int64_t* chrom_len, i
                           reads_out);
 }
 
+int rcp_decoded_width_quantile(int decoded, double prob, double* quantile_out, int64_t* n_le_out) {
+    RCP_TRY(require_ready());
+    auto it = g_decoded.find(decoded);
+    if (it == g_decoded.end()) return fail(RCP_ERR_HANDLE, "unknown decoded handle %d", decoded);
+    const Decoded& d = *it->second;
+    return rcp_reads_width_quantile(d.n, d.start, d.end, prob, RCP_MEM_DEVICE, quantile_out, n_le_out);
+}
+
+int rcp_reads_load_decoded_select(int decoded, double max_width, int64_t k, const int32_t* idx, int n_chrom,
+                                  const int64_t* chrom_len, int frag_len, int64_t* n_kept_out, int* reads_out) {
+    RCP_TRY(require_ready());
+    auto it = g_decoded.find(decoded);
+    if (it == g_decoded.end()) return fail(RCP_ERR_HANDLE, "unknown decoded handle %d", decoded);
+    if (k < 0 || (k > 0 && idx == nullptr)) return fail(RCP_ERR_ARG, "rcp_reads_load_decoded_select: bad index");
+    const Decoded& d = *it->second;
+    DevIn<int32_t> d_idx;
+    RCP_TRY(d_idx.init(idx, (size_t)k, RCP_MEM_HOST));
+    return rcp_reads_load_select(d.n, d.chrom, d.start, d.end, d.strand, max_width, k, d_idx.ptr, n_chrom, chrom_len,
+                                 frag_len, RCP_MEM_DEVICE, n_kept_out, reads_out);
+}
+
 }  // extern "C"

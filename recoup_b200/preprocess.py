@@ -61,6 +61,10 @@ class SelectedGRanges(GRanges):
 def widthQuantile(gr, prob):
     """(quantile(width(gr), prob), number of reads not wider than it)"""
     _lib.ensure_init()
+    if getattr(gr, "decoded_handle", None) is not None:      # decoded on the device: stays there
+        q, n_le = C.c_double(0.0), C.c_int64(0)
+        _lib.check(_lib.lib.rcp_decoded_width_quantile(gr.decoded_handle, float(prob), C.byref(q), C.byref(n_le)))
+        return q.value, n_le.value
     start = np.ascontiguousarray(gr.start, dtype=np.int32)
     end = np.ascontiguousarray(gr.end, dtype=np.int32)
     q = C.c_double(0.0)

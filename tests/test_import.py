@@ -20,12 +20,16 @@ CIGARS = ["36M", "10M500N26M", "5S20M3I11M", "12M2D8M1000N4M4D10M", "3H10=1X25="
           "8M30N8M40N8M50N12M", "36S", "6I", "10M5N2I5N10M", "4D", "15M2000N", "7N20M"]
 
 
-def _synthetic_bam(rng, n):
+def _synthetic_bam(rng, n, clean=False):
+    """clean: no alignment of reference width 0 and none that trim() cuts to width 0 (the reads
+    loader refuses zero-width reads, like a GRanges holding them passed as arrays)"""
     recs, truth = [], []
     for i in range(n):
-        ref = int(rng.integers(0, len(REFS)))
+        ref = int(rng.integers(0, 2 if clean else len(REFS)))
         cigar = CIGARS[int(rng.integers(0, len(CIGARS)))]
-        pos0 = int(rng.integers(0, REFS[ref][1] - 10))
+        while clean and cigar in ("36S", "6I"):
+            cigar = CIGARS[int(rng.integers(0, len(CIGARS)))]
+        pos0 = int(rng.integers(0, REFS[ref][1] - (2200 if clean else 10)))
         flag = int(rng.choice([0, 16, 4, 20, 256, 1024 + 16, 99, 147]))
         if i % 97 == 0:
             ref, pos0, flag = -1, -1, 4                 # unplaced
@@ -144,7 +148,7 @@ def test_read_bam_remove_and_preprocess_ranges_from_files(rb, tmp_path):
     rng = np.random.default_rng(77)
     files = []
     for k in range(2):
-        (raw, bgzf), _ = _synthetic_bam(rng, 3000 + 500 * k)
+        (raw, bgzf), _ = _synthetic_bam(rng, 3000 + 500 * k, clean=True)
         p = tmp_path / ("s%d.bam" % k)
         p.write_bytes(bgzf)
         files.append((str(p), raw))
@@ -169,7 +173,37 @@ def test_read_bam_remove_and_preprocess_ranges_from_files(rb, tmp_path):
         names, lens, first = IO.bam_header(raw)
         c, s, e, st = IO.bam_decode(raw[first:], lens, split=True)
         g = x["ranges"]
+        # the selection is applied on the device to the decoded reads (rcp_reads_load_decoded_select)
+        from tests.helpers import assert_coverage_equal
+        o_mask, g_mask = both_regions_([0, 1, 2, 0], [1, 100, 1, 20000], [50000, 25000, 900, 29999], [1, -1, 0, 1])
+        o_reads = O.Reads(c[ix - 1], s[ix - 1].astype(np.int64), e[ix - 1].astype(np.int64), st[ix - 1], lens)
+        assert g._host is None and g.parent._host is None
+        assert_coverage_equal(rb.calcCoverage(g, g_mask, ignore_strand=False).to_list(),
+                              O.calc_coverage(o_reads, o_mask, None, False))
+        assert g._host is None and g.parent._host is None          # still nothing fetched
         _assert_same((g.seqnames, g.start, g.end, g.strand), (c[ix - 1], s[ix - 1], e[ix - 1], st[ix - 1]))
+
+
+@pytest.mark.gpu
+def test_zero_width_alignments_are_decoded_but_refused_by_the_reads_loader(rb):
+    from recoup_b200 import _lib
+    raw, bgzf = bam_file(REFS, [bam_record(0, 5, 0, "10M"), bam_record(0, 50, 16, "6I")])
+    reads = rb.readBam(bgzf)                           # as(galn, "GRanges") keeps the empty alignment
+    assert reads.start.tolist() == [6, 51] and reads.end.tolist() == [15, 50]
+    o_mask, g_mask = both_regions_([0], [1], [100], [1])
+    with pytest.raises(_lib.RecoupError) as ei:        # the same answer a GRanges with such a read gets
+        rb.calcCoverage(reads, g_mask)
+    assert ei.value.code == _lib.RCP_ERR_DATA
+    assert len(rb.readBam(bgzf, sa="split")) == 1      # grglist drops empty ranges
+
+
+def both_regions_(chrom, start, end, strand):
+    """mask on the BAM's own seqlevels (calcCoverage matches chromosomes by NAME, coverage.R:182,189)"""
+    import recoup_b200 as rb
+    od = dict(chrom=np.asarray(chrom, dtype=np.int64), start=np.asarray(start, dtype=np.int64),
+              end=np.asarray(end, dtype=np.int64), strand=np.asarray(strand, dtype=np.int64))
+    return od, rb.GRanges(np.asarray(chrom, dtype=np.int32), start, end, strand=np.asarray(strand, dtype=np.int8),
+                          seqlevels=[r[0] for r in REFS])
 
 
 @pytest.mark.gpu

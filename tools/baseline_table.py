@@ -50,6 +50,14 @@ def main():
             print("`%s`: %.2f ms/step = %.3g reads/s, %d MB H2D + %d MB D2H per step (%s)." % (
                 k, e["ms_per_step"], e["value"], e["h2d_bytes_per_step"] // 10**6, e["d2h_bytes_per_step"] // 10**6,
                 e.get("inputs", "")))
+    im = cfg.get("import")
+    if im:
+        print("Read import (decode only, %d records / lines in HBM): BAM records %.3g records/s (%.0f GB/s), "
+              "spliceAction split %.3g records/s, BED text %.3g lines/s (%.0f GB/s); from host memory %.1f ms / %.1f ms "
+              "per file; host walk of the BAM record chain %.1f ms." % (
+                  im["records"], im["bam_keep"]["records_per_s"], im["bam_keep"]["GB_per_s"],
+                  im["bam_split"]["records_per_s"], im["bed"]["lines_per_s"], im["bed"]["GB_per_s"],
+                  im["bam_keep"]["ms_from_host"], im["bed"]["ms_from_host"], im["bam_index_host_ms"]))
     cb = one.get("cpu_baseline")
     if cb:
         print("CPU arm (%s, %d cores): %.3g reads/s on %s." % (cb["kind"], cb["cores"], cb["value"], cb["sample"][:80]))
