@@ -146,9 +146,12 @@ int rcp_r_rank_table(int n, int seed, int sample_kind, int* rank_out /* n */);
 /* Upload decoded reads (the `ranges` GRanges produced by preprocessRanges, ranges.R:1-65),
  * validate them and map them to global coordinates on the device (the sorted index is built
  * lazily by the first call that needs it).  `strand` may be NULL (all '*').
- * chrom_len[c] must be the known seqlength (> 0).  Reads must satisfy 1 <= start <= end and,
- * after the optional extension, are trimmed into [1, chrom_len] like readBam's trim()
- * (ranges.R:117).  frag_len > 0 applies the fragment extension named by the north star
+ * chrom_len[c] is the seqlength; <= 0 means unknown (R's NA): coverage(reads)[[chr]] then ends at
+ * the largest end among the reads that overlap a region (coverage.R:201), i.e. a window on such a
+ * chromosome is NULL unless a read reaches its last position (the load then takes one extra pass
+ * over the reads and one host synchronisation).  Reads must satisfy 1 <= start <= end and, after
+ * the optional extension, are trimmed into [1, chrom_len] like readBam's trim() (ranges.R:117;
+ * nothing to trim at on a chromosome of unknown length).  frag_len > 0 applies the fragment extension named by the north star
  * (`trim(resize(reads, frag_len, fix="start"))`; absent from the reference snapshot), 0 = off. */
 int rcp_reads_load(int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end,
                    const int8_t* strand, int n_chrom, const int64_t* chrom_len, int frag_len,

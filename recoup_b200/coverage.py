@@ -43,20 +43,31 @@ def set_verbose(flag):
 # ------------------------------------------------------------------------------------------------
 # device-resident objects
 # ------------------------------------------------------------------------------------------------
+def _seqlengths(gr):
+    """seqlengths(gr) as int64; unknown lengths (None, NaN, <= 0: R's NA) travel as -1: the coverage
+    vector of such a chromosome ends at the last overlapping read (coverage.R:201)."""
+    if gr.seqlengths is None:
+        return np.full(max(len(gr.seqlevels), 1), -1, dtype=np.int64)
+    sl = np.asarray(gr.seqlengths)
+    if sl.dtype.kind == "O":
+        sl = np.asarray([np.nan if v is None else v for v in sl.tolist()], dtype=np.float64)
+    if sl.dtype.kind == "f":
+        sl = np.where(np.isnan(sl), -1, sl)
+    sl = np.ascontiguousarray(sl, dtype=np.int64)
+    return np.where(sl <= 0, -1, sl)
+
+
 class DeviceReads:
     """Device index of one sample's reads (rcp_reads_load)."""
 
     def __init__(self, gr, frag_len=0, use_runs=None):
         """use_runs: send the seqnames as runs (rcp_reads_load_rle); default: when the GRanges
         holds them as an Rle with fewer than n / 2 runs."""
-        if gr.seqlengths is None:
-            raise ValueError("reads need seqlengths (the length of the per-chromosome coverage "
-                             "vector, coverage.R:201)")
         _lib.ensure_init()
         h = C.c_int(0)
         if getattr(gr, "decoded_handle", None) is not None:
             # decoded on the device (readers.DecodedGRanges): no host round trip
-            clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+            clen = _seqlengths(gr)
             _lib_check(_lib.lib.rcp_reads_load_decoded(gr.decoded_handle, clen.shape[0],
                                                        clen.ctypes.data_as(C.POINTER(C.c_int64)), int(frag_len),
                                                        C.byref(h)))
@@ -70,7 +81,7 @@ class DeviceReads:
             p = gr.parent
             if getattr(p, "decoded_handle", None) is not None:
                 # a selection of reads decoded on the device: nothing but the index crosses PCIe
-                clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+                clen = _seqlengths(gr)
                 n_kept = C.c_int64(0)
                 k = 0 if gr.idx is None else gr.idx.shape[0]
                 _lib_check(_lib.lib.rcp_reads_load_decoded_select(
@@ -84,7 +95,7 @@ class DeviceReads:
                 return
             arr = [np.ascontiguousarray(a, dtype=t) for a, t in
                    ((p.seqnames, np.int32), (p.start, np.int32), (p.end, np.int32), (p.strand, np.int8))]
-            clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+            clen = _seqlengths(gr)
             n_kept = C.c_int64(0)
             k = 0 if gr.idx is None else gr.idx.shape[0]
             _lib_check(_lib.lib.rcp_reads_load_select(
@@ -100,7 +111,7 @@ class DeviceReads:
             return
         start = np.ascontiguousarray(gr.start, dtype=np.int32)
         strand = np.ascontiguousarray(gr.strand, dtype=np.int8)
-        clen = np.ascontiguousarray(gr.seqlengths, dtype=np.int64)
+        clen = _seqlengths(gr)
         clen_p = clen.ctypes.data_as(C.POINTER(C.c_int64))
         rle = gr.seqnames_rle
         if use_runs is None:

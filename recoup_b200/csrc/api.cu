@@ -882,6 +882,13 @@ int rcp_coverage(int reads, int64_t n_regions, const int32_t* chrom, const int32
             rc = coverage_ranges(*r, n_regions, chrom, start, end, strand, ignore_strand != 0,
                                  strand_filter, mem, cv);
     }
+    if (rc == RCP_OK && r->any_na && n_regions > 0) {      // NA seqlengths: the rule of coverage.R:201
+        DevIn<int32_t> d_chrom;
+        DevIn<int8_t> d_strand;
+        rc = d_chrom.init(chrom, (size_t)n_regions, mem);
+        if (rc == RCP_OK) rc = d_strand.init(strand, (size_t)n_regions, mem);
+        if (rc == RCP_OK) rc = coverage_na_rule(*r, *cv, n_regions, d_chrom.ptr, d_strand.ptr, nullptr);
+    }
     if (rc != RCP_OK) {
         drop_coverage(h);
         return rc;
@@ -922,6 +929,38 @@ int rcp_coverage_list(int reads, int64_t n_elements, const int64_t* ptr, const i
     if (rc == RCP_SPLIT_NOT_APPLICABLE)
         rc = coverage_list(*r, n_elements, ptr, n_ranges, chrom, start, end, strand,
                            ignore_strand != 0, strand_filter, mem, cv);
+    if (rc == RCP_OK && r->any_na && n_elements > 0) {
+        // NA seqlengths: where the largest range end of an element sits inside its stitched vector
+        // (ranges in list order, a start of 0 dropped, the whole vector reversed when the FIRST
+        // range is on '-': coverage.R:185,202-215)
+        std::vector<int32_t> e_chrom((size_t)n_elements, 0);
+        std::vector<int8_t> e_strand((size_t)n_elements, 0);
+        std::vector<int64_t> e_pos((size_t)n_elements, -1);
+        for (int64_t g = 0; g < n_elements; g++) {
+            const int64_t a = ptr[g], b = ptr[g + 1];
+            if (b <= a) continue;
+            e_chrom[(size_t)g] = chrom[a];
+            e_strand[(size_t)g] = strand ? strand[a] : (int8_t)0;
+            int64_t total = 0, best_end = INT64_MIN, best_pos = -1;
+            for (int64_t j = a; j < b; j++) {
+                const int64_t w = (int64_t)end[j] - std::max<int64_t>(start[j], 1) + 1;
+                if (w <= 0) continue;
+                if ((int64_t)end[j] > best_end) {
+                    best_end = end[j];
+                    best_pos = total + w - 1;
+                }
+                total += w;
+            }
+            if (best_pos >= 0) e_pos[(size_t)g] = e_strand[(size_t)g] < 0 ? total - 1 - best_pos : best_pos;
+        }
+        DevIn<int32_t> d_chrom;
+        DevIn<int8_t> d_strand;
+        DevIn<int64_t> d_pos;
+        rc = d_chrom.init(e_chrom.data(), (size_t)n_elements, RCP_MEM_HOST);
+        if (rc == RCP_OK) rc = d_strand.init(e_strand.data(), (size_t)n_elements, RCP_MEM_HOST);
+        if (rc == RCP_OK) rc = d_pos.init(e_pos.data(), (size_t)n_elements, RCP_MEM_HOST);
+        if (rc == RCP_OK) rc = coverage_na_rule(*r, *cv, n_elements, d_chrom.ptr, d_strand.ptr, d_pos.ptr);
+    }
     if (rc != RCP_OK) {
         drop_coverage(h);
         return rc;
@@ -1124,7 +1163,7 @@ int rcp_coverage_profile(int reads, int64_t n_regions, const int32_t* chrom, con
     if (n_regions > 0x7fffffff) return fail(RCP_ERR_UNSUPPORTED, "more than 2^31-1 regions");
     const bool may_split = g_ctx.coverage_path == RCP_PATH_SPLIT ||
                            (g_ctx.coverage_path == RCP_PATH_AUTO && getenv("RCP_AUTO_NO_SPLIT") == nullptr);
-    if (n_bins >= 1 && may_split) {
+    if (n_bins >= 1 && may_split && !r->any_na) {      // (NA seqlengths: the rule needs the coverage itself)
         MatrixOut m;
         RCP_TRY(m.init(out, ld, n_regions, n_bins, mem));
         uint8_t* d_null = nullptr;

@@ -756,6 +756,68 @@ void coverage_release(Coverage& c) {
     c.stats_pending = false;
 }
 
+// ---- NA seqlengths (coverage.R:201) ----------------------------------------------------------
+// coverage(y$reads)[[chr]] of a chromosome of unknown length ends at the largest end among the
+// reads that OVERLAP the region, and indexing beyond it is the "invalid genomic area" error ->
+// NULL (coverage.R:206-209,217-222).  A read that overlaps the region and ends at or after the
+// region's last position covers that position, so the rule reads: NULL unless the coverage at the
+// region's genomic end is non-zero.
+namespace {
+__global__ void __launch_bounds__(CTA)
+na_rule_kernel(int64_t R, const int32_t* __restrict__ chrom, const int8_t* __restrict__ strand,
+               const uint8_t* __restrict__ len_na, int n_chrom, const int64_t* __restrict__ off,
+               int32_t* __restrict__ len, uint8_t* __restrict__ is_null, const int32_t* __restrict__ cov,
+               const int64_t* __restrict__ end_pos) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    if (r >= R) return;
+    const int32_t L = len[r];
+    const int c = chrom[r];
+    if (L <= 0 || c < 0 || c >= n_chrom || !len_na[c]) return;
+    const int64_t idx = end_pos ? end_pos[r] : ((strand && strand[r] < 0) ? 0 : (int64_t)L - 1);
+    if (idx < 0 || idx >= L || cov[off[r] + idx] == 0) {
+        len[r] = 0;
+        is_null[r] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+len_stats_kernel(int64_t R, const int32_t* __restrict__ len, unsigned long long* __restrict__ stats) {
+    const int64_t r = (int64_t)blockIdx.x * CTA + threadIdx.x;
+    unsigned long long my_null = 0, my_len = 0;
+    if (r < R) {
+        my_len = (unsigned long long)len[r];
+        my_null = my_len == 0 ? 1 : 0;
+    }
+    unsigned long long my_max = my_len;
+    for (int d = 16; d > 0; d >>= 1) {
+        my_null += __shfl_xor_sync(0xffffffffu, my_null, d);
+        my_len += __shfl_xor_sync(0xffffffffu, my_len, d);
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_null) atomicAdd(&stats[0], my_null);
+        if (my_len) atomicAdd(&stats[1], my_len);
+        if (my_max) atomicMax(&stats[2], my_max);
+    }
+}
+}  // namespace
+
+int coverage_na_rule(const ReadsIdx& rd, Coverage& cv, int64_t R, const int32_t* d_chrom, const int8_t* d_strand,
+                     const int64_t* d_end_pos) {
+    if (!rd.any_na || R <= 0) return RCP_OK;
+    RCP_TRY(coverage_resolve_stats(cv));            // (keeps `candidates`; the rest is recomputed)
+    if (!cv.d_stats) RCP_TRY(dalloc(&cv.d_stats, 4));
+    const unsigned long long h[4] = {0ull, 0ull, 0ull, (unsigned long long)cv.candidates};
+    RCP_CUDA(cudaMemcpyAsync(cv.d_stats, h, 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    na_rule_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(R, d_chrom, d_strand, rd.d_len_na, rd.n_chrom, cv.off,
+                                                               cv.len, cv.is_null, cv.cov, d_end_pos);
+    RCP_LAUNCHED();
+    len_stats_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(R, cv.len, cv.d_stats);
+    RCP_LAUNCHED();
+    cv.stats_pending = true;
+    return coverage_resolve_stats(cv);
+}
+
 // split path: n_null / total_len / max_len / candidates were produced after the call returned
 int coverage_resolve_stats(Coverage& c) {
     if (!c.stats_pending) return RCP_OK;

@@ -52,6 +52,31 @@ __device__ __forceinline__ bool map_read(int c, int64_t s, int64_t e, int st, in
     return true;
 }
 
+// NA seqlengths: the largest read end per chromosome, fragment extension applied, nothing trimmed
+// (chromosomes of unknown length have no end to trim at).  Invalid reads are left to the map kernel.
+__global__ void __launch_bounds__(TPB)
+chrom_max_end_kernel(int64_t n, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
+                     const int32_t* __restrict__ end, const int8_t* __restrict__ strand, int n_chrom,
+                     int frag_len, int fixed_width, unsigned long long* __restrict__ max_end) {
+    const int64_t stride = (int64_t)gridDim.x * TPB;
+    int last_c = -1;
+    long long best = 0;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+        const int c = chrom[i];
+        if (c < 0 || c >= n_chrom) continue;
+        const long long s = start[i];
+        long long e = end ? (long long)end[i] : s + fixed_width - 1;
+        if (frag_len > 0 && !(strand && strand[i] < 0)) e = s + frag_len - 1;
+        if (c != last_c) {
+            if (last_c >= 0 && best > 0) atomicMax(max_end + last_c, (unsigned long long)best);
+            last_c = c;
+            best = 0;
+        }
+        best = max(best, e);
+    }
+    if (last_c >= 0 && best > 0) atomicMax(max_end + last_c, (unsigned long long)best);
+}
+
 // VEC = 4: every thread maps four consecutive reads with 16-byte loads/stores (all arrays
 // 16-byte aligned, checked on the host); the n % 4 tail and VEC = 1 use scalar accesses.
 template <int VEC, bool HAS_END>
@@ -362,6 +387,7 @@ void reads_release(ReadsIdx& r) {
     r.pending = false;
     dfree(r.d_chrom_len);
     dfree(r.d_chrom_off);
+    dfree(r.d_len_na);
     dfree(r.g_start);
     dfree(r.g_end1);
     dfree(r.d_strand);
@@ -548,28 +574,35 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     r.has_strand = strand != nullptr;
     r.chrom_len.assign(chrom_len, chrom_len + n_chrom);
     r.chrom_off.resize((size_t)n_chrom + 1);
-    uint64_t off = 0;
-    for (int c = 0; c < n_chrom; c++) {
-        if (chrom_len[c] <= 0)
-            return fail(RCP_ERR_UNSUPPORTED,
-                        "chrom_len[%d] = %lld: unknown (NA) seqlengths are not supported", c,
-                        (long long)chrom_len[c]);
-        r.chrom_off[c] = (uint32_t)off;
-        off += (uint64_t)chrom_len[c] + 2;
-        if (off >= 0xfffffff0ull)
-            return fail(RCP_ERR_UNSUPPORTED,
-                        "genome longer than 2^32 positions: 64-bit coordinates not implemented");
-    }
-    r.chrom_off[n_chrom] = (uint32_t)off;
-    r.key_bits = 1;
-    while (r.key_bits < 32 && (1ull << r.key_bits) <= off) r.key_bits++;
-
+    r.len_na.assign((size_t)n_chrom, 0);
+    r.any_na = false;
+    for (int c = 0; c < n_chrom; c++)
+        if (chrom_len[c] <= 0) {            // NA: a stand-in follows from the reads (below)
+            r.len_na[(size_t)c] = 1;
+            r.any_na = true;
+        }
+    // chromosome layout in the global coordinate; with NA lengths it waits for the stand-ins
+    auto layout = [&]() -> int {
+        uint64_t off = 0;
+        for (int c = 0; c < n_chrom; c++) {
+            r.chrom_off[c] = (uint32_t)off;
+            off += (uint64_t)r.chrom_len[(size_t)c] + 2;
+            if (off >= 0xfffffff0ull)
+                return fail(RCP_ERR_UNSUPPORTED,
+                            "genome longer than 2^32 positions: 64-bit coordinates not implemented");
+        }
+        r.chrom_off[n_chrom] = (uint32_t)off;
+        r.key_bits = 1;
+        while (r.key_bits < 32 && (1ull << r.key_bits) <= off) r.key_bits++;
+        RCP_CUDA(cudaMemcpyAsync(r.d_chrom_len, r.chrom_len.data(), (size_t)n_chrom * 8,
+                                 cudaMemcpyHostToDevice, g_ctx.stream));
+        RCP_CUDA(cudaMemcpyAsync(r.d_chrom_off, r.chrom_off.data(), ((size_t)n_chrom + 1) * 4,
+                                 cudaMemcpyHostToDevice, g_ctx.stream));
+        return RCP_OK;
+    };
     RCP_TRY(dalloc(&r.d_chrom_len, (size_t)n_chrom));
     RCP_TRY(dalloc(&r.d_chrom_off, (size_t)n_chrom + 1));
-    RCP_CUDA(cudaMemcpyAsync(r.d_chrom_len, r.chrom_len.data(), (size_t)n_chrom * 8,
-                             cudaMemcpyHostToDevice, g_ctx.stream));
-    RCP_CUDA(cudaMemcpyAsync(r.d_chrom_off, r.chrom_off.data(), ((size_t)n_chrom + 1) * 4,
-                             cudaMemcpyHostToDevice, g_ctx.stream));
+    if (!r.any_na) RCP_TRY(layout());
 
     DevIn<int32_t> d_chrom, d_start, d_end, d_run_chrom, d_run_len;
     DevIn<int8_t> d_strand;
@@ -597,10 +630,6 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
     RCP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), g_ctx.stream));
     RCP_CUDA(cudaMemsetAsync(d_w, 0, 4 * sizeof(unsigned int), g_ctx.stream));
-    {   // the widest read the split path's packed word holds for this genome (coverage_split.cu)
-        const int wbits = 32 - split_position_bits((int64_t)r.chrom_off[(size_t)n_chrom]) - (r.has_strand ? 2 : 0);
-        r.long_thr = wbits >= 7 ? std::min<uint32_t>((1u << wbits) - 1u, 8191u) : 0xffffffffu;
-    }
     uint32_t* run_first = nullptr;      // exclusive scan of the run lengths + their total
     if (rle) {
         StageTimer t(ST_INDEX_MAP);
@@ -614,6 +643,34 @@ int reads_load_impl(ReadsIdx& r, int64_t n, const int32_t* chrom, int64_t n_runs
         rle_expand_kernel<<<grid_for((n + 3) / 4), TPB, 0, g_ctx.stream>>>(
             n, n_runs, d_run_chrom.ptr, run_first, d_chrom.owned);
         RCP_LAUNCHED();
+    }
+    if (r.any_na) {
+        // stand-in lengths: the largest (extended) read end of each NA chromosome -- one pass over
+        // the reads and one host synchronisation that samples with known seqlengths never pay
+        unsigned long long* d_max = nullptr;
+        RCP_TRY(dalloc(&d_max, (size_t)n_chrom));
+        RCP_CUDA(cudaMemsetAsync(d_max, 0, (size_t)n_chrom * 8, g_ctx.stream));
+        if (n > 0) {
+            chrom_max_end_kernel<<<grid_for(n), TPB, 0, g_ctx.stream>>>(n, d_chrom.ptr, d_start.ptr, d_end.ptr,
+                                                                       d_strand.ptr, n_chrom, frag_len, fixed_width,
+                                                                       d_max);
+            RCP_LAUNCHED();
+        }
+        std::vector<unsigned long long> h_max((size_t)n_chrom, 0ull);
+        RCP_CUDA(cudaMemcpyAsync(h_max.data(), d_max, (size_t)n_chrom * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+        RCP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        dfree(d_max);
+        for (int c = 0; c < n_chrom; c++)
+            if (r.len_na[(size_t)c])
+                r.chrom_len[(size_t)c] = (int64_t)std::min<unsigned long long>(std::max<unsigned long long>(h_max[(size_t)c], 1ull),
+                                                                               0x7ffffff0ull);
+        RCP_TRY(layout());
+        RCP_TRY(dalloc(&r.d_len_na, (size_t)n_chrom));
+        RCP_CUDA(cudaMemcpyAsync(r.d_len_na, r.len_na.data(), (size_t)n_chrom, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    {   // the widest read the split path's packed word holds for this genome (coverage_split.cu)
+        const int wbits = 32 - split_position_bits((int64_t)r.chrom_off[(size_t)n_chrom]) - (r.has_strand ? 2 : 0);
+        r.long_thr = wbits >= 7 ? std::min<uint32_t>((1u << wbits) - 1u, 8191u) : 0xffffffffu;
     }
     ExcBuf exc;
     // (the exception counter is ONE address: a sample whose widths vary hits it once per read

@@ -192,6 +192,14 @@ struct ReadsIdx {
     std::vector<uint32_t> chrom_off;    // n_chrom + 1, global coordinate of position 0
     int64_t* d_chrom_len = nullptr;
     uint32_t* d_chrom_off = nullptr;
+    // Unknown (NA) seqlengths, passed as chrom_len <= 0: coverage(reads)[[chr]] then ends at the
+    // largest end among the reads that overlap the region (coverage.R:201), so a window is NULL
+    // unless a read reaches its last position.  chrom_len holds a stand-in (the largest read end of
+    // the chromosome, fragment extension included) that lays the chromosomes out; the rule itself
+    // is applied to the finished coverage (coverage_na_rule).
+    bool any_na = false;
+    std::vector<uint8_t> len_na;        // n_chrom
+    uint8_t* d_len_na = nullptr;
     // raw reads in global coordinates (kept for lazily built classes / pairs)
     uint32_t* g_start = nullptr;
     uint32_t* g_end1 = nullptr;         // end + 1
@@ -278,6 +286,11 @@ struct Coverage {
 };
 void coverage_release(Coverage& c);
 int coverage_resolve_stats(Coverage& c);
+// NA seqlengths: regions on such chromosomes whose genomic END position nobody covers become NULL.
+// end_pos == nullptr: GRanges mask (the end is the last stored position, the first on '-'
+// regions); else the index of that position inside each stitched element (GRangesList masks).
+int coverage_na_rule(const ReadsIdx& rd, Coverage& cv, int64_t R, const int32_t* d_chrom, const int8_t* d_strand,
+                     const int64_t* d_end_pos);
 
 ReadsIdx* get_reads(int h);
 Coverage* get_coverage(int h);

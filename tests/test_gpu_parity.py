@@ -210,6 +210,52 @@ def test_groups_denser_than_shared_memory(gpu):
     assert_coverage_equal(got.to_list(), want)
 
 
+@pytest.mark.parametrize("frag_len", [0, 150])
+@pytest.mark.parametrize("ignore", [True, False])
+def test_unknown_seqlengths_end_the_coverage_vector_at_the_last_overlapping_read(gpu, frag_len, ignore):
+    """coverage.R:201 with NA seqlengths: coverage(reads)[[chr]] is as long as the largest end among the
+    reads that overlap the region, so a window is NULL unless a read reaches its last position."""
+    rb = gpu
+    rng = np.random.default_rng(61)
+    true_len = [30000, 8000, 500]
+    chrom, s, e, st = synth_reads(rng, 5000, true_len, width=(20, 90))
+    keep = ~((chrom == 0) & (s > 20000))               # nothing on the last third of c0
+    chrom, s, e, st = chrom[keep], s[keep], e[keep], st[keep]
+    na_len = np.asarray([-1, 8000, -1], dtype=np.int64)           # c0 and c2 unknown, c1 known
+    es, ee = O.extend_fragments(s, e, st, frag_len, chrom, np.asarray([10**9, 8000, 10**9])) if frag_len else (s, e)
+    o_reads = O.Reads(chrom, es, ee, st, na_len)
+    g_reads = rb.GRanges(chrom, s, e, strand=st, seqlevels=["c0", "c1", "c2"], seqlengths=na_len)
+    rc, rs, re_, rst = _regions(rng, 300, true_len, [1, 30, 200, 1024, 1500, 6000])
+    rc[:4], rs[:4], re_[:4], rst[:4] = [0, 0, 2, 1], [1, 19000, 1, 1], [30000, 23000, 500, 8000], [1, -1, 0, 1]
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 3)
+    want = O.calc_coverage(o_reads, o_mask, None, ignore)
+    got = rb.calcCoverage(g_reads, g_mask, ignore_strand=ignore, frag_len=frag_len)
+    assert_coverage_equal(got.to_list(), want)
+    n_null = sum(w is None for w in want)
+    assert 0 < n_null < len(want) and got.n_null == n_null
+    # the same windows with the lengths known: fewer NULLs (the rule is what makes the difference)
+    o_known = O.Reads(chrom, es, ee, st, np.asarray([40000, 8000, 600]))
+    assert sum(w is None for w in O.calc_coverage(o_known, o_mask, None, ignore)) < n_null
+    # GRangesList masks: the largest range end of the element decides
+    ptr = np.concatenate((np.arange(0, 300, 4), [300])).astype(np.int64)
+    for g in range(ptr.shape[0] - 1):                   # one chromosome and strand per element
+        rc[ptr[g]:ptr[g + 1]] = rc[ptr[g]]
+    o_mask, g_mask = both_regions(rc, rs, re_, rst, 3)
+    want = O.calc_coverage(o_reads, dict(ptr=ptr, **o_mask), None, ignore)
+    got = rb.calcCoverage(g_reads, rb.GRangesList(g_mask, ptr), ignore_strand=ignore, frag_len=frag_len)
+    assert_coverage_equal(got.to_list(), want)
+    assert any(w is None for w in want) and any(w is not None for w in want)
+    # profile matrix of the NA coverage: NULL rows are zero rows (profile.R:6-12)
+    o_mask1, g_mask1 = both_regions(rc[:100], rs[:100], rs[:100] + 399, rst[:100], 3)
+    want = O.calc_coverage(o_reads, o_mask1, None, ignore)
+    cov = rb.calcCoverage(g_reads, g_mask1, ignore_strand=ignore, frag_len=frag_len)
+    assert_coverage_equal(cov.to_list(), want)
+    inp = [dict(id="s", name="s", coverage=cov)]
+    bp = dict(flankBinSize=0, regionBinSize=20, sumStat="mean", interpolation="auto")
+    rb.profileMatrix(inp, (200, 200), bp)
+    assert_matrix_close(inp[0]["profile"], O.profile_matrix(want, (200, 200), bp))
+
+
 def test_empty_inputs(gpu):
     rb = gpu
     clen = [1000]
