@@ -685,6 +685,26 @@ def run_strong(env, args, world, rank, which="C5"):
     return out
 
 
+def bind_cpu_near_gpu(local):
+    """One process per GPU: run this process (and place its page-locked buffers, by first touch)
+    on the CPUs of the GPU's own NUMA node, so that the N uploads of a step do not cross the socket
+    interconnect.  NVML knows the ideal CPU set of a device.  RCP_BENCH_BIND_CPU=0 turns it off."""
+    if os.environ.get("RCP_BENCH_BIND_CPU", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        bus = "%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "nvml ideal CPUs of %s: %d of %d" % (bus, len(os.sched_getaffinity(0)), before)
+    except Exception as e:       # no NVML, restricted cpuset, old torch: run unbound
+        return "unbound (%s: %s)" % (type(e).__name__, str(e)[:60])
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -699,6 +719,7 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
+    cpu_binding = bind_cpu_near_gpu(local) if world > 1 else "one GPU: not bound"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # a mismatched collective must fail in minutes, not hang the box until the watchdog
@@ -1153,6 +1174,7 @@ def run_b200(args):
             out["fused"] = fused
         if configs is not None:
             out["configs"] = configs
+        out["cpu_binding_rank0"] = cpu_binding
         if strong is not None:
             out["strong"] = strong
         if strong_c3 is not None:

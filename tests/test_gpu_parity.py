@@ -253,7 +253,12 @@ def test_unknown_seqlengths_end_the_coverage_vector_at_the_last_overlapping_read
     inp = [dict(id="s", name="s", coverage=cov)]
     bp = dict(flankBinSize=0, regionBinSize=20, sumStat="mean", interpolation="auto")
     rb.profileMatrix(inp, (200, 200), bp)
-    assert_matrix_close(inp[0]["profile"], O.profile_matrix(want, (200, 200), bp))
+    want_m = O.profile_matrix(want, (200, 200), bp)
+    assert_matrix_close(inp[0]["profile"], want_m)
+    # rcp_coverage_profile composes the two stages for such reads (the rule needs the coverage)
+    m, is_null = rb.coverageProfile(g_reads, g_mask1, 20, ignore_strand=ignore, frag_len=frag_len)
+    assert_matrix_close(m, want_m)
+    assert np.array_equal(is_null, np.asarray([w is None for w in want]))
 
 
 def test_empty_inputs(gpu):
