@@ -62,15 +62,18 @@ def main():
     if cb:
         print("CPU arm (%s, %d cores): %.3g reads/s on %s." % (cb["kind"], cb["cores"], cb["value"], cb["sample"][:80]))
     lines = [one] + [last_line(p) for p in sys.argv[2:]]
-    print("\n| GPUs | C2 replicas: ms/step | reads/s (all GPUs) | efficiency | e2e ms/step | C5 one problem: device-resident ms | with download ms |")
-    print("|---:|---:|---:|---:|---:|---:|---:|")
+    print("\n| GPUs | C2 replicas: ms/step | reads/s (all GPUs) | efficiency | e2e ms/step | C5 one problem: device-resident ms | with download ms | C3 one sample, one problem: device-resident ms | with download ms |")
+    print("|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     base = lines[0]["value"]
     for d in lines:
         s = d.get("strong") or (d.get("configs") or {}).get("C5") or {}
-        print("| %d | %.3f | %.3g | %.2f | %.2f | %s | %s |" % (
+        s3 = d.get("strong_C3") or {}
+        print("| %d | %.3f | %.3g | %.2f | %.2f | %s | %s | %s | %s |" % (
             d["n_gpus"], d["ms_per_step"], d["value"], d["value"] / (base * d["n_gpus"]), d["e2e"]["ms_per_step"],
             "%.2f" % s["ms_device_resident"] if "ms_device_resident" in s else "—",
-            "%.1f" % s["ms_per_step"] if "ms_per_step" in s else "—"))
+            "%.1f" % s["ms_per_step"] if "ms_per_step" in s else "—",
+            "%.2f" % s3["ms_device_resident"] if "ms_device_resident" in s3 else "—",
+            "%.2f" % s3["ms_per_step"] if "ms_per_step" in s3 else "—"))
 
 
 if __name__ == "__main__":
