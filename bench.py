@@ -212,6 +212,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "TORCHELASTIC_RUN_ID" in os.environ or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun sets OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host
+        # thread it can (rank 0 alone works here), so undo that before the OpenMP runtime starts
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     w = W.CONFIGS[args.workload](scale=args.scale)
     from oracle import c_oracle as CO
     total = max(len(w["read_start"]), 1)
