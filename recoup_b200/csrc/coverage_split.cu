@@ -3,8 +3,7 @@
 // over the reads and no per-read random access outside shared memory.
 //
 //   plan     regions -> windows (geometry / NULL rules of coverage.R:209,217-222), tile counts,
-//            storage offsets, and a BLOCK BITMAP of the mask (1 bit per 8 kb, 16 kb for genomes whose
-//            table would not fit the split kernel's shared memory).
+//            storage offsets, and a 1-bit-per-16-kb BLOCK BITMAP of the mask.
 //   split    the genome is cut into <= 1024 GROUPS of 2^P positions (P from the genome length
 //            alone).  Every read is tested against the bitmap in shared memory; a survivor is
 //            packed into ONE 32-bit word (position inside its group | strand class | width) and
@@ -45,11 +44,7 @@ using namespace covk;
 
 namespace {
 
-// blocks of the mask bitmap: 8 kb when the table of the genome still fits beside the rings in the
-// split kernel's shared memory (hg19: 95 KB + 132 KB), else 16 kb.  Finer blocks let fewer reads
-// through that no window wants (a 10-kb window lights 18 kb of 8-kb blocks on average, 26 kb of
-// 16-kb ones), and every later stage pays per surviving read.
-constexpr int BLK_SHIFT_FINE = 13, BLK_SHIFT_COARSE = 14;
+constexpr int BLK_SHIFT = 14;                         // 16384-bp blocks of the bitmap
 #ifndef RCP_SUB_SHIFT
 #define RCP_SUB_SHIFT 10
 #endif
@@ -86,7 +81,7 @@ __global__ void __launch_bounds__(CTA)
 sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __restrict__ start,
                const int32_t* __restrict__ end, const int8_t* __restrict__ strand,
                const uint32_t* __restrict__ chrom_off, const int64_t* __restrict__ chrom_len,
-               int n_chrom, int ignore_strand, int strand_filter, int blk_shift, uint32_t* __restrict__ gs_out,
+               int n_chrom, int ignore_strand, int strand_filter, uint32_t* __restrict__ gs_out,
                int32_t* __restrict__ plen, uint8_t* __restrict__ flags, int64_t* __restrict__ ntile,
                int64_t* __restrict__ padded, uint32_t* __restrict__ tab, unsigned int* __restrict__ err,
                unsigned long long* __restrict__ pstats /* [0] total len [1] max len [2] 2^32 - min len */,
@@ -108,8 +103,8 @@ sp_plan_kernel(int64_t R, const int32_t* __restrict__ chrom, const int32_t* __re
         padded[r] = ((int64_t)len + PAD - 1) / PAD * PAD;
         my_len = (unsigned long long)len;
         if (len > 0) {
-            const uint32_t b1 = (gs + (uint32_t)len - 1u) >> blk_shift;
-            for (uint32_t b = gs >> blk_shift; b <= b1; b++) sp_mark_block(tab, b);
+            const uint32_t b1 = (gs + (uint32_t)len - 1u) >> BLK_SHIFT;
+            for (uint32_t b = gs >> BLK_SHIFT; b <= b1; b++) sp_mark_block(tab, b);
         }
     }
     unsigned long long my_max = my_len, my_inv = my_len ? 0x100000000ull - my_len : 0ull;
@@ -269,8 +264,8 @@ constexpr size_t SP_SMEM_MAX = 232448;                // 227 KB: the most one CT
 template <bool STRANDED>
 __global__ void __launch_bounds__(ST, 1)
 sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t* __restrict__ g_end1,
-                const int8_t* __restrict__ strand, const uint32_t* __restrict__ tab_g, int words, int blk_shift,
-                int P, uint32_t max_pack_w, SplitOut out) {
+                const int8_t* __restrict__ strand, const uint32_t* __restrict__ tab_g, int words, int P,
+                uint32_t max_pack_w, SplitOut out) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
@@ -344,8 +339,8 @@ sp_split_kernel(int64_t n, const uint32_t* __restrict__ g_start, const uint32_t*
 
     // is any block the read touches in the mask?  (crossing reads look at the "next block" bit)
     auto keep_read = [&](uint32_t s, uint32_t e1) -> bool {
-        const uint32_t t = lds32(tab_a + ((s >> (blk_shift + 2)) & 0xfffffffcu)) >> ((s >> blk_shift) & 15u);
-        const bool cross = ((e1 - 1u) >> blk_shift) != (s >> blk_shift);
+        const uint32_t t = lds32(tab_a + ((s >> (BLK_SHIFT + 2)) & 0xfffffffcu)) >> ((s >> BLK_SHIFT) & 15u);
+        const bool cross = ((e1 - 1u) >> BLK_SHIFT) != (s >> BLK_SHIFT);
         return ((t & 1u) | (cross & ((t >> 16) & 1u))) & (e1 - s <= max_pack_w);    // wider: the long-read list
     };
     auto pack = [&](uint32_t s, uint32_t e1, int st) -> uint32_t {
@@ -1446,7 +1441,7 @@ struct SortedCands {
 
 // split kernel + chunk lists + group sort.  tab: the mask's block table on the device.  The
 // result lives in arena K (the caller keeps or drops it); B is scratch of the passes.
-static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int blk_shift, int P, int n_groups, bool stranded,
+static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int P, int n_groups, bool stranded,
                           bool st_arr, uint32_t max_pack_w, Arena& K, Arena& B, SortedCands* sc) {
     const int nb = 1 << (P - SUB_SHIFT);
     const uint32_t pmask = (1u << P) - 1u;
@@ -1478,12 +1473,12 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int blk_
         if (stranded) {     // no strand array: every read is '*'
             RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             sp_split_kernel<true><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1,
-                                                                         st_arr ? rd.d_strand : nullptr, tab, words,
-                                                                         blk_shift, P, max_pack_w, out);
+                                                                         st_arr ? rd.d_strand : nullptr, tab, words, P,
+                                                                         max_pack_w, out);
         } else {
             RCP_CUDA(cudaFuncSetAttribute(sp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             sp_split_kernel<false><<<split_grid, ST, smem, g_ctx.stream>>>(rd.n, rd.g_start, rd.g_end1, nullptr, tab,
-                                                                          words, blk_shift, P, max_pack_w, out);
+                                                                          words, P, max_pack_w, out);
         }
         RCP_LAUNCHED();
     }
@@ -1510,24 +1505,14 @@ static int split_and_sort(ReadsIdx& rd, const uint32_t* tab, int words, int blk_
 
 // The genome's split geometry: position bits of a candidate word, groups, table words.
 struct SplitGeom {
-    int words, blk_shift, P, n_groups, nb;
+    int words, P, n_groups, nb;
     uint32_t pmask;
     bool ok;
 };
-// block size of the bitmap and words of its table (one word per 16 blocks): fine blocks when they fit
-static void block_geometry(int64_t span, int* blk_shift, int* words) {
-    static const bool coarse_only = getenv("RCP_SPLIT_COARSE_BLOCKS") != nullptr;     // A/B timing
-    *blk_shift = BLK_SHIFT_FINE;
-    *words = (int)((span >> (BLK_SHIFT_FINE + 4)) + 2);
-    if (coarse_only || sp_split_smem(*words) > SP_SMEM_MAX) {
-        *blk_shift = BLK_SHIFT_COARSE;
-        *words = (int)((span >> (BLK_SHIFT_COARSE + 4)) + 2);
-    }
-}
 static SplitGeom split_geometry(const ReadsIdx& rd) {
     SplitGeom g;
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
-    block_geometry(span, &g.blk_shift, &g.words);
+    g.words = (int)((span >> (BLK_SHIFT + 4)) + 2);
     g.P = MIN_P;
     while (g.P < MAX_P && ((span + (1ll << g.P) - 1) >> g.P) > NG) g.P++;
     g.n_groups = (int)std::max<int64_t>(1, (span + (1ll << g.P) - 1) >> g.P);
@@ -1599,7 +1584,7 @@ static int reads_build_binned(ReadsIdx& rd) {
     uint32_t* tab = Tb.take<uint32_t>((size_t)g.words);
     RCP_CUDA(cudaMemsetAsync(tab, 0xff, (size_t)g.words * 4, g_ctx.stream));      // the mask "everything"
     SortedCands sc;
-    RCP_TRY(split_and_sort(rd, tab, g.words, g.blk_shift, g.P, g.n_groups, stranded, stranded, max_pack_w, K, B, &sc));
+    RCP_TRY(split_and_sort(rd, tab, g.words, g.P, g.n_groups, stranded, stranded, max_pack_w, K, B, &sc));
     rd.bn_base = K.base;
     K.base = nullptr;                   // the handle owns it now
     rd.bn_cand = sc.cand;
@@ -1629,8 +1614,7 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
     const bool stranded = !((strand_filter == RCP_STRAND_ANY) && (ignore_strand || strand == nullptr));
     const bool st_arr = stranded && rd.d_strand != nullptr;      // strandless reads are all '*'
     const int64_t span = (int64_t)rd.chrom_off[(size_t)rd.n_chrom];
-    int words, blk_shift;
-    block_geometry(span, &blk_shift, &words);
+    const int words = (int)((span >> (BLK_SHIFT + 4)) + 2);
     int P = MIN_P;
     while (P < MAX_P && ((span + (1ll << P) - 1) >> P) > NG) P++;
     const int n_groups = (int)std::max<int64_t>(1, (span + (1ll << P) - 1) >> P);
@@ -1687,7 +1671,7 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
         if (R > 0) {
             sp_plan_kernel<<<blocks_for(R, CTA), CTA, 0, g_ctx.stream>>>(
                 R, d_chrom.ptr, d_start.ptr, d_end.ptr, d_strand.ptr, rd.d_chrom_off, rd.d_chrom_len,
-                rd.n_chrom, ignore_strand, strand_filter, blk_shift, gs, plen, flags, ntile, padded, tab, err,
+                rd.n_chrom, ignore_strand, strand_filter, gs, plen, flags, ntile, padded, tab, err,
                 pstats, cv->d_stats);
             RCP_LAUNCHED();
         }
@@ -1710,7 +1694,7 @@ static int split_impl(ReadsIdx& rd, int64_t R, const int32_t* chrom, const int32
         int n_items = 4;
         reads_pending_items(rd, items, &n_items);       // a deferred rcp_reads_load is validated here
         RCP_TRY(fetch_begin(items, n_items));
-        if (!have_index) RCP_TRY(split_and_sort(rd, tab, words, blk_shift, P, n_groups, stranded, st_arr, 0xffffffffu, K, B, &sc));
+        if (!have_index) RCP_TRY(split_and_sort(rd, tab, words, P, n_groups, stranded, st_arr, 0xffffffffu, K, B, &sc));
         RCP_TRY(fetch_end(items, n_items));
         RCP_TRY(reads_finish(rd));
     }
