@@ -67,6 +67,33 @@ def test_oracle_decodes_known_alignments():
         (0, 100, 109), (0, 610, 635), (1, 1, 31), (2, 881, 900), (0, 50, 71), (0, 1072, 1089), (0, 18, 37)]
 
 
+# The example alignments of the SAM specification (SAMv1.pdf, section 1.1 "An example"): reference
+# `ref` of 45 bases; POS, FLAG and CIGAR as printed there, ends and blocks from its picture.
+SAM_SPEC_EXAMPLE = [          # (name, flag, pos, cigar, keep range, split ranges)
+    (b"r001", 99, 7, "8M2I4M1D3M", (7, 22), [(7, 22)]),
+    (b"r002", 0, 9, "3S6M1P1I4M", (9, 18), [(9, 18)]),
+    (b"r003", 0, 9, "5S6M", (9, 14), [(9, 14)]),
+    (b"r004", 0, 16, "6M14N5M", (16, 40), [(16, 21), (36, 40)]),
+    (b"r003", 2064, 29, "6H5M", (29, 33), [(29, 33)]),
+    (b"r001", 147, 37, "9M", (37, 45), [(37, 45)]),
+]
+
+
+def _sam_spec_bam():
+    return bam_file([("ref", 45)], [bam_record(0, pos - 1, flag, cig, name=nm) for nm, flag, pos, cig, _, _ in SAM_SPEC_EXAMPLE])
+
+
+def test_oracle_on_the_sam_specification_example():
+    raw, _ = _sam_spec_bam()
+    names, lens, first = IO.bam_header(raw)
+    c, s, e, st = IO.bam_decode(raw[first:], lens)
+    assert list(zip(s.tolist(), e.tolist())) == [k for _, _, _, _, k, _ in SAM_SPEC_EXAMPLE]
+    assert st.tolist() == [1, 1, 1, 1, -1, -1]                  # FLAG 0x10: r003 (supplementary) and r001/2
+    c, s, e, st = IO.bam_decode(raw[first:], lens, split=True)
+    assert list(zip(s.tolist(), e.tolist())) == [r for *_, sp in SAM_SPEC_EXAMPLE for r in sp]
+    assert st.tolist() == [1, 1, 1, 1, 1, -1, -1]
+
+
 def test_oracle_bed_known_lines():
     text = (b"track name=x\n# c\nchr1\t0\t10\tn\t0\t+\nchr2 5 9\r\n\nbrowser position\n"
             b"chrM\t3\t4\t.\t1\t.\nchr1\t7\t20\tq\t9\t-")
@@ -123,6 +150,31 @@ def test_bam_decode_matches_the_oracle(rb, n, sa):
     got = rb.readBam(bgzf, sa=sa)
     assert got.seqlevels == names and len(got) == want[0].shape[0]
     _assert_same((got.seqnames, got.start, got.end, got.strand), want)
+
+
+@pytest.mark.gpu
+def test_bam_decode_on_the_sam_specification_example(rb):
+    _, bgzf = _sam_spec_bam()
+    got = rb.readBam(bgzf)
+    assert got.seqlevels == ["ref"] and got.seqlengths.tolist() == [45]
+    assert list(zip(got.start.tolist(), got.end.tolist())) == [k for _, _, _, _, k, _ in SAM_SPEC_EXAMPLE]
+    assert got.strand.tolist() == [1, 1, 1, 1, -1, -1]
+    got = rb.readBam(bgzf, sa="split")
+    assert list(zip(got.start.tolist(), got.end.tolist())) == [r for *_, sp in SAM_SPEC_EXAMPLE for r in sp]
+    # coverage of the example straight from the decoded reads: the spliced r004 covers its gap under
+    # "keep" (as(galn, "GRanges") spans it) and not under "split"
+    from tests.helpers import assert_coverage_equal
+    od = dict(chrom=np.zeros(1, dtype=np.int64), start=np.asarray([1]), end=np.asarray([45]), strand=np.zeros(1, dtype=np.int64))
+    mask = rb.GRanges(np.zeros(1, dtype=np.int32), [1], [45], strand=np.zeros(1, dtype=np.int8), seqlevels=["ref"])
+    for sa in ("keep", "split"):
+        reads = rb.readBam(bgzf, sa=sa)
+        cov = rb.calcCoverage(reads, mask).to_list()[0]
+        want = np.zeros(45, dtype=np.int64)
+        for *_, keep, split in SAM_SPEC_EXAMPLE:
+            for a, b in ([keep] if sa == "keep" else split):
+                want[a - 1:b] += 1
+        assert np.array_equal(cov.astype(np.int64), want)
+        assert (cov[25] == 1) == (sa == "keep")                 # position 26: inside r004's N gap only
 
 
 @pytest.mark.gpu
