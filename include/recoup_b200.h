@@ -202,7 +202,7 @@ int rcp_reads_load_select(int64_t n, const int32_t* chrom, const int32_t* start,
  * FILE ORDER, resident in HBM.
  *
  * rcp_bam_index   walks the length-prefixed alignment records of an INFLATED BAM (the bytes after
- *   the header and the reference list; the BGZF inflate is zlib's job on the host): *n_records_out
+ *   the header and the reference list, e.g. from rcp_bgzf_inflate): *n_records_out
  *   = records; offsets_out (may be NULL; capacity >= records + 1) = byte offset of every record
  *   and of the end.  Host code: the chain is serial.
  * rcp_bam_decode  readGAlignments(file) with its default flag filter (unmapped records dropped),
@@ -217,6 +217,14 @@ int rcp_reads_load_select(int64_t n, const int32_t* chrom, const int32_t* start,
  *   seqlevels (host), chrom id = index into them; a name not among them is RCP_ERR_DATA.
  * rcp_decoded_fetch  the arrays -> host (any pointer may be NULL).
  * rcp_reads_load_decoded  rcp_reads_load of the decoded reads without a host round trip. */
+/* BGZF, the container of a BAM file (SAMv1 4.1): gzip members of <= 64 KB that carry their own
+ * compressed size, inflated independently by n_threads host threads (0: one per core; zlib).
+ * rcp_bgzf_size: inflated bytes and blocks of the file; rcp_bgzf_inflate: the inflated bytes (the
+ * BAM header, then the alignment records).  Host code, no GPU needed; RCP_ERR_DATA when the data
+ * is not BGZF (e.g. plain gzip) or a block fails its CRC32 / ISIZE. */
+int rcp_bgzf_size(const uint8_t* data /* host */, int64_t n_bytes, int64_t* inflated_bytes, int64_t* n_blocks);
+int rcp_bgzf_inflate(const uint8_t* data /* host */, int64_t n_bytes, uint8_t* out /* host */, int64_t capacity,
+                     int n_threads);
 int rcp_bam_index(const uint8_t* rec /* host */, int64_t n_bytes, int64_t* n_records_out,
                   int64_t* offsets_out /* host */, int64_t capacity);
 int rcp_bam_decode(const uint8_t* rec, int64_t n_bytes, const int64_t* offsets, int64_t n_records,

@@ -65,6 +65,8 @@ SIGNATURES = {
                                        C.c_int, C.c_int, _ip]),
     "rcp_reads_load_rle": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64p,
                                      C.c_int, C.c_int, _ip]),
+    "rcp_bgzf_size": (C.c_int, [_vp, C.c_int64, _i64p, _i64p]),
+    "rcp_bgzf_inflate": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int]),
     "rcp_bam_index": (C.c_int, [_vp, C.c_int64, _i64p, _vp, C.c_int64]),
     "rcp_bam_decode": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _i64p, C.c_int, C.c_int, _ip, _i64p]),
     "rcp_bed_decode": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_char_p), C.c_int, _ip, _i64p]),

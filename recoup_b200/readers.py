@@ -4,10 +4,10 @@
     readBam(bam, sa = c("keep", "remove", "split"), sq = 0.75)        ranges.R:111-134
     readBed(bed, bg)                                                  ranges.R:136-146
 
-What stays on the host: opening the file, the BGZF inflate (zlib), the BAM header (text +
-reference list) and the walk of the length-prefixed record chain (rcp_bam_index, C code inside the
-library).  Everything per read -- flag filter, CIGAR walk, N-split, trim, text parsing, compaction
-in file order -- runs on the device (rcp_bam_decode / rcp_bed_decode); the decoded reads stay in
+What stays on the host: opening the file, the BGZF inflate (rcp_bgzf_inflate: zlib, one thread per
+core, C++ inside the library), the BAM header (text + reference list) and the walk of the
+length-prefixed record chain (rcp_bam_index, also inside the library).  Everything per read -- flag
+filter, CIGAR walk, N-split, trim, text parsing, compaction in file order -- runs on the device (rcp_bam_decode / rcp_bed_decode); the decoded reads stay in
 HBM and go to the hot path without a host round trip (rcp_reads_load_decoded).  Their coordinates
 are copied to the host only when somebody reads them.
 """
@@ -69,10 +69,24 @@ class DecodedGRanges(GRanges):
         return self.end.astype(np.int64) - self.start.astype(np.int64) + 1
 
 
+def bgzfInflate(data, threads=0):
+    """The inflated bytes of a BGZF file as a uint8 array: the library's multi-threaded inflate
+    (rcp_bgzf_inflate), or python's gzip for data that is gzip but not BGZF."""
+    buf = np.frombuffer(bytes(data) if not isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    total, nblk = C.c_int64(0), C.c_int64(0)
+    if _lib.lib.rcp_bgzf_size(vp(buf), buf.shape[0], C.byref(total), C.byref(nblk)) != _lib.RCP_OK:
+        return np.frombuffer(gzip.decompress(bytes(data)), dtype=np.uint8)
+    out = np.empty(total.value, dtype=np.uint8)
+    _lib.check(_lib.lib.rcp_bgzf_inflate(vp(buf), buf.shape[0], vp(out), out.shape[0], int(threads)))
+    return out
+
+
 def bam_header(raw):
     """(seqlevels, seqlengths, offset of the first alignment record) of an inflated BAM."""
-    if raw[:4] != b"BAM\x01":
-        raise ValueError("not a BAM file (magic %r)" % raw[:4])
+    raw = memoryview(raw)
+    if bytes(raw[:4]) != b"BAM\x01":
+        raise ValueError("not a BAM file (magic %r)" % bytes(raw[:4]))
     l_text, = struct.unpack_from("<i", raw, 4)
     p = 8 + l_text
     n_ref, = struct.unpack_from("<i", raw, p)
@@ -80,7 +94,7 @@ def bam_header(raw):
     names, lens = [], []
     for _ in range(n_ref):
         l_name, = struct.unpack_from("<i", raw, p)
-        names.append(raw[p + 4:p + 4 + l_name - 1].decode("ascii"))
+        names.append(bytes(raw[p + 4:p + 4 + l_name - 1]).decode("ascii"))
         ln, = struct.unpack_from("<i", raw, p + 4 + l_name)
         lens.append(ln)
         p += 8 + l_name
@@ -112,7 +126,7 @@ def readBam(bam, sa="keep", sq=0.75, params=None):
     if not 0 <= sq <= 1:
         raise ValueError("sq must be in [0, 1]")
     data = bam if isinstance(bam, (bytes, bytearray, memoryview)) else open(bam, "rb").read()
-    raw = gzip.decompress(bytes(data))          # BGZF = concatenated gzip members
+    raw = bgzfInflate(data)                     # BGZF blocks inflated in parallel (host zlib)
     reads = decodeBam(raw, split=(sa == "split"))
     if sa != "remove" or len(reads) == 0:
         return reads

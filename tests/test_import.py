@@ -130,6 +130,40 @@ def test_bam_index_is_host_code_and_matches_the_walk():
         _lib.check(_lib.lib.rcp_bam_index(vp(rec), rec.shape[0] - 3, C.byref(n), None, 0))
 
 
+def test_bgzf_inflate_is_host_code_and_matches_gzip():
+    """rcp_bgzf_inflate (zlib, block-parallel) against python's gzip on the reference's BAM, on a
+    multi-block file of the test writer and on damaged / foreign data."""
+    import gzip
+    import zlib
+    from recoup_b200 import _lib
+    from recoup_b200.readers import bgzfInflate
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(8)
+    (raw, bgzf), _ = _synthetic_bam(rng, 6000)                  # ~ 600 KB: ten blocks and the EOF marker
+    for data, want in ((open(GOLDEN_BAM, "rb").read(), None), (bgzf, raw)):
+        want = gzip.decompress(data) if want is None else want
+        buf = np.frombuffer(data, dtype=np.uint8)
+        total, nblk = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.lib.rcp_bgzf_size(vp(buf), buf.shape[0], C.byref(total), C.byref(nblk)))
+        assert total.value == len(want) and nblk.value >= 2
+        for threads in (1, 3, 0):
+            assert bgzfInflate(data, threads).tobytes() == want
+    buf = np.frombuffer(bgzf, dtype=np.uint8)
+    out = np.empty(len(raw), dtype=np.uint8)
+    assert _lib.lib.rcp_bgzf_inflate(vp(buf), buf.shape[0], vp(out), len(raw) - 1, 1) == _lib.RCP_ERR_ARG
+    bad = buf.copy()
+    bad[200] ^= 0x55                                            # inside the first block's deflate stream
+    assert _lib.lib.rcp_bgzf_inflate(vp(bad), bad.shape[0], vp(out), out.shape[0], 2) == _lib.RCP_ERR_DATA
+    assert _lib.lib.rcp_bgzf_inflate(vp(buf), buf.shape[0] - 5, vp(out), out.shape[0], 1) == _lib.RCP_ERR_DATA
+    plain = gzip.compress(raw)                                  # gzip, but not BGZF: python's gzip takes over
+    pbuf = np.frombuffer(plain, dtype=np.uint8)
+    total = C.c_int64(0)
+    assert _lib.lib.rcp_bgzf_size(vp(pbuf), pbuf.shape[0], C.byref(total), None) == _lib.RCP_ERR_DATA
+    assert bgzfInflate(plain).tobytes() == raw
+    assert bgzfInflate(b"").shape[0] == 0
+    assert zlib.crc32(bgzfInflate(bgzf).tobytes()) == zlib.crc32(raw)
+
+
 # ------------------------------------------------------------------------------- GPU ------------
 @pytest.fixture(scope="module")
 def rb():

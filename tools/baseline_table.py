@@ -58,6 +58,9 @@ def main():
                   im["records"], im["bam_keep"]["records_per_s"], im["bam_keep"]["GB_per_s"],
                   im["bam_split"]["records_per_s"], im["bed"]["lines_per_s"], im["bed"]["GB_per_s"],
                   im["bam_keep"]["ms_from_host"], im["bed"]["ms_from_host"], im["bam_index_host_ms"]))
+        if "bgzf_inflate_host" in im:
+            b = im["bgzf_inflate_host"]
+            print("BGZF inflate on the host (zlib, %d threads): %.2f GB/s of inflated bytes." % (b["threads"], b["GB_per_s_inflated"]))
     cb = one.get("cpu_baseline")
     if cb:
         print("CPU arm (%s, %d cores): %.3g reads/s on %s." % (cb["kind"], cb["cores"], cb["value"], cb["sample"][:80]))
